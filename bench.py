@@ -1,0 +1,507 @@
+#!/usr/bin/env python
+"""Benchmark of the classify hot path (BASELINE.json metric: alignment
+records classified per second; achieved HBM GB/s vs peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N
+    python bench.py --impl reference        # CPU arm (oracle port, all cores)
+
+A step is one pass of the hot path over one batch of synthetic records
+(SURVEY.md §8d generator).  `value` is timed with the int32 SoA columns
+already resident in HBM; `e2e` goes through the reference-facing C-ABI call
+with pinned HOST buffers (H2D of the columns and D2H of the count table inside
+the timed region).  Every rank works on its own batch (weak scaling); the
+per-rank count tables are merged by one NCCL all-reduce per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'alignment records classified per second'
+UNIT = 'records/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3'])
+    ap.add_argument('--records', type=int, default=100_000_000)
+    ap.add_argument('--mode', default='default',
+                    choices=['default', 'major', 'uniq', 'above'])
+    ap.add_argument('--ranks', default='genus')
+    ap.add_argument('--cpu-sample', type=int, default=20_000_000)
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    return ap.parse_args()
+
+
+def peaks():
+    fp = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(fp) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured'
+    except Exception:
+        return 6650.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index),
+                 f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                 '-lms', '100'], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['n/a']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for nm, v in zip(names, r[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ---- workloads ---------------------------------------------------------------
+def make_cfg2(args, device, seed):
+    """genus-rank (or --ranks) classify over the 21,603-node taxonomy."""
+    from tests import cases
+    from woltka_b200 import synth
+    case = cases.Case(synth.Taxonomy(seed=42))
+    entries = args.ranks.split(',')
+    flags = cases.MODES[args.mode]
+    q, s, _, nq = synth.gen_hits(args.records, seed=seed, device=device)
+    return case, entries, flags, q, s, nq
+
+
+def cpu_classify(case, entries, flags, q, s, threads):
+    from tests import cases
+    t0 = time.perf_counter()
+    out = cases.run_oracle(case, entries, flags, 0.8, q, s, n_threads=threads)
+    return out, time.perf_counter() - t0
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference's path, all host threads."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    threads = O.max_threads()
+    n = min(args.records, args.cpu_sample)
+    if args.workload == 'cfg3':
+        return run_reference_cfg3(args, threads)
+    args_records = args.records
+    args.records = n
+    case, entries, flags, q, s, nq = make_cfg2(args, 'cpu', 1002)
+    args.records = args_records
+    q, s = q.numpy(), s.numpy()
+    for _ in range(args.warmup):
+        cpu_classify(case, entries, flags, q, s, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_classify(case, entries, flags, q, s, threads)
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT,
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32',
+        'data': 'synthetic',
+        'config': workload_config(args, entries),
+        'cpu_baseline': {
+            'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+            'sample': f'{n} records of the same generator per step '
+                      f'(C restatement oracle/woltka_oracle.c, OpenMP)'},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def run_reference_cfg3(args, threads):
+    from oracle import oracle as O
+    from woltka_b200 import synth
+    n = min(args.records, 1_000_000)
+    coff, gb, ge = synth.gen_genes()
+    rq, rc, rb, re_, rl, nq = synth.gen_reads(n, seed=1003)
+    cols = [x.numpy() for x in (rc, rb, re_, rl)]
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.ordinal_match(*cols, 0.8, coff, gb, ge)
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT,
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': 0,
+        'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32',
+        'data': 'synthetic', 'config': workload_config(args, ['none']),
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': 1,
+                         'kind': 'port',
+                         'sample': f'{n} reads, sweep matcher only'},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0}, 'gpu_launches': 0}))
+
+
+def workload_config(args, entries):
+    if args.workload == 'cfg3':
+        return {'workload': 'cfg3: coord-match ordinal profile, synthetic '
+                            'reads x 5M gene intervals over 1k contigs, '
+                            'overlap 80, rank none',
+                'records_per_gpu': args.records, 'genes': 5_000_000,
+                'contigs': 1000,
+                'l2': 'inputs larger than L2 (2 GB of columns per step)'}
+    return {'workload': 'cfg2: genus-rank taxonomic classify, synthetic SAM '
+                        'records x 10k-genome / 21,603-node taxonomy',
+            'records_per_gpu': args.records, 'ranks': entries,
+            'mode': args.mode, 'taxonomy_nodes': 21603, 'genomes': 10000,
+            'l2': 'inputs larger than L2 (0.8 GB of columns per step)'}
+
+
+# ---- our arm -----------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from woltka_b200.engine import Engine, pinned_empty
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng = Engine(local)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    n = args.records
+    hbm_peak, peak_src = peaks()
+
+    if args.workload == 'cfg3':
+        return run_ours_cfg3(args, eng, dev, world, rank, barrier, hbm_peak,
+                             peak_src)
+
+    from tests import cases
+    case, entries, flags, q, s, nq = make_cfg2(args, dev, 1002 + rank)
+    kinds, tab, _ = case.tables(entries)
+    eng.set_tree(case.ft.parent, 0)
+    eng.set_plan(kinds, flags, 0.8, 1, case.NF)
+    eng.set_subjects(tab, case.sub_node)
+    counts = eng.counts_tensor()
+    bytes_per_rec = 8
+
+    def step():
+        eng.reset_counts()
+        eng.classify_device(q.data_ptr(), s.data_ptr(), n)
+        if world > 1:
+            dist.all_reduce(counts)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    k_ev = [(torch.cuda.Event(enable_timing=True),
+             torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = eng.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t_beg = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_beg.record()
+    for i in range(args.steps):
+        eng.reset_counts()
+        k_ev[i][0].record()
+        eng.classify_device(q.data_ptr(), s.data_ptr(), n)
+        k_ev[i][1].record()
+        if world > 1:
+            dist.all_reduce(counts)
+    t_end.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = t_beg.elapsed_time(t_end)
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    launches = eng.launch_count() - l0
+    tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    value = n * world * args.steps / (ms * 1e-3)
+    # parity of the timed configuration on a bounded sample + CPU baseline
+    final_units = eng.fetch_counts() if world == 1 else None
+
+    e2e = None
+    if not args.no_e2e:
+        hq = pinned_empty(n)
+        hs = pinned_empty(n)
+        hq[:] = q.cpu().numpy()
+        hs[:] = s.cpu().numpy()
+        for _ in range(2):
+            eng.reset_counts()
+            eng.classify_chunk(hq, hs)
+            res = eng.fetch_counts()
+        barrier()
+        t0 = time.perf_counter()
+        b0 = torch.cuda.Event(enable_timing=True)
+        b1 = torch.cuda.Event(enable_timing=True)
+        b0.record()
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(e2e_steps):
+            eng.reset_counts()
+            eng.classify_chunk(hq, hs)      # H2D inside
+            if world > 1:
+                dist.all_reduce(counts)
+            res = eng.fetch_counts()        # D2H of the count table
+        b1.record()
+        barrier()
+        ems = max(b0.elapsed_time(b1), (time.perf_counter() - t0) * 1e3)
+        tms = torch.tensor([ems], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ems = float(tms.item())
+        e2e = {'value': n * world * e2e_steps / (ems * 1e-3), 'unit': UNIT,
+               'h2d_bytes_per_step': int(2 * 4 * n),
+               'd2h_bytes_per_step': int(res.nbytes),
+               'steps': e2e_steps, 'ms_per_step': ems / e2e_steps,
+               'api': 'wk_classify_chunk(host SoA) + wk_fetch_counts'}
+        if final_units is not None:
+            assert np.array_equal(res, final_units), 'e2e != device path'
+
+    cpu = None
+    parity = None
+    if rank == 0 and not args.no_cpu:
+        from oracle import oracle as O
+        threads = O.max_threads()
+        m = min(n, args.cpu_sample)
+        # cut the sample at a query boundary
+        qh = q[:m + 64].cpu().numpy()
+        sh = s[:m + 64].cpu().numpy()
+        while m < len(qh) and m > 0 and qh[m] == qh[m - 1]:
+            m += 1
+        qh, sh = qh[:m], sh[:m]
+        (eu, eo, _), dt = cpu_classify(case, entries, flags, qh, sh, threads)
+        (_, _, _), dt1 = cpu_classify(case, entries, flags, qh[:m // 8],
+                                      sh[:m // 8], 1)
+        eng.reset_counts()
+        eng.classify_chunk(qh, sh)
+        gu = eng.fetch_counts()
+        ok_, od_ = eng.fetch_overflow()
+        parity = bool(np.array_equal(gu, eu)) and \
+            sorted(zip(ok_.tolist(), od_.tolist())) == eo
+        cpu = {'value': m / dt, 'unit': UNIT, 'cores': threads,
+               'kind': 'port',
+               'sample': f'{m} records of the timed batch, C restatement '
+                         f'of the reference path (oracle/woltka_oracle.c), '
+                         f'{threads} OpenMP threads',
+               'single_thread_value': (m // 8) / dt1}
+        assert parity, 'GPU result differs from the oracle on the sample'
+
+    if rank == 0:
+        achieved = bytes_per_rec * n / (k_ms * 1e-3) / 1e9
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32',
+            'data': 'synthetic', 'config': workload_config(args, entries),
+            'roofline': {'bound': 'hbm', 'achieved': achieved,
+                         'peak': hbm_peak, 'unit': 'GB/s',
+                         'frac': achieved / hbm_peak, 'traffic': None,
+                         'kernel': 'classify_kernel',
+                         'kernel_ms': k_ms, 'peak_source': peak_src,
+                         'algorithmic_bytes_per_record': bytes_per_rec},
+            'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
+            'clocks': clocks, 'parity_on_sample': parity,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_ours_cfg3(args, eng, dev, world, rank, barrier, hbm_peak, peak_src):
+    import torch
+    import torch.distributed as dist
+    from woltka_b200 import synth
+    from woltka_b200._lib import KIND_NONE_ID
+    from woltka_b200.engine import pinned_empty
+    n = args.records
+    coff, gb, ge = synth.gen_genes()
+    G = len(gb)
+    eng.set_plan(np.array([KIND_NONE_ID]), 0, 0.0, 1, G)
+    eng.set_subjects(None, None, G)
+    eng.ordinal_set_genes(coff, gb, ge, np.arange(G, dtype=np.int32))
+    cols = synth.gen_reads(n, seed=1003 + rank, device=dev)
+    rq, rc, rb, re_, rl, nq = cols
+    ptrs = [x.data_ptr() for x in (rq, rc, rb, re_, rl)]
+    counts = eng.counts_tensor()
+
+    def step():
+        eng.reset_counts()
+        eng.ordinal_device(ptrs, n, 0.8)
+        if world > 1:
+            dist.all_reduce(counts)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = eng.launch_count()
+    sampler = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()
+    t_beg = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    k_ev = [(torch.cuda.Event(enable_timing=True),
+             torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_beg.record()
+    for i in range(args.steps):
+        eng.reset_counts()
+        k_ev[i][0].record()
+        eng.ordinal_device(ptrs, n, 0.8)
+        k_ev[i][1].record()
+        if world > 1:
+            dist.all_reduce(counts)
+    t_end.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = t_beg.elapsed_time(t_end)
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    launches = eng.launch_count() - l0
+    tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    value = n * world * args.steps / (ms * 1e-3)
+
+    e2e = None
+    if not args.no_e2e:
+        host = []
+        for x in (rq, rc, rb, re_, rl):
+            h = pinned_empty(n)
+            h[:] = x.cpu().numpy()
+            host.append(h)
+        eng.reset_counts()
+        eng.ordinal_chunk(*host, 0.8)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = 3
+        for _ in range(e2e_steps):
+            eng.reset_counts()
+            eng.ordinal_chunk(*host, 0.8)
+            if world > 1:
+                dist.all_reduce(counts)
+            res = eng.fetch_counts()
+        barrier()
+        ems = (time.perf_counter() - t0) * 1e3
+        e2e = {'value': n * world * e2e_steps / (ems * 1e-3), 'unit': UNIT,
+               'h2d_bytes_per_step': int(5 * 4 * n),
+               'd2h_bytes_per_step': int(res.nbytes), 'steps': e2e_steps,
+               'ms_per_step': ems / e2e_steps,
+               'api': 'wk_ordinal_chunk(host SoA) + wk_fetch_counts'}
+
+    cpu = None
+    parity = None
+    if rank == 0 and not args.no_cpu:
+        from oracle import oracle as O
+        m = min(n, 1_000_000)
+        c4 = [x[:m].cpu().numpy() for x in (rc, rb, re_, rl)]
+        t0 = time.perf_counter()
+        er, eg = O.ordinal_match(*c4, 0.8, coff, gb, ge)
+        dt = time.perf_counter() - t0
+        eng.ordinal_enable_pairs()
+        eng.reset_counts()
+        eng.ordinal_chunk(rq[:m].cpu().numpy(), *c4, 0.8)
+        r, g = eng.ordinal_pairs()
+        parity = bool(np.array_equal(r, er) and np.array_equal(g, eg))
+        cpu = {'value': m / dt, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+               'sample': f'{m} reads of the timed batch, sweep matcher '
+                         f'(ordinal.match_read_gene restated in C)'}
+        assert parity, 'GPU pairs differ from the oracle sweep on the sample'
+
+    if rank == 0:
+        alg_bytes = 20 * n + 8 * G
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        print(json.dumps({
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32',
+            'data': 'synthetic', 'config': workload_config(args, ['none']),
+            'roofline': {'bound': 'hbm', 'achieved': achieved,
+                         'peak': hbm_peak, 'unit': 'GB/s',
+                         'frac': achieved / hbm_peak, 'traffic': None,
+                         'kernel': 'ordinal_match_kernel+classify_kernel',
+                         'kernel_ms': k_ms, 'peak_source': peak_src,
+                         'algorithmic_bytes_per_record': 20,
+                         'algorithmic_bytes_per_gene': 8},
+            'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
+            'clocks': clocks, 'parity_on_sample': parity}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,190 @@
+/* woltka_b200.h — C-ABI of the B200-native `woltka classify` hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / numpy
+ * types.  The reference (qiyunzhu/woltka, pure Python) has no FFI of its own;
+ * each entry point below names the reference function(s) whose work it takes
+ * over (paths relative to /root/reference/woltka/).  The Python host side
+ * (woltka_b200/engine.py) binds these with ctypes; INTEGRATION.md shows the
+ * stub a reference maintainer would add.
+ *
+ * World model
+ * -----------
+ * The reference works on Python str/set/dict.  The host interns strings:
+ *   subject index  s in [0, V)   : every distinct subject string seen so far
+ *   feature  index f in [0, NF)  : tree nodes first (topological order,
+ *                                  parent[i] < i, root == 0 by convention of
+ *                                  the host, any root index accepted), then
+ *                                  subjects that are not tree nodes;
+ *                                  f == NF is the 'Unassigned' column
+ *   query    index q             : one value per query; records of one query
+ *                                  are CONTIGUOUS and carry the same q
+ *                                  (align.py:325-339 groups adjacent QNAMEs)
+ *   sample   index in [0, S)
+ * An alignment chunk is int32 SoA columns (q, s) [+ contig, beg, end, len for
+ * the ordinal path].
+ *
+ * Counts are exact integers in units of 1/WK_UNITS: a unique assignment adds
+ * WK_UNITS, a 1/d split adds WK_UNITS/d (classify.py:163-170).  Denominators
+ * that do not divide WK_UNITS go to an overflow list of (cell, d) pairs that
+ * the host sums as exact rationals.
+ *
+ * Ownership: the caller owns every host array; the library owns all device
+ * memory behind the opaque context.  One context per GPU; calls on one
+ * context must be serialised by the caller.  Every function returns WK_OK or
+ * an error code; wk_last_error() gives the message (thread-local).
+ */
+#ifndef WOLTKA_B200_H
+#define WOLTKA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WK_ABI_VERSION 1
+#define WK_UNITS 720720LL /* lcm(1..16) */
+#define WK_MAX_ENTRIES 8
+
+enum wk_status {
+  WK_OK = 0,
+  WK_ERR_CUDA = 1,     /* CUDA runtime error (message has the details)     */
+  WK_ERR_ARG = 2,      /* invalid argument                                 */
+  WK_ERR_STATE = 3,    /* call sequence error (e.g. chunk before plan)     */
+  WK_ERR_NOMEM = 4,    /* allocation failed                                */
+  WK_ERR_CAPACITY = 5  /* an output list / hash table is full              */
+};
+
+/* How one entry of `ranks` is assigned (workflow.py:1017-1032). */
+enum wk_kind {
+  WK_KIND_NONE = 0,    /* classify.assign_none, feature = tab[e][s]        */
+  WK_KIND_FREE = 1,    /* classify.assign_free                             */
+  WK_KIND_RANK = 2,    /* classify.assign_rank                             */
+  WK_KIND_NONE_ID = 3  /* assign_none with feature == subject index        */
+};
+
+/* Assignment flags (workflow.py:274-278). */
+#define WK_F_UNIQ 1u       /* --uniq                                       */
+#define WK_F_ABOVE 2u      /* --above                                      */
+#define WK_F_MAJOR 4u      /* --major given (threshold in major_th)        */
+#define WK_F_UNASSIGNED 8u /* --unassigned (workflow.py:1038-1039)         */
+
+typedef struct wk_ctx wk_ctx;
+
+/* ---- library / context ------------------------------------------------ */
+const char *wk_last_error(void);
+int wk_abi_version(void);
+int wk_device_count(int *n);
+int wk_create(int device, wk_ctx **out);
+int wk_destroy(wk_ctx *ctx);
+/* Run all work of this context on an existing cudaStream_t (e.g. torch's
+ * current stream) instead of the context's own stream. NULL restores it. */
+int wk_set_stream(wk_ctx *ctx, void *cuda_stream);
+int wk_sync(wk_ctx *ctx);
+/* Number of kernels this context has launched so far. */
+int64_t wk_launch_count(wk_ctx *ctx);
+/* Persistent-grid tuning (0 = default): CTAs, threads per CTA. */
+int wk_set_tuning(wk_ctx *ctx, int grid, int block, int cache_slots);
+
+/* Pinned host memory for chunk producers (H2D at full PCIe rate). */
+int wk_host_alloc(void **out, int64_t bytes);
+int wk_host_free(void *p);
+
+/* ---- hierarchy: replaces the dict walks of tree.py ------------------- */
+/* parent[i] is the parent node of node i; nodes are in topological order
+ * (parent[i] < i for every non-root i, parent[root] == root).  Used by the
+ * LCA of assign_free / --above (tree.py:513-566, get_lineage :391-432). */
+int wk_set_tree(wk_ctx *ctx, const int32_t *parent, int32_t n_nodes,
+                int32_t root);
+
+/* ---- plan: replaces the assigner construction of
+ *      workflow.assign_readmap (workflow.py:1017-1032) ------------------ */
+/* kinds[n_entries]: one wk_kind per element of `ranks`.  major_th is
+ * major/100 computed in double by the caller (workflow.py:276).
+ * n_features = NF (the table gets NF+1 columns, last = 'Unassigned').
+ * Allocates and zeroes the count table [n_entries][n_samples][NF+1]. */
+int wk_set_plan(wk_ctx *ctx, const int32_t *kinds, int32_t n_entries,
+                uint32_t flags, double major_th, int32_t n_samples,
+                int64_t n_features);
+/* Grow the feature / sample space, keeping the counts accumulated so far. */
+int wk_resize_counts(wk_ctx *ctx, int32_t n_samples, int64_t n_features);
+
+/* Per-subject lookup tables, [n_entries][n_subjects] row-major:
+ *   NONE    : feature index of the subject itself
+ *   FREE    : single-hit result, i.e. subok ? feature(s)
+ *             : (parent of node(s), -1 if s is not a node) (classify.py:75)
+ *   RANK    : tree.find_rank(s, rank) as a node index, -1 = None
+ *             (tree.py:467-510)
+ *   NONE_ID : row ignored
+ * sub_node[n_subjects]: node index of each subject, -1 if not in the tree
+ * (needed for FREE; may be NULL otherwise). */
+int wk_set_subjects(wk_ctx *ctx, const int32_t *tab, const int32_t *sub_node,
+                    int64_t n_subjects);
+
+/* ---- classify: replaces the per-chunk body of workflow.classify
+ *      (workflow.py:316-335): demultiplexed assign + count + sum_dict ---- */
+/* Host arrays.  q_sample[n_qry] (indexed by q value) or NULL => `sample`.
+ * q_stratum[n_qry] or NULL; with strata, queries with stratum < 0 are
+ * skipped and counts are keyed by (stratum, feature) (classify.py:216-249). */
+int wk_classify_chunk(wk_ctx *ctx, const int32_t *qidx, const int32_t *sidx,
+                      int64_t n_rec, const int32_t *q_sample,
+                      const int32_t *q_stratum, int64_t n_qry, int32_t sample);
+/* Same, columns already resident in device memory (16-byte aligned).  The
+ * call is asynchronous on the context stream. */
+int wk_classify_device(wk_ctx *ctx, const int32_t *d_qidx,
+                       const int32_t *d_sidx, int64_t n_rec,
+                       const int32_t *d_q_sample, const int32_t *d_q_stratum,
+                       int64_t n_qry, int32_t sample);
+
+/* ---- ordinal: replaces ordinal.load_gene_coords' arrays, flush_chunk and
+ *      match_read_gene[_quart] (ordinal.py:243-335, 476-582, 650-811) ---- */
+/* Genes grouped by contig (contig_off[n_contigs+1]) and sorted by gbeg
+ * within a contig.  gbeg = min(a,b)-1, gend = max(a,b) (ordinal.py:459-465).
+ * gene_subject[g] = subject index of the gene's (prefixed) identifier. */
+int wk_ordinal_set_genes(wk_ctx *ctx, const int64_t *contig_off,
+                         const int32_t *gbeg, const int32_t *gend,
+                         const int32_t *gene_subject, int32_t n_contigs,
+                         int64_t n_genes);
+/* One chunk of alignment records: contig index (-1 = contig without genes),
+ * beg = POS-1, end = beg+span, len = aligned length (align.py:382-398).
+ * th = overlap/100 computed in double (workflow.py:582).  Matches reads to
+ * genes by  min(gend,end) - max(gbeg,beg) >= ceil(len*th)  (ordinal.py:
+ * 644-646), then classifies the (query, gene) pairs like a plain chunk. */
+int wk_ordinal_chunk(wk_ctx *ctx, const int32_t *qidx, const int32_t *contig,
+                     const int32_t *beg, const int32_t *end,
+                     const int32_t *len, int64_t n_rec, double th,
+                     const int32_t *q_sample, const int32_t *q_stratum,
+                     int64_t n_qry, int32_t sample);
+int wk_ordinal_device(wk_ctx *ctx, const int32_t *d_qidx,
+                      const int32_t *d_contig, const int32_t *d_beg,
+                      const int32_t *d_end, const int32_t *d_len,
+                      int64_t n_rec, double th, const int32_t *d_q_sample,
+                      const int32_t *d_q_stratum, int64_t n_qry,
+                      int32_t sample);
+/* Match only: (read index, gene index-in-table) pairs of the last ordinal
+ * chunk in record order; *n_pairs receives the count (call with pairs NULL
+ * to query it). */
+int wk_ordinal_fetch_pairs(wk_ctx *ctx, int64_t *n_pairs, int32_t *read_idx,
+                           int32_t *gene_idx, int64_t cap);
+
+/* ---- results: replaces the `data[rank][sample]` dicts
+ *      (workflow.py:268, util.sum_dict util.py:78-94) ------------------- */
+/* units[n_entries][n_samples][NF+1], in 1/WK_UNITS. */
+int wk_fetch_counts(wk_ctx *ctx, int64_t *units);
+/* Contributions 1/den with den not dividing WK_UNITS: cell = flat index into
+ * the units table. Call with cell == NULL to get the count. */
+int wk_fetch_overflow(wk_ctx *ctx, int64_t *n, int64_t *cell, int32_t *den,
+                      int64_t cap);
+/* Stratified counts: (entry, sample, stratum, feature) -> units. */
+int wk_fetch_strata(wk_ctx *ctx, int64_t *n, int32_t *entry, int32_t *sample,
+                    int32_t *stratum, int64_t *feature, int64_t *units,
+                    int64_t cap);
+int wk_reset_counts(wk_ctx *ctx);
+/* Device address / length (in int64 elements) of the units table, for a
+ * caller-side NCCL reduce (torch.distributed) across GPUs. */
+int wk_counts_device(wk_ctx *ctx, void **d_ptr, int64_t *n_elems);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WOLTKA_B200_H */

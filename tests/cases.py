@@ -1,0 +1,129 @@
+"""Seeded integer-world cases shared by the GPU parity tests and smoke()."""
+import numpy as np
+
+from woltka_b200 import synth
+from woltka_b200._lib import (KIND_NONE, KIND_FREE, KIND_RANK, KIND_NONE_ID,
+                              F_UNIQ, F_ABOVE, F_MAJOR, F_UNASSIGNED)
+from woltka_b200.hierarchy import FlatTree
+
+
+class Case:
+    """A classify problem in the integer world of include/woltka_b200.h."""
+
+    def __init__(self, tax, n_extra=0, internal_subjects=0, seed=0):
+        # subjects: every genome, then `internal_subjects` internal nodes,
+        # then `n_extra` subjects that are not in the tree
+        rng = np.random.default_rng(seed)
+        self.tax = tax
+        self.ft = FlatTree.from_arrays(tax.parent, tax.node_rank,
+                                       tax.rank_names, tax.level_off)
+        T = tax.T
+        g = np.arange(tax.n_genomes, dtype=np.int32) + tax.genome_node0
+        inner = rng.integers(0, tax.genome_node0, internal_subjects,
+                             dtype=np.int32)
+        self.sub_node = np.concatenate(
+            [g, inner, np.full(n_extra, -1, dtype=np.int32)]).astype(np.int32)
+        self.sub_feat = self.sub_node.copy()
+        self.sub_feat[self.sub_node < 0] = T + np.arange(n_extra)
+        self.V = len(self.sub_node)
+        self.NF = T + n_extra
+
+    def tables(self, entries, subok=False):
+        """entries: list of 'none' | 'free' | rank name -> (kinds, tab, trk)"""
+        kinds, rows, trk = [], [], []
+        for e in entries:
+            if e == 'none':
+                kinds.append(KIND_NONE)
+                rows.append(self.sub_feat)
+                trk.append(0)
+            elif e == 'free':
+                kinds.append(KIND_FREE)
+                par = np.where(self.sub_node >= 0,
+                               self.ft.parent[np.maximum(self.sub_node, 0)],
+                               -1)
+                rows.append(self.sub_feat if subok else par)
+                trk.append(0)
+            else:
+                kinds.append(KIND_RANK)
+                anc = self.ft.anc_at_rank(e)
+                rows.append(np.where(self.sub_node >= 0,
+                                     anc[np.maximum(self.sub_node, 0)], -1))
+                trk.append(self.ft.rank_id(e))
+        return (np.array(kinds, dtype=np.int32),
+                np.stack(rows).astype(np.int32),
+                np.array(trk, dtype=np.int32))
+
+
+def random_hits(case, n_qry, seed, kmax=16, p=0.48, long_every=0,
+                long_len=100, window=20):
+    """Random records over ALL subjects of the case, with duplicates and,
+    optionally, a query of `long_len` hits every `long_every` queries."""
+    rng = np.random.default_rng(seed)
+    k = np.minimum(rng.geometric(p, n_qry), kmax)
+    if long_every:
+        k[long_every - 1::long_every] = long_len
+    q = np.repeat(np.arange(n_qry, dtype=np.int32), k)
+    n = len(q)
+    first = rng.integers(0, case.V, n_qry)
+    start = np.cumsum(k) - k
+    pos = np.arange(n) - start[q]
+    s = (first[q] + np.where(pos == 0, 0, rng.integers(0, window, n))) % case.V
+    dup = (rng.random(n) < 0.05) & (pos > 0)
+    s = np.where(dup, np.roll(s, 1), s)
+    return q, s.astype(np.int32)
+
+
+MODES = {
+    'default': 0,
+    'uniq': F_UNIQ,
+    'above': F_ABOVE,
+    'major': F_MAJOR,
+    'uniq+unassigned': F_UNIQ | F_UNASSIGNED,
+    'major+unassigned': F_MAJOR | F_UNASSIGNED,
+    'above+unassigned': F_ABOVE | F_UNASSIGNED,
+}
+
+
+def run_engine(eng, case, entries, flags, major_th, q, s, n_samples=1,
+               q_sample=None, q_stratum=None, sample=0, subok=False,
+               root=0, chunks=1):
+    kinds, tab, _ = case.tables(entries, subok)
+    eng.set_tree(case.ft.parent, root)
+    eng.set_plan(kinds, flags, major_th, n_samples, case.NF)
+    eng.set_subjects(tab, case.sub_node)
+    # split at query boundaries into `chunks` calls
+    n = len(q)
+    cuts = [0]
+    for c in range(1, chunks):
+        x = n * c // chunks
+        while 0 < x < n and q[x] == q[x - 1]:
+            x += 1
+        cuts.append(max(x, cuts[-1]))
+    cuts.append(n)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        eng.classify_chunk(q[a:b], s[a:b], q_sample, q_stratum, sample)
+    units = eng.fetch_counts()
+    ok, od = eng.fetch_overflow()
+    overflow = sorted(zip(ok.tolist(), od.tolist()))
+    strata = {}
+    if q_stratum is not None:
+        e, sm, st, f, u = eng.fetch_strata()
+        NF1 = case.NF + 1
+        for i in range(len(e)):
+            cell = (int(e[i]) * n_samples + int(sm[i])) * NF1 + int(f[i])
+            strata[(int(st[i]) << 40) | cell] = int(u[i])
+    return units, overflow, strata
+
+
+def run_oracle(case, entries, flags, major_th, q, s, n_samples=1,
+               q_sample=None, q_stratum=None, sample=0, subok=False, root=0,
+               n_threads=1):
+    from oracle import oracle as O
+    kinds, _, trk = case.tables(entries, subok)
+    return O.classify(q, s, parent=case.ft.parent,
+                      node_rank=case.ft.node_rank, root=root,
+                      sub_node=case.sub_node, sub_feat=case.sub_feat,
+                      kinds=kinds, target_rank=trk, flags=flags,
+                      major_th=major_th, subok=subok, n_samples=n_samples,
+                      n_features=case.NF, q_sample=q_sample,
+                      q_stratum=q_stratum, sample=sample, n_threads=n_threads)

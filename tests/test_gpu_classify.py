@@ -1,0 +1,153 @@
+"""GPU parity: CUDA classify path (through the C-ABI) vs the CPU oracle,
+bit-exact on the integer units tables."""
+import numpy as np
+import pytest
+
+from tests import cases
+from woltka_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def small_case():
+    tax = synth.Taxonomy(seed=7, level_sizes=[1, 2, 5, 12, 30, 60, 150, 400],
+                         n_genomes=900)
+    return cases.Case(tax, n_extra=40, internal_subjects=60, seed=3)
+
+
+@pytest.fixture(scope='module')
+def big_case():
+    return cases.Case(synth.Taxonomy(seed=42))
+
+
+def _same(a, b):
+    ua, oa, sa = a
+    ub, ob, sb = b
+    assert ua.shape == ub.shape
+    bad = np.argwhere(ua != ub)
+    assert len(bad) == 0, f'{len(bad)} cells differ, first {bad[:5]}'
+    assert oa == ob
+    assert sa == sb
+
+
+@pytest.mark.parametrize('mode', list(cases.MODES))
+@pytest.mark.parametrize('entries', [['genus'], ['none'], ['free'],
+                                     ['phylum', 'genus', 'species'],
+                                     ['none', 'free', 'family']])
+def test_modes_small(engine, small_case, mode, entries):
+    q, s = cases.random_hits(small_case, 20000, seed=11)
+    flags = cases.MODES[mode]
+    th = 0.8
+    _same(cases.run_engine(engine, small_case, entries, flags, th, q, s),
+          cases.run_oracle(small_case, entries, flags, th, q, s))
+
+
+@pytest.mark.parametrize('th', [0.54, 0.55, 0.6, 0.81, 0.5, 0.3, 1.0])
+def test_major_thresholds(engine, small_case, th):
+    # includes th <= 0.5 (first-seen top item) and the fp-sensitive values
+    q, s = cases.random_hits(small_case, 30000, seed=5, kmax=12, p=0.3,
+                             window=8)
+    fl = cases.MODES['major+unassigned']
+    _same(cases.run_engine(engine, small_case, ['genus', 'family'], fl, th, q, s),
+          cases.run_oracle(small_case, ['genus', 'family'], fl, th, q, s))
+
+
+@pytest.mark.parametrize('mode', ['default', 'major', 'above', 'uniq'])
+def test_long_queries(engine, small_case, mode):
+    # queries of 100 and 700 hits take the slow path, k > 16 exercises the
+    # overflow list (denominators that do not divide 720720)
+    fl = cases.MODES[mode]
+    for ll in (33, 100, 700):
+        q, s = cases.random_hits(small_case, 3000, seed=ll, kmax=31,
+                                 p=0.15, long_every=97, long_len=ll,
+                                 window=300)
+        ent = ['none', 'free', 'genus', 'phylum']
+        _same(cases.run_engine(engine, small_case, ent, fl, 0.6, q, s),
+              cases.run_oracle(small_case, ent, fl, 0.6, q, s))
+
+
+def test_subok_and_no_root(engine, small_case):
+    q, s = cases.random_hits(small_case, 20000, seed=2)
+    for subok in (False, True):
+        for root in (0, -1):
+            _same(cases.run_engine(engine, small_case, ['free'], 0, 0, q, s,
+                                   subok=subok, root=root),
+                  cases.run_oracle(small_case, ['free'], 0, 0, q, s,
+                                   subok=subok, root=root))
+
+
+def test_samples_and_chunks(engine, small_case):
+    q, s = cases.random_hits(small_case, 50000, seed=9)
+    rng = np.random.default_rng(1)
+    nq = int(q.max()) + 1
+    q_sample = rng.integers(-1, 7, nq).astype(np.int32)  # -1 = dropped
+    ent = ['genus', 'none']
+    ref = cases.run_oracle(small_case, ent, 0, 0, q, s, n_samples=7,
+                           q_sample=q_sample)
+    for chunks in (1, 3, 17):
+        _same(cases.run_engine(engine, small_case, ent, 0, 0, q, s,
+                               n_samples=7, q_sample=q_sample, chunks=chunks),
+              ref)
+    # scalar sample
+    _same(cases.run_engine(engine, small_case, ent, 0, 0, q, s, n_samples=7,
+                           sample=5),
+          cases.run_oracle(small_case, ent, 0, 0, q, s, n_samples=7, sample=5))
+
+
+def test_strata(engine, small_case):
+    q, s = cases.random_hits(small_case, 40000, seed=21)
+    rng = np.random.default_rng(4)
+    nq = int(q.max()) + 1
+    q_sample = rng.integers(0, 3, nq).astype(np.int32)
+    q_stratum = rng.integers(-1, 50, nq).astype(np.int32)
+    for mode in ('default', 'uniq+unassigned'):
+        fl = cases.MODES[mode]
+        _same(cases.run_engine(engine, small_case, ['genus', 'none'], fl, 0,
+                               q, s, n_samples=3, q_sample=q_sample,
+                               q_stratum=q_stratum),
+              cases.run_oracle(small_case, ['genus', 'none'], fl, 0, q, s,
+                               n_samples=3, q_sample=q_sample,
+                               q_stratum=q_stratum))
+
+
+def test_edge_inputs(engine, small_case):
+    ent = ['genus']
+    # empty chunk
+    e = np.zeros(0, dtype=np.int32)
+    _same(cases.run_engine(engine, small_case, ent, 0, 0, e, e),
+          cases.run_oracle(small_case, ent, 0, 0, e, e))
+    # single record, and sizes around the tile / window boundaries
+    for n in (1, 2, 31, 32, 33, 63, 64, 65, 4095, 4096, 4097, 8191, 8193):
+        q, s = cases.random_hits(small_case, n, seed=n)
+        _same(cases.run_engine(engine, small_case, ent, 0, 0, q, s),
+              cases.run_oracle(small_case, ent, 0, 0, q, s))
+    # one query spanning several tiles; all records one subject
+    q = np.zeros(10000, dtype=np.int32)
+    s = np.full(10000, 5, dtype=np.int32)
+    _same(cases.run_engine(engine, small_case, ent, 0, 0, q, s),
+          cases.run_oracle(small_case, ent, 0, 0, q, s))
+    # every record its own query
+    q = np.arange(9999, dtype=np.int32)
+    s = (q * 7 % small_case.V).astype(np.int32)
+    _same(cases.run_engine(engine, small_case, ent, 0, 0, q, s),
+          cases.run_oracle(small_case, ent, 0, 0, q, s))
+
+
+def test_bad_subject_is_an_error(engine, small_case):
+    from woltka_b200.engine import WoltkaB200Error
+    q = np.array([0, 1], dtype=np.int32)
+    s = np.array([0, small_case.V + 5], dtype=np.int32)
+    with pytest.raises(WoltkaB200Error):
+        cases.run_engine(engine, small_case, ['genus'], 0, 0, q, s)
+
+
+@pytest.mark.parametrize('mode', ['default', 'major', 'uniq', 'above'])
+def test_cfg2_shape_1e6(engine, big_case, mode):
+    # the §8(d) generator at 1e6 records on the 21,603-node taxonomy
+    qi, si, _, nq = synth.gen_hits(1_000_000, seed=1002)
+    q, s = qi.numpy(), si.numpy()
+    fl = cases.MODES[mode]
+    ent = ['phylum', 'genus', 'species']
+    _same(cases.run_engine(engine, big_case, ent, fl, 0.8, q, s),
+          cases.run_oracle(big_case, ent, fl, 0.8, q, s, n_threads=4))

@@ -1,0 +1,140 @@
+"""GPU parity: closed-form read-gene matching kernel vs the reference's
+endpoint sweep (oracle restatement of ordinal.match_read_gene)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from woltka_b200 import synth
+from woltka_b200.engine import Engine
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_pairs(coff, gb, ge, cols, th):
+    eng = Engine(0)
+    try:
+        eng.ordinal_set_genes(coff, gb, ge, np.arange(len(gb), dtype=np.int32))
+        eng.ordinal_enable_pairs()
+        eng.ordinal_chunk(*cols, th)
+        return eng.ordinal_pairs()
+    finally:
+        eng.close()
+
+
+def _check(coff, gb, ge, cols, th):
+    r, g = _gpu_pairs(coff, gb, ge, cols, th)
+    q, c, b, e, l = cols
+    er, eg = O.ordinal_match(c, b, e, l, th, coff, gb, ge)
+    assert len(r) == len(er)
+    assert np.array_equal(r, er) and np.array_equal(g, eg)
+    return len(r)
+
+
+def _kat(genes, reads, lens, th):
+    order = np.argsort([g[0] for g in genes], kind='stable')
+    gb = np.array([genes[i][0] for i in order], dtype=np.int32)
+    ge = np.array([genes[i][1] for i in order], dtype=np.int32)
+    coff = np.array([0, len(gb)], dtype=np.int64)
+    n = len(reads)
+    cols = (np.arange(n, dtype=np.int32), np.zeros(n, dtype=np.int32),
+            np.array([r[0] for r in reads], dtype=np.int32),
+            np.array([r[1] for r in reads], dtype=np.int32),
+            np.full(n, lens, dtype=np.int32))
+    r, g = _gpu_pairs(coff, gb, ge, cols, th)
+    return sorted(zip(r.tolist(), order[g].tolist()))
+
+
+def test_reference_kats():
+    # known answers of the reference's own unit tests, coordinates as they
+    # appear in the encoded queues (gene start already lo-1)
+    # tests/test_ordinal.py:121-161 (match_read_gene), L = 20 * 0.8 = 16
+    genes = [(5, 29), (33, 61), (65, 94)]
+    reads = [(10, 29), (16, 35), (20, 39), (22, 41), (30, 49), (30, 49),
+             (60, 79), (65, 84), (82, 95)]
+    assert _kat(genes, reads, 20, 0.8) == [(0, 0), (4, 1), (5, 1), (7, 2)]
+    # tests/test_ordinal.py:163-197 (match_read_gene_naive), L = 14
+    genes = [(4, 29), (32, 61), (64, 94)]
+    reads = [(9, 29), (15, 35), (19, 39), (21, 41), (29, 49), (29, 49),
+             (59, 79), (64, 84), (81, 95)]
+    assert _kat(genes, reads, 14, 1.0) == [(0, 0), (1, 0), (4, 1), (5, 1),
+                                           (6, 2), (7, 2)]
+    # tests/test_ordinal.py:199-237 (match_read_gene_quart), nested genes
+    genes = [(4, 29), (32, 61), (64, 94), (60, 76), (66, 72)]
+    reads = [(9, 29), (15, 35), (19, 39), (21, 41), (29, 49), (29, 49),
+             (59, 79), (64, 84), (69, 75), (81, 95)]
+    assert _kat(genes, reads, 14, 1.0) == sorted(
+        [(0, 0), (1, 0), (4, 1), (5, 1), (6, 3), (6, 2), (7, 2)])
+    # tests/test_ordinal.py:239-251 "giant read": no match
+    assert _kat([(0, 5), (5, 7), (6, 8)], [(3, 9)], 5, 1.0) == []
+
+
+@pytest.mark.parametrize('th', [0.8, 0.55, 0.81, 0.07, 1.0, 0.5])
+def test_random_vs_sweep(th):
+    coff, gb, ge = synth.gen_genes(30, 400, 500_000, seed=11)
+    rq, rc, rb, re_, rl, _ = synth.gen_reads(200_000, 30, 500_000, seed=12)
+    cols = tuple(x.numpy() for x in (rq, rc, rb, re_, rl))
+    assert _check(coff, gb, ge, cols, th) > 0
+
+
+def test_nested_and_giant_genes():
+    rng = np.random.default_rng(3)
+    # a giant gene covering the contig, nested small genes, ties on starts
+    nb = 3000
+    b = np.sort(rng.integers(0, 100_000, nb)).astype(np.int32)
+    e = (b + rng.integers(1, 400, nb)).astype(np.int32)
+    gb = np.concatenate([[0], b, [50], [50]]).astype(np.int32)
+    ge = np.concatenate([[120_000], e, [60], [70000]]).astype(np.int32)
+    order = np.argsort(gb, kind='stable')
+    gb, ge = gb[order], ge[order]
+    coff = np.array([0, len(gb)], dtype=np.int64)
+    n = 50_000
+    rb = rng.integers(0, 110_000, n).astype(np.int32)
+    ln = rng.integers(1, 300, n).astype(np.int32)
+    cols = (np.arange(n, dtype=np.int32), np.zeros(n, dtype=np.int32), rb,
+            rb + ln, ln)
+    for th in (0.8, 0.2):
+        _check(coff, gb, ge, cols, th)
+
+
+def test_edges():
+    coff, gb, ge = synth.gen_genes(4, 50, 60_000, seed=2)
+    # contig without genes (index 4), unknown contig (-1), zero length
+    coff = np.concatenate([coff, [coff[-1]]])
+    rng = np.random.default_rng(9)
+    n = 5000
+    c = rng.integers(-1, 5, n).astype(np.int32)
+    b = rng.integers(0, 60_000, n).astype(np.int32)
+    ln = rng.integers(0, 200, n).astype(np.int32)
+    cols = (np.arange(n, dtype=np.int32), c, b, b + ln, ln)
+    _check(coff, gb, ge, cols, 0.8)
+    # sizes around the tile boundary, and a single read
+    for m in (1, 3, 2047, 2048, 2049, 4097):
+        cc = tuple(x[:m] for x in cols)
+        _check(coff, gb, ge, cc, 0.8)
+
+
+def test_ordinal_then_classify(engine):
+    """match + classify fused on the device == oracle sweep + oracle classify
+    over the (query, gene) pairs."""
+    coff, gb, ge = synth.gen_genes(20, 300, 300_000, seed=21)
+    G = len(gb)
+    rq, rc, rb, re_, rl, nq = synth.gen_reads(100_000, 20, 300_000, seed=22)
+    cols = tuple(x.numpy() for x in (rq, rc, rb, re_, rl))
+    from woltka_b200._lib import KIND_NONE_ID
+    eng = Engine(0)
+    try:
+        eng.set_plan(np.array([KIND_NONE_ID]), 0, 0.0, 2, G)
+        eng.set_subjects(None, None, G)
+        eng.ordinal_set_genes(coff, gb, ge, np.arange(G, dtype=np.int32))
+        q_sample = (np.arange(nq) % 2).astype(np.int32)
+        eng.ordinal_chunk(*cols, 0.8, q_sample=q_sample)
+        units = eng.fetch_counts()
+    finally:
+        eng.close()
+    er, eg = O.ordinal_match(cols[1], cols[2], cols[3], cols[4], 0.8, coff,
+                             gb, ge)
+    pq = cols[0][er]
+    exp, ovf, _ = O.classify(pq, eg, kinds=[KIND_NONE_ID], n_samples=2,
+                             n_features=G, q_sample=q_sample)
+    assert not ovf
+    assert np.array_equal(units, exp)

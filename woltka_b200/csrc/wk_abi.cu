@@ -1,0 +1,1006 @@
+// wk_abi.cu — C-ABI of the B200-native woltka classify hot path
+// (declarations + reference citations: include/woltka_b200.h).
+//
+// Host-side responsibilities kept here: device memory ownership, table
+// packing (uint16 staging copies), the gene bin index, H2D pipelining of host
+// chunks, growth of the strata hash, error reporting.  No CPU fallback: every
+// entry point that computes launches the sm_100a kernels or fails.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "wk_classify.cuh"
+#include "wk_ordinal.cuh"
+
+using namespace wk;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                          \
+  do {                                                                    \
+    cudaError_t e_ = (call);                                              \
+    if (e_ != cudaSuccess)                                                \
+      return fail(e_ == cudaErrorMemoryAllocation ? WK_ERR_NOMEM          \
+                                                  : WK_ERR_CUDA,          \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                    \
+  } while (0)
+#define TRY(call)             \
+  do {                        \
+    int r_ = (call);          \
+    if (r_ != WK_OK) return r_; \
+  } while (0)
+
+namespace {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return WK_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + (bytes >> 3) + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      e = cudaMalloc(&p, bytes + 256);
+      want = bytes + 256;
+    }
+    if (e != cudaSuccess)
+      return fail(WK_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes,
+                  cudaGetErrorString(e));
+    cap = want;
+    return WK_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T *as() const {
+    return static_cast<T *>(p);
+  }
+};
+
+__global__ void fill_u64_kernel(ull *p, size_t n, ull v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t st = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) p[i] = v;
+}
+
+__global__ void rehash_kernel(const ull *ok, const ull *ov, uint64_t ocap,
+                              ClsParams P) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t st = (size_t)gridDim.x * blockDim.x;
+  for (; i < ocap; i += st)
+    if (ok[i] != ~0ull) strat_add(P, ok[i], ov[i]);
+}
+
+__global__ void compact_hash_kernel(const ull *k, const ull *v, uint64_t cap,
+                                    ull *outk, ull *outv, ull *cursor) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t st = (size_t)gridDim.x * blockDim.x;
+  for (; i < cap; i += st)
+    if (k[i] != ~0ull) {
+      ull at = atomicAdd(cursor, 1ull);
+      outk[at] = k[i];
+      outv[at] = v[i];
+    }
+}
+
+// copy [E][oS][oNF1] into [E][nS][nNF1]; the Unassigned column moves last
+__global__ void regrid_kernel(const ull *o, ull *nw, int E, int oS, int64_t oNF1,
+                              int nS, int64_t nNF1) {
+  size_t tot = (size_t)E * oS * oNF1;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t st = (size_t)gridDim.x * blockDim.x;
+  for (; i < tot; i += st) {
+    ull v = o[i];
+    if (!v) continue;
+    int64_t f = i % oNF1;
+    size_t es = i / oNF1;
+    int s = (int)(es % oS);
+    int e = (int)(es / oS);
+    int64_t nf = f == oNF1 - 1 ? nNF1 - 1 : f;
+    nw[((size_t)e * nS + s) * nNF1 + nf] = v;
+  }
+}
+
+}  // namespace
+
+struct wk_ctx {
+  int device = 0;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+  cudaStream_t own_stream = nullptr, copy_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+  cudaEvent_t ev_free = nullptr;
+  int64_t launches = 0;
+  int tune_grid = 0, tune_cache = 0;
+  // tree
+  DevBuf parent;
+  int32_t T = 0, root = -1;
+  // plan
+  bool have_plan = false;
+  int E = 0;
+  int32_t kind[WK_MAX_ENTRIES];
+  uint32_t flags = 0;
+  double major_th = 0;
+  int S = 0;
+  int64_t NF = 0;
+  DevBuf cnt;
+  // subjects
+  DevBuf tab, tab16, sub_node;
+  int64_t V = 0;
+  int Vp = 0;
+  bool tab16_ok = false, have_sub_node = false;
+  // overflow + err
+  DevBuf ovf_key, ovf_den, small;  // small: [0]=ovf_n [1]=sh_used [2]=n_pairs [3]=cursor, err after
+  int64_t ovf_cap = 0;
+  // strata hash
+  DevBuf sh_keys, sh_vals;
+  uint64_t sh_cap = 0;
+  // staging for host chunks
+  DevBuf dq, ds, dqsamp, dqstrat, scratch;
+  DevBuf dcontig, dbeg, dend, dlen;
+  // ordinal
+  DevBuf contig_off, genes, gene_subject, bin_off, bin_first;
+  int32_t C = 0;
+  int64_t G = 0;
+  int shift = 0;
+  DevBuf pair_q, pair_s, pair_r, pair_g, tile_desc, ticket;
+  int64_t pair_cap = 0;
+  int64_t last_pairs = 0;
+  bool keep_pairs = false;
+
+  ull *d_ovf_n() { return small.as<ull>() + 0; }
+  ull *d_sh_used() { return small.as<ull>() + 1; }
+  ull *d_n_pairs() { return small.as<ull>() + 2; }
+  ull *d_cursor() { return small.as<ull>() + 3; }
+  int32_t *d_err() { return reinterpret_cast<int32_t *>(small.as<ull>() + 4); }
+};
+
+static int use_device(wk_ctx *c) {
+  CK(cudaSetDevice(c->device));
+  return WK_OK;
+}
+
+static int fill_u64(wk_ctx *c, ull *p, size_t n, ull v) {
+  if (!n) return WK_OK;
+  if (v == 0) {
+    CK(cudaMemsetAsync(p, 0, n * 8, c->stream));
+    return WK_OK;
+  }
+  int grid = (int)std::min<size_t>((n + 255) / 256, (size_t)c->sm_count * 8);
+  fill_u64_kernel<<<grid, 256, 0, c->stream>>>(p, n, v);
+  c->launches++;
+  CK(cudaGetLastError());
+  return WK_OK;
+}
+
+extern "C" {
+
+const char *wk_last_error(void) { return g_err.c_str(); }
+int wk_abi_version(void) { return WK_ABI_VERSION; }
+
+int wk_device_count(int *n) {
+  if (!n) return fail(WK_ERR_ARG, "n is NULL");
+  CK(cudaGetDeviceCount(n));
+  return WK_OK;
+}
+
+int wk_create(int device, wk_ctx **out) {
+  if (!out) return fail(WK_ERR_ARG, "out is NULL");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev)
+    return fail(WK_ERR_ARG, "device %d out of range (have %d)", device, ndev);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(WK_ERR_CUDA,
+                "device %d is sm_%d%d; this library is built for sm_100a only",
+                device, prop.major, prop.minor);
+  wk_ctx *c = new wk_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->smem_optin = prop.sharedMemPerBlockOptin;
+  CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  for (int i = 0; i < 2; ++i)
+    CK(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_free, cudaEventDisableTiming));
+  TRY(c->small.reserve(64));
+  CK(cudaMemset(c->small.p, 0, 64));
+  c->ovf_cap = 1 << 20;
+  TRY(c->ovf_key.reserve(c->ovf_cap * 8));
+  TRY(c->ovf_den.reserve(c->ovf_cap * 4));
+  CK(cudaFuncSetAttribute(classify_kernel<true>,
+                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)c->smem_optin));
+  CK(cudaFuncSetAttribute(classify_kernel<false>,
+                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)c->smem_optin));
+  *out = c;
+  return WK_OK;
+}
+
+int wk_destroy(wk_ctx *c) {
+  if (!c) return WK_OK;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  DevBuf *bufs[] = {&c->parent, &c->cnt, &c->tab, &c->tab16, &c->sub_node,
+                    &c->ovf_key, &c->ovf_den, &c->small, &c->sh_keys,
+                    &c->sh_vals, &c->dq, &c->ds, &c->dqsamp, &c->dqstrat,
+                    &c->scratch, &c->dcontig, &c->dbeg, &c->dend, &c->dlen,
+                    &c->contig_off, &c->genes, &c->gene_subject, &c->bin_off,
+                    &c->bin_first, &c->pair_q, &c->pair_s, &c->pair_r,
+                    &c->pair_g, &c->tile_desc, &c->ticket};
+  for (DevBuf *b : bufs) b->release();
+  for (int i = 0; i < 2; ++i)
+    if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
+  if (c->ev_free) cudaEventDestroy(c->ev_free);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  delete c;
+  return WK_OK;
+}
+
+int wk_set_stream(wk_ctx *c, void *s) {
+  if (!c) return fail(WK_ERR_ARG, "ctx is NULL");
+  c->stream = s ? static_cast<cudaStream_t>(s) : c->own_stream;
+  return WK_OK;
+}
+
+int wk_sync(wk_ctx *c) {
+  if (!c) return fail(WK_ERR_ARG, "ctx is NULL");
+  TRY(use_device(c));
+  CK(cudaStreamSynchronize(c->copy_stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return WK_OK;
+}
+
+int64_t wk_launch_count(wk_ctx *c) { return c ? c->launches : 0; }
+
+int wk_set_tuning(wk_ctx *c, int grid, int block, int cache_slots) {
+  if (!c) return fail(WK_ERR_ARG, "ctx is NULL");
+  (void)block;
+  c->tune_grid = grid;
+  c->tune_cache = cache_slots;
+  return WK_OK;
+}
+
+int wk_host_alloc(void **out, int64_t bytes) {
+  if (!out || bytes < 0) return fail(WK_ERR_ARG, "bad arguments");
+  CK(cudaMallocHost(out, (size_t)std::max<int64_t>(bytes, 16)));
+  return WK_OK;
+}
+int wk_host_free(void *p) {
+  if (p) CK(cudaFreeHost(p));
+  return WK_OK;
+}
+
+int wk_set_tree(wk_ctx *c, const int32_t *parent, int32_t n_nodes,
+                int32_t root) {
+  if (!c) return fail(WK_ERR_ARG, "ctx is NULL");
+  TRY(use_device(c));
+  if (n_nodes < 0 || (n_nodes > 0 && !parent))
+    return fail(WK_ERR_ARG, "bad tree arguments");
+  if (root >= n_nodes) return fail(WK_ERR_ARG, "root %d out of range", root);
+  for (int32_t i = 0; i < n_nodes; ++i) {
+    int32_t p = parent[i];
+    bool is_root = (p == i);
+    if (p < 0 || p >= n_nodes || (!is_root && p >= i))
+      return fail(WK_ERR_ARG,
+                  "tree is not in topological order at node %d (parent %d)", i,
+                  p);
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  TRY(c->parent.reserve((size_t)std::max(n_nodes, 1) * 4));
+  if (n_nodes)
+    CK(cudaMemcpy(c->parent.p, parent, (size_t)n_nodes * 4,
+                  cudaMemcpyHostToDevice));
+  c->T = n_nodes;
+  c->root = root;
+  return WK_OK;
+}
+
+int wk_set_plan(wk_ctx *c, const int32_t *kinds, int32_t n_entries,
+                uint32_t flags, double major_th, int32_t n_samples,
+                int64_t n_features) {
+  if (!c) return fail(WK_ERR_ARG, "ctx is NULL");
+  TRY(use_device(c));
+  if (!kinds || n_entries < 1 || n_entries > WK_MAX_ENTRIES)
+    return fail(WK_ERR_ARG, "n_entries must be in [1, %d]", WK_MAX_ENTRIES);
+  if (n_samples < 1 || n_features < 0)
+    return fail(WK_ERR_ARG, "bad n_samples / n_features");
+  for (int i = 0; i < n_entries; ++i)
+    if (kinds[i] < 0 || kinds[i] > 3)
+      return fail(WK_ERR_ARG, "bad kind %d at entry %d", kinds[i], i);
+  size_t len = (size_t)n_entries * n_samples * (n_features + 1);
+  if (len >= (1ull << 40))
+    return fail(WK_ERR_ARG, "count table too large (%zu cells)", len);
+  CK(cudaStreamSynchronize(c->stream));
+  TRY(c->cnt.reserve(len * 8));
+  c->E = n_entries;
+  for (int i = 0; i < n_entries; ++i) c->kind[i] = kinds[i];
+  c->flags = flags;
+  c->major_th = major_th;
+  c->S = n_samples;
+  c->NF = n_features;
+  c->have_plan = true;
+  c->V = 0;
+  c->tab16_ok = false;
+  return wk_reset_counts(c);
+}
+
+int wk_resize_counts(wk_ctx *c, int32_t n_samples, int64_t n_features) {
+  if (!c || !c->have_plan) return fail(WK_ERR_STATE, "no plan set");
+  TRY(use_device(c));
+  if (n_samples < c->S || n_features < c->NF)
+    return fail(WK_ERR_ARG, "counts can only grow");
+  if (n_samples == c->S && n_features == c->NF) return WK_OK;
+  size_t nlen = (size_t)c->E * n_samples * (n_features + 1);
+  if (nlen >= (1ull << 40)) return fail(WK_ERR_ARG, "count table too large");
+  DevBuf nb;
+  TRY(nb.reserve(nlen * 8));
+  CK(cudaMemsetAsync(nb.p, 0, nlen * 8, c->stream));
+  size_t olen = (size_t)c->E * c->S * (c->NF + 1);
+  int grid = (int)std::min<size_t>((olen + 255) / 256, (size_t)c->sm_count * 8);
+  regrid_kernel<<<grid, 256, 0, c->stream>>>(c->cnt.as<ull>(), nb.as<ull>(),
+                                            c->E, c->S, c->NF + 1, n_samples,
+                                            n_features + 1);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  c->cnt.release();
+  c->cnt = nb;
+  c->S = n_samples;
+  c->NF = n_features;
+  return WK_OK;
+}
+
+int wk_set_subjects(wk_ctx *c, const int32_t *tab, const int32_t *sub_node,
+                    int64_t n_subjects) {
+  if (!c || !c->have_plan) return fail(WK_ERR_STATE, "no plan set");
+  TRY(use_device(c));
+  if (n_subjects < 0 || n_subjects >= (1ll << 31))
+    return fail(WK_ERR_ARG, "bad n_subjects");
+  bool need_tab = false, need_node = false;
+  for (int e = 0; e < c->E; ++e) {
+    if (c->kind[e] != WK_KIND_NONE_ID) need_tab = true;
+    if (c->kind[e] == WK_KIND_FREE) need_node = true;
+  }
+  if (need_tab && n_subjects && !tab)
+    return fail(WK_ERR_ARG, "tab is NULL but the plan needs subject tables");
+  if (need_node && n_subjects && !sub_node)
+    return fail(WK_ERR_ARG, "sub_node is NULL but the plan has a FREE entry");
+  CK(cudaStreamSynchronize(c->stream));
+  c->V = n_subjects;
+  c->tab16_ok = false;
+  c->have_sub_node = false;
+  const int64_t V = n_subjects;
+  if (tab && V) {
+    const int64_t lim = c->NF;  // valid values are -1 or [0, NF)
+    int32_t vmax = -1;
+    for (int e = 0; e < c->E; ++e) {
+      if (c->kind[e] == WK_KIND_NONE_ID) continue;
+      for (int64_t i = 0; i < V; ++i) {
+        int32_t v = tab[(size_t)e * V + i];
+        if (v < -1 || v >= lim)
+          return fail(WK_ERR_ARG,
+                      "tab[%d][%lld] = %d is outside [-1, n_features)", e,
+                      (long long)i, v);
+        vmax = std::max(vmax, v);
+      }
+    }
+    TRY(c->tab.reserve((size_t)c->E * V * 4));
+    CK(cudaMemcpy(c->tab.p, tab, (size_t)c->E * V * 4, cudaMemcpyHostToDevice));
+    // uint16 copy for shared-memory staging
+    int64_t Vp = (V + 7) & ~7ll;
+    if (need_tab && vmax < 0xFFFF && (size_t)c->E * Vp * 2 <= 200 * 1024) {
+      std::vector<uint16_t> t16((size_t)c->E * Vp, 0xFFFF);
+      for (int e = 0; e < c->E; ++e) {
+        if (c->kind[e] == WK_KIND_NONE_ID) continue;
+        for (int64_t i = 0; i < V; ++i) {
+          int32_t v = tab[(size_t)e * V + i];
+          t16[(size_t)e * Vp + i] = v < 0 ? 0xFFFF : (uint16_t)v;
+        }
+      }
+      TRY(c->tab16.reserve(t16.size() * 2 + 16));
+      CK(cudaMemcpy(c->tab16.p, t16.data(), t16.size() * 2,
+                    cudaMemcpyHostToDevice));
+      c->Vp = (int)Vp;
+      c->tab16_ok = true;
+    }
+  }
+  if (sub_node && V) {
+    for (int64_t i = 0; i < V; ++i)
+      if (sub_node[i] < -1 || sub_node[i] >= c->T)
+        return fail(WK_ERR_ARG, "sub_node[%lld] = %d is not a tree node",
+                    (long long)i, sub_node[i]);
+    TRY(c->sub_node.reserve((size_t)V * 4));
+    CK(cudaMemcpy(c->sub_node.p, sub_node, (size_t)V * 4,
+                  cudaMemcpyHostToDevice));
+    c->have_sub_node = true;
+  }
+  return WK_OK;
+}
+
+int wk_reset_counts(wk_ctx *c) {
+  if (!c || !c->have_plan) return fail(WK_ERR_STATE, "no plan set");
+  TRY(use_device(c));
+  size_t len = (size_t)c->E * c->S * (c->NF + 1);
+  CK(cudaMemsetAsync(c->cnt.p, 0, len * 8, c->stream));
+  CK(cudaMemsetAsync(c->small.p, 0, 64, c->stream));
+  if (c->sh_cap) {
+    TRY(fill_u64(c, c->sh_keys.as<ull>(), c->sh_cap, ~0ull));
+    TRY(fill_u64(c, c->sh_vals.as<ull>(), c->sh_cap, 0));
+  }
+  return WK_OK;
+}
+
+}  // extern "C"
+
+// ---- launch helpers ---------------------------------------------------------
+static int check_plan_ready(wk_ctx *c, bool strata) {
+  if (!c) return fail(WK_ERR_ARG, "ctx is NULL");
+  if (!c->have_plan) return fail(WK_ERR_STATE, "wk_set_plan has not been called");
+  bool need_tab = false, need_tree = false, need_node = false;
+  for (int e = 0; e < c->E; ++e) {
+    if (c->kind[e] != WK_KIND_NONE_ID) need_tab = true;
+    if (c->kind[e] == WK_KIND_FREE) need_tree = need_node = true;
+    if (c->kind[e] == WK_KIND_RANK && (c->flags & WK_F_ABOVE) &&
+        !(c->flags & WK_F_MAJOR))
+      need_tree = true;
+  }
+  if (need_tab && c->V == 0)
+    return fail(WK_ERR_STATE, "wk_set_subjects has not been called");
+  if (need_tree && c->T == 0)
+    return fail(WK_ERR_STATE, "plan needs a tree (wk_set_tree)");
+  if (need_node && !c->have_sub_node)
+    return fail(WK_ERR_STATE, "plan needs sub_node (wk_set_subjects)");
+  if (strata && (size_t)c->E * c->S * (c->NF + 1) >= (1ull << 40))
+    return fail(WK_ERR_ARG, "count space too large for strata keys");
+  return WK_OK;
+}
+
+static int ensure_strata(wk_ctx *c, int64_t new_keys_bound) {
+  ull used = 0;
+  if (c->sh_cap) {
+    CK(cudaMemcpyAsync(&used, c->d_sh_used(), 8, cudaMemcpyDeviceToHost,
+                       c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  uint64_t need = 2 * (used + (uint64_t)new_keys_bound) + 1024;
+  if (need <= c->sh_cap) return WK_OK;
+  uint64_t ncap = 1 << 16;
+  while (ncap < need) ncap <<= 1;
+  DevBuf nk, nv;
+  TRY(nk.reserve(ncap * 8));
+  TRY(nv.reserve(ncap * 8));
+  TRY(fill_u64(c, nk.as<ull>(), ncap, ~0ull));
+  TRY(fill_u64(c, nv.as<ull>(), ncap, 0));
+  DevBuf ok = c->sh_keys, ov = c->sh_vals;
+  uint64_t ocap = c->sh_cap;
+  c->sh_keys = nk;
+  c->sh_vals = nv;
+  c->sh_cap = ncap;
+  if (ocap) {
+    CK(cudaMemsetAsync(c->d_sh_used(), 0, 8, c->stream));
+    ClsParams P;
+    memset(&P, 0, sizeof P);
+    P.sh_keys = nk.as<ull>();
+    P.sh_vals = nv.as<ull>();
+    P.sh_mask = ncap - 1;
+    P.sh_used = c->d_sh_used();
+    P.err = c->d_err();
+    int grid = (int)std::min<uint64_t>((ocap + 255) / 256, (uint64_t)c->sm_count * 8);
+    rehash_kernel<<<grid, 256, 0, c->stream>>>(ok.as<ull>(), ov.as<ull>(), ocap, P);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    ok.release();
+    ov.release();
+  }
+  return WK_OK;
+}
+
+// Launch the classify kernel over queries with head in [r0, r1) of device
+// columns dq/ds holding n readable records.
+static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
+                           int64_t n, const ull *n_dev, int64_t n_bound,
+                           int64_t r0, int64_t r1, const int32_t *dqsamp,
+                           const int32_t *dqstrat, int32_t sample) {
+  if (((uintptr_t)dq | (uintptr_t)ds) & 15)
+    return fail(WK_ERR_ARG, "record columns must be 16-byte aligned");
+  ClsParams P;
+  memset(&P, 0, sizeof P);
+  P.q = dq;
+  P.s = ds;
+  P.n = n;
+  P.n_dev = n_dev;
+  P.r0 = r0;
+  P.r1 = r1;
+  P.q_sample = dqsamp;
+  P.q_stratum = dqstrat;
+  P.sample = sample;
+  P.E = c->E;
+  for (int e = 0; e < c->E; ++e) P.kind[e] = c->kind[e];
+  P.flags = c->flags;
+  P.major_th = c->major_th;
+  P.tab = c->tab.as<int32_t>();
+  P.tab16 = c->tab16.as<uint16_t>();
+  P.V = c->V;
+  P.Vp = c->Vp;
+  bool all_id = true;
+  for (int e = 0; e < c->E; ++e) all_id &= (c->kind[e] == WK_KIND_NONE_ID);
+  if (all_id) P.V = std::max<int64_t>(c->V, c->NF);  // subject == feature
+  P.sub_node = c->have_sub_node ? c->sub_node.as<int32_t>() : nullptr;
+  P.parent = c->T ? c->parent.as<int32_t>() : nullptr;
+  P.root = c->root;
+  P.cnt = c->cnt.as<ull>();
+  P.NF1 = c->NF + 1;
+  P.S = c->S;
+  P.ovf_n = c->d_ovf_n();
+  P.ovf_key = c->ovf_key.as<int64_t>();
+  P.ovf_den = c->ovf_den.as<int32_t>();
+  P.ovf_cap = c->ovf_cap;
+  P.sh_keys = c->sh_keys.as<ull>();
+  P.sh_vals = c->sh_vals.as<ull>();
+  P.sh_mask = c->sh_cap ? c->sh_cap - 1 : 0;
+  P.sh_used = c->d_sh_used();
+  P.err = c->d_err();
+  TRY(c->scratch.reserve((size_t)std::max<int64_t>(n_bound, 1) * 4));
+  P.scratch = c->scratch.as<int32_t>();
+
+  const bool staged = c->tab16_ok && !all_id;
+  const int64_t tab_bytes = staged ? (int64_t)c->E * c->Vp * 2 : 0;
+  const size_t cells = (size_t)c->E * c->S * (c->NF + 1);
+  int cache_log = 0;
+  if (!dqstrat && cells < 0xFFFFFFFFull) {
+    int want = c->tune_cache > 0 ? 0 : 13;
+    if (c->tune_cache > 0)
+      while ((1 << (want + 1)) <= c->tune_cache) ++want;
+    for (cache_log = want; cache_log >= 8; --cache_log)
+      if (cls_layout(cache_log, tab_bytes).total <= c->smem_optin) break;
+    if (cache_log < 8) cache_log = 0;
+    if (c->tune_cache < 0) cache_log = 0;
+  }
+  P.cache_log = cache_log;
+  ClsSmemLayout L = cls_layout(cache_log, tab_bytes);
+  if (L.total > c->smem_optin)
+    return fail(WK_ERR_STATE, "shared memory layout does not fit (%u B)", L.total);
+  int64_t span = (n_dev ? n_bound : r1) - (r0 & ~3ll);
+  int64_t n_tiles = (span + CLS_TILE - 1) / CLS_TILE;
+  if (n_tiles <= 0) return WK_OK;
+  int grid = c->tune_grid > 0 ? c->tune_grid : c->sm_count;
+  grid = (int)std::min<int64_t>(grid, n_tiles);
+  if (staged)
+    classify_kernel<true><<<grid, CLS_NT, L.total, c->stream>>>(P);
+  else
+    classify_kernel<false><<<grid, CLS_NT, L.total, c->stream>>>(P);
+  c->launches++;
+  CK(cudaGetLastError());
+  return WK_OK;
+}
+
+static int check_device_err(wk_ctx *c) {
+  int32_t err = 0;
+  CK(cudaMemcpyAsync(&err, c->d_err(), 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (!err) return WK_OK;
+  CK(cudaMemsetAsync(c->d_err(), 0, 4, c->stream));
+  if (err & ERR_BAD_SUBJECT)
+    return fail(WK_ERR_ARG, "a subject index is outside [0, n_subjects)");
+  if (err & ERR_OVF_FULL)
+    return fail(WK_ERR_CAPACITY, "fraction overflow list is full");
+  if (err & ERR_HASH_FULL)
+    return fail(WK_ERR_CAPACITY, "strata hash table is full");
+  if (err & ERR_PAIR_FULL)
+    return fail(WK_ERR_CAPACITY, "read-gene pair buffer is full");
+  return fail(WK_ERR_CUDA, "device error word %d", err);
+}
+
+static int upload_per_query(wk_ctx *c, const int32_t *q_sample,
+                            const int32_t *q_stratum, int64_t n_qry,
+                            const int32_t **dqs, const int32_t **dqt) {
+  *dqs = *dqt = nullptr;
+  if ((q_sample || q_stratum) && n_qry <= 0)
+    return fail(WK_ERR_ARG, "n_qry must be given with per-query arrays");
+  if (q_sample) {
+    TRY(c->dqsamp.reserve((size_t)n_qry * 4));
+    CK(cudaMemcpyAsync(c->dqsamp.p, q_sample, (size_t)n_qry * 4,
+                       cudaMemcpyHostToDevice, c->stream));
+    *dqs = c->dqsamp.as<int32_t>();
+  }
+  if (q_stratum) {
+    TRY(c->dqstrat.reserve((size_t)n_qry * 4));
+    CK(cudaMemcpyAsync(c->dqstrat.p, q_stratum, (size_t)n_qry * 4,
+                       cudaMemcpyHostToDevice, c->stream));
+    *dqt = c->dqstrat.as<int32_t>();
+  }
+  return WK_OK;
+}
+
+extern "C" {
+
+int wk_classify_device(wk_ctx *c, const int32_t *d_qidx, const int32_t *d_sidx,
+                       int64_t n_rec, const int32_t *d_q_sample,
+                       const int32_t *d_q_stratum, int64_t n_qry,
+                       int32_t sample) {
+  (void)n_qry;
+  TRY(check_plan_ready(c, d_q_stratum != nullptr));
+  TRY(use_device(c));
+  if (n_rec < 0) return fail(WK_ERR_ARG, "n_rec < 0");
+  if (!d_q_sample && (sample < 0 || sample >= c->S))
+    return fail(WK_ERR_ARG, "sample %d out of range", sample);
+  if (n_rec == 0) return WK_OK;
+  if (d_q_stratum) TRY(ensure_strata(c, n_rec * c->E));
+  TRY(launch_classify(c, d_qidx, d_sidx, n_rec, nullptr, n_rec, 0, n_rec,
+                      d_q_sample, d_q_stratum, sample));
+  return WK_OK;
+}
+
+int wk_classify_chunk(wk_ctx *c, const int32_t *qidx, const int32_t *sidx,
+                      int64_t n_rec, const int32_t *q_sample,
+                      const int32_t *q_stratum, int64_t n_qry, int32_t sample) {
+  TRY(check_plan_ready(c, q_stratum != nullptr));
+  TRY(use_device(c));
+  if (n_rec < 0 || (n_rec && (!qidx || !sidx)))
+    return fail(WK_ERR_ARG, "bad record columns");
+  if (!q_sample && (sample < 0 || sample >= c->S))
+    return fail(WK_ERR_ARG, "sample %d out of range", sample);
+  if (n_rec == 0) return WK_OK;
+  if (q_stratum) TRY(ensure_strata(c, n_rec * c->E));
+  TRY(c->dq.reserve((size_t)n_rec * 4 + 64));
+  TRY(c->ds.reserve((size_t)n_rec * 4 + 64));
+  const int32_t *dqs, *dqt;
+  TRY(upload_per_query(c, q_sample, q_stratum, n_qry, &dqs, &dqt));
+  // H2D in sub-chunks on the copy stream; the kernel for sub-chunk j needs
+  // sub-chunk j+1 resident (a query may straddle the boundary), so it waits
+  // on copy j+1 while copy j+2 is already in flight.
+  const int64_t SUB = 8ll << 20;
+  const int64_t nsub = (n_rec + SUB - 1) / SUB;
+  CK(cudaEventRecord(c->ev_free, c->stream));
+  CK(cudaStreamWaitEvent(c->copy_stream, c->ev_free, 0));
+  std::vector<cudaEvent_t> evs((size_t)nsub);
+  for (int64_t j = 0; j < nsub; ++j) {
+    int64_t a = j * SUB, b = std::min(n_rec, a + SUB);
+    CK(cudaMemcpyAsync(c->dq.as<int32_t>() + a, qidx + a, (size_t)(b - a) * 4,
+                       cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaMemcpyAsync(c->ds.as<int32_t>() + a, sidx + a, (size_t)(b - a) * 4,
+                       cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaEventCreateWithFlags(&evs[j], cudaEventDisableTiming));
+    CK(cudaEventRecord(evs[j], c->copy_stream));
+  }
+  int rc = WK_OK;
+  for (int64_t j = 0; j < nsub && rc == WK_OK; ++j) {
+    int64_t a = j * SUB, b = std::min(n_rec, a + SUB);
+    int64_t jn = std::min(nsub - 1, j + 1);
+    int64_t nread = std::min(n_rec, (jn + 1) * SUB);
+    cudaStreamWaitEvent(c->stream, evs[jn], 0);
+    rc = launch_classify(c, c->dq.as<int32_t>(), c->ds.as<int32_t>(), nread,
+                         nullptr, n_rec, a, b, dqs, dqt, sample);
+  }
+  int rc2 = rc == WK_OK ? check_device_err(c) : rc;
+  cudaStreamSynchronize(c->copy_stream);
+  for (auto &e : evs)
+    if (e) cudaEventDestroy(e);
+  return rc2;
+}
+
+// ---- ordinal ------------------------------------------------------------------
+int wk_ordinal_set_genes(wk_ctx *c, const int64_t *contig_off,
+                         const int32_t *gbeg, const int32_t *gend,
+                         const int32_t *gene_subject, int32_t n_contigs,
+                         int64_t n_genes) {
+  if (!c) return fail(WK_ERR_ARG, "ctx is NULL");
+  TRY(use_device(c));
+  if (n_contigs < 0 || n_genes < 0 || n_genes >= (1ll << 31) || !contig_off)
+    return fail(WK_ERR_ARG, "bad gene table arguments");
+  if (n_genes && (!gbeg || !gend || !gene_subject))
+    return fail(WK_ERR_ARG, "gene columns are NULL");
+  if (contig_off[0] != 0 || contig_off[n_contigs] != n_genes)
+    return fail(WK_ERR_ARG, "contig_off must span [0, n_genes]");
+  // bin width from the mean gene spacing
+  std::vector<int32_t> pmax((size_t)n_genes);
+  double total_span = 0;
+  for (int32_t ci = 0; ci < n_contigs; ++ci) {
+    int64_t a = contig_off[ci], b = contig_off[ci + 1];
+    if (b < a) return fail(WK_ERR_ARG, "contig_off is not monotone");
+    int32_t m = INT32_MIN;
+    for (int64_t g = a; g < b; ++g) {
+      if (g > a && gbeg[g] < gbeg[g - 1])
+        return fail(WK_ERR_ARG, "genes of contig %d are not sorted by start", ci);
+      if (gend[g] < gbeg[g])
+        return fail(WK_ERR_ARG, "gene %lld has end < start", (long long)g);
+      m = std::max(m, gend[g]);
+      pmax[g] = m;
+    }
+    if (b > a) total_span += std::max(m, 0);
+  }
+  double spacing = n_genes ? total_span / (double)n_genes : 1024.0;
+  int shift = 4;
+  while (shift < 24 && (double)(2ll << shift) <= spacing) ++shift;
+  std::vector<int64_t> bin_off((size_t)n_contigs + 1, 0);
+  for (int32_t ci = 0; ci < n_contigs; ++ci) {
+    int64_t a = contig_off[ci], b = contig_off[ci + 1];
+    int64_t nb = 0;
+    if (b > a && pmax[b - 1] >= 0) nb = ((int64_t)pmax[b - 1] >> shift) + 1;
+    bin_off[ci + 1] = bin_off[ci] + nb;
+  }
+  int64_t nbins = bin_off[n_contigs];
+  if (nbins >= (1ll << 31)) return fail(WK_ERR_ARG, "too many coordinate bins");
+  std::vector<int32_t> bin_first((size_t)std::max<int64_t>(nbins, 1));
+  for (int32_t ci = 0; ci < n_contigs; ++ci) {
+    int64_t a = contig_off[ci], b = contig_off[ci + 1];
+    int64_t nb = bin_off[ci + 1] - bin_off[ci];
+    int64_t g = a;
+    for (int64_t k = 0; k < nb; ++k) {
+      int64_t lo = k << shift;
+      while (g < b && (int64_t)pmax[g] < lo) ++g;
+      bin_first[bin_off[ci] + k] = (int32_t)g;
+    }
+  }
+  std::vector<int2> genes((size_t)std::max<int64_t>(n_genes, 1));
+  for (int64_t g = 0; g < n_genes; ++g) genes[g] = make_int2(gbeg[g], gend[g]);
+
+  CK(cudaStreamSynchronize(c->stream));
+  TRY(c->contig_off.reserve(((size_t)n_contigs + 1) * 8));
+  TRY(c->bin_off.reserve(((size_t)n_contigs + 1) * 8));
+  TRY(c->genes.reserve(genes.size() * 8));
+  TRY(c->gene_subject.reserve((size_t)std::max<int64_t>(n_genes, 1) * 4));
+  TRY(c->bin_first.reserve(bin_first.size() * 4));
+  CK(cudaMemcpy(c->contig_off.p, contig_off, ((size_t)n_contigs + 1) * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->bin_off.p, bin_off.data(), ((size_t)n_contigs + 1) * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->genes.p, genes.data(), (size_t)n_genes * 8, cudaMemcpyHostToDevice));
+  if (n_genes)
+    CK(cudaMemcpy(c->gene_subject.p, gene_subject, (size_t)n_genes * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->bin_first.p, bin_first.data(), (size_t)nbins * 4, cudaMemcpyHostToDevice));
+  c->C = n_contigs;
+  c->G = n_genes;
+  c->shift = shift;
+  return WK_OK;
+}
+
+static int run_ordinal(wk_ctx *c, const int32_t *dq, const int32_t *dcontig,
+                       const int32_t *dbeg, const int32_t *dend,
+                       const int32_t *dlen, int64_t n_rec, double th,
+                       const int32_t *dqs, const int32_t *dqt, int32_t sample,
+                       bool classify) {
+  if (((uintptr_t)dq | (uintptr_t)dcontig | (uintptr_t)dbeg | (uintptr_t)dend |
+       (uintptr_t)dlen) & 15)
+    return fail(WK_ERR_ARG, "record columns must be 16-byte aligned");
+  const int64_t n_tiles = (n_rec + ORD_TILE - 1) / ORD_TILE;
+  if (c->pair_cap < n_rec + 1024) {
+    c->pair_cap = n_rec + (n_rec >> 2) + 1024;
+  }
+  for (int attempt = 0; attempt < 6; ++attempt) {
+    TRY(c->pair_q.reserve((size_t)c->pair_cap * 4 + 64));
+    TRY(c->pair_s.reserve((size_t)c->pair_cap * 4 + 64));
+    if (c->keep_pairs) {
+      TRY(c->pair_r.reserve((size_t)c->pair_cap * 4));
+      TRY(c->pair_g.reserve((size_t)c->pair_cap * 4));
+    }
+    TRY(c->tile_desc.reserve((size_t)n_tiles * 8));
+    TRY(c->ticket.reserve(16));
+    CK(cudaMemsetAsync(c->tile_desc.p, 0, (size_t)n_tiles * 8, c->stream));
+    CK(cudaMemsetAsync(c->ticket.p, 0, 16, c->stream));
+    CK(cudaMemsetAsync(c->d_n_pairs(), 0, 8, c->stream));
+    OrdParams P;
+    memset(&P, 0, sizeof P);
+    P.q = dq;
+    P.contig = dcontig;
+    P.beg = dbeg;
+    P.end = dend;
+    P.len = dlen;
+    P.n = n_rec;
+    P.th = th;
+    P.contig_off = c->contig_off.as<int64_t>();
+    P.genes = c->genes.as<int2>();
+    P.gene_subject = c->gene_subject.as<int32_t>();
+    P.bin_off = c->bin_off.as<int64_t>();
+    P.bin_first = c->bin_first.as<int32_t>();
+    P.shift = c->shift;
+    P.C = c->C;
+    P.pair_q = c->pair_q.as<int32_t>();
+    P.pair_s = c->pair_s.as<int32_t>();
+    P.pair_r = c->keep_pairs ? c->pair_r.as<int32_t>() : nullptr;
+    P.pair_g = c->keep_pairs ? c->pair_g.as<int32_t>() : nullptr;
+    P.cap = c->pair_cap;
+    P.n_pairs = c->d_n_pairs();
+    P.tile_desc = c->tile_desc.as<ull>();
+    P.ticket = c->ticket.as<unsigned>();
+    P.err = c->d_err();
+    ordinal_match_kernel<<<(unsigned)n_tiles, ORD_NT, 0, c->stream>>>(P);
+    c->launches++;
+    CK(cudaGetLastError());
+    if (classify)
+      TRY(launch_classify(c, c->pair_q.as<int32_t>(), c->pair_s.as<int32_t>(),
+                          0, c->d_n_pairs(), c->pair_cap, 0, 0, dqs, dqt,
+                          sample));
+    // the pair count decides whether the buffers were large enough
+    ull np = 0;
+    int32_t err = 0;
+    CK(cudaMemcpyAsync(&np, c->d_n_pairs(), 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&err, c->d_err(), 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->last_pairs = (int64_t)np;
+    if (!(err & ERR_PAIR_FULL)) return check_device_err(c);
+    // too small: nothing was counted (classify_kernel returns early); retry
+    CK(cudaMemsetAsync(c->d_err(), 0, 4, c->stream));
+    c->pair_cap = (int64_t)np + (int64_t)(np >> 3) + 1024;
+  }
+  return fail(WK_ERR_CAPACITY, "read-gene pair buffer could not be sized");
+}
+
+int wk_ordinal_device(wk_ctx *c, const int32_t *d_qidx, const int32_t *d_contig,
+                      const int32_t *d_beg, const int32_t *d_end,
+                      const int32_t *d_len, int64_t n_rec, double th,
+                      const int32_t *d_q_sample, const int32_t *d_q_stratum,
+                      int64_t n_qry, int32_t sample) {
+  (void)n_qry;
+  TRY(check_plan_ready(c, d_q_stratum != nullptr));
+  TRY(use_device(c));
+  if (!c->C && !c->G) return fail(WK_ERR_STATE, "wk_ordinal_set_genes has not been called");
+  if (n_rec < 0) return fail(WK_ERR_ARG, "n_rec < 0");
+  if (!d_q_sample && (sample < 0 || sample >= c->S))
+    return fail(WK_ERR_ARG, "sample %d out of range", sample);
+  if (n_rec == 0) return WK_OK;
+  if (d_q_stratum) TRY(ensure_strata(c, 4 * n_rec * c->E));
+  return run_ordinal(c, d_qidx, d_contig, d_beg, d_end, d_len, n_rec, th,
+                     d_q_sample, d_q_stratum, sample, true);
+}
+
+int wk_ordinal_chunk(wk_ctx *c, const int32_t *qidx, const int32_t *contig,
+                     const int32_t *beg, const int32_t *end, const int32_t *len,
+                     int64_t n_rec, double th, const int32_t *q_sample,
+                     const int32_t *q_stratum, int64_t n_qry, int32_t sample) {
+  if (!c) return fail(WK_ERR_ARG, "ctx is NULL");
+  TRY(use_device(c));
+  if (!c->C && !c->G) return fail(WK_ERR_STATE, "wk_ordinal_set_genes has not been called");
+  const bool classify = c->have_plan;
+  if (classify) TRY(check_plan_ready(c, q_stratum != nullptr));
+  if (n_rec < 0 || (n_rec && (!qidx || !contig || !beg || !end || !len)))
+    return fail(WK_ERR_ARG, "bad record columns");
+  if (classify && !q_sample && (sample < 0 || sample >= c->S))
+    return fail(WK_ERR_ARG, "sample %d out of range", sample);
+  c->last_pairs = 0;
+  if (n_rec == 0) return WK_OK;
+  if (classify && q_stratum) TRY(ensure_strata(c, 4 * n_rec * c->E));
+  DevBuf *bufs[5] = {&c->dq, &c->dcontig, &c->dbeg, &c->dend, &c->dlen};
+  const int32_t *src[5] = {qidx, contig, beg, end, len};
+  for (int i = 0; i < 5; ++i) {
+    TRY(bufs[i]->reserve((size_t)n_rec * 4 + 64));
+    CK(cudaMemcpyAsync(bufs[i]->p, src[i], (size_t)n_rec * 4,
+                       cudaMemcpyHostToDevice, c->stream));
+  }
+  const int32_t *dqs = nullptr, *dqt = nullptr;
+  if (classify) TRY(upload_per_query(c, q_sample, q_stratum, n_qry, &dqs, &dqt));
+  return run_ordinal(c, c->dq.as<int32_t>(), c->dcontig.as<int32_t>(),
+                     c->dbeg.as<int32_t>(), c->dend.as<int32_t>(),
+                     c->dlen.as<int32_t>(), n_rec, th, dqs, dqt, sample,
+                     classify);
+}
+
+int wk_ordinal_fetch_pairs(wk_ctx *c, int64_t *n_pairs, int32_t *read_idx,
+                           int32_t *gene_idx, int64_t cap) {
+  if (!c || !n_pairs) return fail(WK_ERR_ARG, "bad arguments");
+  TRY(use_device(c));
+  if (!read_idx || !gene_idx) {
+    // enable pair recording for subsequent chunks and report the last count
+    c->keep_pairs = true;
+    *n_pairs = c->last_pairs;
+    return WK_OK;
+  }
+  if (!c->keep_pairs || !c->pair_r.p)
+    return fail(WK_ERR_STATE, "pair recording was not enabled before the chunk");
+  if (cap < c->last_pairs) return fail(WK_ERR_CAPACITY, "pair output too small");
+  CK(cudaMemcpy(read_idx, c->pair_r.p, (size_t)c->last_pairs * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(gene_idx, c->pair_g.p, (size_t)c->last_pairs * 4, cudaMemcpyDeviceToHost));
+  *n_pairs = c->last_pairs;
+  return WK_OK;
+}
+
+// ---- results ---------------------------------------------------------------------
+int wk_fetch_counts(wk_ctx *c, int64_t *units) {
+  if (!c || !c->have_plan) return fail(WK_ERR_STATE, "no plan set");
+  if (!units) return fail(WK_ERR_ARG, "units is NULL");
+  TRY(use_device(c));
+  size_t len = (size_t)c->E * c->S * (c->NF + 1);
+  CK(cudaMemcpyAsync(units, c->cnt.p, len * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return WK_OK;
+}
+
+int wk_fetch_overflow(wk_ctx *c, int64_t *n, int64_t *cell, int32_t *den,
+                      int64_t cap) {
+  if (!c || !n) return fail(WK_ERR_ARG, "bad arguments");
+  TRY(use_device(c));
+  ull cnt = 0;
+  CK(cudaMemcpyAsync(&cnt, c->d_ovf_n(), 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *n = (int64_t)cnt;
+  if (!cell || !den) return WK_OK;
+  if (cap < (int64_t)cnt) return fail(WK_ERR_CAPACITY, "overflow output too small");
+  if (cnt) {
+    CK(cudaMemcpy(cell, c->ovf_key.p, cnt * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(den, c->ovf_den.p, cnt * 4, cudaMemcpyDeviceToHost));
+  }
+  return WK_OK;
+}
+
+int wk_fetch_strata(wk_ctx *c, int64_t *n, int32_t *entry, int32_t *sample,
+                    int32_t *stratum, int64_t *feature, int64_t *units,
+                    int64_t cap) {
+  if (!c || !n) return fail(WK_ERR_ARG, "bad arguments");
+  if (!c->have_plan) return fail(WK_ERR_STATE, "no plan set");
+  TRY(use_device(c));
+  ull used = 0;
+  if (c->sh_cap) {
+    CK(cudaMemcpyAsync(&used, c->d_sh_used(), 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  *n = (int64_t)used;
+  if (!entry) return WK_OK;
+  if (!sample || !stratum || !feature || !units)
+    return fail(WK_ERR_ARG, "output arrays are NULL");
+  if (cap < (int64_t)used) return fail(WK_ERR_CAPACITY, "strata output too small");
+  if (!used) return WK_OK;
+  DevBuf ok, ov;
+  TRY(ok.reserve(used * 8));
+  TRY(ov.reserve(used * 8));
+  CK(cudaMemsetAsync(c->d_cursor(), 0, 8, c->stream));
+  int grid = (int)std::min<uint64_t>((c->sh_cap + 255) / 256, (uint64_t)c->sm_count * 8);
+  compact_hash_kernel<<<grid, 256, 0, c->stream>>>(
+      c->sh_keys.as<ull>(), c->sh_vals.as<ull>(), c->sh_cap, ok.as<ull>(),
+      ov.as<ull>(), c->d_cursor());
+  c->launches++;
+  CK(cudaGetLastError());
+  std::vector<ull> hk(used), hv(used);
+  CK(cudaMemcpyAsync(hk.data(), ok.p, used * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(hv.data(), ov.p, used * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  ok.release();
+  ov.release();
+  const int64_t NF1 = c->NF + 1;
+  for (ull i = 0; i < used; ++i) {
+    ull key = hk[i];
+    int64_t cellv = (int64_t)(key & ((1ull << 40) - 1));
+    stratum[i] = (int32_t)(key >> 40);
+    feature[i] = cellv % NF1;
+    int64_t es = cellv / NF1;
+    sample[i] = (int32_t)(es % c->S);
+    entry[i] = (int32_t)(es / c->S);
+    units[i] = (int64_t)hv[i];
+  }
+  return WK_OK;
+}
+
+int wk_counts_device(wk_ctx *c, void **d_ptr, int64_t *n_elems) {
+  if (!c || !c->have_plan) return fail(WK_ERR_STATE, "no plan set");
+  if (!d_ptr || !n_elems) return fail(WK_ERR_ARG, "bad arguments");
+  *d_ptr = c->cnt.p;
+  *n_elems = (int64_t)c->E * c->S * (c->NF + 1);
+  return WK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,664 @@
+// wk_classify.cuh — persistent classify+count kernel for sm_100a.
+//
+// What it replaces (reference, /root/reference/woltka/):
+//   workflow.py:316-335  per-chunk loop: for sample → for rank → assign_readmap
+//   workflow.py:1017-1058 assign_readmap: assigner per query + counter + sum_dict
+//   classify.py:32-127   assign_none / assign_free / assign_rank
+//   classify.py:300-317  majority            tree.py:513-566 find_lca
+//   classify.py:144-171  counter             classify.py:216-249 counter_strat
+//
+// Shape of the kernel
+//   * grid = one persistent CTA per SM; each CTA walks tiles of TILE records.
+//   * the two int32 columns (query idx, subject idx) of a tile are brought to
+//     shared memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier
+//     complete_tx), STAGES deep, issued by one thread — no LSU work, no
+//     registers, 16-byte aligned sources.
+//   * the per-subject lookup tables (find_rank results etc.) are staged once
+//     per CTA into shared memory as uint16 by the same bulk-copy engine when
+//     they fit; otherwise they are read through L1/L2 as int32.
+//   * one lane = one alignment record.  A warp owns TILE/NW consecutive
+//     records of the tile and advances over them in 32-record windows that
+//     start at a query head and only consume whole queries; all per-query
+//     logic (set-dedup of subjects, all-equal test, majority, 1/k split, LCA)
+//     is warp ballots / match.any / shuffles over the query's lane segment.
+//   * counts go to a per-CTA shared-memory write-back cache (tag + 32-bit low
+//     word, carry propagated to the global table) and only cold or conflicting
+//     cells become global 64-bit reductions; the cache is flushed once per CTA.
+//   * queries longer than a window take a warp-cooperative slow path that
+//     reads global memory directly (any length).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/woltka_b200.h"
+
+namespace wk {
+
+typedef unsigned long long ull;
+
+constexpr int CLS_TILE = 4096;                 // records per tile
+constexpr int CLS_PRE = 4;                     // records staged before the tile
+constexpr int CLS_POST = 44;                   // halo after the tile (>= 33)
+constexpr int CLS_TBUF = CLS_TILE + CLS_PRE + CLS_POST;  // 4144 rec, 16 B multiple
+constexpr int CLS_STAGES = 3;
+constexpr int CLS_NT = 1024;                   // threads per CTA
+constexpr int CLS_NW = CLS_NT / 32;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr uint32_t CACHE_EMPTY = 0xffffffffu;
+constexpr int DUPMARK = INT32_MIN;
+
+struct ClsParams {
+  const int32_t *q, *s;       // record columns (device)
+  int64_t n;                  // records readable in q/s
+  const ull *n_dev;           // if non-null: n = r1 = *n_dev (ordinal pairs)
+  int64_t r0, r1;             // queries whose head lies in [r0, r1) are ours
+  const int32_t *q_sample, *q_stratum;  // per query (indexed by q) or null
+  int32_t sample;
+  int32_t E;
+  int32_t kind[WK_MAX_ENTRIES];
+  uint32_t flags;
+  double major_th;
+  const int32_t *tab;         // [E][V] int32
+  const uint16_t *tab16;      // [E][Vp] uint16 (0xFFFF = none) or null
+  int64_t V;
+  int32_t Vp;
+  const int32_t *sub_node;    // [V] or null
+  const int32_t *parent;      // [T] or null
+  int32_t root;               // -1 = no root given (root=None)
+  ull *cnt;                   // [E][S][NF1] units
+  int64_t NF1;
+  int32_t S;
+  ull *ovf_n;                 // overflow list cursor
+  int64_t *ovf_key;
+  int32_t *ovf_den;
+  int64_t ovf_cap;
+  ull *sh_keys, *sh_vals;     // strata hash (open addressing)
+  uint64_t sh_mask;
+  ull *sh_used;
+  int32_t *err;               // device error word (bit flags)
+  int32_t *scratch;           // [>= n] long-query scratch
+  int32_t cache_log;          // log2(cache slots), 0 = no cache
+};
+
+enum { ERR_BAD_SUBJECT = 1, ERR_OVF_FULL = 2, ERR_HASH_FULL = 4,
+       ERR_PAIR_FULL = 8 };
+
+__constant__ uint32_t c_units[33] = {
+    0,      720720, 360360, 240240, 180180, 144144, 120120, 102960, 90090,
+    80080,  72072,  65520,  60060,  55440,  51480,  48048,  45045,  0,
+    40040,  0,      36036,  34320,  32760,  0,      30030,  0,      27720,
+    0,      25740,  0,      24024,  0,      0};
+
+__device__ __forceinline__ unsigned lowmask(int n) {
+  return n >= 32 ? FULL : ((1u << n) - 1u);
+}
+
+// ---- mbarrier / TMA bulk copy (PTX) ------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(void *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, uint32_t bytes) {
+  asm volatile(
+      "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WK_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra WK_DONE;\n"
+      "bra WK_WAIT;\n"
+      "WK_DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src,
+                                         uint32_t bytes, void *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---- count sinks --------------------------------------------------------
+struct Cache {
+  uint32_t *tag, *lo;
+  int log2n;
+};
+
+__device__ __forceinline__ void strat_add(const ClsParams &P, ull key,
+                                          ull units) {
+  ull h = key * 0x9E3779B97F4A7C15ull;
+  h ^= h >> 29;
+  uint64_t i = h & P.sh_mask;
+  for (uint64_t probe = 0; probe <= P.sh_mask; ++probe) {
+    ull k0 = P.sh_keys[i];
+    if (k0 == ~0ull) {
+      k0 = atomicCAS(&P.sh_keys[i], ~0ull, key);
+      if (k0 == ~0ull) {
+        atomicAdd(P.sh_used, 1ull);
+        k0 = key;
+      }
+    }
+    if (k0 == key) {
+      atomicAdd(&P.sh_vals[i], units);
+      return;
+    }
+    i = (i + 1) & P.sh_mask;
+  }
+  atomicOr(P.err, ERR_HASH_FULL);
+}
+
+__device__ __forceinline__ void emit_units(const ClsParams &P, const Cache &C,
+                                           int e, int samp, int strat,
+                                           int64_t f, uint32_t units) {
+  int64_t cell = ((int64_t)e * P.S + samp) * P.NF1 + f;
+  if (P.q_stratum) {
+    strat_add(P, ((ull)(uint32_t)strat << 40) | (ull)cell, units);
+    return;
+  }
+  if (C.log2n) {
+    uint32_t key = (uint32_t)cell;
+    uint32_t h = (key * 2654435761u) >> (32 - C.log2n);
+    uint32_t tag = C.tag[h];
+    if (tag == CACHE_EMPTY) {
+      uint32_t old = atomicCAS(&C.tag[h], CACHE_EMPTY, key);
+      tag = (old == CACHE_EMPTY) ? key : old;
+    }
+    if (tag == key) {
+      uint32_t old = atomicAdd(&C.lo[h], units);
+      if (old + units < old) atomicAdd(&P.cnt[cell], 1ull << 32);
+      return;
+    }
+  }
+  atomicAdd(&P.cnt[cell], (ull)units);
+}
+
+// one 1/d share (classify.py:168-170)
+__device__ __forceinline__ void emit_frac(const ClsParams &P, const Cache &C,
+                                          int e, int samp, int strat,
+                                          int64_t f, int64_t d) {
+  uint32_t u = d <= 32 ? c_units[d]
+                       : (uint32_t)((WK_UNITS % d) == 0 ? WK_UNITS / d : 0);
+  if (u) {
+    emit_units(P, C, e, samp, strat, f, u);
+    return;
+  }
+  ull at = atomicAdd(P.ovf_n, 1ull);
+  if ((int64_t)at < P.ovf_cap) {
+    int64_t cell = ((int64_t)e * P.S + samp) * P.NF1 + f;
+    P.ovf_key[at] =
+        P.q_stratum ? (int64_t)(((ull)(uint32_t)strat << 40) | (ull)cell) : cell;
+    P.ovf_den[at] = (int32_t)d;
+  } else {
+    atomicOr(P.err, ERR_OVF_FULL);
+  }
+}
+
+// ---- tree ---------------------------------------------------------------
+// LCA of two nodes on a topologically numbered tree (parent[i] < i): lifting
+// the larger index can never step over the LCA.  Same result as
+// tree.find_lca (tree.py:513-566) on a single-rooted tree.
+__device__ __forceinline__ int lca2(const int32_t *__restrict__ parent, int a,
+                                    int b) {
+  while (a != b) {
+    if (a > b)
+      a = __ldg(parent + a);
+    else
+      b = __ldg(parent + b);
+  }
+  return a;
+}
+
+template <bool STAGED>
+__device__ __forceinline__ int tab_get(const ClsParams &P,
+                                       const uint16_t *stab, int e, int s) {
+  if (STAGED) {
+    unsigned v = stab[e * P.Vp + s];
+    return v == 0xFFFFu ? -1 : (int)v;
+  } else {
+    return __ldg(P.tab + (int64_t)e * P.V + s);
+  }
+}
+
+// LCA over the non-duplicate members of each lane segment; result valid at
+// head lanes with need == true.  All lanes must call.
+__device__ __forceinline__ int warp_seg_lca(const int32_t *parent, int v,
+                                            unsigned segnd, int se, bool need,
+                                            int lane) {
+  int maxlen = __reduce_max_sync(FULL, need ? (se - lane) : 0);
+  int acc = v;
+  for (int m = 1; m < maxlen; ++m) {
+    int o = __shfl_down_sync(FULL, v, m);
+    if (need && lane + m < se && ((segnd >> (lane + m)) & 1u))
+      acc = lca2(parent, acc, o);
+  }
+  return acc;
+}
+
+__device__ __forceinline__ int warp_sum(int v) {
+  return __reduce_add_sync(FULL, v);
+}
+
+// ---- slow path: one query of any length, whole warp, global memory -------
+template <bool STAGED>
+__device__ int64_t process_long(const ClsParams &P, const Cache &C,
+                                const uint16_t *stab, int64_t n,
+                                int64_t start, int lane) {
+  const int32_t *gq = P.q, *gs = P.s;
+  const int qid = gq[start];
+  int64_t end = start + 1;
+  for (;;) {
+    int64_t i = end + lane;
+    bool brk = (i >= n) || (gq[i] != qid);
+    unsigned m = __ballot_sync(FULL, brk);
+    if (m) {
+      end += __ffs(m) - 1;
+      break;
+    }
+    end += 32;
+  }
+  int samp = P.q_sample ? P.q_sample[qid] : P.sample;
+  int strat = P.q_stratum ? P.q_stratum[qid] : 0;
+  if (strat < 0 || (unsigned)samp >= (unsigned)P.S) return end;
+
+  // set semantics of the subject pool (align.py:339): mark repeats
+  int kloc = 0;
+  for (int64_t j = start + lane; j < end; j += 32) {
+    int sj = gs[j];
+    bool dup = false;
+    if ((unsigned)sj >= (uint64_t)P.V) {
+      atomicOr(P.err, ERR_BAD_SUBJECT);
+      dup = true;
+    }
+    for (int64_t j2 = start; j2 < j && !dup; ++j2) dup = (gs[j2] == sj);
+    __stcg(P.scratch + j, dup ? DUPMARK : 0);
+    kloc += !dup;
+  }
+  const int k = warp_sum(kloc);
+  __syncwarp();
+  const int s0 = gs[start];
+  const int64_t NF = P.NF1 - 1;
+  const bool unas = P.flags & WK_F_UNASSIGNED;
+
+  for (int e = 0; e < P.E; ++e) {
+    const int kind = P.kind[e];
+    int result = -1;
+    bool uniqres = true;
+    if (kind == WK_KIND_NONE || kind == WK_KIND_NONE_ID) {
+      if (k == 1) {
+        result = kind == WK_KIND_NONE_ID ? s0 : tab_get<STAGED>(P, stab, e, s0);
+      } else if (P.flags & WK_F_UNIQ) {
+        result = -1;
+      } else {
+        uniqres = false;
+        for (int64_t j = start + lane; j < end; j += 32) {
+          if (__ldcg(P.scratch + j) == DUPMARK) continue;
+          int sj = gs[j];
+          int f = kind == WK_KIND_NONE_ID ? sj : tab_get<STAGED>(P, stab, e, sj);
+          emit_frac(P, C, e, samp, strat, f, k);
+        }
+      }
+    } else {
+      const bool is_free = kind == WK_KIND_FREE;
+      if (is_free && k == 1) {
+        result = tab_get<STAGED>(P, stab, e, s0);
+      } else {
+        // per-record value: rank-level ancestor, or the node itself (free)
+        const int t0 = is_free ? P.sub_node[s0] : tab_get<STAGED>(P, stab, e, s0);
+        int neq = 0, nvalid = 0, nneg = 0;
+        for (int64_t j = start + lane; j < end; j += 32) {
+          if (__ldcg(P.scratch + j) == DUPMARK) continue;
+          int sj = gs[j];
+          int t = is_free ? P.sub_node[sj] : tab_get<STAGED>(P, stab, e, sj);
+          __stcg(P.scratch + j, t);
+          neq |= (t != t0);
+          nvalid += (t >= 0);
+          nneg += (t < 0);
+        }
+        neq = __any_sync(FULL, neq);
+        nvalid = warp_sum(nvalid);
+        nneg = warp_sum(nneg);
+        __syncwarp();
+        if (!is_free && !neq) {
+          result = t0;
+        } else if (!is_free && (P.flags & WK_F_MAJOR)) {
+          // majority (classify.py:300-317): top count, first seen wins ties
+          int bc = 0;
+          int64_t bj = end;
+          for (int64_t j = start + lane; j < end; j += 32) {
+            int t = __ldcg(P.scratch + j);
+            if (t == DUPMARK) continue;
+            int c = 0;
+            for (int64_t j2 = start; j2 < end; ++j2)
+              c += (__ldcg(P.scratch + j2) == t);
+            if (c > bc || (c == bc && j < bj)) {
+              bc = c;
+              bj = j;
+            }
+          }
+          for (int off = 16; off; off >>= 1) {
+            int oc = __shfl_xor_sync(FULL, bc, off);
+            int64_t oj = __shfl_xor_sync(FULL, bj, off);
+            if (oc > bc || (oc == bc && oj < bj)) {
+              bc = oc;
+              bj = oj;
+            }
+          }
+          int tw = __ldcg(P.scratch + bj);
+          result = ((double)bc >= __dmul_rn((double)k, P.major_th)) ? tw : -1;
+        } else if (is_free || (P.flags & WK_F_ABOVE)) {
+          if (nneg) {
+            result = -1;
+          } else {
+            int acc = -2;
+            for (int64_t j = start + lane; j < end; j += 32) {
+              int t = __ldcg(P.scratch + j);
+              if (t == DUPMARK) continue;
+              acc = acc == -2 ? t : lca2(P.parent, acc, t);
+            }
+            for (int off = 16; off; off >>= 1) {
+              int o = __shfl_xor_sync(FULL, acc, off);
+              if (acc == -2)
+                acc = o;
+              else if (o != -2)
+                acc = lca2(P.parent, acc, o);
+            }
+            result = acc == P.root ? -1 : acc;
+          }
+        } else if (P.flags & WK_F_UNIQ) {
+          result = -1;
+        } else {
+          uniqres = false;
+          for (int64_t j = start + lane; j < end; j += 32) {
+            int t = __ldcg(P.scratch + j);
+            if (t == DUPMARK || t < 0) continue;
+            emit_frac(P, C, e, samp, strat, t, nvalid);
+          }
+        }
+        // restore dup marks for the next entry
+        __syncwarp();
+        for (int64_t j = start + lane; j < end; j += 32)
+          if (__ldcg(P.scratch + j) != DUPMARK) __stcg(P.scratch + j, 0);
+        __syncwarp();
+      }
+    }
+    if (lane == 0 && uniqres) {
+      if (result >= 0)
+        emit_units(P, C, e, samp, strat, result, (uint32_t)WK_UNITS);
+      else if (unas)
+        emit_units(P, C, e, samp, strat, NF, (uint32_t)WK_UNITS);
+    }
+  }
+  return end;
+}
+
+// ---- the kernel -----------------------------------------------------------
+struct ClsSmemLayout {
+  uint32_t bars, tiles, ctag, clo, tab, total;
+};
+__host__ __device__ inline ClsSmemLayout cls_layout(int cache_log,
+                                                    int64_t tab_bytes) {
+  ClsSmemLayout L;
+  L.bars = 0;
+  L.tiles = 128;
+  L.ctag = L.tiles + CLS_STAGES * 2 * CLS_TBUF * 4;
+  uint32_t slots = cache_log ? (1u << cache_log) : 0;
+  L.clo = L.ctag + slots * 4;
+  L.tab = (L.clo + slots * 4 + 127) & ~127u;
+  L.total = L.tab + (uint32_t)((tab_bytes + 15) & ~15ll);
+  return L;
+}
+
+template <bool STAGED>
+__global__ void __launch_bounds__(CLS_NT, 1)
+    classify_kernel(const __grid_constant__ ClsParams P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t tab_bytes = STAGED ? (int64_t)P.E * P.Vp * 2 : 0;
+  const ClsSmemLayout L = cls_layout(P.cache_log, tab_bytes);
+  ull *bars = reinterpret_cast<ull *>(smem + L.bars);  // [STAGES] full, [STAGES] = tab
+  int32_t *tiles = reinterpret_cast<int32_t *>(smem + L.tiles);
+  Cache C;
+  C.tag = reinterpret_cast<uint32_t *>(smem + L.ctag);
+  C.lo = reinterpret_cast<uint32_t *>(smem + L.clo);
+  C.log2n = P.cache_log;
+  const uint16_t *stab = reinterpret_cast<const uint16_t *>(smem + L.tab);
+
+  int64_t n = P.n, r0 = P.r0, r1 = P.r1;
+  if (P.n_dev) {
+    n = (int64_t)*P.n_dev;
+    r0 = 0;
+    r1 = n;
+  }
+  if (*P.err & ERR_PAIR_FULL) return;  // upstream stage overflowed: do nothing
+  const int64_t tb0 = r0 & ~3ll;
+  const int64_t n_tiles = r1 > tb0 ? (r1 - tb0 + CLS_TILE - 1) / CLS_TILE : 0;
+
+  if (tid == 0) {
+    for (int i = 0; i <= CLS_STAGES; ++i) mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](int64_t tile, int stage) {
+    // stage records [tb-PRE, tb+TILE+POST) ∩ [0, n) of both columns
+    int64_t tb = tb0 + tile * CLS_TILE;
+    int64_t g0 = tb >= CLS_PRE ? tb - CLS_PRE : 0;
+    int64_t g1 = tb + CLS_TILE + CLS_POST;
+    if (g1 > n) g1 = n;
+    uint32_t bytes = (uint32_t)(((g1 - g0) * 4 + 15) & ~15ll);
+    int32_t *dq = tiles + (size_t)stage * 2 * CLS_TBUF + (g0 - (tb - CLS_PRE));
+    int32_t *ds = dq + CLS_TBUF;
+    mbar_expect_tx(&bars[stage], 2 * bytes);
+    bulk_g2s(dq, P.q + g0, bytes, &bars[stage]);
+    bulk_g2s(ds, P.s + g0, bytes, &bars[stage]);
+  };
+
+  if (tid == 0) {
+    if (STAGED) {
+      uint32_t bytes = (uint32_t)((tab_bytes + 15) & ~15ll);
+      mbar_expect_tx(&bars[CLS_STAGES], bytes);
+      bulk_g2s(const_cast<uint16_t *>(stab), P.tab16, bytes, &bars[CLS_STAGES]);
+    }
+    for (int st = 0; st < CLS_STAGES; ++st) {
+      int64_t tile = (int64_t)blockIdx.x + (int64_t)st * gridDim.x;
+      if (tile < n_tiles) issue(tile, st);
+    }
+  }
+  if (C.log2n) {
+    for (uint32_t h = tid; h < (1u << C.log2n); h += CLS_NT) {
+      C.tag[h] = CACHE_EMPTY;
+      C.lo[h] = 0;
+    }
+  }
+  __syncthreads();
+  if (STAGED) mbar_wait(&bars[CLS_STAGES], 0);
+
+  const int64_t NF = P.NF1 - 1;
+  const bool unas = P.flags & WK_F_UNASSIGNED;
+  const unsigned le = lowmask(lane + 1), lt = lowmask(lane);
+
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int stage = it % CLS_STAGES;
+    mbar_wait(&bars[stage], (it / CLS_STAGES) & 1);
+    const int64_t tb = tb0 + tile * CLS_TILE;
+    const int32_t *sq = tiles + (size_t)stage * 2 * CLS_TBUF;
+    const int32_t *ss = sq + CLS_TBUF;
+    const int64_t sbase = tb - CLS_PRE;  // global index of sq[0]
+
+    int64_t w0 = tb + (int64_t)warp * (CLS_TILE / CLS_NW);
+    int64_t w1 = w0 + CLS_TILE / CLS_NW;
+    if (w0 < r0) w0 = r0;
+    if (w1 > r1) w1 = r1;
+
+    int64_t cur = w0;
+    while (cur < w1) {
+      const int64_t i = cur + lane;
+      const bool inb = i < n;
+      const int qv = inb ? sq[i - sbase] : 0;
+      const int qp = (inb && i > 0) ? sq[i - 1 - sbase] : 0;
+      const bool head = inb && (i == 0 || qv != qp);
+      const unsigned heads = __ballot_sync(FULL, head);
+      if (heads == 0) {
+        cur += 32;
+        continue;
+      }
+      const int first = __ffs(heads) - 1;
+      const int lim = (int)(w1 - cur < 32 ? w1 - cur : 32);
+      if (first >= lim) break;
+      const int64_t nx = cur + 32;
+      const bool nh = nx >= n || sq[nx - sbase] != sq[nx - 1 - sbase];
+      const int nvalid = (int)(n - cur < 32 ? n - cur : 32);
+      const int cend = nh ? nvalid : 31 - __clz(heads);
+      const unsigned fh = lim < 32 ? (heads >> lim) : 0u;
+      int wend = cend;
+      if (fh) {
+        int p = lim + __ffs(fh) - 1;
+        wend = p < cend ? p : cend;
+      }
+      if (wend <= first) {
+        if (first > 0) {
+          cur += first;
+          continue;
+        }
+        cur = process_long<STAGED>(P, C, stab, n, cur, lane);
+        continue;
+      }
+
+      // ---- lanes [first, wend) hold whole queries ----
+      const bool act = lane >= first && lane < wend;
+      const unsigned actm = lowmask(wend) & ~lowmask(first);
+      int sv = act ? ss[i - sbase] : (-1 - lane);
+      if (act && (unsigned)sv >= (uint64_t)P.V) {
+        atomicOr(P.err, ERR_BAD_SUBJECT);
+        sv = -1 - lane;
+      }
+      const unsigned hm = heads & actm;
+      const int sl = act ? 31 - __clz(hm & le) : lane;
+      const unsigned ab = hm & ~le;
+      const int se = ab ? (__ffs(ab) - 1) : wend;
+      const unsigned segm = act ? (lowmask(se) & ~lowmask(sl)) : 0u;
+      const unsigned mm = __match_any_sync(FULL, sv);
+      const bool nd = act && sv >= 0 && !(mm & segm & lt);
+      const unsigned segnd = __ballot_sync(FULL, nd) & segm;
+      const int k = __popc(segnd);
+      const bool ishead = act && lane == sl;
+
+      int samp = P.sample, strat = 0;
+      if (P.q_sample || P.q_stratum) {
+        if (ishead) {
+          if (P.q_sample) samp = __ldg(P.q_sample + qv);
+          if (P.q_stratum) strat = __ldg(P.q_stratum + qv);
+        }
+        samp = __shfl_sync(FULL, samp, sl);
+        strat = __shfl_sync(FULL, strat, sl);
+      }
+      const bool live = act && strat >= 0 && (unsigned)samp < (unsigned)P.S;
+
+      for (int e = 0; e < P.E; ++e) {
+        const int kind = P.kind[e];
+        int result = -1;
+        bool uniqres = true;
+        if (kind == WK_KIND_NONE || kind == WK_KIND_NONE_ID) {
+          // classify.assign_none (classify.py:32-51)
+          const int f = !nd ? -1
+                            : (kind == WK_KIND_NONE_ID
+                                   ? sv
+                                   : tab_get<STAGED>(P, stab, e, sv));
+          if (k == 1) {
+            result = f;
+          } else if (!(P.flags & WK_F_UNIQ)) {
+            uniqres = false;
+            if (live && nd) emit_frac(P, C, e, samp, strat, f, k);
+          }
+        } else if (kind == WK_KIND_RANK) {
+          // classify.assign_rank (classify.py:81-127)
+          const int t = nd ? tab_get<STAGED>(P, stab, e, sv) : -1;
+          const int th = __shfl_sync(FULL, t, sl);
+          const unsigned neq = __ballot_sync(FULL, nd && t != th);
+          const bool alleq = (neq & segm) == 0;
+          result = th;
+          if (__any_sync(FULL, act && !alleq)) {
+            if (P.flags & WK_F_MAJOR) {
+              const unsigned tm = __match_any_sync(FULL, nd ? t : (-2 - lane));
+              const int c = nd ? __popc(tm & segnd) : 0;
+              int mx = c;
+#pragma unroll
+              for (int off = 1; off < 32; off <<= 1) {
+                int o = __shfl_down_sync(FULL, mx, off);
+                if (lane + off < se && o > mx) mx = o;
+              }
+              mx = __shfl_sync(FULL, mx, sl);
+              const unsigned wm = __ballot_sync(FULL, nd && c == mx) & segm;
+              const int tw = __shfl_sync(FULL, t, wm ? __ffs(wm) - 1 : 0);
+              if (!alleq)
+                result = ((double)mx >= __dmul_rn((double)k, P.major_th)) ? tw
+                                                                          : -1;
+            } else if (P.flags & WK_F_ABOVE) {
+              const unsigned neg = __ballot_sync(FULL, nd && t < 0) & segm;
+              const bool need = ishead && !alleq && !neg;
+              const int l = warp_seg_lca(P.parent, t, segnd, se, need, lane);
+              if (!alleq) result = (neg || l == P.root) ? -1 : l;
+            } else if (P.flags & WK_F_UNIQ) {
+              if (!alleq) result = -1;
+            } else {
+              const unsigned vm = __ballot_sync(FULL, nd && t >= 0) & segm;
+              if (!alleq) {
+                uniqres = false;
+                if (live && nd && t >= 0)
+                  emit_frac(P, C, e, samp, strat, t, __popc(vm));
+              }
+            }
+          }
+        } else {
+          // classify.assign_free (classify.py:54-78)
+          const int t1 = nd ? tab_get<STAGED>(P, stab, e, sv) : -1;
+          result = t1;
+          if (__any_sync(FULL, act && k > 1)) {
+            const int v = nd ? __ldg(P.sub_node + sv) : -1;
+            const unsigned neg = __ballot_sync(FULL, nd && v < 0) & segm;
+            const bool need = ishead && k > 1 && !neg;
+            const int l = warp_seg_lca(P.parent, v, segnd, se, need, lane);
+            if (k > 1) result = (neg || l == P.root) ? -1 : l;
+          }
+        }
+        if (ishead && live && uniqres) {
+          if (result >= 0)
+            emit_units(P, C, e, samp, strat, result, (uint32_t)WK_UNITS);
+          else if (unas)
+            emit_units(P, C, e, samp, strat, NF, (uint32_t)WK_UNITS);
+        }
+      }
+      cur += wend;
+      if (wend >= lim) break;
+    }
+
+    __syncthreads();  // every warp is done with this stage
+    if (tid == 0) {
+      int64_t nt = tile + (int64_t)CLS_STAGES * gridDim.x;
+      if (nt < n_tiles) issue(nt, stage);
+    }
+  }
+
+  // write the CTA's cached partial counts back (util.sum_dict, util.py:78-94)
+  if (C.log2n) {
+    __syncthreads();
+    for (uint32_t h = tid; h < (1u << C.log2n); h += CLS_NT) {
+      uint32_t tag = C.tag[h];
+      if (tag != CACHE_EMPTY && C.lo[h]) atomicAdd(&P.cnt[tag], (ull)C.lo[h]);
+    }
+  }
+}
+
+}  // namespace wk

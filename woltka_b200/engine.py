@@ -1,0 +1,269 @@
+"""Thin Python face of one GPU context of the C-ABI (include/woltka_b200.h).
+
+The engine speaks integer SoA only; strings are interned one level up
+(woltka_b200.session).  Host inputs are numpy int32 arrays, device inputs are
+raw device addresses (e.g. ``tensor.data_ptr()``).
+"""
+import ctypes as C
+from fractions import Fraction
+
+import numpy as np
+
+from . import _lib
+from ._lib import (UNITS, MAX_ENTRIES, KIND_NONE, KIND_FREE, KIND_RANK,
+                   KIND_NONE_ID, F_UNIQ, F_ABOVE, F_MAJOR, F_UNASSIGNED,
+                   WoltkaB200Error)
+
+__all__ = ['Engine', 'UNITS', 'MAX_ENTRIES', 'KIND_NONE', 'KIND_FREE',
+           'KIND_RANK', 'KIND_NONE_ID', 'F_UNIQ', 'F_ABOVE', 'F_MAJOR',
+           'F_UNASSIGNED', 'WoltkaB200Error', 'pinned_empty']
+
+
+def _i32(a):
+    """Contiguous int32 view/copy of an array-like, or None."""
+    if a is None:
+        return None
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.ctypes.data)
+
+
+class _Pinned:
+    def __init__(self, nbytes):
+        self.lib = _lib.load()
+        p = C.c_void_p()
+        _lib.check(self.lib.wk_host_alloc(C.byref(p), nbytes))
+        self.ptr = p.value
+        self.nbytes = nbytes
+
+    def __del__(self):
+        try:
+            self.lib.wk_host_free(C.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
+def pinned_empty(n, dtype=np.int32):
+    """numpy array backed by page-locked host memory (wk_host_alloc)."""
+    dtype = np.dtype(dtype)
+    owner = _Pinned(max(int(n), 1) * dtype.itemsize)
+    buf = (C.c_char * owner.nbytes).from_address(owner.ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(n))
+    arr = arr.view(_PinnedArray)
+    arr._owner = owner
+    return arr
+
+
+class _PinnedArray(np.ndarray):
+    _owner = None
+
+    def __array_finalize__(self, obj):
+        if obj is not None:
+            self._owner = getattr(obj, '_owner', None)
+
+
+class Engine:
+    """One wk_ctx (one GPU)."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        ctx = C.c_void_p()
+        _lib.check(self.lib.wk_create(device, C.byref(ctx)))
+        self.ctx = ctx
+        self.device = device
+        self.E = self.S = 0
+        self.NF = 0
+        self.T = 0
+
+    def close(self):
+        if getattr(self, 'ctx', None):
+            self.lib.wk_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing ----------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        _lib.check(self.lib.wk_set_stream(self.ctx, C.c_void_p(cuda_stream or 0)))
+
+    def sync(self):
+        _lib.check(self.lib.wk_sync(self.ctx))
+
+    def launch_count(self):
+        return int(self.lib.wk_launch_count(self.ctx))
+
+    def set_tuning(self, grid=0, block=0, cache_slots=0):
+        _lib.check(self.lib.wk_set_tuning(self.ctx, grid, block, cache_slots))
+
+    # -- model -------------------------------------------------------------
+    def set_tree(self, parent, root):
+        parent = _i32(parent)
+        self._keep_parent = parent
+        _lib.check(self.lib.wk_set_tree(self.ctx, _ptr(parent), len(parent),
+                                        -1 if root is None else int(root)))
+        self.T = len(parent)
+
+    def set_plan(self, kinds, flags=0, major_th=0.0, n_samples=1,
+                 n_features=0):
+        kinds = _i32(kinds)
+        _lib.check(self.lib.wk_set_plan(self.ctx, _ptr(kinds), len(kinds),
+                                        flags, float(major_th), n_samples,
+                                        n_features))
+        self.E, self.S, self.NF = len(kinds), n_samples, n_features
+        self.kinds = kinds
+
+    def resize_counts(self, n_samples, n_features):
+        _lib.check(self.lib.wk_resize_counts(self.ctx, n_samples, n_features))
+        self.S, self.NF = n_samples, n_features
+
+    def set_subjects(self, tab, sub_node=None, n_subjects=None):
+        tab = _i32(tab)
+        sub_node = _i32(sub_node)
+        if n_subjects is None:
+            n_subjects = (tab.shape[-1] if tab is not None and tab.ndim == 2
+                          else len(sub_node) if sub_node is not None else 0)
+        if tab is not None and tab.size != self.E * n_subjects:
+            raise ValueError('tab must have shape [n_entries, n_subjects]')
+        _lib.check(self.lib.wk_set_subjects(self.ctx, _ptr(tab),
+                                            _ptr(sub_node), n_subjects))
+        self.V = n_subjects
+
+    # -- classify ----------------------------------------------------------
+    def classify_chunk(self, qidx, sidx, q_sample=None, q_stratum=None,
+                       sample=0):
+        qidx, sidx = _i32(qidx), _i32(sidx)
+        q_sample, q_stratum = _i32(q_sample), _i32(q_stratum)
+        if len(qidx) != len(sidx):
+            raise ValueError('qidx and sidx differ in length')
+        n_qry = max(len(q_sample) if q_sample is not None else 0,
+                    len(q_stratum) if q_stratum is not None else 0)
+        _lib.check(self.lib.wk_classify_chunk(
+            self.ctx, _ptr(qidx), _ptr(sidx), len(qidx), _ptr(q_sample),
+            _ptr(q_stratum), n_qry, sample))
+
+    def classify_device(self, d_qidx, d_sidx, n_rec, d_q_sample=None,
+                        d_q_stratum=None, n_qry=0, sample=0):
+        _lib.check(self.lib.wk_classify_device(
+            self.ctx, _ptr(d_qidx), _ptr(d_sidx), n_rec, _ptr(d_q_sample),
+            _ptr(d_q_stratum), n_qry, sample))
+
+    # -- ordinal -----------------------------------------------------------
+    def ordinal_set_genes(self, contig_off, gbeg, gend, gene_subject):
+        contig_off = np.ascontiguousarray(contig_off, dtype=np.int64)
+        gbeg, gend, gene_subject = _i32(gbeg), _i32(gend), _i32(gene_subject)
+        _lib.check(self.lib.wk_ordinal_set_genes(
+            self.ctx, _ptr(contig_off), _ptr(gbeg), _ptr(gend),
+            _ptr(gene_subject), len(contig_off) - 1, len(gbeg)))
+
+    def ordinal_chunk(self, qidx, contig, beg, end, length, th, q_sample=None,
+                      q_stratum=None, sample=0):
+        cols = [_i32(x) for x in (qidx, contig, beg, end, length)]
+        if len({len(x) for x in cols}) != 1:
+            raise ValueError('record columns differ in length')
+        q_sample, q_stratum = _i32(q_sample), _i32(q_stratum)
+        n_qry = max(len(q_sample) if q_sample is not None else 0,
+                    len(q_stratum) if q_stratum is not None else 0)
+        _lib.check(self.lib.wk_ordinal_chunk(
+            self.ctx, *[_ptr(x) for x in cols], len(cols[0]), float(th),
+            _ptr(q_sample), _ptr(q_stratum), n_qry, sample))
+
+    def ordinal_device(self, d_cols, n_rec, th, d_q_sample=None,
+                       d_q_stratum=None, n_qry=0, sample=0):
+        _lib.check(self.lib.wk_ordinal_device(
+            self.ctx, *[_ptr(x) for x in d_cols], n_rec, float(th),
+            _ptr(d_q_sample), _ptr(d_q_stratum), n_qry, sample))
+
+    def ordinal_enable_pairs(self):
+        n = C.c_int64()
+        _lib.check(self.lib.wk_ordinal_fetch_pairs(self.ctx, C.byref(n), None,
+                                                   None, 0))
+        return n.value
+
+    def ordinal_pairs(self):
+        """(read index, gene index) pairs of the last ordinal chunk."""
+        n = self.ordinal_enable_pairs()
+        r = np.empty(n, dtype=np.int32)
+        g = np.empty(n, dtype=np.int32)
+        if n:
+            m = C.c_int64()
+            _lib.check(self.lib.wk_ordinal_fetch_pairs(
+                self.ctx, C.byref(m), _ptr(r), _ptr(g), n))
+        return r, g
+
+    # -- results -----------------------------------------------------------
+    def fetch_counts(self):
+        """int64 units table [n_entries, n_samples, n_features + 1]."""
+        out = np.empty((self.E, self.S, self.NF + 1), dtype=np.int64)
+        _lib.check(self.lib.wk_fetch_counts(self.ctx, _ptr(out)))
+        return out
+
+    def fetch_overflow(self):
+        n = C.c_int64()
+        _lib.check(self.lib.wk_fetch_overflow(self.ctx, C.byref(n), None, None,
+                                              0))
+        key = np.empty(n.value, dtype=np.int64)
+        den = np.empty(n.value, dtype=np.int32)
+        if n.value:
+            _lib.check(self.lib.wk_fetch_overflow(
+                self.ctx, C.byref(n), _ptr(key), _ptr(den), len(key)))
+        return key, den
+
+    def fetch_strata(self):
+        """(entry, sample, stratum, feature, units) arrays."""
+        n = C.c_int64()
+        _lib.check(self.lib.wk_fetch_strata(self.ctx, C.byref(n), None, None,
+                                            None, None, None, 0))
+        m = n.value
+        e = np.empty(m, dtype=np.int32)
+        s = np.empty(m, dtype=np.int32)
+        t = np.empty(m, dtype=np.int32)
+        f = np.empty(m, dtype=np.int64)
+        u = np.empty(m, dtype=np.int64)
+        if m:
+            _lib.check(self.lib.wk_fetch_strata(
+                self.ctx, C.byref(n), _ptr(e), _ptr(s), _ptr(t), _ptr(f),
+                _ptr(u), m))
+        return e, s, t, f, u
+
+    def reset_counts(self):
+        _lib.check(self.lib.wk_reset_counts(self.ctx))
+
+    def counts_device(self):
+        """(device address, number of int64 elements) of the units table."""
+        p = C.c_void_p()
+        n = C.c_int64()
+        _lib.check(self.lib.wk_counts_device(self.ctx, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def counts_tensor(self):
+        """Zero-copy torch view of the units table (for an NCCL reduce)."""
+        import torch
+        ptr, n = self.counts_device()
+
+        class _Wrap:
+            __cuda_array_interface__ = {
+                'shape': (n,), 'typestr': '<i8', 'data': (ptr, False),
+                'version': 2}
+        return torch.as_tensor(_Wrap(), device=f'cuda:{self.device}')
+
+
+def units_to_value(units, extra=None):
+    """Exact count from units (+ optional list of overflow denominators):
+    int when integral, else the correctly rounded double."""
+    if not extra:
+        q, r = divmod(int(units), UNITS)
+        return q if r == 0 else float(Fraction(int(units), UNITS))
+    v = Fraction(int(units), UNITS)
+    for d in extra:
+        v += Fraction(1, int(d))
+    return int(v) if v.denominator == 1 else float(v)
