@@ -641,7 +641,6 @@ __global__ void __launch_bounds__(CLS_NT, 1)
         }
       }
       cur += wend;
-      if (wend >= lim) break;
     }
 
     __syncthreads();  // every warp is done with this stage
