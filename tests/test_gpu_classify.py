@@ -151,3 +151,35 @@ def test_cfg2_shape_1e6(engine, big_case, mode):
     ent = ['phylum', 'genus', 'species']
     _same(cases.run_engine(engine, big_case, ent, fl, 0.8, q, s),
           cases.run_oracle(big_case, ent, fl, 0.8, q, s, n_threads=4))
+
+
+@pytest.mark.parametrize('cache_slots', [0, 4096, 256, -1])
+def test_every_count_sink(engine, small_case, cache_slots):
+    # 0 = automatic (direct table here), >0 = hashed write-back cache,
+    # -1 = straight to global memory
+    q, s = cases.random_hits(small_case, 60000, seed=31)
+    ent = ['phylum', 'genus', 'none', 'free']
+    engine.set_tuning(0, 0, cache_slots)
+    try:
+        for mode in ('default', 'major+unassigned', 'above'):
+            fl = cases.MODES[mode]
+            _same(cases.run_engine(engine, small_case, ent, fl, 0.7, q, s,
+                                   n_samples=2, sample=1),
+                  cases.run_oracle(small_case, ent, fl, 0.7, q, s,
+                                   n_samples=2, sample=1))
+    finally:
+        engine.set_tuning(0, 0, 0)
+
+
+def test_carry_out_of_the_32bit_low_words(engine, small_case):
+    # > 5958 unit counts into one cell overflow a 32-bit low word
+    n = 200_000
+    q = np.arange(n, dtype=np.int32)
+    s = np.full(n, 3, dtype=np.int32)
+    for cache_slots in (0, 1024):
+        engine.set_tuning(0, 0, cache_slots)
+        try:
+            _same(cases.run_engine(engine, small_case, ['genus'], 0, 0, q, s),
+                  cases.run_oracle(small_case, ['genus'], 0, 0, q, s))
+        finally:
+            engine.set_tuning(0, 0, 0)

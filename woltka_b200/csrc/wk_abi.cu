@@ -232,12 +232,18 @@ int wk_create(int device, wk_ctx **out) {
   c->ovf_cap = 1 << 20;
   TRY(c->ovf_key.reserve(c->ovf_cap * 8));
   TRY(c->ovf_den.reserve(c->ovf_cap * 4));
-  CK(cudaFuncSetAttribute(classify_kernel<true>,
-                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)c->smem_optin));
-  CK(cudaFuncSetAttribute(classify_kernel<false>,
-                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)c->smem_optin));
+  {
+    const void *variants[] = {
+        (const void *)classify_kernel<true, SINK_DIRECT>,
+        (const void *)classify_kernel<true, SINK_HASHED>,
+        (const void *)classify_kernel<true, SINK_GLOBAL>,
+        (const void *)classify_kernel<false, SINK_DIRECT>,
+        (const void *)classify_kernel<false, SINK_HASHED>,
+        (const void *)classify_kernel<false, SINK_GLOBAL>};
+    for (const void *fn : variants)
+      CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)c->smem_optin));
+  }
   *out = c;
   return WK_OK;
 }
@@ -574,18 +580,39 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   const bool staged = c->tab16_ok && !all_id;
   const int64_t tab_bytes = staged ? (int64_t)c->E * c->Vp * 2 : 0;
   const size_t cells = (size_t)c->E * c->S * (c->NF + 1);
-  int cache_log = 0;
-  if (!dqstrat && cells < 0xFFFFFFFFull) {
-    int want = c->tune_cache > 0 ? 0 : 13;
-    if (c->tune_cache > 0)
-      while ((1 << (want + 1)) <= c->tune_cache) ++want;
-    for (cache_log = want; cache_log >= 8; --cache_log)
-      if (cls_layout(cache_log, tab_bytes).total <= c->smem_optin) break;
-    if (cache_log < 8) cache_log = 0;
-    if (c->tune_cache < 0) cache_log = 0;
+  // where counts are accumulated first (wk_classify.cuh, "count sinks")
+  int sink = SINK_GLOBAL, cache_log = 0;
+  if (!dqstrat && c->tune_cache >= 0) {
+    if (cells < (1u << 24) &&
+        cls_layout(SINK_DIRECT, 0, (uint32_t)cells, tab_bytes).total <=
+            c->smem_optin) {
+      sink = SINK_DIRECT;
+    } else if (cells < 0xFFFFFFFFull) {
+      int want = 13;
+      if (c->tune_cache > 0) {
+        want = 0;
+        while ((1 << (want + 1)) <= c->tune_cache) ++want;
+      }
+      for (cache_log = want; cache_log >= 8; --cache_log)
+        if (cls_layout(SINK_HASHED, cache_log, 0, tab_bytes).total <=
+            c->smem_optin)
+          break;
+      if (cache_log >= 8) sink = SINK_HASHED;
+    }
   }
-  P.cache_log = cache_log;
-  ClsSmemLayout L = cls_layout(cache_log, tab_bytes);
+  if (c->tune_cache > 0 && sink == SINK_DIRECT && c->tune_cache < 1000000) {
+    // explicit request for the hashed cache (tests exercise every sink)
+    int want = 0;
+    while ((1 << (want + 1)) <= c->tune_cache) ++want;
+    if (want >= 8 &&
+        cls_layout(SINK_HASHED, want, 0, tab_bytes).total <= c->smem_optin) {
+      sink = SINK_HASHED;
+      cache_log = want;
+    }
+  }
+  P.cache_log = sink == SINK_HASHED ? cache_log : 0;
+  P.direct_cells = sink == SINK_DIRECT ? (uint32_t)cells : 0;
+  ClsSmemLayout L = cls_layout(sink, P.cache_log, P.direct_cells, tab_bytes);
   if (L.total > c->smem_optin)
     return fail(WK_ERR_STATE, "shared memory layout does not fit (%u B)", L.total);
   int64_t span = (n_dev ? n_bound : r1) - (r0 & ~3ll);
@@ -593,10 +620,18 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   if (n_tiles <= 0) return WK_OK;
   int grid = c->tune_grid > 0 ? c->tune_grid : c->sm_count;
   grid = (int)std::min<int64_t>(grid, n_tiles);
-  if (staged)
-    classify_kernel<true><<<grid, CLS_NT, L.total, c->stream>>>(P);
-  else
-    classify_kernel<false><<<grid, CLS_NT, L.total, c->stream>>>(P);
+#define WK_LAUNCH(ST, SK) \
+  classify_kernel<ST, SK><<<grid, CLS_NT, L.total, c->stream>>>(P)
+  if (staged) {
+    if (sink == SINK_DIRECT) WK_LAUNCH(true, SINK_DIRECT);
+    else if (sink == SINK_HASHED) WK_LAUNCH(true, SINK_HASHED);
+    else WK_LAUNCH(true, SINK_GLOBAL);
+  } else {
+    if (sink == SINK_DIRECT) WK_LAUNCH(false, SINK_DIRECT);
+    else if (sink == SINK_HASHED) WK_LAUNCH(false, SINK_HASHED);
+    else WK_LAUNCH(false, SINK_GLOBAL);
+  }
+#undef WK_LAUNCH
   c->launches++;
   CK(cudaGetLastError());
   return WK_OK;

@@ -18,12 +18,15 @@
 //     they fit; otherwise they are read through L1/L2 as int32.
 //   * one lane = one alignment record.  A warp owns TILE/NW consecutive
 //     records of the tile and advances over them in 32-record windows that
-//     start at a query head and only consume whole queries; all per-query
-//     logic (set-dedup of subjects, all-equal test, majority, 1/k split, LCA)
-//     is warp ballots / match.any / shuffles over the query's lane segment.
-//   * counts go to a per-CTA shared-memory write-back cache (tag + 32-bit low
-//     word, carry propagated to the global table) and only cold or conflicting
-//     cells become global 64-bit reductions; the cache is flushed once per CTA.
+//     start at a query head and only consume whole queries.  A record is the
+//     tail of its query iff q[i] != q[i+1]; the ballot of tails gives every
+//     lane its segment [sl, se) with two bit scans, and all per-query logic
+//     (set-dedup of subjects, all-equal test, majority, 1/k split, LCA) is
+//     match.any / ballots / shuffles over that lane segment.
+//   * counts go to shared memory first: a direct-indexed private table of
+//     32-bit low words when the whole count space fits (SINK_DIRECT), else a
+//     hashed write-back cache (SINK_HASHED); carries and cold cells become
+//     global 64-bit reductions.  Flushed once per CTA.
 //   * queries longer than a window take a warp-cooperative slow path that
 //     reads global memory directly (any length).
 #pragma once
@@ -37,14 +40,17 @@ typedef unsigned long long ull;
 
 constexpr int CLS_TILE = 4096;                 // records per tile
 constexpr int CLS_PRE = 4;                     // records staged before the tile
-constexpr int CLS_POST = 44;                   // halo after the tile (>= 33)
+constexpr int CLS_POST = 44;                   // halo after the tile (>= 34)
 constexpr int CLS_TBUF = CLS_TILE + CLS_PRE + CLS_POST;  // 4144 rec, 16 B multiple
 constexpr int CLS_STAGES = 3;
 constexpr int CLS_NT = 1024;                   // threads per CTA
 constexpr int CLS_NW = CLS_NT / 32;
+constexpr int CLS_SUB = CLS_TILE / CLS_NW;     // records per warp per tile
 constexpr unsigned FULL = 0xffffffffu;
 constexpr uint32_t CACHE_EMPTY = 0xffffffffu;
 constexpr int DUPMARK = INT32_MIN;
+
+enum { SINK_DIRECT = 0, SINK_HASHED = 1, SINK_GLOBAL = 2 };
 
 struct ClsParams {
   const int32_t *q, *s;       // record columns (device)
@@ -76,7 +82,8 @@ struct ClsParams {
   ull *sh_used;
   int32_t *err;               // device error word (bit flags)
   int32_t *scratch;           // [>= n] long-query scratch
-  int32_t cache_log;          // log2(cache slots), 0 = no cache
+  int32_t cache_log;          // SINK_HASHED: log2(cache slots)
+  uint32_t direct_cells;      // SINK_DIRECT: E*S*NF1
 };
 
 enum { ERR_BAD_SUBJECT = 1, ERR_OVF_FULL = 2, ERR_HASH_FULL = 4,
@@ -88,26 +95,49 @@ __constant__ uint32_t c_units[33] = {
     40040,  0,      36036,  34320,  32760,  0,      30030,  0,      27720,
     0,      25740,  0,      24024,  0,      0};
 
-__device__ __forceinline__ unsigned lowmask(int n) {
-  return n >= 32 ? FULL : ((1u << n) - 1u);
-}
-
-// ---- mbarrier / TMA bulk copy (PTX) ------------------------------------
+// ---- shared memory by 32-bit address, mbarrier, TMA bulk copy (PTX) --------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
-__device__ __forceinline__ void mbar_init(void *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(count));
+__device__ __forceinline__ int lds32(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
 }
-__device__ __forceinline__ void mbar_expect_tx(void *bar, uint32_t bytes) {
-  asm volatile(
-      "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "r"(bytes)
-      : "memory");
+__device__ __forceinline__ unsigned lds16(uint32_t a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return v;
 }
-__device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity) {
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;"
+               : "=r"(old)
+               : "r"(a), "r"(v)
+               : "memory");
+  return old;
+}
+__device__ __forceinline__ uint32_t atoms_cas(uint32_t a, uint32_t cmp,
+                                              uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;"
+               : "=r"(old)
+               : "r"(a), "r"(cmp), "r"(v)
+               : "memory");
+  return old;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
@@ -116,23 +146,24 @@ __device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity) {
       "@P1 bra WK_DONE;\n"
       "bra WK_WAIT;\n"
       "WK_DONE:\n"
-      "}" ::"r"(smem_u32(bar)),
+      "}" ::"r"(bar),
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src,
-                                         uint32_t bytes, void *bar) {
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src,
+                                         uint32_t bytes, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
-      "[%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      "[%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
 
-// ---- count sinks --------------------------------------------------------
-struct Cache {
-  uint32_t *tag, *lo;
-  int log2n;
+// ---- count sinks -------------------------------------------------------------
+struct Sink {
+  uint32_t a0;   // DIRECT: low-word table; HASHED: tags
+  uint32_t a1;   // HASHED: low words
+  int sh;        // HASHED: 32 - log2(slots)
 };
 
 __device__ __forceinline__ void strat_add(const ClsParams &P, ull key,
@@ -158,39 +189,48 @@ __device__ __forceinline__ void strat_add(const ClsParams &P, ull key,
   atomicOr(P.err, ERR_HASH_FULL);
 }
 
-__device__ __forceinline__ void emit_units(const ClsParams &P, const Cache &C,
+// add `units` (< 2^32) to cell (e, samp, f)
+template <int SINK>
+__device__ __forceinline__ void emit_units(const ClsParams &P, const Sink &K,
                                            int e, int samp, int strat,
                                            int64_t f, uint32_t units) {
-  int64_t cell = ((int64_t)e * P.S + samp) * P.NF1 + f;
-  if (P.q_stratum) {
-    strat_add(P, ((ull)(uint32_t)strat << 40) | (ull)cell, units);
+  if (SINK == SINK_DIRECT) {
+    uint32_t key = (uint32_t)((e * P.S + samp) * (int)P.NF1 + (int)f);
+    uint32_t old = atoms_add(K.a0 + key * 4u, units);
+    if (old + units < old) atomicAdd(&P.cnt[key], 1ull << 32);
     return;
   }
-  if (C.log2n) {
+  int64_t cell = ((int64_t)e * P.S + samp) * P.NF1 + f;
+  if (SINK == SINK_HASHED) {
     uint32_t key = (uint32_t)cell;
-    uint32_t h = (key * 2654435761u) >> (32 - C.log2n);
-    uint32_t tag = C.tag[h];
+    uint32_t h = (key * 2654435761u) >> K.sh;
+    uint32_t ta = K.a0 + h * 4u;
+    uint32_t tag = (uint32_t)lds32(ta);
     if (tag == CACHE_EMPTY) {
-      uint32_t old = atomicCAS(&C.tag[h], CACHE_EMPTY, key);
+      uint32_t old = atoms_cas(ta, CACHE_EMPTY, key);
       tag = (old == CACHE_EMPTY) ? key : old;
     }
     if (tag == key) {
-      uint32_t old = atomicAdd(&C.lo[h], units);
+      uint32_t old = atoms_add(K.a1 + h * 4u, units);
       if (old + units < old) atomicAdd(&P.cnt[cell], 1ull << 32);
       return;
     }
+  } else if (P.q_stratum) {
+    strat_add(P, ((ull)(uint32_t)strat << 40) | (ull)cell, units);
+    return;
   }
   atomicAdd(&P.cnt[cell], (ull)units);
 }
 
 // one 1/d share (classify.py:168-170)
-__device__ __forceinline__ void emit_frac(const ClsParams &P, const Cache &C,
+template <int SINK>
+__device__ __forceinline__ void emit_frac(const ClsParams &P, const Sink &K,
                                           int e, int samp, int strat,
                                           int64_t f, int64_t d) {
   uint32_t u = d <= 32 ? c_units[d]
                        : (uint32_t)((WK_UNITS % d) == 0 ? WK_UNITS / d : 0);
   if (u) {
-    emit_units(P, C, e, samp, strat, f, u);
+    emit_units<SINK>(P, K, e, samp, strat, f, u);
     return;
   }
   ull at = atomicAdd(P.ovf_n, 1ull);
@@ -204,26 +244,31 @@ __device__ __forceinline__ void emit_frac(const ClsParams &P, const Cache &C,
   }
 }
 
-// ---- tree ---------------------------------------------------------------
+// ---- tree ----------------------------------------------------------------------
 // LCA of two nodes on a topologically numbered tree (parent[i] < i): lifting
 // the larger index can never step over the LCA.  Same result as
 // tree.find_lca (tree.py:513-566) on a single-rooted tree.
 __device__ __forceinline__ int lca2(const int32_t *__restrict__ parent, int a,
                                     int b) {
   while (a != b) {
-    if (a > b)
-      a = __ldg(parent + a);
-    else
-      b = __ldg(parent + b);
+    if (a > b) {
+      int p = __ldg(parent + a);
+      if (p == a) return b;  // second root: never loop (host rejects such trees)
+      a = p;
+    } else {
+      int p = __ldg(parent + b);
+      if (p == b) return a;
+      b = p;
+    }
   }
   return a;
 }
 
 template <bool STAGED>
-__device__ __forceinline__ int tab_get(const ClsParams &P,
-                                       const uint16_t *stab, int e, int s) {
+__device__ __forceinline__ int tab_get(const ClsParams &P, uint32_t stab,
+                                       int e, int s) {
   if (STAGED) {
-    unsigned v = stab[e * P.Vp + s];
+    unsigned v = lds16(stab + (uint32_t)(e * P.Vp + s) * 2u);
     return v == 0xFFFFu ? -1 : (int)v;
   } else {
     return __ldg(P.tab + (int64_t)e * P.V + s);
@@ -249,11 +294,11 @@ __device__ __forceinline__ int warp_sum(int v) {
   return __reduce_add_sync(FULL, v);
 }
 
-// ---- slow path: one query of any length, whole warp, global memory -------
-template <bool STAGED>
-__device__ int64_t process_long(const ClsParams &P, const Cache &C,
-                                const uint16_t *stab, int64_t n,
-                                int64_t start, int lane) {
+// ---- slow path: one query of any length, whole warp, global memory ----------
+template <bool STAGED, int SINK>
+__device__ __noinline__ int64_t process_long(const ClsParams &P, const Sink &K,
+                                             uint32_t stab, int64_t n,
+                                             int64_t start, int lane) {
   const int32_t *gq = P.q, *gs = P.s;
   const int qid = gq[start];
   int64_t end = start + 1;
@@ -276,7 +321,7 @@ __device__ int64_t process_long(const ClsParams &P, const Cache &C,
   for (int64_t j = start + lane; j < end; j += 32) {
     int sj = gs[j];
     bool dup = false;
-    if ((unsigned)sj >= (uint64_t)P.V) {
+    if ((uint64_t)(unsigned)sj >= (uint64_t)P.V || sj < 0) {
       atomicOr(P.err, ERR_BAD_SUBJECT);
       dup = true;
     }
@@ -305,7 +350,7 @@ __device__ int64_t process_long(const ClsParams &P, const Cache &C,
           if (__ldcg(P.scratch + j) == DUPMARK) continue;
           int sj = gs[j];
           int f = kind == WK_KIND_NONE_ID ? sj : tab_get<STAGED>(P, stab, e, sj);
-          emit_frac(P, C, e, samp, strat, f, k);
+          emit_frac<SINK>(P, K, e, samp, strat, f, k);
         }
       }
     } else {
@@ -382,7 +427,7 @@ __device__ int64_t process_long(const ClsParams &P, const Cache &C,
           for (int64_t j = start + lane; j < end; j += 32) {
             int t = __ldcg(P.scratch + j);
             if (t == DUPMARK || t < 0) continue;
-            emit_frac(P, C, e, samp, strat, t, nvalid);
+            emit_frac<SINK>(P, K, e, samp, strat, t, nvalid);
           }
         }
         // restore dup marks for the next entry
@@ -394,45 +439,53 @@ __device__ int64_t process_long(const ClsParams &P, const Cache &C,
     }
     if (lane == 0 && uniqres) {
       if (result >= 0)
-        emit_units(P, C, e, samp, strat, result, (uint32_t)WK_UNITS);
+        emit_units<SINK>(P, K, e, samp, strat, result, (uint32_t)WK_UNITS);
       else if (unas)
-        emit_units(P, C, e, samp, strat, NF, (uint32_t)WK_UNITS);
+        emit_units<SINK>(P, K, e, samp, strat, NF, (uint32_t)WK_UNITS);
     }
   }
   return end;
 }
 
-// ---- the kernel -----------------------------------------------------------
+// ---- the kernel ------------------------------------------------------------------
 struct ClsSmemLayout {
-  uint32_t bars, tiles, ctag, clo, tab, total;
+  uint32_t bars, tiles, sink0, sink1, tab, total;
 };
-__host__ __device__ inline ClsSmemLayout cls_layout(int cache_log,
+__host__ __device__ inline ClsSmemLayout cls_layout(int sink, int cache_log,
+                                                    uint32_t direct_cells,
                                                     int64_t tab_bytes) {
   ClsSmemLayout L;
   L.bars = 0;
   L.tiles = 128;
-  L.ctag = L.tiles + CLS_STAGES * 2 * CLS_TBUF * 4;
-  uint32_t slots = cache_log ? (1u << cache_log) : 0;
-  L.clo = L.ctag + slots * 4;
-  L.tab = (L.clo + slots * 4 + 127) & ~127u;
+  L.sink0 = L.tiles + CLS_STAGES * 2 * CLS_TBUF * 4;
+  uint32_t w0 = 0, w1 = 0;
+  if (sink == SINK_DIRECT) w0 = direct_cells * 4;
+  if (sink == SINK_HASHED) w0 = w1 = (1u << cache_log) * 4;
+  L.sink1 = L.sink0 + w0;
+  L.tab = (L.sink1 + w1 + 127) & ~127u;
   L.total = L.tab + (uint32_t)((tab_bytes + 15) & ~15ll);
   return L;
 }
 
-template <bool STAGED>
+template <bool STAGED, int SINK>
 __global__ void __launch_bounds__(CLS_NT, 1)
     classify_kernel(const __grid_constant__ ClsParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t tab_bytes = STAGED ? (int64_t)P.E * P.Vp * 2 : 0;
-  const ClsSmemLayout L = cls_layout(P.cache_log, tab_bytes);
-  ull *bars = reinterpret_cast<ull *>(smem + L.bars);  // [STAGES] full, [STAGES] = tab
-  int32_t *tiles = reinterpret_cast<int32_t *>(smem + L.tiles);
-  Cache C;
-  C.tag = reinterpret_cast<uint32_t *>(smem + L.ctag);
-  C.lo = reinterpret_cast<uint32_t *>(smem + L.clo);
-  C.log2n = P.cache_log;
-  const uint16_t *stab = reinterpret_cast<const uint16_t *>(smem + L.tab);
+  const ClsSmemLayout L =
+      cls_layout(SINK, P.cache_log, P.direct_cells, tab_bytes);
+  const uint32_t sbase32 = smem_u32(smem);
+  const uint32_t bars = sbase32 + L.bars;  // [STAGES] tiles, [STAGES] = tables
+  const uint32_t tiles = sbase32 + L.tiles;
+  const uint32_t stab = sbase32 + L.tab;
+  Sink K;
+  K.a0 = sbase32 + L.sink0;
+  K.a1 = sbase32 + L.sink1;
+  K.sh = 32 - P.cache_log;
+  const uint32_t sink_words =
+      SINK == SINK_DIRECT ? P.direct_cells
+                          : (SINK == SINK_HASHED ? (2u << P.cache_log) : 0u);
 
   int64_t n = P.n, r0 = P.r0, r1 = P.r1;
   if (P.n_dev) {
@@ -445,7 +498,7 @@ __global__ void __launch_bounds__(CLS_NT, 1)
   const int64_t n_tiles = r1 > tb0 ? (r1 - tb0 + CLS_TILE - 1) / CLS_TILE : 0;
 
   if (tid == 0) {
-    for (int i = 0; i <= CLS_STAGES; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i <= CLS_STAGES; ++i) mbar_init(bars + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -457,140 +510,141 @@ __global__ void __launch_bounds__(CLS_NT, 1)
     int64_t g1 = tb + CLS_TILE + CLS_POST;
     if (g1 > n) g1 = n;
     uint32_t bytes = (uint32_t)(((g1 - g0) * 4 + 15) & ~15ll);
-    int32_t *dq = tiles + (size_t)stage * 2 * CLS_TBUF + (g0 - (tb - CLS_PRE));
-    int32_t *ds = dq + CLS_TBUF;
-    mbar_expect_tx(&bars[stage], 2 * bytes);
-    bulk_g2s(dq, P.q + g0, bytes, &bars[stage]);
-    bulk_g2s(ds, P.s + g0, bytes, &bars[stage]);
+    uint32_t dq = tiles + (uint32_t)stage * (2 * CLS_TBUF * 4) +
+                  (uint32_t)(g0 - (tb - CLS_PRE)) * 4u;
+    uint32_t bar = bars + 8 * stage;
+    mbar_expect_tx(bar, 2 * bytes);
+    bulk_g2s(dq, P.q + g0, bytes, bar);
+    bulk_g2s(dq + CLS_TBUF * 4, P.s + g0, bytes, bar);
   };
 
   if (tid == 0) {
     if (STAGED) {
       uint32_t bytes = (uint32_t)((tab_bytes + 15) & ~15ll);
-      mbar_expect_tx(&bars[CLS_STAGES], bytes);
-      bulk_g2s(const_cast<uint16_t *>(stab), P.tab16, bytes, &bars[CLS_STAGES]);
+      mbar_expect_tx(bars + 8 * CLS_STAGES, bytes);
+      bulk_g2s(stab, P.tab16, bytes, bars + 8 * CLS_STAGES);
     }
     for (int st = 0; st < CLS_STAGES; ++st) {
       int64_t tile = (int64_t)blockIdx.x + (int64_t)st * gridDim.x;
       if (tile < n_tiles) issue(tile, st);
     }
   }
-  if (C.log2n) {
-    for (uint32_t h = tid; h < (1u << C.log2n); h += CLS_NT) {
-      C.tag[h] = CACHE_EMPTY;
-      C.lo[h] = 0;
+  if (SINK == SINK_DIRECT) {
+    for (uint32_t h = tid; h < sink_words; h += CLS_NT) sts32(K.a0 + h * 4, 0);
+  } else if (SINK == SINK_HASHED) {
+    const uint32_t slots = 1u << P.cache_log;
+    for (uint32_t h = tid; h < slots; h += CLS_NT) {
+      sts32(K.a0 + h * 4, CACHE_EMPTY);
+      sts32(K.a1 + h * 4, 0);
     }
   }
   __syncthreads();
-  if (STAGED) mbar_wait(&bars[CLS_STAGES], 0);
+  if (STAGED) mbar_wait(bars + 8 * CLS_STAGES, 0);
 
   const int64_t NF = P.NF1 - 1;
-  const bool unas = P.flags & WK_F_UNASSIGNED;
-  const unsigned le = lowmask(lane + 1), lt = lowmask(lane);
+  const uint32_t flags = P.flags;
+  const bool unas = flags & WK_F_UNASSIGNED;
+  const int E = P.E;
+  const unsigned le = FULL >> (31 - lane), lt = le >> 1;
+  const bool per_query = P.q_sample || P.q_stratum;
 
   int it = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int stage = it % CLS_STAGES;
-    mbar_wait(&bars[stage], (it / CLS_STAGES) & 1);
+    mbar_wait(bars + 8 * stage, (it / CLS_STAGES) & 1);
     const int64_t tb = tb0 + tile * CLS_TILE;
-    const int32_t *sq = tiles + (size_t)stage * 2 * CLS_TBUF;
-    const int32_t *ss = sq + CLS_TBUF;
-    const int64_t sbase = tb - CLS_PRE;  // global index of sq[0]
+    const int64_t sbase = tb - CLS_PRE;  // global index of staged slot 0
+    // shared addresses of staged slot 0 of the two columns
+    const uint32_t aq = tiles + (uint32_t)stage * (2 * CLS_TBUF * 4);
+    const uint32_t as = aq + CLS_TBUF * 4;
+    // everything below is in staged-slot coordinates x = i - sbase
+    const int nrel = (int)(n - sbase < (1 << 30) ? n - sbase : (1 << 30));
+    const bool full = nrel >= CLS_TBUF;  // no bounds checks needed
+    int w0 = CLS_PRE + warp * CLS_SUB;
+    int w1 = w0 + CLS_SUB;
+    if (r0 - sbase > w0) w0 = (int)(r0 - sbase);
+    {
+      int64_t lim1 = r1 - sbase;
+      if (lim1 < w1) w1 = (int)lim1;
+    }
+    // first own head: the record after the first tail at or after w0 - 1
+    int cur = w0;
+    bool seek = (sbase + w0) > 0;
+    if (seek) --cur;
 
-    int64_t w0 = tb + (int64_t)warp * (CLS_TILE / CLS_NW);
-    int64_t w1 = w0 + CLS_TILE / CLS_NW;
-    if (w0 < r0) w0 = r0;
-    if (w1 > r1) w1 = r1;
-
-    int64_t cur = w0;
     while (cur < w1) {
-      const int64_t i = cur + lane;
-      const bool inb = i < n;
-      const int qv = inb ? sq[i - sbase] : 0;
-      const int qp = (inb && i > 0) ? sq[i - 1 - sbase] : 0;
-      const bool head = inb && (i == 0 || qv != qp);
-      const unsigned heads = __ballot_sync(FULL, head);
-      if (heads == 0) {
-        cur += 32;
-        continue;
-      }
-      const int first = __ffs(heads) - 1;
-      const int lim = (int)(w1 - cur < 32 ? w1 - cur : 32);
-      if (first >= lim) break;
-      const int64_t nx = cur + 32;
-      const bool nh = nx >= n || sq[nx - sbase] != sq[nx - 1 - sbase];
-      const int nvalid = (int)(n - cur < 32 ? n - cur : 32);
-      const int cend = nh ? nvalid : 31 - __clz(heads);
-      const unsigned fh = lim < 32 ? (heads >> lim) : 0u;
-      int wend = cend;
-      if (fh) {
-        int p = lim + __ffs(fh) - 1;
-        wend = p < cend ? p : cend;
-      }
-      if (wend <= first) {
-        if (first > 0) {
-          cur += first;
-          continue;
+      const int x = cur + lane;
+      const uint32_t ax = aq + (uint32_t)x * 4u;
+      const int qa = lds32(ax);
+      const int qb = lds32(ax + 4);
+      bool tail = qa != qb;
+      if (!full) tail = (x < nrel) && (x + 1 >= nrel || tail);
+      const unsigned T = __ballot_sync(FULL, tail);
+      if (seek) {
+        if (T) {
+          cur += __ffs(T);
+          seek = false;
+        } else {
+          cur += 32;
         }
-        cur = process_long<STAGED>(P, C, stab, n, cur, lane);
         continue;
       }
-
-      // ---- lanes [first, wend) hold whole queries ----
-      const bool act = lane >= first && lane < wend;
-      const unsigned actm = lowmask(wend) & ~lowmask(first);
-      int sv = act ? ss[i - sbase] : (-1 - lane);
-      if (act && (unsigned)sv >= (uint64_t)P.V) {
-        atomicOr(P.err, ERR_BAD_SUBJECT);
-        sv = -1 - lane;
+      // whole queries among lanes [0, cons); a query belongs to the warp
+      // whose sub-range holds its head
+      const int lim = w1 - cur;
+      unsigned Tl = T;
+      if (lim <= 32) {
+        unsigned t2 = T & (FULL << (lim - 1));
+        if (t2) Tl = T & (FULL >> (32 - __ffs(t2)));
       }
-      const unsigned hm = heads & actm;
-      const int sl = act ? 31 - __clz(hm & le) : lane;
-      const unsigned ab = hm & ~le;
-      const int se = ab ? (__ffs(ab) - 1) : wend;
-      const unsigned segm = act ? (lowmask(se) & ~lowmask(sl)) : 0u;
+      if (Tl == 0) {
+        int64_t e2 = process_long<STAGED, SINK>(P, K, stab, n, sbase + cur, lane);
+        cur = (int)(e2 - sbase < (1 << 30) ? e2 - sbase : (1 << 30));
+        continue;
+      }
+      const int cons = 32 - __clz(Tl);
+      const bool act = lane < cons;
+      const unsigned H = (Tl << 1) | 1u;           // heads
+      const int sl = 31 - __clz(H & le);           // my query's first lane
+      const int se = __ffs(Tl & ~lt);              // one past its last lane
+      const unsigned segm = act ? ((FULL << sl) & (FULL >> (32 - se))) : 0u;
+      int sv = act ? lds32(as + (uint32_t)x * 4u) : ~lane;
+      if (act && (unsigned)sv >= (unsigned)P.V) {
+        atomicOr(P.err, ERR_BAD_SUBJECT);
+        sv = ~lane;
+      }
+      // set semantics (align.py:339): a repeat has an equal subject on a
+      // lower lane of the same query
       const unsigned mm = __match_any_sync(FULL, sv);
-      const bool nd = act && sv >= 0 && !(mm & segm & lt);
+      const bool nd = sv >= 0 && !(mm & segm & lt);
       const unsigned segnd = __ballot_sync(FULL, nd) & segm;
       const int k = __popc(segnd);
       const bool ishead = act && lane == sl;
 
       int samp = P.sample, strat = 0;
-      if (P.q_sample || P.q_stratum) {
+      if (per_query) {
         if (ishead) {
-          if (P.q_sample) samp = __ldg(P.q_sample + qv);
-          if (P.q_stratum) strat = __ldg(P.q_stratum + qv);
+          if (P.q_sample) samp = __ldg(P.q_sample + qa);
+          if (P.q_stratum) strat = __ldg(P.q_stratum + qa);
         }
         samp = __shfl_sync(FULL, samp, sl);
         strat = __shfl_sync(FULL, strat, sl);
       }
       const bool live = act && strat >= 0 && (unsigned)samp < (unsigned)P.S;
 
-      for (int e = 0; e < P.E; ++e) {
+      for (int e = 0; e < E; ++e) {
         const int kind = P.kind[e];
         int result = -1;
         bool uniqres = true;
-        if (kind == WK_KIND_NONE || kind == WK_KIND_NONE_ID) {
-          // classify.assign_none (classify.py:32-51)
-          const int f = !nd ? -1
-                            : (kind == WK_KIND_NONE_ID
-                                   ? sv
-                                   : tab_get<STAGED>(P, stab, e, sv));
-          if (k == 1) {
-            result = f;
-          } else if (!(P.flags & WK_F_UNIQ)) {
-            uniqres = false;
-            if (live && nd) emit_frac(P, C, e, samp, strat, f, k);
-          }
-        } else if (kind == WK_KIND_RANK) {
+        if (kind == WK_KIND_RANK) {
           // classify.assign_rank (classify.py:81-127)
           const int t = nd ? tab_get<STAGED>(P, stab, e, sv) : -1;
           const int th = __shfl_sync(FULL, t, sl);
           const unsigned neq = __ballot_sync(FULL, nd && t != th);
           const bool alleq = (neq & segm) == 0;
           result = th;
-          if (__any_sync(FULL, act && !alleq)) {
-            if (P.flags & WK_F_MAJOR) {
+          if (neq) {  // some query of this window has differing taxa
+            if (flags & WK_F_MAJOR) {
               const unsigned tm = __match_any_sync(FULL, nd ? t : (-2 - lane));
               const int c = nd ? __popc(tm & segnd) : 0;
               int mx = c;
@@ -605,23 +659,23 @@ __global__ void __launch_bounds__(CLS_NT, 1)
               if (!alleq)
                 result = ((double)mx >= __dmul_rn((double)k, P.major_th)) ? tw
                                                                           : -1;
-            } else if (P.flags & WK_F_ABOVE) {
+            } else if (flags & WK_F_ABOVE) {
               const unsigned neg = __ballot_sync(FULL, nd && t < 0) & segm;
               const bool need = ishead && !alleq && !neg;
               const int l = warp_seg_lca(P.parent, t, segnd, se, need, lane);
               if (!alleq) result = (neg || l == P.root) ? -1 : l;
-            } else if (P.flags & WK_F_UNIQ) {
+            } else if (flags & WK_F_UNIQ) {
               if (!alleq) result = -1;
             } else {
               const unsigned vm = __ballot_sync(FULL, nd && t >= 0) & segm;
               if (!alleq) {
                 uniqres = false;
                 if (live && nd && t >= 0)
-                  emit_frac(P, C, e, samp, strat, t, __popc(vm));
+                  emit_frac<SINK>(P, K, e, samp, strat, t, __popc(vm));
               }
             }
           }
-        } else {
+        } else if (kind == WK_KIND_FREE) {
           // classify.assign_free (classify.py:54-78)
           const int t1 = nd ? tab_get<STAGED>(P, stab, e, sv) : -1;
           result = t1;
@@ -632,15 +686,27 @@ __global__ void __launch_bounds__(CLS_NT, 1)
             const int l = warp_seg_lca(P.parent, v, segnd, se, need, lane);
             if (k > 1) result = (neg || l == P.root) ? -1 : l;
           }
+        } else {
+          // classify.assign_none (classify.py:32-51)
+          const int f = !nd ? -1
+                            : (kind == WK_KIND_NONE_ID
+                                   ? sv
+                                   : tab_get<STAGED>(P, stab, e, sv));
+          if (k == 1) {
+            result = f;
+          } else if (!(flags & WK_F_UNIQ)) {
+            uniqres = false;
+            if (live && nd) emit_frac<SINK>(P, K, e, samp, strat, f, k);
+          }
         }
         if (ishead && live && uniqres) {
           if (result >= 0)
-            emit_units(P, C, e, samp, strat, result, (uint32_t)WK_UNITS);
+            emit_units<SINK>(P, K, e, samp, strat, result, (uint32_t)WK_UNITS);
           else if (unas)
-            emit_units(P, C, e, samp, strat, NF, (uint32_t)WK_UNITS);
+            emit_units<SINK>(P, K, e, samp, strat, NF, (uint32_t)WK_UNITS);
         }
       }
-      cur += wend;
+      cur += cons;
     }
 
     __syncthreads();  // every warp is done with this stage
@@ -650,12 +716,21 @@ __global__ void __launch_bounds__(CLS_NT, 1)
     }
   }
 
-  // write the CTA's cached partial counts back (util.sum_dict, util.py:78-94)
-  if (C.log2n) {
+  // write the CTA's partial counts back (util.sum_dict, util.py:78-94)
+  if (SINK != SINK_GLOBAL) {
     __syncthreads();
-    for (uint32_t h = tid; h < (1u << C.log2n); h += CLS_NT) {
-      uint32_t tag = C.tag[h];
-      if (tag != CACHE_EMPTY && C.lo[h]) atomicAdd(&P.cnt[tag], (ull)C.lo[h]);
+    if (SINK == SINK_DIRECT) {
+      for (uint32_t h = tid; h < sink_words; h += CLS_NT) {
+        uint32_t v = (uint32_t)lds32(K.a0 + h * 4);
+        if (v) atomicAdd(&P.cnt[h], (ull)v);
+      }
+    } else {
+      const uint32_t slots = 1u << P.cache_log;
+      for (uint32_t h = tid; h < slots; h += CLS_NT) {
+        uint32_t tag = (uint32_t)lds32(K.a0 + h * 4);
+        uint32_t v = (uint32_t)lds32(K.a1 + h * 4);
+        if (tag != CACHE_EMPTY && v) atomicAdd(&P.cnt[tag], (ull)v);
+      }
     }
   }
 }

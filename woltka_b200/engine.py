@@ -94,7 +94,13 @@ class Engine:
 
     # -- plumbing ----------------------------------------------------------
     def set_stream(self, cuda_stream):
-        _lib.check(self.lib.wk_set_stream(self.ctx, C.c_void_p(cuda_stream or 0)))
+        """Run on an existing cudaStream_t handle; 0 means the legacy default
+        stream (torch's default), None restores the context's own stream."""
+        if cuda_stream is None:
+            handle = 0
+        else:
+            handle = int(cuda_stream) or 1   # cudaStreamLegacy == 0x1
+        _lib.check(self.lib.wk_set_stream(self.ctx, C.c_void_p(handle)))
 
     def sync(self):
         _lib.check(self.lib.wk_sync(self.ctx))
