@@ -475,7 +475,8 @@ __global__ void __launch_bounds__(CLS_NT, 1)
   const int64_t tab_bytes = STAGED ? (int64_t)P.E * P.Vp * 2 : 0;
   const ClsSmemLayout L =
       cls_layout(SINK, P.cache_log, P.direct_cells, tab_bytes);
-  const uint32_t sbase32 = smem_u32(smem);
+  uint32_t sbase32 = smem_u32(smem);
+  asm volatile("" : "+r"(sbase32));  // keep the window base in a register
   const uint32_t bars = sbase32 + L.bars;  // [STAGES] tiles, [STAGES] = tables
   const uint32_t tiles = sbase32 + L.tiles;
   const uint32_t stab = sbase32 + L.tab;
@@ -614,9 +615,20 @@ __global__ void __launch_bounds__(CLS_NT, 1)
         sv = ~lane;
       }
       // set semantics (align.py:339): a repeat has an equal subject on a
-      // lower lane of the same query
-      const unsigned mm = __match_any_sync(FULL, sv);
-      const bool nd = sv >= 0 && !(mm & segm & lt);
+      // lower lane of the same query.  Look back lane by lane with shuffles
+      // (match.any serialises on one unit per SM and was 80 % of the kernel):
+      // `reach` holds the lanes whose query extends at least m lanes back.
+      const unsigned cont = ~H & (FULL >> (32 - cons));  // non-head, active
+      bool dup = false;
+      {
+        unsigned reach = cont;
+        for (int m = 1; reach; ++m) {
+          const int o = __shfl_up_sync(FULL, sv, m);
+          if ((reach >> lane) & 1u) dup |= (o == sv);
+          reach &= cont << m;
+        }
+      }
+      const bool nd = sv >= 0 && !dup;
       const unsigned segnd = __ballot_sync(FULL, nd) & segm;
       const int k = __popc(segnd);
       const bool ishead = act && lane == sl;
@@ -645,8 +657,24 @@ __global__ void __launch_bounds__(CLS_NT, 1)
           result = th;
           if (neq) {  // some query of this window has differing taxa
             if (flags & WK_F_MAJOR) {
-              const unsigned tm = __match_any_sync(FULL, nd ? t : (-2 - lane));
-              const int c = nd ? __popc(tm & segnd) : 0;
+              // occurrences of my taxon among the query's distinct subjects
+              // (util.count_list, util.py:387-403): look both ways
+              int c = nd ? 1 : 0;
+              {
+                unsigned up = cont, dn = cont >> 1;
+                for (int m = 1; up | dn; ++m) {
+                  const int ou = __shfl_up_sync(FULL, t, m);
+                  const int od = __shfl_down_sync(FULL, t, m);
+                  if (nd && ((up >> lane) & 1u) &&
+                      ((segnd >> (lane - m)) & 1u) && ou == t)
+                    ++c;
+                  if (nd && ((dn >> lane) & 1u) &&
+                      ((segnd >> (lane + m)) & 1u) && od == t)
+                    ++c;
+                  up &= cont << m;
+                  dn &= cont >> (m + 1);
+                }
+              }
               int mx = c;
 #pragma unroll
               for (int off = 1; off < 32; off <<= 1) {
