@@ -172,9 +172,10 @@ int wk_ordinal_fetch_pairs(wk_ctx *ctx, int64_t *n_pairs, int32_t *read_idx,
 /* units[n_entries][n_samples][NF+1], in 1/WK_UNITS. */
 int wk_fetch_counts(wk_ctx *ctx, int64_t *units);
 /* Contributions 1/den with den not dividing WK_UNITS: cell = flat index into
- * the units table. Call with cell == NULL to get the count. */
-int wk_fetch_overflow(wk_ctx *ctx, int64_t *n, int64_t *cell, int32_t *den,
-                      int64_t cap);
+ * the units table (current dimensions), stratum = -1 unless stratified.
+ * Call with cell == NULL to get the count. */
+int wk_fetch_overflow(wk_ctx *ctx, int64_t *n, int64_t *cell, int32_t *stratum,
+                      int32_t *den, int64_t cap);
 /* Stratified counts: (entry, sample, stratum, feature) -> units. */
 int wk_fetch_strata(wk_ctx *ctx, int64_t *n, int32_t *entry, int32_t *sample,
                     int32_t *stratum, int64_t *feature, int64_t *units,

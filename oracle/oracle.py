@@ -68,7 +68,8 @@ def classify(q, s, *, parent=None, node_rank=None, root=-1, sub_node=None,
              sub_feat=None, kinds, target_rank=None, flags=0, major_th=0.0,
              subok=False, n_samples=1, n_features, q_sample=None,
              q_stratum=None, sample=0, n_threads=1):
-    """Returns (units[E,S,NF+1], overflow [(key, den)], strata {key: units})."""
+    """Returns (units[E,S,NF+1], overflow [(entry, sample, stratum|-1, feature,
+    den)], strata {(entry, sample, stratum, feature): units})."""
     q, s = _i32(q), _i32(s)
     keep = [_i32(parent), _i32(node_rank), _i32(sub_node), _i32(sub_feat),
             _i32(kinds), _i32(target_rank if target_rank is not None
@@ -100,13 +101,28 @@ def classify(q, s, *, parent=None, node_rank=None, root=-1, sub_node=None,
         C.cast(su, C.POINTER(C.c_int64)), (max(sn.value, 1),))[:sn.value].copy()
     for p_ in (ok, od, sk, su):
         lib().wko_free(p_)
+    # canonical, capacity-independent forms
+    NF1 = n_features + 1
+
+    def split(key):
+        cell = key & ((1 << 40) - 1)
+        es, f = divmod(cell, NF1)
+        return es // n_samples, es % n_samples, f
+
+    stratified = q_stratum is not None
     strata = {}
     if len(st_key):
         uk, inv = np.unique(st_key, return_inverse=True)
         tot = np.zeros(len(uk), dtype=np.int64)
         np.add.at(tot, inv, st_units)
-        strata = dict(zip(uk.tolist(), tot.tolist()))
-    overflow = sorted(zip(ovf_key.tolist(), ovf_den.tolist()))
+        for key, val in zip(uk.tolist(), tot.tolist()):
+            e, smp, f = split(key)
+            strata[(e, smp, key >> 40, f)] = val
+    overflow = []
+    for key, den in zip(ovf_key.tolist(), ovf_den.tolist()):
+        e, smp, f = split(key)
+        overflow.append((e, smp, (key >> 40) if stratified else -1, f, den))
+    overflow.sort()
     return units, overflow, strata
 
 

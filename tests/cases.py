@@ -102,16 +102,23 @@ def run_engine(eng, case, entries, flags, major_th, q, s, n_samples=1,
     cuts.append(n)
     for a, b in zip(cuts[:-1], cuts[1:]):
         eng.classify_chunk(q[a:b], s[a:b], q_sample, q_stratum, sample)
+    return collect(eng, n_samples, case.NF)
+
+
+def collect(eng, n_samples, NF):
+    """Engine results in the canonical form oracle.classify returns."""
     units = eng.fetch_counts()
-    ok, od = eng.fetch_overflow()
-    overflow = sorted(zip(ok.tolist(), od.tolist()))
+    cell, strat, den = eng.fetch_overflow()
+    NF1 = NF + 1
+    overflow = []
+    for c, t, d in zip(cell.tolist(), strat.tolist(), den.tolist()):
+        es, f = divmod(c, NF1)
+        overflow.append((es // n_samples, es % n_samples, t, f, d))
+    overflow.sort()
     strata = {}
-    if q_stratum is not None:
-        e, sm, st, f, u = eng.fetch_strata()
-        NF1 = case.NF + 1
-        for i in range(len(e)):
-            cell = (int(e[i]) * n_samples + int(sm[i])) * NF1 + int(f[i])
-            strata[(int(st[i]) << 40) | cell] = int(u[i])
+    e, sm, st, f, u = eng.fetch_strata()
+    for i in range(len(e)):
+        strata[(int(e[i]), int(sm[i]), int(st[i]), int(f[i]))] = int(u[i])
     return units, overflow, strata
 
 

@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Generate tests/golden/ by running the UNMODIFIED reference
+(/root/reference, woltka 0.1.7) in the build container.
+
+    python tests/golden/make_golden.py
+
+For every case it stores the inputs the product needs (alignment files copied
+or reduced from the reference's bundled test data, or produced by the seeded
+synthetic generator; the hierarchy as the dicts `build_hierarchy` returned,
+restricted to what the case can reach) and the reference's answer: the raw
+dict `woltka.workflow.classify()` returned and the same after
+`round_profiles`.  The GPU box has neither /root/reference nor biom-format,
+so tests only read these fixtures.
+
+`biom-format` is not installed here; `woltka.workflow` imports it for the
+table writers only, so a three-line stub module is put on sys.path.
+"""
+import bz2
+import copy
+import gzip
+import json
+import lzma
+import os
+import shutil
+import sys
+import tempfile
+from os.path import join, dirname, abspath, basename
+
+import numpy as np
+
+HERE = dirname(abspath(__file__))
+ROOT = dirname(dirname(HERE))
+REF = '/root/reference'
+DATA = join(REF, 'woltka', 'tests', 'data')
+OUT = join(HERE, 'data')
+sys.path.insert(0, ROOT)
+
+stub = tempfile.mkdtemp()
+os.makedirs(join(stub, 'biom'))
+with open(join(stub, 'biom', '__init__.py'), 'w') as f:
+    f.write('class Table: pass\n\ndef load_table(*a, **k): raise IOError\n')
+with open(join(stub, 'biom', 'util.py'), 'w') as f:
+    f.write('def biom_open(*a, **k): raise IOError\n')
+sys.path.insert(0, stub)
+sys.path.insert(0, REF)
+os.environ.setdefault('PYTHONDONTWRITEBYTECODE', '1')
+sys.dont_write_bytecode = True
+
+from woltka import workflow as W          # noqa: E402
+from woltka.file import readzip           # noqa: E402
+from woltka_b200 import synth             # noqa: E402
+
+
+def openany(fp, mode='rt'):
+    if fp.endswith('.xz'):
+        return lzma.open(fp, mode)
+    if fp.endswith('.bz2'):
+        return bz2.open(fp, mode)
+    if fp.endswith('.gz'):
+        return gzip.open(fp, mode)
+    return open(fp, mode.replace('t', ''))
+
+
+def reduce_sam(src, dst):
+    """Keep the six columns the readers use (align.py:376); drop the rest."""
+    with openany(src) as fi, lzma.open(dst, 'wt') as fo:
+        for line in fi:
+            if line[0] == '@':
+                fo.write(line)
+                continue
+            x = line.rstrip('\n').split('\t')
+            fo.write('\t'.join(x[:6] + ['*', '0', '0', '*', '*']) + '\n')
+
+
+def copy_dir(src, dst, reduce=False):
+    os.makedirs(dst, exist_ok=True)
+    for fn in sorted(os.listdir(src)):
+        sp = join(src, fn)
+        if os.path.isdir(sp):
+            continue
+        if reduce and '.sam' in fn:
+            reduce_sam(sp, join(dst, fn))
+        else:
+            shutil.copyfile(sp, join(dst, fn))
+
+
+def closure(tree, seeds):
+    """Sub-tree holding every seed and all of its ancestors."""
+    keep = {}
+    for s in seeds:
+        cur = s
+        while cur in tree and cur not in keep:
+            keep[cur] = tree[cur]
+            if tree[cur] == cur or tree[cur] is None:
+                break
+            cur = tree[cur]
+    return keep
+
+
+def enc_key(k):
+    if isinstance(k, tuple):
+        return '\x1f'.join(k)
+    return '\x00' if k is None else k
+
+
+def enc(data):
+    return {rank: {enc_key(s): {enc_key(f): v for f, v in prof.items()}
+                   for s, prof in samples.items()}
+            for rank, samples in data.items()}
+
+
+def subjects_of(files, fmt=None, trimsub=None, mapper=None):
+    """All subject ids a plain alignment set can produce."""
+    from woltka.align import plain_mapper
+    subs = set()
+    for fp in files:
+        with readzip(fp, {}) as fh:
+            for _, subque in plain_mapper(fh, fmt=fmt, n=65536):
+                for ss in subque:
+                    subs.update(ss)
+    if trimsub:
+        subs = {x.rsplit(trimsub, 1)[0] for x in subs}
+    return subs
+
+
+CASES = []
+
+
+def run_case(name, input_rel, *, hier=None, ranks, coords_rel=None,
+             overlap=80, strata_rel=None, fmt=None, demux=None, samples=None,
+             trimsub=None, uniq=False, major=None, above=False, subok=False,
+             unasgd=False, exclude=None, chunk=None, note=''):
+    input_fp = join(OUT, input_rel)
+    samples_, files, demux_ = W.parse_samples(input_fp, None, samples, demux)
+    tree = rankdic = namedic = root = None
+    if hier:
+        tree, rankdic, namedic, root = W.build_hierarchy(**hier)
+    mapper, chunk_ = W.build_mapper(
+        join(OUT, coords_rel) if coords_rel else None, None, overlap, chunk,
+        {})
+    ranks_, _ = W.prepare_ranks(ranks, None, tree, rankdic)
+    stratmap = W.parse_strata(join(OUT, strata_rel), samples_) \
+        if strata_rel else None
+    excl = W.parse_exclude(exclude)
+    data = W.classify(mapper, files, samples_, fmt, demux_, trimsub, tree,
+                      rankdic, None, root, ranks_, None, None, uniq, major,
+                      above, subok, None, unasgd, stratmap, excl, chunk_, 1024,
+                      {}, None, None)
+    raw = copy.deepcopy(data)
+    W.round_profiles(data, None)
+    # hierarchy restricted to what this case can reach
+    tree_small = None
+    if tree is not None:
+        seeds = set()
+        for rank in raw.values():
+            for prof in rank.values():
+                for k in prof:
+                    seeds.update(k if isinstance(k, tuple) else (k,))
+        if coords_rel:
+            # every gene a read can match: take the subjects of a rank-none run
+            d2 = W.classify(mapper, files, samples_, fmt, demux_, trimsub,
+                            None, None, None, None, ['none'], None, None,
+                            False, None, False, False, None, False, None,
+                            excl, chunk_, 1024, {}, None, None)
+            for prof in d2['none'].values():
+                seeds.update(prof)
+        else:
+            flist = files if isinstance(files, list) else list(files)
+            seeds.update(subjects_of(flist, fmt, trimsub))
+        tree_small = closure(tree, seeds)
+    prefix = mapper.keywords['prefix'] if coords_rel else None
+    case = {
+        'name': name, 'note': note, 'input': input_rel,
+        'files': ({basename(k): v for k, v in files.items()}
+                  if isinstance(files, dict) else
+                  [basename(x) for x in files]),
+        'samples': samples_, 'demux': demux_, 'fmt': fmt, 'trimsub': trimsub,
+        'tree': tree_small,
+        'rankdic': ({k: v for k, v in rankdic.items() if k in tree_small}
+                    if tree_small is not None and rankdic else rankdic),
+        'root': root, 'ranks': ranks_, 'uniq': uniq, 'major': major,
+        'above': above, 'subok': subok, 'unasgd': unasgd,
+        'exclude': sorted(excl) if excl else None, 'coords': coords_rel,
+        'overlap': overlap, 'prefix': prefix, 'strata': strata_rel,
+        'chunk': chunk, 'expected_raw': enc(raw),
+        'expected_rounded': enc(data),
+    }
+    with open(join(HERE, f'{name}.json'), 'w') as f:
+        json.dump(case, f, sort_keys=True)
+    ncell = sum(len(p) for r in data.values() for p in r.values())
+    print(f'{name}: {ncell} cells')
+    CASES.append(name)
+
+
+def bundled():
+    tax = join(DATA, 'taxonomy')
+    fun = join(DATA, 'function')
+    copy_dir(join(DATA, 'align', 'bowtie2'), join(OUT, 'bowtie2'), True)
+    copy_dir(join(DATA, 'align', 'bt2sho'), join(OUT, 'bt2sho'), True)
+    copy_dir(join(DATA, 'align', 'blastn'), join(OUT, 'blastn'))
+    copy_dir(join(DATA, 'align', 'burst'), join(OUT, 'burst'))
+    copy_dir(join(DATA, 'align', 'burst', 'split'), join(OUT, 'split'))
+    copy_dir(join(DATA, 'output', 'burst.genus.map'),
+             join(OUT, 'burst.genus.map'))
+    nodes = dict(nodes_fps=[join(tax, 'nodes.dmp')],
+                 map_fps=[join(tax, 'taxid.map')],
+                 names_fps=[join(tax, 'names.dmp')])
+
+    # cfg1 of BASELINE.json; tests/test_cli.py:50-53, test_workflow.py:38-48
+    run_case('bowtie2_ogu', 'bowtie2', ranks=None,
+             note='woltka classify -i align/bowtie2 (bowtie2.ogu.tsv)')
+    run_case('bowtie2_free', 'bowtie2', hier=nodes, ranks='free',
+             note='bowtie2.free.tsv (tests/test_cli.py:55-61)')
+    run_case('blastn_species', join('blastn', 'mux.b6o.xz'),
+             hier=dict(lineage_fps=[join(tax, 'lineages.txt')]),
+             ranks='species',
+             note='blastn.species.tsv: demux + 22.5 % multi-hit fractions')
+    run_case('burst_genus', 'burst', hier=nodes, ranks='genus',
+             note='burst.genus.tsv (tests/test_cli.py:70-79)')
+    run_case('blastn_family', join('blastn', 'mux.b6o.xz'), hier=nodes,
+             ranks='family', note='blastn.family.percent.tsv before --frac')
+    run_case('bt2sho_phylo', 'bt2sho',
+             hier=dict(newick_fps=[join(DATA, 'tree.nwk')]), ranks='free',
+             subok=True, note='bt2sho.phylo.tsv: newick, free, --subok')
+    run_case('bt2sho_filt_ogu', 'bt2sho', ranks=None, exclude='G000215745',
+             note='bt2sho.filt.ogu.tsv: --exclude')
+    run_case('split_genus', 'split',
+             hier=dict(nodes_fps=[join(tax, 'nodes.dmp')],
+                       map_fps=[join(tax, 'nucl', 'nucl2tid.txt')],
+                       names_fps=[join(tax, 'names.dmp')]),
+             ranks='genus', trimsub='_', note='split.genus.tsv: --trim-sub')
+    # modes the bundled goldens do not cover, on bundled multi-hit data
+    for mode, kw in [('uniq', dict(uniq=True)), ('major80', dict(major=80)),
+                     ('major54', dict(major=54)), ('above', dict(above=True)),
+                     ('unasgd', dict(unasgd=True, uniq=True))]:
+        run_case(f'blastn_multi_{mode}', join('blastn', 'mux.b6o.xz'),
+                 hier=nodes, ranks='phylum,genus,species,none,free', **kw,
+                 note='multi-rank in one run')
+    run_case('blastn_multi_default', join('blastn', 'mux.b6o.xz'), hier=nodes,
+             ranks='phylum,genus,species,none,free',
+             samples='S01,S03', note='sample whitelist')
+
+    # ordinal: coordinates restricted to the contigs the reads hit
+    hit = subjects_of([join(OUT, 'burst', f) for f in
+                       sorted(os.listdir(join(OUT, 'burst')))]) | \
+        subjects_of([join(OUT, 'bowtie2', f) for f in
+                     sorted(os.listdir(join(OUT, 'bowtie2')))][:1])
+    with lzma.open(join(fun, 'coords.txt.xz'), 'rt') as fi, \
+            lzma.open(join(OUT, 'coords.txt.xz'), 'wt') as fo:
+        keep = False
+        for line in fi:
+            if line[0] in '>#':
+                keep = line[1:].strip() in hit
+            if keep:
+                fo.write(line)
+    fmaps = dict(map_fps=[join(fun, 'uniref', 'uniref.map.xz'),
+                          join(fun, 'go', 'process.tsv.xz')], map_rank=True)
+    run_case('burst_orf', 'burst', ranks=None, coords_rel='coords.txt.xz',
+             note='coord-match, gene table (cf. bowtie2.orf.tsv)')
+    run_case('burst_process', 'burst', hier=fmaps, ranks='process',
+             coords_rel='coords.txt.xz', note='burst.process.tsv')
+    run_case('burst_genus_process', 'burst', hier=fmaps, ranks='process',
+             coords_rel='coords.txt.xz', strata_rel='burst.genus.map',
+             note='burst.genus.process.tsv: ordinal + stratified')
+    run_case('burst_process_ov55', 'burst', hier=fmaps, ranks='process,none',
+             coords_rel='coords.txt.xz', overlap=55,
+             note='overlap 55: ceil(len*0.55) differs from exact arithmetic')
+    run_case('bowtie2_orf_s01', join('bowtie2', 'S01.sam.xz'), ranks=None,
+             coords_rel='coords.txt.xz', overlap=81,
+             note='SAM + CIGAR lengths, overlap 81')
+
+
+def synthetic():
+    """Modes and edge cases no bundled file has: SAM mates with multi-hits,
+    exact duplicate records, subjects missing from the tree, long queries."""
+    d = join(OUT, 'synth')
+    os.makedirs(d, exist_ok=True)
+    tax = synth.Taxonomy(seed=5, level_sizes=[1, 2, 6, 15, 40, 90, 200, 500],
+                         n_genomes=1200)
+    dt = join(OUT, 'synth_tax')
+    os.makedirs(dt, exist_ok=True)
+    tax.write_nodes_dmp(join(dt, 'nodes.dmp'))
+    tax.write_taxid_map(join(dt, 'taxid.map'))
+    rng = np.random.default_rng(77)
+    for si in range(3):
+        qn, sn, fl = [], [], []
+        for qi in range(6000):
+            k = min(rng.geometric(0.45), 16)
+            if qi % 997 == 0:
+                k = 40                       # long query (slow path, d > 16)
+            base = int(rng.integers(0, tax.n_genomes))
+            paired = rng.random() < 0.3
+            for j in range(k):
+                g = (base + int(rng.integers(0, 25)) * (j > 0)) % tax.n_genomes
+                sid = tax.genome_id(g) if rng.random() > 0.03 else f'X{g}'
+                flag = 0
+                if paired:
+                    flag = 64 if rng.random() < 0.5 else 128
+                qn.append(f'S{si}R{qi}')
+                sn.append(sid)
+                fl.append(flag)
+                if rng.random() < 0.04:      # exact duplicate record
+                    qn.append(qn[-1])
+                    sn.append(sid)
+                    fl.append(flag)
+        tmp = join(d, f'S{si}.sam')
+        synth.write_sam(tmp, qn, sn, flags=fl)
+        with open(tmp, 'rb') as fi, lzma.open(tmp + '.xz', 'wb') as fo:
+            shutil.copyfileobj(fi, fo)
+        os.remove(tmp)
+    hier = dict(nodes_fps=[join(dt, 'nodes.dmp')],
+                map_fps=[join(dt, 'taxid.map')])
+    for mode, kw in [('default', {}), ('uniq', dict(uniq=True)),
+                     ('major80', dict(major=80)), ('major54', dict(major=54)),
+                     ('major81', dict(major=81)), ('above', dict(above=True)),
+                     ('unasgd', dict(unasgd=True)),
+                     ('above_unasgd', dict(above=True, unasgd=True))]:
+        run_case(f'synth_{mode}', 'synth', hier=hier,
+                 ranks='phylum,genus,species,free,none', **kw,
+                 note='synthetic SAM: mates, duplicates, unknown subjects, '
+                      '40-hit queries')
+
+
+if __name__ == '__main__':
+    if os.path.isdir(OUT):
+        shutil.rmtree(OUT)
+    os.makedirs(OUT)
+    bundled()
+    synthetic()
+    with open(join(HERE, 'INDEX.json'), 'w') as f:
+        json.dump(CASES, f)
+    shutil.rmtree(stub)

@@ -52,7 +52,7 @@ SIGNATURES = {
                                     C.c_int32]),
     'wk_ordinal_fetch_pairs': (C.c_int, [_vp, _i64p, _vp, _vp, C.c_int64]),
     'wk_fetch_counts': (C.c_int, [_vp, _vp]),
-    'wk_fetch_overflow': (C.c_int, [_vp, _i64p, _vp, _vp, C.c_int64]),
+    'wk_fetch_overflow': (C.c_int, [_vp, _i64p, _vp, _vp, _vp, C.c_int64]),
     'wk_fetch_strata': (C.c_int, [_vp, _i64p, _vp, _vp, _vp, _vp, _vp,
                                   C.c_int64]),
     'wk_reset_counts': (C.c_int, [_vp]),

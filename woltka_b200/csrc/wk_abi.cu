@@ -167,6 +167,7 @@ struct wk_ctx {
   int64_t pair_cap = 0;
   int64_t last_pairs = 0;
   bool keep_pairs = false;
+  bool strata_keys = false;  // overflow list holds stratified keys
 
   ull *d_ovf_n() { return small.as<ull>() + 0; }
   ull *d_sh_used() { return small.as<ull>() + 1; }
@@ -456,6 +457,7 @@ int wk_reset_counts(wk_ctx *c) {
   size_t len = (size_t)c->E * c->S * (c->NF + 1);
   CK(cudaMemsetAsync(c->cnt.p, 0, len * 8, c->stream));
   CK(cudaMemsetAsync(c->small.p, 0, 64, c->stream));
+  c->strata_keys = false;
   if (c->sh_cap) {
     TRY(fill_u64(c, c->sh_keys.as<ull>(), c->sh_cap, ~0ull));
     TRY(fill_u64(c, c->sh_vals.as<ull>(), c->sh_cap, 0));
@@ -483,8 +485,11 @@ static int check_plan_ready(wk_ctx *c, bool strata) {
     return fail(WK_ERR_STATE, "plan needs a tree (wk_set_tree)");
   if (need_node && !c->have_sub_node)
     return fail(WK_ERR_STATE, "plan needs sub_node (wk_set_subjects)");
-  if (strata && (size_t)c->E * c->S * (c->NF + 1) >= (1ull << 40))
-    return fail(WK_ERR_ARG, "count space too large for strata keys");
+  if (strata && (c->S > (1 << 16) || c->NF >= (int64_t)KEY_F24))
+    return fail(WK_ERR_ARG,
+                "stratified counting supports at most 65536 samples and "
+                "2^24-2 features");
+  if (c->S > (1 << 20)) return fail(WK_ERR_ARG, "too many samples");
   return WK_OK;
 }
 
@@ -547,6 +552,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   P.r1 = r1;
   P.q_sample = dqsamp;
   P.q_stratum = dqstrat;
+  if (dqstrat) c->strata_keys = true;
   P.sample = sample;
   P.E = c->E;
   for (int e = 0; e < c->E; ++e) P.kind[e] = c->kind[e];
@@ -651,6 +657,8 @@ static int check_device_err(wk_ctx *c) {
     return fail(WK_ERR_CAPACITY, "strata hash table is full");
   if (err & ERR_PAIR_FULL)
     return fail(WK_ERR_CAPACITY, "read-gene pair buffer is full");
+  if (err & ERR_KEY_RANGE)
+    return fail(WK_ERR_ARG, "stratum index exceeds 2^21 - 1");
   return fail(WK_ERR_CUDA, "device error word %d", err);
 }
 
@@ -966,19 +974,38 @@ int wk_fetch_counts(wk_ctx *c, int64_t *units) {
   return WK_OK;
 }
 
-int wk_fetch_overflow(wk_ctx *c, int64_t *n, int64_t *cell, int32_t *den,
-                      int64_t cap) {
+int wk_fetch_overflow(wk_ctx *c, int64_t *n, int64_t *cell, int32_t *stratum,
+                      int32_t *den, int64_t cap) {
   if (!c || !n) return fail(WK_ERR_ARG, "bad arguments");
   TRY(use_device(c));
   ull cnt = 0;
   CK(cudaMemcpyAsync(&cnt, c->d_ovf_n(), 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   *n = (int64_t)cnt;
-  if (!cell || !den) return WK_OK;
+  if (!cell || !den || !stratum) return WK_OK;
   if (cap < (int64_t)cnt) return fail(WK_ERR_CAPACITY, "overflow output too small");
-  if (cnt) {
-    CK(cudaMemcpy(cell, c->ovf_key.p, cnt * 8, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(den, c->ovf_den.p, cnt * 4, cudaMemcpyDeviceToHost));
+  if (!cnt) return WK_OK;
+  std::vector<ull> keys(cnt);
+  CK(cudaMemcpy(keys.data(), c->ovf_key.p, cnt * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(den, c->ovf_den.p, cnt * 4, cudaMemcpyDeviceToHost));
+  const int64_t NF1 = c->NF + 1;
+  for (ull i = 0; i < cnt; ++i) {
+    ull key = keys[i];
+    int64_t e, samp, f;
+    if (c->strata_keys) {
+      stratum[i] = (int32_t)(key >> 43);
+      e = (key >> 40) & 7;
+      samp = (key >> 24) & 0xFFFF;
+      uint32_t f24 = (uint32_t)(key & KEY_F24);
+      f = f24 == KEY_F24 ? c->NF : (int64_t)f24;
+    } else {
+      stratum[i] = -1;
+      e = (int64_t)(key >> 52);
+      samp = (key >> 32) & 0xFFFFF;
+      uint32_t f32 = (uint32_t)key;
+      f = f32 == 0xFFFFFFFFu ? c->NF : (int64_t)f32;
+    }
+    cell[i] = (e * c->S + samp) * NF1 + f;
   }
   return WK_OK;
 }
@@ -1016,15 +1043,13 @@ int wk_fetch_strata(wk_ctx *c, int64_t *n, int32_t *entry, int32_t *sample,
   CK(cudaStreamSynchronize(c->stream));
   ok.release();
   ov.release();
-  const int64_t NF1 = c->NF + 1;
   for (ull i = 0; i < used; ++i) {
     ull key = hk[i];
-    int64_t cellv = (int64_t)(key & ((1ull << 40) - 1));
-    stratum[i] = (int32_t)(key >> 40);
-    feature[i] = cellv % NF1;
-    int64_t es = cellv / NF1;
-    sample[i] = (int32_t)(es % c->S);
-    entry[i] = (int32_t)(es / c->S);
+    stratum[i] = (int32_t)(key >> 43);
+    entry[i] = (int32_t)((key >> 40) & 7);
+    sample[i] = (int32_t)((key >> 24) & 0xFFFF);
+    uint32_t f24 = (uint32_t)(key & KEY_F24);
+    feature[i] = f24 == KEY_F24 ? c->NF : (int64_t)f24;
     units[i] = (int64_t)hv[i];
   }
   return WK_OK;

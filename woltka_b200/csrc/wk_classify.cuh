@@ -87,7 +87,7 @@ struct ClsParams {
 };
 
 enum { ERR_BAD_SUBJECT = 1, ERR_OVF_FULL = 2, ERR_HASH_FULL = 4,
-       ERR_PAIR_FULL = 8 };
+       ERR_PAIR_FULL = 8, ERR_KEY_RANGE = 16 };
 
 __constant__ uint32_t c_units[33] = {
     0,      720720, 360360, 240240, 180180, 144144, 120120, 102960, 90090,
@@ -189,6 +189,25 @@ __device__ __forceinline__ void strat_add(const ClsParams &P, ull key,
   atomicOr(P.err, ERR_HASH_FULL);
 }
 
+// Capacity-independent keys of the strata hash and of the overflow list (the
+// count table may be re-gridded between chunks, wk_resize_counts):
+//   stratified: stratum 21 bits | entry 3 | sample 16 | feature 24
+//   plain     : entry (bits 52+) | sample 20 bits | feature 32 bits
+// the 'Unassigned' column is the all-ones feature value.
+constexpr uint32_t KEY_F24 = 0xFFFFFFu;
+__device__ __forceinline__ ull pack_strat(const ClsParams &P, int strat, int e,
+                                          int samp, int64_t f) {
+  if ((unsigned)strat >= (1u << 21)) atomicOr(P.err, ERR_KEY_RANGE);
+  uint32_t f24 = f == P.NF1 - 1 ? KEY_F24 : (uint32_t)f;
+  return ((ull)(uint32_t)strat << 43) | ((ull)e << 40) |
+         ((ull)(uint32_t)samp << 24) | f24;
+}
+__device__ __forceinline__ ull pack_plain(const ClsParams &P, int e, int samp,
+                                          int64_t f) {
+  uint32_t f32 = f == P.NF1 - 1 ? 0xFFFFFFFFu : (uint32_t)f;
+  return ((ull)e << 52) | ((ull)(uint32_t)samp << 32) | f32;
+}
+
 // add `units` (< 2^32) to cell (e, samp, f)
 template <int SINK>
 __device__ __forceinline__ void emit_units(const ClsParams &P, const Sink &K,
@@ -216,7 +235,7 @@ __device__ __forceinline__ void emit_units(const ClsParams &P, const Sink &K,
       return;
     }
   } else if (P.q_stratum) {
-    strat_add(P, ((ull)(uint32_t)strat << 40) | (ull)cell, units);
+    strat_add(P, pack_strat(P, strat, e, samp, f), units);
     return;
   }
   atomicAdd(&P.cnt[cell], (ull)units);
@@ -235,9 +254,8 @@ __device__ __forceinline__ void emit_frac(const ClsParams &P, const Sink &K,
   }
   ull at = atomicAdd(P.ovf_n, 1ull);
   if ((int64_t)at < P.ovf_cap) {
-    int64_t cell = ((int64_t)e * P.S + samp) * P.NF1 + f;
-    P.ovf_key[at] =
-        P.q_stratum ? (int64_t)(((ull)(uint32_t)strat << 40) | (ull)cell) : cell;
+    P.ovf_key[at] = (int64_t)(P.q_stratum ? pack_strat(P, strat, e, samp, f)
+                                          : pack_plain(P, e, samp, f));
     P.ovf_den[at] = (int32_t)d;
   } else {
     atomicOr(P.err, ERR_OVF_FULL);

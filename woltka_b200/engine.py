@@ -214,15 +214,19 @@ class Engine:
         return out
 
     def fetch_overflow(self):
+        """(cell, stratum, den): shares 1/den that do not divide UNITS; cell is
+        the flat index into the units table, stratum -1 unless stratified."""
         n = C.c_int64()
         _lib.check(self.lib.wk_fetch_overflow(self.ctx, C.byref(n), None, None,
-                                              0))
-        key = np.empty(n.value, dtype=np.int64)
+                                              None, 0))
+        cell = np.empty(n.value, dtype=np.int64)
+        strat = np.empty(n.value, dtype=np.int32)
         den = np.empty(n.value, dtype=np.int32)
         if n.value:
             _lib.check(self.lib.wk_fetch_overflow(
-                self.ctx, C.byref(n), _ptr(key), _ptr(den), len(key)))
-        return key, den
+                self.ctx, C.byref(n), _ptr(cell), _ptr(strat), _ptr(den),
+                len(cell)))
+        return cell, strat, den
 
     def fetch_strata(self):
         """(entry, sample, stratum, feature, units) arrays."""

@@ -1,0 +1,316 @@
+"""String world <-> integer world for one `classify()` call.
+
+The reference keeps everything as Python str / set / dict
+(/root/reference/woltka/workflow.py:268-335).  The GPU engine wants dense
+int32 indices, so this module owns the vocabularies and the per-subject
+tables, converts `(qryque, subque)` chunks to SoA columns, and turns the
+device count tables back into `{rank: {sample: {feature: count}}}`.
+
+Index spaces (see include/woltka_b200.h):
+  subjects  first-seen order over the whole run (after --trim-sub)
+  features  tree nodes (breadth-first order) then subjects not in the tree;
+            the table has spare columns that are claimed as subjects appear
+  samples   first-seen order
+  strata    first-seen order of stratum labels
+"""
+from collections import Counter
+from fractions import Fraction
+
+import numpy as np
+
+from ._lib import (UNITS, MAX_ENTRIES, KIND_NONE, KIND_FREE, KIND_RANK,
+                   KIND_NONE_ID, F_UNIQ, F_ABOVE, F_MAJOR, F_UNASSIGNED)
+from .hierarchy import FlatTree
+
+_SEP = '_'
+
+
+def _split_sample(query):
+    """workflow.demultiplex (workflow.py:889-893): sample = text before the
+    first '_' when something follows it, else ''."""
+    left, _, right = query.partition(_SEP)
+    return (left, right) if right else ('', right or left)
+
+
+class Session:
+    def __init__(self, ranks, tree=None, rankdic=None, root=None, uniq=False,
+                 major=None, above=False, subok=False, unasgd=False,
+                 trimsub=None, engine_factory=None, device=0):
+        if engine_factory is None:
+            from .engine import Engine
+            engine_factory = Engine
+        self.ranks = list(ranks)
+        self.order = list(dict.fromkeys(self.ranks))   # unique, first-seen
+        self.mult = Counter(self.ranks)
+        self.trimsub = trimsub
+        self.subok = subok
+        self.ft = FlatTree.from_dicts(tree, rankdic, root) \
+            if tree is not None else None
+        self.T = self.ft.n_nodes if self.ft else 0
+
+        # how each entry is assigned (workflow.py:1017-1032)
+        self.kinds = []
+        for rank in self.order:
+            if rank is None or rank == 'none' or tree is None:
+                self.kinds.append(KIND_NONE_ID if tree is None else KIND_NONE)
+            elif rank == 'free':
+                self.kinds.append(KIND_FREE)
+            else:
+                self.kinds.append(KIND_RANK)
+        need_lca = any(k == KIND_FREE for k in self.kinds) or (
+            above and not major and any(k == KIND_RANK for k in self.kinds))
+        if need_lca and self.ft is not None and self.ft.n_roots > 1:
+            raise ValueError('Hierarchy has more than one root; run '
+                             'fill_root before LCA-based assignment.')
+        self.flags = ((F_UNIQ if uniq else 0) | (F_ABOVE if above else 0) |
+                      (F_MAJOR if major else 0) |
+                      (F_UNASSIGNED if unasgd else 0))
+        self.major_th = float(major) if major else 0.0
+
+        # vocabularies
+        self.sub_index = {}
+        self.sub_node = []
+        self.sub_feat = []
+        self.extra_names = []        # features beyond the tree
+        self.extra_index = {}
+        self.sample_index = {}
+        self.sample_names = []
+        self.stratum_index = {}
+        self.stratum_names = []
+        self.uses_strata = False
+        self._tab_rows = [[] for _ in self.order]
+        self._rank_tabs = [self.ft.anc_at_rank(r) if k == KIND_RANK else None
+                           for r, k in zip(self.order, self.kinds)]
+        self._dirty = True
+
+        # engines: groups of at most MAX_ENTRIES entries
+        self.NF_cap = self.T + 1024
+        self.S_cap = 8
+        self.groups = [list(range(i, min(i + MAX_ENTRIES, len(self.order))))
+                       for i in range(0, len(self.order), MAX_ENTRIES)]
+        self.engines = []
+        for grp in self.groups:
+            eng = engine_factory(device)
+            if self.ft is not None:
+                eng.set_tree(self.ft.parent, self.ft.root)
+            eng.set_plan(np.array([self.kinds[i] for i in grp], dtype=np.int32),
+                         self.flags, self.major_th, self.S_cap, self.NF_cap)
+            self.engines.append(eng)
+
+    def close(self):
+        for eng in self.engines:
+            eng.close()
+        self.engines = []
+
+    # -- vocabularies ------------------------------------------------------
+    def subject(self, name):
+        """Index of a subject string (after trimming), interning it."""
+        if self.trimsub:
+            name = name.rsplit(self.trimsub, 1)[0]   # workflow.py:840-841
+        idx = self.sub_index.get(name)
+        if idx is not None:
+            return idx
+        idx = self.sub_index[name] = len(self.sub_node)
+        node = self.ft.node_of(name) if self.ft else -1
+        if node >= 0:
+            feat = node
+        else:
+            feat = self.extra_index.get(name)
+            if feat is None:
+                feat = self.extra_index[name] = self.T + len(self.extra_names)
+                self.extra_names.append(name)
+        self.sub_node.append(node)
+        self.sub_feat.append(feat)
+        for e, kind in enumerate(self.kinds):
+            if kind == KIND_RANK:
+                v = int(self._rank_tabs[e][node]) if node >= 0 else -1
+            elif kind == KIND_FREE:
+                # single-hit result (classify.py:75)
+                v = feat if self.subok else (
+                    int(self.ft.parent[node]) if node >= 0 else -1)
+            else:
+                v = feat
+            self._tab_rows[e].append(v)
+        self._dirty = True
+        return idx
+
+    def sample(self, name):
+        idx = self.sample_index.get(name)
+        if idx is None:
+            idx = self.sample_index[name] = len(self.sample_names)
+            self.sample_names.append(name)
+        return idx
+
+    def stratum(self, name):
+        idx = self.stratum_index.get(name)
+        if idx is None:
+            idx = self.stratum_index[name] = len(self.stratum_names)
+            self.stratum_names.append(name)
+        return idx
+
+    def _sync_tables(self):
+        """Push grown vocabularies / tables to the device(s)."""
+        nf = self.T + len(self.extra_names)
+        ns = len(self.sample_names)
+        if nf > self.NF_cap or ns > self.S_cap:
+            while nf > self.NF_cap:
+                self.NF_cap = self.NF_cap * 2
+            while ns > self.S_cap:
+                self.S_cap *= 2
+            for eng in self.engines:
+                eng.resize_counts(self.S_cap, self.NF_cap)
+            self._dirty = True
+        if not self._dirty:
+            return
+        V = len(self.sub_node)
+        sub_node = np.asarray(self.sub_node, dtype=np.int32)
+        for grp, eng in zip(self.groups, self.engines):
+            if all(self.kinds[i] == KIND_NONE_ID for i in grp):
+                eng.set_subjects(None, None, V)
+                continue
+            tab = np.asarray([self._tab_rows[i] for i in grp],
+                             dtype=np.int32).reshape(len(grp), V)
+            eng.set_subjects(tab, sub_node if self.ft is not None else None, V)
+        self._dirty = False
+
+    # -- chunks -------------------------------------------------------------
+    def add_chunk(self, qryque, subque, demux, sample_name, samples=None,
+                  strata_of=None):
+        """One `(qryque, subque)` chunk of the mapper protocol
+        (workflow.py:304-335): demultiplex, intern, classify on the GPU.
+
+        strata_of(sample_name) -> dict read -> stratum label, or None.
+        Returns the number of queries in the chunk."""
+        q, s, q_sample, q_stratum = [], [], [], []
+        nq = 0
+        use_strata = strata_of is not None
+        for query, subjects in zip(qryque, subque):
+            if demux:
+                sname, read = _split_sample(query)
+                if samples is not None and sname not in samples:
+                    continue
+            else:
+                sname, read = sample_name, query
+            stratum = 0
+            if use_strata:
+                label = strata_of(sname).get(read)
+                # counter_strat skips reads without a stratum but the sample
+                # still gets its (possibly empty) profile (workflow.py:1058)
+                stratum = self.stratum(label) if label is not None else -1
+            q_sample.append(self.sample(sname))
+            q_stratum.append(stratum)
+            for sub in subjects:
+                q.append(nq)
+                s.append(self.subject(sub))
+            nq += 1
+        if not q:
+            return
+        self.uses_strata = self.uses_strata or use_strata
+        self._sync_tables()
+        q = np.asarray(q, dtype=np.int32)
+        s = np.asarray(s, dtype=np.int32)
+        q_sample = np.asarray(q_sample, dtype=np.int32)
+        q_stratum = np.asarray(q_stratum, dtype=np.int32) if use_strata \
+            else None
+        for eng in self.engines:
+            eng.classify_chunk(q, s, q_sample, q_stratum)
+
+    def add_ordinal_chunk(self, genes, qnames, contigs, beg, end, length, th,
+                          demux, sample_name, samples=None, strata_of=None):
+        """One chunk of alignment records with coordinates: reads are matched
+        to genes and classified on the GPU (ordinal.py:167-335 followed by
+        workflow.py:304-335).  `qnames`/`contigs` are per-record strings."""
+        use_strata = strata_of is not None
+        qindex = {}
+        q = np.empty(len(qnames), dtype=np.int32)
+        q_sample, q_stratum = [], []
+        keep = np.ones(len(qnames), dtype=bool)
+        for i, query in enumerate(qnames):
+            j = qindex.get(query)
+            if j is None:
+                j = qindex[query] = len(q_sample)
+                if demux:
+                    sname, read = _split_sample(query)
+                    if samples is not None and sname not in samples:
+                        sname = None
+                else:
+                    sname, read = sample_name, query
+                if sname is None and demux:
+                    q_sample.append(-1)
+                    q_stratum.append(-1)
+                else:
+                    stratum = 0
+                    if use_strata:
+                        label = strata_of(sname).get(read)
+                        stratum = self.stratum(label) \
+                            if label is not None else -1
+                    q_sample.append(self.sample(sname))
+                    q_stratum.append(stratum)
+            q[i] = j
+        if not len(q):
+            return
+        # ordinal.py:332 merges equal query names anywhere in the chunk: make
+        # the records of one query contiguous
+        order = None
+        if np.any(np.diff(q) < 0):
+            order = np.argsort(q, kind='stable')
+        cidx = np.asarray([genes.contig_index.get(c, -1) for c in contigs],
+                          dtype=np.int32)
+        cols = [q, cidx, np.asarray(beg, dtype=np.int32),
+                np.asarray(end, dtype=np.int32),
+                np.asarray(length, dtype=np.int32)]
+        if order is not None:
+            cols = [c[order] for c in cols]
+        self.uses_strata = self.uses_strata or use_strata
+        genes.bind(self)
+        self._sync_tables()
+        q_sample = np.asarray(q_sample, dtype=np.int32)
+        q_stratum = np.asarray(q_stratum, dtype=np.int32) if use_strata \
+            else None
+        for eng in self.engines:
+            eng.ordinal_chunk(*cols, th, q_sample, q_stratum)
+
+    # -- results --------------------------------------------------------------
+    def feature_name(self, f):
+        if f == self.NF_cap:
+            return 'Unassigned'
+        if f < self.T:
+            return self.ft.ids[f]
+        return self.extra_names[f - self.T]
+
+    def results(self):
+        """{rank: {sample: {feature | (stratum, feature): count}}} with exact
+        counts: int when integral, else the correctly rounded double."""
+        data = {rank: {} for rank in self.order}
+        for rank in self.order:
+            for sname in self.sample_names:
+                data[rank][sname] = {}
+        NF1 = self.NF_cap + 1
+        for grp, eng in zip(self.groups, self.engines):
+            cells = {}    # (e, sample, stratum | None, feature) -> Fraction
+            ocell, ostrat, oden = eng.fetch_overflow()
+            if self.uses_strata:
+                e_, s_, t_, f_, u_ = eng.fetch_strata()
+                for e, s, t, f, u in zip(e_.tolist(), s_.tolist(), t_.tolist(),
+                                         f_.tolist(), u_.tolist()):
+                    cells[(e, s, t, f)] = Fraction(u, UNITS)
+            else:
+                units = eng.fetch_counts()
+                for e, s, f in zip(*np.nonzero(units)):
+                    cells[(int(e), int(s), None, int(f))] = Fraction(
+                        int(units[e, s, f]), UNITS)
+            for cell, t, den in zip(ocell.tolist(), ostrat.tolist(),
+                                    oden.tolist()):
+                es, f = divmod(cell, NF1)
+                k = (es // self.S_cap, es % self.S_cap,
+                     t if self.uses_strata else None, f)
+                cells[k] = cells.get(k, 0) + Fraction(1, den)
+            for (e, s, t, f), v in cells.items():
+                rank = self.order[grp[e]]
+                v = v * self.mult[rank]
+                val = int(v) if v.denominator == 1 else float(v)
+                name = self.feature_name(f)
+                if t is not None:
+                    name = (self.stratum_names[t], name)
+                data[rank][self.sample_names[s]][name] = val
+        return data

@@ -1,0 +1,171 @@
+"""Drop-in replacements for the two seams of the reference's classify path:
+
+    build_mapper(coords_fp, outcov_dir, overlap, chunk, zippers)
+    classify(mapper, files, samples, fmt, demux, trimsub, tree, rankdic,
+             namedic, root, ranks, rank2dir, outzip, uniq, major, above,
+             subok, sizes, unasgd, stratmap, exclude, chunk, cache, zippers,
+             outcov_dir, outcov_fmt) -> {rank: {sample: {feature: count}}}
+
+(/root/reference/woltka/workflow.py:536-585 and :162-353; same names,
+argument meaning, defaults and error texts.)  The per-chunk body of the
+reference — demultiplex, strip_suffix, one assigner + counter per rank,
+sum_dict — runs on the GPU through woltka_b200.session / the C-ABI; there is
+no CPU fallback.  Everything around it (sample discovery, hierarchy readers,
+frac/scale/round, table writers) is the reference's own code and is called
+unchanged by its `workflow()`.
+
+Not re-implemented in this round (rows F3-F5 of SURVEY.md §8f): read-map
+output (`rank2dir`), size-weighted counting (`sizes`) and coverage
+(`outcov_dir`) raise NotImplementedError instead of silently falling back.
+"""
+import bz2
+import gzip
+import lzma
+import sys
+from functools import partial
+from os.path import basename
+
+from .align import plain_mapper
+from .ordinal import load_gene_coords, ordinal_mapper, GeneIndex, iter_records
+from .session import Session
+
+__all__ = ['classify', 'build_mapper', 'readzip']
+
+_OPENERS = {'.gz': gzip.open, '.bz2': bz2.open, '.xz': lzma.open,
+            '.lzma': lzma.open}
+
+
+def readzip(fp, zippers=None):
+    """Text handle on a plain or gz/bz2/xz-compressed file (file.py:62-129;
+    `zippers` is accepted for signature compatibility — decompression is done
+    in-process)."""
+    for ext, opener in _OPENERS.items():
+        if fp.endswith(ext):
+            return opener(fp, 'rt')
+    return open(fp, 'r')
+
+
+def _echo(msg, nl=True):
+    sys.stdout.write(msg + ('\n' if nl else ''))
+    sys.stdout.flush()
+
+
+def build_mapper(coords_fp=None, outcov_dir=None, overlap=None, chunk=None,
+                 zippers=None):
+    """Plain or ordinal mapper and its chunk size (workflow.py:536-585)."""
+    if coords_fp:
+        _echo('Reading gene coordinates...', nl=False)
+        with readzip(coords_fp, zippers) as fh:
+            coords, idmap, prefix = load_gene_coords(fh, sort=True)
+        _echo(' Done.')
+        _echo(f'  Total number of host sequences: {len(coords)}.')
+        chunk = chunk or 2 ** 20
+        return partial(ordinal_mapper, coords=coords, idmap=idmap,
+                       prefix=prefix, th=overlap and overlap / 100), chunk
+    if outcov_dir:
+        raise NotImplementedError(
+            'Subject coverage (--outcov) is not part of the GPU hot path.')
+    return plain_mapper, chunk or 1024
+
+
+def _read_strata(fp, zippers=None):
+    """Read-to-stratum map of one sample (workflow.py:912-938 with
+    file.read_map_uniq, file.py:368-385: only two-column lines count)."""
+    strata = {}
+    with readzip(fp, zippers) as fh:
+        for line in fh:
+            key, found, value = line.partition('\t')
+            if found and '\t' not in value:
+                strata[key] = value.rstrip()
+    if not strata:
+        raise ValueError('No stratification information is found in file: '
+                         f'{basename(fp)}.')
+    return strata
+
+
+def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
+             tree=None, rankdic=None, namedic=None, root=None, ranks=None,
+             rank2dir=None, outzip=None, uniq=False, major=None, above=False,
+             subok=False, sizes=None, unasgd=False, stratmap=None,
+             exclude=None, chunk=None, cache=1024, zippers=None,
+             outcov_dir=None, outcov_fmt=None, _engine_factory=None,
+             _device=0):
+    """Core of the classification workflow (workflow.py:162-353) on the GPU.
+
+    `cache` (LRU size of the reference's assigners) has no effect on results
+    and is ignored.  Counts are exact: integers where the reference holds
+    integers, and the correctly rounded value of the exact rational sum where
+    the reference accumulates 1/k shares in floating point; after
+    `round_profiles` the two are identical.
+    """
+    if rank2dir is not None:
+        raise NotImplementedError(
+            'Read-map output (--outmap) is not part of the GPU hot path yet.')
+    if sizes:
+        raise NotImplementedError(
+            'Size-normalised counting (--sizes) is not part of the GPU hot '
+            'path yet.')
+    if outcov_dir:
+        raise NotImplementedError(
+            'Subject coverage (--outcov) is not part of the GPU hot path.')
+
+    is_ordinal = getattr(mapper, 'func', None) is ordinal_mapper
+    genes = None
+    if is_ordinal:
+        kw = mapper.keywords
+        genes = GeneIndex(kw['coords'], kw['idmap'], kw.get('prefix', False))
+        th = kw.get('th', 0.8)
+
+    sess = Session(ranks, tree, rankdic, root, uniq, major and major / 100,
+                   above, subok, unasgd, trimsub, _engine_factory, _device)
+    samset = set(samples) if samples else None
+    strata_cache = {}
+
+    def strata_of(sname):
+        try:
+            return strata_cache[sname]
+        except KeyError:
+            st = strata_cache[sname] = _read_strata(stratmap[sname], zippers)
+            return st
+
+    try:
+        for fp in sorted(files):
+            if fp == '-':
+                fileobj = sys.stdin
+                _echo('Parsing alignment from stdin ', nl=False)
+            else:
+                fileobj = readzip(fp, zippers)
+                _echo(f'Parsing alignment file {basename(fp)} ', nl=False)
+            sname = None if demux else (files[fp] if isinstance(files, dict)
+                                        else None)
+            kwargs = dict(demux=bool(demux), sample_name=sname,
+                          samples=samset if demux else None,
+                          strata_of=strata_of if stratmap else None)
+            nqry, nstep = 0, -1
+            try:
+                if is_ordinal:
+                    for qn, cn, bg, en, ln in iter_records(
+                            iter(fileobj), fmt, exclude, chunk or 2 ** 20):
+                        nqry += len(set(qn))
+                        sess.add_ordinal_chunk(genes, qn, cn, bg, en, ln, th,
+                                               **kwargs)
+                else:
+                    for qryque, subque in mapper(iter(fileobj), fmt=fmt,
+                                                 excl=exclude, n=chunk):
+                        nqry += len(qryque)
+                        sess.add_chunk(qryque, subque, **kwargs)
+                        istep = nqry // 1000000 - nstep
+                        if istep:
+                            _echo('.' * istep, nl=False)
+                            nstep += istep
+            finally:
+                if fileobj is not sys.stdin:
+                    fileobj.close()
+            _echo(' Done.')
+            _echo(f'  Number of sequences classified: {nqry}.')
+        _echo('Classification completed.')
+        data = sess.results()
+    finally:
+        sess.close()
+    # one (possibly empty) profile per requested rank, like workflow.py:268
+    return {rank: data[rank] for rank in dict.fromkeys(ranks)}
