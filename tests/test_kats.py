@@ -1,0 +1,178 @@
+"""Known answers of the reference's unit tests for the assign / count path
+(/root/reference/woltka/tests/test_classify.py, test_tree.py,
+test_workflow.py), driven through the drop-in classify()."""
+import os
+import tempfile
+
+import pytest
+
+from tests.oracle_engine import make_factory
+from woltka_b200.workflow import classify, build_mapper
+
+ENGINES = ['oracle', pytest.param('gpu', marks=pytest.mark.gpu)]
+
+TREE = {'G1': 'T1', 'G2': 'T1', 'G3': 'T2', 'T1': 'T0', 'T2': 'T0',
+        'T0': 'T0'}
+
+
+def run(engine, queries, ranks, tree=None, rankdic=None, root=None,
+        sample='S1', **kw):
+    """queries: list of (name, iterable of subjects)."""
+    qryque = [q for q, _ in queries]
+    subque = [set(s) for _, s in queries]
+
+    def mapper(fh, fmt=None, excl=None, n=None):
+        yield qryque, subque
+
+    fd, path = tempfile.mkstemp()
+    os.close(fd)
+    try:
+        factory = make_factory(tree, rankdic, root, ranks,
+                               kw.get('subok', False)) \
+            if engine == 'oracle' else None
+        return classify(mapper, {path: sample}, tree=tree, rankdic=rankdic,
+                        root=root, ranks=ranks, _engine_factory=factory, **kw)
+    finally:
+        os.remove(path)
+
+
+@pytest.mark.parametrize('engine', ENGINES)
+def test_assign_readmap_kats(engine):
+    # tests/test_workflow.py:549-589
+    q = [('R1', ['G1']), ('R2', ['G1', 'G2']), ('R3', ['G2', 'G3'])]
+    assert run(engine, q, ['none'])['none']['S1'] == \
+        {'G1': 1.5, 'G2': 1.0, 'G3': 0.5}
+    assert run(engine, q, ['none'], uniq=True, unasgd=True)['none']['S1'] == \
+        {'G1': 1, 'Unassigned': 2}
+    assert run(engine, q, ['free'], tree=TREE)['free']['S1'] == \
+        {'T0': 1, 'T1': 2}
+    rankdic = {'T1': 'ko', 'T2': 'ko', 'T0': 'mo'}
+    assert run(engine, q, ['ko'], tree=TREE, rankdic=rankdic)['ko']['S1'] == \
+        {'T1': 2.5, 'T2': 0.5}
+
+
+@pytest.mark.parametrize('engine', ENGINES)
+def test_assign_free_kats(engine):
+    # tests/test_classify.py:42-66
+    kw = dict(tree=TREE, root='T0')
+    one = lambda subs, **k: run(engine, [('R', subs)], ['free'], **kw,
+                                **k)['free']['S1']
+    assert one(['G1', 'G2']) == {'T1': 1}
+    assert one(['G1', 'G2', 'G3']) == {}          # LCA is the root
+    assert one(['G1']) == {'T1': 1}
+    assert one(['G1'], subok=True) == {'G1': 1}
+    assert one(['Gx']) == {}                      # not in the tree
+    assert one(['Gx'], subok=True) == {'Gx': 1}
+    assert one(['T0']) == {'T0': 1}               # parent of root is root
+
+
+@pytest.mark.parametrize('engine', ENGINES)
+def test_assign_rank_kats(engine):
+    # tests/test_classify.py:68-107
+    rankdic = {'T1': 'general', 'T2': 'general', 'T0': 'marshal'}
+    kw = dict(tree=TREE, rankdic=rankdic, root='T0')
+    one = lambda subs, rank, **k: run(engine, [('R', subs)], [rank],
+                                      **{**kw, **k})[rank]['S1']
+    assert one(['G1', 'G2', 'G3'], 'marshal') == {'T0': 1}
+    assert one(['G1', 'G2'], 'general') == {'T1': 1}
+    assert one(['G1'], 'general') == {'T1': 1}
+    assert one(['G1', 'G2', 'G3'], 'admiral', uniq=True) == {}
+    assert one(['G1', 'G2', 'G3'], 'general', uniq=True) == {}
+    assert one(['G1', 'G2', 'G3'], 'general', major=60) == {'T1': 1}
+    assert one(['G1', 'G2', 'G3'], 'general', major=80) == {}
+    got = one(['G1', 'G2', 'G3'], 'general')
+    assert got.keys() == {'T1', 'T2'}
+    assert abs(got['T1'] - 2 / 3) < 1e-12 and abs(got['T2'] - 1 / 3) < 1e-12
+    assert one(['G1', 'G2', 'G3'], 'general', root=None, above=True) == \
+        {'T0': 1}
+    assert one(['G1', 'G2', 'G3'], 'general', above=True) == {}
+    assert one(['G1', 'G2', 'G3', 'Gx'], 'general', root=None,
+               above=True) == {}
+
+
+@pytest.mark.parametrize('engine', ENGINES)
+def test_counter_kats(engine):
+    # tests/test_classify.py:109-114: 1/k' per remaining occurrence
+    tree = {'G1': 'Ecoli', 'G4': 'Ecoli', 'G6': 'Ecoli', 'G2': 'Cdiff',
+            'G5': 'Cdiff', 'G3': 'Strep', 'Ecoli': 'root', 'Cdiff': 'root',
+            'Strep': 'root', 'root': 'root'}
+    rankdic = {'Ecoli': 'species', 'Cdiff': 'species', 'Strep': 'species'}
+    q = [('a', ['G1']), ('b', ['G2', 'G3']),
+         ('c', ['G3', 'G4', 'G5', 'G6', 'G7']), ('d', ['G4', 'G6']),
+         ('e', ['G7'])]
+    got = run(engine, q, ['species'], tree=tree, rankdic=rankdic,
+              root='root')['species']['S1']
+    assert got == {'Ecoli': 2.5, 'Cdiff': 0.75, 'Strep': 0.75}
+
+
+@pytest.mark.parametrize('engine', ENGINES)
+def test_demultiplex_and_strata_kats(engine):
+    # tests/test_workflow.py:513-547 (demultiplex), classify.py:216-249
+    q = [('S1_R1', ['G1']), ('S1_R2', ['G2']), ('S2_R1', ['G1', 'G2']),
+         ('R9', ['G3']), ('S3_', ['G3']), ('S1_R3', ['G1'])]
+    got = run(engine, q, ['none'], demux=True)['none']
+    assert got == {'S1': {'G1': 2, 'G2': 1}, 'S2': {'G1': 0.5, 'G2': 0.5},
+                   '': {'G3': 2}}
+    got = run(engine, q, ['none'], demux=True, samples=['S1', 'SX'])['none']
+    assert got == {'S1': {'G1': 2, 'G2': 1}}
+    # stratified: only reads present in the strata map count
+    d = tempfile.mkdtemp()
+    with open(os.path.join(d, 'S1.txt'), 'w') as f:
+        f.write('R1\tEsch\nR2\tEsch\tx\nR3\tShig\n')
+    with open(os.path.join(d, 'S2.txt'), 'w') as f:
+        f.write('R1\tEsch\n')
+    stratmap = {'S1': os.path.join(d, 'S1.txt'),
+                'S2': os.path.join(d, 'S2.txt')}
+    got = run(engine, q[:3] + q[5:], ['none'], demux=True,
+              stratmap=stratmap)['none']
+    assert got == {'S1': {('Esch', 'G1'): 1, ('Shig', 'G1'): 1},
+                   'S2': {('Esch', 'G1'): 0.5, ('Esch', 'G2'): 0.5}}
+
+
+def test_build_mapper_seams():
+    # tests/test_workflow.py:293-312
+    obs = build_mapper()
+    assert obs[0].__name__ == 'plain_mapper' and obs[1] == 1024
+    d = tempfile.mkdtemp()
+    fp = os.path.join(d, 'coords.txt')
+    with open(fp, 'w') as f:
+        f.write('>G1\n1\t10\t20\n2\t35\t50\n')
+    obs = build_mapper(fp)
+    assert obs[0].func.__name__ == 'ordinal_mapper' and obs[1] == 1048576
+    obs = build_mapper(fp, overlap=75, chunk=50000)
+    assert obs[0].keywords['th'] == 0.75 and obs[1] == 50000
+    assert set(obs[0].keywords) >= {'coords', 'idmap', 'prefix', 'th'}
+
+
+def test_gene_coords_encoding():
+    # tests/test_ordinal.py:358-400: bit layout of the endpoint codes
+    from woltka_b200.ordinal import load_gene_coords, GeneIndex
+    coords, idmap, isdup = load_gene_coords(
+        ('>n1', 'g1\t5\t29', 'g2\t33\t61', 'g3\t65\t94', 'gx\t108\t135'),
+        sort=True)
+    assert not isdup and idmap == {'n1': ['g1', 'g2', 'g3', 'gx']}
+    exp = [(5 - 1 << 24) + (1 << 22) + 0, (29 << 24) + (3 << 22) + 0,
+           (33 - 1 << 24) + (1 << 22) + 1, (61 << 24) + (3 << 22) + 1,
+           (65 - 1 << 24) + (1 << 22) + 2, (94 << 24) + (3 << 22) + 2,
+           (108 - 1 << 24) + (1 << 22) + 3, (135 << 24) + (3 << 22) + 3]
+    assert coords['n1'].tolist() == exp
+    gi = GeneIndex(coords, idmap, False)
+    assert gi.gbeg.tolist() == [4, 32, 64, 107]
+    assert gi.gend.tolist() == [29, 61, 94, 135]
+    # reversed coordinates, duplicate ids -> prefix, '##' headers ignored
+    coords, idmap, isdup = load_gene_coords(
+        ('##genome', '>n1', 'g1\t29\t5', '#n2', 'g1\t7\t9'), sort=True)
+    assert isdup and list(coords) == ['n1', 'n2']
+    gi = GeneIndex(coords, idmap, True)
+    assert gi.gene_ids == ['n1_g1', 'n2_g1'] and gi.gbeg.tolist() == [4, 6]
+    with pytest.raises(ValueError, match='No coordinate was read'):
+        load_gene_coords(())
+    with pytest.raises(ValueError, match='Cannot extract coordinates'):
+        load_gene_coords(('>n1', 'g1\t5'))
+
+
+def test_unsupported_options_are_loud():
+    with pytest.raises(NotImplementedError):
+        classify(None, [], ranks=['none'], rank2dir={})
+    with pytest.raises(NotImplementedError):
+        classify(None, [], ranks=['none'], sizes={'a': 1.0})

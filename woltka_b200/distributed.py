@@ -1,0 +1,36 @@
+"""Multi-GPU plumbing: one process per GPU, records sharded at query
+boundaries, ONE collective at the end.
+
+The reference has no parallel mode; its documented scale-out is "split the
+input, run independent jobs, `woltka merge` the tables"
+(/root/reference/doc/perform.md:70-92; tools.merge_wf sums cells).  Counts are
+additive over any partition of the queries, so the same holds here: each rank
+classifies its shard into its own units table and the tables are summed by
+one NCCL all-reduce over NVLink (int64, exact).
+"""
+import numpy as np
+
+
+def shard_bounds(qidx, world):
+    """Cut [0, n) into `world` contiguous ranges that never split a query
+    (all records of a query must be classified together, classify.py:81-127).
+    Returns world+1 offsets."""
+    qidx = np.asarray(qidx)
+    n = len(qidx)
+    cuts = [0]
+    for r in range(1, world):
+        c = max(n * r // world, cuts[-1])
+        while 0 < c < n and qidx[c] == qidx[c - 1]:
+            c += 1
+        cuts.append(c)
+    cuts.append(n)
+    return cuts
+
+
+def allreduce_counts(tensor):
+    """Sum the per-rank units tables in place (no-op for a single rank)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and \
+            dist.get_world_size() > 1:
+        dist.all_reduce(tensor, op=dist.ReduceOp.SUM)
+    return tensor
