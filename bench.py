@@ -48,6 +48,15 @@ def parse_args():
     return ap.parse_args()
 
 
+def host_threads():
+    """Host cores this process may use (torchrun exports OMP_NUM_THREADS=1,
+    which is not what the CPU arm should be limited to)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def peaks():
     fp = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     try:
@@ -136,7 +145,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle as O
-    threads = O.max_threads()
+    threads = host_threads()
     n = min(args.records, args.cpu_sample)
     if args.workload == 'cfg3':
         return run_reference_cfg3(args, threads)
@@ -327,7 +336,7 @@ def run_ours(args):
     parity = None
     if rank == 0 and not args.no_cpu:
         from oracle import oracle as O
-        threads = O.max_threads()
+        threads = host_threads()
         m = min(n, args.cpu_sample)
         # cut the sample at a query boundary
         qh = q[:m + 64].cpu().numpy()
@@ -340,10 +349,8 @@ def run_ours(args):
                                       sh[:m // 8], 1)
         eng.reset_counts()
         eng.classify_chunk(qh, sh)
-        gu = eng.fetch_counts()
-        ok_, od_ = eng.fetch_overflow()
-        parity = bool(np.array_equal(gu, eu)) and \
-            sorted(zip(ok_.tolist(), od_.tolist())) == eo
+        gu, go, _ = cases.collect(eng, 1, case.NF)
+        parity = bool(np.array_equal(gu, eu)) and go == eo
         cpu = {'value': m / dt, 'unit': UNIT, 'cores': threads,
                'kind': 'port',
                'sample': f'{m} records of the timed batch, C restatement '

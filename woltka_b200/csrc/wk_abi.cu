@@ -235,12 +235,18 @@ int wk_create(int device, wk_ctx **out) {
   TRY(c->ovf_den.reserve(c->ovf_cap * 4));
   {
     const void *variants[] = {
-        (const void *)classify_kernel<true, SINK_DIRECT>,
-        (const void *)classify_kernel<true, SINK_HASHED>,
-        (const void *)classify_kernel<true, SINK_GLOBAL>,
-        (const void *)classify_kernel<false, SINK_DIRECT>,
-        (const void *)classify_kernel<false, SINK_HASHED>,
-        (const void *)classify_kernel<false, SINK_GLOBAL>};
+        (const void *)classify_kernel<true, SINK_DIRECT, true>,
+        (const void *)classify_kernel<true, SINK_HASHED, true>,
+        (const void *)classify_kernel<true, SINK_GLOBAL, true>,
+        (const void *)classify_kernel<false, SINK_DIRECT, true>,
+        (const void *)classify_kernel<false, SINK_HASHED, true>,
+        (const void *)classify_kernel<false, SINK_GLOBAL, true>,
+        (const void *)classify_kernel<true, SINK_DIRECT, false>,
+        (const void *)classify_kernel<true, SINK_HASHED, false>,
+        (const void *)classify_kernel<true, SINK_GLOBAL, false>,
+        (const void *)classify_kernel<false, SINK_DIRECT, false>,
+        (const void *)classify_kernel<false, SINK_HASHED, false>,
+        (const void *)classify_kernel<false, SINK_GLOBAL, false>};
     for (const void *fn : variants)
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)c->smem_optin));
@@ -626,8 +632,14 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   if (n_tiles <= 0) return WK_OK;
   int grid = c->tune_grid > 0 ? c->tune_grid : c->sm_count;
   grid = (int)std::min<int64_t>(grid, n_tiles);
-#define WK_LAUNCH(ST, SK) \
-  classify_kernel<ST, SK><<<grid, CLS_NT, L.total, c->stream>>>(P)
+  const bool lean = c->E == 1 && c->kind[0] == WK_KIND_RANK && !dqsamp && !dqstrat;
+#define WK_LAUNCH(ST, SK)                                                    \
+  do {                                                                       \
+    if (lean)                                                                \
+      classify_kernel<ST, SK, true><<<grid, CLS_NT, L.total, c->stream>>>(P); \
+    else                                                                     \
+      classify_kernel<ST, SK, false><<<grid, CLS_NT, L.total, c->stream>>>(P); \
+  } while (0)
   if (staged) {
     if (sink == SINK_DIRECT) WK_LAUNCH(true, SINK_DIRECT);
     else if (sink == SINK_HASHED) WK_LAUNCH(true, SINK_HASHED);

@@ -485,7 +485,10 @@ __host__ __device__ inline ClsSmemLayout cls_layout(int sink, int cache_log,
   return L;
 }
 
-template <bool STAGED, int SINK>
+// LEAN: the plan is one RANK entry with a scalar sample and no strata (the
+// genus / species profile of one sample); the entry loop and the per-query
+// gathers are compiled out.
+template <bool STAGED, int SINK, bool LEAN>
 __global__ void __launch_bounds__(CLS_NT, 1)
     classify_kernel(const __grid_constant__ ClsParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -561,11 +564,16 @@ __global__ void __launch_bounds__(CLS_NT, 1)
   if (STAGED) mbar_wait(bars + 8 * CLS_STAGES, 0);
 
   const int64_t NF = P.NF1 - 1;
-  const uint32_t flags = P.flags;
+  uint32_t flags = P.flags;
+  int E = LEAN ? 1 : P.E;
+  int per_query = LEAN ? 0 : (P.q_sample || P.q_stratum);
+  int V32 = (int)P.V;
+  // the compiler otherwise re-reads these from the constant bank (or even
+  // recomputes them in 64-bit) inside the window loop to save registers
+  asm volatile("" : "+r"(flags), "+r"(E), "+r"(per_query), "+r"(V32));
   const bool unas = flags & WK_F_UNASSIGNED;
-  const int E = P.E;
   const unsigned le = FULL >> (31 - lane), lt = le >> 1;
-  const bool per_query = P.q_sample || P.q_stratum;
+  const unsigned mybit = 1u << lane;
 
   int it = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -586,10 +594,25 @@ __global__ void __launch_bounds__(CLS_NT, 1)
       int64_t lim1 = r1 - sbase;
       if (lim1 < w1) w1 = (int)lim1;
     }
+    int nrel_r = nrel;
+    asm volatile("" : "+r"(w1), "+r"(nrel_r));
     // first own head: the record after the first tail at or after w0 - 1
     int cur = w0;
-    bool seek = (sbase + w0) > 0;
-    if (seek) --cur;
+    if (sbase + w0 > 0) {
+      --cur;
+      while (cur < w1) {
+        const int x = cur + lane;
+        const uint32_t ax = aq + (uint32_t)x * 4u;
+        bool tail = lds32(ax) != lds32(ax + 4);
+        if (!full) tail = (x < nrel_r) && (x + 1 >= nrel_r || tail);
+        const unsigned T = __ballot_sync(FULL, tail);
+        if (T) {
+          cur += __ffs(T);
+          break;
+        }
+        cur += 32;
+      }
+    }
 
     while (cur < w1) {
       const int x = cur + lane;
@@ -597,17 +620,8 @@ __global__ void __launch_bounds__(CLS_NT, 1)
       const int qa = lds32(ax);
       const int qb = lds32(ax + 4);
       bool tail = qa != qb;
-      if (!full) tail = (x < nrel) && (x + 1 >= nrel || tail);
+      if (!full) tail = (x < nrel_r) && (x + 1 >= nrel_r || tail);
       const unsigned T = __ballot_sync(FULL, tail);
-      if (seek) {
-        if (T) {
-          cur += __ffs(T);
-          seek = false;
-        } else {
-          cur += 32;
-        }
-        continue;
-      }
       // whole queries among lanes [0, cons); a query belongs to the warp
       // whose sub-range holds its head
       const int lim = w1 - cur;
@@ -628,7 +642,7 @@ __global__ void __launch_bounds__(CLS_NT, 1)
       const int se = __ffs(Tl & ~lt);              // one past its last lane
       const unsigned segm = act ? ((FULL << sl) & (FULL >> (32 - se))) : 0u;
       int sv = act ? lds32(as + (uint32_t)x * 4u) : ~lane;
-      if (act && (unsigned)sv >= (unsigned)P.V) {
+      if (act && (unsigned)sv >= (unsigned)V32) {
         atomicOr(P.err, ERR_BAD_SUBJECT);
         sv = ~lane;
       }
@@ -637,16 +651,16 @@ __global__ void __launch_bounds__(CLS_NT, 1)
       // (match.any serialises on one unit per SM and was 80 % of the kernel):
       // `reach` holds the lanes whose query extends at least m lanes back.
       const unsigned cont = ~H & (FULL >> (32 - cons));  // non-head, active
-      bool dup = false;
+      unsigned dupm = 0;
       {
         unsigned reach = cont;
         for (int m = 1; reach; ++m) {
           const int o = __shfl_up_sync(FULL, sv, m);
-          if ((reach >> lane) & 1u) dup |= (o == sv);
+          dupm |= (o == sv) ? reach : 0u;
           reach &= cont << m;
         }
       }
-      const bool nd = sv >= 0 && !dup;
+      const bool nd = sv >= 0 && !(dupm & mybit);
       const unsigned segnd = __ballot_sync(FULL, nd) & segm;
       const int k = __popc(segnd);
       const bool ishead = act && lane == sl;
@@ -663,7 +677,7 @@ __global__ void __launch_bounds__(CLS_NT, 1)
       const bool live = act && strat >= 0 && (unsigned)samp < (unsigned)P.S;
 
       for (int e = 0; e < E; ++e) {
-        const int kind = P.kind[e];
+        const int kind = LEAN ? (int)WK_KIND_RANK : P.kind[e];
         int result = -1;
         bool uniqres = true;
         if (kind == WK_KIND_RANK) {
