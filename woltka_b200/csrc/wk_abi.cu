@@ -159,7 +159,9 @@ struct wk_ctx {
   DevBuf dq, ds, dqsamp, dqstrat, scratch;
   DevBuf dcontig, dbeg, dend, dlen;
   // ordinal
-  DevBuf contig_off, genes, gene_subject, bin_off, bin_first;
+  DevBuf cinfo, genes, gene_subject;  // genes buffer = [genes | bin_first]
+  size_t bins_offset = 0, hot_bytes = 0;
+  size_t l2_window_max = 0;
   int32_t C = 0;
   int64_t G = 0;
   int shift = 0;
@@ -222,6 +224,11 @@ int wk_create(int device, wk_ctx **out) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   c->smem_optin = prop.sharedMemPerBlockOptin;
+  if (prop.persistingL2CacheMaxSize > 0) {
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize,
+                       (size_t)prop.persistingL2CacheMaxSize);
+    c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+  }
   CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
@@ -263,8 +270,7 @@ int wk_destroy(wk_ctx *c) {
                     &c->ovf_key, &c->ovf_den, &c->small, &c->sh_keys,
                     &c->sh_vals, &c->dq, &c->ds, &c->dqsamp, &c->dqstrat,
                     &c->scratch, &c->dcontig, &c->dbeg, &c->dend, &c->dlen,
-                    &c->contig_off, &c->genes, &c->gene_subject, &c->bin_off,
-                    &c->bin_first, &c->pair_q, &c->pair_s, &c->pair_r,
+                    &c->cinfo, &c->genes, &c->gene_subject, &c->pair_q, &c->pair_s, &c->pair_r,
                     &c->pair_g, &c->tile_desc, &c->ticket};
   for (DevBuf *b : bufs) b->release();
   for (int i = 0; i < 2; ++i)
@@ -632,7 +638,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   if (n_tiles <= 0) return WK_OK;
   int grid = c->tune_grid > 0 ? c->tune_grid : c->sm_count;
   grid = (int)std::min<int64_t>(grid, n_tiles);
-  const bool lean = c->E == 1 && c->kind[0] == WK_KIND_RANK && !dqsamp && !dqstrat;
+  const bool lean = c->E == 1 && !dqsamp && !dqstrat;
 #define WK_LAUNCH(ST, SK)                                                    \
   do {                                                                       \
     if (lean)                                                                \
@@ -792,9 +798,11 @@ int wk_ordinal_set_genes(wk_ctx *c, const int64_t *contig_off,
     }
     if (b > a) total_span += std::max(m, 0);
   }
+  // bin width: the first power of two >= the mean gene spacing (about one
+  // bin per gene, 4 B/bin next to 8 B/gene)
   double spacing = n_genes ? total_span / (double)n_genes : 1024.0;
   int shift = 4;
-  while (shift < 24 && (double)(2ll << shift) <= spacing) ++shift;
+  while (shift < 24 && (double)(1ll << shift) < spacing) ++shift;
   std::vector<int64_t> bin_off((size_t)n_contigs + 1, 0);
   for (int32_t ci = 0; ci < n_contigs; ++ci) {
     int64_t a = contig_off[ci], b = contig_off[ci + 1];
@@ -805,6 +813,7 @@ int wk_ordinal_set_genes(wk_ctx *c, const int64_t *contig_off,
   int64_t nbins = bin_off[n_contigs];
   if (nbins >= (1ll << 31)) return fail(WK_ERR_ARG, "too many coordinate bins");
   std::vector<int32_t> bin_first((size_t)std::max<int64_t>(nbins, 1));
+  std::vector<int4> cinfo((size_t)std::max(n_contigs, 1));
   for (int32_t ci = 0; ci < n_contigs; ++ci) {
     int64_t a = contig_off[ci], b = contig_off[ci + 1];
     int64_t nb = bin_off[ci + 1] - bin_off[ci];
@@ -814,22 +823,24 @@ int wk_ordinal_set_genes(wk_ctx *c, const int64_t *contig_off,
       while (g < b && (int64_t)pmax[g] < lo) ++g;
       bin_first[bin_off[ci] + k] = (int32_t)g;
     }
+    cinfo[ci] = make_int4((int)bin_off[ci], (int)nb, (int)b, 0);
   }
   std::vector<int2> genes((size_t)std::max<int64_t>(n_genes, 1));
   for (int64_t g = 0; g < n_genes; ++g) genes[g] = make_int2(gbeg[g], gend[g]);
 
   CK(cudaStreamSynchronize(c->stream));
-  TRY(c->contig_off.reserve(((size_t)n_contigs + 1) * 8));
-  TRY(c->bin_off.reserve(((size_t)n_contigs + 1) * 8));
-  TRY(c->genes.reserve(genes.size() * 8));
+  // one allocation [genes | bin_first]: the randomly accessed, L2-resident set
+  c->bins_offset = (genes.size() * 8 + 255) & ~(size_t)255;
+  c->hot_bytes = c->bins_offset + bin_first.size() * 4;
+  TRY(c->cinfo.reserve(cinfo.size() * 16));
+  TRY(c->genes.reserve(c->hot_bytes));
   TRY(c->gene_subject.reserve((size_t)std::max<int64_t>(n_genes, 1) * 4));
-  TRY(c->bin_first.reserve(bin_first.size() * 4));
-  CK(cudaMemcpy(c->contig_off.p, contig_off, ((size_t)n_contigs + 1) * 8, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(c->bin_off.p, bin_off.data(), ((size_t)n_contigs + 1) * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->cinfo.p, cinfo.data(), cinfo.size() * 16, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->genes.p, genes.data(), (size_t)n_genes * 8, cudaMemcpyHostToDevice));
   if (n_genes)
     CK(cudaMemcpy(c->gene_subject.p, gene_subject, (size_t)n_genes * 4, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(c->bin_first.p, bin_first.data(), (size_t)nbins * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy((char *)c->genes.p + c->bins_offset, bin_first.data(),
+                (size_t)nbins * 4, cudaMemcpyHostToDevice));
   c->C = n_contigs;
   c->G = n_genes;
   c->shift = shift;
@@ -869,11 +880,11 @@ static int run_ordinal(wk_ctx *c, const int32_t *dq, const int32_t *dcontig,
     P.len = dlen;
     P.n = n_rec;
     P.th = th;
-    P.contig_off = c->contig_off.as<int64_t>();
+    P.cinfo = c->cinfo.as<int4>();
     P.genes = c->genes.as<int2>();
     P.gene_subject = c->gene_subject.as<int32_t>();
-    P.bin_off = c->bin_off.as<int64_t>();
-    P.bin_first = c->bin_first.as<int32_t>();
+    P.bin_first = reinterpret_cast<const int32_t *>(
+        (const char *)c->genes.p + c->bins_offset);
     P.shift = c->shift;
     P.C = c->C;
     P.pair_q = c->pair_q.as<int32_t>();
@@ -885,7 +896,28 @@ static int run_ordinal(wk_ctx *c, const int32_t *dq, const int32_t *dcontig,
     P.tile_desc = c->tile_desc.as<ull>();
     P.ticket = c->ticket.as<unsigned>();
     P.err = c->d_err();
-    ordinal_match_kernel<<<(unsigned)n_tiles, ORD_NT, 0, c->stream>>>(P);
+    {
+      // keep the gene table + bins persisting in L2, stream everything else
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)n_tiles);
+      cfg.blockDim = dim3(ORD_NT);
+      cfg.stream = c->stream;
+      cudaLaunchAttribute attr[1];
+      int nattr = 0;
+      if (c->l2_window_max && c->hot_bytes) {
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = c->genes.p;
+        attr[0].val.accessPolicyWindow.num_bytes =
+            std::min(c->hot_bytes, c->l2_window_max);
+        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        nattr = 1;
+      }
+      cfg.attrs = attr;
+      cfg.numAttrs = nattr;
+      CK(cudaLaunchKernelEx(&cfg, ordinal_match_kernel, P));
+    }
     c->launches++;
     CK(cudaGetLastError());
     if (classify)

@@ -41,9 +41,9 @@ typedef unsigned long long ull;
 constexpr int CLS_TILE = 4096;                 // records per tile
 constexpr int CLS_PRE = 4;                     // records staged before the tile
 constexpr int CLS_POST = 44;                   // halo after the tile (>= 34)
-constexpr int CLS_TBUF = CLS_TILE + CLS_PRE + CLS_POST;  // 4144 rec, 16 B multiple
+constexpr int CLS_TBUF = CLS_TILE + CLS_PRE + CLS_POST;  // 16 B multiple
 constexpr int CLS_STAGES = 3;
-constexpr int CLS_NT = 1024;                   // threads per CTA
+constexpr int CLS_NT = 1024;                   // threads per CTA (64 regs)
 constexpr int CLS_NW = CLS_NT / 32;
 constexpr int CLS_SUB = CLS_TILE / CLS_NW;     // records per warp per tile
 constexpr unsigned FULL = 0xffffffffu;
@@ -485,14 +485,16 @@ __host__ __device__ inline ClsSmemLayout cls_layout(int sink, int cache_log,
   return L;
 }
 
-// LEAN: the plan is one RANK entry with a scalar sample and no strata (the
-// genus / species profile of one sample); the entry loop and the per-query
+// LEAN: the plan is one entry with a scalar sample and no strata (the genus
+// profile or the gene table of one sample); the entry loop and the per-query
 // gathers are compiled out.
 template <bool STAGED, int SINK, bool LEAN>
 __global__ void __launch_bounds__(CLS_NT, 1)
     classify_kernel(const __grid_constant__ ClsParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  int lane = tid & 31;
+  asm volatile("" : "+r"(lane));  // S2R is slow: keep the lane id live
   const int64_t tab_bytes = STAGED ? (int64_t)P.E * P.Vp * 2 : 0;
   const ClsSmemLayout L =
       cls_layout(SINK, P.cache_log, P.direct_cells, tab_bytes);
@@ -571,6 +573,8 @@ __global__ void __launch_bounds__(CLS_NT, 1)
   // the compiler otherwise re-reads these from the constant bank (or even
   // recomputes them in 64-bit) inside the window loop to save registers
   asm volatile("" : "+r"(flags), "+r"(E), "+r"(per_query), "+r"(V32));
+  int kind0 = P.kind[0];
+  asm volatile("" : "+r"(kind0));
   const bool unas = flags & WK_F_UNASSIGNED;
   const unsigned le = FULL >> (31 - lane), lt = le >> 1;
   const unsigned mybit = 1u << lane;
@@ -677,7 +681,7 @@ __global__ void __launch_bounds__(CLS_NT, 1)
       const bool live = act && strat >= 0 && (unsigned)samp < (unsigned)P.S;
 
       for (int e = 0; e < E; ++e) {
-        const int kind = LEAN ? (int)WK_KIND_RANK : P.kind[e];
+        const int kind = LEAN ? kind0 : P.kind[e];
         int result = -1;
         bool uniqres = true;
         if (kind == WK_KIND_RANK) {

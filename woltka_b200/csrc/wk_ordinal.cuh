@@ -34,10 +34,9 @@ struct OrdParams {
   const int32_t *q, *contig, *beg, *end, *len;
   int64_t n;
   double th;
-  const int64_t *contig_off;   // [C+1] gene ranges
+  const int4 *cinfo;           // [C] (first bin, n bins, gene end, 0)
   const int2 *genes;           // [G] (gbeg, gend), sorted by gbeg per contig
   const int32_t *gene_subject; // [G]
-  const int64_t *bin_off;      // [C+1]
   const int32_t *bin_first;    // [sum bins]
   int32_t shift;
   int32_t C;
@@ -69,10 +68,10 @@ __device__ __forceinline__ ReadQ ord_prepare(const OrdParams &P, int c, int rb,
   int64_t L = (int64_t)(uint32_t)(long long)Lf;
   int64_t x = (int64_t)rb + L;  // a matching gene must end at or after x
   int64_t b = x <= 0 ? 0 : (x >> P.shift);
-  int64_t b0 = __ldg(P.bin_off + c), b1 = __ldg(P.bin_off + c + 1);
-  if (b >= b1 - b0) return r;
-  r.g0 = __ldg(P.bin_first + b0 + b);
-  r.g1 = (int32_t)__ldg(P.contig_off + c + 1);
+  const int4 ci = __ldg(P.cinfo + c);   // one 16-byte load per read
+  if (b >= ci.y) return r;
+  r.g0 = __ldg(P.bin_first + ci.x + (int)b);
+  r.g1 = ci.z;
   r.L = L;
   return r;
 }
@@ -128,16 +127,52 @@ __global__ void __launch_bounds__(ORD_NT)
   }
 
   ReadQ rq[ORD_ITEMS];
-  int cnt[ORD_ITEMS];
+  int cnt[ORD_ITEMS], mt[ORD_ITEMS][4];  // first four matches per read
   int tot = 0;
 #pragma unroll
   for (int j = 0; j < ORD_ITEMS; ++j)
     rq[j] = ord_prepare(P, cv[j], bv[j], ev[j], lv[j]);
+  // first four candidate genes of every read, all loads in flight together
+  // (the scan is otherwise a chain of dependent L2 round trips)
+  int2 cand[ORD_ITEMS][4];
+#pragma unroll
+  for (int j = 0; j < ORD_ITEMS; ++j)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int g = rq[j].g0 + u;
+      cand[j][u] = g < rq[j].g1 ? __ldg(P.genes + g) : make_int2(INT32_MAX, 0);
+    }
 #pragma unroll
   for (int j = 0; j < ORD_ITEMS; ++j) {
-    int c = 0;
-    ord_scan(P, rq[j], [&](int) { ++c; });
+    int c = 0, a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    auto hit = [&](int g) {
+      if (c == 0) a0 = g;
+      if (c == 1) a1 = g;
+      if (c == 2) a2 = g;
+      if (c == 3) a3 = g;
+      ++c;
+    };
+    const int64_t y = (int64_t)rq[j].re - rq[j].L;
+    bool more = rq[j].g0 < rq[j].g1;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int2 ge = cand[j][u];
+      if (more && (int64_t)ge.x > y) more = false;  // also ends at the pad
+      if (more) {
+        int64_t ov = (int64_t)min(ge.y, rq[j].re) - (int64_t)max(ge.x, rq[j].rb);
+        if (ov >= rq[j].L) hit(rq[j].g0 + u);
+      }
+    }
+    if (more && rq[j].g0 + 4 < rq[j].g1) {  // rare: keep scanning
+      ReadQ rest = rq[j];
+      rest.g0 += 4;
+      ord_scan(P, rest, hit);
+    }
     cnt[j] = c;
+    mt[j][0] = a0;
+    mt[j][1] = a1;
+    mt[j][2] = a2;
+    mt[j][3] = a3;
     tot += c;
   }
 
@@ -207,7 +242,7 @@ __global__ void __launch_bounds__(ORD_NT)
     if (!cnt[j]) continue;
     const int qq = qv[j];
     const int64_t ri = i0 + j;
-    ord_scan(P, rq[j], [&](int g) {
+    auto put = [&](int g) {
       P.pair_q[off] = qq;
       P.pair_s[off] = __ldg(P.gene_subject + g);
       if (P.pair_r) {
@@ -215,7 +250,14 @@ __global__ void __launch_bounds__(ORD_NT)
         P.pair_g[off] = g;
       }
       ++off;
-    });
+    };
+    if (cnt[j] <= 4) {  // the usual case: matches kept in registers
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (u < cnt[j]) put(mt[j][u]);
+    } else {
+      ord_scan(P, rq[j], put);
+    }
   }
 }
 
