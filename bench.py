@@ -57,6 +57,17 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def measured_traffic(kernel, records):
+    """DRAM bytes per launch from the committed `ncu --set full` capture
+    (profiles/traffic.json), valid for the same record count only."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            t = json.load(f)[kernel]
+        return t['bytes'] if t['records'] == records else None
+    except Exception:
+        return None
+
+
 def peaks():
     fp = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     try:
@@ -139,6 +150,40 @@ def cpu_classify(case, entries, flags, q, s, threads):
     return out, time.perf_counter() - t0
 
 
+def python_port_rate(case, entries, flags, q, s, m=200_000):
+    """Records/s of the pure-Python restatement (oracle/pyport.py: str / set
+    / dict like the reference) on the first m records of the batch."""
+    from oracle import pyport
+    from tests import cases as C
+    tax = case.tax
+    ids = tax.ids()
+    tree = {ids[i]: ids[tax.parent[i]] for i in range(tax.T)}
+    rankdic = {ids[i]: tax.rank_names[tax.node_rank[i]]
+               for i in range(tax.T) if tax.node_rank[i] >= 0}
+    m = min(m, len(q))
+    while 0 < m < len(q) and q[m] == q[m - 1]:
+        m += 1
+    gid = [tax.genome_id(g) for g in range(tax.n_genomes)]
+    qryque, subque, last = [], [], None
+    for qi, si in zip(q[:m].tolist(), s[:m].tolist()):
+        if qi != last:
+            qryque.append(f'R{qi}')
+            subque.append(set())
+            last = qi
+        subque[-1].add(gid[si])
+    chunks = [(qryque[i:i + 1024], subque[i:i + 1024])
+              for i in range(0, len(qryque), 1024)]
+    kw = dict(uniq=bool(flags & 1), above=bool(flags & 2),
+              major=0.8 if flags & 4 else None, unasgd=bool(flags & 8))
+    t0 = time.perf_counter()
+    pyport.classify_chunks(chunks, entries, tree, rankdic, ids[0],
+                           sample='S', **kw)
+    dt = time.perf_counter() - t0
+    return {'value': m / dt, 'unit': UNIT, 'cores': 1,
+            'sample': f'{m} records, oracle/pyport.py (pure Python, the '
+                      f'reference\'s data structures)'}
+
+
 def run_reference(args):
     """CPU arm: the oracle port of the reference's path, all host threads."""
     rank = int(os.environ.get('RANK', '0'))
@@ -171,7 +216,8 @@ def run_reference(args):
         'cpu_baseline': {
             'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port',
             'sample': f'{n} records of the same generator per step '
-                      f'(C restatement oracle/woltka_oracle.c, OpenMP)'},
+                      f'(C restatement oracle/woltka_oracle.c, OpenMP)',
+            'python_port': python_port_rate(case, entries, flags, q, s)},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -356,7 +402,8 @@ def run_ours(args):
                'sample': f'{m} records of the timed batch, C restatement '
                          f'of the reference path (oracle/woltka_oracle.c), '
                          f'{threads} OpenMP threads',
-               'single_thread_value': (m // 8) / dt1}
+               'single_thread_value': (m // 8) / dt1,
+               'python_port': python_port_rate(case, entries, flags, qh, sh)}
         assert parity, 'GPU result differs from the oracle on the sample'
 
     if rank == 0:
@@ -369,7 +416,10 @@ def run_ours(args):
             'data': 'synthetic', 'config': workload_config(args, entries),
             'roofline': {'bound': 'hbm', 'achieved': achieved,
                          'peak': hbm_peak, 'unit': 'GB/s',
-                         'frac': achieved / hbm_peak, 'traffic': None,
+                         'frac': achieved / hbm_peak,
+                         'traffic': measured_traffic(
+                             'classify_kernel:' + ','.join(entries) + ':' +
+                             args.mode, n),
                          'kernel': 'classify_kernel',
                          'kernel_ms': k_ms, 'peak_source': peak_src,
                          'algorithmic_bytes_per_record': bytes_per_rec},
@@ -491,7 +541,8 @@ def run_ours_cfg3(args, eng, dev, world, rank, barrier, hbm_peak, peak_src):
             'data': 'synthetic', 'config': workload_config(args, ['none']),
             'roofline': {'bound': 'hbm', 'achieved': achieved,
                          'peak': hbm_peak, 'unit': 'GB/s',
-                         'frac': achieved / hbm_peak, 'traffic': None,
+                         'frac': achieved / hbm_peak,
+                         'traffic': measured_traffic('ordinal:cfg3', n),
                          'kernel': 'ordinal_match_kernel+classify_kernel',
                          'kernel_ms': k_ms, 'peak_source': peak_src,
                          'algorithmic_bytes_per_record': 20,
