@@ -183,3 +183,62 @@ def test_carry_out_of_the_32bit_low_words(engine, small_case):
                   cases.run_oracle(small_case, ['genus'], 0, 0, q, s))
         finally:
             engine.set_tuning(0, 0, 0)
+
+
+def test_lca_on_a_tree_that_is_not_level_ordered(engine):
+    """parent[i] < i holds for a depth-first numbering too; the kernel then
+    falls back from the level-synchronous LCA to the pairwise climb."""
+    from oracle import oracle as O
+    from woltka_b200._lib import KIND_FREE, KIND_RANK, F_ABOVE
+    rng = np.random.default_rng(17)
+    T = 700
+    # random tree, then renumber in depth-first preorder
+    par0 = np.zeros(T, dtype=np.int64)
+    for i in range(1, T):
+        par0[i] = rng.integers(max(0, i - 40), i)
+    children = [[] for _ in range(T)]
+    for i in range(1, T):
+        children[par0[i]].append(i)
+    order, stack = [], [0]
+    while stack:
+        v = stack.pop()
+        order.append(v)
+        stack.extend(reversed(children[v]))
+    new = np.empty(T, dtype=np.int64)
+    new[order] = np.arange(T)
+    parent = np.zeros(T, dtype=np.int32)
+    for old in range(T):
+        parent[new[old]] = new[par0[old]]
+    depth = np.zeros(T, dtype=np.int64)
+    for i in range(1, T):
+        depth[i] = depth[parent[i]] + 1
+    assert np.any(np.diff(depth) < 0)          # really not level ordered
+    node_rank = (depth == 3).astype(np.int32) - 1   # rank 0 at depth 3
+    sub_node = np.arange(T, dtype=np.int32)
+    anc = np.full(T, -1, dtype=np.int32)
+    for i in range(T):
+        v = i
+        while True:
+            if node_rank[v] == 0:
+                anc[i] = v
+                break
+            if parent[v] == v:
+                break
+            v = parent[v]
+    nq = 20000
+    k = np.minimum(rng.geometric(0.4, nq), 12)
+    q = np.repeat(np.arange(nq, dtype=np.int32), k)
+    first = rng.integers(0, T, nq)
+    s = ((first[q] + rng.integers(0, 30, len(q))) % T).astype(np.int32)
+    par_tab = parent[sub_node]
+    kinds = np.array([KIND_FREE, KIND_RANK], dtype=np.int32)
+    tab = np.stack([par_tab, anc]).astype(np.int32)
+    engine.set_tree(parent, 0)
+    engine.set_plan(kinds, F_ABOVE, 0.0, 1, T)
+    engine.set_subjects(tab, sub_node)
+    engine.classify_chunk(q, s)
+    got = engine.fetch_counts()
+    exp, ovf, _ = O.classify(q, s, parent=parent, node_rank=node_rank, root=0,
+                             sub_node=sub_node, sub_feat=sub_node, kinds=kinds,
+                             target_rank=[0, 0], flags=F_ABOVE, n_features=T)
+    assert np.array_equal(got, exp)

@@ -149,6 +149,11 @@ struct wk_ctx {
   int64_t V = 0;
   int Vp = 0;
   bool tab16_ok = false, have_sub_node = false;
+  // host copies for (re)packing the shared-memory staging block
+  std::vector<int32_t> h_parent, h_tab, h_sub_node;
+  bool stage_dirty = true;
+  int32_t sn16_off = -1, par16_off = -1, stage_elems = 0;
+  int32_t n_levels = 0, level_off[40];
   // overflow + err
   DevBuf ovf_key, ovf_den, small;  // small: [0]=ovf_n [1]=sh_used [2]=n_pairs [3]=cursor, err after
   int64_t ovf_cap = 0;
@@ -336,6 +341,30 @@ int wk_set_tree(wk_ctx *c, const int32_t *parent, int32_t n_nodes,
   if (n_nodes)
     CK(cudaMemcpy(c->parent.p, parent, (size_t)n_nodes * 4,
                   cudaMemcpyHostToDevice));
+  c->h_parent.assign(parent, parent + n_nodes);
+  c->stage_dirty = true;
+  // level structure: usable when the nodes are numbered level by level
+  c->n_levels = 0;
+  {
+    std::vector<int32_t> depth((size_t)std::max(n_nodes, 1), 0);
+    bool ordered = true;
+    int32_t nl = 0;
+    for (int32_t i = 0; i < n_nodes && ordered; ++i) {
+      depth[i] = parent[i] == i ? 0 : depth[parent[i]] + 1;
+      if (i && depth[i] < depth[i - 1]) ordered = false;
+      if (!i || depth[i] != depth[i - 1]) {
+        if (depth[i] != nl || nl >= 39) {
+          ordered = false;
+          break;
+        }
+        c->level_off[nl++] = i;
+      }
+    }
+    if (ordered && n_nodes > 0) {
+      c->level_off[nl] = n_nodes;
+      c->n_levels = nl;
+    }
+  }
   c->T = n_nodes;
   c->root = root;
   return WK_OK;
@@ -367,6 +396,9 @@ int wk_set_plan(wk_ctx *c, const int32_t *kinds, int32_t n_entries,
   c->have_plan = true;
   c->V = 0;
   c->tab16_ok = false;
+  c->stage_dirty = true;
+  c->h_tab.clear();
+  c->h_sub_node.clear();
   return wk_reset_counts(c);
 }
 
@@ -415,6 +447,7 @@ int wk_set_subjects(wk_ctx *c, const int32_t *tab, const int32_t *sub_node,
   c->V = n_subjects;
   c->tab16_ok = false;
   c->have_sub_node = false;
+  c->stage_dirty = true;
   const int64_t V = n_subjects;
   if (tab && V) {
     const int64_t lim = c->NF;  // valid values are -1 or [0, NF)
@@ -432,23 +465,9 @@ int wk_set_subjects(wk_ctx *c, const int32_t *tab, const int32_t *sub_node,
     }
     TRY(c->tab.reserve((size_t)c->E * V * 4));
     CK(cudaMemcpy(c->tab.p, tab, (size_t)c->E * V * 4, cudaMemcpyHostToDevice));
-    // uint16 copy for shared-memory staging
-    int64_t Vp = (V + 7) & ~7ll;
-    if (need_tab && vmax < 0xFFFF && (size_t)c->E * Vp * 2 <= 200 * 1024) {
-      std::vector<uint16_t> t16((size_t)c->E * Vp, 0xFFFF);
-      for (int e = 0; e < c->E; ++e) {
-        if (c->kind[e] == WK_KIND_NONE_ID) continue;
-        for (int64_t i = 0; i < V; ++i) {
-          int32_t v = tab[(size_t)e * V + i];
-          t16[(size_t)e * Vp + i] = v < 0 ? 0xFFFF : (uint16_t)v;
-        }
-      }
-      TRY(c->tab16.reserve(t16.size() * 2 + 16));
-      CK(cudaMemcpy(c->tab16.p, t16.data(), t16.size() * 2,
-                    cudaMemcpyHostToDevice));
-      c->Vp = (int)Vp;
-      c->tab16_ok = true;
-    }
+    c->h_tab.assign(tab, tab + (size_t)c->E * V);
+  } else {
+    c->h_tab.clear();
   }
   if (sub_node && V) {
     for (int64_t i = 0; i < V; ++i)
@@ -459,7 +478,11 @@ int wk_set_subjects(wk_ctx *c, const int32_t *tab, const int32_t *sub_node,
     CK(cudaMemcpy(c->sub_node.p, sub_node, (size_t)V * 4,
                   cudaMemcpyHostToDevice));
     c->have_sub_node = true;
+    c->h_sub_node.assign(sub_node, sub_node + V);
+  } else {
+    c->h_sub_node.clear();
   }
+  c->stage_dirty = true;
   return WK_OK;
 }
 
@@ -546,6 +569,80 @@ static int ensure_strata(wk_ctx *c, int64_t new_keys_bound) {
   return WK_OK;
 }
 
+// (Re)pack everything the kernel gathers from into one uint16 block that a
+// single TMA bulk copy stages in shared memory: E table rows of Vp entries,
+// then sub_node (FREE plans), then parent (LCA plans).  0xFFFF = none.
+static int pack_stage(wk_ctx *c) {
+  if (!c->stage_dirty) return WK_OK;
+  c->stage_dirty = false;
+  c->tab16_ok = false;
+  c->sn16_off = c->par16_off = -1;
+  c->stage_elems = 0;
+  const int64_t V = c->V;
+  if (!V || c->h_tab.empty()) return WK_OK;
+  bool any_free = false, any_rank = false;
+  for (int e = 0; e < c->E; ++e) {
+    any_free |= c->kind[e] == WK_KIND_FREE;
+    any_rank |= c->kind[e] == WK_KIND_RANK;
+  }
+  const bool need_lca =
+      any_free || (any_rank && (c->flags & WK_F_ABOVE) && !(c->flags & WK_F_MAJOR));
+  int32_t vmax = -1;
+  for (int e = 0; e < c->E; ++e) {
+    if (c->kind[e] == WK_KIND_NONE_ID) continue;
+    for (int64_t i = 0; i < V; ++i) vmax = std::max(vmax, c->h_tab[(size_t)e * V + i]);
+  }
+  if (vmax >= 0xFFFF) return WK_OK;
+  const int64_t Vp = (V + 7) & ~7ll;
+  size_t elems = (size_t)c->E * Vp;
+  const bool sn = any_free && !c->h_sub_node.empty() && c->T < 0xFFFF;
+  const bool par = need_lca && !c->h_parent.empty() && c->T < 0xFFFF;
+  size_t sn_off = elems;
+  if (sn) elems += Vp;
+  size_t par_off = elems;
+  if (par) elems += ((size_t)c->T + 7) & ~(size_t)7;
+  if (elems * 2 > 200 * 1024) {
+    // drop the optional parts first, then give up staging
+    elems = (size_t)c->E * Vp;
+    if (elems * 2 > 200 * 1024) return WK_OK;
+    std::vector<uint16_t> t16(elems, 0xFFFF);
+    for (int e = 0; e < c->E; ++e) {
+      if (c->kind[e] == WK_KIND_NONE_ID) continue;
+      for (int64_t i = 0; i < V; ++i) {
+        int32_t v = c->h_tab[(size_t)e * V + i];
+        t16[(size_t)e * Vp + i] = v < 0 ? 0xFFFF : (uint16_t)v;
+      }
+    }
+    TRY(c->tab16.reserve(t16.size() * 2 + 16));
+    CK(cudaMemcpy(c->tab16.p, t16.data(), t16.size() * 2, cudaMemcpyHostToDevice));
+    c->Vp = (int)Vp;
+    c->stage_elems = (int32_t)elems;
+    c->tab16_ok = true;
+    return WK_OK;
+  }
+  std::vector<uint16_t> t16(elems, 0xFFFF);
+  for (int e = 0; e < c->E; ++e) {
+    if (c->kind[e] == WK_KIND_NONE_ID) continue;
+    for (int64_t i = 0; i < V; ++i) {
+      int32_t v = c->h_tab[(size_t)e * V + i];
+      t16[(size_t)e * Vp + i] = v < 0 ? 0xFFFF : (uint16_t)v;
+    }
+  }
+  if (sn)
+    for (int64_t i = 0; i < V; ++i)
+      t16[sn_off + i] = c->h_sub_node[i] < 0 ? 0xFFFF : (uint16_t)c->h_sub_node[i];
+  if (par)
+    for (int32_t i = 0; i < c->T; ++i) t16[par_off + i] = (uint16_t)c->h_parent[i];
+  TRY(c->tab16.reserve(t16.size() * 2 + 16));
+  CK(cudaMemcpy(c->tab16.p, t16.data(), t16.size() * 2, cudaMemcpyHostToDevice));
+  c->Vp = (int)Vp;
+  c->stage_elems = (int32_t)elems;
+  c->sn16_off = sn ? (int32_t)sn_off : -1;
+  c->par16_off = par ? (int32_t)par_off : -1;
+  c->tab16_ok = true;
+  return WK_OK;
+}
+
 // Launch the classify kernel over queries with head in [r0, r1) of device
 // columns dq/ds holding n readable records.
 static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
@@ -554,12 +651,18 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
                            const int32_t *dqstrat, int32_t sample) {
   if (((uintptr_t)dq | (uintptr_t)ds) & 15)
     return fail(WK_ERR_ARG, "record columns must be 16-byte aligned");
+  TRY(pack_stage(c));
   ClsParams P;
   memset(&P, 0, sizeof P);
   P.q = dq;
   P.s = ds;
   P.n = n;
   P.n_dev = n_dev;
+  P.sn16_off = c->sn16_off;
+  P.par16_off = c->par16_off;
+  P.stage_elems = c->stage_elems;
+  P.n_levels = c->n_levels;
+  for (int i = 0; i <= c->n_levels && i < 40; ++i) P.level_off[i] = c->level_off[i];
   P.r0 = r0;
   P.r1 = r1;
   P.q_sample = dqsamp;
@@ -596,7 +699,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   P.scratch = c->scratch.as<int32_t>();
 
   const bool staged = c->tab16_ok && !all_id;
-  const int64_t tab_bytes = staged ? (int64_t)c->E * c->Vp * 2 : 0;
+  const int64_t tab_bytes = staged ? (int64_t)c->stage_elems * 2 : 0;
   const size_t cells = (size_t)c->E * c->S * (c->NF + 1);
   // where counts are accumulated first (wk_classify.cuh, "count sinks")
   int sink = SINK_GLOBAL, cache_log = 0;

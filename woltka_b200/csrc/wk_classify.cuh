@@ -69,6 +69,11 @@ struct ClsParams {
   int32_t Vp;
   const int32_t *sub_node;    // [V] or null
   const int32_t *parent;      // [T] or null
+  int32_t sn16_off, par16_off; // uint16 copies inside the staged block (element
+                               // offsets, -1 = not staged)
+  int32_t stage_elems;        // total uint16 elements staged
+  int32_t n_levels;           // nodes are sorted by depth: level l holds node
+  int32_t level_off[40];      // indices [level_off[l], level_off[l+1]); 0 = n/a
   int32_t root;               // -1 = no root given (root=None)
   ull *cnt;                   // [E][S][NF1] units
   int64_t NF1;
@@ -136,6 +141,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
                "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -266,15 +274,21 @@ __device__ __forceinline__ void emit_frac(const ClsParams &P, const Sink &K,
 // LCA of two nodes on a topologically numbered tree (parent[i] < i): lifting
 // the larger index can never step over the LCA.  Same result as
 // tree.find_lca (tree.py:513-566) on a single-rooted tree.
-__device__ __forceinline__ int lca2(const int32_t *__restrict__ parent, int a,
-                                    int b) {
+struct TreeRef {
+  const int32_t *parent;  // global
+  uint32_t par16;         // shared address of the uint16 copy, 0 = none
+};
+__device__ __forceinline__ int parent_of(const TreeRef &T, int a) {
+  return T.par16 ? (int)lds16(T.par16 + (uint32_t)a * 2u) : __ldg(T.parent + a);
+}
+__device__ __forceinline__ int lca2(const TreeRef &T, int a, int b) {
   while (a != b) {
     if (a > b) {
-      int p = __ldg(parent + a);
+      int p = parent_of(T, a);
       if (p == a) return b;  // second root: never loop (host rejects such trees)
       a = p;
     } else {
-      int p = __ldg(parent + b);
+      int p = parent_of(T, b);
       if (p == b) return a;
       b = p;
     }
@@ -295,7 +309,7 @@ __device__ __forceinline__ int tab_get(const ClsParams &P, uint32_t stab,
 
 // LCA over the non-duplicate members of each lane segment; result valid at
 // head lanes with need == true.  All lanes must call.
-__device__ __forceinline__ int warp_seg_lca(const int32_t *parent, int v,
+__device__ __forceinline__ int warp_seg_lca(const TreeRef &parent, int v,
                                             unsigned segnd, int se, bool need,
                                             int lane) {
   int maxlen = __reduce_max_sync(FULL, need ? (se - lane) : 0);
@@ -308,6 +322,40 @@ __device__ __forceinline__ int warp_seg_lca(const int32_t *parent, int v,
   return acc;
 }
 
+// Same result on a tree whose nodes are numbered level by level (the host's
+// breadth-first order): every member climbs to the shallowest member's depth,
+// then the members of a query climb in lockstep until they agree.  At most
+// 2 x depth shared-memory loads per lane instead of a serial fold over the
+// members.  memb: non-duplicate member of a query that needs the LCA (all of
+// its members are tree nodes).
+__device__ __forceinline__ int warp_seg_lca_level(const ClsParams &P,
+                                                  const TreeRef &T, int v,
+                                                  bool memb, int sl, int se,
+                                                  unsigned segm, int lane) {
+  int d = 0;
+  if (memb)
+    for (int i = 1; i < P.n_levels; ++i) d += (v >= P.level_off[i]);
+  int dm = memb ? d : 0x7fffffff;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    int o = __shfl_down_sync(FULL, dm, off);
+    if (lane + off < se && o < dm) dm = o;
+  }
+  dm = __shfl_sync(FULL, dm, sl);
+  if (memb)
+    while (d > dm) {
+      v = parent_of(T, v);
+      --d;
+    }
+  for (int guard = 0; guard <= P.n_levels; ++guard) {
+    const int vh = __shfl_sync(FULL, v, sl);
+    const unsigned ne = __ballot_sync(FULL, memb && v != vh);
+    if (!ne) break;
+    if (memb && (ne & segm)) v = parent_of(T, v);
+  }
+  return v;
+}
+
 __device__ __forceinline__ int warp_sum(int v) {
   return __reduce_add_sync(FULL, v);
 }
@@ -317,6 +365,9 @@ template <bool STAGED, int SINK>
 __device__ __noinline__ int64_t process_long(const ClsParams &P, const Sink &K,
                                              uint32_t stab, int64_t n,
                                              int64_t start, int lane) {
+  TreeRef TR;
+  TR.parent = P.parent;
+  TR.par16 = (STAGED && P.par16_off >= 0) ? stab + (uint32_t)P.par16_off * 2u : 0u;
   const int32_t *gq = P.q, *gs = P.s;
   const int qid = gq[start];
   int64_t end = start + 1;
@@ -427,14 +478,14 @@ __device__ __noinline__ int64_t process_long(const ClsParams &P, const Sink &K,
             for (int64_t j = start + lane; j < end; j += 32) {
               int t = __ldcg(P.scratch + j);
               if (t == DUPMARK) continue;
-              acc = acc == -2 ? t : lca2(P.parent, acc, t);
+              acc = acc == -2 ? t : lca2(TR, acc, t);
             }
             for (int off = 16; off; off >>= 1) {
               int o = __shfl_xor_sync(FULL, acc, off);
               if (acc == -2)
                 acc = o;
               else if (o != -2)
-                acc = lca2(P.parent, acc, o);
+                acc = lca2(TR, acc, o);
             }
             result = acc == P.root ? -1 : acc;
           }
@@ -495,7 +546,7 @@ __global__ void __launch_bounds__(CLS_NT, 1)
   const int tid = threadIdx.x, warp = tid >> 5;
   int lane = tid & 31;
   asm volatile("" : "+r"(lane));  // S2R is slow: keep the lane id live
-  const int64_t tab_bytes = STAGED ? (int64_t)P.E * P.Vp * 2 : 0;
+  const int64_t tab_bytes = STAGED ? (int64_t)P.stage_elems * 2 : 0;
   const ClsSmemLayout L =
       cls_layout(SINK, P.cache_log, P.direct_cells, tab_bytes);
   uint32_t sbase32 = smem_u32(smem);
@@ -521,8 +572,12 @@ __global__ void __launch_bounds__(CLS_NT, 1)
   const int64_t tb0 = r0 & ~3ll;
   const int64_t n_tiles = r1 > tb0 ? (r1 - tb0 + CLS_TILE - 1) / CLS_TILE : 0;
 
+  // bars: [0, STAGES) tile landed ("full"), [STAGES] tables landed,
+  // (STAGES, 2*STAGES] every warp is done with the stage ("empty")
   if (tid == 0) {
     for (int i = 0; i <= CLS_STAGES; ++i) mbar_init(bars + 8 * i, 1);
+    for (int i = 0; i < CLS_STAGES; ++i)
+      mbar_init(bars + 8 * (CLS_STAGES + 1 + i), CLS_NW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -565,6 +620,11 @@ __global__ void __launch_bounds__(CLS_NT, 1)
   __syncthreads();
   if (STAGED) mbar_wait(bars + 8 * CLS_STAGES, 0);
 
+  TreeRef TR;
+  TR.parent = P.parent;
+  TR.par16 = (STAGED && P.par16_off >= 0) ? stab + (uint32_t)P.par16_off * 2u : 0u;
+  const uint32_t sn16 =
+      (STAGED && P.sn16_off >= 0) ? stab + (uint32_t)P.sn16_off * 2u : 0u;
   const int64_t NF = P.NF1 - 1;
   uint32_t flags = P.flags;
   int E = LEAN ? 1 : P.E;
@@ -726,7 +786,14 @@ __global__ void __launch_bounds__(CLS_NT, 1)
             } else if (flags & WK_F_ABOVE) {
               const unsigned neg = __ballot_sync(FULL, nd && t < 0) & segm;
               const bool need = ishead && !alleq && !neg;
-              const int l = warp_seg_lca(P.parent, t, segnd, se, need, lane);
+              int l;
+              if (P.n_levels) {
+                const bool sneed = __shfl_sync(FULL, (int)need, sl);
+                l = warp_seg_lca_level(P, TR, t, act && sneed && nd, sl, se,
+                                       segm, lane);
+              } else {
+                l = warp_seg_lca(TR, t, segnd, se, need, lane);
+              }
               if (!alleq) result = (neg || l == P.root) ? -1 : l;
             } else if (flags & WK_F_UNIQ) {
               if (!alleq) result = -1;
@@ -744,10 +811,25 @@ __global__ void __launch_bounds__(CLS_NT, 1)
           const int t1 = nd ? tab_get<STAGED>(P, stab, e, sv) : -1;
           result = t1;
           if (__any_sync(FULL, act && k > 1)) {
-            const int v = nd ? __ldg(P.sub_node + sv) : -1;
+            int v = -1;
+            if (nd) {
+              if (sn16) {
+                unsigned u = lds16(sn16 + (uint32_t)sv * 2u);
+                v = u == 0xFFFFu ? -1 : (int)u;
+              } else {
+                v = __ldg(P.sub_node + sv);
+              }
+            }
             const unsigned neg = __ballot_sync(FULL, nd && v < 0) & segm;
             const bool need = ishead && k > 1 && !neg;
-            const int l = warp_seg_lca(P.parent, v, segnd, se, need, lane);
+            int l;
+            if (P.n_levels) {
+              const bool sneed = __shfl_sync(FULL, (int)need, sl);
+              l = warp_seg_lca_level(P, TR, v, act && sneed && nd, sl, se,
+                                     segm, lane);
+            } else {
+              l = warp_seg_lca(TR, v, segnd, se, need, lane);
+            }
             if (k > 1) result = (neg || l == P.root) ? -1 : l;
           }
         } else {
@@ -773,6 +855,8 @@ __global__ void __launch_bounds__(CLS_NT, 1)
       cur += cons;
     }
 
+    // (handing the stage back through an "empty" mbarrier instead of a CTA
+    // barrier was measured slower: 1.39 ms vs 1.06 ms on cfg2)
     __syncthreads();  // every warp is done with this stage
     if (tid == 0) {
       int64_t nt = tile + (int64_t)CLS_STAGES * gridDim.x;
