@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3'])
+    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3', 'cfg4'])
     ap.add_argument('--records', type=int, default=100_000_000)
     ap.add_argument('--mode', default='default',
                     choices=['default', 'major', 'uniq', 'above'])
@@ -45,7 +45,14 @@ def parse_args():
     ap.add_argument('--cpu-sample', type=int, default=20_000_000)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
-    return ap.parse_args()
+    ap.add_argument('--samples', type=int, default=1,
+                    help='samples per GPU (per-query sample column if > 1)')
+    args = ap.parse_args()
+    if args.workload == 'cfg4':
+        # BASELINE.json configs[3]: phylum/genus/species with multi-hit LCA,
+        # 64 samples sharded 8 per GPU
+        args.ranks, args.mode, args.samples = 'phylum,genus,species', 'above', 8
+    return args
 
 
 def host_threads():
@@ -139,14 +146,17 @@ def make_cfg2(args, device, seed):
     case = cases.Case(synth.Taxonomy(seed=42))
     entries = args.ranks.split(',')
     flags = cases.MODES[args.mode]
-    q, s, _, nq = synth.gen_hits(args.records, seed=seed, device=device)
+    q, s, qs, nq = synth.gen_hits(args.records, seed=seed, device=device,
+                                  n_samples=args.samples)
+    args._q_sample = qs if args.samples > 1 else None
     return case, entries, flags, q, s, nq
 
 
-def cpu_classify(case, entries, flags, q, s, threads):
+def cpu_classify(case, entries, flags, q, s, threads, **kw):
     from tests import cases
     t0 = time.perf_counter()
-    out = cases.run_oracle(case, entries, flags, 0.8, q, s, n_threads=threads)
+    out = cases.run_oracle(case, entries, flags, 0.8, q, s, n_threads=threads,
+                           **kw)
     return out, time.perf_counter() - t0
 
 
@@ -199,11 +209,14 @@ def run_reference(args):
     case, entries, flags, q, s, nq = make_cfg2(args, 'cpu', 1002)
     args.records = args_records
     q, s = q.numpy(), s.numpy()
+    kw = {}
+    if args._q_sample is not None:
+        kw = dict(n_samples=args.samples, q_sample=args._q_sample.numpy())
     for _ in range(args.warmup):
-        cpu_classify(case, entries, flags, q, s, threads)
+        cpu_classify(case, entries, flags, q, s, threads, **kw)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_classify(case, entries, flags, q, s, threads)
+        cpu_classify(case, entries, flags, q, s, threads, **kw)
     dt = time.perf_counter() - t0
     val = n * args.steps / dt
     line = {
@@ -258,6 +271,13 @@ def workload_config(args, entries):
                 'records_per_gpu': args.records, 'genes': 5_000_000,
                 'contigs': 1000,
                 'l2': 'inputs larger than L2 (2 GB of columns per step)'}
+    if args.workload == 'cfg4':
+        return {'workload': 'cfg4: phylum/genus/species with multi-hit LCA '
+                            '(--above), synthetic records, 8 samples per GPU',
+                'records_per_gpu': args.records, 'ranks': entries,
+                'mode': args.mode, 'samples_per_gpu': args.samples,
+                'taxonomy_nodes': 21603, 'genomes': 10000,
+                'l2': 'inputs larger than L2'}
     return {'workload': 'cfg2: genus-rank taxonomic classify, synthetic SAM '
                         'records x 10k-genome / 21,603-node taxonomy',
             'records_per_gpu': args.records, 'ranks': entries,
@@ -296,15 +316,27 @@ def run_ours(args):
     from tests import cases
     case, entries, flags, q, s, nq = make_cfg2(args, dev, 1002 + rank)
     kinds, tab, _ = case.tables(entries)
+    # every rank owns `samples` sample columns of one shared table
+    S_loc = args.samples
+    S_all = S_loc * world
+    qs = args._q_sample
+    if qs is not None:
+        qs = (qs + rank * S_loc).contiguous()
+    qs_ptr = qs.data_ptr() if qs is not None else None
+    smp = 0 if qs is not None else rank * S_loc
     eng.set_tree(case.ft.parent, 0)
-    eng.set_plan(kinds, flags, 0.8, 1, case.NF)
+    eng.set_plan(kinds, flags, 0.8, S_all, case.NF)
     eng.set_subjects(tab, case.sub_node)
     counts = eng.counts_tensor()
     bytes_per_rec = 8
 
+    def classify_dev():
+        eng.classify_device(q.data_ptr(), s.data_ptr(), n, qs_ptr, None, nq,
+                            smp)
+
     def step():
         eng.reset_counts()
-        eng.classify_device(q.data_ptr(), s.data_ptr(), n)
+        classify_dev()
         if world > 1:
             dist.all_reduce(counts)
 
@@ -323,7 +355,7 @@ def run_ours(args):
     for i in range(args.steps):
         eng.reset_counts()
         k_ev[i][0].record()
-        eng.classify_device(q.data_ptr(), s.data_ptr(), n)
+        classify_dev()
         k_ev[i][1].record()
         if world > 1:
             dist.all_reduce(counts)
@@ -347,9 +379,13 @@ def run_ours(args):
         hs = pinned_empty(n)
         hq[:] = q.cpu().numpy()
         hs[:] = s.cpu().numpy()
+        hqs = None
+        if qs is not None:
+            hqs = pinned_empty(nq)
+            hqs[:] = qs.cpu().numpy()
         for _ in range(2):
             eng.reset_counts()
-            eng.classify_chunk(hq, hs)
+            eng.classify_chunk(hq, hs, hqs, None, smp)
             res = eng.fetch_counts()
         barrier()
         t0 = time.perf_counter()
@@ -359,7 +395,7 @@ def run_ours(args):
         e2e_steps = max(3, min(args.steps, 10))
         for _ in range(e2e_steps):
             eng.reset_counts()
-            eng.classify_chunk(hq, hs)      # H2D inside
+            eng.classify_chunk(hq, hs, hqs, None, smp)      # H2D inside
             if world > 1:
                 dist.all_reduce(counts)
             res = eng.fetch_counts()        # D2H of the count table
@@ -371,7 +407,8 @@ def run_ours(args):
             dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ems = float(tms.item())
         e2e = {'value': n * world * e2e_steps / (ems * 1e-3), 'unit': UNIT,
-               'h2d_bytes_per_step': int(2 * 4 * n),
+               'h2d_bytes_per_step': int(2 * 4 * n + (4 * nq if hqs is not
+                                                      None else 0)),
                'd2h_bytes_per_step': int(res.nbytes),
                'steps': e2e_steps, 'ms_per_step': ems / e2e_steps,
                'api': 'wk_classify_chunk(host SoA) + wk_fetch_counts'}
@@ -390,12 +427,15 @@ def run_ours(args):
         while m < len(qh) and m > 0 and qh[m] == qh[m - 1]:
             m += 1
         qh, sh = qh[:m], sh[:m]
-        (eu, eo, _), dt = cpu_classify(case, entries, flags, qh, sh, threads)
+        qsh = qs.cpu().numpy() if qs is not None else None
+        kw = dict(n_samples=S_all, q_sample=qsh, sample=smp)
+        (eu, eo, _), dt = cpu_classify(case, entries, flags, qh, sh, threads,
+                                       **kw)
         (_, _, _), dt1 = cpu_classify(case, entries, flags, qh[:m // 8],
-                                      sh[:m // 8], 1)
+                                      sh[:m // 8], 1, **kw)
         eng.reset_counts()
-        eng.classify_chunk(qh, sh)
-        gu, go, _ = cases.collect(eng, 1, case.NF)
+        eng.classify_chunk(qh, sh, qsh, None, smp)
+        gu, go, _ = cases.collect(eng, S_all, case.NF)
         parity = bool(np.array_equal(gu, eu)) and go == eo
         cpu = {'value': m / dt, 'unit': UNIT, 'cores': threads,
                'kind': 'port',

@@ -704,8 +704,9 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   // where counts are accumulated first (wk_classify.cuh, "count sinks")
   int sink = SINK_GLOBAL, cache_log = 0;
   if (!dqstrat && c->tune_cache >= 0) {
-    if (cells < (1u << 24) &&
-        cls_layout(SINK_DIRECT, 0, (uint32_t)cells, tab_bytes).total <=
+    const size_t dcells = (size_t)c->E * (c->NF + 1);  // one sample at a time
+    if (dcells < (1u << 24) &&
+        cls_layout(SINK_DIRECT, 0, (uint32_t)dcells, tab_bytes).total <=
             c->smem_optin) {
       sink = SINK_DIRECT;
     } else if (cells < 0xFFFFFFFFull) {
@@ -732,7 +733,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
     }
   }
   P.cache_log = sink == SINK_HASHED ? cache_log : 0;
-  P.direct_cells = sink == SINK_DIRECT ? (uint32_t)cells : 0;
+  P.direct_cells = sink == SINK_DIRECT ? (uint32_t)((size_t)c->E * (c->NF + 1)) : 0;
   ClsSmemLayout L = cls_layout(sink, P.cache_log, P.direct_cells, tab_bytes);
   if (L.total > c->smem_optin)
     return fail(WK_ERR_STATE, "shared memory layout does not fit (%u B)", L.total);

@@ -88,7 +88,7 @@ struct ClsParams {
   int32_t *err;               // device error word (bit flags)
   int32_t *scratch;           // [>= n] long-query scratch
   int32_t cache_log;          // SINK_HASHED: log2(cache slots)
-  uint32_t direct_cells;      // SINK_DIRECT: E*S*NF1
+  uint32_t direct_cells;      // SINK_DIRECT: E*NF1 (one sample at a time)
 };
 
 enum { ERR_BAD_SUBJECT = 1, ERR_OVF_FULL = 2, ERR_HASH_FULL = 4,
@@ -172,6 +172,7 @@ struct Sink {
   uint32_t a0;   // DIRECT: low-word table; HASHED: tags
   uint32_t a1;   // HASHED: low words
   int sh;        // HASHED: 32 - log2(slots)
+  int cur;       // DIRECT: the sample the CTA's private table belongs to
 };
 
 __device__ __forceinline__ void strat_add(const ClsParams &P, ull key,
@@ -222,10 +223,15 @@ __device__ __forceinline__ void emit_units(const ClsParams &P, const Sink &K,
                                            int e, int samp, int strat,
                                            int64_t f, uint32_t units) {
   if (SINK == SINK_DIRECT) {
-    uint32_t key = (uint32_t)((e * P.S + samp) * (int)P.NF1 + (int)f);
-    uint32_t old = atoms_add(K.a0 + key * 4u, units);
-    if (old + units < old) atomicAdd(&P.cnt[key], 1ull << 32);
-    return;
+    // private [entry][feature] table of ONE sample at a time (samples are
+    // contiguous in the stream); other samples go straight to HBM
+    if (samp == K.cur) {
+      uint32_t key = (uint32_t)(e * (int)P.NF1 + (int)f);
+      uint32_t old = atoms_add(K.a0 + key * 4u, units);
+      if (old + units < old)
+        atomicAdd(&P.cnt[((int64_t)e * P.S + samp) * P.NF1 + f], 1ull << 32);
+      return;
+    }
   }
   int64_t cell = ((int64_t)e * P.S + samp) * P.NF1 + f;
   if (SINK == SINK_HASHED) {
@@ -608,8 +614,11 @@ __global__ void __launch_bounds__(CLS_NT, 1)
       if (tile < n_tiles) issue(tile, st);
     }
   }
+  const uint32_t prop_addr = bars + 64;  // DIRECT: sample proposed for the table
+  K.cur = P.q_sample ? -1 : P.sample;
   if (SINK == SINK_DIRECT) {
     for (uint32_t h = tid; h < sink_words; h += CLS_NT) sts32(K.a0 + h * 4, 0);
+    if (tid == 0) sts32(prop_addr, 0xFFFFFFFFu);
   } else if (SINK == SINK_HASHED) {
     const uint32_t slots = 1u << P.cache_log;
     for (uint32_t h = tid; h < slots; h += CLS_NT) {
@@ -638,6 +647,21 @@ __global__ void __launch_bounds__(CLS_NT, 1)
   const bool unas = flags & WK_F_UNASSIGNED;
   const unsigned le = FULL >> (31 - lane), lt = le >> 1;
   const unsigned mybit = 1u << lane;
+
+  // DIRECT: add the private table of sample K.cur to the global table
+  auto flush_direct = [&]() {
+    if (K.cur >= 0) {
+      const uint32_t NF1u = (uint32_t)P.NF1;
+      for (uint32_t h = tid; h < sink_words; h += CLS_NT) {
+        uint32_t v = (uint32_t)lds32(K.a0 + h * 4);
+        if (v) {
+          uint32_t e = h / NF1u, f = h - e * NF1u;
+          atomicAdd(&P.cnt[((int64_t)e * P.S + K.cur) * P.NF1 + f], (ull)v);
+          sts32(K.a0 + h * 4, 0);
+        }
+      }
+    }
+  };
 
   int it = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -705,6 +729,16 @@ __global__ void __launch_bounds__(CLS_NT, 1)
       const int sl = 31 - __clz(H & le);           // my query's first lane
       const int se = __ffs(Tl & ~lt);              // one past its last lane
       const unsigned segm = act ? ((FULL << sl) & (FULL >> (32 - se))) : 0u;
+      // per-query sample / stratum: every lane of a query loads the same word
+      // (coalesced, issued early so the latency hides behind the dedup)
+      int samp = P.sample, strat = 0;
+      if (per_query && act) {
+        if (P.q_sample) samp = __ldg(P.q_sample + qa);
+        if (P.q_stratum) strat = __ldg(P.q_stratum + qa);
+      }
+      if (SINK == SINK_DIRECT && per_query && act && samp != K.cur &&
+          (unsigned)samp < (unsigned)P.S)
+        sts32(prop_addr, (uint32_t)samp);  // ask for the table to follow
       int sv = act ? lds32(as + (uint32_t)x * 4u) : ~lane;
       if (act && (unsigned)sv >= (unsigned)V32) {
         atomicOr(P.err, ERR_BAD_SUBJECT);
@@ -729,15 +763,6 @@ __global__ void __launch_bounds__(CLS_NT, 1)
       const int k = __popc(segnd);
       const bool ishead = act && lane == sl;
 
-      int samp = P.sample, strat = 0;
-      if (per_query) {
-        if (ishead) {
-          if (P.q_sample) samp = __ldg(P.q_sample + qa);
-          if (P.q_stratum) strat = __ldg(P.q_stratum + qa);
-        }
-        samp = __shfl_sync(FULL, samp, sl);
-        strat = __shfl_sync(FULL, strat, sl);
-      }
       const bool live = act && strat >= 0 && (unsigned)samp < (unsigned)P.S;
 
       for (int e = 0; e < E; ++e) {
@@ -862,16 +887,26 @@ __global__ void __launch_bounds__(CLS_NT, 1)
       int64_t nt = tile + (int64_t)CLS_STAGES * gridDim.x;
       if (nt < n_tiles) issue(nt, stage);
     }
+    if (SINK == SINK_DIRECT && per_query) {
+      // the stream moved on to another sample: flush and re-target the table
+      // (read between two barriers: no warp may post a new proposal from
+      // the next tile before every thread has seen this one)
+      const int prop = lds32(prop_addr);
+      __syncthreads();
+      if (prop >= 0 && prop != K.cur) {
+        flush_direct();
+        if (tid == 0) sts32(prop_addr, 0xFFFFFFFFu);
+        K.cur = prop;
+        __syncthreads();
+      }
+    }
   }
 
   // write the CTA's partial counts back (util.sum_dict, util.py:78-94)
   if (SINK != SINK_GLOBAL) {
     __syncthreads();
     if (SINK == SINK_DIRECT) {
-      for (uint32_t h = tid; h < sink_words; h += CLS_NT) {
-        uint32_t v = (uint32_t)lds32(K.a0 + h * 4);
-        if (v) atomicAdd(&P.cnt[h], (ull)v);
-      }
+      flush_direct();
     } else {
       const uint32_t slots = 1u << P.cache_log;
       for (uint32_t h = tid; h < slots; h += CLS_NT) {
