@@ -749,18 +749,24 @@ __global__ void __launch_bounds__(CLS_NT, 1)
       // (match.any serialises on one unit per SM and was 80 % of the kernel):
       // `reach` holds the lanes whose query extends at least m lanes back.
       const unsigned cont = ~H & (FULL >> (32 - cons));  // non-head, active
-      unsigned dupm = 0;
-      {
-        unsigned reach = cont;
+      // ... computed lazily: a window whose queries are all unanimous at the
+      // requested rank (the common case on real data) never needs it.
+      bool have_nd = false, nd = sv >= 0;
+      unsigned segnd = 0;
+      int k = 0;
+      auto dedup = [&]() {
+        if (have_nd) return;
+        have_nd = true;
+        unsigned dupm = 0, reach = cont;
         for (int m = 1; reach; ++m) {
           const int o = __shfl_up_sync(FULL, sv, m);
           dupm |= (o == sv) ? reach : 0u;
           reach &= cont << m;
         }
-      }
-      const bool nd = sv >= 0 && !(dupm & mybit);
-      const unsigned segnd = __ballot_sync(FULL, nd) & segm;
-      const int k = __popc(segnd);
+        nd = sv >= 0 && !(dupm & mybit);
+        segnd = __ballot_sync(FULL, nd) & segm;
+        k = __popc(segnd);
+      };
       const bool ishead = act && lane == sl;
 
       const bool live = act && strat >= 0 && (unsigned)samp < (unsigned)P.S;
@@ -771,12 +777,15 @@ __global__ void __launch_bounds__(CLS_NT, 1)
         bool uniqres = true;
         if (kind == WK_KIND_RANK) {
           // classify.assign_rank (classify.py:81-127)
-          const int t = nd ? tab_get<STAGED>(P, stab, e, sv) : -1;
+          // repeats carry the taxon of their first occurrence, so the
+          // all-equal test can run on the raw records
+          const int t = sv >= 0 ? tab_get<STAGED>(P, stab, e, sv) : -1;
           const int th = __shfl_sync(FULL, t, sl);
-          const unsigned neq = __ballot_sync(FULL, nd && t != th);
+          const unsigned neq = __ballot_sync(FULL, sv >= 0 && t != th);
           const bool alleq = (neq & segm) == 0;
           result = th;
           if (neq) {  // some query of this window has differing taxa
+            dedup();
             if (flags & WK_F_MAJOR) {
               // occurrences of my taxon among the query's distinct subjects
               // (util.count_list, util.py:387-403): look both ways
@@ -833,6 +842,7 @@ __global__ void __launch_bounds__(CLS_NT, 1)
           }
         } else if (kind == WK_KIND_FREE) {
           // classify.assign_free (classify.py:54-78)
+          dedup();
           const int t1 = nd ? tab_get<STAGED>(P, stab, e, sv) : -1;
           result = t1;
           if (__any_sync(FULL, act && k > 1)) {
@@ -859,6 +869,7 @@ __global__ void __launch_bounds__(CLS_NT, 1)
           }
         } else {
           // classify.assign_none (classify.py:32-51)
+          dedup();
           const int f = !nd ? -1
                             : (kind == WK_KIND_NONE_ID
                                    ? sv
