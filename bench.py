@@ -101,7 +101,7 @@ class ClockSampler:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index),
                  f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                 '-lms', '100'], stdout=subprocess.PIPE,
+                 '-lms', '20'], stdout=subprocess.PIPE,
                 stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
