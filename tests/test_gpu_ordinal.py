@@ -138,3 +138,37 @@ def test_ordinal_then_classify(engine):
                              n_features=G, q_sample=q_sample)
     assert not ovf
     assert np.array_equal(units, exp)
+
+
+def test_queries_straddling_tiles(engine):
+    """A CTA owns the queries whose first record lies in its tile and follows
+    the last one past the tile end — including queries longer than a tile."""
+    coff, gb, ge = synth.gen_genes(6, 400, 200_000, seed=31)
+    G = len(gb)
+    rng = np.random.default_rng(5)
+    from woltka_b200._lib import KIND_NONE_ID
+    for sizes in ([2047, 3, 2046, 5000, 1, 1, 7], [1] * 10 + [6000] + [2] * 50,
+                  [4096, 4096], [2048, 2048, 100]):
+        q = np.repeat(np.arange(len(sizes), dtype=np.int32), sizes)
+        n = len(q)
+        c = rng.integers(0, 6, n).astype(np.int32)
+        b = rng.integers(0, 199_000, n).astype(np.int32)
+        ln = rng.integers(20, 200, n).astype(np.int32)
+        eng = Engine(0)
+        try:
+            eng.set_plan(np.array([KIND_NONE_ID]), 0, 0.0, 1, G)
+            eng.set_subjects(None, None, G)
+            eng.ordinal_set_genes(coff, gb, ge, np.arange(G, dtype=np.int32))
+            eng.ordinal_enable_pairs()
+            eng.ordinal_chunk(q, c, b, b + ln, ln, 0.5)
+            r, g = eng.ordinal_pairs()
+            units = eng.fetch_counts()
+            ovf = eng.fetch_overflow()
+        finally:
+            eng.close()
+        er, eg = O.ordinal_match(c, b, b + ln, ln, 0.5, coff, gb, ge)
+        assert np.array_equal(r, er) and np.array_equal(g, eg)
+        exp, eovf, _ = O.classify(q[er], eg, kinds=[KIND_NONE_ID],
+                                  n_features=G)
+        assert np.array_equal(units, exp)
+        assert len(ovf[0]) == len(eovf)

@@ -970,10 +970,6 @@ static int run_ordinal(wk_ctx *c, const int32_t *dq, const int32_t *dcontig,
       TRY(c->pair_r.reserve((size_t)c->pair_cap * 4));
       TRY(c->pair_g.reserve((size_t)c->pair_cap * 4));
     }
-    TRY(c->tile_desc.reserve((size_t)n_tiles * 8));
-    TRY(c->ticket.reserve(16));
-    CK(cudaMemsetAsync(c->tile_desc.p, 0, (size_t)n_tiles * 8, c->stream));
-    CK(cudaMemsetAsync(c->ticket.p, 0, 16, c->stream));
     CK(cudaMemsetAsync(c->d_n_pairs(), 0, 8, c->stream));
     OrdParams P;
     memset(&P, 0, sizeof P);
@@ -997,8 +993,6 @@ static int run_ordinal(wk_ctx *c, const int32_t *dq, const int32_t *dcontig,
     P.pair_g = c->keep_pairs ? c->pair_g.as<int32_t>() : nullptr;
     P.cap = c->pair_cap;
     P.n_pairs = c->d_n_pairs();
-    P.tile_desc = c->tile_desc.as<ull>();
-    P.ticket = c->ticket.as<unsigned>();
     P.err = c->d_err();
     {
       // keep the gene table + bins persisting in L2, stream everything else
@@ -1107,6 +1101,18 @@ int wk_ordinal_fetch_pairs(wk_ctx *c, int64_t *n_pairs, int32_t *read_idx,
   if (cap < c->last_pairs) return fail(WK_ERR_CAPACITY, "pair output too small");
   CK(cudaMemcpy(read_idx, c->pair_r.p, (size_t)c->last_pairs * 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(gene_idx, c->pair_g.p, (size_t)c->last_pairs * 4, cudaMemcpyDeviceToHost));
+  {
+    // CTAs append their ranges in any order: hand the pairs back sorted by
+    // (read, gene)
+    std::vector<uint64_t> keys((size_t)c->last_pairs);
+    for (int64_t i = 0; i < c->last_pairs; ++i)
+      keys[i] = ((uint64_t)(uint32_t)read_idx[i] << 32) | (uint32_t)gene_idx[i];
+    std::sort(keys.begin(), keys.end());
+    for (int64_t i = 0; i < c->last_pairs; ++i) {
+      read_idx[i] = (int32_t)(keys[i] >> 32);
+      gene_idx[i] = (int32_t)(keys[i] & 0xffffffffu);
+    }
+  }
   *n_pairs = c->last_pairs;
   return WK_OK;
 }

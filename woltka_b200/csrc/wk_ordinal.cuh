@@ -16,9 +16,13 @@
 //     then scanned while g.beg <= r.end - L.
 //   * no sort of the reads: the gene table + bins are L2-resident
 //     (8 B/gene + ~4 B/bin), reads stream through once with 128-bit loads.
-//   * matches leave the kernel as (query idx, gene subject idx) pairs in
-//     RECORD ORDER (single-pass chained scan with decoupled look-back), so a
-//     query's pairs stay contiguous and feed classify_kernel unchanged.
+//   * matches leave the kernel as (query idx, gene subject idx) pairs with the
+//     pairs of a query CONTIGUOUS, which is all classify_kernel needs: tiles
+//     are aligned to query boundaries (a CTA owns the queries whose first
+//     record lies in its tile and follows the last one past the tile end), a
+//     block scan orders the pairs inside the CTA and one atomicAdd reserves
+//     the CTA's range.  (The first version kept global record order with a
+//     decoupled look-back chain: 28 % of its time was barrier stall.)
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -40,12 +44,10 @@ struct OrdParams {
   const int32_t *bin_first;    // [sum bins]
   int32_t shift;
   int32_t C;
-  int32_t *pair_q, *pair_s;    // out, record order
+  int32_t *pair_q, *pair_s;    // out, pairs of one query contiguous
   int32_t *pair_r, *pair_g;    // optional (read idx, gene idx) or null
   int64_t cap;
-  ull *n_pairs;                // out: total number of pairs
-  ull *tile_desc;              // [n_tiles], zeroed
-  unsigned *ticket;            // zeroed
+  ull *n_pairs;                // in/out: pair cursor (zeroed), total at the end
   int32_t *err;
 };
 
@@ -89,20 +91,56 @@ __device__ __forceinline__ void ord_scan(const OrdParams &P, const ReadQ &r,
   }
 }
 
-__global__ void __launch_bounds__(ORD_NT)
+__global__ void __launch_bounds__(ORD_NT, 2)
     ordinal_match_kernel(const __grid_constant__ OrdParams P) {
-  __shared__ unsigned s_tile;
   __shared__ int s_warp[ORD_NT / 32];
-  __shared__ ull s_base;
+  __shared__ long long s_base;
+  __shared__ int s_skip, s_ext, s_ext_tot;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(P.ticket, 1u);
+  const int64_t t0 = (int64_t)blockIdx.x * ORD_TILE;
+  const int64_t t1 = t0 + ORD_TILE < P.n ? t0 + ORD_TILE : P.n;
+
+  // tile ownership by query: skip the records that continue the previous
+  // tile's last query, follow our last query past the tile end
+  if (warp == 0) {
+    int64_t skip = 0;
+    if (t0 > 0) {
+      const int prevq = P.q[t0 - 1];
+      for (int64_t i = t0;; i += 32) {
+        const bool brk = (i + lane >= t1) || P.q[i + lane] != prevq;
+        const unsigned m = __ballot_sync(FULL, brk);
+        if (m) {
+          skip = i - t0 + __ffs(m) - 1;
+          break;
+        }
+      }
+    }
+    int64_t ext = 0;
+    if (t1 < P.n && t0 + skip < t1) {
+      const int lastq = P.q[t1 - 1];
+      for (int64_t i = t1;; i += 32) {
+        const bool brk = (i + lane >= P.n) || P.q[i + lane] != lastq;
+        const unsigned m = __ballot_sync(FULL, brk);
+        if (m) {
+          ext = i - t1 + __ffs(m) - 1;
+          break;
+        }
+      }
+    }
+    if (lane == 0) {
+      s_skip = (int)skip;
+      s_ext = (int)(ext < (1 << 30) ? ext : (1 << 30));
+      s_ext_tot = 0;
+    }
+  }
   __syncthreads();
-  const int64_t tile = s_tile;
-  const int64_t i0 = tile * ORD_TILE + (int64_t)tid * ORD_ITEMS;
+  const int64_t own0 = t0 + s_skip;
+  const int ext = s_ext;
+  const int64_t i0 = t0 + (int64_t)tid * ORD_ITEMS;
 
   int32_t qv[ORD_ITEMS], cv[ORD_ITEMS], bv[ORD_ITEMS], ev[ORD_ITEMS],
       lv[ORD_ITEMS];
-  if (i0 + ORD_ITEMS <= P.n) {
+  if (i0 + ORD_ITEMS <= t1) {
     int4 a = __ldcs(reinterpret_cast<const int4 *>(P.q + i0));
     int4 b = __ldcs(reinterpret_cast<const int4 *>(P.contig + i0));
     int4 c = __ldcs(reinterpret_cast<const int4 *>(P.beg + i0));
@@ -117,7 +155,7 @@ __global__ void __launch_bounds__(ORD_NT)
 #pragma unroll
     for (int j = 0; j < ORD_ITEMS; ++j) {
       int64_t i = i0 + j;
-      bool ok = i < P.n;
+      bool ok = i < t1;
       qv[j] = ok ? P.q[i] : 0;
       cv[j] = ok ? P.contig[i] : -1;
       bv[j] = ok ? P.beg[i] : 0;
@@ -125,6 +163,9 @@ __global__ void __launch_bounds__(ORD_NT)
       lv[j] = ok ? P.len[i] : 0;
     }
   }
+#pragma unroll
+  for (int j = 0; j < ORD_ITEMS; ++j)
+    if (i0 + j < own0) cv[j] = -1;  // belongs to the previous tile's CTA
 
   ReadQ rq[ORD_ITEMS];
   int cnt[ORD_ITEMS], mt[ORD_ITEMS][4];  // first four matches per read
@@ -176,7 +217,24 @@ __global__ void __launch_bounds__(ORD_NT)
     tot += c;
   }
 
-  // block exclusive scan of per-thread totals
+  // records past the tile end that finish our last query (warp 0, one record
+  // per lane and round; rare, so matches are simply recounted when written)
+  if (warp == 0 && ext > 0) {
+    int et = 0;
+    for (int r = 0; r < ext; r += 32) {
+      const int64_t i = t1 + r + lane;
+      if (r + lane < ext) {
+        ReadQ x = ord_prepare(P, P.contig[i], P.beg[i], P.end[i], P.len[i]);
+        ord_scan(P, x, [&](int) { ++et; });
+      }
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) et += __shfl_xor_sync(FULL, et, off);
+    if (lane == 0) s_ext_tot = et;
+  }
+
+  // block exclusive scan of per-thread totals, then ONE atomic reserves the
+  // CTA's contiguous range of the pair list
   int incl = tot;
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
@@ -194,69 +252,65 @@ __global__ void __launch_bounds__(ORD_NT)
       if (lane >= off) wi += o;
     }
     if (lane < ORD_NT / 32) s_warp[lane] = wi - w;  // exclusive
-    const ull agg = (ull)__shfl_sync(FULL, wi, 31);
-    // chained scan across tiles, decoupled look-back (32 tiles per round)
-    const ull VAL = (1ull << 62) - 1;
-    volatile ull *desc = P.tile_desc;
-    ull prefix = 0;
-    if (tile == 0) {
-      if (lane == 0) desc[0] = (2ull << 62) | agg;
-    } else {
-      if (lane == 0) desc[tile] = (1ull << 62) | agg;
-      __threadfence();
-      int64_t p = tile - 1;
-      for (;;) {
-        int64_t idx = p - lane;
-        ull d = idx >= 0 ? desc[idx] : (2ull << 62);
-        while (__any_sync(FULL, (d >> 62) == 0)) {
-          if ((d >> 62) == 0) d = desc[idx];
-        }
-        unsigned incm = __ballot_sync(FULL, (d >> 62) == 2);
-        int fi = incm ? __ffs(incm) - 1 : 31;
-        ull v = lane <= fi ? (d & VAL) : 0;
-#pragma unroll
-        for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
-        prefix += v;
-        if (incm) break;
-        p -= 32;
-      }
-      if (lane == 0) {
-        __threadfence();
-        desc[tile] = (2ull << 62) | (prefix + agg);
-      }
-    }
+    const int main_tot = __shfl_sync(FULL, wi, 31);
     if (lane == 0) {
-      s_base = prefix;
-      if ((tile + 1) * ORD_TILE >= P.n) *P.n_pairs = prefix + agg;  // last tile
+      const long long block_tot = (long long)main_tot + s_ext_tot;
+      long long base = block_tot ? (long long)atomicAdd(P.n_pairs, (ull)block_tot) : 0;
+      if (base + block_tot > P.cap) {
+        atomicOr(P.err, ERR_PAIR_FULL);
+        base = -1;
+      }
+      s_base = base;
+      s_ext_tot = main_tot;  // reused: where the extension's pairs start
     }
   }
   __syncthreads();
+  if (s_base < 0) return;
 
-  int64_t off = (int64_t)s_base + s_warp[warp] + (incl - tot);
-  if (off + tot > P.cap) {
-    if (tot) atomicOr(P.err, ERR_PAIR_FULL);
-    return;
-  }
+  int64_t off = s_base + s_warp[warp] + (incl - tot);
+  auto put = [&](int64_t ri, int qq, int g) {
+    P.pair_q[off] = qq;
+    P.pair_s[off] = __ldg(P.gene_subject + g);
+    if (P.pair_r) {
+      P.pair_r[off] = (int32_t)ri;
+      P.pair_g[off] = g;
+    }
+    ++off;
+  };
 #pragma unroll
   for (int j = 0; j < ORD_ITEMS; ++j) {
     if (!cnt[j]) continue;
-    const int qq = qv[j];
-    const int64_t ri = i0 + j;
-    auto put = [&](int g) {
-      P.pair_q[off] = qq;
-      P.pair_s[off] = __ldg(P.gene_subject + g);
-      if (P.pair_r) {
-        P.pair_r[off] = (int32_t)ri;
-        P.pair_g[off] = g;
-      }
-      ++off;
-    };
     if (cnt[j] <= 4) {  // the usual case: matches kept in registers
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        if (u < cnt[j]) put(mt[j][u]);
+        if (u < cnt[j]) put(i0 + j, qv[j], mt[j][u]);
     } else {
-      ord_scan(P, rq[j], put);
+      ord_scan(P, rq[j], [&](int g) { put(i0 + j, qv[j], g); });
+    }
+  }
+  if (warp == 0 && ext > 0) {
+    int64_t ebase = s_base + s_ext_tot;
+    for (int r = 0; r < ext; r += 32) {
+      const int64_t i = t1 + r + lane;
+      int c = 0;
+      ReadQ x;
+      x.g0 = x.g1 = 0;
+      if (r + lane < ext) {
+        x = ord_prepare(P, P.contig[i], P.beg[i], P.end[i], P.len[i]);
+        ord_scan(P, x, [&](int) { ++c; });
+      }
+      int inc = c;
+#pragma unroll
+      for (int o2 = 1; o2 < 32; o2 <<= 1) {
+        int o = __shfl_up_sync(FULL, inc, o2);
+        if (lane >= o2) inc += o;
+      }
+      off = ebase + inc - c;
+      if (c) {
+        const int qq = P.q[i];
+        ord_scan(P, x, [&](int g) { put(i, qq, g); });
+      }
+      ebase += __shfl_sync(FULL, inc, 31);
     }
   }
 }
