@@ -181,6 +181,17 @@ int wk_fetch_strata(wk_ctx *ctx, int64_t *n, int32_t *entry, int32_t *sample,
                     int32_t *stratum, int64_t *feature, int64_t *units,
                     int64_t cap);
 int wk_reset_counts(wk_ctx *ctx);
+/* Read maps (replaces the taxque handed to file.write_readmap,
+ * workflow.py:1042-1046, file.py:469-500).  When enabled, every plain chunk
+ * also records, per entry and record, what that record contributed:
+ *   -1                    nothing (repeat of a subject, or no assignment)
+ *   f | WK_ASSIGN_UNIQ    on the FIRST record of a query: its single
+ *                         assignment f (f == NF means 'Unassigned')
+ *   f                     one element of the query's list of assignments
+ * out[n_entries][n_rec] for the last chunk of n_rec records. */
+#define WK_ASSIGN_UNIQ (1 << 30)
+int wk_set_assign_output(wk_ctx *ctx, int enable);
+int wk_fetch_assignments(wk_ctx *ctx, int32_t *out, int64_t n_rec);
 /* Device address / length (in int64 elements) of the units table, for a
  * caller-side NCCL reduce (torch.distributed) across GPUs. */
 int wk_counts_device(wk_ctx *ctx, void **d_ptr, int64_t *n_elems);

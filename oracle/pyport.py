@@ -139,10 +139,30 @@ def split_by_sample(qryque, subque, samples=None):
     return out
 
 
+def readmap_lines(queries, results, namedic=None):
+    """file.write_readmap (file.py:469-500) as a list of lines."""
+    label = (lambda t: namedic[t] if namedic and t in namedic else t)
+    out = []
+    for query, taxa in zip(queries, results):
+        if not taxa:
+            continue
+        if isinstance(taxa, list):
+            counts = {}
+            for t in taxa:
+                if t:
+                    counts[t] = counts.get(t, 0) + 1
+            ranked = sorted(counts.items(), key=lambda x: (-x[1], x[0]))
+            out.append('\t'.join([query] + [f'{label(t)}:{c}'
+                                             for t, c in ranked]))
+        else:
+            out.append(f'{query}\t{label(taxa)}')
+    return out
+
+
 def classify_chunks(chunks, ranks, tree=None, rankdic=None, root=None,
                     uniq=False, major=None, above=False, subok=False,
                     unasgd=False, demux=False, samples=None, sample=None,
-                    trimsub=None, strata_of=None):
+                    trimsub=None, strata_of=None, maps=None, namedic=None):
     """workflow.classify body (workflow.py:304-335, 1017-1058) over an
     iterable of (qryque, subque) chunks; `major` is the fraction."""
     data = {r: {} for r in ranks}
@@ -161,6 +181,9 @@ def classify_chunks(chunks, ranks, tree=None, rankdic=None, root=None,
                               above, subok) for s in ss]
                 if unasgd:
                     res = [x or 'Unassigned' for x in res]
+                if maps is not None:
+                    maps.setdefault(rank, {}).setdefault(sname, []).extend(
+                        readmap_lines(qs, res, namedic))
                 counts = tally(qs, res, strata)
                 total = data[rank].setdefault(sname, {})
                 for k, v in counts.items():           # util.sum_dict

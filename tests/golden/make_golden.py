@@ -129,7 +129,8 @@ CASES = []
 def run_case(name, input_rel, *, hier=None, ranks, coords_rel=None,
              overlap=80, strata_rel=None, fmt=None, demux=None, samples=None,
              trimsub=None, uniq=False, major=None, above=False, subok=False,
-             unasgd=False, exclude=None, chunk=None, note=''):
+             unasgd=False, exclude=None, chunk=None, note='', maps=False,
+             name_as_id=False):
     input_fp = join(OUT, input_rel)
     samples_, files, demux_ = W.parse_samples(input_fp, None, samples, demux)
     tree = rankdic = namedic = root = None
@@ -142,10 +143,26 @@ def run_case(name, input_rel, *, hier=None, ranks, coords_rel=None,
     stratmap = W.parse_strata(join(OUT, strata_rel), samples_) \
         if strata_rel else None
     excl = W.parse_exclude(exclude)
+    rank2dir = None
+    if maps:
+        mapdir = tempfile.mkdtemp()
+        rank2dir = {}
+        for r in ranks_:
+            rank2dir[r] = join(mapdir, str(r))
+            os.makedirs(rank2dir[r])
     data = W.classify(mapper, files, samples_, fmt, demux_, trimsub, tree,
-                      rankdic, None, root, ranks_, None, None, uniq, major,
-                      above, subok, None, unasgd, stratmap, excl, chunk_, 1024,
-                      {}, None, None)
+                      rankdic, namedic if name_as_id else None, root, ranks_,
+                      rank2dir, None, uniq, major, above, subok, None, unasgd,
+                      stratmap, excl, chunk_, 1024, {}, None, None)
+    expected_maps = None
+    if maps:
+        expected_maps = {}
+        for r, d in rank2dir.items():
+            expected_maps[str(r)] = {}
+            for fn in sorted(os.listdir(d)):
+                with open(join(d, fn)) as fh:
+                    expected_maps[str(r)][fn[:-4]] = fh.read().splitlines()
+        shutil.rmtree(mapdir)
     raw = copy.deepcopy(data)
     W.round_profiles(data, None)
     # hierarchy restricted to what this case can reach
@@ -182,7 +199,10 @@ def run_case(name, input_rel, *, hier=None, ranks, coords_rel=None,
         'above': above, 'subok': subok, 'unasgd': unasgd,
         'exclude': sorted(excl) if excl else None, 'coords': coords_rel,
         'overlap': overlap, 'prefix': prefix, 'strata': strata_rel,
-        'chunk': chunk, 'expected_raw': enc(raw),
+        'chunk': chunk, 'expected_maps': expected_maps,
+        'namedic': ({k: v for k, v in namedic.items() if k in tree_small}
+                    if name_as_id and tree_small is not None else None),
+        'expected_raw': enc(raw),
         'expected_rounded': enc(data),
     }
     with open(join(HERE, f'{name}.json'), 'w') as f:
@@ -236,6 +256,12 @@ def bundled():
         run_case(f'blastn_multi_{mode}', join('blastn', 'mux.b6o.xz'),
                  hier=nodes, ranks='phylum,genus,species,none,free', **kw,
                  note='multi-rank in one run')
+    # read maps (tests/test_cli.py:70-90 checks burst.genus.map/*.txt.gz)
+    run_case('burst_genus_map', 'burst', hier=nodes, ranks='genus', maps=True,
+             name_as_id=True, note='burst.genus.map: --outmap --name-as-id')
+    run_case('blastn_species_map', join('blastn', 'mux.b6o.xz'), hier=nodes,
+             ranks='species,none', maps=True,
+             note='read maps with taxon:count lists, demultiplexed')
     run_case('blastn_multi_default', join('blastn', 'mux.b6o.xz'), hier=nodes,
              ranks='phylum,genus,species,none,free',
              samples='S01,S03', note='sample whitelist')
@@ -310,6 +336,12 @@ def synthetic():
         os.remove(tmp)
     hier = dict(nodes_fps=[join(dt, 'nodes.dmp')],
                 map_fps=[join(dt, 'taxid.map')])
+    run_case('synth_default_map', 'synth', hier=hier,
+             ranks='phylum,genus,free,none', maps=True,
+             note='read maps: mates, duplicates, unknown subjects, 40-hit '
+                  'queries')
+    run_case('synth_unasgd_map', 'synth', hier=hier, ranks='genus,free',
+             maps=True, unasgd=True, uniq=True, note='read maps with Unassigned')
     for mode, kw in [('default', {}), ('uniq', dict(uniq=True)),
                      ('major80', dict(major=80)), ('major54', dict(major=54)),
                      ('major81', dict(major=81)), ('above', dict(above=True)),

@@ -85,9 +85,19 @@ def run_case(name, engine_factory=None):
         for fn in os.listdir(sdir):
             stratmap[fn.split('.')[0]] = join(sdir, fn)
     ranks = case['ranks']
+    rank2dir = None
     if engine_factory == 'oracle':
+        # (read maps need the kernel's assignment column: GPU test only; the
+        # CPU twin of that check is tests/test_pyport.py)
         engine_factory = make_factory(case['tree'], case['rankdic'],
                                       case['root'], ranks, case['subok'])
+    elif case.get('expected_maps'):
+        import tempfile
+        mapdir = tempfile.mkdtemp()
+        rank2dir = {}
+        for r in ranks:
+            rank2dir[r] = join(mapdir, str(r))
+            os.makedirs(rank2dir[r])
     got = classify(
         mapper, files, samples=case['samples'], fmt=case['fmt'],
         demux=case['demux'], trimsub=case['trimsub'], tree=case['tree'],
@@ -95,7 +105,16 @@ def run_case(name, engine_factory=None):
         uniq=case['uniq'], major=case['major'], above=case['above'],
         subok=case['subok'], unasgd=case['unasgd'], stratmap=stratmap,
         exclude=set(case['exclude']) if case['exclude'] else None,
-        chunk=chunk, _engine_factory=engine_factory)
+        chunk=chunk, _engine_factory=engine_factory, rank2dir=rank2dir,
+        namedic=case.get('namedic'))
+    if rank2dir is not None:
+        maps = {}
+        for r, d in rank2dir.items():
+            maps[str(r)] = {}
+            for fn in sorted(os.listdir(d)):
+                with open(join(d, fn)) as fh:
+                    maps[str(r)][fn[:-4]] = fh.read().splitlines()
+        assert maps == case['expected_maps'], 'read maps differ'
     exp_raw = dec(case['expected_raw'])
     exp_rounded = dec(case['expected_rounded'])
     return got, exp_raw, exp_rounded

@@ -173,6 +173,4 @@ def test_gene_coords_encoding():
 
 def test_unsupported_options_are_loud():
     with pytest.raises(NotImplementedError):
-        classify(None, [], ranks=['none'], rank2dir={})
-    with pytest.raises(NotImplementedError):
         classify(None, [], ranks=['none'], sizes={'a': 1.0})

@@ -32,6 +32,7 @@ def test_pyport_matches_reference(name):
                  for k in case['files']}
     ranks = case['ranks']
     total = {r: {} for r in ranks}
+    maps = {} if case.get('expected_maps') else None
     excl = set(case['exclude']) if case['exclude'] else None
     for fp in sorted(files):
         with readzip(fp) as fh:
@@ -43,10 +44,16 @@ def test_pyport_matches_reference(name):
                 demux=case['demux'],
                 samples=set(case['samples']) if case['demux'] and
                 case['samples'] else None,
-                sample=files[fp], trimsub=case['trimsub'])
+                sample=files[fp], trimsub=case['trimsub'], maps=maps,
+                namedic=case.get('namedic'))
         for r in ranks:
             for s, prof in data[r].items():
                 tgt = total[r].setdefault(s, {})
                 for k, v in prof.items():
                     tgt[k] = tgt.get(k, 0) + v
     check(total, dec(case['expected_raw']), dec(case['expected_rounded']))
+    if maps is not None:
+        # taxon:count lists tie-break on the taxon name, so set order of the
+        # subjects cannot change a line
+        got = {str(r): d for r, d in maps.items()}
+        assert got == case['expected_maps']

@@ -56,6 +56,8 @@ SIGNATURES = {
     'wk_fetch_strata': (C.c_int, [_vp, _i64p, _vp, _vp, _vp, _vp, _vp,
                                   C.c_int64]),
     'wk_reset_counts': (C.c_int, [_vp]),
+    'wk_set_assign_output': (C.c_int, [_vp, C.c_int]),
+    'wk_fetch_assignments': (C.c_int, [_vp, _vp, C.c_int64]),
     'wk_counts_device': (C.c_int, [_vp, C.POINTER(_vp), _i64p]),
 }
 

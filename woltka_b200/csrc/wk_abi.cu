@@ -175,6 +175,9 @@ struct wk_ctx {
   int64_t last_pairs = 0;
   bool keep_pairs = false;
   bool strata_keys = false;  // overflow list holds stratified keys
+  bool want_assign = false;
+  DevBuf assign;
+  int64_t assign_n = 0;  // records of the chunk the buffer belongs to
 
   ull *d_ovf_n() { return small.as<ull>() + 0; }
   ull *d_sh_used() { return small.as<ull>() + 1; }
@@ -276,7 +279,7 @@ int wk_destroy(wk_ctx *c) {
                     &c->sh_vals, &c->dq, &c->ds, &c->dqsamp, &c->dqstrat,
                     &c->scratch, &c->dcontig, &c->dbeg, &c->dend, &c->dlen,
                     &c->cinfo, &c->genes, &c->gene_subject, &c->pair_q, &c->pair_s, &c->pair_r,
-                    &c->pair_g, &c->tile_desc, &c->ticket};
+                    &c->pair_g, &c->tile_desc, &c->ticket, &c->assign};
   for (DevBuf *b : bufs) b->release();
   for (int i = 0; i < 2; ++i)
     if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
@@ -695,6 +698,13 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   P.sh_mask = c->sh_cap ? c->sh_cap - 1 : 0;
   P.sh_used = c->d_sh_used();
   P.err = c->d_err();
+  P.assign = nullptr;
+  if (c->want_assign && !n_dev) {
+    TRY(c->assign.reserve((size_t)c->E * (size_t)std::max<int64_t>(n_bound, 1) * 4));
+    P.assign = c->assign.as<int32_t>();
+    P.assign_stride = n_bound;
+    c->assign_n = n_bound;
+  }
   TRY(c->scratch.reserve((size_t)std::max<int64_t>(n_bound, 1) * 4));
   P.scratch = c->scratch.as<int32_t>();
 
@@ -1206,6 +1216,27 @@ int wk_fetch_strata(wk_ctx *c, int64_t *n, int32_t *entry, int32_t *sample,
     feature[i] = f24 == KEY_F24 ? c->NF : (int64_t)f24;
     units[i] = (int64_t)hv[i];
   }
+  return WK_OK;
+}
+
+int wk_set_assign_output(wk_ctx *c, int enable) {
+  if (!c) return fail(WK_ERR_ARG, "ctx is NULL");
+  c->want_assign = enable != 0;
+  c->assign_n = 0;
+  return WK_OK;
+}
+
+int wk_fetch_assignments(wk_ctx *c, int32_t *out, int64_t n_rec) {
+  if (!c || !c->have_plan) return fail(WK_ERR_STATE, "no plan set");
+  if (!out) return fail(WK_ERR_ARG, "out is NULL");
+  if (!c->want_assign || c->assign_n != n_rec)
+    return fail(WK_ERR_STATE,
+                "no assignments recorded for a chunk of %lld records",
+                (long long)n_rec);
+  TRY(use_device(c));
+  CK(cudaMemcpyAsync(out, c->assign.p, (size_t)c->E * n_rec * 4,
+                     cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   return WK_OK;
 }
 

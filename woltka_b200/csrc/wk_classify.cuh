@@ -49,6 +49,7 @@ constexpr int CLS_SUB = CLS_TILE / CLS_NW;     // records per warp per tile
 constexpr unsigned FULL = 0xffffffffu;
 constexpr uint32_t CACHE_EMPTY = 0xffffffffu;
 constexpr int DUPMARK = INT32_MIN;
+constexpr int ASSIGN_UNIQ = 1 << 30;  // flag: the query's single assignment
 
 enum { SINK_DIRECT = 0, SINK_HASHED = 1, SINK_GLOBAL = 2 };
 
@@ -87,6 +88,8 @@ struct ClsParams {
   ull *sh_used;
   int32_t *err;               // device error word (bit flags)
   int32_t *scratch;           // [>= n] long-query scratch
+  int32_t *assign;            // optional per-record assignment [E][stride]
+  int64_t assign_stride;      // (read maps, file.write_readmap file.py:469-500)
   int32_t cache_log;          // SINK_HASHED: log2(cache slots)
   uint32_t direct_cells;      // SINK_DIRECT: E*NF1 (one sample at a time)
 };
@@ -389,7 +392,9 @@ __device__ __noinline__ int64_t process_long(const ClsParams &P, const Sink &K,
   }
   int samp = P.q_sample ? P.q_sample[qid] : P.sample;
   int strat = P.q_stratum ? P.q_stratum[qid] : 0;
-  if (strat < 0 || (unsigned)samp >= (unsigned)P.S) return end;
+  // counts need a valid sample and stratum; the read map does not
+  const bool live = !(strat < 0 || (unsigned)samp >= (unsigned)P.S);
+  if (!live && !P.assign) return end;
 
   // set semantics of the subject pool (align.py:339): mark repeats
   int kloc = 0;
@@ -414,6 +419,11 @@ __device__ __noinline__ int64_t process_long(const ClsParams &P, const Sink &K,
     const int kind = P.kind[e];
     int result = -1;
     bool uniqres = true;
+    int32_t *asg = P.assign ? P.assign + (int64_t)e * P.assign_stride : nullptr;
+    if (asg) {
+      for (int64_t j = start + lane; j < end; j += 32) asg[j] = -1;
+      __syncwarp();
+    }
     if (kind == WK_KIND_NONE || kind == WK_KIND_NONE_ID) {
       if (k == 1) {
         result = kind == WK_KIND_NONE_ID ? s0 : tab_get<STAGED>(P, stab, e, s0);
@@ -425,7 +435,8 @@ __device__ __noinline__ int64_t process_long(const ClsParams &P, const Sink &K,
           if (__ldcg(P.scratch + j) == DUPMARK) continue;
           int sj = gs[j];
           int f = kind == WK_KIND_NONE_ID ? sj : tab_get<STAGED>(P, stab, e, sj);
-          emit_frac<SINK>(P, K, e, samp, strat, f, k);
+          if (live) emit_frac<SINK>(P, K, e, samp, strat, f, k);
+          if (asg) asg[j] = f;
         }
       }
     } else {
@@ -502,7 +513,8 @@ __device__ __noinline__ int64_t process_long(const ClsParams &P, const Sink &K,
           for (int64_t j = start + lane; j < end; j += 32) {
             int t = __ldcg(P.scratch + j);
             if (t == DUPMARK || t < 0) continue;
-            emit_frac<SINK>(P, K, e, samp, strat, t, nvalid);
+            if (live) emit_frac<SINK>(P, K, e, samp, strat, t, nvalid);
+            if (asg) asg[j] = t;
           }
         }
         // restore dup marks for the next entry
@@ -513,10 +525,12 @@ __device__ __noinline__ int64_t process_long(const ClsParams &P, const Sink &K,
       }
     }
     if (lane == 0 && uniqres) {
-      if (result >= 0)
+      if (live && result >= 0)
         emit_units<SINK>(P, K, e, samp, strat, result, (uint32_t)WK_UNITS);
-      else if (unas)
+      else if (live && unas)
         emit_units<SINK>(P, K, e, samp, strat, NF, (uint32_t)WK_UNITS);
+      if (asg && (result >= 0 || unas))
+        asg[start] = (int)(result >= 0 ? result : NF) | ASSIGN_UNIQ;
     }
   }
   return end;
@@ -775,6 +789,7 @@ __global__ void __launch_bounds__(CLS_NT, 1)
         const int kind = LEAN ? kind0 : P.kind[e];
         int result = -1;
         bool uniqres = true;
+        int aval = -1;  // this record's contribution to the read map
         if (kind == WK_KIND_RANK) {
           // classify.assign_rank (classify.py:81-127)
           // repeats carry the taxon of their first occurrence, so the
@@ -835,6 +850,7 @@ __global__ void __launch_bounds__(CLS_NT, 1)
               const unsigned vm = __ballot_sync(FULL, nd && t >= 0) & segm;
               if (!alleq) {
                 uniqres = false;
+                if (nd && t >= 0) aval = t;
                 if (live && nd && t >= 0)
                   emit_frac<SINK>(P, K, e, samp, strat, t, __popc(vm));
               }
@@ -878,6 +894,7 @@ __global__ void __launch_bounds__(CLS_NT, 1)
             result = f;
           } else if (!(flags & WK_F_UNIQ)) {
             uniqres = false;
+            if (nd) aval = f;
             if (live && nd) emit_frac<SINK>(P, K, e, samp, strat, f, k);
           }
         }
@@ -886,6 +903,11 @@ __global__ void __launch_bounds__(CLS_NT, 1)
             emit_units<SINK>(P, K, e, samp, strat, result, (uint32_t)WK_UNITS);
           else if (unas)
             emit_units<SINK>(P, K, e, samp, strat, NF, (uint32_t)WK_UNITS);
+        }
+        if (P.assign) {
+          if (ishead && uniqres && (result >= 0 || unas))
+            aval = (int)(result >= 0 ? result : NF) | ASSIGN_UNIQ;
+          if (act) P.assign[(int64_t)e * P.assign_stride + sbase + x] = aval;
         }
       }
       cur += cons;

@@ -14,7 +14,9 @@ from ._lib import (UNITS, MAX_ENTRIES, KIND_NONE, KIND_FREE, KIND_RANK,
                    KIND_NONE_ID, F_UNIQ, F_ABOVE, F_MAJOR, F_UNASSIGNED,
                    WoltkaB200Error)
 
-__all__ = ['Engine', 'UNITS', 'MAX_ENTRIES', 'KIND_NONE', 'KIND_FREE',
+ASSIGN_UNIQ = 1 << 30
+
+__all__ = ['Engine', 'ASSIGN_UNIQ', 'UNITS', 'MAX_ENTRIES', 'KIND_NONE', 'KIND_FREE',
            'KIND_RANK', 'KIND_NONE_ID', 'F_UNIQ', 'F_ABOVE', 'F_MAJOR',
            'F_UNASSIGNED', 'WoltkaB200Error', 'pinned_empty']
 
@@ -244,6 +246,16 @@ class Engine:
                 self.ctx, C.byref(n), _ptr(e), _ptr(s), _ptr(t), _ptr(f),
                 _ptr(u), m))
         return e, s, t, f, u
+
+    def set_assign_output(self, enable=True):
+        _lib.check(self.lib.wk_set_assign_output(self.ctx, int(enable)))
+
+    def fetch_assignments(self, n_rec):
+        """int32 [n_entries, n_rec] of the last plain chunk (read maps): -1,
+        feature | ASSIGN_UNIQ on a query's first record, or a list member."""
+        out = np.empty((self.E, n_rec), dtype=np.int32)
+        _lib.check(self.lib.wk_fetch_assignments(self.ctx, _ptr(out), n_rec))
+        return out
 
     def reset_counts(self):
         _lib.check(self.lib.wk_reset_counts(self.ctx))

@@ -35,7 +35,8 @@ def _split_sample(query):
 class Session:
     def __init__(self, ranks, tree=None, rankdic=None, root=None, uniq=False,
                  major=None, above=False, subok=False, unasgd=False,
-                 trimsub=None, engine_factory=None, device=0):
+                 trimsub=None, engine_factory=None, device=0, rank2dir=None,
+                 outzip=None, namedic=None):
         if engine_factory is None:
             from .engine import Engine
             engine_factory = Engine
@@ -44,6 +45,9 @@ class Session:
         self.mult = Counter(self.ranks)
         self.trimsub = trimsub
         self.subok = subok
+        self.rank2dir = rank2dir
+        self.outzip = outzip if outzip != 'none' else None
+        self.namedic = namedic
         self.ft = FlatTree.from_dicts(tree, rankdic, root) \
             if tree is not None else None
         self.T = self.ft.n_nodes if self.ft else 0
@@ -95,6 +99,8 @@ class Session:
                 eng.set_tree(self.ft.parent, self.ft.root)
             eng.set_plan(np.array([self.kinds[i] for i in grp], dtype=np.int32),
                          self.flags, self.major_th, self.S_cap, self.NF_cap)
+            if rank2dir is not None:
+                eng.set_assign_output(True)
             self.engines.append(eng)
 
     def close(self):
@@ -182,6 +188,7 @@ class Session:
         strata_of(sample_name) -> dict read -> stratum label, or None.
         Returns the number of queries in the chunk."""
         q, s, q_sample, q_stratum = [], [], [], []
+        reads, starts = [], []
         nq = 0
         use_strata = strata_of is not None
         for query, subjects in zip(qryque, subque):
@@ -199,6 +206,8 @@ class Session:
                 stratum = self.stratum(label) if label is not None else -1
             q_sample.append(self.sample(sname))
             q_stratum.append(stratum)
+            reads.append(read)
+            starts.append(len(q))
             for sub in subjects:
                 q.append(nq)
                 s.append(self.subject(sub))
@@ -214,6 +223,55 @@ class Session:
             else None
         for eng in self.engines:
             eng.classify_chunk(q, s, q_sample, q_stratum)
+        if self.rank2dir is not None:
+            starts.append(len(q))
+            self._write_readmaps(len(q), reads, starts, q_sample)
+
+    def _write_readmaps(self, n_rec, reads, starts, q_sample):
+        """Append this chunk's read-to-taxon lines (file.write_readmap,
+        file.py:469-500, called at workflow.py:1042-1046): one line per
+        assigned query; a unique assignment prints the taxon, a list prints
+        `taxon:count` sorted by count (high to low) then name."""
+        from os.path import join
+        from .engine import ASSIGN_UNIQ
+        from .workflow import openzip
+        namedic = self.namedic
+        for grp, eng in zip(self.groups, self.engines):
+            asg = eng.fetch_assignments(n_rec)
+            for e, gi in enumerate(grp):
+                rank = self.order[gi]
+                lines = {}
+                row = asg[e]
+                for j, read in enumerate(reads):
+                    vals = row[starts[j]:starts[j + 1]]
+                    vals = vals[vals >= 0]
+                    if not len(vals):
+                        continue
+                    if vals[0] & ASSIGN_UNIQ:
+                        name = self.feature_name(int(vals[0]) & ~ASSIGN_UNIQ)
+                        if namedic and name in namedic:
+                            name = namedic[name]
+                        text = f'{read}\t{name}'
+                    else:
+                        counts = {}
+                        for v in vals.tolist():
+                            name = self.feature_name(v)
+                            counts[name] = counts.get(name, 0) + 1
+                        parts = [read]
+                        for name, c in sorted(counts.items(),
+                                              key=lambda x: (-x[1], x[0])):
+                            if namedic and name in namedic:
+                                name = namedic[name]
+                            parts.append(f'{name}:{c}')
+                        text = '\t'.join(parts)
+                    lines.setdefault(int(q_sample[j]), []).append(text)
+                for si, rows in lines.items():
+                    fp = join(self.rank2dir[rank],
+                              f'{self.sample_names[si]}.txt')
+                    if self.outzip:
+                        fp = f'{fp}.{self.outzip}'
+                    with openzip(fp, 'at') as fh:
+                        fh.write('\n'.join(rows) + '\n')
 
     def add_ordinal_chunk(self, genes, qnames, contigs, beg, end, length, th,
                           demux, sample_name, samples=None, strata_of=None):

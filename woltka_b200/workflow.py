@@ -14,9 +14,11 @@ no CPU fallback.  Everything around it (sample discovery, hierarchy readers,
 frac/scale/round, table writers) is the reference's own code and is called
 unchanged by its `workflow()`.
 
-Not re-implemented in this round (rows F3-F5 of SURVEY.md §8f): read-map
-output (`rank2dir`), size-weighted counting (`sizes`) and coverage
-(`outcov_dir`) raise NotImplementedError instead of silently falling back.
+Read maps (`rank2dir`) come from a per-record
+assignment column the kernel writes next to the counts.  Not re-implemented in
+this round (rows F4-F5): size-weighted counting (`sizes`), coverage
+(`outcov_dir`) and read maps of the ordinal path raise NotImplementedError
+instead of silently falling back.
 """
 import bz2
 import gzip
@@ -43,6 +45,14 @@ def readzip(fp, zippers=None):
         if fp.endswith(ext):
             return opener(fp, 'rt')
     return open(fp, 'r')
+
+
+def openzip(fp, mode='rt'):
+    """Open a plain or gz/bz2/xz file by extension (file.py:31-59)."""
+    for ext, opener in _OPENERS.items():
+        if fp.endswith(ext):
+            return opener(fp, mode)
+    return open(fp, mode.replace('t', '') if 'b' in mode else mode)
 
 
 def _echo(msg, nl=True):
@@ -98,9 +108,11 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
     the reference accumulates 1/k shares in floating point; after
     `round_profiles` the two are identical.
     """
-    if rank2dir is not None:
+    is_ordinal = getattr(mapper, 'func', None) is ordinal_mapper
+    if rank2dir is not None and is_ordinal:
         raise NotImplementedError(
-            'Read-map output (--outmap) is not part of the GPU hot path yet.')
+            'Read-map output (--outmap) with --coords is not part of the GPU '
+            'hot path yet.')
     if sizes:
         raise NotImplementedError(
             'Size-normalised counting (--sizes) is not part of the GPU hot '
@@ -109,7 +121,6 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
         raise NotImplementedError(
             'Subject coverage (--outcov) is not part of the GPU hot path.')
 
-    is_ordinal = getattr(mapper, 'func', None) is ordinal_mapper
     genes = None
     if is_ordinal:
         kw = mapper.keywords
@@ -117,7 +128,8 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
         th = kw.get('th', 0.8)
 
     sess = Session(ranks, tree, rankdic, root, uniq, major and major / 100,
-                   above, subok, unasgd, trimsub, _engine_factory, _device)
+                   above, subok, unasgd, trimsub, _engine_factory, _device,
+                   rank2dir, outzip, namedic)
     samset = set(samples) if samples else None
     strata_cache = {}
 
