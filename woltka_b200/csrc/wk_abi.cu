@@ -14,6 +14,7 @@
 
 #include "wk_classify.cuh"
 #include "wk_ordinal.cuh"
+#include "wk_sweep.cuh"
 
 using namespace wk;
 
@@ -131,7 +132,7 @@ struct wk_ctx {
   cudaEvent_t ev_copy[2] = {nullptr, nullptr};
   cudaEvent_t ev_free = nullptr;
   int64_t launches = 0;
-  int tune_grid = 0, tune_cache = 0;
+  int tune_grid = 0, tune_cache = 0, tune_block = 0;
   // tree
   DevBuf parent;
   int32_t T = 0, root = -1;
@@ -152,7 +153,7 @@ struct wk_ctx {
   // host copies for (re)packing the shared-memory staging block
   std::vector<int32_t> h_parent, h_tab, h_sub_node;
   bool stage_dirty = true;
-  int32_t sn16_off = -1, par16_off = -1, stage_elems = 0;
+  int32_t sn16_off = -1, par16_off = -1, stage_elems = 0, stage_vmax = -1;
   int32_t n_levels = 0, level_off[40];
   // overflow + err
   DevBuf ovf_key, ovf_den, small;  // small: [0]=ovf_n [1]=sh_used [2]=n_pairs [3]=cursor, err after
@@ -261,7 +262,19 @@ int wk_create(int device, wk_ctx **out) {
         (const void *)classify_kernel<true, SINK_GLOBAL, false>,
         (const void *)classify_kernel<false, SINK_DIRECT, false>,
         (const void *)classify_kernel<false, SINK_HASHED, false>,
-        (const void *)classify_kernel<false, SINK_GLOBAL, false>};
+        (const void *)classify_kernel<false, SINK_GLOBAL, false>,
+        (const void *)classify_sweep_kernel<true, SINK_DIRECT, true>,
+        (const void *)classify_sweep_kernel<true, SINK_HASHED, true>,
+        (const void *)classify_sweep_kernel<true, SINK_GLOBAL, true>,
+        (const void *)classify_sweep_kernel<false, SINK_DIRECT, true>,
+        (const void *)classify_sweep_kernel<false, SINK_HASHED, true>,
+        (const void *)classify_sweep_kernel<false, SINK_GLOBAL, true>,
+        (const void *)classify_sweep_kernel<true, SINK_DIRECT, false>,
+        (const void *)classify_sweep_kernel<true, SINK_HASHED, false>,
+        (const void *)classify_sweep_kernel<true, SINK_GLOBAL, false>,
+        (const void *)classify_sweep_kernel<false, SINK_DIRECT, false>,
+        (const void *)classify_sweep_kernel<false, SINK_HASHED, false>,
+        (const void *)classify_sweep_kernel<false, SINK_GLOBAL, false>};
     for (const void *fn : variants)
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)c->smem_optin));
@@ -308,7 +321,7 @@ int64_t wk_launch_count(wk_ctx *c) { return c ? c->launches : 0; }
 
 int wk_set_tuning(wk_ctx *c, int grid, int block, int cache_slots) {
   if (!c) return fail(WK_ERR_ARG, "ctx is NULL");
-  (void)block;
+  c->tune_block = block;  // 1 = window kernel (classify_kernel) instead of sweep
   c->tune_grid = grid;
   c->tune_cache = cache_slots;
   return WK_OK;
@@ -595,6 +608,7 @@ static int pack_stage(wk_ctx *c) {
     if (c->kind[e] == WK_KIND_NONE_ID) continue;
     for (int64_t i = 0; i < V; ++i) vmax = std::max(vmax, c->h_tab[(size_t)e * V + i]);
   }
+  c->stage_vmax = vmax;
   if (vmax >= 0xFFFF) return WK_OK;
   const int64_t Vp = (V + 7) & ~7ll;
   size_t elems = (size_t)c->E * Vp;
@@ -708,9 +722,82 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   TRY(c->scratch.reserve((size_t)std::max<int64_t>(n_bound, 1) * 4));
   P.scratch = c->scratch.as<int32_t>();
 
-  const bool staged = c->tab16_ok && !all_id;
-  const int64_t tab_bytes = staged ? (int64_t)c->stage_elems * 2 : 0;
+  bool staged = c->tab16_ok && !all_id;
+  const bool lean = c->E == 1 && !dqsamp && !dqstrat;
   const size_t cells = (size_t)c->E * c->S * (c->NF + 1);
+  int grid = c->tune_grid > 0 ? c->tune_grid : c->sm_count;
+
+  // ---- the sweep kernel (wk_sweep.cuh) unless the window kernel is forced ----
+  if (c->tune_block != 1) {
+    // its scratch column is uint16 next to staged tables: every value an
+    // entry can produce must stay below the two markers
+    bool st = staged && c->stage_vmax < 0xFFFE;
+    for (int e = 0; e < c->E && st; ++e) {
+      if (c->kind[e] == WK_KIND_FREE && c->T >= 0xFFFE) st = false;
+      if (c->kind[e] == WK_KIND_NONE_ID && c->V >= 0xFFFE) st = false;
+    }
+    const int64_t tbytes = st ? (int64_t)c->stage_elems * 2 : 0;
+    const int tsb = st ? 2 : 4;
+    auto pick_r = [&](int sk, int cl, uint32_t dc) {
+      for (int R = SW_RMAX; R >= 3; R -= 2)
+        if (sw_layout(R, sk, cl, dc, tbytes, tsb).total <= c->smem_optin) return R;
+      return 0;
+    };
+    int sink = SINK_GLOBAL, cache_log = 0, R = 0;
+    uint32_t dcells = 0;
+    if (!dqstrat && c->tune_cache >= 0) {
+      const size_t dc = (size_t)c->E * (c->NF + 1);  // one sample at a time
+      const bool want_hashed = c->tune_cache > 0 && c->tune_cache < 1000000;
+      if (!want_hashed && dc < (1u << 24) && (R = pick_r(SINK_DIRECT, 0, (uint32_t)dc)) >= 7) {
+        sink = SINK_DIRECT;
+        dcells = (uint32_t)dc;
+      } else if (cells < 0xFFFFFFFFull) {
+        int want = 13;
+        if (c->tune_cache > 0) {
+          want = 0;
+          while ((1 << (want + 1)) <= c->tune_cache) ++want;
+        }
+        for (cache_log = want; cache_log >= 8; --cache_log)
+          if ((R = pick_r(SINK_HASHED, cache_log, 0)) >= 7) break;
+        if (cache_log >= 8) sink = SINK_HASHED;
+        else cache_log = 0;
+      }
+    }
+    if (sink == SINK_GLOBAL) R = pick_r(SINK_GLOBAL, 0, 0);
+    if (R >= 3) {
+      P.sw_R = R;
+      P.cache_log = cache_log;
+      P.direct_cells = dcells;
+      SwSmemLayout L = sw_layout(R, sink, cache_log, dcells, tbytes, tsb);
+      const int64_t tile = (int64_t)SW_NT * R;
+      int64_t span = (n_dev ? n_bound : r1) - (r0 & ~3ll);
+      int64_t n_tiles = (span + tile - 1) / tile;
+      if (n_tiles <= 0) return WK_OK;
+      grid = (int)std::min<int64_t>(grid, n_tiles);
+#define WK_SWEEP(ST, SK)                                                         \
+  do {                                                                           \
+    if (lean)                                                                    \
+      classify_sweep_kernel<ST, SK, true><<<grid, SW_NT, L.total, c->stream>>>(P); \
+    else                                                                         \
+      classify_sweep_kernel<ST, SK, false><<<grid, SW_NT, L.total, c->stream>>>(P); \
+  } while (0)
+      if (st) {
+        if (sink == SINK_DIRECT) WK_SWEEP(true, SINK_DIRECT);
+        else if (sink == SINK_HASHED) WK_SWEEP(true, SINK_HASHED);
+        else WK_SWEEP(true, SINK_GLOBAL);
+      } else {
+        if (sink == SINK_DIRECT) WK_SWEEP(false, SINK_DIRECT);
+        else if (sink == SINK_HASHED) WK_SWEEP(false, SINK_HASHED);
+        else WK_SWEEP(false, SINK_GLOBAL);
+      }
+#undef WK_SWEEP
+      c->launches++;
+      CK(cudaGetLastError());
+      return WK_OK;
+    }
+  }
+
+  const int64_t tab_bytes = staged ? (int64_t)c->stage_elems * 2 : 0;
   // where counts are accumulated first (wk_classify.cuh, "count sinks")
   int sink = SINK_GLOBAL, cache_log = 0;
   if (!dqstrat && c->tune_cache >= 0) {
@@ -750,9 +837,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   int64_t span = (n_dev ? n_bound : r1) - (r0 & ~3ll);
   int64_t n_tiles = (span + CLS_TILE - 1) / CLS_TILE;
   if (n_tiles <= 0) return WK_OK;
-  int grid = c->tune_grid > 0 ? c->tune_grid : c->sm_count;
   grid = (int)std::min<int64_t>(grid, n_tiles);
-  const bool lean = c->E == 1 && !dqsamp && !dqstrat;
 #define WK_LAUNCH(ST, SK)                                                    \
   do {                                                                       \
     if (lean)                                                                \

@@ -92,6 +92,7 @@ struct ClsParams {
   int64_t assign_stride;      // (read maps, file.write_readmap file.py:469-500)
   int32_t cache_log;          // SINK_HASHED: log2(cache slots)
   uint32_t direct_cells;      // SINK_DIRECT: E*NF1 (one sample at a time)
+  int32_t sw_R;               // classify_sweep_kernel: records per lane and tile
 };
 
 enum { ERR_BAD_SUBJECT = 1, ERR_OVF_FULL = 2, ERR_HASH_FULL = 4,
