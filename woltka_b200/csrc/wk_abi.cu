@@ -729,18 +729,14 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
 
   // ---- the sweep kernel (wk_sweep.cuh) unless the window kernel is forced ----
   if (c->tune_block != 1) {
-    // its scratch column is uint16 next to staged tables: every value an
-    // entry can produce must stay below the two markers
-    bool st = staged && c->stage_vmax < 0xFFFE;
-    for (int e = 0; e < c->E && st; ++e) {
-      if (c->kind[e] == WK_KIND_FREE && c->T >= 0xFFFE) st = false;
-      if (c->kind[e] == WK_KIND_NONE_ID && c->V >= 0xFFFE) st = false;
-    }
+    // its scratch words hold 24-bit values
+    const bool st = staged;
     const int64_t tbytes = st ? (int64_t)c->stage_elems * 2 : 0;
-    const int tsb = st ? 2 : 4;
     auto pick_r = [&](int sk, int cl, uint32_t dc) {
+      if (std::max<int64_t>(std::max<int64_t>(c->NF + 1, c->T), P.V) > SW_MAX_VALUE)
+        return 0;
       for (int R = SW_RMAX; R >= 3; R -= 2)
-        if (sw_layout(R, sk, cl, dc, tbytes, tsb).total <= c->smem_optin) return R;
+        if (sw_layout(R, sk, cl, dc, tbytes).total <= c->smem_optin) return R;
       return 0;
     };
     int sink = SINK_GLOBAL, cache_log = 0, R = 0;
@@ -768,7 +764,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
       P.sw_R = R;
       P.cache_log = cache_log;
       P.direct_cells = dcells;
-      SwSmemLayout L = sw_layout(R, sink, cache_log, dcells, tbytes, tsb);
+      SwSmemLayout L = sw_layout(R, sink, cache_log, dcells, tbytes);
       const int64_t tile = (int64_t)SW_NT * R;
       int64_t span = (n_dev ? n_bound : r1) - (r0 & ~3ll);
       int64_t n_tiles = (span + tile - 1) / tile;

@@ -17,13 +17,17 @@
 //
 //   * tiles of SW_NT*R records of both columns land in shared memory through
 //     TMA bulk copies (cp.async.bulk + mbarrier complete_tx), 2 stages;
-//   * set semantics of the subject pool (align.py:339): a record repeats an
-//     earlier subject of its query iff a look-back over the query finds it;
-//   * per record the entry's table value goes to a per-tile scratch column
-//     `ts` (uint16 when the tables are staged), so that the per-query work at
-//     the tail (1/k' split, majority, LCA fold) re-reads values, not tables;
+//   * sweep A (per entry of the plan) walks the run once: set semantics of
+//     the subject pool (align.py:339) through a 32-bit signature of the query's
+//     subjects, exact look-back only on a signature hit; the entry's table
+//     value of every record goes to a per-tile scratch column `em`; at the
+//     tail of a query its assignment (unique result, or the denominator of
+//     the 1/k' split) is written into the head's word;
+//   * sweep B walks the same records again and emits: one unit at the head of
+//     a uniquely assigned query, 1/k' at every contributing record otherwise —
+//     no per-query loop, no divergence beyond the predicate;
 //   * counts leave through the same sinks as classify_kernel;
-//   * queries longer than SW_LONGK records are handed, after the sweep, to
+//   * queries longer than SW_LONGK records are handed, after the sweeps, to
 //     the warp-cooperative process_long.
 #pragma once
 #include "wk_classify.cuh"
@@ -36,24 +40,42 @@ constexpr int SW_PRE = 4;       // records staged before the tile
 constexpr int SW_POST = 44;     // halo after the tile (>= SW_LONGK + 3)
 constexpr int SW_LONGK = 40;    // longer queries take process_long
 constexpr int SW_RMAX = 21;     // records per lane and tile (odd)
-constexpr int TS_DUP = -2;      // ts marker: repeat of an earlier subject
+
+// scratch word of a record: value (24 bits) | denominator (6 bits, head only,
+// 0 = unique assignment) | head flag (bit 31)
+constexpr uint32_t EM_VMASK = 0xFFFFFFu;
+constexpr uint32_t EM_NONE = 0xFFFFFFu;  // no value (None)
+constexpr uint32_t EM_DUP = 0xFFFFFEu;   // repeat of an earlier subject
+constexpr uint32_t EM_HEAD = 0x80000000u;
+constexpr int64_t SW_MAX_VALUE = 0xFFFFFD;  // largest feature / node / subject
+
+// units of one 1/d share, d = 0 meaning a unique assignment; 0 = d does not
+// divide WK_UNITS (overflow list)
+__constant__ uint32_t c_units64[64] = {
+    720720, 720720, 360360, 240240, 180180, 144144, 120120, 102960, 90090,
+    80080,  72072,  65520,  60060,  55440,  51480,  48048,  45045,  0,
+    40040,  0,      36036,  34320,  32760,  0,      30030,  0,      27720,
+    0,      25740,  0,      24024,  0,      0,      21840,  0,      20592,
+    20020,  0,      0,      18480,  18018,  0,      17160,  0,      16380,
+    16016,  0,      0,      15015,  0,      0,      0,      13860,  0,
+    0,      13104,  12870,  0,      0,      0,      12012,  0,      0,
+    11440};
 
 struct SwSmemLayout {
-  uint32_t bars, tiles, ts, sink0, sink1, tab, total;
+  uint32_t bars, tiles, em, sink0, sink1, tab, total;
   int R, tbuf;
 };
 __host__ __device__ inline SwSmemLayout sw_layout(int R, int sink,
                                                   int cache_log,
                                                   uint32_t direct_cells,
-                                                  int64_t tab_bytes,
-                                                  int ts_bytes) {
+                                                  int64_t tab_bytes) {
   SwSmemLayout L;
   L.R = R;
   L.tbuf = SW_NT * R + SW_PRE + SW_POST;
   L.bars = 0;
   L.tiles = 128;
-  L.ts = L.tiles + SW_STAGES * 2 * (uint32_t)L.tbuf * 4;
-  L.sink0 = (L.ts + (uint32_t)L.tbuf * ts_bytes + 15) & ~15u;
+  L.em = L.tiles + SW_STAGES * 2 * (uint32_t)L.tbuf * 4;
+  L.sink0 = L.em + (uint32_t)L.tbuf * 4;
   uint32_t w0 = 0, w1 = 0;
   if (sink == SINK_DIRECT) w0 = direct_cells * 4;
   if (sink == SINK_HASHED) w0 = w1 = (1u << cache_log) * 4;
@@ -63,237 +85,246 @@ __host__ __device__ inline SwSmemLayout sw_layout(int R, int sink,
   return L;
 }
 
-// per-tile scratch column
-template <bool STAGED>
-__device__ __forceinline__ void ts_put(uint32_t ts, int x, int v) {
-  if (STAGED) {
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(ts + (uint32_t)x * 2u),
-                 "h"((unsigned short)v)
-                 : "memory");
-  } else {
-    sts32(ts + (uint32_t)x * 4u, (uint32_t)v);
-  }
-}
-template <bool STAGED>
-__device__ __forceinline__ int ts_get(uint32_t ts, int x) {
-  if (STAGED) {
-    int u = (int)lds16(ts + (uint32_t)x * 2u);
-    return u >= 0xFFFE ? u - 0x10000 : u;  // 0xFFFF = none, 0xFFFE = repeat
-  } else {
-    return lds32(ts + (uint32_t)x * 4u);
-  }
-}
-
 struct SwRun {
-  int w0, w1;        // own records [w0, w1) in staged coordinates
-  int nrel;          // staged records that exist
-  int xstop;         // one past the last record of an owned, finished query
-  int longa;         // head of an owned query longer than SW_LONGK, or -1
-  bool own0;         // record w0 starts a query
-  ull tailm, dupm;   // bit (x - w0): record x ends its query / is a repeat
+  int w0, w1;   // own records [w0, w1) in staged coordinates
+  int nrel;     // staged records that exist
+  int xfirst;   // first owned head
+  int xstop;    // one past the last record of an owned, finished query
+  int longa;    // head of an owned query longer than SW_LONGK, or -1
 };
 
-// One entry of the plan over one run.  FIRST also finds the query structure
-// (tails, repeats, the long query); later entries replay it from the masks.
-template <bool STAGED, int SINK, bool LEAN, bool FIRST>
-__device__ __forceinline__ void sweep_entry(const ClsParams &P, const Sink &K,
-                                            const TreeRef &TR, uint32_t aq,
-                                            uint32_t as, uint32_t ts,
-                                            uint32_t stab, uint32_t sn16,
-                                            uint32_t prop_addr, int64_t sbase,
-                                            int e, int kind, uint32_t flags,
-                                            int V32, SwRun &S) {
-  const int64_t NF = P.NF1 - 1;
-  const bool unas = flags & WK_F_UNASSIGNED;
-  const bool per_query = !LEAN && (P.q_sample || P.q_stratum);
-  int32_t *asg = P.assign ? P.assign + (int64_t)e * P.assign_stride + sbase
-                          : nullptr;
-  const int w0 = S.w0;
-  int x = w0;
-  bool owned = S.own0, atstart = true;
-  int a = x;
-  ull tm = FIRST ? 0ull : S.tailm, dm = FIRST ? 0ull : S.dupm;
-  int t0 = -1, nvalid = 0, k = 0;
-  bool alleq = true, anyneg = false;
-  int samp = P.sample, strat = 0;
-  int qc = 0;
+// table value of subject sv at entry e as a scratch value
+template <bool STAGED>
+__device__ __forceinline__ uint32_t sw_tab(const ClsParams &P, uint32_t stab,
+                                           int e, int sv) {
+  if (STAGED) {
+    const uint32_t v = lds16(stab + (uint32_t)(e * P.Vp + sv) * 2u);
+    return v == 0xFFFFu ? EM_NONE : v;
+  } else {
+    return (uint32_t)__ldg(P.tab + (int64_t)e * P.V + sv) & EM_VMASK;
+  }
+}
+
+__device__ __forceinline__ uint32_t sw_lca_fold(const TreeRef &TR, uint32_t em,
+                                                int a, int x, int root) {
+  int acc = lds32(em + (uint32_t)a * 4u) & EM_VMASK;
+#pragma unroll 1
+  for (int j = a + 1; j <= x; ++j) {
+    const uint32_t vj = (uint32_t)lds32(em + (uint32_t)j * 4u) & EM_VMASK;
+    if (vj != EM_DUP) acc = lca2(TR, acc, (int)vj);
+  }
+  return acc == root ? EM_NONE : (uint32_t)acc;
+}
+
+// classify.majority (classify.py:300-317): top count among the distinct
+// subjects' values, first seen wins ties; None is a value like any other
+__device__ __noinline__ uint32_t sw_majority(uint32_t em, int a, int x, int k,
+                                             double th) {
+  int best = 0;
+  uint32_t tw = EM_NONE;
+#pragma unroll 1
+  for (int j = a; j <= x; ++j) {
+    const uint32_t vj = (uint32_t)lds32(em + (uint32_t)j * 4u) & EM_VMASK;
+    if (vj == EM_DUP) continue;
+    int c = 0;
+#pragma unroll 1
+    for (int j2 = a; j2 <= x; ++j2)
+      c += ((uint32_t)lds32(em + (uint32_t)j2 * 4u) & EM_VMASK) == vj;
+    if (c > best) {
+      best = c;
+      tw = vj;
+    }
+  }
+  return ((double)best >= __dmul_rn((double)k, th)) ? tw : EM_NONE;
+}
+
+// Sweep A of one entry: values + per-query assignment into `em`.
+template <bool STAGED, bool FIRST>
+__device__ __forceinline__ void sweep_assign(const ClsParams &P,
+                                             const TreeRef &TR, uint32_t aq,
+                                             uint32_t as, uint32_t em,
+                                             uint32_t stab, uint32_t sn16,
+                                             int e, int kind, uint32_t flags,
+                                             int V32, SwRun &S) {
+  int x;
   if (FIRST) {
     S.longa = -1;
-    if (x < S.w1) qc = lds32(aq + (uint32_t)x * 4u);
-  }
-  for (;;) {
-    if (FIRST) {
-      if (x >= S.w1 && (atstart || !owned)) break;
-    } else {
-      if (x >= S.xstop) break;
+    S.xfirst = S.xstop = S.w0;
+    x = S.w0;
+    if (x >= S.w1) return;
+    // skip the records that continue a query of the previous run
+    const bool own0 = lds32(aq + (uint32_t)x * 4u - 4u) != lds32(aq + (uint32_t)x * 4u);
+    if (!own0) {
+#pragma unroll 1
+      for (;;) {
+        bool tail = true;
+        if (x + 1 < S.nrel)
+          tail = lds32(aq + (uint32_t)x * 4u) != lds32(aq + (uint32_t)x * 4u + 4u);
+        ++x;
+        if (tail || x >= S.w1) break;
+      }
     }
-    const int i = x - w0;
-    bool tail, dup;
-    int sv = lds32(as + (uint32_t)x * 4u);
+    if (x >= S.w1) return;  // no head in this run
+    S.xfirst = S.xstop = x;
+  } else {
+    x = S.xfirst;
+    if (x >= S.xstop) return;
+  }
+  const uint32_t NFv = (uint32_t)(P.NF1 - 1);
+  const bool unas = flags & WK_F_UNASSIGNED;
+  int a = x;
+  uint32_t t0 = EM_NONE, sig = 0;
+  int nvalid = 0, k = 0, alleq = 1, anyneg = 0;
+  int qc = 0;
+  if (FIRST) qc = lds32(aq + (uint32_t)x * 4u);
+#pragma unroll 1
+  for (;;) {
+    const bool ishead = x == a;
+    const int sv = lds32(as + (uint32_t)x * 4u);
+    bool tail, dup = false;
     if (FIRST) {
       int qn = ~qc;
       if (x + 1 < S.nrel) qn = lds32(aq + (uint32_t)x * 4u + 4u);
       tail = qn != qc;
       qc = qn;
-      dup = false;
-      if (owned) {
-        if ((unsigned)sv >= (unsigned)V32) {
-          atomicOr(P.err, ERR_BAD_SUBJECT);
-          dup = true;
-        } else {
-          // set semantics (align.py:339): look back over the query
+      if ((unsigned)sv >= (unsigned)V32) {
+        atomicOr(P.err, ERR_BAD_SUBJECT);
+        dup = true;
+      } else {
+        // set semantics (align.py:339): signature of the query's subjects,
+        // exact look-back only when the bit is already taken
+        const uint32_t b = 1u << (sv & 31);
+        if (ishead) sig = 0;
+        if (sig & b) {
+#pragma unroll 1
           for (int j = a; j < x; ++j) dup |= lds32(as + (uint32_t)j * 4u) == sv;
         }
-      }
-      if (!LEAN) {
-        tm |= (ull)tail << i;
-        dm |= (ull)dup << i;
+        sig |= b;
       }
     } else {
-      tail = (tm >> i) & 1ull;
-      dup = (dm >> i) & 1ull;
+      // structure left behind by the previous entry
+      dup = ((uint32_t)lds32(em + (uint32_t)x * 4u) & EM_VMASK) == EM_DUP ||
+            (unsigned)sv >= (unsigned)V32;
+      tail = x + 1 >= S.xstop || lds32(em + (uint32_t)x * 4u + 4u) < 0;
     }
 
-    if (owned) {
-      if (x == a && per_query) {
-        const int qid = lds32(aq + (uint32_t)x * 4u);
-        samp = P.q_sample ? __ldg(P.q_sample + qid) : P.sample;
-        strat = P.q_stratum ? __ldg(P.q_stratum + qid) : 0;
-      }
-      int v = TS_DUP;
-      if (!dup) {
-        ++k;
-        if (kind == WK_KIND_RANK) {
-          v = tab_get<STAGED>(P, stab, e, sv);
-          if (x == a) t0 = v;
-          alleq &= (v == t0);
-          nvalid += (v >= 0);
-          anyneg |= (v < 0);
-        } else if (kind == WK_KIND_FREE) {
-          if (sn16) {
-            unsigned u = lds16(sn16 + (uint32_t)sv * 2u);
-            v = u == 0xFFFFu ? -1 : (int)u;
-          } else {
-            v = __ldg(P.sub_node + sv);
-          }
-          anyneg |= (v < 0);
-        } else if (kind == WK_KIND_NONE) {
-          v = tab_get<STAGED>(P, stab, e, sv);
+    uint32_t v = EM_DUP;
+    if (!dup) {
+      ++k;
+      if (kind == WK_KIND_RANK) {
+        v = sw_tab<STAGED>(P, stab, e, sv);
+        if (ishead) t0 = v;
+        alleq &= (v == t0);
+        nvalid += (v != EM_NONE);
+        anyneg |= (v == EM_NONE);
+      } else if (kind == WK_KIND_FREE) {
+        if (sn16) {
+          v = lds16(sn16 + (uint32_t)sv * 2u);
+          if (v == 0xFFFFu) v = EM_NONE;
         } else {
-          v = sv;
+          v = (uint32_t)__ldg(P.sub_node + sv) & EM_VMASK;
         }
+        anyneg |= (v == EM_NONE);
+      } else if (kind == WK_KIND_NONE) {
+        v = sw_tab<STAGED>(P, stab, e, sv);
+        if (ishead) t0 = v;
+      } else {
+        v = (uint32_t)sv;
+        if (ishead) t0 = v;
       }
-      ts_put<STAGED>(ts, x, v);
-      if (asg) asg[x] = -1;
     }
+    sts32(em + (uint32_t)x * 4u, v | (ishead ? EM_HEAD : 0u));
 
     if (tail) {
-      if (owned) {
-        // ---- the query [a, x] is complete: assign + count ----------------
-        const bool live = strat >= 0 && (unsigned)samp < (unsigned)P.S;
-        if (SINK == SINK_DIRECT && per_query && live && samp != K.cur)
-          sts32(prop_addr, (uint32_t)samp);  // ask for the table to follow
-        int result = -1;
-        bool uniqres = true;
-        if (k == 0) {
-          result = -1;  // only reachable with a bad subject (error raised)
-        } else if (kind == WK_KIND_RANK) {
-          // classify.assign_rank (classify.py:81-127)
-          if (alleq) {
-            result = t0;
-          } else if (flags & WK_F_MAJOR) {
-            // classify.majority (classify.py:300-317): top count, first seen
-            // wins ties; None (-1) is a value like any other
-            int best = 0, tw = -1;
-            for (int j = a; j <= x; ++j) {
-              const int tj = ts_get<STAGED>(ts, j);
-              if (tj == TS_DUP) continue;
-              int c = 0;
-              for (int j2 = a; j2 <= x; ++j2) c += ts_get<STAGED>(ts, j2) == tj;
-              if (c > best) {
-                best = c;
-                tw = tj;
-              }
-            }
-            result = ((double)best >= __dmul_rn((double)k, P.major_th)) ? tw : -1;
-          } else if (flags & WK_F_ABOVE) {
-            if (!anyneg) {
-              int acc = ts_get<STAGED>(ts, a);
-              for (int j = a + 1; j <= x; ++j) {
-                const int tj = ts_get<STAGED>(ts, j);
-                if (tj >= 0) acc = lca2(TR, acc, tj);
-              }
-              result = acc == P.root ? -1 : acc;
-            }
-          } else if (!(flags & WK_F_UNIQ)) {
-            uniqres = false;  // 1/k' to every subject with a taxon at the rank
-            for (int j = a; j <= x; ++j) {
-              const int tj = ts_get<STAGED>(ts, j);
-              if (tj < 0) continue;
-              if (live) emit_frac<SINK>(P, K, e, samp, strat, tj, nvalid);
-              if (asg) asg[j] = tj;
-            }
-          }
-        } else if (kind == WK_KIND_FREE) {
-          // classify.assign_free (classify.py:54-78)
-          if (k == 1) {
-            result = tab_get<STAGED>(P, stab, e, lds32(as + (uint32_t)a * 4u));
-          } else if (!anyneg) {
-            int acc = ts_get<STAGED>(ts, a);
-            for (int j = a + 1; j <= x; ++j) {
-              const int tj = ts_get<STAGED>(ts, j);
-              if (tj >= 0) acc = lca2(TR, acc, tj);
-            }
-            result = acc == P.root ? -1 : acc;
-          }
-        } else {
-          // classify.assign_none (classify.py:32-51)
-          if (k == 1) {
-            result = ts_get<STAGED>(ts, a);
-          } else if (!(flags & WK_F_UNIQ)) {
-            uniqres = false;
-            for (int j = a; j <= x; ++j) {
-              const int fj = ts_get<STAGED>(ts, j);
-              if (fj < 0) continue;
-              if (live) emit_frac<SINK>(P, K, e, samp, strat, fj, k);
-              if (asg) asg[j] = fj;
-            }
-          }
+      // ---- the query [a, x] is complete: its assignment ------------------
+      uint32_t d = 0, r = EM_NONE;
+      if (k == 0) {
+        // only reachable with a bad subject (the call fails)
+      } else if (kind == WK_KIND_RANK) {
+        // classify.assign_rank (classify.py:81-127)
+        if (alleq) {
+          r = t0;
+        } else if (flags & WK_F_MAJOR) {
+          r = sw_majority(em, a, x, k, P.major_th);
+        } else if (flags & WK_F_ABOVE) {
+          if (!anyneg) r = sw_lca_fold(TR, em, a, x, P.root);
+        } else if (!(flags & WK_F_UNIQ)) {
+          d = (uint32_t)nvalid;  // 1/k' to every subject with a taxon
+          r = t0;
         }
-        if (uniqres) {
-          if (live) {
-            if (result >= 0)
-              emit_units<SINK>(P, K, e, samp, strat, result, (uint32_t)WK_UNITS);
-            else if (unas)
-              emit_units<SINK>(P, K, e, samp, strat, NF, (uint32_t)WK_UNITS);
-          }
-          if (asg && (result >= 0 || unas))
-            asg[a] = (int)(result >= 0 ? result : NF) | ASSIGN_UNIQ;
+      } else if (kind == WK_KIND_FREE) {
+        // classify.assign_free (classify.py:54-78)
+        if (k == 1) {
+          r = sw_tab<STAGED>(P, stab, e, lds32(as + (uint32_t)a * 4u));
+        } else if (!anyneg) {
+          r = sw_lca_fold(TR, em, a, x, P.root);
+        }
+      } else {
+        // classify.assign_none (classify.py:32-51)
+        if (k == 1) {
+          r = t0;
+        } else if (!(flags & WK_F_UNIQ)) {
+          d = (uint32_t)k;
+          r = t0;
         }
       }
-      owned = true;
-      atstart = true;
+      if (d == 0 && r == EM_NONE && unas) r = NFv;
+      sts32(em + (uint32_t)a * 4u, EM_HEAD | (d << 24) | r);
       a = x + 1;
-      t0 = -1;
       nvalid = 0;
       k = 0;
-      alleq = true;
-      anyneg = false;
+      alleq = 1;
+      anyneg = 0;
+      ++x;
+      if (FIRST ? x >= S.w1 : x >= S.xstop) break;
     } else {
-      atstart = false;
-      if (FIRST && owned && x + 1 - a >= SW_LONGK) {
+      ++x;
+      if (FIRST && x - a >= SW_LONGK) {
         S.longa = a;  // the rest of this run is one long query
         break;
       }
     }
-    ++x;
   }
-  if (FIRST) {
-    S.xstop = owned ? a : w0;
-    if (!LEAN) {
-      S.tailm = tm;
-      S.dupm = dm;
+  if (FIRST) S.xstop = a;
+}
+
+// Sweep B of one entry: emit what sweep A decided.
+template <int SINK, bool LEAN>
+__device__ __forceinline__ void sweep_emit(const ClsParams &P, const Sink &K,
+                                           uint32_t aq, uint32_t em,
+                                           uint32_t prop_addr, int64_t sbase,
+                                           int e, const SwRun &S) {
+  const bool per_query = !LEAN && (P.q_sample || P.q_stratum);
+  int32_t *asg = P.assign ? P.assign + (int64_t)e * P.assign_stride + sbase
+                          : nullptr;
+  int samp = P.sample, strat = 0;
+  bool live = true;
+  uint32_t d = 0, u = 0;
+#pragma unroll 1
+  for (int x = S.xfirst; x < S.xstop; ++x) {
+    const int w = lds32(em + (uint32_t)x * 4u);
+    const uint32_t v = (uint32_t)w & EM_VMASK;
+    const bool head = w < 0;
+    if (head) {
+      d = ((uint32_t)w >> 24) & 63u;
+      u = c_units64[d];
+      if (per_query) {
+        const int qid = lds32(aq + (uint32_t)x * 4u);
+        samp = P.q_sample ? __ldg(P.q_sample + qid) : P.sample;
+        strat = P.q_stratum ? __ldg(P.q_stratum + qid) : 0;
+        live = strat >= 0 && (unsigned)samp < (unsigned)P.S;
+        if (SINK == SINK_DIRECT && live && samp != K.cur)
+          sts32(prop_addr, (uint32_t)samp);  // ask for the table to follow
+      }
     }
+    const bool emit = v < EM_DUP && (head || d != 0);
+    if (emit && live) {
+      if (u)
+        emit_units<SINK>(P, K, e, samp, strat, (int64_t)v, u);
+      else
+        emit_frac<SINK>(P, K, e, samp, strat, (int64_t)v, (int64_t)d);
+    }
+    if (asg) asg[x] = emit ? (int)(v | (head && d == 0 ? (uint32_t)ASSIGN_UNIQ : 0u)) : -1;
   }
 }
 
@@ -305,12 +336,12 @@ __global__ void __launch_bounds__(SW_NT, 1)
   const int R = P.sw_R;
   const int TILE = SW_NT * R;
   const int64_t tab_bytes = STAGED ? (int64_t)P.stage_elems * 2 : 0;
-  const SwSmemLayout L = sw_layout(R, SINK, P.cache_log, P.direct_cells,
-                                   tab_bytes, STAGED ? 2 : 4);
+  const SwSmemLayout L =
+      sw_layout(R, SINK, P.cache_log, P.direct_cells, tab_bytes);
   const uint32_t sbase32 = smem_u32(smem);
   const uint32_t bars = sbase32 + L.bars;  // [STAGES] tiles, [STAGES] = tables
   const uint32_t tiles = sbase32 + L.tiles;
-  const uint32_t ts = sbase32 + L.ts;
+  const uint32_t em = sbase32 + L.em;
   const uint32_t stab = sbase32 + L.tab;
   const uint32_t stage_bytes = 2u * (uint32_t)L.tbuf * 4u;
   Sink K;
@@ -417,22 +448,21 @@ __global__ void __launch_bounds__(SW_NT, 1)
     if (r0 - sbase > S.w0) S.w0 = (int)(r0 - sbase < (1 << 30) ? r0 - sbase : (1 << 30));
     if (r1 - sbase < S.w1) S.w1 = (int)(r1 - sbase);
     if (S.w1 > S.nrel) S.w1 = S.nrel;
-    S.own0 = false;
-    if (S.w0 < S.w1)
-      S.own0 = (sbase + S.w0 == 0) ||
-               lds32(aq + (uint32_t)S.w0 * 4u - 4u) != lds32(aq + (uint32_t)S.w0 * 4u);
-    S.xstop = S.w0;
-    S.longa = -1;
-    S.tailm = S.dupm = 0;
+    if (sbase + S.w0 == 0 && S.w0 < S.w1) {
+      // record 0 of the column starts a query whatever lies before it in
+      // shared memory: make the slot before it differ
+      sts32(aq + (uint32_t)S.w0 * 4u - 4u, ~(uint32_t)lds32(aq + (uint32_t)S.w0 * 4u));
+    }
 
-    sweep_entry<STAGED, SINK, LEAN, true>(P, K, TR, aq, as, ts, stab, sn16,
-                                          prop_addr, sbase, 0,
-                                          P.kind[0], flags, V32, S);
+    sweep_assign<STAGED, true>(P, TR, aq, as, em, stab, sn16, 0, P.kind[0],
+                               flags, V32, S);
+    sweep_emit<SINK, LEAN>(P, K, aq, em, prop_addr, sbase, 0, S);
     if (!LEAN)
-      for (int e = 1; e < E; ++e)
-        sweep_entry<STAGED, SINK, LEAN, false>(P, K, TR, aq, as, ts, stab,
-                                               sn16, prop_addr, sbase, e,
-                                               P.kind[e], flags, V32, S);
+      for (int e = 1; e < E; ++e) {
+        sweep_assign<STAGED, false>(P, TR, aq, as, em, stab, sn16, e,
+                                    P.kind[e], flags, V32, S);
+        sweep_emit<SINK, LEAN>(P, K, aq, em, prop_addr, sbase, e, S);
+      }
     // queries longer than SW_LONGK: the whole warp, from global memory
     unsigned lm = __ballot_sync(FULL, S.longa >= 0);
     while (lm) {
@@ -442,7 +472,7 @@ __global__ void __launch_bounds__(SW_NT, 1)
       process_long<STAGED, SINK>(P, K, stab, n, sbase + la, lane);
     }
 
-    __syncthreads();  // every thread is done with this stage and with ts
+    __syncthreads();  // every thread is done with this stage and with em
     if (tid == 0) {
       int64_t nt = tile + (int64_t)SW_STAGES * gridDim.x;
       if (nt < n_tiles) issue(nt, stage);
