@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -155,6 +156,7 @@ struct wk_ctx {
   bool stage_dirty = true;
   int32_t sn16_off = -1, par16_off = -1, stage_elems = 0, stage_vmax = -1;
   int32_t n_levels = 0, level_off[40];
+  std::vector<int64_t> dir_lo, dir_hi;  // per entry: range of the table values
   // overflow + err
   DevBuf ovf_key, ovf_den, small;  // small: [0]=ovf_n [1]=sh_used [2]=n_pairs [3]=cursor, err after
   int64_t ovf_cap = 0;
@@ -247,6 +249,7 @@ int wk_create(int device, wk_ctx **out) {
   TRY(c->small.reserve(64));
   CK(cudaMemset(c->small.p, 0, 64));
   c->ovf_cap = 1 << 20;
+  if (const char *ev = getenv("WK_TUNE_BLOCK")) c->tune_block = atoi(ev);
   TRY(c->ovf_key.reserve(c->ovf_cap * 8));
   TRY(c->ovf_den.reserve(c->ovf_cap * 4));
   {
@@ -263,18 +266,42 @@ int wk_create(int device, wk_ctx **out) {
         (const void *)classify_kernel<false, SINK_DIRECT, false>,
         (const void *)classify_kernel<false, SINK_HASHED, false>,
         (const void *)classify_kernel<false, SINK_GLOBAL, false>,
-        (const void *)classify_sweep_kernel<true, SINK_DIRECT, true>,
-        (const void *)classify_sweep_kernel<true, SINK_HASHED, true>,
-        (const void *)classify_sweep_kernel<true, SINK_GLOBAL, true>,
-        (const void *)classify_sweep_kernel<false, SINK_DIRECT, true>,
-        (const void *)classify_sweep_kernel<false, SINK_HASHED, true>,
-        (const void *)classify_sweep_kernel<false, SINK_GLOBAL, true>,
-        (const void *)classify_sweep_kernel<true, SINK_DIRECT, false>,
-        (const void *)classify_sweep_kernel<true, SINK_HASHED, false>,
-        (const void *)classify_sweep_kernel<true, SINK_GLOBAL, false>,
-        (const void *)classify_sweep_kernel<false, SINK_DIRECT, false>,
-        (const void *)classify_sweep_kernel<false, SINK_HASHED, false>,
-        (const void *)classify_sweep_kernel<false, SINK_GLOBAL, false>};
+        (const void *)classify_sweep_kernel<true, SINK_DIRECT, true, 512>,
+        (const void *)classify_sweep_kernel<true, SINK_DIRECT, false, 512>,
+        (const void *)classify_sweep_kernel<true, SINK_HASHED, true, 512>,
+        (const void *)classify_sweep_kernel<true, SINK_HASHED, false, 512>,
+        (const void *)classify_sweep_kernel<true, SINK_GLOBAL, true, 512>,
+        (const void *)classify_sweep_kernel<true, SINK_GLOBAL, false, 512>,
+        (const void *)classify_sweep_kernel<false, SINK_DIRECT, true, 512>,
+        (const void *)classify_sweep_kernel<false, SINK_DIRECT, false, 512>,
+        (const void *)classify_sweep_kernel<false, SINK_HASHED, true, 512>,
+        (const void *)classify_sweep_kernel<false, SINK_HASHED, false, 512>,
+        (const void *)classify_sweep_kernel<false, SINK_GLOBAL, true, 512>,
+        (const void *)classify_sweep_kernel<false, SINK_GLOBAL, false, 512>,
+        (const void *)classify_sweep_kernel<true, SINK_DIRECT, true, 768>,
+        (const void *)classify_sweep_kernel<true, SINK_DIRECT, false, 768>,
+        (const void *)classify_sweep_kernel<true, SINK_HASHED, true, 768>,
+        (const void *)classify_sweep_kernel<true, SINK_HASHED, false, 768>,
+        (const void *)classify_sweep_kernel<true, SINK_GLOBAL, true, 768>,
+        (const void *)classify_sweep_kernel<true, SINK_GLOBAL, false, 768>,
+        (const void *)classify_sweep_kernel<false, SINK_DIRECT, true, 768>,
+        (const void *)classify_sweep_kernel<false, SINK_DIRECT, false, 768>,
+        (const void *)classify_sweep_kernel<false, SINK_HASHED, true, 768>,
+        (const void *)classify_sweep_kernel<false, SINK_HASHED, false, 768>,
+        (const void *)classify_sweep_kernel<false, SINK_GLOBAL, true, 768>,
+        (const void *)classify_sweep_kernel<false, SINK_GLOBAL, false, 768>,
+        (const void *)classify_sweep_kernel<true, SINK_DIRECT, true, 1024>,
+        (const void *)classify_sweep_kernel<true, SINK_DIRECT, false, 1024>,
+        (const void *)classify_sweep_kernel<true, SINK_HASHED, true, 1024>,
+        (const void *)classify_sweep_kernel<true, SINK_HASHED, false, 1024>,
+        (const void *)classify_sweep_kernel<true, SINK_GLOBAL, true, 1024>,
+        (const void *)classify_sweep_kernel<true, SINK_GLOBAL, false, 1024>,
+        (const void *)classify_sweep_kernel<false, SINK_DIRECT, true, 1024>,
+        (const void *)classify_sweep_kernel<false, SINK_DIRECT, false, 1024>,
+        (const void *)classify_sweep_kernel<false, SINK_HASHED, true, 1024>,
+        (const void *)classify_sweep_kernel<false, SINK_HASHED, false, 1024>,
+        (const void *)classify_sweep_kernel<false, SINK_GLOBAL, true, 1024>,
+        (const void *)classify_sweep_kernel<false, SINK_GLOBAL, false, 1024>};
     for (const void *fn : variants)
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)c->smem_optin));
@@ -415,6 +442,8 @@ int wk_set_plan(wk_ctx *c, const int32_t *kinds, int32_t n_entries,
   c->stage_dirty = true;
   c->h_tab.clear();
   c->h_sub_node.clear();
+  c->dir_lo.clear();
+  c->dir_hi.clear();
   return wk_reset_counts(c);
 }
 
@@ -482,8 +511,26 @@ int wk_set_subjects(wk_ctx *c, const int32_t *tab, const int32_t *sub_node,
     TRY(c->tab.reserve((size_t)c->E * V * 4));
     CK(cudaMemcpy(c->tab.p, tab, (size_t)c->E * V * 4, cudaMemcpyHostToDevice));
     c->h_tab.assign(tab, tab + (size_t)c->E * V);
+    c->dir_lo.assign((size_t)c->E, 0);
+    c->dir_hi.assign((size_t)c->E, -1);
+    for (int e = 0; e < c->E; ++e) {
+      if (c->kind[e] == WK_KIND_NONE_ID) continue;
+      int64_t lo = INT64_MAX, hi = -1;
+      for (int64_t i = 0; i < V; ++i) {
+        int32_t v = tab[(size_t)e * V + i];
+        if (v < 0) continue;
+        lo = std::min<int64_t>(lo, v);
+        hi = std::max<int64_t>(hi, v);
+      }
+      if (hi >= 0) {
+        c->dir_lo[e] = lo;
+        c->dir_hi[e] = hi;
+      }
+    }
   } else {
     c->h_tab.clear();
+    c->dir_lo.clear();
+    c->dir_hi.clear();
   }
   if (sub_node && V) {
     for (int64_t i = 0; i < V; ++i)
@@ -660,6 +707,33 @@ static int pack_stage(wk_ctx *c) {
   return WK_OK;
 }
 
+// SINK_DIRECT: the feature range every entry keeps in the private table
+// (ClsParams::dir_*).  Values outside it still count, through global memory.
+static uint32_t plan_direct_ranges(wk_ctx *c, ClsParams &P) {
+  uint64_t cells = 0;
+  for (int e = 0; e < c->E; ++e) {
+    int64_t lo = 0, hi = c->NF - 1;
+    if (c->kind[e] != WK_KIND_NONE_ID && (int)c->dir_lo.size() == c->E) {
+      lo = c->dir_lo[e];
+      hi = c->dir_hi[e];
+      // an LCA is an ancestor: anything from the root down to the largest value
+      if (c->kind[e] == WK_KIND_FREE ||
+          (c->kind[e] == WK_KIND_RANK && (c->flags & WK_F_ABOVE) &&
+           !(c->flags & WK_F_MAJOR))) {
+        lo = 0;
+        if (c->kind[e] == WK_KIND_FREE) hi = std::max<int64_t>(hi, c->T - 1);
+      }
+    }
+    if (hi < lo) hi = lo - 1;
+    P.dir_off[e] = (int32_t)lo;
+    P.dir_w[e] = (int32_t)(hi - lo + 1);
+    P.dir_base[e] = (int32_t)cells;
+    cells += (uint64_t)(hi - lo + 1) + 1;
+    if (cells >= (1u << 24)) return 0xFFFFFFFFu;
+  }
+  return (uint32_t)cells;
+}
+
 // Launch the classify kernel over queries with head in [r0, r1) of device
 // columns dq/ds holding n readable records.
 static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
@@ -727,26 +801,31 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   const size_t cells = (size_t)c->E * c->S * (c->NF + 1);
   int grid = c->tune_grid > 0 ? c->tune_grid : c->sm_count;
 
+  const uint32_t dir_cells = plan_direct_ranges(c, P);
   // ---- the sweep kernel (wk_sweep.cuh) unless the window kernel is forced ----
-  if (c->tune_block != 1) {
-    // its scratch words hold 24-bit values
+  if (c->tune_block != 1 &&
+      std::max<int64_t>(std::max<int64_t>(c->NF + 1, c->T), P.V) <= SW_MAX_VALUE) {
     const bool st = staged;
     const int64_t tbytes = st ? (int64_t)c->stage_elems * 2 : 0;
+    int NT = c->tune_block % 10000, NS = c->tune_block / 10000;
+    if (NT < 64 || NT > SW_NT) NT = SW_NT;
+    if (NS < 1 || NS > 4) NS = 1;
+    const int NW = NT / 32;
+    int rmax = SW_RMAX;
+    if (const char *ev = getenv("WK_SWEEP_R")) rmax = std::max(3, std::min(SW_RMAX, atoi(ev) | 1));
     auto pick_r = [&](int sk, int cl, uint32_t dc) {
-      if (std::max<int64_t>(std::max<int64_t>(c->NF + 1, c->T), P.V) > SW_MAX_VALUE)
-        return 0;
-      for (int R = SW_RMAX; R >= 3; R -= 2)
-        if (sw_layout(R, sk, cl, dc, tbytes).total <= c->smem_optin) return R;
+      for (int R = rmax; R >= 3; R -= 2)
+        if (sw_layout(NW, R, NS, sk, cl, dc, tbytes).total <= c->smem_optin) return R;
       return 0;
     };
     int sink = SINK_GLOBAL, cache_log = 0, R = 0;
     uint32_t dcells = 0;
     if (!dqstrat && c->tune_cache >= 0) {
-      const size_t dc = (size_t)c->E * (c->NF + 1);  // one sample at a time
       const bool want_hashed = c->tune_cache > 0 && c->tune_cache < 1000000;
-      if (!want_hashed && dc < (1u << 24) && (R = pick_r(SINK_DIRECT, 0, (uint32_t)dc)) >= 7) {
+      if (!want_hashed && dir_cells != 0xFFFFFFFFu &&
+          (R = pick_r(SINK_DIRECT, 0, dir_cells)) >= 7) {
         sink = SINK_DIRECT;
-        dcells = (uint32_t)dc;
+        dcells = dir_cells;
       } else if (cells < 0xFFFFFFFFull) {
         int want = 13;
         if (c->tune_cache > 0) {
@@ -762,20 +841,28 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
     if (sink == SINK_GLOBAL) R = pick_r(SINK_GLOBAL, 0, 0);
     if (R >= 3) {
       P.sw_R = R;
+      P.sw_S = NS;
       P.cache_log = cache_log;
       P.direct_cells = dcells;
-      SwSmemLayout L = sw_layout(R, sink, cache_log, dcells, tbytes);
-      const int64_t tile = (int64_t)SW_NT * R;
+      SwSmemLayout L = sw_layout(NW, R, NS, sink, cache_log, dcells, tbytes);
+      const int64_t wt = 32ll * R;
       int64_t span = (n_dev ? n_bound : r1) - (r0 & ~3ll);
-      int64_t n_tiles = (span + tile - 1) / tile;
+      int64_t n_tiles = (span + wt - 1) / wt;
       if (n_tiles <= 0) return WK_OK;
-      grid = (int)std::min<int64_t>(grid, n_tiles);
-#define WK_SWEEP(ST, SK)                                                         \
-  do {                                                                           \
-    if (lean)                                                                    \
-      classify_sweep_kernel<ST, SK, true><<<grid, SW_NT, L.total, c->stream>>>(P); \
-    else                                                                         \
-      classify_sweep_kernel<ST, SK, false><<<grid, SW_NT, L.total, c->stream>>>(P); \
+      grid = (int)std::min<int64_t>(grid, (n_tiles + NW - 1) / NW);
+#define WK_SWEEP2(ST, SK, LN)                                                     \
+  do {                                                                            \
+    if (NT <= 512)                                                                \
+      classify_sweep_kernel<ST, SK, LN, 512><<<grid, NT, L.total, c->stream>>>(P);  \
+    else if (NT <= 768)                                                           \
+      classify_sweep_kernel<ST, SK, LN, 768><<<grid, NT, L.total, c->stream>>>(P);  \
+    else                                                                          \
+      classify_sweep_kernel<ST, SK, LN, 1024><<<grid, NT, L.total, c->stream>>>(P); \
+  } while (0)
+#define WK_SWEEP(ST, SK)              \
+  do {                                \
+    if (lean) WK_SWEEP2(ST, SK, true); \
+    else WK_SWEEP2(ST, SK, false);    \
   } while (0)
       if (st) {
         if (sink == SINK_DIRECT) WK_SWEEP(true, SINK_DIRECT);
@@ -787,6 +874,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
         else WK_SWEEP(false, SINK_GLOBAL);
       }
 #undef WK_SWEEP
+#undef WK_SWEEP2
       c->launches++;
       CK(cudaGetLastError());
       return WK_OK;
@@ -797,9 +885,8 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   // where counts are accumulated first (wk_classify.cuh, "count sinks")
   int sink = SINK_GLOBAL, cache_log = 0;
   if (!dqstrat && c->tune_cache >= 0) {
-    const size_t dcells = (size_t)c->E * (c->NF + 1);  // one sample at a time
-    if (dcells < (1u << 24) &&
-        cls_layout(SINK_DIRECT, 0, (uint32_t)dcells, tab_bytes).total <=
+    if (dir_cells != 0xFFFFFFFFu &&
+        cls_layout(SINK_DIRECT, 0, dir_cells, tab_bytes).total <=
             c->smem_optin) {
       sink = SINK_DIRECT;
     } else if (cells < 0xFFFFFFFFull) {
@@ -826,7 +913,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
     }
   }
   P.cache_log = sink == SINK_HASHED ? cache_log : 0;
-  P.direct_cells = sink == SINK_DIRECT ? (uint32_t)((size_t)c->E * (c->NF + 1)) : 0;
+  P.direct_cells = sink == SINK_DIRECT ? dir_cells : 0;
   ClsSmemLayout L = cls_layout(sink, P.cache_log, P.direct_cells, tab_bytes);
   if (L.total > c->smem_optin)
     return fail(WK_ERR_STATE, "shared memory layout does not fit (%u B)", L.total);

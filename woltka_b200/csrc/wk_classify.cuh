@@ -91,8 +91,12 @@ struct ClsParams {
   int32_t *assign;            // optional per-record assignment [E][stride]
   int64_t assign_stride;      // (read maps, file.write_readmap file.py:469-500)
   int32_t cache_log;          // SINK_HASHED: log2(cache slots)
-  uint32_t direct_cells;      // SINK_DIRECT: E*NF1 (one sample at a time)
-  int32_t sw_R;               // classify_sweep_kernel: records per lane and tile
+  uint32_t direct_cells;      // SINK_DIRECT: private slots (one sample at a time)
+  // SINK_DIRECT: entry e keeps features [dir_off, dir_off + dir_w) at slots
+  // dir_base + (f - dir_off) and 'Unassigned' at slot dir_base + dir_w; any
+  // other feature goes straight to the global table
+  int32_t dir_off[WK_MAX_ENTRIES], dir_w[WK_MAX_ENTRIES], dir_base[WK_MAX_ENTRIES];
+  int32_t sw_R, sw_S;         // classify_sweep_kernel: records per lane and tile, stages
 };
 
 enum { ERR_BAD_SUBJECT = 1, ERR_OVF_FULL = 2, ERR_HASH_FULL = 4,
@@ -230,11 +234,15 @@ __device__ __forceinline__ void emit_units(const ClsParams &P, const Sink &K,
     // private [entry][feature] table of ONE sample at a time (samples are
     // contiguous in the stream); other samples go straight to HBM
     if (samp == K.cur) {
-      uint32_t key = (uint32_t)(e * (int)P.NF1 + (int)f);
-      uint32_t old = atoms_add(K.a0 + key * 4u, units);
-      if (old + units < old)
-        atomicAdd(&P.cnt[((int64_t)e * P.S + samp) * P.NF1 + f], 1ull << 32);
-      return;
+      const uint32_t r = (uint32_t)f - (uint32_t)P.dir_off[e];
+      const uint32_t w = (uint32_t)P.dir_w[e];
+      if (r < w || f == P.NF1 - 1) {
+        const uint32_t key = (uint32_t)P.dir_base[e] + (r < w ? r : w);
+        uint32_t old = atoms_add(K.a0 + key * 4u, units);
+        if (old + units < old)
+          atomicAdd(&P.cnt[((int64_t)e * P.S + samp) * P.NF1 + f], 1ull << 32);
+        return;
+      }
     }
   }
   int64_t cell = ((int64_t)e * P.S + samp) * P.NF1 + f;
@@ -277,6 +285,23 @@ __device__ __forceinline__ void emit_frac(const ClsParams &P, const Sink &K,
     P.ovf_den[at] = (int32_t)d;
   } else {
     atomicOr(P.err, ERR_OVF_FULL);
+  }
+}
+
+// SINK_DIRECT: add the private table of sample K.cur to the global table
+__device__ __forceinline__ void direct_flush(const ClsParams &P, const Sink &K,
+                                             int tid, int nthreads) {
+  if (K.cur < 0) return;
+  for (uint32_t h = tid; h < P.direct_cells; h += nthreads) {
+    uint32_t v = (uint32_t)lds32(K.a0 + h * 4);
+    if (v) {
+      int e = 0;
+      while (e + 1 < P.E && h >= (uint32_t)P.dir_base[e + 1]) ++e;
+      const uint32_t r = h - (uint32_t)P.dir_base[e];
+      const int64_t f = r < (uint32_t)P.dir_w[e] ? (int64_t)P.dir_off[e] + r : P.NF1 - 1;
+      atomicAdd(&P.cnt[((int64_t)e * P.S + K.cur) * P.NF1 + f], (ull)v);
+      sts32(K.a0 + h * 4, 0);
+    }
   }
 }
 
@@ -664,19 +689,7 @@ __global__ void __launch_bounds__(CLS_NT, 1)
   const unsigned mybit = 1u << lane;
 
   // DIRECT: add the private table of sample K.cur to the global table
-  auto flush_direct = [&]() {
-    if (K.cur >= 0) {
-      const uint32_t NF1u = (uint32_t)P.NF1;
-      for (uint32_t h = tid; h < sink_words; h += CLS_NT) {
-        uint32_t v = (uint32_t)lds32(K.a0 + h * 4);
-        if (v) {
-          uint32_t e = h / NF1u, f = h - e * NF1u;
-          atomicAdd(&P.cnt[((int64_t)e * P.S + K.cur) * P.NF1 + f], (ull)v);
-          sts32(K.a0 + h * 4, 0);
-        }
-      }
-    }
-  };
+  auto flush_direct = [&]() { direct_flush(P, K, tid, CLS_NT); };
 
   int it = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {

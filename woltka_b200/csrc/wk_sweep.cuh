@@ -7,22 +7,24 @@
 // classify_kernel gives every lane one record and resolves the queries of a
 // 32-record window with ballots and shuffles: ~250 warp instructions per
 // window, 9.5 per record, ALU-pipe bound (profiles/README.md).  Here every
-// lane owns a RUN of R consecutive records of the tile and walks it
-// sequentially from shared memory with a small per-query state machine; a
-// warp instruction then advances 32 records at once and the per-record cost is
-// the length of the loop body / 32.  A query belongs to the run that holds its
-// first record; the owner follows it past the end of its run (the next lane
-// skips the records up to its own first head).  R is odd, so the 32 lanes of
-// a warp (stride R words) hit 32 different banks.
+// lane owns a RUN of R consecutive records and walks it sequentially from
+// shared memory with a small per-query state machine; a warp instruction then
+// advances 32 records at once and the per-record cost is the length of the
+// loop body / 32.  A query belongs to the run that holds its first record; the
+// owner follows it past the end of its run (the next lane skips the records up
+// to its own first head).  R is odd, so the 32 lanes of a warp (stride R words)
+// hit 32 different banks.
 //
-//   * tiles of SW_NT*R records of both columns land in shared memory through
-//     TMA bulk copies (cp.async.bulk + mbarrier complete_tx), 2 stages;
+//   * every WARP runs its own pipeline: tiles of 32*R records of both columns
+//     land in the warp's slice of shared memory through TMA bulk copies
+//     (cp.async.bulk + mbarrier complete_tx) issued by its lane 0; there is
+//     no CTA-wide barrier in the steady state, warps drift freely;
 //   * sweep A (per entry of the plan) walks the run once: set semantics of
 //     the subject pool (align.py:339) through a 32-bit signature of the query's
 //     subjects, exact look-back only on a signature hit; the entry's table
-//     value of every record goes to a per-tile scratch column `em`; at the
-//     tail of a query its assignment (unique result, or the denominator of
-//     the 1/k' split) is written into the head's word;
+//     value of every record goes to a scratch column `em`; at the tail of a
+//     query its assignment (unique result, or the denominator of the 1/k'
+//     split) is written into the head's word;
 //   * sweep B walks the same records again and emits: one unit at the head of
 //     a uniquely assigned query, 1/k' at every contributing record otherwise —
 //     no per-query loop, no divergence beyond the predicate;
@@ -34,12 +36,12 @@
 
 namespace wk {
 
-constexpr int SW_NT = 512;      // threads per CTA
-constexpr int SW_STAGES = 2;
+constexpr int SW_NT = 1024;     // launch bound: threads per CTA
 constexpr int SW_PRE = 4;       // records staged before the tile
 constexpr int SW_POST = 44;     // halo after the tile (>= SW_LONGK + 3)
 constexpr int SW_LONGK = 40;    // longer queries take process_long
 constexpr int SW_RMAX = 21;     // records per lane and tile (odd)
+constexpr int SW_EPOCH = 8;     // rounds between CTA barriers (sample following)
 
 // scratch word of a record: value (24 bits) | denominator (6 bits, head only,
 // 0 = unique assignment) | head flag (bit 31)
@@ -62,20 +64,22 @@ __constant__ uint32_t c_units64[64] = {
     11440};
 
 struct SwSmemLayout {
-  uint32_t bars, tiles, em, sink0, sink1, tab, total;
-  int R, tbuf;
+  uint32_t bars, warp0, warp_bytes, sink0, sink1, tab, total;
+  int R, S, NW, tbuf;
 };
-__host__ __device__ inline SwSmemLayout sw_layout(int R, int sink,
+__host__ __device__ inline SwSmemLayout sw_layout(int NW, int R, int S, int sink,
                                                   int cache_log,
                                                   uint32_t direct_cells,
                                                   int64_t tab_bytes) {
   SwSmemLayout L;
   L.R = R;
-  L.tbuf = SW_NT * R + SW_PRE + SW_POST;
-  L.bars = 0;
-  L.tiles = 128;
-  L.em = L.tiles + SW_STAGES * 2 * (uint32_t)L.tbuf * 4;
-  L.sink0 = L.em + (uint32_t)L.tbuf * 4;
+  L.S = S;
+  L.NW = NW;
+  L.tbuf = 32 * R + SW_PRE + SW_POST;
+  L.bars = 0;  // NW*S tile barriers, 1 table barrier, 1 word (sample proposal)
+  L.warp0 = (uint32_t)((NW * S + 2) * 8 + 127) & ~127u;
+  L.warp_bytes = (uint32_t)(2 * S + 1) * (uint32_t)L.tbuf * 4u;
+  L.sink0 = L.warp0 + (uint32_t)NW * L.warp_bytes;
   uint32_t w0 = 0, w1 = 0;
   if (sink == SINK_DIRECT) w0 = direct_cells * 4;
   if (sink == SINK_HASHED) w0 = w1 = (1u << cache_log) * 4;
@@ -87,30 +91,30 @@ __host__ __device__ inline SwSmemLayout sw_layout(int R, int sink,
 
 struct SwRun {
   int w0, w1;   // own records [w0, w1) in staged coordinates
-  int nrel;     // staged records that exist
   int xfirst;   // first owned head
   int xstop;    // one past the last record of an owned, finished query
   int longa;    // head of an owned query longer than SW_LONGK, or -1
 };
 
-// table value of subject sv at entry e as a scratch value
+// table value of subject sv as a scratch value; `row` = the entry's row
 template <bool STAGED>
-__device__ __forceinline__ uint32_t sw_tab(const ClsParams &P, uint32_t stab,
-                                           int e, int sv) {
+__device__ __forceinline__ uint32_t sw_tab(const ClsParams &P, uint32_t row16,
+                                           const int32_t *row32, int sv) {
   if (STAGED) {
-    const uint32_t v = lds16(stab + (uint32_t)(e * P.Vp + sv) * 2u);
+    const uint32_t v = lds16(row16 + (uint32_t)sv * 2u);
     return v == 0xFFFFu ? EM_NONE : v;
   } else {
-    return (uint32_t)__ldg(P.tab + (int64_t)e * P.V + sv) & EM_VMASK;
+    return (uint32_t)__ldg(row32 + sv) & EM_VMASK;
   }
 }
 
-__device__ __forceinline__ uint32_t sw_lca_fold(const TreeRef &TR, uint32_t em,
-                                                int a, int x, int root) {
-  int acc = lds32(em + (uint32_t)a * 4u) & EM_VMASK;
+__device__ __noinline__ uint32_t sw_lca_fold(const TreeRef TR, uint32_t em,
+                                             uint32_t ao, uint32_t xo,
+                                             int root) {
+  int acc = lds32(em + ao) & EM_VMASK;
 #pragma unroll 1
-  for (int j = a + 1; j <= x; ++j) {
-    const uint32_t vj = (uint32_t)lds32(em + (uint32_t)j * 4u) & EM_VMASK;
+  for (uint32_t j = ao + 4; j <= xo; j += 4) {
+    const uint32_t vj = (uint32_t)lds32(em + j) & EM_VMASK;
     if (vj != EM_DUP) acc = lca2(TR, acc, (int)vj);
   }
   return acc == root ? EM_NONE : (uint32_t)acc;
@@ -118,18 +122,18 @@ __device__ __forceinline__ uint32_t sw_lca_fold(const TreeRef &TR, uint32_t em,
 
 // classify.majority (classify.py:300-317): top count among the distinct
 // subjects' values, first seen wins ties; None is a value like any other
-__device__ __noinline__ uint32_t sw_majority(uint32_t em, int a, int x, int k,
-                                             double th) {
+__device__ __noinline__ uint32_t sw_majority(uint32_t em, uint32_t ao,
+                                             uint32_t xo, int k, double th) {
   int best = 0;
   uint32_t tw = EM_NONE;
 #pragma unroll 1
-  for (int j = a; j <= x; ++j) {
-    const uint32_t vj = (uint32_t)lds32(em + (uint32_t)j * 4u) & EM_VMASK;
+  for (uint32_t j = ao; j <= xo; j += 4) {
+    const uint32_t vj = (uint32_t)lds32(em + j) & EM_VMASK;
     if (vj == EM_DUP) continue;
     int c = 0;
 #pragma unroll 1
-    for (int j2 = a; j2 <= x; ++j2)
-      c += ((uint32_t)lds32(em + (uint32_t)j2 * 4u) & EM_VMASK) == vj;
+    for (uint32_t j2 = ao; j2 <= xo; j2 += 4)
+      c += ((uint32_t)lds32(em + j2) & EM_VMASK) == vj;
     if (c > best) {
       best = c;
       tw = vj;
@@ -138,53 +142,55 @@ __device__ __noinline__ uint32_t sw_majority(uint32_t em, int a, int x, int k,
   return ((double)best >= __dmul_rn((double)k, th)) ? tw : EM_NONE;
 }
 
-// Sweep A of one entry: values + per-query assignment into `em`.
-template <bool STAGED, bool FIRST>
+// Sweep A of one entry: values + per-query assignment into `em`.  All
+// positions are byte offsets (record index * 4) into the staged columns.
+template <bool STAGED, bool FIRST, int KIND>
 __device__ __forceinline__ void sweep_assign(const ClsParams &P,
                                              const TreeRef &TR, uint32_t aq,
                                              uint32_t as, uint32_t em,
                                              uint32_t stab, uint32_t sn16,
-                                             int e, int kind, uint32_t flags,
-                                             int V32, SwRun &S) {
-  int x;
+                                             int e, uint32_t flags, int V32,
+                                             SwRun &S) {
+  uint32_t xo;
+  const uint32_t w1o = (uint32_t)S.w1 * 4u;
   if (FIRST) {
     S.longa = -1;
     S.xfirst = S.xstop = S.w0;
-    x = S.w0;
-    if (x >= S.w1) return;
+    xo = (uint32_t)S.w0 * 4u;
+    if (S.w0 >= S.w1) return;
     // skip the records that continue a query of the previous run
-    const bool own0 = lds32(aq + (uint32_t)x * 4u - 4u) != lds32(aq + (uint32_t)x * 4u);
-    if (!own0) {
+    if (lds32(aq + xo - 4u) == lds32(aq + xo)) {
+      bool tail;
 #pragma unroll 1
-      for (;;) {
-        bool tail = true;
-        if (x + 1 < S.nrel)
-          tail = lds32(aq + (uint32_t)x * 4u) != lds32(aq + (uint32_t)x * 4u + 4u);
-        ++x;
-        if (tail || x >= S.w1) break;
-      }
+      do {
+        tail = lds32(aq + xo) != lds32(aq + xo + 4u);
+        xo += 4u;
+      } while (!tail && xo < w1o);
     }
-    if (x >= S.w1) return;  // no head in this run
-    S.xfirst = S.xstop = x;
+    if (xo >= w1o) return;  // no head in this run
+    S.xfirst = S.xstop = (int)(xo >> 2);
   } else {
-    x = S.xfirst;
-    if (x >= S.xstop) return;
+    xo = (uint32_t)S.xfirst * 4u;
+    if (S.xfirst >= S.xstop) return;
   }
+  const uint32_t stopo = (uint32_t)S.xstop * 4u;
   const uint32_t NFv = (uint32_t)(P.NF1 - 1);
   const bool unas = flags & WK_F_UNASSIGNED;
-  int a = x;
+  const uint32_t row16 = stab + (uint32_t)(e * P.Vp) * 2u;
+  const int32_t *row32 = P.tab + (int64_t)e * P.V;
+  uint32_t ao = xo;
   uint32_t t0 = EM_NONE, sig = 0;
-  int nvalid = 0, k = 0, alleq = 1, anyneg = 0;
+  int nvalid = 0, k = 0;
+  bool alleq = true, anyneg = false;
   int qc = 0;
-  if (FIRST) qc = lds32(aq + (uint32_t)x * 4u);
+  if (FIRST) qc = lds32(aq + xo);
 #pragma unroll 1
   for (;;) {
-    const bool ishead = x == a;
-    const int sv = lds32(as + (uint32_t)x * 4u);
+    const bool ishead = xo == ao;
+    const int sv = lds32(as + xo);
     bool tail, dup = false;
     if (FIRST) {
-      int qn = ~qc;
-      if (x + 1 < S.nrel) qn = lds32(aq + (uint32_t)x * 4u + 4u);
+      const int qn = lds32(aq + xo + 4u);
       tail = qn != qc;
       qc = qn;
       if ((unsigned)sv >= (unsigned)V32) {
@@ -194,30 +200,29 @@ __device__ __forceinline__ void sweep_assign(const ClsParams &P,
         // set semantics (align.py:339): signature of the query's subjects,
         // exact look-back only when the bit is already taken
         const uint32_t b = 1u << (sv & 31);
-        if (ishead) sig = 0;
         if (sig & b) {
 #pragma unroll 1
-          for (int j = a; j < x; ++j) dup |= lds32(as + (uint32_t)j * 4u) == sv;
+          for (uint32_t j = ao; j < xo; j += 4u) dup |= lds32(as + j) == sv;
         }
         sig |= b;
       }
     } else {
       // structure left behind by the previous entry
-      dup = ((uint32_t)lds32(em + (uint32_t)x * 4u) & EM_VMASK) == EM_DUP ||
+      dup = ((uint32_t)lds32(em + xo) & EM_VMASK) == EM_DUP ||
             (unsigned)sv >= (unsigned)V32;
-      tail = x + 1 >= S.xstop || lds32(em + (uint32_t)x * 4u + 4u) < 0;
+      tail = xo + 4u >= stopo || lds32(em + xo + 4u) < 0;
     }
 
     uint32_t v = EM_DUP;
     if (!dup) {
       ++k;
-      if (kind == WK_KIND_RANK) {
-        v = sw_tab<STAGED>(P, stab, e, sv);
+      if (KIND == WK_KIND_RANK) {
+        v = sw_tab<STAGED>(P, row16, row32, sv);
         if (ishead) t0 = v;
         alleq &= (v == t0);
         nvalid += (v != EM_NONE);
         anyneg |= (v == EM_NONE);
-      } else if (kind == WK_KIND_FREE) {
+      } else if (KIND == WK_KIND_FREE) {
         if (sn16) {
           v = lds16(sn16 + (uint32_t)sv * 2u);
           if (v == 0xFFFFu) v = EM_NONE;
@@ -225,39 +230,39 @@ __device__ __forceinline__ void sweep_assign(const ClsParams &P,
           v = (uint32_t)__ldg(P.sub_node + sv) & EM_VMASK;
         }
         anyneg |= (v == EM_NONE);
-      } else if (kind == WK_KIND_NONE) {
-        v = sw_tab<STAGED>(P, stab, e, sv);
+      } else if (KIND == WK_KIND_NONE) {
+        v = sw_tab<STAGED>(P, row16, row32, sv);
         if (ishead) t0 = v;
       } else {
         v = (uint32_t)sv;
         if (ishead) t0 = v;
       }
     }
-    sts32(em + (uint32_t)x * 4u, v | (ishead ? EM_HEAD : 0u));
+    sts32(em + xo, v | (ishead ? EM_HEAD : 0u));
 
     if (tail) {
-      // ---- the query [a, x] is complete: its assignment ------------------
+      // ---- the query [ao, xo] is complete: its assignment ----------------
       uint32_t d = 0, r = EM_NONE;
       if (k == 0) {
         // only reachable with a bad subject (the call fails)
-      } else if (kind == WK_KIND_RANK) {
+      } else if (KIND == WK_KIND_RANK) {
         // classify.assign_rank (classify.py:81-127)
         if (alleq) {
           r = t0;
         } else if (flags & WK_F_MAJOR) {
-          r = sw_majority(em, a, x, k, P.major_th);
+          r = sw_majority(em, ao, xo, k, P.major_th);
         } else if (flags & WK_F_ABOVE) {
-          if (!anyneg) r = sw_lca_fold(TR, em, a, x, P.root);
+          if (!anyneg) r = sw_lca_fold(TR, em, ao, xo, P.root);
         } else if (!(flags & WK_F_UNIQ)) {
           d = (uint32_t)nvalid;  // 1/k' to every subject with a taxon
           r = t0;
         }
-      } else if (kind == WK_KIND_FREE) {
+      } else if (KIND == WK_KIND_FREE) {
         // classify.assign_free (classify.py:54-78)
         if (k == 1) {
-          r = sw_tab<STAGED>(P, stab, e, lds32(as + (uint32_t)a * 4u));
+          r = sw_tab<STAGED>(P, row16, row32, lds32(as + ao));
         } else if (!anyneg) {
-          r = sw_lca_fold(TR, em, a, x, P.root);
+          r = sw_lca_fold(TR, em, ao, xo, P.root);
         }
       } else {
         // classify.assign_none (classify.py:32-51)
@@ -269,23 +274,24 @@ __device__ __forceinline__ void sweep_assign(const ClsParams &P,
         }
       }
       if (d == 0 && r == EM_NONE && unas) r = NFv;
-      sts32(em + (uint32_t)a * 4u, EM_HEAD | (d << 24) | r);
-      a = x + 1;
+      sts32(em + ao, EM_HEAD | (d << 24) | r);
+      xo += 4u;
+      ao = xo;
       nvalid = 0;
       k = 0;
-      alleq = 1;
-      anyneg = 0;
-      ++x;
-      if (FIRST ? x >= S.w1 : x >= S.xstop) break;
+      sig = 0;
+      alleq = true;
+      anyneg = false;
+      if (FIRST ? xo >= w1o : xo >= stopo) break;
     } else {
-      ++x;
-      if (FIRST && x - a >= SW_LONGK) {
-        S.longa = a;  // the rest of this run is one long query
+      xo += 4u;
+      if (FIRST && xo - ao >= SW_LONGK * 4u) {
+        S.longa = (int)(ao >> 2);  // the rest of this run is one long query
         break;
       }
     }
   }
-  if (FIRST) S.xstop = a;
+  if (FIRST) S.xstop = (int)(ao >> 2);
 }
 
 // Sweep B of one entry: emit what sweep A decided.
@@ -300,16 +306,17 @@ __device__ __forceinline__ void sweep_emit(const ClsParams &P, const Sink &K,
   int samp = P.sample, strat = 0;
   bool live = true;
   uint32_t d = 0, u = 0;
+  const uint32_t stopo = (uint32_t)S.xstop * 4u;
 #pragma unroll 1
-  for (int x = S.xfirst; x < S.xstop; ++x) {
-    const int w = lds32(em + (uint32_t)x * 4u);
+  for (uint32_t xo = (uint32_t)S.xfirst * 4u; xo < stopo; xo += 4u) {
+    const int w = lds32(em + xo);
     const uint32_t v = (uint32_t)w & EM_VMASK;
     const bool head = w < 0;
     if (head) {
       d = ((uint32_t)w >> 24) & 63u;
       u = c_units64[d];
       if (per_query) {
-        const int qid = lds32(aq + (uint32_t)x * 4u);
+        const int qid = lds32(aq + xo);
         samp = P.q_sample ? __ldg(P.q_sample + qid) : P.sample;
         strat = P.q_stratum ? __ldg(P.q_stratum + qid) : 0;
         live = strat >= 0 && (unsigned)samp < (unsigned)P.S;
@@ -324,33 +331,52 @@ __device__ __forceinline__ void sweep_emit(const ClsParams &P, const Sink &K,
       else
         emit_frac<SINK>(P, K, e, samp, strat, (int64_t)v, (int64_t)d);
     }
-    if (asg) asg[x] = emit ? (int)(v | (head && d == 0 ? (uint32_t)ASSIGN_UNIQ : 0u)) : -1;
+    if (asg)
+      asg[xo >> 2] =
+          emit ? (int)(v | (head && d == 0 ? (uint32_t)ASSIGN_UNIQ : 0u)) : -1;
   }
 }
 
-template <bool STAGED, int SINK, bool LEAN>
-__global__ void __launch_bounds__(SW_NT, 1)
+template <bool STAGED, bool FIRST>
+__device__ __forceinline__ void sweep_assign_any(const ClsParams &P,
+                                                 const TreeRef &TR, uint32_t aq,
+                                                 uint32_t as, uint32_t em,
+                                                 uint32_t stab, uint32_t sn16,
+                                                 int e, int kind, uint32_t flags,
+                                                 int V32, SwRun &S) {
+  if (kind == WK_KIND_RANK)
+    sweep_assign<STAGED, FIRST, WK_KIND_RANK>(P, TR, aq, as, em, stab, sn16, e, flags, V32, S);
+  else if (kind == WK_KIND_FREE)
+    sweep_assign<STAGED, FIRST, WK_KIND_FREE>(P, TR, aq, as, em, stab, sn16, e, flags, V32, S);
+  else if (kind == WK_KIND_NONE)
+    sweep_assign<STAGED, FIRST, WK_KIND_NONE>(P, TR, aq, as, em, stab, sn16, e, flags, V32, S);
+  else
+    sweep_assign<STAGED, FIRST, WK_KIND_NONE_ID>(P, TR, aq, as, em, stab, sn16, e, flags, V32, S);
+}
+
+template <bool STAGED, int SINK, bool LEAN, int NTB>
+__global__ void __launch_bounds__(NTB, 1)
     classify_sweep_kernel(const __grid_constant__ ClsParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int R = P.sw_R;
-  const int TILE = SW_NT * R;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NW = blockDim.x >> 5;
+  const int R = P.sw_R, NS = P.sw_S;
+  const int WT = 32 * R;
   const int64_t tab_bytes = STAGED ? (int64_t)P.stage_elems * 2 : 0;
   const SwSmemLayout L =
-      sw_layout(R, SINK, P.cache_log, P.direct_cells, tab_bytes);
+      sw_layout(NW, R, NS, SINK, P.cache_log, P.direct_cells, tab_bytes);
   const uint32_t sbase32 = smem_u32(smem);
-  const uint32_t bars = sbase32 + L.bars;  // [STAGES] tiles, [STAGES] = tables
-  const uint32_t tiles = sbase32 + L.tiles;
-  const uint32_t em = sbase32 + L.em;
+  const uint32_t tabbar = sbase32 + L.bars + (uint32_t)(NW * NS) * 8u;
+  const uint32_t prop_addr = tabbar + 8u;  // DIRECT: sample proposed for the table
+  const uint32_t mybars = sbase32 + L.bars + (uint32_t)(warp * NS) * 8u;
+  const uint32_t wbase = sbase32 + L.warp0 + (uint32_t)warp * L.warp_bytes;
+  const uint32_t em = wbase + (uint32_t)(2 * NS) * (uint32_t)L.tbuf * 4u;
   const uint32_t stab = sbase32 + L.tab;
   const uint32_t stage_bytes = 2u * (uint32_t)L.tbuf * 4u;
   Sink K;
   K.a0 = sbase32 + L.sink0;
   K.a1 = sbase32 + L.sink1;
   K.sh = 32 - P.cache_log;
-  const uint32_t sink_words =
-      SINK == SINK_DIRECT ? P.direct_cells
-                          : (SINK == SINK_HASHED ? (2u << P.cache_log) : 0u);
 
   int64_t n = P.n, r0 = P.r0, r1 = P.r1;
   if (P.n_dev) {
@@ -360,54 +386,55 @@ __global__ void __launch_bounds__(SW_NT, 1)
   }
   if (*P.err & ERR_PAIR_FULL) return;  // upstream stage overflowed: do nothing
   const int64_t tb0 = r0 & ~3ll;
-  const int64_t n_tiles = r1 > tb0 ? (r1 - tb0 + TILE - 1) / TILE : 0;
+  const int64_t n_tiles = r1 > tb0 ? (r1 - tb0 + WT - 1) / WT : 0;
+  const int64_t GW = (int64_t)gridDim.x * NW;
+  const int64_t gw = (int64_t)blockIdx.x * NW + warp;
+  const int64_t n_rounds = (n_tiles + GW - 1) / GW;
 
-  if (tid == 0) {
-    for (int i = 0; i <= SW_STAGES; ++i) mbar_init(bars + 8 * i, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
+  if (lane == 0)
+    for (int i = 0; i < NS; ++i) mbar_init(mybars + 8 * i, 1);
+  if (tid == 0) mbar_init(tabbar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
 
   auto issue = [&](int64_t tile, int stage) {
-    // stage records [tb-PRE, tb+TILE+POST) ∩ [0, n) of both columns
-    int64_t tb = tb0 + tile * TILE;
+    // stage records [tb-PRE, tb+WT+POST) ∩ [0, n) of both columns
+    int64_t tb = tb0 + tile * WT;
     int64_t g0 = tb >= SW_PRE ? tb - SW_PRE : 0;
-    int64_t g1 = tb + TILE + SW_POST;
+    int64_t g1 = tb + WT + SW_POST;
     if (g1 > n) g1 = n;
     uint32_t bytes = (uint32_t)(((g1 - g0) * 4 + 15) & ~15ll);
-    uint32_t dq = tiles + (uint32_t)stage * stage_bytes +
+    uint32_t dq = wbase + (uint32_t)stage * stage_bytes +
                   (uint32_t)(g0 - (tb - SW_PRE)) * 4u;
-    uint32_t bar = bars + 8 * stage;
+    uint32_t bar = mybars + 8 * stage;
     mbar_expect_tx(bar, 2 * bytes);
     bulk_g2s(dq, P.q + g0, bytes, bar);
     bulk_g2s(dq + (uint32_t)L.tbuf * 4u, P.s + g0, bytes, bar);
   };
 
-  if (tid == 0) {
-    if (STAGED) {
-      uint32_t bytes = (uint32_t)((tab_bytes + 15) & ~15ll);
-      mbar_expect_tx(bars + 8 * SW_STAGES, bytes);
-      bulk_g2s(stab, P.tab16, bytes, bars + 8 * SW_STAGES);
-    }
-    for (int st = 0; st < SW_STAGES; ++st) {
-      int64_t tile = (int64_t)blockIdx.x + (int64_t)st * gridDim.x;
+  if (STAGED && tid == 0) {
+    uint32_t bytes = (uint32_t)((tab_bytes + 15) & ~15ll);
+    mbar_expect_tx(tabbar, bytes);
+    bulk_g2s(stab, P.tab16, bytes, tabbar);
+  }
+  if (lane == 0)
+    for (int st = 0; st < NS; ++st) {
+      int64_t tile = gw + (int64_t)st * GW;
       if (tile < n_tiles) issue(tile, st);
     }
-  }
-  const uint32_t prop_addr = bars + 64;  // DIRECT: sample proposed for the table
   K.cur = P.q_sample ? -1 : P.sample;
   if (SINK == SINK_DIRECT) {
-    for (uint32_t h = tid; h < sink_words; h += SW_NT) sts32(K.a0 + h * 4, 0);
+    for (uint32_t h = tid; h < P.direct_cells; h += blockDim.x) sts32(K.a0 + h * 4, 0);
     if (tid == 0) sts32(prop_addr, 0xFFFFFFFFu);
   } else if (SINK == SINK_HASHED) {
     const uint32_t slots = 1u << P.cache_log;
-    for (uint32_t h = tid; h < slots; h += SW_NT) {
+    for (uint32_t h = tid; h < slots; h += blockDim.x) {
       sts32(K.a0 + h * 4, CACHE_EMPTY);
       sts32(K.a1 + h * 4, 0);
     }
   }
   __syncthreads();
-  if (STAGED) mbar_wait(bars + 8 * SW_STAGES, 0);
+  if (STAGED) mbar_wait(tabbar, 0);
 
   TreeRef TR;
   TR.parent = P.parent;
@@ -419,70 +446,69 @@ __global__ void __launch_bounds__(SW_NT, 1)
   const bool per_query = !LEAN && (P.q_sample || P.q_stratum);
   const int V32 = (int)P.V;
 
-  auto flush_direct = [&]() {
-    if (K.cur >= 0) {
-      const uint32_t NF1u = (uint32_t)P.NF1;
-      for (uint32_t h = tid; h < sink_words; h += SW_NT) {
-        uint32_t v = (uint32_t)lds32(K.a0 + h * 4);
-        if (v) {
-          uint32_t e = h / NF1u, f = h - e * NF1u;
-          atomicAdd(&P.cnt[((int64_t)e * P.S + K.cur) * P.NF1 + f], (ull)v);
-          sts32(K.a0 + h * 4, 0);
+  for (int64_t round = 0; round < n_rounds; ++round) {
+    const int64_t tile = round * GW + gw;
+    if (tile < n_tiles) {
+      const int stage = (int)(round % NS);
+      mbar_wait(mybars + 8 * stage, (uint32_t)((round / NS) & 1));
+      const int64_t tb = tb0 + tile * WT;
+      const int64_t sbase = tb - SW_PRE;  // global index of staged slot 0
+      const uint32_t aq = wbase + (uint32_t)stage * stage_bytes;
+      const uint32_t as = aq + (uint32_t)L.tbuf * 4u;
+      const int nrel = (int)(n - sbase < L.tbuf ? n - sbase : L.tbuf);
+      if (lane == 0) {
+        // sentinels: record 0 of the column starts a query, the last record
+        // of the column ends one
+        if (sbase + SW_PRE == 0)
+          sts32(aq + SW_PRE * 4u - 4u, ~(uint32_t)lds32(aq + SW_PRE * 4u));
+        if (nrel < L.tbuf)
+          sts32(aq + (uint32_t)nrel * 4u, ~(uint32_t)lds32(aq + (uint32_t)nrel * 4u - 4u));
+      }
+      __syncwarp();
+      SwRun S;
+      S.w0 = SW_PRE + lane * R;
+      S.w1 = S.w0 + R;
+      if (r0 - sbase > S.w0) S.w0 = (int)(r0 - sbase < (1 << 30) ? r0 - sbase : (1 << 30));
+      if (r1 - sbase < S.w1) S.w1 = (int)(r1 - sbase);
+      if (S.w1 > nrel) S.w1 = nrel;
+
+      sweep_assign_any<STAGED, true>(P, TR, aq, as, em, stab, sn16, 0,
+                                     P.kind[0], flags, V32, S);
+      __syncwarp();
+      sweep_emit<SINK, LEAN>(P, K, aq, em, prop_addr, sbase, 0, S);
+      if (!LEAN)
+        for (int e = 1; e < E; ++e) {
+          __syncwarp();
+          sweep_assign_any<STAGED, false>(P, TR, aq, as, em, stab, sn16, e,
+                                          P.kind[e], flags, V32, S);
+          __syncwarp();
+          sweep_emit<SINK, LEAN>(P, K, aq, em, prop_addr, sbase, e, S);
+        }
+      // queries longer than SW_LONGK: the whole warp, from global memory
+      unsigned lm = __ballot_sync(FULL, S.longa >= 0);
+      while (lm) {
+        const int src = __ffs(lm) - 1;
+        lm &= lm - 1;
+        const int la = __shfl_sync(FULL, S.longa, src);
+        process_long<STAGED, SINK>(P, K, stab, n, sbase + la, lane);
+      }
+      __syncwarp();  // every lane is done with this stage
+      if (lane == 0) {
+        const int64_t nt = tile + (int64_t)NS * GW;
+        if (nt < n_tiles) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          issue(nt, stage);
         }
       }
     }
-  };
-
-  int it = 0;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-    const int stage = it % SW_STAGES;
-    mbar_wait(bars + 8 * stage, (it / SW_STAGES) & 1);
-    const int64_t tb = tb0 + tile * TILE;
-    const int64_t sbase = tb - SW_PRE;  // global index of staged slot 0
-    const uint32_t aq = tiles + (uint32_t)stage * stage_bytes;
-    const uint32_t as = aq + (uint32_t)L.tbuf * 4u;
-    SwRun S;
-    S.nrel = (int)(n - sbase < L.tbuf ? n - sbase : L.tbuf);
-    S.w0 = SW_PRE + tid * R;
-    S.w1 = S.w0 + R;
-    if (r0 - sbase > S.w0) S.w0 = (int)(r0 - sbase < (1 << 30) ? r0 - sbase : (1 << 30));
-    if (r1 - sbase < S.w1) S.w1 = (int)(r1 - sbase);
-    if (S.w1 > S.nrel) S.w1 = S.nrel;
-    if (sbase + S.w0 == 0 && S.w0 < S.w1) {
-      // record 0 of the column starts a query whatever lies before it in
-      // shared memory: make the slot before it differ
-      sts32(aq + (uint32_t)S.w0 * 4u - 4u, ~(uint32_t)lds32(aq + (uint32_t)S.w0 * 4u));
-    }
-
-    sweep_assign<STAGED, true>(P, TR, aq, as, em, stab, sn16, 0, P.kind[0],
-                               flags, V32, S);
-    sweep_emit<SINK, LEAN>(P, K, aq, em, prop_addr, sbase, 0, S);
-    if (!LEAN)
-      for (int e = 1; e < E; ++e) {
-        sweep_assign<STAGED, false>(P, TR, aq, as, em, stab, sn16, e,
-                                    P.kind[e], flags, V32, S);
-        sweep_emit<SINK, LEAN>(P, K, aq, em, prop_addr, sbase, e, S);
-      }
-    // queries longer than SW_LONGK: the whole warp, from global memory
-    unsigned lm = __ballot_sync(FULL, S.longa >= 0);
-    while (lm) {
-      const int src = __ffs(lm) - 1;
-      lm &= lm - 1;
-      const int la = __shfl_sync(FULL, S.longa, src);
-      process_long<STAGED, SINK>(P, K, stab, n, sbase + la, lane);
-    }
-
-    __syncthreads();  // every thread is done with this stage and with em
-    if (tid == 0) {
-      int64_t nt = tile + (int64_t)SW_STAGES * gridDim.x;
-      if (nt < n_tiles) issue(nt, stage);
-    }
-    if (SINK == SINK_DIRECT && per_query) {
+    if (SINK == SINK_DIRECT && per_query &&
+        ((round % SW_EPOCH) == SW_EPOCH - 1)) {
       // the stream moved on to another sample: flush and re-target the table
+      __syncthreads();
       const int prop = lds32(prop_addr);
       __syncthreads();
       if (prop >= 0 && prop != K.cur) {
-        flush_direct();
+        direct_flush(P, K, tid, blockDim.x);
         if (tid == 0) sts32(prop_addr, 0xFFFFFFFFu);
         K.cur = prop;
         __syncthreads();
@@ -494,10 +520,10 @@ __global__ void __launch_bounds__(SW_NT, 1)
   if (SINK != SINK_GLOBAL) {
     __syncthreads();
     if (SINK == SINK_DIRECT) {
-      flush_direct();
+      direct_flush(P, K, tid, blockDim.x);
     } else {
       const uint32_t slots = 1u << P.cache_log;
-      for (uint32_t h = tid; h < slots; h += SW_NT) {
+      for (uint32_t h = tid; h < slots; h += blockDim.x) {
         uint32_t tag = (uint32_t)lds32(K.a0 + h * 4);
         uint32_t v = (uint32_t)lds32(K.a1 + h * 4);
         if (tag != CACHE_EMPTY && v) atomicAdd(&P.cnt[tag], (ull)v);
