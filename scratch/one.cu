@@ -1,3 +1,4 @@
 #include "../woltka_b200/csrc/wk_sweep.cuh"
 using namespace wk;
-void* f() { return (void*)classify_sweep_kernel<true, SINK_DIRECT, true, 1024>; }
+void* f() { return (void*)classify_fast_kernel<WK_KIND_RANK, 1024>; }
+void* g() { return (void*)classify_fast_kernel<WK_KIND_RANK, 768>; }

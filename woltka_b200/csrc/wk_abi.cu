@@ -302,6 +302,14 @@ int wk_create(int device, wk_ctx **out) {
         (const void *)classify_sweep_kernel<false, SINK_HASHED, false, 1024>,
         (const void *)classify_sweep_kernel<false, SINK_GLOBAL, true, 1024>,
         (const void *)classify_sweep_kernel<false, SINK_GLOBAL, false, 1024>};
+    const void *fast[] = {
+        (const void *)classify_fast_kernel<WK_KIND_RANK, 768>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE, 768>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, 1024>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE, 1024>};
+    for (const void *fn : fast)
+      CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)c->smem_optin));
     for (const void *fn : variants)
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)c->smem_optin));
@@ -850,6 +858,21 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
       int64_t n_tiles = (span + wt - 1) / wt;
       if (n_tiles <= 0) return WK_OK;
       grid = (int)std::min<int64_t>(grid, (n_tiles + NW - 1) / NW);
+      // the hand-trimmed kernel for one-entry plans (wk_sweep.cuh)
+      if (lean && st && sink == SINK_DIRECT && !n_dev && !P.assign && NT > 512 &&
+          !getenv("WK_NO_FAST") &&
+          (c->kind[0] == WK_KIND_RANK || c->kind[0] == WK_KIND_NONE)) {
+        if (c->kind[0] == WK_KIND_RANK) {
+          if (NT <= 768) classify_fast_kernel<WK_KIND_RANK, 768><<<grid, NT, L.total, c->stream>>>(P);
+          else classify_fast_kernel<WK_KIND_RANK, 1024><<<grid, NT, L.total, c->stream>>>(P);
+        } else {
+          if (NT <= 768) classify_fast_kernel<WK_KIND_NONE, 768><<<grid, NT, L.total, c->stream>>>(P);
+          else classify_fast_kernel<WK_KIND_NONE, 1024><<<grid, NT, L.total, c->stream>>>(P);
+        }
+        c->launches++;
+        CK(cudaGetLastError());
+        return WK_OK;
+      }
 #define WK_SWEEP2(ST, SK, LN)                                                     \
   do {                                                                            \
     if (NT <= 512)                                                                \
