@@ -303,10 +303,24 @@ int wk_create(int device, wk_ctx **out) {
         (const void *)classify_sweep_kernel<false, SINK_GLOBAL, true, 1024>,
         (const void *)classify_sweep_kernel<false, SINK_GLOBAL, false, 1024>};
     const void *fast[] = {
-        (const void *)classify_fast_kernel<WK_KIND_RANK, 768>,
-        (const void *)classify_fast_kernel<WK_KIND_NONE, 768>,
-        (const void *)classify_fast_kernel<WK_KIND_RANK, 1024>,
-        (const void *)classify_fast_kernel<WK_KIND_NONE, 1024>};
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_FRAC, 5>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_UNIQ, 5>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_MAJOR, 5>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_ABOVE, 5>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_FRAC, 5>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_UNIQ, 5>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_FRAC, 9>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_UNIQ, 9>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_MAJOR, 9>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_ABOVE, 9>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_FRAC, 9>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_UNIQ, 9>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_FRAC, 13>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_UNIQ, 13>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_MAJOR, 13>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_ABOVE, 13>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_FRAC, 13>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_UNIQ, 13>};
     for (const void *fn : fast)
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)c->smem_optin));
@@ -665,7 +679,7 @@ static int pack_stage(wk_ctx *c) {
   }
   c->stage_vmax = vmax;
   if (vmax >= 0xFFFF) return WK_OK;
-  const int64_t Vp = (V + 7) & ~7ll;
+  const int64_t Vp = (V + 8) & ~7ll;  // at least one 'none' pad slot after V
   size_t elems = (size_t)c->E * Vp;
   const bool sn = any_free && !c->h_sub_node.empty() && c->T < 0xFFFF;
   const bool par = need_lca && !c->h_parent.empty() && c->T < 0xFFFF;
@@ -859,19 +873,49 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
       if (n_tiles <= 0) return WK_OK;
       grid = (int)std::min<int64_t>(grid, (n_tiles + NW - 1) / NW);
       // the hand-trimmed kernel for one-entry plans (wk_sweep.cuh)
-      if (lean && st && sink == SINK_DIRECT && !n_dev && !P.assign && NT > 512 &&
+      if (lean && st && sink == SINK_DIRECT && !n_dev && !P.assign && NS == 1 &&
           !getenv("WK_NO_FAST") &&
           (c->kind[0] == WK_KIND_RANK || c->kind[0] == WK_KIND_NONE)) {
-        if (c->kind[0] == WK_KIND_RANK) {
-          if (NT <= 768) classify_fast_kernel<WK_KIND_RANK, 768><<<grid, NT, L.total, c->stream>>>(P);
-          else classify_fast_kernel<WK_KIND_RANK, 1024><<<grid, NT, L.total, c->stream>>>(P);
-        } else {
-          if (NT <= 768) classify_fast_kernel<WK_KIND_NONE, 768><<<grid, NT, L.total, c->stream>>>(P);
-          else classify_fast_kernel<WK_KIND_NONE, 1024><<<grid, NT, L.total, c->stream>>>(P);
+        int FR = 0;
+        for (int r : {13, 9, 5})
+          if (r <= rmax &&
+              sw_layout(NW, r, 1, SINK_DIRECT, 0, 2 * dcells, tbytes).total <= c->smem_optin) {
+            FR = r;
+            break;
+          }
+        const bool rk = c->kind[0] == WK_KIND_RANK;
+        const int mode = (rk && (c->flags & WK_F_MAJOR))   ? FX_MAJOR
+                         : (rk && (c->flags & WK_F_ABOVE)) ? FX_ABOVE
+                         : (c->flags & WK_F_UNIQ)          ? FX_UNIQ
+                                                           : FX_FRAC;
+        if (FR) {
+          SwSmemLayout FL = sw_layout(NW, FR, 1, SINK_DIRECT, 0, 2 * dcells, tbytes);
+          const int64_t ft = (span + 32ll * FR - 1) / (32ll * FR);
+          int fgrid = c->tune_grid > 0 ? c->tune_grid : c->sm_count;
+          fgrid = (int)std::min<int64_t>(fgrid, (ft + NW - 1) / NW);
+#define WK_FAST3(KD, MD, RR) \
+  classify_fast_kernel<KD, MD, RR><<<fgrid, NT, FL.total, c->stream>>>(P)
+#define WK_FAST2(KD, MD)              \
+  do {                                \
+    if (FR == 13) WK_FAST3(KD, MD, 13); \
+    else if (FR == 9) WK_FAST3(KD, MD, 9); \
+    else WK_FAST3(KD, MD, 5);          \
+  } while (0)
+          if (rk) {
+            if (mode == FX_MAJOR) WK_FAST2(WK_KIND_RANK, FX_MAJOR);
+            else if (mode == FX_ABOVE) WK_FAST2(WK_KIND_RANK, FX_ABOVE);
+            else if (mode == FX_UNIQ) WK_FAST2(WK_KIND_RANK, FX_UNIQ);
+            else WK_FAST2(WK_KIND_RANK, FX_FRAC);
+          } else {
+            if (mode == FX_UNIQ) WK_FAST2(WK_KIND_NONE, FX_UNIQ);
+            else WK_FAST2(WK_KIND_NONE, FX_FRAC);
+          }
+#undef WK_FAST2
+#undef WK_FAST3
+          c->launches++;
+          CK(cudaGetLastError());
+          return WK_OK;
         }
-        c->launches++;
-        CK(cudaGetLastError());
-        return WK_OK;
       }
 #define WK_SWEEP2(ST, SK, LN)                                                     \
   do {                                                                            \

@@ -599,92 +599,114 @@ __device__ __noinline__ void fx_overflow(const ClsParams &P, int64_t f, int d) {
   }
 }
 
-template <int KIND, int NTB>
-__global__ void __launch_bounds__(NTB, 1)
+enum { FX_FRAC = 0, FX_UNIQ = 1, FX_MAJOR = 2, FX_ABOVE = 3 };
+
+// The emissions sweep B leaves out: shares 1/d with d not dividing WK_UNITS
+// (overflow list) and values outside the private table's range.  Walks the
+// run again; called only when some lane of the warp met such a record.
+__device__ __noinline__ void fx_slow_emit(const ClsParams &P, uint32_t em,
+                                          uint32_t first, uint32_t stop) {
+  const uint32_t off = (uint32_t)P.dir_off[0], wid = (uint32_t)P.dir_w[0];
+  uint32_t d = 0, u = 0;
+#pragma unroll 1
+  for (uint32_t yo = first; yo < stop; yo += 4u) {
+    const int w = lds32(em + yo);
+    if (w < 0) {
+      d = ((uint32_t)w >> 24) & 63u;
+      u = c_units64[d];
+    }
+    const uint32_t code = (uint32_t)w & FX_CODE;
+    const bool isun = code == FX_UNAS;
+    if (!(w < 0 || d != 0) || !(code < FX_NONE || isun)) continue;
+    const bool inr = isun || code - off < wid;
+    const int64_t f = isun ? P.NF1 - 1 : (int64_t)code;
+    if (!u)
+      fx_overflow(P, f, (int)d);
+    else if (!inr)
+      atomicAdd(P.cnt + (int64_t)P.sample * P.NF1 + f, (ull)u);
+  }
+}
+
+// One tile stage per warp (the other warps of the SM hide the copy latency).
+// R is a template parameter so that the three per-warp columns (query,
+// subject, scratch) sit at immediate offsets of one running address.
+template <int KIND, int MODE, int R>
+__global__ void __launch_bounds__(SW_NT, 1)
     classify_fast_kernel(const __grid_constant__ ClsParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int WT = 32 * R;
+  constexpr int TBUF = WT + SW_PRE + SW_POST;
+  constexpr uint32_t SCOL = (uint32_t)TBUF * 4u;  // subject column after the query column
+  constexpr uint32_t ECOL = 2u * SCOL;            // scratch column
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int NW = blockDim.x >> 5;
-  const int R = P.sw_R, NS = P.sw_S;
-  const int WT = 32 * R;
-  const int64_t tab_bytes = (int64_t)P.stage_elems * 2;
-  const SwSmemLayout L =
-      sw_layout(NW, R, NS, SINK_DIRECT, 0, P.direct_cells, tab_bytes);
+  const SwSmemLayout L = sw_layout(NW, R, 1, SINK_DIRECT, 0, 2u * P.direct_cells,
+                                   (int64_t)P.stage_elems * 2);
   const uint32_t sbase32 = smem_u32(smem);
-  const uint32_t tabbar = sbase32 + L.bars + (uint32_t)(NW * NS) * 8u;
-  const uint32_t mybars = sbase32 + L.bars + (uint32_t)(warp * NS) * 8u;
-  const uint32_t wbase = sbase32 + L.warp0 + (uint32_t)warp * L.warp_bytes;
-  const uint32_t em = wbase + (uint32_t)(2 * NS) * (uint32_t)L.tbuf * 4u;
+  const uint32_t tabbar = sbase32 + L.bars + (uint32_t)NW * 8u;
+  const uint32_t mybar = sbase32 + L.bars + (uint32_t)warp * 8u;
+  const uint32_t aq = sbase32 + L.warp0 + (uint32_t)warp * L.warp_bytes;
   const uint32_t stab = sbase32 + L.tab;
-  const uint32_t stage_bytes = 2u * (uint32_t)L.tbuf * 4u;
-  const uint32_t scol = (uint32_t)L.tbuf * 4u;  // subject column after the query column
   const uint32_t tbl = sbase32 + L.sink0;
 
-  const int64_t n = P.n;
   const int64_t tb0 = P.r0 & ~3ll;
-  // tiles, warps and rounds fit 32 bits (a launch covers < 2^31 records)
+  // tiles and warps fit 32 bits (a launch covers < 2^31 records)
   const int n_tiles = P.r1 > tb0 ? (int)((P.r1 - tb0 + WT - 1) / WT) : 0;
   const int GW = (int)gridDim.x * NW;
   const int gw = (int)blockIdx.x * NW + warp;
 
-  if (lane == 0)
-    for (int i = 0; i < NS; ++i) mbar_init(mybars + 8 * i, 1);
-  if (tid == 0) mbar_init(tabbar, 1);
+  if (lane == 0) mbar_init(mybar, 1);
+  if (tid == 0) {
+    mbar_init(tabbar, 1);
+    sts32(tabbar + 8u, 0);
+  }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
 
-  auto issue = [&](int tile, int stage) {
-    int64_t tb = tb0 + (int64_t)tile * WT;
-    int64_t g0 = tb >= SW_PRE ? tb - SW_PRE : 0;
+  auto issue = [&](int tile) {
+    const int64_t tb = tb0 + (int64_t)tile * WT;
+    const int64_t g0 = tb >= SW_PRE ? tb - SW_PRE : 0;
     int64_t g1 = tb + WT + SW_POST;
-    if (g1 > n) g1 = n;
-    uint32_t bytes = (uint32_t)(((g1 - g0) * 4 + 15) & ~15ll);
-    uint32_t dq = wbase + (uint32_t)stage * stage_bytes +
-                  (uint32_t)(g0 - (tb - SW_PRE)) * 4u;
-    uint32_t bar = mybars + 8 * stage;
-    mbar_expect_tx(bar, 2 * bytes);
-    bulk_g2s(dq, P.q + g0, bytes, bar);
-    bulk_g2s(dq + scol, P.s + g0, bytes, bar);
+    if (g1 > P.n) g1 = P.n;
+    const uint32_t bytes = (uint32_t)(((g1 - g0) * 4 + 15) & ~15ll);
+    const uint32_t dq = aq + (uint32_t)(g0 - (tb - SW_PRE)) * 4u;
+    mbar_expect_tx(mybar, 2 * bytes);
+    bulk_g2s(dq, P.q + g0, bytes, mybar);
+    bulk_g2s(dq + SCOL, P.s + g0, bytes, mybar);
   };
 
   if (tid == 0) {
-    uint32_t bytes = (uint32_t)((tab_bytes + 15) & ~15ll);
+    const uint32_t bytes = (uint32_t)(((int64_t)P.stage_elems * 2 + 15) & ~15ll);
     mbar_expect_tx(tabbar, bytes);
     bulk_g2s(stab, P.tab16, bytes, tabbar);
   }
-  if (lane == 0)
-    for (int st = 0; st < NS; ++st) {
-      const int tile = gw + st * GW;
-      if (tile < n_tiles) issue(tile, st);
-    }
+  if (lane == 0 && gw < n_tiles) issue(gw);
 #pragma unroll 1
-  for (uint32_t h = tid; h < P.direct_cells; h += blockDim.x) sts32(tbl + h * 4, 0);
+  for (uint32_t h = tid; h < 2u * P.direct_cells; h += blockDim.x) sts32(tbl + h * 4, 0);
   __syncthreads();
   mbar_wait(tabbar, 0);
 
-  const uint32_t flags = P.flags;
-  const uint32_t V32 = (uint32_t)P.V;
+  const uint32_t V32 = (uint32_t)P.V;  // the staged row has a 'none' pad slot at V
   const uint32_t off = (uint32_t)P.dir_off[0], wid = (uint32_t)P.dir_w[0];
-  const uint32_t par16 = P.par16_off >= 0 ? stab + (uint32_t)P.par16_off * 2u : 0u;
-  ull *const cnt0 = P.cnt + (int64_t)P.sample * P.NF1;  // E == 1
+  const uint32_t unas_code = (P.flags & WK_F_UNASSIGNED) ? FX_UNAS : FX_NONE;
+  const uint32_t tblhi = tbl + P.direct_cells * 4u;  // carries out of the low words
+  const uint32_t badflag = tabbar + 8u;
 
-  int round = 0;
+  uint32_t phase = 0;
 #pragma unroll 1
-  for (int tile = gw; tile < n_tiles; tile += GW, ++round) {
-    const int stage = round % NS;
-    mbar_wait(mybars + 8 * stage, (uint32_t)((round / NS) & 1));
-    const uint32_t aq = wbase + (uint32_t)stage * stage_bytes;
+  for (int tile = gw; tile < n_tiles; tile += GW, phase ^= 1u) {
+    mbar_wait(mybar, phase);
     int w0 = SW_PRE + lane * R, w1 = w0 + R;
     if (tile == 0 || tile >= n_tiles - 2) {
       // the first and the last tiles: clip the runs to [r0, r1) and to the
       // end of the column, and plant the sentinels (record 0 of the column
       // starts a query, the last one ends one)
       const int64_t sbase = tb0 + (int64_t)tile * WT - SW_PRE;
-      const int nrel = (int)(n - sbase < L.tbuf ? n - sbase : L.tbuf);
+      const int nrel = (int)(P.n - sbase < TBUF ? P.n - sbase : TBUF);
       if (lane == 0) {
         if (sbase + SW_PRE == 0)
           sts32(aq + SW_PRE * 4u - 4u, ~(uint32_t)lds32(aq + SW_PRE * 4u));
-        if (nrel < L.tbuf)
+        if (nrel < TBUF)
           sts32(aq + (uint32_t)nrel * 4u, ~(uint32_t)lds32(aq + (uint32_t)nrel * 4u - 4u));
       }
       if (P.r0 - sbase > w0) w0 = (int)(P.r0 - sbase < (1 << 30) ? P.r0 - sbase : (1 << 30));
@@ -694,102 +716,102 @@ __global__ void __launch_bounds__(NTB, 1)
     }
 
     // ---- sweep A: values and per-query assignment ---------------------------
-    const uint32_t w1o = (uint32_t)w1 * 4u;
-    uint32_t xo = (uint32_t)w0 * 4u;
-    uint32_t first = w1o, stop = w1o;
-    int longa = -1;
+    // x, a, first, stop, end are shared-memory addresses of query-column slots
+    const uint32_t end = aq + (uint32_t)w1 * 4u;
+    uint32_t x = aq + (uint32_t)w0 * 4u;
+    uint32_t first = end, stop = end;
+    uint32_t longa = 0;
     if (w0 < w1) {
-      int qc = lds32(aq + xo);
-      if (lds32(aq + xo - 4u) == qc) {
+      int qc = lds32(x);
+      if (lds32(x - 4u) == qc) {
         // the records up to the first tail continue the previous run's query
         bool tail;
 #pragma unroll 1
         do {
-          const int qn = lds32(aq + xo + 4u);
-          xo += 4u;
+          const int qn = lds32(x + 4u);
+          x += 4u;
           tail = qn != qc;
           qc = qn;
-        } while (!tail && xo < w1o);
-        if (!tail) xo = w1o;
+        } while (!tail && x < end);
+        if (!tail) x = end;
       }
-      if (xo < w1o) {
-        first = xo;
-        uint32_t ao = xo, sig = 0, t0 = 0, neq = 0;
-        int nvalid = 0, k = 0;
+      if (x < end) {
+        first = x;
+        uint32_t a = x, sig = 0, t0 = 0, neq = 0;
+        uint32_t nvalid = 0, k = 0;
 #pragma unroll 1
         for (;;) {
-          const uint32_t sv = (uint32_t)lds32(aq + scol + xo);
-          const int qn = lds32(aq + xo + 4u);
-          const bool ishead = xo == ao;
-          uint32_t code = FX_DUP;
-          if (sv >= V32) {
-            atomicOr(P.err, ERR_BAD_SUBJECT);
-          } else {
-            // set semantics (align.py:339): signature of the query's
-            // subjects, exact look-back only when the bit is already taken
-            const uint32_t b = 1u << (sv & 31u);
-            bool dup = false;
-            if (sig & b) {
+          const uint32_t sv = (uint32_t)lds32(x + SCOL);
+          const int qn = lds32(x + 4u);
+          const uint32_t svc = min(sv, V32);
+          if (sv != svc) sts32(badflag, 1u);
+          uint32_t code = lds16(stab + svc * 2u);
+          // set semantics (align.py:339): signature of the query's subjects,
+          // exact look-back only when the bit is already taken
+          const uint32_t b = 1u << (sv & 31u);
+          bool nd = true;
+          if (sig & b) {
+            uint32_t j = a;
 #pragma unroll 1
-              for (uint32_t j = ao; j < xo; j += 4u)
-                dup |= (uint32_t)lds32(aq + scol + j) == sv;
-            }
-            sig |= b;
-            if (!dup) {
-              code = lds16(stab + sv * 2u);
-              if (ishead) t0 = code;
-              neq |= code ^ t0;
-              nvalid += (code != FX_NONE);
-              ++k;
-            }
+            do {
+              if ((uint32_t)lds32(j + SCOL) == sv) nd = false;
+              j += 4u;
+            } while (j < x);
           }
-          sts32(em + xo, code | (ishead ? EM_HEAD : 0u));
-          xo += 4u;
+          sig |= b;
+          const bool ishead = x == a;
+          if (ishead) t0 = code;
+          if (nd) {
+            neq |= code ^ t0;
+            nvalid += (code != FX_NONE);
+            ++k;
+          } else {
+            code = FX_DUP;
+          }
+          sts32(x + ECOL, code | (ishead ? EM_HEAD : 0u));
+          x += 4u;
           if (qn != qc) {
-            // the query [ao, xo) is complete
+            // the query [a, x) is complete
             uint32_t d = 0, r = t0;
             if (KIND == WK_KIND_RANK) {
               // classify.assign_rank (classify.py:81-127)
-              if (neq) {
-                if (flags & WK_F_MAJOR) {
-                  r = fx_majority(em, ao, xo - 4u, k, P.major_th);
-                } else if (flags & WK_F_ABOVE) {
+              if (MODE == FX_FRAC) {
+                if (neq) d = nvalid;  // 1/k' per subject with a taxon
+              } else if (MODE == FX_UNIQ) {
+                if (neq) r = FX_NONE;
+              } else if (MODE == FX_MAJOR) {
+                if (neq) r = fx_majority(ECOL, a, x - 4u, (int)k, P.major_th);
+              } else {
+                if (neq)
                   r = nvalid != k ? FX_NONE
-                                  : fx_lca_fold(par16, P.parent, em, ao, xo - 4u, P.root);
-                } else if (flags & WK_F_UNIQ) {
-                  r = FX_NONE;
-                } else {
-                  d = (uint32_t)nvalid;  // 1/k' per subject with a taxon
-                }
+                                  : fx_lca_fold(P.par16_off >= 0
+                                                    ? stab + (uint32_t)P.par16_off * 2u
+                                                    : 0u,
+                                                P.parent, ECOL, a, x - 4u, P.root);
               }
             } else {
               // classify.assign_none (classify.py:32-51)
-              if (k > 1) {
-                if (flags & WK_F_UNIQ)
-                  r = FX_NONE;
-                else
-                  d = (uint32_t)k;
+              if (MODE == FX_FRAC) {
+                if (k > 1) d = k;
+              } else {
+                if (k > 1) r = FX_NONE;
               }
             }
-            if (k == 0) {
-              d = 0;
-              r = FX_NONE;  // only with a bad subject (the call fails)
-            }
-            if (d == 0 && r == FX_NONE && (flags & WK_F_UNASSIGNED)) r = FX_UNAS;
-            sts32(em + ao, EM_HEAD | (d << 24) | r);
-            ao = xo;
+            if (d == 0 && r == FX_NONE) r = unas_code;
+            sts32(a + ECOL, (d << 24) + (r | EM_HEAD));
+            a = x;
             sig = 0;
             neq = 0;
             nvalid = 0;
             k = 0;
-            if (xo >= w1o) break;
-          } else if (xo - ao >= SW_LONGK * 4u) {
-            longa = (int)(ao >> 2);  // the rest of this run is one long query
+            if (x >= end) break;
+          } else if (x - a >= SW_LONGK * 4u) {
+            longa = a;  // the rest of this run is one long query
             break;
           }
           qc = qn;
         }
-        stop = ao;
+        stop = a;
       }
     }
     __syncwarp();
@@ -797,37 +819,31 @@ __global__ void __launch_bounds__(NTB, 1)
     // ---- sweep B: emit ------------------------------------------------------
     {
       uint32_t d = 0, u = 0;
+      bool slow = false;
 #pragma unroll 1
-      for (uint32_t yo = first; yo < stop; yo += 4u) {
-        const int w = lds32(em + yo);
+      for (uint32_t y = first; y < stop; y += 4u) {
+        const int w = lds32(y + ECOL);
         if (w < 0) {
           d = ((uint32_t)w >> 24) & 63u;
           u = c_units64[d];
         }
         const uint32_t code = (uint32_t)w & FX_CODE;
-        uint32_t slot = code - off;
-        if (code == FX_UNAS) slot = wid;
-        const bool want = w < 0 || d != 0;
-        if (want && (slot < wid || code == FX_UNAS)) {
-          if (u) {
-            const uint32_t old = atoms_add(tbl + slot * 4u, u);
-            if (old + u < old)
-              fx_global_add(cnt0 + (code == FX_UNAS ? (uint32_t)(P.NF1 - 1) : code), 1ull << 32);
-          } else {
-            fx_overflow(P, code == FX_UNAS ? P.NF1 - 1 : (int64_t)code, (int)d);
-          }
-        } else if (want && code < FX_NONE) {
-          // a value outside the private range
-          if (u)
-            fx_global_add(cnt0 + code, (ull)u);
-          else
-            fx_overflow(P, (int64_t)code, (int)d);
+        const bool isun = code == FX_UNAS;
+        const uint32_t slot = isun ? wid : code - off;
+        const bool want = w < 0 || d != 0;           // head, or a 1/k' share
+        const bool inr = slot < wid || isun;         // a value of the private range
+        if (want && inr && u) {
+          const uint32_t old = atoms_add(tbl + slot * 4u, u);
+          if (old + u < old) atoms_add(tblhi + slot * 4u, 1u);
+        } else if (want && (inr || code < FX_NONE)) {
+          slow = true;  // overflow denominator or out-of-range value
         }
       }
+      if (__any_sync(FULL, slow)) fx_slow_emit(P, ECOL, first, stop);
     }
 
     // queries longer than SW_LONGK: the whole warp, from global memory
-    unsigned lm = __ballot_sync(FULL, longa >= 0);
+    unsigned lm = __ballot_sync(FULL, longa != 0);
     if (lm) {
       Sink K;
       K.a0 = tbl;
@@ -837,30 +853,29 @@ __global__ void __launch_bounds__(NTB, 1)
       while (lm) {
         const int src = __ffs(lm) - 1;
         lm &= lm - 1;
-        const int la = __shfl_sync(FULL, longa, src);
+        const uint32_t la = __shfl_sync(FULL, longa, src);
         process_long<true, SINK_DIRECT>(
-            P, K, stab, n, tb0 + (int64_t)tile * WT - SW_PRE + la, lane);
+            P, K, stab, P.n,
+            tb0 + (int64_t)tile * WT - SW_PRE + (int64_t)((la - aq) >> 2), lane);
       }
     }
     __syncwarp();  // every lane is done with this stage
-    if (lane == 0) {
-      const int nt = tile + NS * GW;
-      if (nt < n_tiles) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue(nt, stage);
-      }
+    if (lane == 0 && tile + GW < n_tiles) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(tile + GW);
     }
   }
-
   // write the CTA's partial counts back (util.sum_dict, util.py:78-94)
   __syncthreads();
-  {
-    Sink K;
-    K.a0 = tbl;
-    K.a1 = 0;
-    K.sh = 0;
-    K.cur = P.sample;
-    direct_flush(P, K, tid, blockDim.x);
+  if (tid == 0 && lds32(badflag)) atomicOr(P.err, ERR_BAD_SUBJECT);
+#pragma unroll 1
+  for (uint32_t h = tid; h < P.direct_cells; h += blockDim.x) {
+    const ull v = (ull)(uint32_t)lds32(tbl + h * 4u) |
+                  ((ull)(uint32_t)lds32(tblhi + h * 4u) << 32);
+    if (v) {
+      const int64_t f = h < wid ? (int64_t)off + h : P.NF1 - 1;
+      atomicAdd(P.cnt + (int64_t)P.sample * P.NF1 + f, v);
+    }
   }
 }
 
