@@ -265,43 +265,7 @@ int wk_create(int device, wk_ctx **out) {
         (const void *)classify_kernel<true, SINK_GLOBAL, false>,
         (const void *)classify_kernel<false, SINK_DIRECT, false>,
         (const void *)classify_kernel<false, SINK_HASHED, false>,
-        (const void *)classify_kernel<false, SINK_GLOBAL, false>,
-        (const void *)classify_sweep_kernel<true, SINK_DIRECT, true, 512>,
-        (const void *)classify_sweep_kernel<true, SINK_DIRECT, false, 512>,
-        (const void *)classify_sweep_kernel<true, SINK_HASHED, true, 512>,
-        (const void *)classify_sweep_kernel<true, SINK_HASHED, false, 512>,
-        (const void *)classify_sweep_kernel<true, SINK_GLOBAL, true, 512>,
-        (const void *)classify_sweep_kernel<true, SINK_GLOBAL, false, 512>,
-        (const void *)classify_sweep_kernel<false, SINK_DIRECT, true, 512>,
-        (const void *)classify_sweep_kernel<false, SINK_DIRECT, false, 512>,
-        (const void *)classify_sweep_kernel<false, SINK_HASHED, true, 512>,
-        (const void *)classify_sweep_kernel<false, SINK_HASHED, false, 512>,
-        (const void *)classify_sweep_kernel<false, SINK_GLOBAL, true, 512>,
-        (const void *)classify_sweep_kernel<false, SINK_GLOBAL, false, 512>,
-        (const void *)classify_sweep_kernel<true, SINK_DIRECT, true, 768>,
-        (const void *)classify_sweep_kernel<true, SINK_DIRECT, false, 768>,
-        (const void *)classify_sweep_kernel<true, SINK_HASHED, true, 768>,
-        (const void *)classify_sweep_kernel<true, SINK_HASHED, false, 768>,
-        (const void *)classify_sweep_kernel<true, SINK_GLOBAL, true, 768>,
-        (const void *)classify_sweep_kernel<true, SINK_GLOBAL, false, 768>,
-        (const void *)classify_sweep_kernel<false, SINK_DIRECT, true, 768>,
-        (const void *)classify_sweep_kernel<false, SINK_DIRECT, false, 768>,
-        (const void *)classify_sweep_kernel<false, SINK_HASHED, true, 768>,
-        (const void *)classify_sweep_kernel<false, SINK_HASHED, false, 768>,
-        (const void *)classify_sweep_kernel<false, SINK_GLOBAL, true, 768>,
-        (const void *)classify_sweep_kernel<false, SINK_GLOBAL, false, 768>,
-        (const void *)classify_sweep_kernel<true, SINK_DIRECT, true, 1024>,
-        (const void *)classify_sweep_kernel<true, SINK_DIRECT, false, 1024>,
-        (const void *)classify_sweep_kernel<true, SINK_HASHED, true, 1024>,
-        (const void *)classify_sweep_kernel<true, SINK_HASHED, false, 1024>,
-        (const void *)classify_sweep_kernel<true, SINK_GLOBAL, true, 1024>,
-        (const void *)classify_sweep_kernel<true, SINK_GLOBAL, false, 1024>,
-        (const void *)classify_sweep_kernel<false, SINK_DIRECT, true, 1024>,
-        (const void *)classify_sweep_kernel<false, SINK_DIRECT, false, 1024>,
-        (const void *)classify_sweep_kernel<false, SINK_HASHED, true, 1024>,
-        (const void *)classify_sweep_kernel<false, SINK_HASHED, false, 1024>,
-        (const void *)classify_sweep_kernel<false, SINK_GLOBAL, true, 1024>,
-        (const void *)classify_sweep_kernel<false, SINK_GLOBAL, false, 1024>};
+        (const void *)classify_kernel<false, SINK_GLOBAL, false>};
     const void *fast[] = {
         (const void *)classify_fast_kernel<WK_KIND_RANK, FX_FRAC, 5>,
         (const void *)classify_fast_kernel<WK_KIND_RANK, FX_UNIQ, 5>,
@@ -824,128 +788,60 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   int grid = c->tune_grid > 0 ? c->tune_grid : c->sm_count;
 
   const uint32_t dir_cells = plan_direct_ranges(c, P);
-  // ---- the sweep kernel (wk_sweep.cuh) unless the window kernel is forced ----
-  if (c->tune_block != 1 &&
-      std::max<int64_t>(std::max<int64_t>(c->NF + 1, c->T), P.V) <= SW_MAX_VALUE) {
-    const bool st = staged;
-    const int64_t tbytes = st ? (int64_t)c->stage_elems * 2 : 0;
-    int NT = c->tune_block % 10000, NS = c->tune_block / 10000;
+  // ---- the run-per-lane kernel for one-entry plans (wk_sweep.cuh) ----------
+  // tune_block: 1 = always the window kernel; otherwise threads per CTA
+  if (c->tune_block != 1 && lean && staged && !dqstrat && c->tune_cache == 0 &&
+      dir_cells != 0xFFFFFFFFu && !n_dev && !P.assign &&
+      (c->kind[0] == WK_KIND_RANK || c->kind[0] == WK_KIND_NONE)) {
+    const int64_t tbytes = (int64_t)c->stage_elems * 2;
+    int NT = c->tune_block;
     if (NT < 64 || NT > SW_NT) NT = SW_NT;
-    if (NS < 1 || NS > 4) NS = 1;
+    NT &= ~31;
     const int NW = NT / 32;
-    int rmax = SW_RMAX;
-    if (const char *ev = getenv("WK_SWEEP_R")) rmax = std::max(3, std::min(SW_RMAX, atoi(ev) | 1));
-    auto pick_r = [&](int sk, int cl, uint32_t dc) {
-      for (int R = rmax; R >= 3; R -= 2)
-        if (sw_layout(NW, R, NS, sk, cl, dc, tbytes).total <= c->smem_optin) return R;
-      return 0;
-    };
-    int sink = SINK_GLOBAL, cache_log = 0, R = 0;
-    uint32_t dcells = 0;
-    if (!dqstrat && c->tune_cache >= 0) {
-      const bool want_hashed = c->tune_cache > 0 && c->tune_cache < 1000000;
-      if (!want_hashed && dir_cells != 0xFFFFFFFFu &&
-          (R = pick_r(SINK_DIRECT, 0, dir_cells)) >= 7) {
-        sink = SINK_DIRECT;
-        dcells = dir_cells;
-      } else if (cells < 0xFFFFFFFFull) {
-        int want = 13;
-        if (c->tune_cache > 0) {
-          want = 0;
-          while ((1 << (want + 1)) <= c->tune_cache) ++want;
-        }
-        for (cache_log = want; cache_log >= 8; --cache_log)
-          if ((R = pick_r(SINK_HASHED, cache_log, 0)) >= 7) break;
-        if (cache_log >= 8) sink = SINK_HASHED;
-        else cache_log = 0;
+    int rmax = 13;
+    if (const char *ev = getenv("WK_SWEEP_R")) rmax = atoi(ev);
+    int FR = 0;
+    for (int r : {13, 9, 5})
+      if (r <= rmax &&
+          sw_layout(NW, r, 2 * dir_cells, tbytes).total <= c->smem_optin) {
+        FR = r;
+        break;
       }
-    }
-    if (sink == SINK_GLOBAL) R = pick_r(SINK_GLOBAL, 0, 0);
-    if (R >= 3) {
-      P.sw_R = R;
-      P.sw_S = NS;
-      P.cache_log = cache_log;
-      P.direct_cells = dcells;
-      SwSmemLayout L = sw_layout(NW, R, NS, sink, cache_log, dcells, tbytes);
-      const int64_t wt = 32ll * R;
-      int64_t span = (n_dev ? n_bound : r1) - (r0 & ~3ll);
-      int64_t n_tiles = (span + wt - 1) / wt;
-      if (n_tiles <= 0) return WK_OK;
-      grid = (int)std::min<int64_t>(grid, (n_tiles + NW - 1) / NW);
-      // the hand-trimmed kernel for one-entry plans (wk_sweep.cuh)
-      if (lean && st && sink == SINK_DIRECT && !n_dev && !P.assign && NS == 1 &&
-          !getenv("WK_NO_FAST") &&
-          (c->kind[0] == WK_KIND_RANK || c->kind[0] == WK_KIND_NONE)) {
-        int FR = 0;
-        for (int r : {13, 9, 5})
-          if (r <= rmax &&
-              sw_layout(NW, r, 1, SINK_DIRECT, 0, 2 * dcells, tbytes).total <= c->smem_optin) {
-            FR = r;
-            break;
-          }
-        const bool rk = c->kind[0] == WK_KIND_RANK;
-        const int mode = (rk && (c->flags & WK_F_MAJOR))   ? FX_MAJOR
-                         : (rk && (c->flags & WK_F_ABOVE)) ? FX_ABOVE
-                         : (c->flags & WK_F_UNIQ)          ? FX_UNIQ
-                                                           : FX_FRAC;
-        if (FR) {
-          SwSmemLayout FL = sw_layout(NW, FR, 1, SINK_DIRECT, 0, 2 * dcells, tbytes);
-          const int64_t ft = (span + 32ll * FR - 1) / (32ll * FR);
-          int fgrid = c->tune_grid > 0 ? c->tune_grid : c->sm_count;
-          fgrid = (int)std::min<int64_t>(fgrid, (ft + NW - 1) / NW);
+    const bool rk = c->kind[0] == WK_KIND_RANK;
+    const int mode = (rk && (c->flags & WK_F_MAJOR))   ? FX_MAJOR
+                     : (rk && (c->flags & WK_F_ABOVE)) ? FX_ABOVE
+                     : (c->flags & WK_F_UNIQ)          ? FX_UNIQ
+                                                       : FX_FRAC;
+    const int64_t span = r1 - (r0 & ~3ll);
+    if (FR && span > 0) {
+      P.direct_cells = dir_cells;
+      const SwSmemLayout FL = sw_layout(NW, FR, 2 * dir_cells, tbytes);
+      const int64_t ft = (span + 32ll * FR - 1) / (32ll * FR);
+      const int fgrid = (int)std::min<int64_t>(grid, (ft + NW - 1) / NW);
 #define WK_FAST3(KD, MD, RR) \
   classify_fast_kernel<KD, MD, RR><<<fgrid, NT, FL.total, c->stream>>>(P)
-#define WK_FAST2(KD, MD)              \
-  do {                                \
-    if (FR == 13) WK_FAST3(KD, MD, 13); \
+#define WK_FAST2(KD, MD)                   \
+  do {                                     \
+    if (FR == 13) WK_FAST3(KD, MD, 13);    \
     else if (FR == 9) WK_FAST3(KD, MD, 9); \
-    else WK_FAST3(KD, MD, 5);          \
+    else WK_FAST3(KD, MD, 5);              \
   } while (0)
-          if (rk) {
-            if (mode == FX_MAJOR) WK_FAST2(WK_KIND_RANK, FX_MAJOR);
-            else if (mode == FX_ABOVE) WK_FAST2(WK_KIND_RANK, FX_ABOVE);
-            else if (mode == FX_UNIQ) WK_FAST2(WK_KIND_RANK, FX_UNIQ);
-            else WK_FAST2(WK_KIND_RANK, FX_FRAC);
-          } else {
-            if (mode == FX_UNIQ) WK_FAST2(WK_KIND_NONE, FX_UNIQ);
-            else WK_FAST2(WK_KIND_NONE, FX_FRAC);
-          }
+      if (rk) {
+        if (mode == FX_MAJOR) WK_FAST2(WK_KIND_RANK, FX_MAJOR);
+        else if (mode == FX_ABOVE) WK_FAST2(WK_KIND_RANK, FX_ABOVE);
+        else if (mode == FX_UNIQ) WK_FAST2(WK_KIND_RANK, FX_UNIQ);
+        else WK_FAST2(WK_KIND_RANK, FX_FRAC);
+      } else {
+        if (mode == FX_UNIQ) WK_FAST2(WK_KIND_NONE, FX_UNIQ);
+        else WK_FAST2(WK_KIND_NONE, FX_FRAC);
+      }
 #undef WK_FAST2
 #undef WK_FAST3
-          c->launches++;
-          CK(cudaGetLastError());
-          return WK_OK;
-        }
-      }
-#define WK_SWEEP2(ST, SK, LN)                                                     \
-  do {                                                                            \
-    if (NT <= 512)                                                                \
-      classify_sweep_kernel<ST, SK, LN, 512><<<grid, NT, L.total, c->stream>>>(P);  \
-    else if (NT <= 768)                                                           \
-      classify_sweep_kernel<ST, SK, LN, 768><<<grid, NT, L.total, c->stream>>>(P);  \
-    else                                                                          \
-      classify_sweep_kernel<ST, SK, LN, 1024><<<grid, NT, L.total, c->stream>>>(P); \
-  } while (0)
-#define WK_SWEEP(ST, SK)              \
-  do {                                \
-    if (lean) WK_SWEEP2(ST, SK, true); \
-    else WK_SWEEP2(ST, SK, false);    \
-  } while (0)
-      if (st) {
-        if (sink == SINK_DIRECT) WK_SWEEP(true, SINK_DIRECT);
-        else if (sink == SINK_HASHED) WK_SWEEP(true, SINK_HASHED);
-        else WK_SWEEP(true, SINK_GLOBAL);
-      } else {
-        if (sink == SINK_DIRECT) WK_SWEEP(false, SINK_DIRECT);
-        else if (sink == SINK_HASHED) WK_SWEEP(false, SINK_HASHED);
-        else WK_SWEEP(false, SINK_GLOBAL);
-      }
-#undef WK_SWEEP
-#undef WK_SWEEP2
       c->launches++;
       CK(cudaGetLastError());
       return WK_OK;
     }
+    if (span <= 0) return WK_OK;
   }
 
   const int64_t tab_bytes = staged ? (int64_t)c->stage_elems * 2 : 0;

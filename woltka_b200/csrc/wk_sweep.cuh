@@ -1,8 +1,9 @@
-// wk_sweep.cuh — run-per-lane classify+count kernel for sm_100a.
+// wk_sweep.cuh — run-per-lane classify+count kernel for sm_100a
+// (classify_fast_kernel): the hot path of one-entry plans.
 //
 // Same contract as classify_kernel (wk_classify.cuh; reference
-// workflow.py:316-335, :1017-1058, classify.py:32-127, :144-171, :216-249,
-// :300-317, tree.py:513-566), different decomposition.
+// workflow.py:316-335, :1017-1058, classify.py:32-127, :144-171, :300-317,
+// tree.py:513-566), different decomposition.
 //
 // classify_kernel gives every lane one record and resolves the queries of a
 // 32-record window with ballots and shuffles: ~250 warp instructions per
@@ -17,20 +18,28 @@
 //
 //   * every WARP runs its own pipeline: tiles of 32*R records of both columns
 //     land in the warp's slice of shared memory through TMA bulk copies
-//     (cp.async.bulk + mbarrier complete_tx) issued by its lane 0; there is
+//     (cp.async.bulk + mbarrier complete_tx) issued by its lane 0, one stage
+//     per warp — the other 31 warps of the SM hide the copy latency; there is
 //     no CTA-wide barrier in the steady state, warps drift freely;
-//   * sweep A (per entry of the plan) walks the run once: set semantics of
-//     the subject pool (align.py:339) through a 32-bit signature of the query's
-//     subjects, exact look-back only on a signature hit; the entry's table
-//     value of every record goes to a scratch column `em`; at the tail of a
-//     query its assignment (unique result, or the denominator of the 1/k'
-//     split) is written into the head's word;
+//   * sweep A walks the run once: set semantics of the subject pool
+//     (align.py:339) through a 32-bit signature of the query's subjects, exact
+//     look-back only on a signature hit; the table value of every record goes
+//     to a scratch column; --above folds the LCA and --major runs a
+//     Boyer-Moore vote record by record; at the tail of a query its assignment
+//     (unique result, or the denominator of the 1/k' split) is written into
+//     the head's scratch word;
 //   * sweep B walks the same records again and emits: one unit at the head of
 //     a uniquely assigned query, 1/k' at every contributing record otherwise —
-//     no per-query loop, no divergence beyond the predicate;
-//   * counts leave through the same sinks as classify_kernel;
-//   * queries longer than SW_LONGK records are handed, after the sweeps, to
-//     the warp-cooperative process_long.
+//     no per-query loop, no divergence beyond the predicate; counts go to the
+//     CTA's private direct table (low words + a carry table);
+//   * rare events never sit in the hot loops: denominators that do not divide
+//     WK_UNITS and values outside the private table are re-walked by a
+//     separate routine, queries longer than SW_LONGK records are handed to
+//     the warp-cooperative process_long after the sweeps.
+//
+// Scope: ONE entry (a rank, or --rank none through a table), scalar sample,
+// no strata, no read map, tables staged as uint16.  Every other plan takes
+// classify_kernel.
 #pragma once
 #include "wk_classify.cuh"
 
@@ -40,16 +49,7 @@ constexpr int SW_NT = 1024;     // launch bound: threads per CTA
 constexpr int SW_PRE = 4;       // records staged before the tile
 constexpr int SW_POST = 44;     // halo after the tile (>= SW_LONGK + 3)
 constexpr int SW_LONGK = 40;    // longer queries take process_long
-constexpr int SW_RMAX = 21;     // records per lane and tile (odd)
-constexpr int SW_EPOCH = 8;     // rounds between CTA barriers (sample following)
-
-// scratch word of a record: value (24 bits) | denominator (6 bits, head only,
-// 0 = unique assignment) | head flag (bit 31)
-constexpr uint32_t EM_VMASK = 0xFFFFFFu;
-constexpr uint32_t EM_NONE = 0xFFFFFFu;  // no value (None)
-constexpr uint32_t EM_DUP = 0xFFFFFEu;   // repeat of an earlier subject
 constexpr uint32_t EM_HEAD = 0x80000000u;
-constexpr int64_t SW_MAX_VALUE = 0xFFFFFD;  // largest feature / node / subject
 
 // units of one 1/d share, d = 0 meaning a unique assignment; 0 = d does not
 // divide WK_UNITS (overflow list)
@@ -64,505 +64,30 @@ __constant__ uint32_t c_units64[64] = {
     11440};
 
 struct SwSmemLayout {
-  uint32_t bars, warp0, warp_bytes, sink0, sink1, tab, total;
-  int R, S, NW, tbuf;
+  uint32_t bars, warp0, warp_bytes, sink0, tab, total;
+  int tbuf;
 };
-__host__ __device__ inline SwSmemLayout sw_layout(int NW, int R, int S, int sink,
-                                                  int cache_log,
-                                                  uint32_t direct_cells,
+// NW warps, runs of R records, `cells` 32-bit words of count table, staged
+// tables of tab_bytes
+__host__ __device__ inline SwSmemLayout sw_layout(int NW, int R, uint32_t cells,
                                                   int64_t tab_bytes) {
   SwSmemLayout L;
-  L.R = R;
-  L.S = S;
-  L.NW = NW;
   L.tbuf = 32 * R + SW_PRE + SW_POST;
-  L.bars = 0;  // NW*S tile barriers, 1 table barrier, 1 word (sample proposal)
-  L.warp0 = (uint32_t)((NW * S + 2) * 8 + 127) & ~127u;
-  L.warp_bytes = (uint32_t)(2 * S + 1) * (uint32_t)L.tbuf * 4u;
+  L.bars = 0;  // NW tile barriers, 1 table barrier, 1 flag word
+  L.warp0 = (uint32_t)((NW + 2) * 8 + 127) & ~127u;
+  L.warp_bytes = 3u * (uint32_t)L.tbuf * 4u;  // query, subject, scratch columns
   L.sink0 = L.warp0 + (uint32_t)NW * L.warp_bytes;
-  uint32_t w0 = 0, w1 = 0;
-  if (sink == SINK_DIRECT) w0 = direct_cells * 4;
-  if (sink == SINK_HASHED) w0 = w1 = (1u << cache_log) * 4;
-  L.sink1 = L.sink0 + w0;
-  L.tab = (L.sink1 + w1 + 127) & ~127u;
+  L.tab = (L.sink0 + cells * 4u + 127) & ~127u;
   L.total = L.tab + (uint32_t)((tab_bytes + 15) & ~15ll);
   return L;
 }
 
-struct SwRun {
-  int w0, w1;   // own records [w0, w1) in staged coordinates
-  int xfirst;   // first owned head
-  int xstop;    // one past the last record of an owned, finished query
-  int longa;    // head of an owned query longer than SW_LONGK, or -1
-};
-
-// table value of subject sv as a scratch value; `row` = the entry's row
-template <bool STAGED>
-__device__ __forceinline__ uint32_t sw_tab(const ClsParams &P, uint32_t row16,
-                                           const int32_t *row32, int sv) {
-  if (STAGED) {
-    const uint32_t v = lds16(row16 + (uint32_t)sv * 2u);
-    return v == 0xFFFFu ? EM_NONE : v;
-  } else {
-    return (uint32_t)__ldg(row32 + sv) & EM_VMASK;
-  }
-}
-
-__device__ __noinline__ uint32_t sw_lca_fold(const TreeRef TR, uint32_t em,
-                                             uint32_t ao, uint32_t xo,
-                                             int root) {
-  int acc = lds32(em + ao) & EM_VMASK;
-#pragma unroll 1
-  for (uint32_t j = ao + 4; j <= xo; j += 4) {
-    const uint32_t vj = (uint32_t)lds32(em + j) & EM_VMASK;
-    if (vj != EM_DUP) acc = lca2(TR, acc, (int)vj);
-  }
-  return acc == root ? EM_NONE : (uint32_t)acc;
-}
-
-// classify.majority (classify.py:300-317): top count among the distinct
-// subjects' values, first seen wins ties; None is a value like any other
-__device__ __noinline__ uint32_t sw_majority(uint32_t em, uint32_t ao,
-                                             uint32_t xo, int k, double th) {
-  int best = 0;
-  uint32_t tw = EM_NONE;
-#pragma unroll 1
-  for (uint32_t j = ao; j <= xo; j += 4) {
-    const uint32_t vj = (uint32_t)lds32(em + j) & EM_VMASK;
-    if (vj == EM_DUP) continue;
-    int c = 0;
-#pragma unroll 1
-    for (uint32_t j2 = ao; j2 <= xo; j2 += 4)
-      c += ((uint32_t)lds32(em + j2) & EM_VMASK) == vj;
-    if (c > best) {
-      best = c;
-      tw = vj;
-    }
-  }
-  return ((double)best >= __dmul_rn((double)k, th)) ? tw : EM_NONE;
-}
-
-// Sweep A of one entry: values + per-query assignment into `em`.  All
-// positions are byte offsets (record index * 4) into the staged columns.
-template <bool STAGED, bool FIRST, int KIND>
-__device__ __forceinline__ void sweep_assign(const ClsParams &P,
-                                             const TreeRef &TR, uint32_t aq,
-                                             uint32_t as, uint32_t em,
-                                             uint32_t stab, uint32_t sn16,
-                                             int e, uint32_t flags, int V32,
-                                             SwRun &S) {
-  uint32_t xo;
-  const uint32_t w1o = (uint32_t)S.w1 * 4u;
-  if (FIRST) {
-    S.longa = -1;
-    S.xfirst = S.xstop = S.w0;
-    xo = (uint32_t)S.w0 * 4u;
-    if (S.w0 >= S.w1) return;
-    // skip the records that continue a query of the previous run
-    if (lds32(aq + xo - 4u) == lds32(aq + xo)) {
-      bool tail;
-#pragma unroll 1
-      do {
-        tail = lds32(aq + xo) != lds32(aq + xo + 4u);
-        xo += 4u;
-      } while (!tail && xo < w1o);
-    }
-    if (xo >= w1o) return;  // no head in this run
-    S.xfirst = S.xstop = (int)(xo >> 2);
-  } else {
-    xo = (uint32_t)S.xfirst * 4u;
-    if (S.xfirst >= S.xstop) return;
-  }
-  const uint32_t stopo = (uint32_t)S.xstop * 4u;
-  const uint32_t NFv = (uint32_t)(P.NF1 - 1);
-  const bool unas = flags & WK_F_UNASSIGNED;
-  const uint32_t row16 = stab + (uint32_t)(e * P.Vp) * 2u;
-  const int32_t *row32 = P.tab + (int64_t)e * P.V;
-  uint32_t ao = xo;
-  uint32_t t0 = EM_NONE, sig = 0;
-  int nvalid = 0, k = 0;
-  bool alleq = true, anyneg = false;
-  int qc = 0;
-  if (FIRST) qc = lds32(aq + xo);
-#pragma unroll 1
-  for (;;) {
-    const bool ishead = xo == ao;
-    const int sv = lds32(as + xo);
-    bool tail, dup = false;
-    if (FIRST) {
-      const int qn = lds32(aq + xo + 4u);
-      tail = qn != qc;
-      qc = qn;
-      if ((unsigned)sv >= (unsigned)V32) {
-        atomicOr(P.err, ERR_BAD_SUBJECT);
-        dup = true;
-      } else {
-        // set semantics (align.py:339): signature of the query's subjects,
-        // exact look-back only when the bit is already taken
-        const uint32_t b = 1u << (sv & 31);
-        if (sig & b) {
-#pragma unroll 1
-          for (uint32_t j = ao; j < xo; j += 4u) dup |= lds32(as + j) == sv;
-        }
-        sig |= b;
-      }
-    } else {
-      // structure left behind by the previous entry
-      dup = ((uint32_t)lds32(em + xo) & EM_VMASK) == EM_DUP ||
-            (unsigned)sv >= (unsigned)V32;
-      tail = xo + 4u >= stopo || lds32(em + xo + 4u) < 0;
-    }
-
-    uint32_t v = EM_DUP;
-    if (!dup) {
-      ++k;
-      if (KIND == WK_KIND_RANK) {
-        v = sw_tab<STAGED>(P, row16, row32, sv);
-        if (ishead) t0 = v;
-        alleq &= (v == t0);
-        nvalid += (v != EM_NONE);
-        anyneg |= (v == EM_NONE);
-      } else if (KIND == WK_KIND_FREE) {
-        if (sn16) {
-          v = lds16(sn16 + (uint32_t)sv * 2u);
-          if (v == 0xFFFFu) v = EM_NONE;
-        } else {
-          v = (uint32_t)__ldg(P.sub_node + sv) & EM_VMASK;
-        }
-        anyneg |= (v == EM_NONE);
-      } else if (KIND == WK_KIND_NONE) {
-        v = sw_tab<STAGED>(P, row16, row32, sv);
-        if (ishead) t0 = v;
-      } else {
-        v = (uint32_t)sv;
-        if (ishead) t0 = v;
-      }
-    }
-    sts32(em + xo, v | (ishead ? EM_HEAD : 0u));
-
-    if (tail) {
-      // ---- the query [ao, xo] is complete: its assignment ----------------
-      uint32_t d = 0, r = EM_NONE;
-      if (k == 0) {
-        // only reachable with a bad subject (the call fails)
-      } else if (KIND == WK_KIND_RANK) {
-        // classify.assign_rank (classify.py:81-127)
-        if (alleq) {
-          r = t0;
-        } else if (flags & WK_F_MAJOR) {
-          r = sw_majority(em, ao, xo, k, P.major_th);
-        } else if (flags & WK_F_ABOVE) {
-          if (!anyneg) r = sw_lca_fold(TR, em, ao, xo, P.root);
-        } else if (!(flags & WK_F_UNIQ)) {
-          d = (uint32_t)nvalid;  // 1/k' to every subject with a taxon
-          r = t0;
-        }
-      } else if (KIND == WK_KIND_FREE) {
-        // classify.assign_free (classify.py:54-78)
-        if (k == 1) {
-          r = sw_tab<STAGED>(P, row16, row32, lds32(as + ao));
-        } else if (!anyneg) {
-          r = sw_lca_fold(TR, em, ao, xo, P.root);
-        }
-      } else {
-        // classify.assign_none (classify.py:32-51)
-        if (k == 1) {
-          r = t0;
-        } else if (!(flags & WK_F_UNIQ)) {
-          d = (uint32_t)k;
-          r = t0;
-        }
-      }
-      if (d == 0 && r == EM_NONE && unas) r = NFv;
-      sts32(em + ao, EM_HEAD | (d << 24) | r);
-      xo += 4u;
-      ao = xo;
-      nvalid = 0;
-      k = 0;
-      sig = 0;
-      alleq = true;
-      anyneg = false;
-      if (FIRST ? xo >= w1o : xo >= stopo) break;
-    } else {
-      xo += 4u;
-      if (FIRST && xo - ao >= SW_LONGK * 4u) {
-        S.longa = (int)(ao >> 2);  // the rest of this run is one long query
-        break;
-      }
-    }
-  }
-  if (FIRST) S.xstop = (int)(ao >> 2);
-}
-
-// Sweep B of one entry: emit what sweep A decided.
-template <int SINK, bool LEAN>
-__device__ __forceinline__ void sweep_emit(const ClsParams &P, const Sink &K,
-                                           uint32_t aq, uint32_t em,
-                                           uint32_t prop_addr, int64_t sbase,
-                                           int e, const SwRun &S) {
-  const bool per_query = !LEAN && (P.q_sample || P.q_stratum);
-  int32_t *asg = P.assign ? P.assign + (int64_t)e * P.assign_stride + sbase
-                          : nullptr;
-  int samp = P.sample, strat = 0;
-  bool live = true;
-  uint32_t d = 0, u = 0;
-  const uint32_t stopo = (uint32_t)S.xstop * 4u;
-#pragma unroll 1
-  for (uint32_t xo = (uint32_t)S.xfirst * 4u; xo < stopo; xo += 4u) {
-    const int w = lds32(em + xo);
-    const uint32_t v = (uint32_t)w & EM_VMASK;
-    const bool head = w < 0;
-    if (head) {
-      d = ((uint32_t)w >> 24) & 63u;
-      u = c_units64[d];
-      if (per_query) {
-        const int qid = lds32(aq + xo);
-        samp = P.q_sample ? __ldg(P.q_sample + qid) : P.sample;
-        strat = P.q_stratum ? __ldg(P.q_stratum + qid) : 0;
-        live = strat >= 0 && (unsigned)samp < (unsigned)P.S;
-        if (SINK == SINK_DIRECT && live && samp != K.cur)
-          sts32(prop_addr, (uint32_t)samp);  // ask for the table to follow
-      }
-    }
-    const bool emit = v < EM_DUP && (head || d != 0);
-    if (emit && live) {
-      if (u)
-        emit_units<SINK>(P, K, e, samp, strat, (int64_t)v, u);
-      else
-        emit_frac<SINK>(P, K, e, samp, strat, (int64_t)v, (int64_t)d);
-    }
-    if (asg)
-      asg[xo >> 2] =
-          emit ? (int)(v | (head && d == 0 ? (uint32_t)ASSIGN_UNIQ : 0u)) : -1;
-  }
-}
-
-template <bool STAGED, bool FIRST>
-__device__ __forceinline__ void sweep_assign_any(const ClsParams &P,
-                                                 const TreeRef &TR, uint32_t aq,
-                                                 uint32_t as, uint32_t em,
-                                                 uint32_t stab, uint32_t sn16,
-                                                 int e, int kind, uint32_t flags,
-                                                 int V32, SwRun &S) {
-  if (kind == WK_KIND_RANK)
-    sweep_assign<STAGED, FIRST, WK_KIND_RANK>(P, TR, aq, as, em, stab, sn16, e, flags, V32, S);
-  else if (kind == WK_KIND_FREE)
-    sweep_assign<STAGED, FIRST, WK_KIND_FREE>(P, TR, aq, as, em, stab, sn16, e, flags, V32, S);
-  else if (kind == WK_KIND_NONE)
-    sweep_assign<STAGED, FIRST, WK_KIND_NONE>(P, TR, aq, as, em, stab, sn16, e, flags, V32, S);
-  else
-    sweep_assign<STAGED, FIRST, WK_KIND_NONE_ID>(P, TR, aq, as, em, stab, sn16, e, flags, V32, S);
-}
-
-template <bool STAGED, int SINK, bool LEAN, int NTB>
-__global__ void __launch_bounds__(NTB, 1)
-    classify_sweep_kernel(const __grid_constant__ ClsParams P) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int NW = blockDim.x >> 5;
-  const int R = P.sw_R, NS = P.sw_S;
-  const int WT = 32 * R;
-  const int64_t tab_bytes = STAGED ? (int64_t)P.stage_elems * 2 : 0;
-  const SwSmemLayout L =
-      sw_layout(NW, R, NS, SINK, P.cache_log, P.direct_cells, tab_bytes);
-  const uint32_t sbase32 = smem_u32(smem);
-  const uint32_t tabbar = sbase32 + L.bars + (uint32_t)(NW * NS) * 8u;
-  const uint32_t prop_addr = tabbar + 8u;  // DIRECT: sample proposed for the table
-  const uint32_t mybars = sbase32 + L.bars + (uint32_t)(warp * NS) * 8u;
-  const uint32_t wbase = sbase32 + L.warp0 + (uint32_t)warp * L.warp_bytes;
-  const uint32_t em = wbase + (uint32_t)(2 * NS) * (uint32_t)L.tbuf * 4u;
-  const uint32_t stab = sbase32 + L.tab;
-  const uint32_t stage_bytes = 2u * (uint32_t)L.tbuf * 4u;
-  Sink K;
-  K.a0 = sbase32 + L.sink0;
-  K.a1 = sbase32 + L.sink1;
-  K.sh = 32 - P.cache_log;
-
-  int64_t n = P.n, r0 = P.r0, r1 = P.r1;
-  if (P.n_dev) {
-    n = (int64_t)*P.n_dev;
-    r0 = 0;
-    r1 = n;
-  }
-  if (*P.err & ERR_PAIR_FULL) return;  // upstream stage overflowed: do nothing
-  const int64_t tb0 = r0 & ~3ll;
-  const int64_t n_tiles = r1 > tb0 ? (r1 - tb0 + WT - 1) / WT : 0;
-  const int64_t GW = (int64_t)gridDim.x * NW;
-  const int64_t gw = (int64_t)blockIdx.x * NW + warp;
-  const int64_t n_rounds = (n_tiles + GW - 1) / GW;
-
-  if (lane == 0)
-    for (int i = 0; i < NS; ++i) mbar_init(mybars + 8 * i, 1);
-  if (tid == 0) mbar_init(tabbar, 1);
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();
-
-  auto issue = [&](int64_t tile, int stage) {
-    // stage records [tb-PRE, tb+WT+POST) ∩ [0, n) of both columns
-    int64_t tb = tb0 + tile * WT;
-    int64_t g0 = tb >= SW_PRE ? tb - SW_PRE : 0;
-    int64_t g1 = tb + WT + SW_POST;
-    if (g1 > n) g1 = n;
-    uint32_t bytes = (uint32_t)(((g1 - g0) * 4 + 15) & ~15ll);
-    uint32_t dq = wbase + (uint32_t)stage * stage_bytes +
-                  (uint32_t)(g0 - (tb - SW_PRE)) * 4u;
-    uint32_t bar = mybars + 8 * stage;
-    mbar_expect_tx(bar, 2 * bytes);
-    bulk_g2s(dq, P.q + g0, bytes, bar);
-    bulk_g2s(dq + (uint32_t)L.tbuf * 4u, P.s + g0, bytes, bar);
-  };
-
-  if (STAGED && tid == 0) {
-    uint32_t bytes = (uint32_t)((tab_bytes + 15) & ~15ll);
-    mbar_expect_tx(tabbar, bytes);
-    bulk_g2s(stab, P.tab16, bytes, tabbar);
-  }
-  if (lane == 0)
-    for (int st = 0; st < NS; ++st) {
-      int64_t tile = gw + (int64_t)st * GW;
-      if (tile < n_tiles) issue(tile, st);
-    }
-  K.cur = P.q_sample ? -1 : P.sample;
-  if (SINK == SINK_DIRECT) {
-    for (uint32_t h = tid; h < P.direct_cells; h += blockDim.x) sts32(K.a0 + h * 4, 0);
-    if (tid == 0) sts32(prop_addr, 0xFFFFFFFFu);
-  } else if (SINK == SINK_HASHED) {
-    const uint32_t slots = 1u << P.cache_log;
-    for (uint32_t h = tid; h < slots; h += blockDim.x) {
-      sts32(K.a0 + h * 4, CACHE_EMPTY);
-      sts32(K.a1 + h * 4, 0);
-    }
-  }
-  __syncthreads();
-  if (STAGED) mbar_wait(tabbar, 0);
-
-  TreeRef TR;
-  TR.parent = P.parent;
-  TR.par16 = (STAGED && P.par16_off >= 0) ? stab + (uint32_t)P.par16_off * 2u : 0u;
-  const uint32_t sn16 =
-      (STAGED && P.sn16_off >= 0) ? stab + (uint32_t)P.sn16_off * 2u : 0u;
-  const uint32_t flags = P.flags;
-  const int E = LEAN ? 1 : P.E;
-  const bool per_query = !LEAN && (P.q_sample || P.q_stratum);
-  const int V32 = (int)P.V;
-
-  for (int64_t round = 0; round < n_rounds; ++round) {
-    const int64_t tile = round * GW + gw;
-    if (tile < n_tiles) {
-      const int stage = (int)(round % NS);
-      mbar_wait(mybars + 8 * stage, (uint32_t)((round / NS) & 1));
-      const int64_t tb = tb0 + tile * WT;
-      const int64_t sbase = tb - SW_PRE;  // global index of staged slot 0
-      const uint32_t aq = wbase + (uint32_t)stage * stage_bytes;
-      const uint32_t as = aq + (uint32_t)L.tbuf * 4u;
-      const int nrel = (int)(n - sbase < L.tbuf ? n - sbase : L.tbuf);
-      if (lane == 0) {
-        // sentinels: record 0 of the column starts a query, the last record
-        // of the column ends one
-        if (sbase + SW_PRE == 0)
-          sts32(aq + SW_PRE * 4u - 4u, ~(uint32_t)lds32(aq + SW_PRE * 4u));
-        if (nrel < L.tbuf)
-          sts32(aq + (uint32_t)nrel * 4u, ~(uint32_t)lds32(aq + (uint32_t)nrel * 4u - 4u));
-      }
-      __syncwarp();
-      SwRun S;
-      S.w0 = SW_PRE + lane * R;
-      S.w1 = S.w0 + R;
-      if (r0 - sbase > S.w0) S.w0 = (int)(r0 - sbase < (1 << 30) ? r0 - sbase : (1 << 30));
-      if (r1 - sbase < S.w1) S.w1 = (int)(r1 - sbase);
-      if (S.w1 > nrel) S.w1 = nrel;
-
-      sweep_assign_any<STAGED, true>(P, TR, aq, as, em, stab, sn16, 0,
-                                     P.kind[0], flags, V32, S);
-      __syncwarp();
-      sweep_emit<SINK, LEAN>(P, K, aq, em, prop_addr, sbase, 0, S);
-      if (!LEAN)
-        for (int e = 1; e < E; ++e) {
-          __syncwarp();
-          sweep_assign_any<STAGED, false>(P, TR, aq, as, em, stab, sn16, e,
-                                          P.kind[e], flags, V32, S);
-          __syncwarp();
-          sweep_emit<SINK, LEAN>(P, K, aq, em, prop_addr, sbase, e, S);
-        }
-      // queries longer than SW_LONGK: the whole warp, from global memory
-      unsigned lm = __ballot_sync(FULL, S.longa >= 0);
-      while (lm) {
-        const int src = __ffs(lm) - 1;
-        lm &= lm - 1;
-        const int la = __shfl_sync(FULL, S.longa, src);
-        process_long<STAGED, SINK>(P, K, stab, n, sbase + la, lane);
-      }
-      __syncwarp();  // every lane is done with this stage
-      if (lane == 0) {
-        const int64_t nt = tile + (int64_t)NS * GW;
-        if (nt < n_tiles) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          issue(nt, stage);
-        }
-      }
-    }
-    if (SINK == SINK_DIRECT && per_query &&
-        ((round % SW_EPOCH) == SW_EPOCH - 1)) {
-      // the stream moved on to another sample: flush and re-target the table
-      __syncthreads();
-      const int prop = lds32(prop_addr);
-      __syncthreads();
-      if (prop >= 0 && prop != K.cur) {
-        direct_flush(P, K, tid, blockDim.x);
-        if (tid == 0) sts32(prop_addr, 0xFFFFFFFFu);
-        K.cur = prop;
-        __syncthreads();
-      }
-    }
-  }
-
-  // write the CTA's partial counts back (util.sum_dict, util.py:78-94)
-  if (SINK != SINK_GLOBAL) {
-    __syncthreads();
-    if (SINK == SINK_DIRECT) {
-      direct_flush(P, K, tid, blockDim.x);
-    } else {
-      const uint32_t slots = 1u << P.cache_log;
-      for (uint32_t h = tid; h < slots; h += blockDim.x) {
-        uint32_t tag = (uint32_t)lds32(K.a0 + h * 4);
-        uint32_t v = (uint32_t)lds32(K.a1 + h * 4);
-        if (tag != CACHE_EMPTY && v) atomicAdd(&P.cnt[tag], (ull)v);
-      }
-    }
-  }
-}
-
-}  // namespace wk
-
-// =============================================================================
-// classify_fast_kernel — the same two sweeps, hand-trimmed for the plans the
-// benchmarks and most real runs use: ONE entry (a rank, or --rank none through
-// a table), scalar sample, no strata, no read map, tables staged as uint16,
-// counts in the private direct table.  Everything else takes the generic
-// kernels above.  Scratch word here: code (18 bits) | denominator << 24 | head.
+// Scratch word of a record: code (18 bits) | denominator << 24 | head flag.
 //   code 0..0xFFFE value, 0xFFFF none, FX_UNAS 'Unassigned', FX_DUP repeat
-// =============================================================================
-namespace wk {
-
 constexpr uint32_t FX_NONE = 0xFFFFu;
 constexpr uint32_t FX_UNAS = 0x10000u;
 constexpr uint32_t FX_DUP = 0x20000u;
 constexpr uint32_t FX_CODE = 0x3FFFFu;
-
-__device__ __noinline__ uint32_t fx_lca_fold(uint32_t par16,
-                                             const int32_t *parent, uint32_t em,
-                                             uint32_t ao, uint32_t xo, int root) {
-  TreeRef TR;
-  TR.parent = parent;
-  TR.par16 = par16;
-  int acc = lds32(em + ao) & 0xFFFF;
-#pragma unroll 1
-  for (uint32_t j = ao + 4; j <= xo; j += 4) {
-    const uint32_t wj = (uint32_t)lds32(em + j);
-    if (!(wj & FX_DUP)) acc = lca2(TR, acc, (int)(wj & 0xFFFFu));
-  }
-  return acc == root ? FX_NONE : (uint32_t)acc;
-}
 
 __device__ __noinline__ uint32_t fx_majority(uint32_t em, uint32_t ao,
                                              uint32_t xo, int k, double th) {
@@ -640,8 +165,7 @@ __global__ void __launch_bounds__(SW_NT, 1)
   constexpr uint32_t ECOL = 2u * SCOL;            // scratch column
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int NW = blockDim.x >> 5;
-  const SwSmemLayout L = sw_layout(NW, R, 1, SINK_DIRECT, 0, 2u * P.direct_cells,
-                                   (int64_t)P.stage_elems * 2);
+  const SwSmemLayout L = sw_layout(NW, R, 2u * P.direct_cells, (int64_t)P.stage_elems * 2);
   const uint32_t sbase32 = smem_u32(smem);
   const uint32_t tabbar = sbase32 + L.bars + (uint32_t)NW * 8u;
   const uint32_t mybar = sbase32 + L.bars + (uint32_t)warp * 8u;
@@ -691,6 +215,9 @@ __global__ void __launch_bounds__(SW_NT, 1)
   const uint32_t unas_code = (P.flags & WK_F_UNASSIGNED) ? FX_UNAS : FX_NONE;
   const uint32_t tblhi = tbl + P.direct_cells * 4u;  // carries out of the low words
   const uint32_t badflag = tabbar + 8u;
+  TreeRef TR;
+  TR.parent = P.parent;
+  TR.par16 = P.par16_off >= 0 ? stab + (uint32_t)P.par16_off * 2u : 0u;
 
   uint32_t phase = 0;
 #pragma unroll 1
@@ -739,6 +266,8 @@ __global__ void __launch_bounds__(SW_NT, 1)
         first = x;
         uint32_t a = x, sig = 0, t0 = 0, neq = 0;
         uint32_t nvalid = 0, k = 0;
+        uint32_t acc = 0;  // --above: running LCA; --major: vote candidate
+        int votes = 0;
 #pragma unroll 1
         for (;;) {
           const uint32_t sv = (uint32_t)lds32(x + SCOL);
@@ -765,6 +294,22 @@ __global__ void __launch_bounds__(SW_NT, 1)
             neq |= code ^ t0;
             nvalid += (code != FX_NONE);
             ++k;
+            if (KIND == WK_KIND_RANK && MODE == FX_ABOVE) {
+              // tree.find_lca (tree.py:513-566), folded as the records pass
+              if (ishead)
+                acc = code;
+              else if (code != acc && code != FX_NONE && acc != FX_NONE)
+                acc = (uint32_t)lca2(TR, (int)acc, (int)code);
+            }
+            if (KIND == WK_KIND_RANK && MODE == FX_MAJOR) {
+              // Boyer-Moore vote: the only value that can reach a share > 1/2
+              if (ishead || votes == 0) {
+                acc = code;
+                votes = 1;
+              } else {
+                votes += code == acc ? 1 : -1;
+              }
+            }
           } else {
             code = FX_DUP;
           }
@@ -780,14 +325,21 @@ __global__ void __launch_bounds__(SW_NT, 1)
               } else if (MODE == FX_UNIQ) {
                 if (neq) r = FX_NONE;
               } else if (MODE == FX_MAJOR) {
-                if (neq) r = fx_majority(ECOL, a, x - 4u, (int)k, P.major_th);
+                // classify.majority (classify.py:300-317)
+                if (neq) {
+                  if (P.major_th > 0.5) {
+                    int c = 0;  // occurrences of the candidate
+#pragma unroll 1
+                    for (uint32_t j = a; j < x; j += 4u)
+                      c += ((uint32_t)lds32(j + ECOL) & FX_CODE) == acc;
+                    r = ((double)c >= __dmul_rn((double)k, P.major_th)) ? acc : FX_NONE;
+                  } else {
+                    r = fx_majority(ECOL, a, x - 4u, (int)k, P.major_th);
+                  }
+                }
               } else {
-                if (neq)
-                  r = nvalid != k ? FX_NONE
-                                  : fx_lca_fold(P.par16_off >= 0
-                                                    ? stab + (uint32_t)P.par16_off * 2u
-                                                    : 0u,
-                                                P.parent, ECOL, a, x - 4u, P.root);
+                // --above: None if any subject has no taxon, else the LCA
+                if (neq) r = (nvalid != k || acc == (uint32_t)P.root) ? FX_NONE : acc;
               }
             } else {
               // classify.assign_none (classify.py:32-51)
