@@ -458,9 +458,9 @@ def run_ours(args):
                          'peak': hbm_peak, 'unit': 'GB/s',
                          'frac': achieved / hbm_peak,
                          'traffic': measured_traffic(
-                             'classify_kernel:' + ','.join(entries) + ':' +
-                             args.mode, n),
-                         'kernel': 'classify_kernel',
+                             eng.last_kernel() + ':' + ','.join(entries) +
+                             ':' + args.mode, n),
+                         'kernel': eng.last_kernel(),
                          'kernel_ms': k_ms, 'peak_source': peak_src,
                          'algorithmic_bytes_per_record': bytes_per_rec},
             'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,

@@ -83,8 +83,12 @@ int wk_set_stream(wk_ctx *ctx, void *cuda_stream);
 int wk_sync(wk_ctx *ctx);
 /* Number of kernels this context has launched so far. */
 int64_t wk_launch_count(wk_ctx *ctx);
-/* Persistent-grid tuning (0 = default): CTAs, threads per CTA. */
+/* Persistent-grid tuning (0 = default): CTAs; threads per CTA of the
+ * run-per-lane kernel (block == 1 forces the window kernel); count sink
+ * (0 = automatic, > 0 = hashed cache with that many slots, -1 = global). */
 int wk_set_tuning(wk_ctx *ctx, int grid, int block, int cache_slots);
+/* Name of the classify kernel the last chunk was launched with. */
+const char *wk_last_kernel(wk_ctx *ctx);
 
 /* Pinned host memory for chunk producers (H2D at full PCIe rate). */
 int wk_host_alloc(void **out, int64_t bytes);

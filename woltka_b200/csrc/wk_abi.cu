@@ -134,6 +134,7 @@ struct wk_ctx {
   cudaEvent_t ev_free = nullptr;
   int64_t launches = 0;
   int tune_grid = 0, tune_cache = 0, tune_block = 0;
+  const char *last_kernel = "";
   // tree
   DevBuf parent;
   int32_t T = 0, root = -1;
@@ -331,6 +332,7 @@ int wk_sync(wk_ctx *c) {
 }
 
 int64_t wk_launch_count(wk_ctx *c) { return c ? c->launches : 0; }
+const char *wk_last_kernel(wk_ctx *c) { return c ? c->last_kernel : ""; }
 
 int wk_set_tuning(wk_ctx *c, int grid, int block, int cache_slots) {
   if (!c) return fail(WK_ERR_ARG, "ctx is NULL");
@@ -837,6 +839,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
       }
 #undef WK_FAST2
 #undef WK_FAST3
+      c->last_kernel = "classify_fast_kernel";
       c->launches++;
       CK(cudaGetLastError());
       return WK_OK;
@@ -901,6 +904,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
     else WK_LAUNCH(false, SINK_GLOBAL);
   }
 #undef WK_LAUNCH
+  c->last_kernel = "classify_kernel";
   c->launches++;
   CK(cudaGetLastError());
   return WK_OK;

@@ -110,6 +110,9 @@ class Engine:
     def launch_count(self):
         return int(self.lib.wk_launch_count(self.ctx))
 
+    def last_kernel(self):
+        return self.lib.wk_last_kernel(self.ctx).decode()
+
     def set_tuning(self, grid=0, block=0, cache_slots=0):
         _lib.check(self.lib.wk_set_tuning(self.ctx, grid, block, cache_slots))
 
