@@ -168,8 +168,9 @@ struct wk_ctx {
   DevBuf dq, ds, dqsamp, dqstrat, scratch;
   DevBuf dcontig, dbeg, dend, dlen;
   // ordinal
-  DevBuf cinfo, genes, gene_subject;  // genes buffer = [genes | bin_first]
-  size_t bins_offset = 0, hot_bytes = 0;
+  DevBuf cinfo, genes;  // genes buffer = [genes | bin_first | gene_subject]
+  size_t bins_offset = 0, subj_offset = 0, hot_bytes = 0;
+  size_t l2_persist_max = 0;
   size_t l2_window_max = 0;
   int32_t C = 0;
   int64_t G = 0;
@@ -240,6 +241,7 @@ int wk_create(int device, wk_ctx **out) {
     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize,
                        (size_t)prop.persistingL2CacheMaxSize);
     c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    c->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
   }
   CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -305,7 +307,7 @@ int wk_destroy(wk_ctx *c) {
                     &c->ovf_key, &c->ovf_den, &c->small, &c->sh_keys,
                     &c->sh_vals, &c->dq, &c->ds, &c->dqsamp, &c->dqstrat,
                     &c->scratch, &c->dcontig, &c->dbeg, &c->dend, &c->dlen,
-                    &c->cinfo, &c->genes, &c->gene_subject, &c->pair_q, &c->pair_s, &c->pair_r,
+                    &c->cinfo, &c->genes, &c->pair_q, &c->pair_s, &c->pair_r,
                     &c->pair_g, &c->tile_desc, &c->ticket, &c->assign};
   for (DevBuf *b : bufs) b->release();
   for (int i = 0; i < 2; ++i)
@@ -1080,14 +1082,14 @@ int wk_ordinal_set_genes(wk_ctx *c, const int64_t *contig_off,
   CK(cudaStreamSynchronize(c->stream));
   // one allocation [genes | bin_first]: the randomly accessed, L2-resident set
   c->bins_offset = (genes.size() * 8 + 255) & ~(size_t)255;
-  c->hot_bytes = c->bins_offset + bin_first.size() * 4;
+  c->subj_offset = (c->bins_offset + bin_first.size() * 4 + 255) & ~(size_t)255;
+  c->hot_bytes = c->subj_offset + (size_t)std::max<int64_t>(n_genes, 1) * 4;
   TRY(c->cinfo.reserve(cinfo.size() * 16));
   TRY(c->genes.reserve(c->hot_bytes));
-  TRY(c->gene_subject.reserve((size_t)std::max<int64_t>(n_genes, 1) * 4));
   CK(cudaMemcpy(c->cinfo.p, cinfo.data(), cinfo.size() * 16, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->genes.p, genes.data(), (size_t)n_genes * 8, cudaMemcpyHostToDevice));
   if (n_genes)
-    CK(cudaMemcpy(c->gene_subject.p, gene_subject, (size_t)n_genes * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy((char *)c->genes.p + c->subj_offset, gene_subject, (size_t)n_genes * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy((char *)c->genes.p + c->bins_offset, bin_first.data(),
                 (size_t)nbins * 4, cudaMemcpyHostToDevice));
   c->C = n_contigs;
@@ -1127,7 +1129,8 @@ static int run_ordinal(wk_ctx *c, const int32_t *dq, const int32_t *dcontig,
     P.th = th;
     P.cinfo = c->cinfo.as<int4>();
     P.genes = c->genes.as<int2>();
-    P.gene_subject = c->gene_subject.as<int32_t>();
+    P.gene_subject = reinterpret_cast<const int32_t *>(
+        (const char *)c->genes.p + c->subj_offset);
     P.bin_first = reinterpret_cast<const int32_t *>(
         (const char *)c->genes.p + c->bins_offset);
     P.shift = c->shift;
@@ -1147,12 +1150,16 @@ static int run_ordinal(wk_ctx *c, const int32_t *dq, const int32_t *dcontig,
       cfg.stream = c->stream;
       cudaLaunchAttribute attr[1];
       int nattr = 0;
-      if (c->l2_window_max && c->hot_bytes) {
+      if (c->l2_window_max && c->hot_bytes && !getenv("WK_ORD_NOWIN")) {
         attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
         attr[0].val.accessPolicyWindow.base_ptr = c->genes.p;
         attr[0].val.accessPolicyWindow.num_bytes =
             std::min(c->hot_bytes, c->l2_window_max);
-        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+        // a window larger than the persisting carve-out would thrash it
+        attr[0].val.accessPolicyWindow.hitRatio =
+            c->l2_persist_max && c->hot_bytes > c->l2_persist_max
+                ? (float)((double)c->l2_persist_max / (double)c->hot_bytes)
+                : 1.0f;
         attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         nattr = 1;

@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(ORD_NT, 2)
 
   int64_t off = s_base + s_warp[warp] + (incl - tot);
   auto put = [&](int64_t ri, int qq, int g) {
-    P.pair_q[off] = qq;
-    P.pair_s[off] = __ldg(P.gene_subject + g);
+    __stcs(P.pair_q + off, qq);
+    __stcs(P.pair_s + off, __ldg(P.gene_subject + g));
     if (P.pair_r) {
       P.pair_r[off] = (int32_t)ri;
       P.pair_g[off] = g;
