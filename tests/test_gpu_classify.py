@@ -242,3 +242,63 @@ def test_lca_on_a_tree_that_is_not_level_ordered(engine):
                              sub_node=sub_node, sub_feat=sub_node, kinds=kinds,
                              target_rank=[0, 0], flags=F_ABOVE, n_features=T)
     assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize('mode', ['default', 'above', 'major+unassigned'])
+@pytest.mark.parametrize('entries', [['genus'], ['phylum', 'genus', 'species'],
+                                     ['none']])
+def test_contiguous_samples_take_the_run_per_lane_kernel(engine, small_case,
+                                                         entries, mode):
+    """Samples that follow one another in the stream (one file per sample):
+    the run-per-lane kernel works segment by segment; a dropped sample (-1)
+    in the middle and long queries are part of the stream."""
+    q, s = cases.random_hits(small_case, 60000, seed=77, long_every=5000,
+                             long_len=90)
+    nq = int(q.max()) + 1
+    rng = np.random.default_rng(8)
+    q_sample = np.sort(rng.integers(0, 6, nq)).astype(np.int32)
+    q_sample[q_sample == 3] = -1          # a dropped sample in the middle
+    fl = cases.MODES[mode]
+    ref = cases.run_oracle(small_case, entries, fl, 0.7, q, s, n_samples=6,
+                           q_sample=q_sample)
+    for chunks in (1, 4):
+        _same(cases.run_engine(engine, small_case, entries, fl, 0.7, q, s,
+                               n_samples=6, q_sample=q_sample, chunks=chunks),
+              ref)
+    assert engine.last_kernel() == 'classify_fast_kernel'
+
+
+def test_which_kernel_runs(engine, small_case):
+    """One-kind plans with staged tables take classify_fast_kernel; strata,
+    mixed kinds and read maps take classify_kernel."""
+    q, s = cases.random_hits(small_case, 5000, seed=1)
+    cases.run_engine(engine, small_case, ['genus'], 0, 0, q, s)
+    assert engine.last_kernel() == 'classify_fast_kernel'
+    cases.run_engine(engine, small_case, ['phylum', 'genus'], 0, 0, q, s)
+    assert engine.last_kernel() == 'classify_fast_kernel'
+    cases.run_engine(engine, small_case, ['none', 'free'], 0, 0, q, s)
+    assert engine.last_kernel() == 'classify_kernel'
+    nq = int(q.max()) + 1
+    strat = np.zeros(nq, dtype=np.int32)
+    cases.run_engine(engine, small_case, ['genus'], 0, 0, q, s,
+                     q_stratum=strat, q_sample=np.zeros(nq, dtype=np.int32))
+    assert engine.last_kernel() == 'classify_kernel'
+    engine.set_tuning(0, 1, 0)
+    try:
+        a = cases.run_engine(engine, small_case, ['genus'], 0, 0, q, s)
+        assert engine.last_kernel() == 'classify_kernel'
+    finally:
+        engine.set_tuning(0, 0, 0)
+    _same(a, cases.run_engine(engine, small_case, ['genus'], 0, 0, q, s))
+
+
+def test_run_per_lane_kernel_at_1e6(engine, big_case):
+    # one-entry plans on the 21,603-node taxonomy, every mode, both kinds
+    qi, si, _, nq = synth.gen_hits(1_000_000, seed=1002)
+    q, s = qi.numpy(), si.numpy()
+    for ent in (['genus'], ['species'], ['none']):
+        for mode in ('default', 'uniq', 'major', 'above', 'uniq+unassigned'):
+            fl = cases.MODES[mode]
+            _same(cases.run_engine(engine, big_case, ent, fl, 0.8, q, s),
+                  cases.run_oracle(big_case, ent, fl, 0.8, q, s, n_threads=4))
+            assert engine.last_kernel() == 'classify_fast_kernel'

@@ -175,7 +175,7 @@ struct wk_ctx {
   int32_t C = 0;
   int64_t G = 0;
   int shift = 0;
-  DevBuf pair_q, pair_s, pair_r, pair_g, tile_desc, ticket;
+  DevBuf pair_q, pair_s, pair_r, pair_g, tile_desc, ticket, seglist;
   int64_t pair_cap = 0;
   int64_t last_pairs = 0;
   bool keep_pairs = false;
@@ -270,24 +270,42 @@ int wk_create(int device, wk_ctx **out) {
         (const void *)classify_kernel<false, SINK_HASHED, false>,
         (const void *)classify_kernel<false, SINK_GLOBAL, false>};
     const void *fast[] = {
-        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_FRAC, 5>,
-        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_UNIQ, 5>,
-        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_MAJOR, 5>,
-        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_ABOVE, 5>,
-        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_FRAC, 5>,
-        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_UNIQ, 5>,
-        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_FRAC, 9>,
-        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_UNIQ, 9>,
-        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_MAJOR, 9>,
-        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_ABOVE, 9>,
-        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_FRAC, 9>,
-        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_UNIQ, 9>,
-        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_FRAC, 13>,
-        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_UNIQ, 13>,
-        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_MAJOR, 13>,
-        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_ABOVE, 13>,
-        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_FRAC, 13>,
-        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_UNIQ, 13>};
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_FRAC, 5, false>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_FRAC, 5, true>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_UNIQ, 5, false>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_UNIQ, 5, true>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_MAJOR, 5, false>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_MAJOR, 5, true>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_ABOVE, 5, false>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_ABOVE, 5, true>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_FRAC, 5, false>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_FRAC, 5, true>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_UNIQ, 5, false>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_UNIQ, 5, true>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_FRAC, 9, false>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_FRAC, 9, true>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_UNIQ, 9, false>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_UNIQ, 9, true>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_MAJOR, 9, false>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_MAJOR, 9, true>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_ABOVE, 9, false>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_ABOVE, 9, true>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_FRAC, 9, false>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_FRAC, 9, true>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_UNIQ, 9, false>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_UNIQ, 9, true>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_FRAC, 13, false>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_FRAC, 13, true>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_UNIQ, 13, false>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_UNIQ, 13, true>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_MAJOR, 13, false>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_MAJOR, 13, true>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_ABOVE, 13, false>,
+        (const void *)classify_fast_kernel<WK_KIND_RANK, FX_ABOVE, 13, true>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_FRAC, 13, false>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_FRAC, 13, true>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_UNIQ, 13, false>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_UNIQ, 13, true>};
     for (const void *fn : fast)
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)c->smem_optin));
@@ -308,7 +326,7 @@ int wk_destroy(wk_ctx *c) {
                     &c->sh_vals, &c->dq, &c->ds, &c->dqsamp, &c->dqstrat,
                     &c->scratch, &c->dcontig, &c->dbeg, &c->dend, &c->dlen,
                     &c->cinfo, &c->genes, &c->pair_q, &c->pair_s, &c->pair_r,
-                    &c->pair_g, &c->tile_desc, &c->ticket, &c->assign};
+                    &c->pair_g, &c->tile_desc, &c->ticket, &c->assign, &c->seglist};
   for (DevBuf *b : bufs) b->release();
   for (int i = 0; i < 2; ++i)
     if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
@@ -721,6 +739,7 @@ static uint32_t plan_direct_ranges(wk_ctx *c, ClsParams &P) {
     cells += (uint64_t)(hi - lo + 1) + 1;
     if (cells >= (1u << 24)) return 0xFFFFFFFFu;
   }
+  P.dir_base[c->E] = (int32_t)cells;
   return (uint32_t)cells;
 }
 
@@ -751,6 +770,9 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   if (dqstrat) c->strata_keys = true;
   P.sample = sample;
   P.E = c->E;
+  P.e_lo = 0;
+  P.e_hi = c->E;
+  P.T = c->T;
   for (int e = 0; e < c->E; ++e) P.kind[e] = c->kind[e];
   P.flags = c->flags;
   P.major_th = c->major_th;
@@ -792,61 +814,111 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   int grid = c->tune_grid > 0 ? c->tune_grid : c->sm_count;
 
   const uint32_t dir_cells = plan_direct_ranges(c, P);
-  // ---- the run-per-lane kernel for one-entry plans (wk_sweep.cuh) ----------
+  // ---- the run-per-lane kernel (wk_sweep.cuh): entries of one kind (ranks, or
+  // --rank none through a table), staged tables, no strata, no read map; a
+  // per-query sample column is accepted when the samples are contiguous.
   // tune_block: 1 = always the window kernel; otherwise threads per CTA
-  if (c->tune_block != 1 && lean && staged && !dqstrat && c->tune_cache == 0 &&
-      dir_cells != 0xFFFFFFFFu && !n_dev && !P.assign &&
-      (c->kind[0] == WK_KIND_RANK || c->kind[0] == WK_KIND_NONE)) {
-    const int64_t tbytes = (int64_t)c->stage_elems * 2;
+  bool same_kind = c->kind[0] == WK_KIND_RANK || c->kind[0] == WK_KIND_NONE;
+  for (int e = 1; e < c->E; ++e) same_kind &= c->kind[e] == c->kind[0];
+  P.seg_list = nullptr;
+  P.skip_flag = nullptr;
+  if (c->tune_block != 1 && same_kind && staged && !dqstrat && c->tune_cache == 0 &&
+      dir_cells != 0xFFFFFFFFu && !n_dev && !P.assign && !getenv("WK_NO_FAST")) {
     int NT = c->tune_block;
     if (NT < 64 || NT > SW_NT) NT = SW_NT;
     NT &= ~31;
     const int NW = NT / 32;
     int rmax = 13;
     if (const char *ev = getenv("WK_SWEEP_R")) rmax = atoi(ev);
-    int FR = 0;
-    for (int r : {13, 9, 5})
-      if (r <= rmax &&
-          sw_layout(NW, r, 2 * dir_cells, tbytes).total <= c->smem_optin) {
-        FR = r;
-        break;
-      }
     const bool rk = c->kind[0] == WK_KIND_RANK;
     const int mode = (rk && (c->flags & WK_F_MAJOR))   ? FX_MAJOR
                      : (rk && (c->flags & WK_F_ABOVE)) ? FX_ABOVE
                      : (c->flags & WK_F_UNIQ)          ? FX_UNIQ
                                                        : FX_FRAC;
+    const int64_t par_bytes = mode == FX_ABOVE ? (((int64_t)c->T + 7) & ~7ll) * 2 : 0;
+    const bool par_ok = mode != FX_ABOVE || (c->par16_off >= 0 && (c->par16_off & 7) == 0);
+    // all entries in one launch when that leaves room for runs of 13 (or the
+    // plan is one entry); otherwise one launch per entry
+    auto pick = [&](int e0, int en) {
+      const uint32_t cells = (uint32_t)(P.dir_base[e0 + en] - P.dir_base[e0]);
+      const int64_t tb = (int64_t)en * c->Vp * 2 + par_bytes;
+      for (int r : {13, 9, 5})
+        if (r <= rmax && sw_layout(NW, r, cells, tb).total <= c->smem_optin) return r;
+      return 0;
+    };
+    int group = c->E;
+    int FR = par_ok ? pick(0, c->E) : 0;
+    if (par_ok && c->E > 1 && FR < 13) {
+      int worst = 13;
+      for (int e = 0; e < c->E; ++e) worst = std::min(worst, pick(e, 1));
+      if (worst > FR) {
+        group = 1;
+        FR = worst;
+      }
+    }
     const int64_t span = r1 - (r0 & ~3ll);
-    if (FR && span > 0) {
+    if (span <= 0) return WK_OK;
+    if (FR) {
+      const bool multi = !lean;
+      if (dqsamp) {
+        // where the sample of the stream changes (device side, no host sync)
+        TRY(c->seglist.reserve(sizeof(SegList)));
+        SegList *sl = c->seglist.as<SegList>();
+        CK(cudaMemsetAsync(sl, 0, 8, c->stream));
+        const int sgrid = (int)std::min<int64_t>((r1 - r0 + 255) / 256, (int64_t)c->sm_count * 16);
+        seg_scan_kernel<<<sgrid, 256, 0, c->stream>>>(dq, dqsamp, r0, r1, sl);
+        seg_sort_kernel<<<1, 256, 0, c->stream>>>(dq, dqsamp, r0, r1, sl);
+        c->launches += 2;
+        P.seg_list = sl;
+      }
       P.direct_cells = dir_cells;
-      const SwSmemLayout FL = sw_layout(NW, FR, 2 * dir_cells, tbytes);
-      const int64_t ft = (span + 32ll * FR - 1) / (32ll * FR);
-      const int fgrid = (int)std::min<int64_t>(grid, (ft + NW - 1) / NW);
-#define WK_FAST3(KD, MD, RR) \
-  classify_fast_kernel<KD, MD, RR><<<fgrid, NT, FL.total, c->stream>>>(P)
+      for (int e0 = 0; e0 < c->E; e0 += group) {
+        P.e_lo = e0;
+        P.e_hi = e0 + group;
+        const int R1 = pick(e0, group);
+        const SwSmemLayout FL =
+            sw_layout(NW, R1, (uint32_t)(P.dir_base[e0 + group] - P.dir_base[e0]),
+                      (int64_t)group * c->Vp * 2 + par_bytes);
+        const int64_t ft = (span + 32ll * R1 - 1) / (32ll * R1);
+        const int fgrid = (int)std::min<int64_t>(grid, (ft + NW - 1) / NW);
+#define WK_FAST4(KD, MD, RR, MU) \
+  classify_fast_kernel<KD, MD, RR, MU><<<fgrid, NT, FL.total, c->stream>>>(P)
+#define WK_FAST3(KD, MD, RR)               \
+  do {                                     \
+    if (multi) WK_FAST4(KD, MD, RR, true); \
+    else WK_FAST4(KD, MD, RR, false);      \
+  } while (0)
 #define WK_FAST2(KD, MD)                   \
   do {                                     \
-    if (FR == 13) WK_FAST3(KD, MD, 13);    \
-    else if (FR == 9) WK_FAST3(KD, MD, 9); \
+    if (R1 == 13) WK_FAST3(KD, MD, 13);    \
+    else if (R1 == 9) WK_FAST3(KD, MD, 9); \
     else WK_FAST3(KD, MD, 5);              \
   } while (0)
-      if (rk) {
-        if (mode == FX_MAJOR) WK_FAST2(WK_KIND_RANK, FX_MAJOR);
-        else if (mode == FX_ABOVE) WK_FAST2(WK_KIND_RANK, FX_ABOVE);
-        else if (mode == FX_UNIQ) WK_FAST2(WK_KIND_RANK, FX_UNIQ);
-        else WK_FAST2(WK_KIND_RANK, FX_FRAC);
-      } else {
-        if (mode == FX_UNIQ) WK_FAST2(WK_KIND_NONE, FX_UNIQ);
-        else WK_FAST2(WK_KIND_NONE, FX_FRAC);
-      }
+        if (rk) {
+          if (mode == FX_MAJOR) WK_FAST2(WK_KIND_RANK, FX_MAJOR);
+          else if (mode == FX_ABOVE) WK_FAST2(WK_KIND_RANK, FX_ABOVE);
+          else if (mode == FX_UNIQ) WK_FAST2(WK_KIND_RANK, FX_UNIQ);
+          else WK_FAST2(WK_KIND_RANK, FX_FRAC);
+        } else {
+          if (mode == FX_UNIQ) WK_FAST2(WK_KIND_NONE, FX_UNIQ);
+          else WK_FAST2(WK_KIND_NONE, FX_FRAC);
+        }
 #undef WK_FAST2
 #undef WK_FAST3
+#undef WK_FAST4
+        c->launches++;
+        CK(cudaGetLastError());
+      }
+      P.e_lo = 0;
+      P.e_hi = c->E;
       c->last_kernel = "classify_fast_kernel";
-      c->launches++;
-      CK(cudaGetLastError());
-      return WK_OK;
+      if (!dqsamp) return WK_OK;
+      // interleaved samples (more than FX_MAX_SEG changes): the kernel above
+      // returned at once and classify_kernel below does the chunk; otherwise
+      // classify_kernel returns at once
+      P.seg_list = nullptr;
+      P.skip_flag = &c->seglist.as<SegList>()->nseg;
     }
-    if (span <= 0) return WK_OK;
   }
 
   const int64_t tab_bytes = staged ? (int64_t)c->stage_elems * 2 : 0;
@@ -906,7 +978,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
     else WK_LAUNCH(false, SINK_GLOBAL);
   }
 #undef WK_LAUNCH
-  c->last_kernel = "classify_kernel";
+  if (!P.skip_flag) c->last_kernel = "classify_kernel";
   c->launches++;
   CK(cudaGetLastError());
   return WK_OK;

@@ -68,6 +68,7 @@ struct ClsParams {
   const uint16_t *tab16;      // [E][Vp] uint16 (0xFFFF = none) or null
   int64_t V;
   int32_t Vp;
+  int32_t T;                  // tree nodes
   const int32_t *sub_node;    // [V] or null
   const int32_t *parent;      // [T] or null
   int32_t sn16_off, par16_off; // uint16 copies inside the staged block (element
@@ -95,8 +96,10 @@ struct ClsParams {
   // SINK_DIRECT: entry e keeps features [dir_off, dir_off + dir_w) at slots
   // dir_base + (f - dir_off) and 'Unassigned' at slot dir_base + dir_w; any
   // other feature goes straight to the global table
-  int32_t dir_off[WK_MAX_ENTRIES], dir_w[WK_MAX_ENTRIES], dir_base[WK_MAX_ENTRIES];
-  int32_t sw_R, sw_S;         // classify_sweep_kernel: records per lane and tile, stages
+  int32_t dir_off[WK_MAX_ENTRIES], dir_w[WK_MAX_ENTRIES], dir_base[WK_MAX_ENTRIES + 1];
+  int32_t e_lo, e_hi;         // entries this launch works on (process_long, fast kernel)
+  const void *seg_list;       // classify_fast_kernel<MULTI>: SegList of the stream, or null
+  const int32_t *skip_flag;   // classify_kernel: do nothing if *skip_flag >= 0
 };
 
 enum { ERR_BAD_SUBJECT = 1, ERR_OVF_FULL = 2, ERR_HASH_FULL = 4,
@@ -441,7 +444,7 @@ __device__ __noinline__ int64_t process_long(const ClsParams &P, const Sink &K,
   const int64_t NF = P.NF1 - 1;
   const bool unas = P.flags & WK_F_UNASSIGNED;
 
-  for (int e = 0; e < P.E; ++e) {
+  for (int e = P.e_lo; e < P.e_hi; ++e) {
     const int kind = P.kind[e];
     int result = -1;
     bool uniqres = true;
@@ -615,6 +618,7 @@ __global__ void __launch_bounds__(CLS_NT, 1)
     r1 = n;
   }
   if (*P.err & ERR_PAIR_FULL) return;  // upstream stage overflowed: do nothing
+  if (P.skip_flag && *P.skip_flag >= 0) return;  // classify_fast_kernel took the chunk
   const int64_t tb0 = r0 & ~3ll;
   const int64_t n_tiles = r1 > tb0 ? (r1 - tb0 + CLS_TILE - 1) / CLS_TILE : 0;
 
