@@ -824,10 +824,9 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   P.skip_flag = nullptr;
   if (c->tune_block != 1 && same_kind && staged && !dqstrat && c->tune_cache == 0 &&
       dir_cells != 0xFFFFFFFFu && !n_dev && !P.assign && !getenv("WK_NO_FAST")) {
-    int NT = c->tune_block;
-    if (NT < 64 || NT > SW_NT) NT = SW_NT;
-    NT &= ~31;
-    const int NW = NT / 32;
+    int NTmax = c->tune_block;
+    if (NTmax < 64 || NTmax > SW_NT) NTmax = SW_NT;
+    NTmax &= ~31;
     int rmax = 13;
     if (const char *ev = getenv("WK_SWEEP_R")) rmax = atoi(ev);
     const bool rk = c->kind[0] == WK_KIND_RANK;
@@ -837,21 +836,31 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
                                                        : FX_FRAC;
     const int64_t par_bytes = mode == FX_ABOVE ? (((int64_t)c->T + 7) & ~7ll) * 2 : 0;
     const bool par_ok = mode != FX_ABOVE || (c->par16_off >= 0 && (c->par16_off & 7) == 0);
-    // all entries in one launch when that leaves room for runs of 13 (or the
-    // plan is one entry); otherwise one launch per entry
+    // (run length, warps) for entries [e0, e0+en): long runs first (fewer
+    // records walked twice at run ends), then as many warps as fit
+    struct Shape { int R, NW; };
     auto pick = [&](int e0, int en) {
       const uint32_t cells = (uint32_t)(P.dir_base[e0 + en] - P.dir_base[e0]);
       const int64_t tb = (int64_t)en * c->Vp * 2 + par_bytes;
-      for (int r : {13, 9, 5})
-        if (r <= rmax && sw_layout(NW, r, cells, tb).total <= c->smem_optin) return r;
-      return 0;
+      for (int r : {13, 9})
+        for (int nw : {32, 28, 24})
+          if (r <= rmax && nw * 32 <= NTmax &&
+              sw_layout(nw, r, cells, tb).total <= c->smem_optin)
+            return Shape{r, nw};
+      for (int nw : {32, 24, 16, 8})
+        if (5 <= rmax && nw * 32 <= NTmax &&
+            sw_layout(nw, 5, cells, tb).total <= c->smem_optin)
+          return Shape{5, nw};
+      return Shape{0, 0};
     };
+    // all entries in one launch when that leaves room for runs of 13 (or the
+    // plan is one entry); otherwise one launch per entry
     int group = c->E;
-    int FR = par_ok ? pick(0, c->E) : 0;
+    int FR = par_ok ? pick(0, c->E).R : 0;
     if (par_ok && c->E > 1 && FR < 13) {
       int worst = 13;
-      for (int e = 0; e < c->E; ++e) worst = std::min(worst, pick(e, 1));
-      if (worst > FR) {
+      for (int e = 0; e < c->E; ++e) worst = std::min(worst, pick(e, 1).R);
+      if (worst > FR || (worst == FR && FR > 0 && pick(0, c->E).NW < 32)) {
         group = 1;
         FR = worst;
       }
@@ -875,7 +884,8 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
       for (int e0 = 0; e0 < c->E; e0 += group) {
         P.e_lo = e0;
         P.e_hi = e0 + group;
-        const int R1 = pick(e0, group);
+        const Shape sh = pick(e0, group);
+        const int R1 = sh.R, NW = sh.NW, NT = sh.NW * 32;
         const SwSmemLayout FL =
             sw_layout(NW, R1, (uint32_t)(P.dir_base[e0 + group] - P.dir_base[e0]),
                       (int64_t)group * c->Vp * 2 + par_bytes);

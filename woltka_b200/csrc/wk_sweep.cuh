@@ -166,18 +166,32 @@ struct SegList {
 
 __global__ void seg_scan_kernel(const int32_t *q, const int32_t *q_sample,
                                 int64_t r0, int64_t r1, SegList *out) {
-  int64_t i = r0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t st = (int64_t)gridDim.x * blockDim.x;
-  for (; i < r1; i += st) {
-    if (i == r0) continue;
-    const int a = __ldg(q + i - 1), b = __ldg(q + i);
-    if (a == b) continue;
+  // four records per thread and step (128-bit loads once aligned)
+  const int64_t a0 = (r0 + 3) & ~3ll;
+  const int64_t st = (int64_t)gridDim.x * blockDim.x * 4;
+  auto check = [&](int64_t i, int a, int b) {
+    if (a == b) return;
     const int sa = __ldg(q_sample + a), sb = __ldg(q_sample + b);
-    if (sa == sb) continue;
+    if (sa == sb) return;
     const int at = atomicAdd(&out->n, 1);
     if (at < FX_MAX_SEG) {
       out->raw_at[at] = i;
       out->raw_sample[at] = sb;
+    }
+  };
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int64_t i = r0 + 1; i < a0 && i < r1; ++i) check(i, q[i - 1], q[i]);
+  for (int64_t i = a0 + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < r1;
+       i += st) {
+    if (i + 4 <= r1) {
+      const int4 v = __ldg(reinterpret_cast<const int4 *>(q + i));
+      if (i > r0) check(i, __ldg(q + i - 1), v.x);
+      check(i + 1, v.x, v.y);
+      check(i + 2, v.y, v.z);
+      check(i + 3, v.z, v.w);
+    } else {
+      for (int64_t j = i; j < r1; ++j)
+        if (j > r0) check(j, q[j - 1], q[j]);
     }
   }
 }
