@@ -302,3 +302,50 @@ def test_run_per_lane_kernel_at_1e6(engine, big_case):
             _same(cases.run_engine(engine, big_case, ent, fl, 0.8, q, s),
                   cases.run_oracle(big_case, ent, fl, 0.8, q, s, n_threads=4))
             assert engine.last_kernel() == 'classify_fast_kernel'
+
+
+def test_cfg5_shape_gene_to_ko_stratified_by_genus(engine):
+    """BASELINE.json configs[4] at test size: subjects are genes, the rank is
+    'ko' through a gene -> KO map read as a two-level tree (tree.read_map /
+    find_rank), counts are keyed by (genus stratum, KO) and split over samples
+    (classify.counter_strat, classify.py:216-249).  The gene table is too large
+    to stage as uint16 rows at full size; here V = 60,000 > 65,535 - so the
+    int32 table path of classify_kernel runs."""
+    from oracle import oracle as O
+    from woltka_b200._lib import KIND_RANK
+    rng = np.random.default_rng(1005)
+    n_genomes, genes_per, n_ko, n_genus, n_samples = 1200, 50, 900, 300, 8
+    V = n_genomes * genes_per
+    # nodes: 0 = root, 1..n_ko = KOs (rank 0), then one node per gene
+    T = 1 + n_ko + V
+    parent = np.zeros(T, dtype=np.int32)
+    node_rank = np.full(T, -1, dtype=np.int32)
+    node_rank[1:1 + n_ko] = 0
+    ko_of_gene = np.where(rng.random(V) < 0.6, rng.integers(1, n_ko + 1, V), 0)
+    parent[1 + n_ko:] = ko_of_gene          # unannotated genes hang off the root
+    sub_node = (1 + n_ko + np.arange(V)).astype(np.int32)
+    tab = np.where(ko_of_gene > 0, ko_of_gene, -1).astype(np.int32)[None, :]
+    # records: k hits per query on genes of neighbouring genomes
+    nq = 150_000
+    k = np.minimum(rng.geometric(0.48, nq), 16)
+    q = np.repeat(np.arange(nq, dtype=np.int32), k)
+    first = rng.integers(0, n_genomes, nq)
+    genome = (first[q] + rng.integers(0, 3, len(q))) % n_genomes
+    s = (genome * genes_per + rng.integers(0, genes_per, len(q))).astype(np.int32)
+    genus_of_genome = rng.integers(0, n_genus, n_genomes)
+    q_stratum = np.where(rng.random(nq) < 0.8, genus_of_genome[first], -1).astype(np.int32)
+    q_sample = (np.arange(nq) * n_samples // nq).astype(np.int32)
+    kinds = np.array([KIND_RANK], dtype=np.int32)
+    engine.set_tree(parent, 0)
+    engine.set_plan(kinds, 0, 0.0, n_samples, T)
+    engine.set_subjects(tab, sub_node)
+    engine.classify_chunk(q, s, q_sample, q_stratum, 0)
+    got = cases.collect(engine, n_samples, T)
+    exp = O.classify(q, s, parent=parent, node_rank=node_rank, root=0,
+                     sub_node=sub_node, sub_feat=sub_node, kinds=kinds,
+                     target_rank=[0], flags=0, n_samples=n_samples,
+                     n_features=T, q_sample=q_sample, q_stratum=q_stratum,
+                     n_threads=4)
+    _same(got, exp)
+    assert len(got[2]) > 10000          # (sample, genus, KO) cells
+    assert engine.last_kernel() == 'classify_kernel'
