@@ -196,6 +196,35 @@ int wk_reset_counts(wk_ctx *ctx);
 #define WK_ASSIGN_UNIQ (1 << 30)
 int wk_set_assign_output(wk_ctx *ctx, int enable);
 int wk_fetch_assignments(wk_ctx *ctx, int32_t *out, int64_t n_rec);
+/* ---- SAM text -> columns on the device: replaces
+ *      align.parse_sam_file (align.py:258-347), the chunk packing of
+ *      plain_mapper (align.py:47-115), workflow.demultiplex
+ *      (workflow.py:844-909) and the host-side interning ------------------ */
+/* Parse one chunk of SAM body text (header lines removed; the chunk ends at a
+ * line end and, unless it is the end of the file, where the QNAME changes).
+ * Lines with RNAME '*' are skipped; adjacent equal QNAMEs form a group whose
+ * mates (FLAG >> 6 & 3) become the queries name, name/1, name/2 in that
+ * order.  Subjects (and, with demux, the sample prefixes of the query names)
+ * are interned in device tables that persist over chunks: indices are dense,
+ * in order of first appearance per chunk batch; *n_subjects / *n_samples
+ * return the totals so far.  The columns stay on the device. */
+int wk_parse_sam(wk_ctx *ctx, const char *text, int64_t n_bytes, int demux,
+                 int64_t *n_rec, int64_t *n_qry, int32_t *n_subjects,
+                 int32_t *n_samples);
+/* Names with index in [from, to) of the subject (which = 0) or sample
+ * (which = 1) table: bytes concatenated into buf, lengths into lens. */
+int wk_parse_fetch_names(wk_ctx *ctx, int which, int32_t from, int32_t to,
+                         char *buf, int64_t cap, int64_t *used, int32_t *lens);
+/* Columns of the last parsed chunk (any pointer may be NULL): q[n_rec],
+ * s[n_rec], q_sample[n_qry] (demux only), q_line[n_qry] = index of the line
+ * carrying the query's name | mate << 30. */
+int wk_parse_fetch_columns(wk_ctx *ctx, int32_t *q, int32_t *s,
+                           int32_t *q_sample, uint32_t *q_line);
+/* Classify the last parsed chunk.  demux: sample_map[parsed sample index] =
+ * sample index of the plan or -1 (dropped); otherwise `sample`. */
+int wk_classify_parsed(wk_ctx *ctx, const int32_t *sample_map, int32_t n_map,
+                       int32_t sample);
+
 /* Device address / length (in int64 elements) of the units table, for a
  * caller-side NCCL reduce (torch.distributed) across GPUs. */
 int wk_counts_device(wk_ctx *ctx, void **d_ptr, int64_t *n_elems);

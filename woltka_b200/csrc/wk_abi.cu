@@ -16,6 +16,7 @@
 #include "wk_classify.cuh"
 #include "wk_ordinal.cuh"
 #include "wk_sweep.cuh"
+#include "wk_parse.cuh"
 
 using namespace wk;
 
@@ -181,6 +182,13 @@ struct wk_ctx {
   bool keep_pairs = false;
   bool strata_keys = false;  // overflow list holds stratified keys
   bool want_assign = false;
+  // SAM reader (wk_parse.cuh)
+  DevBuf p_text, p_a, p_b, p_sums, p_line_start, p_rec, p_valid, p_vpos, p_vline,
+      p_ghead, p_slot, p_phead, p_qpos, p_rslot, p_sslot, p_qline, p_tot;
+  DevBuf t_keys[2], t_ids[2], t_soff[2], t_slen[2], t_first[2], t_pool[2], t_meta[2];
+  bool p_tables = false;
+  int64_t p_nrec = 0, p_nqry = 0;
+  int p_demux = 0;
   DevBuf assign;
   int64_t assign_n = 0;  // records of the chunk the buffer belongs to
 
@@ -326,7 +334,14 @@ int wk_destroy(wk_ctx *c) {
                     &c->sh_vals, &c->dq, &c->ds, &c->dqsamp, &c->dqstrat,
                     &c->scratch, &c->dcontig, &c->dbeg, &c->dend, &c->dlen,
                     &c->cinfo, &c->genes, &c->pair_q, &c->pair_s, &c->pair_r,
-                    &c->pair_g, &c->tile_desc, &c->ticket, &c->assign, &c->seglist};
+                    &c->pair_g, &c->tile_desc, &c->ticket, &c->assign, &c->seglist,
+                    &c->p_text, &c->p_a, &c->p_b, &c->p_sums, &c->p_line_start,
+                    &c->p_rec, &c->p_valid, &c->p_vpos, &c->p_vline, &c->p_ghead,
+                    &c->p_slot, &c->p_phead, &c->p_qpos, &c->p_rslot, &c->p_sslot,
+                    &c->p_qline, &c->p_tot, &c->t_keys[0], &c->t_keys[1],
+                    &c->t_ids[0], &c->t_ids[1], &c->t_soff[0], &c->t_soff[1],
+                    &c->t_slen[0], &c->t_slen[1], &c->t_first[0], &c->t_first[1],
+                    &c->t_pool[0], &c->t_pool[1], &c->t_meta[0], &c->t_meta[1]};
   for (DevBuf *b : bufs) b->release();
   for (int i = 0; i < 2; ++i)
     if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
@@ -1462,6 +1477,290 @@ int wk_fetch_assignments(wk_ctx *c, int32_t *out, int64_t n_rec) {
                      cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return WK_OK;
+}
+
+// ---- SAM reader (wk_parse.cuh) ---------------------------------------------------
+}  // extern "C"
+
+static const uint64_t kInternCap[2] = {1ull << 21, 1ull << 16};     // subjects, samples
+static const uint64_t kInternPool[2] = {64ull << 20, 4ull << 20};
+
+static int parse_tables(wk_ctx *c) {
+  if (c->p_tables) return WK_OK;
+  for (int w = 0; w < 2; ++w) {
+    const uint64_t cap = kInternCap[w];
+    TRY(c->t_keys[w].reserve(cap * 8));
+    TRY(c->t_ids[w].reserve(cap * 4));
+    TRY(c->t_soff[w].reserve(cap * 4));
+    TRY(c->t_slen[w].reserve(cap * 4));
+    TRY(c->t_first[w].reserve(cap * 4));
+    TRY(c->t_pool[w].reserve(kInternPool[w]));
+    TRY(c->t_meta[w].reserve(16));
+    CK(cudaMemsetAsync(c->t_keys[w].p, 0xFF, cap * 8, c->stream));
+    CK(cudaMemsetAsync(c->t_ids[w].p, 0xFF, cap * 4, c->stream));
+    CK(cudaMemsetAsync(c->t_meta[w].p, 0, 16, c->stream));
+  }
+  c->p_tables = true;
+  return WK_OK;
+}
+static InternTable intern_table(wk_ctx *c, int w) {
+  InternTable T;
+  T.keys = c->t_keys[w].as<ull>();
+  T.ids = c->t_ids[w].as<int32_t>();
+  T.soff = c->t_soff[w].as<uint32_t>();
+  T.slen = c->t_slen[w].as<uint32_t>();
+  T.first = c->t_first[w].as<uint32_t>();
+  T.pool = c->t_pool[w].as<uint8_t>();
+  T.pool_used = c->t_meta[w].as<ull>();
+  T.count = reinterpret_cast<int32_t *>(c->t_meta[w].as<ull>() + 1);
+  T.cap_mask = kInternCap[w] - 1;
+  T.pool_cap = kInternPool[w];
+  return T;
+}
+// out = exclusive prefix sum of in[0, n); *total (host) = sum
+static int device_scan(wk_ctx *c, const int32_t *in, int64_t n, int32_t *out,
+                       int64_t *total) {
+  const int nb = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+  TRY(c->p_sums.reserve((size_t)std::max(nb, 1) * 4));
+  TRY(c->p_tot.reserve(8));
+  scan_sums_kernel<<<nb, SCAN_NT, 0, c->stream>>>(in, n, c->p_sums.as<int32_t>());
+  scan_tops_kernel<<<1, 1024, 0, c->stream>>>(c->p_sums.as<int32_t>(), nb,
+                                              c->p_tot.as<int64_t>());
+  scan_apply_kernel<<<nb, SCAN_NT, 0, c->stream>>>(in, n, c->p_sums.as<int32_t>(), out);
+  c->launches += 3;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(total, c->p_tot.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return WK_OK;
+}
+static int parse_error(wk_ctx *c) {
+  int32_t err = 0;
+  CK(cudaMemcpyAsync(&err, c->d_err(), 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (!err) return WK_OK;
+  CK(cudaMemsetAsync(c->d_err(), 0, 4, c->stream));
+  if (err & PERR_FIELDS)
+    return fail(WK_ERR_ARG, "a SAM line has fewer than four tab-separated fields");
+  if (err & PERR_FLAG) return fail(WK_ERR_ARG, "a SAM line has an invalid FLAG");
+  if (err & PERR_COLLISION)
+    return fail(WK_ERR_CAPACITY, "two identifiers share a 64-bit hash");
+  if (err & PERR_TABLE_FULL) return fail(WK_ERR_CAPACITY, "identifier table is full");
+  if (err & PERR_POOL_FULL) return fail(WK_ERR_CAPACITY, "identifier pool is full");
+  if (err & PERR_GROUP)
+    return fail(WK_ERR_CAPACITY, "more than 65536 adjacent lines share a query name");
+  return fail(WK_ERR_CUDA, "device error word %d", err);
+}
+
+extern "C" {
+
+int wk_parse_sam(wk_ctx *c, const char *text, int64_t n_bytes, int demux,
+                 int64_t *n_rec, int64_t *n_qry, int32_t *n_subjects,
+                 int32_t *n_samples) {
+  if (!c || !n_rec || !n_qry || !n_subjects || !n_samples)
+    return fail(WK_ERR_ARG, "bad arguments");
+  if (n_bytes < 0 || n_bytes >= (1ll << 31) || (n_bytes && !text))
+    return fail(WK_ERR_ARG, "a text chunk must be smaller than 2 GiB");
+  TRY(use_device(c));
+  TRY(parse_tables(c));
+  c->p_nrec = c->p_nqry = 0;
+  c->p_demux = demux;
+  *n_rec = *n_qry = 0;
+  InternTable TS = intern_table(c, 0), TP = intern_table(c, 1);
+  auto counts = [&]() {
+    CK(cudaMemcpyAsync(n_subjects, TS.count, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(n_samples, TP.count, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return (int)WK_OK;
+  };
+  if (n_bytes == 0) return counts();
+  const uint8_t *h = reinterpret_cast<const uint8_t *>(text);
+  TRY(c->p_text.reserve((size_t)n_bytes + 64));
+  CK(cudaMemcpyAsync(c->p_text.p, text, (size_t)n_bytes, cudaMemcpyHostToDevice, c->stream));
+  const uint8_t *dt = c->p_text.as<uint8_t>();
+  // 1 line starts
+  const int64_t n16 = (n_bytes + 15) / 16;
+  TRY(c->p_a.reserve((size_t)n16 * 4));
+  TRY(c->p_b.reserve((size_t)n16 * 4));
+  newline_flags_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, c->stream>>>(
+      dt, n_bytes, c->p_a.as<int32_t>());
+  c->launches++;
+  int64_t n_nl = 0;
+  TRY(device_scan(c, c->p_a.as<int32_t>(), n16, c->p_b.as<int32_t>(), &n_nl));
+  const int64_t n_lines = n_nl + (h[n_bytes - 1] != '\n' ? 1 : 0);
+  if (n_lines == 0) return counts();
+  TRY(c->p_line_start.reserve((size_t)(n_nl + 2) * 4));
+  line_starts_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, c->stream>>>(
+      dt, n_bytes, c->p_b.as<int32_t>(), c->p_line_start.as<uint32_t>());
+  // 2 fields, 3 compaction
+  TRY(c->p_rec.reserve((size_t)n_lines * sizeof(LineRec)));
+  TRY(c->p_valid.reserve((size_t)n_lines * 4));
+  TRY(c->p_vpos.reserve((size_t)n_lines * 4));
+  const unsigned gl = (unsigned)((n_lines + 255) / 256);
+  sam_fields_kernel<<<gl, 256, 0, c->stream>>>(dt, n_bytes, c->p_line_start.as<uint32_t>(),
+                                              n_lines, c->p_rec.as<LineRec>(),
+                                              c->p_valid.as<int32_t>(), c->d_err());
+  c->launches += 2;
+  int64_t N = 0;
+  TRY(device_scan(c, c->p_valid.as<int32_t>(), n_lines, c->p_vpos.as<int32_t>(), &N));
+  TRY(parse_error(c));
+  if (N == 0) return counts();
+  TRY(c->p_vline.reserve((size_t)N * 4));
+  TRY(c->p_ghead.reserve((size_t)N));
+  TRY(c->p_slot.reserve((size_t)N * 4));
+  TRY(c->p_phead.reserve((size_t)N * 4));
+  TRY(c->p_qpos.reserve((size_t)N * 4));
+  TRY(c->p_rslot.reserve((size_t)N * 4));
+  TRY(c->p_sslot.reserve((size_t)N * 4));
+  compact_lines_kernel<<<gl, 256, 0, c->stream>>>(c->p_valid.as<int32_t>(),
+                                                 c->p_vpos.as<int32_t>(), n_lines,
+                                                 c->p_vline.as<uint32_t>());
+  // 4 grouping
+  const unsigned gr = (unsigned)((N + 255) / 256);
+  group_heads_kernel<<<gr, 256, 0, c->stream>>>(dt, c->p_line_start.as<uint32_t>(),
+                                               c->p_rec.as<LineRec>(),
+                                               c->p_vline.as<uint32_t>(), N,
+                                               c->p_ghead.as<uint8_t>());
+  order_kernel<<<gr, 256, 0, c->stream>>>(c->p_rec.as<LineRec>(), c->p_vline.as<uint32_t>(),
+                                         c->p_ghead.as<uint8_t>(), N,
+                                         c->p_slot.as<uint32_t>(), c->p_phead.as<int32_t>(),
+                                         c->d_err());
+  c->launches += 3;
+  int64_t Q = 0;
+  TRY(device_scan(c, c->p_phead.as<int32_t>(), N, c->p_qpos.as<int32_t>(), &Q));
+  // 5 interning
+  subject_probe_kernel<<<gr, 256, 0, c->stream>>>(TS, dt, c->p_rec.as<LineRec>(),
+                                                 c->p_vline.as<uint32_t>(), N,
+                                                 c->p_rslot.as<uint32_t>(), c->d_err());
+  intern_assign_kernel<<<(unsigned)((kInternCap[0] + 255) / 256), 256, 0, c->stream>>>(
+      TS, dt, c->d_err());
+  c->launches += 2;
+  if (demux) {
+    sample_probe_kernel<<<gr, 256, 0, c->stream>>>(
+        TP, dt, c->p_line_start.as<uint32_t>(), c->p_rec.as<LineRec>(),
+        c->p_vline.as<uint32_t>(), c->p_slot.as<uint32_t>(), c->p_phead.as<int32_t>(), N,
+        c->p_sslot.as<uint32_t>(), c->d_err());
+    intern_assign_kernel<<<(unsigned)((kInternCap[1] + 255) / 256), 256, 0, c->stream>>>(
+        TP, dt, c->d_err());
+    c->launches += 2;
+  }
+  TRY(c->dq.reserve((size_t)N * 4 + 64));
+  TRY(c->ds.reserve((size_t)N * 4 + 64));
+  TRY(c->dqsamp.reserve((size_t)Q * 4 + 64));
+  TRY(c->p_qline.reserve((size_t)Q * 4 + 64));
+  emit_columns_kernel<<<gr, 256, 0, c->stream>>>(
+      TS, TP, demux, dt, c->p_line_start.as<uint32_t>(), c->p_rec.as<LineRec>(),
+      c->p_vline.as<uint32_t>(), c->p_slot.as<uint32_t>(), c->p_phead.as<int32_t>(),
+      c->p_qpos.as<int32_t>(), c->p_rslot.as<uint32_t>(), c->p_sslot.as<uint32_t>(), N,
+      c->dq.as<int32_t>(), c->ds.as<int32_t>(), c->dqsamp.as<int32_t>(),
+      c->p_qline.as<uint32_t>(), c->d_err());
+  c->launches++;
+  CK(cudaGetLastError());
+  TRY(parse_error(c));
+  c->p_nrec = N;
+  c->p_nqry = Q;
+  *n_rec = N;
+  *n_qry = Q;
+  return counts();
+}
+
+}  // extern "C"
+
+__global__ void names_by_id_kernel(InternTable T, int32_t from, int32_t to,
+                                   uint32_t *off, uint32_t *len) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > T.cap_mask || T.keys[i] == ~0ull) return;
+  const int32_t id = T.ids[i];
+  if (id >= from && id < to) {
+    off[id - from] = T.soff[i];
+    len[id - from] = T.slen[i];
+  }
+}
+
+extern "C" {
+
+int wk_parse_fetch_names(wk_ctx *c, int which, int32_t from, int32_t to, char *buf,
+                         int64_t cap, int64_t *used, int32_t *lens) {
+  if (!c || which < 0 || which > 1 || from < 0 || to < from || !used)
+    return fail(WK_ERR_ARG, "bad arguments");
+  TRY(use_device(c));
+  *used = 0;
+  if (!c->p_tables || to == from) return WK_OK;
+  if (!buf || !lens) return fail(WK_ERR_ARG, "output buffers are NULL");
+  InternTable T = intern_table(c, which);
+  const int32_t m = to - from;
+  DevBuf doff, dlen;
+  TRY(doff.reserve((size_t)m * 4));
+  TRY(dlen.reserve((size_t)m * 4));
+  names_by_id_kernel<<<(unsigned)((kInternCap[which] + 255) / 256), 256, 0, c->stream>>>(
+      T, from, to, doff.as<uint32_t>(), dlen.as<uint32_t>());
+  c->launches++;
+  CK(cudaGetLastError());
+  std::vector<uint32_t> off((size_t)m), len((size_t)m);
+  ull pool_used = 0;
+  CK(cudaMemcpyAsync(off.data(), doff.p, (size_t)m * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(len.data(), dlen.p, (size_t)m * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&pool_used, T.pool_used, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  doff.release();
+  dlen.release();
+  std::vector<char> pool((size_t)pool_used + 1);
+  if (pool_used)
+    CK(cudaMemcpy(pool.data(), T.pool, (size_t)pool_used, cudaMemcpyDeviceToHost));
+  int64_t at = 0;
+  for (int32_t i = 0; i < m; ++i) {
+    if (at + len[i] > cap) return fail(WK_ERR_CAPACITY, "name buffer too small");
+    memcpy(buf + at, pool.data() + off[i], len[i]);
+    lens[i] = (int32_t)len[i];
+    at += len[i];
+  }
+  *used = at;
+  return WK_OK;
+}
+
+int wk_parse_fetch_columns(wk_ctx *c, int32_t *q, int32_t *s, int32_t *q_sample,
+                           uint32_t *q_line) {
+  if (!c) return fail(WK_ERR_ARG, "ctx is NULL");
+  TRY(use_device(c));
+  const size_t N = (size_t)c->p_nrec, Q = (size_t)c->p_nqry;
+  if (q && N) CK(cudaMemcpyAsync(q, c->dq.p, N * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (s && N) CK(cudaMemcpyAsync(s, c->ds.p, N * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (q_sample && Q && c->p_demux)
+    CK(cudaMemcpyAsync(q_sample, c->dqsamp.p, Q * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (q_line && Q)
+    CK(cudaMemcpyAsync(q_line, c->p_qline.p, Q * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return WK_OK;
+}
+
+int wk_classify_parsed(wk_ctx *c, const int32_t *sample_map, int32_t n_map,
+                       int32_t sample) {
+  TRY(check_plan_ready(c, false));
+  TRY(use_device(c));
+  const int64_t N = c->p_nrec, Q = c->p_nqry;
+  if (N == 0) return WK_OK;
+  const int32_t *dqs = nullptr;
+  if (c->p_demux) {
+    if (!sample_map || n_map <= 0)
+      return fail(WK_ERR_ARG, "a demultiplexed chunk needs the sample map");
+    DevBuf dm;
+    TRY(dm.reserve((size_t)n_map * 4));
+    CK(cudaMemcpyAsync(dm.p, sample_map, (size_t)n_map * 4, cudaMemcpyHostToDevice,
+                       c->stream));
+    remap_samples_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, c->stream>>>(
+        c->dqsamp.as<int32_t>(), Q, dm.as<int32_t>(), n_map);
+    c->launches++;
+    CK(cudaStreamSynchronize(c->stream));
+    dm.release();
+    dqs = c->dqsamp.as<int32_t>();
+    TRY(launch_classify(c, c->dq.as<int32_t>(), c->ds.as<int32_t>(), N, nullptr, N, 0, N,
+                        dqs, nullptr, 0));
+    c->p_nrec = 0;  // the sample column now holds plan samples: one classify per parse
+    return check_device_err(c);
+  }
+  if (sample < 0 || sample >= c->S) return fail(WK_ERR_ARG, "sample %d out of range", sample);
+  TRY(launch_classify(c, c->dq.as<int32_t>(), c->ds.as<int32_t>(), N, nullptr, N, 0, N,
+                      nullptr, nullptr, sample));
+  return check_device_err(c);
 }
 
 int wk_counts_device(wk_ctx *c, void **d_ptr, int64_t *n_elems) {

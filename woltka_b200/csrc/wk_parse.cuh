@@ -1,0 +1,396 @@
+// wk_parse.cuh — SAM text -> int32 SoA columns on the device.
+//
+// What it replaces (reference, /root/reference/woltka/):
+//   align.py:258-347   parse_sam_file: per line split('\t', 3), skip RNAME '*',
+//                      mate = (FLAG >> 6) & 3, adjacent equal QNAMEs form a
+//                      group whose mates 0/1/2 become up to three queries
+//                      (name, name/1, name/2) emitted in that order, subjects
+//                      pooled as a set per query
+//   workflow.py:844-909 demultiplex: sample = text of the query name before
+//                      the first '_' when something follows it, else ''
+// and the per-record Python work of the host-side interning
+// (woltka_b200/session.py).  Header lines are cut off by the caller.
+//
+// Pipeline (every step is a data-parallel kernel, no host loop over lines):
+//   1 newline scan   16 bytes per thread -> line starts
+//   2 fields         one thread per line: the first three tabs, FLAG, '*'
+//   3 compaction     valid lines only (unmapped lines do not break a group)
+//   4 grouping       byte-compare of adjacent QNAMEs -> group heads; inside a
+//                    group records are ordered by mate (stable), pool heads
+//                    become query heads; prefix sum -> query index
+//   5 interning      RNAME -> subject index, sample prefix -> sample index
+//                    through device hash tables that persist over chunks
+//                    (key = 64-bit hash, every lookup verified byte by byte
+//                    against the interned string: a hash collision is
+//                    reported, never silently merged)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace wk {
+
+typedef unsigned long long ull;
+
+enum { PERR_FIELDS = 1, PERR_FLAG = 2, PERR_COLLISION = 4, PERR_TABLE_FULL = 8,
+       PERR_POOL_FULL = 16, PERR_GROUP = 32 };
+
+// ---- exclusive prefix sum of int32 (three small kernels) ----------------------
+constexpr int SCAN_NT = 512, SCAN_ITEMS = 8, SCAN_TILE = SCAN_NT * SCAN_ITEMS;
+
+__device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int *total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < (blockDim.x >> 5) ? s_warp[lane] : 0, wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    if (lane < (blockDim.x >> 5)) s_warp[lane] = wi - w;
+    if (lane == 31) *total = wi;
+  }
+  __syncthreads();
+  return s_warp[warp] + incl - v;
+}
+
+__global__ void scan_sums_kernel(const int32_t *in, int64_t n, int32_t *sums) {
+  __shared__ int s_warp[32];
+  __shared__ int s_tot;
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int v = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j)
+    if (base + j < n) v += in[base + j];
+  block_excl_scan(v, s_warp, &s_tot);
+  if (threadIdx.x == 0) sums[blockIdx.x] = s_tot;
+}
+__global__ void scan_tops_kernel(int32_t *sums, int n_blocks, int64_t *total) {
+  __shared__ int s_warp[32];
+  __shared__ int s_tot;
+  int64_t run = 0;
+  for (int b0 = 0; b0 < n_blocks; b0 += blockDim.x) {
+    const int i = b0 + threadIdx.x;
+    const int v = i < n_blocks ? sums[i] : 0;
+    const int ex = block_excl_scan(v, s_warp, &s_tot);
+    if (i < n_blocks) sums[i] = (int)(run + ex);
+    run += s_tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = run;
+}
+__global__ void scan_apply_kernel(const int32_t *in, int64_t n, const int32_t *sums,
+                                  int32_t *out) {
+  __shared__ int s_warp[32];
+  __shared__ int s_tot;
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int x[SCAN_ITEMS], v = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    x[j] = base + j < n ? in[base + j] : 0;
+    v += x[j];
+  }
+  int ex = block_excl_scan(v, s_warp, &s_tot) + sums[blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    if (base + j < n) out[base + j] = ex;
+    ex += x[j];
+  }
+}
+
+// ---- 1: line starts -----------------------------------------------------------
+// nl[i] = 1 if byte i is '\n'; a line start is 0 and every position after '\n'
+__global__ void newline_flags_kernel(const uint8_t *text, int64_t n, int32_t *cnt16) {
+  // one thread per 16 bytes: number of newlines in them
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t b = t * 16;
+  if (b >= n) return;
+  int c = 0;
+  if (b + 16 <= n) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(text + b);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t x = w[k] ^ 0x0a0a0a0au;  // zero byte where '\n'
+      const uint32_t z = (x - 0x01010101u) & ~x & 0x80808080u;
+      c += __popc(z);
+    }
+  } else {
+    for (int64_t i = b; i < n; ++i) c += text[i] == '\n';
+  }
+  cnt16[t] = c;
+}
+__global__ void line_starts_kernel(const uint8_t *text, int64_t n,
+                                   const int32_t *pos16, uint32_t *line_start) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t b = t * 16;
+  if (b >= n) return;
+  int k = pos16[t] + 1;  // line 0 starts at byte 0
+  const int64_t e = b + 16 < n ? b + 16 : n;
+  for (int64_t i = b; i < e; ++i)
+    if (text[i] == '\n') line_start[k++] = (uint32_t)(i + 1);
+  if (t == 0) line_start[0] = 0;
+}
+
+// ---- 2: fields ------------------------------------------------------------------
+struct LineRec {
+  uint32_t qlen;   // QNAME = text[start, start + qlen)
+  uint32_t roff;   // RNAME = text[roff, roff + rlen)
+  uint32_t rlen;
+  uint32_t mate;   // 0..2 (both mate bits set is an error, as in the reference)
+};
+
+__device__ __forceinline__ ull hash_bytes(const uint8_t *p, uint32_t len) {
+  ull h = 0x9E3779B97F4A7C15ull ^ len;
+  for (uint32_t i = 0; i < len; ++i) {
+    h ^= p[i];
+    h *= 0x100000001B3ull;
+    h ^= h >> 29;
+  }
+  h ^= h >> 32;
+  h *= 0xD6E8FEB86659FD93ull;
+  h ^= h >> 32;
+  return h == ~0ull ? 0 : h;  // ~0 marks an empty slot
+}
+
+__global__ void sam_fields_kernel(const uint8_t *text, int64_t n,
+                                  const uint32_t *line_start, int64_t n_lines,
+                                  LineRec *rec, int32_t *valid, int32_t *err) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_lines) return;
+  const uint32_t s = line_start[i];
+  uint32_t e = i + 1 < n_lines ? line_start[i + 1] - 1 : (uint32_t)n;  // excl. '\n'
+  if (e > s && e <= n && text[e - 1] == '\n') --e;   // last line with '\n'
+  LineRec r = {0, 0, 0, 0};
+  int ok = 0;
+  if (e > s) {
+    // the first three tabs
+    uint32_t t1 = e, t2 = e, t3 = e;
+    uint32_t p = s;
+    for (; p < e && text[p] != '\t'; ++p) {}
+    t1 = p;
+    for (p = t1 + 1; p < e && text[p] != '\t'; ++p) {}
+    t2 = p < e ? p : e;
+    for (p = t2 + 1; p < e && text[p] != '\t'; ++p) {}
+    t3 = p < e ? p : e;
+    if (t1 >= e || t2 >= e || t3 >= e) {
+      atomicOr(err, PERR_FIELDS);  // fewer than four fields (split('\t', 3))
+    } else {
+      r.qlen = t1 - s;
+      r.roff = t2 + 1;
+      r.rlen = t3 - t2 - 1;
+      // FLAG: a decimal integer (int(flag), align.py:322)
+      uint32_t flag = 0;
+      bool good = t2 > t1 + 1;
+      for (p = t1 + 1; p < t2; ++p) {
+        const uint32_t d = (uint32_t)text[p] - '0';
+        if (d > 9) good = false;
+        flag = flag * 10 + d;
+      }
+      if (!good) atomicOr(err, PERR_FLAG);
+      r.mate = (flag >> 6) & 3u;
+      if (r.mate == 3u) atomicOr(err, PERR_FLAG);  // the reference's pool has no slot 3
+      ok = !(r.rlen == 1 && text[r.roff] == '*');
+    }
+  } else {
+    atomicOr(err, PERR_FIELDS);  // empty line
+  }
+  rec[i] = r;
+  valid[i] = ok;
+}
+
+// ---- 3: compaction ------------------------------------------------------------------
+__global__ void compact_lines_kernel(const int32_t *valid, const int32_t *vpos,
+                                     int64_t n_lines, uint32_t *vline) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_lines && valid[i]) vline[vpos[i]] = (uint32_t)i;
+}
+
+// ---- 4: grouping ------------------------------------------------------------------------
+__device__ __forceinline__ bool same_bytes(const uint8_t *a, const uint8_t *b, uint32_t len) {
+  for (uint32_t i = 0; i < len; ++i)
+    if (a[i] != b[i]) return false;
+  return true;
+}
+// ghead[j] = 1 if valid record j starts a QNAME group
+__global__ void group_heads_kernel(const uint8_t *text, const uint32_t *line_start,
+                                   const LineRec *rec, const uint32_t *vline,
+                                   int64_t n_rec, uint8_t *ghead) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_rec) return;
+  bool head = true;
+  if (j > 0) {
+    const uint32_t a = vline[j - 1], b = vline[j];
+    head = rec[a].qlen != rec[b].qlen ||
+           !same_bytes(text + line_start[a], text + line_start[b], rec[b].qlen);
+  }
+  ghead[j] = head;
+}
+constexpr int PARSE_MAX_GROUP = 1 << 16;
+// output slot of record j: records of a group ordered by mate, stable; phead
+// (indexed by output slot) = 1 at the first record of a (group, mate) pool
+__global__ void order_kernel(const LineRec *rec, const uint32_t *vline,
+                             const uint8_t *ghead, int64_t n_rec, uint32_t *slot,
+                             int32_t *phead, int32_t *err) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_rec) return;
+  const uint32_t m = rec[vline[j]].mate;
+  int64_t ga = j;
+  while (!ghead[ga]) {
+    --ga;
+    if (j - ga > PARSE_MAX_GROUP) {
+      atomicOr(err, PERR_GROUP);
+      break;
+    }
+  }
+  uint32_t less = 0, before = 0;
+  for (int64_t i = ga; i < j; ++i) {
+    const uint32_t mi = rec[vline[i]].mate;
+    less += mi < m;
+    before += mi == m;
+  }
+  for (int64_t i = j + 1; i < n_rec && !ghead[i]; ++i) {
+    less += rec[vline[i]].mate < m;
+    if (i - j > PARSE_MAX_GROUP) {
+      atomicOr(err, PERR_GROUP);
+      break;
+    }
+  }
+  const int64_t out = ga + less + before;
+  slot[j] = (uint32_t)out;
+  phead[out] = before == 0;
+}
+
+// ---- 5: interning --------------------------------------------------------------------------
+struct InternTable {
+  ull *keys;          // [cap] 64-bit hash, ~0 = empty
+  int32_t *ids;       // [cap] index, -1 = not assigned yet
+  uint32_t *soff;     // [cap] offset of the string in the pool
+  uint32_t *slen;     // [cap]
+  uint32_t *first;    // [cap] text offset of the first occurrence (this chunk)
+  uint8_t *pool;      // interned strings, persistent over chunks
+  ull *pool_used;     // cursor
+  int32_t *count;     // strings interned so far
+  uint64_t cap_mask;
+  uint64_t pool_cap;
+};
+
+// find or claim the slot of text[off, off+len); returns the slot
+__device__ __forceinline__ uint32_t intern_probe(const InternTable &T, const uint8_t *text,
+                                                 uint32_t off, uint32_t len, int32_t *err) {
+  const ull h = hash_bytes(text + off, len);
+  uint64_t i = h & T.cap_mask;
+  for (uint64_t probe = 0; probe <= T.cap_mask; ++probe) {
+    ull k = T.keys[i];
+    if (k == ~0ull) {
+      k = atomicCAS(&T.keys[i], ~0ull, h);
+      if (k == ~0ull) {
+        T.first[i] = off;  // the claimer's occurrence is copied into the pool
+        T.slen[i] = len;
+        return (uint32_t)i;
+      }
+    }
+    if (k == h) return (uint32_t)i;
+    i = (i + 1) & T.cap_mask;
+  }
+  atomicOr(err, PERR_TABLE_FULL);
+  return 0;
+}
+// slots claimed in this chunk get their index and their copy in the pool
+__global__ void intern_assign_kernel(InternTable T, const uint8_t *text, int32_t *err) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > T.cap_mask) return;
+  if (T.keys[i] == ~0ull || T.ids[i] >= 0) return;
+  const uint32_t len = T.slen[i];
+  const ull at = atomicAdd(T.pool_used, (ull)len);
+  if (at + len > T.pool_cap) {
+    atomicOr(err, PERR_POOL_FULL);
+    return;
+  }
+  for (uint32_t b = 0; b < len; ++b) T.pool[at + b] = text[T.first[i] + b];
+  T.soff[i] = (uint32_t)at;
+  T.ids[i] = atomicAdd(T.count, 1);
+}
+// index of a string whose slot is known; verifies the bytes
+__device__ __forceinline__ int32_t intern_id(const InternTable &T, uint32_t slot,
+                                             const uint8_t *text, uint32_t off,
+                                             uint32_t len, int32_t *err) {
+  if (T.slen[slot] != len || !same_bytes(T.pool + T.soff[slot], text + off, len))
+    atomicOr(err, PERR_COLLISION);
+  return T.ids[slot];
+}
+
+// subjects: slot per valid record (in input order)
+__global__ void subject_probe_kernel(InternTable T, const uint8_t *text, const LineRec *rec,
+                                     const uint32_t *vline, int64_t n_rec,
+                                     uint32_t *rslot, int32_t *err) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_rec) return;
+  const LineRec r = rec[vline[j]];
+  rslot[j] = intern_probe(T, text, r.roff, r.rlen, err);
+}
+// sample prefix of a query name: [start, start+plen) (plen = 0: sample '')
+__device__ __forceinline__ uint32_t sample_prefix_len(const uint8_t *q, uint32_t qlen,
+                                                      uint32_t mate) {
+  // workflow.py:889-893 on the name the parser yields (QNAME + '' | '/1' | '/2')
+  uint32_t u = 0;
+  for (; u < qlen && q[u] != '_'; ++u) {}
+  if (u >= qlen) return 0;                      // no '_': sample ''
+  const bool follows = u + 1 < qlen || (mate == 1 || mate == 2);
+  return follows ? u : 0;
+}
+__global__ void sample_probe_kernel(InternTable T, const uint8_t *text,
+                                    const uint32_t *line_start, const LineRec *rec,
+                                    const uint32_t *vline, const uint32_t *slot,
+                                    const int32_t *phead, int64_t n_rec, uint32_t *sslot,
+                                    int32_t *err) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_rec || !phead[slot[j]]) return;
+  const uint32_t li = vline[j];
+  const uint32_t s = line_start[li];
+  const uint32_t pl = sample_prefix_len(text + s, rec[li].qlen, rec[li].mate);
+  sslot[j] = intern_probe(T, text, s, pl, err);
+}
+// final columns in output order
+__global__ void emit_columns_kernel(InternTable TS, InternTable TP, int demux,
+                                    const uint8_t *text, const uint32_t *line_start,
+                                    const LineRec *rec, const uint32_t *vline,
+                                    const uint32_t *slot, const int32_t *phead,
+                                    const int32_t *qpos, const uint32_t *rslot,
+                                    const uint32_t *sslot, int64_t n_rec, int32_t *q,
+                                    int32_t *s, int32_t *q_sample, uint32_t *q_line,
+                                    int32_t *err) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_rec) return;
+  const uint32_t li = vline[j];
+  const LineRec r = rec[li];
+  const uint32_t out = slot[j];
+  // query index = number of pool heads at or before the slot, minus one
+  const int32_t qi = qpos[out] + phead[out] - 1;
+  q[out] = qi;
+  s[out] = intern_id(TS, rslot[j], text, r.roff, r.rlen, err);
+  if (phead[out]) {
+    q_line[qi] = li | (r.mate << 30);  // where the query's name is (mate in the top bits)
+    if (demux) {
+      const uint32_t st = line_start[li];
+      const uint32_t pl = sample_prefix_len(text + st, r.qlen, r.mate);
+      q_sample[qi] = intern_id(TP, sslot[j], text, st, pl, err);
+    }
+  }
+}
+__global__ void remap_samples_kernel(int32_t *q_sample, int64_t n_qry, const int32_t *map,
+                                     int32_t n_map) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_qry) return;
+  const int32_t v = q_sample[i];
+  q_sample[i] = (v >= 0 && v < n_map) ? map[v] : -1;
+}
+
+}  // namespace wk

@@ -270,6 +270,56 @@ class Engine:
         _lib.check(self.lib.wk_counts_device(self.ctx, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    # -- SAM text on the device (wk_parse.cuh) -----------------------------
+    def parse_sam(self, text, demux=False):
+        """Parse a chunk of SAM body text (bytes); returns (n_rec, n_qry,
+        n_subjects_total, n_samples_total)."""
+        buf = text if isinstance(text, bytes) else bytes(text)
+        n_rec, n_qry = C.c_int64(), C.c_int64()
+        n_sub, n_smp = C.c_int32(), C.c_int32()
+        _lib.check(self.lib.wk_parse_sam(
+            self.ctx, C.cast(C.c_char_p(buf), C.c_void_p), len(buf),
+            int(bool(demux)),
+            C.byref(n_rec), C.byref(n_qry), C.byref(n_sub), C.byref(n_smp)))
+        return n_rec.value, n_qry.value, n_sub.value, n_smp.value
+
+    def fetch_names(self, which, lo, hi):
+        """Interned names [lo, hi) of the subject (0) / sample (1) table."""
+        if hi <= lo:
+            return []
+        cap = 1 << 20
+        while True:
+            buf = C.create_string_buffer(cap)
+            lens = np.empty(hi - lo, dtype=np.int32)
+            used = C.c_int64()
+            rc = self.lib.wk_parse_fetch_names(self.ctx, which, lo, hi, buf, cap,
+                                               C.byref(used), _ptr(lens))
+            if rc == 5 and cap < (1 << 30):     # WK_ERR_CAPACITY: grow
+                cap *= 8
+                continue
+            _lib.check(rc)
+            break
+        raw = buf.raw[:used.value]
+        out, at = [], 0
+        for n in lens.tolist():
+            out.append(raw[at:at + n].decode())
+            at += n
+        return out
+
+    def fetch_parsed_columns(self, n_rec, n_qry, demux=False):
+        q = np.empty(n_rec, dtype=np.int32)
+        s = np.empty(n_rec, dtype=np.int32)
+        qs = np.empty(n_qry, dtype=np.int32) if demux else None
+        ql = np.empty(n_qry, dtype=np.uint32)
+        _lib.check(self.lib.wk_parse_fetch_columns(self.ctx, _ptr(q), _ptr(s),
+                                                   _ptr(qs), _ptr(ql)))
+        return q, s, qs, ql
+
+    def classify_parsed(self, sample_map=None, sample=0):
+        sm = _i32(sample_map)
+        _lib.check(self.lib.wk_classify_parsed(
+            self.ctx, _ptr(sm), 0 if sm is None else len(sm), sample))
+
     def counts_tensor(self):
         """Zero-copy torch view of the units table (for an NCCL reduce)."""
         import torch

@@ -227,6 +227,45 @@ class Session:
             starts.append(len(q))
             self._write_readmaps(len(q), reads, starts, q_sample)
 
+    # -- SAM text parsed on the device (wk_parse_sam) ---------------------------
+    def can_parse_on_device(self):
+        """One engine, no --trim-sub, no read maps, and an engine that has
+        the device reader (the test stand-in engine does not)."""
+        return (len(self.engines) == 1 and not self.trimsub and
+                self.rank2dir is None and
+                hasattr(self.engines[0], 'parse_sam'))
+
+    def add_text_chunk(self, text, demux, sample_name, samples=None):
+        """One chunk of SAM body text: lines -> queries -> indices on the
+        GPU (align.py:258-347, workflow.py:844-909); the host only names the
+        subjects and samples that appear for the first time.  Returns the
+        number of queries in the chunk."""
+        eng = self.engines[0]
+        if not hasattr(self, '_dev_sub'):
+            if self.sub_node:
+                raise RuntimeError('device and host readers cannot be mixed '
+                                   'in one run')
+            self._dev_sub = 0          # subjects named so far
+            self._dev_smp = []         # device sample index -> plan sample
+        n_rec, n_qry, n_sub, n_smp = eng.parse_sam(text, demux)
+        for name in eng.fetch_names(0, self._dev_sub, n_sub):
+            if self.subject(name) != self._dev_sub:
+                raise RuntimeError('subject numbering diverged')
+            self._dev_sub += 1
+        if not n_rec:
+            return 0
+        if demux:
+            for name in eng.fetch_names(1, len(self._dev_smp), n_smp):
+                keep = samples is None or name in samples
+                self._dev_smp.append(self.sample(name) if keep else -1)
+            self._sync_tables()
+            eng.classify_parsed(np.asarray(self._dev_smp, dtype=np.int32))
+        else:
+            si = self.sample(sample_name)
+            self._sync_tables()
+            eng.classify_parsed(None, si)
+        return n_qry
+
     def _write_readmaps(self, n_rec, reads, starts, q_sample):
         """Append this chunk's read-to-taxon lines (file.write_readmap,
         file.py:469-500, called at workflow.py:1042-1046): one line per

@@ -23,6 +23,7 @@ instead of silently falling back.
 import bz2
 import gzip
 import lzma
+import os
 import sys
 from functools import partial
 from os.path import basename
@@ -55,6 +56,60 @@ def openzip(fp, mode='rt'):
     return open(fp, mode.replace('t', '') if 'b' in mode else mode)
 
 
+def _text_chunks(fp, block=64 << 20):
+    """Body of a SAM file as byte chunks that end at a line end and where
+    the query name changes (a query is never split, align.py:73-79); leading
+    '@' lines are dropped (align.py:296-300)."""
+    opener = open
+    for ext, op in _OPENERS.items():
+        if fp.endswith(ext):
+            opener = op
+    with opener(fp, 'rb') as fh:
+        carry, first = b'', True
+        while True:
+            data = fh.read(block)
+            buf = carry + data
+            if first and buf:
+                pos = 0
+                while pos < len(buf) and buf[pos:pos + 1] == b'@':
+                    nl = buf.find(b'\n', pos)
+                    if nl < 0:
+                        pos = len(buf) if not data else pos
+                        break
+                    pos = nl + 1
+                if pos < len(buf) or not data:
+                    buf, first = buf[pos:], False
+                elif data:
+                    carry = buf
+                    continue
+            if not data:
+                if buf:
+                    yield buf
+                return
+            end = buf.rfind(b'\n')
+            if end < 0:
+                carry = buf
+                continue
+            # back over the trailing lines that share the last query name
+            ls = buf.rfind(b'\n', 0, end) + 1
+            name = buf[ls:end].split(b'\t', 1)[0]
+            cut = ls
+            while cut > 0:
+                ps = buf.rfind(b'\n', 0, cut - 1) + 1
+                if buf[ps:cut - 1].split(b'\t', 1)[0] != name:
+                    break
+                cut = ps
+            if cut == 0:
+                carry = buf
+                continue
+            yield buf[:cut]
+            carry = buf[cut:]
+
+
+# which reader fed the last file of the last classify() call ('device' | 'host')
+LAST_READER = None
+
+
 def _echo(msg, nl=True):
     sys.stdout.write(msg + ('\n' if nl else ''))
     sys.stdout.flush()
@@ -76,6 +131,21 @@ def build_mapper(coords_fp=None, outcov_dir=None, overlap=None, chunk=None,
         raise NotImplementedError(
             'Subject coverage (--outcov) is not part of the GPU hot path.')
     return plain_mapper, chunk or 1024
+
+
+def _is_sam(fileobj, fmt):
+    """Format of the file: given, or inferred from its first line like
+    align.infer_align_format (align.py:153-223)."""
+    if fmt:
+        return fmt == 'sam'
+    from .align import infer_align_format
+    try:
+        pos = fileobj.tell()
+        kind, _ = infer_align_format(fileobj)
+        fileobj.seek(pos)
+    except (ValueError, OSError):
+        return False
+    return kind == 'sam'
 
 
 def _read_strata(fp, zippers=None):
@@ -154,8 +224,23 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
                           samples=samset if demux else None,
                           strata_of=strata_of if stratmap else None)
             nqry, nstep = 0, -1
+            on_device = (not is_ordinal and fp != '-' and not exclude and
+                         not stratmap and mapper is plain_mapper and
+                         not os.environ.get('WOLTKA_B200_HOST_READER') and
+                         sess.can_parse_on_device() and
+                         _is_sam(fileobj, fmt))
+            global LAST_READER
+            LAST_READER = 'device' if on_device else 'host'
             try:
-                if is_ordinal:
+                if on_device:
+                    for text in _text_chunks(fp):
+                        nqry += sess.add_text_chunk(
+                            text, bool(demux), sname, samset if demux else None)
+                        istep = nqry // 1000000 - nstep
+                        if istep:
+                            _echo('.' * istep, nl=False)
+                            nstep += istep
+                elif is_ordinal:
                     for qn, cn, bg, en, ln in iter_records(
                             iter(fileobj), fmt, exclude, chunk or 2 ** 20):
                         nqry += len(set(qn))
