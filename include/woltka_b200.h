@@ -211,6 +211,12 @@ int wk_fetch_assignments(wk_ctx *ctx, int32_t *out, int64_t n_rec);
 int wk_parse_sam(wk_ctx *ctx, const char *text, int64_t n_bytes, int demux,
                  int64_t *n_rec, int64_t *n_qry, int32_t *n_subjects,
                  int32_t *n_samples);
+/* Same for every plain-mode format of align.iter_align: fmt 0 = sam, 1 = b6o
+ * (align.py:753-802: fields 0/1, short lines skipped), 2 = paf (:984-1044:
+ * fields 0/5), 3 = map (:621-666: fields 0/1, subject right-stripped). */
+int wk_parse_text(wk_ctx *ctx, const char *text, int64_t n_bytes, int fmt,
+                  int demux, int64_t *n_rec, int64_t *n_qry,
+                  int32_t *n_subjects, int32_t *n_samples);
 /* Names with index in [from, to) of the subject (which = 0) or sample
  * (which = 1) table: bytes concatenated into buf, lengths into lens. */
 int wk_parse_fetch_names(wk_ctx *ctx, int which, int32_t from, int32_t to,

@@ -17,15 +17,15 @@ DATA = os.path.join(os.path.dirname(__file__), 'golden', 'data')
 SUFFIX = ('', '/1', '/2')
 
 
-def host_queries(text):
+def host_queries(text, fmt='sam'):
     lines = text.decode().splitlines(keepends=True)
-    return list(align.iter_align(iter(lines), 'sam'))
+    return list(align.iter_align(iter(lines), fmt))
 
 
-def device_queries(engine, text, demux=False):
+def device_queries(engine, text, demux=False, fmt='sam'):
     """[(query name, set of subject names[, sample name])] from the device."""
     body = text
-    n_rec, n_qry, n_sub, n_smp = engine.parse_sam(body, demux)
+    n_rec, n_qry, n_sub, n_smp = engine.parse_sam(body, demux, fmt)
     subjects = engine.fetch_names(0, 0, n_sub)
     samples = engine.fetch_names(1, 0, n_smp)
     q, s, qs, ql = engine.fetch_parsed_columns(n_rec, n_qry, demux)
@@ -148,10 +148,51 @@ def test_classify_from_text_equals_classify_from_host_reader(monkeypatch, tmp_pa
     fp.write_bytes(b'@HD\tVN:1.0\n@SQ\tSN:x\tLN:1\n' + synthetic_sam(3000, 5))
     orig = workflow._text_chunks
     monkeypatch.setattr(workflow, '_text_chunks',
-                        lambda p: orig(p, block=20000))
+                        lambda p, header=True: orig(p, block=20000, header=header))
     dev, reader = _run_classify([str(fp)], True)
     assert reader == 'device'
     monkeypatch.setenv('WOLTKA_B200_HOST_READER', '1')
     host, _ = _run_classify([str(fp)], True)
     assert dev == host
     assert len(dev['none']) > 3
+
+
+def _open_any(path):
+    import bz2
+    import gzip
+    op = {'.xz': lzma.open, '.bz2': bz2.open, '.gz': gzip.open}
+    for ext, f in op.items():
+        if path.endswith(ext):
+            return f(path)
+    return open(path, 'rb')
+
+
+@pytest.mark.parametrize('path,fmt', [('blastn/mux.b6o.xz', 'b6o'),
+                                      ('burst/S02.b6.bz2', 'b6o'),
+                                      ('split/S04.map.bz2', 'map')])
+def test_bundled_other_formats(path, fmt):
+    from woltka_b200.engine import Engine
+    eng = Engine(0)
+    with _open_any(os.path.join(DATA, path)) as f:
+        text = f.read()
+    got, _ = device_queries(eng, text, demux=True, fmt=fmt)
+    exp = host_queries(text, fmt)
+    assert [g[0] for g in got] == [e[0] for e in exp]
+    assert [g[1] for g in got] == [e[1] for e in exp]
+    assert [g[2] for g in got] == [_split_sample(e[0])[0] for e in exp]
+    eng.close()
+
+
+def test_odd_lines_of_map_b6o_paf():
+    from woltka_b200.engine import Engine
+    eng = Engine(0)
+    cases_ = {
+        'map': b'q1\tA\nq1\tB \t x\nno_tab_line\nq2\t\nq2\tC\r\nq3\tA\textra\n',
+        'b6o': b'q1\tA\t99\nshort\tline\nq1\tB\t\nq2\tA\t1\t2\t3\n',
+        'paf': b'q1\t1\t2\t3\t+\tT1\t9\nq1\t1\t2\t3\t+\tT2\nq2\t1\t2\t3\t-\tT1\t9\t8\n',
+    }
+    for fmt, text in cases_.items():
+        got, _ = device_queries(eng, text, fmt=fmt)
+        exp = host_queries(text, fmt)
+        assert got == [(e[0], e[1]) for e in exp], fmt
+    eng.close()

@@ -62,6 +62,8 @@ SIGNATURES = {
     'wk_counts_device': (C.c_int, [_vp, C.POINTER(_vp), _i64p]),
     'wk_parse_sam': (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _i64p, _i64p,
                                _i32p, _i32p]),
+    'wk_parse_text': (C.c_int, [_vp, _vp, C.c_int64, C.c_int, C.c_int, _i64p,
+                                _i64p, _i32p, _i32p]),
     'wk_parse_fetch_names': (C.c_int, [_vp, C.c_int, C.c_int32, C.c_int32, _vp,
                                        C.c_int64, _i64p, _vp]),
     'wk_parse_fetch_columns': (C.c_int, [_vp, _vp, _vp, _vp, _vp]),

@@ -1553,13 +1553,14 @@ static int parse_error(wk_ctx *c) {
 
 extern "C" {
 
-int wk_parse_sam(wk_ctx *c, const char *text, int64_t n_bytes, int demux,
-                 int64_t *n_rec, int64_t *n_qry, int32_t *n_subjects,
-                 int32_t *n_samples) {
+int wk_parse_text(wk_ctx *c, const char *text, int64_t n_bytes, int fmt, int demux,
+                  int64_t *n_rec, int64_t *n_qry, int32_t *n_subjects,
+                  int32_t *n_samples) {
   if (!c || !n_rec || !n_qry || !n_subjects || !n_samples)
     return fail(WK_ERR_ARG, "bad arguments");
   if (n_bytes < 0 || n_bytes >= (1ll << 31) || (n_bytes && !text))
     return fail(WK_ERR_ARG, "a text chunk must be smaller than 2 GiB");
+  if (fmt < 0 || fmt > 3) return fail(WK_ERR_ARG, "bad format code %d", fmt);
   TRY(use_device(c));
   TRY(parse_tables(c));
   c->p_nrec = c->p_nqry = 0;
@@ -1596,9 +1597,10 @@ int wk_parse_sam(wk_ctx *c, const char *text, int64_t n_bytes, int demux,
   TRY(c->p_valid.reserve((size_t)n_lines * 4));
   TRY(c->p_vpos.reserve((size_t)n_lines * 4));
   const unsigned gl = (unsigned)((n_lines + 255) / 256);
-  sam_fields_kernel<<<gl, 256, 0, c->stream>>>(dt, n_bytes, c->p_line_start.as<uint32_t>(),
-                                              n_lines, c->p_rec.as<LineRec>(),
-                                              c->p_valid.as<int32_t>(), c->d_err());
+  line_fields_kernel<<<gl, 256, 0, c->stream>>>(dt, n_bytes, fmt,
+                                               c->p_line_start.as<uint32_t>(), n_lines,
+                                               c->p_rec.as<LineRec>(),
+                                               c->p_valid.as<int32_t>(), c->d_err());
   c->launches += 2;
   int64_t N = 0;
   TRY(device_scan(c, c->p_valid.as<int32_t>(), n_lines, c->p_vpos.as<int32_t>(), &N));
@@ -1664,6 +1666,13 @@ int wk_parse_sam(wk_ctx *c, const char *text, int64_t n_bytes, int demux,
 }
 
 }  // extern "C"
+
+extern "C" int wk_parse_sam(wk_ctx *c, const char *text, int64_t n_bytes, int demux,
+                            int64_t *n_rec, int64_t *n_qry, int32_t *n_subjects,
+                            int32_t *n_samples) {
+  return wk_parse_text(c, text, n_bytes, PFMT_SAM, demux, n_rec, n_qry, n_subjects,
+                       n_samples);
+}
 
 __global__ void names_by_id_kernel(InternTable T, int32_t from, int32_t to,
                                    uint32_t *off, uint32_t *len) {

@@ -160,9 +160,18 @@ __device__ __forceinline__ ull hash_bytes(const uint8_t *p, uint32_t len) {
   return h == ~0ull ? 0 : h;  // ~0 marks an empty slot
 }
 
-__global__ void sam_fields_kernel(const uint8_t *text, int64_t n,
-                                  const uint32_t *line_start, int64_t n_lines,
-                                  LineRec *rec, int32_t *valid, int32_t *err) {
+enum { PFMT_SAM = 0, PFMT_B6O = 1, PFMT_PAF = 2, PFMT_MAP = 3 };
+
+// One thread per line: query name and subject fields of the format.
+//   sam  fields 0 / 2, FLAG = field 1, '*' skipped, < 4 fields is an error
+//        (align.py:315-322)
+//   b6o  fields 0 / 1, lines with < 3 fields are skipped (align.py:784-788)
+//   paf  fields 0 / 5, lines with < 7 fields are skipped (align.py:1026-1030)
+//   map  fields 0 / 1 (subject stripped of trailing blanks), lines without a
+//        tab are skipped (align.py:650-655)
+__global__ void line_fields_kernel(const uint8_t *text, int64_t n, int fmt,
+                                   const uint32_t *line_start, int64_t n_lines,
+                                   LineRec *rec, int32_t *valid, int32_t *err) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_lines) return;
   const uint32_t s = line_start[i];
@@ -170,26 +179,33 @@ __global__ void sam_fields_kernel(const uint8_t *text, int64_t n,
   if (e > s && e <= n && text[e - 1] == '\n') --e;   // last line with '\n'
   LineRec r = {0, 0, 0, 0};
   int ok = 0;
-  if (e > s) {
-    // the first three tabs
-    uint32_t t1 = e, t2 = e, t3 = e;
+  // positions of the first six tabs (e = not there)
+  uint32_t tab[6];
+  {
     uint32_t p = s;
-    for (; p < e && text[p] != '\t'; ++p) {}
-    t1 = p;
-    for (p = t1 + 1; p < e && text[p] != '\t'; ++p) {}
-    t2 = p < e ? p : e;
-    for (p = t2 + 1; p < e && text[p] != '\t'; ++p) {}
-    t3 = p < e ? p : e;
-    if (t1 >= e || t2 >= e || t3 >= e) {
+    const int need = fmt == PFMT_SAM ? 3 : fmt == PFMT_PAF ? 6 : 2;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      if (k < need) {
+        for (; p < e && text[p] != '\t'; ++p) {}
+        tab[k] = p;
+        if (p < e) ++p;
+      } else {
+        tab[k] = e;
+      }
+    }
+  }
+  if (fmt == PFMT_SAM) {
+    if (e <= s || tab[0] >= e || tab[1] >= e || tab[2] >= e) {
       atomicOr(err, PERR_FIELDS);  // fewer than four fields (split('\t', 3))
     } else {
-      r.qlen = t1 - s;
-      r.roff = t2 + 1;
-      r.rlen = t3 - t2 - 1;
+      r.qlen = tab[0] - s;
+      r.roff = tab[1] + 1;
+      r.rlen = tab[2] - tab[1] - 1;
       // FLAG: a decimal integer (int(flag), align.py:322)
       uint32_t flag = 0;
-      bool good = t2 > t1 + 1;
-      for (p = t1 + 1; p < t2; ++p) {
+      bool good = tab[1] > tab[0] + 1;
+      for (uint32_t p = tab[0] + 1; p < tab[1]; ++p) {
         const uint32_t d = (uint32_t)text[p] - '0';
         if (d > 9) good = false;
         flag = flag * 10 + d;
@@ -199,8 +215,33 @@ __global__ void sam_fields_kernel(const uint8_t *text, int64_t n,
       if (r.mate == 3u) atomicOr(err, PERR_FLAG);  // the reference's pool has no slot 3
       ok = !(r.rlen == 1 && text[r.roff] == '*');
     }
+  } else if (fmt == PFMT_B6O) {
+    if (tab[0] < e && tab[1] < e) {  // at least three fields
+      r.qlen = tab[0] - s;
+      r.roff = tab[0] + 1;
+      r.rlen = tab[1] - tab[0] - 1;
+      ok = 1;
+    }
+  } else if (fmt == PFMT_PAF) {
+    if (tab[5] < e) {  // at least seven fields
+      r.qlen = tab[0] - s;
+      r.roff = tab[4] + 1;
+      r.rlen = tab[5] - tab[4] - 1;
+      ok = 1;
+    }
   } else {
-    atomicOr(err, PERR_FIELDS);  // empty line
+    if (tab[0] < e) {  // query <tab> subject [<tab> ...]
+      r.qlen = tab[0] - s;
+      r.roff = tab[0] + 1;
+      uint32_t q = tab[1];  // end of the second field (or of the line)
+      // str.rstrip(): trailing whitespace of the subject goes
+      while (q > r.roff && (text[q - 1] == ' ' || text[q - 1] == '\r' ||
+                            text[q - 1] == '\t' || text[q - 1] == '\n' ||
+                            text[q - 1] == '\v' || text[q - 1] == '\f'))
+        --q;
+      r.rlen = q - r.roff;
+      ok = 1;
+    }
   }
   rec[i] = r;
   valid[i] = ok;

@@ -271,15 +271,18 @@ class Engine:
         return p.value, n.value
 
     # -- SAM text on the device (wk_parse.cuh) -----------------------------
-    def parse_sam(self, text, demux=False):
-        """Parse a chunk of SAM body text (bytes); returns (n_rec, n_qry,
-        n_subjects_total, n_samples_total)."""
+    FORMATS = {'sam': 0, 'b6o': 1, 'paf': 2, 'map': 3}
+
+    def parse_sam(self, text, demux=False, fmt='sam'):
+        """Parse a chunk of alignment text (bytes; SAM body or b6o / paf /
+        map lines); returns (n_rec, n_qry, n_subjects_total,
+        n_samples_total)."""
         buf = text if isinstance(text, bytes) else bytes(text)
         n_rec, n_qry = C.c_int64(), C.c_int64()
         n_sub, n_smp = C.c_int32(), C.c_int32()
-        _lib.check(self.lib.wk_parse_sam(
+        _lib.check(self.lib.wk_parse_text(
             self.ctx, C.cast(C.c_char_p(buf), C.c_void_p), len(buf),
-            int(bool(demux)),
+            self.FORMATS[fmt], int(bool(demux)),
             C.byref(n_rec), C.byref(n_qry), C.byref(n_sub), C.byref(n_smp)))
         return n_rec.value, n_qry.value, n_sub.value, n_smp.value
 

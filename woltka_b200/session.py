@@ -235,7 +235,8 @@ class Session:
                 self.rank2dir is None and
                 hasattr(self.engines[0], 'parse_sam'))
 
-    def add_text_chunk(self, text, demux, sample_name, samples=None):
+    def add_text_chunk(self, text, demux, sample_name, samples=None,
+                       fmt='sam'):
         """One chunk of SAM body text: lines -> queries -> indices on the
         GPU (align.py:258-347, workflow.py:844-909); the host only names the
         subjects and samples that appear for the first time.  Returns the
@@ -247,7 +248,7 @@ class Session:
                                    'in one run')
             self._dev_sub = 0          # subjects named so far
             self._dev_smp = []         # device sample index -> plan sample
-        n_rec, n_qry, n_sub, n_smp = eng.parse_sam(text, demux)
+        n_rec, n_qry, n_sub, n_smp = eng.parse_sam(text, demux, fmt)
         for name in eng.fetch_names(0, self._dev_sub, n_sub):
             if self.subject(name) != self._dev_sub:
                 raise RuntimeError('subject numbering diverged')

@@ -56,16 +56,16 @@ def openzip(fp, mode='rt'):
     return open(fp, mode.replace('t', '') if 'b' in mode else mode)
 
 
-def _text_chunks(fp, block=64 << 20):
-    """Body of a SAM file as byte chunks that end at a line end and where
-    the query name changes (a query is never split, align.py:73-79); leading
-    '@' lines are dropped (align.py:296-300)."""
+def _text_chunks(fp, block=64 << 20, header=True):
+    """An alignment file as byte chunks that end at a line end and where the
+    query name changes (a query is never split, align.py:73-79); the leading
+    '@' lines of a SAM file are dropped (align.py:296-300)."""
     opener = open
     for ext, op in _OPENERS.items():
         if fp.endswith(ext):
             opener = op
     with opener(fp, 'rb') as fh:
-        carry, first = b'', True
+        carry, first = b'', header
         while True:
             data = fh.read(block)
             buf = carry + data
@@ -133,19 +133,18 @@ def build_mapper(coords_fp=None, outcov_dir=None, overlap=None, chunk=None,
     return plain_mapper, chunk or 1024
 
 
-def _is_sam(fileobj, fmt):
-    """Format of the file: given, or inferred from its first line like
-    align.infer_align_format (align.py:153-223)."""
-    if fmt:
-        return fmt == 'sam'
-    from .align import infer_align_format
-    try:
-        pos = fileobj.tell()
-        kind, _ = infer_align_format(fileobj)
-        fileobj.seek(pos)
-    except (ValueError, OSError):
-        return False
-    return kind == 'sam'
+def _device_format(fileobj, fmt):
+    """Format of the file if the device reader knows it: given, or inferred
+    from its first line like align.infer_align_format (align.py:153-223)."""
+    if not fmt:
+        from .align import infer_align_format
+        try:
+            pos = fileobj.tell()
+            fmt, _ = infer_align_format(fileobj)
+            fileobj.seek(pos)
+        except (ValueError, OSError):
+            return None
+    return fmt if fmt in ('sam', 'b6o', 'paf', 'map') else None
 
 
 def _read_strata(fp, zippers=None):
@@ -227,15 +226,17 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
             on_device = (not is_ordinal and fp != '-' and not exclude and
                          not stratmap and mapper is plain_mapper and
                          not os.environ.get('WOLTKA_B200_HOST_READER') and
-                         sess.can_parse_on_device() and
-                         _is_sam(fileobj, fmt))
+                         sess.can_parse_on_device())
+            dfmt = _device_format(fileobj, fmt) if on_device else None
+            on_device = dfmt is not None
             global LAST_READER
             LAST_READER = 'device' if on_device else 'host'
             try:
                 if on_device:
-                    for text in _text_chunks(fp):
+                    for text in _text_chunks(fp, header=dfmt == 'sam'):
                         nqry += sess.add_text_chunk(
-                            text, bool(demux), sname, samset if demux else None)
+                            text, bool(demux), sname,
+                            samset if demux else None, dfmt)
                         istep = nqry // 1000000 - nstep
                         if istep:
                             _echo('.' * istep, nl=False)
