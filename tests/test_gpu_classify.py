@@ -349,3 +349,24 @@ def test_cfg5_shape_gene_to_ko_stratified_by_genus(engine):
     _same(got, exp)
     assert len(got[2]) > 10000          # (sample, genus, KO) cells
     assert engine.last_kernel() == 'classify_kernel'
+
+
+@pytest.mark.parametrize('r', ['5', '9'])
+@pytest.mark.parametrize('block', [0, 768, 512])
+def test_short_runs_and_fewer_warps(engine, small_case, monkeypatch, r, block):
+    """The run-per-lane kernel at every run length it is built for (13 is the
+    default) and with fewer warps per CTA, as chosen for large tables."""
+    monkeypatch.setenv('WK_SWEEP_R', r)
+    q, s = cases.random_hits(small_case, 30000, seed=int(r), long_every=3000,
+                             long_len=60)
+    engine.set_tuning(0, block, 0)
+    try:
+        for ent, mode in ((['genus'], 'default'), (['none'], 'uniq'),
+                          (['phylum', 'genus', 'species'], 'above'),
+                          (['family', 'genus'], 'major+unassigned')):
+            fl = cases.MODES[mode]
+            _same(cases.run_engine(engine, small_case, ent, fl, 0.8, q, s),
+                  cases.run_oracle(small_case, ent, fl, 0.8, q, s))
+            assert engine.last_kernel() == 'classify_fast_kernel'
+    finally:
+        engine.set_tuning(0, 0, 0)
