@@ -1662,7 +1662,14 @@ int wk_parse_text(wk_ctx *c, const char *text, int64_t n_bytes, int fmt, int dem
   c->p_nqry = Q;
   *n_rec = N;
   *n_qry = Q;
-  return counts();
+  TRY(counts());
+  // open addressing degrades long before the tables are full
+  if ((uint64_t)*n_subjects > kInternCap[0] / 2 || (uint64_t)*n_samples > kInternCap[1] / 2)
+    return fail(WK_ERR_CAPACITY,
+                "more than %llu subjects or %llu samples: use the host reader",
+                (unsigned long long)(kInternCap[0] / 2),
+                (unsigned long long)(kInternCap[1] / 2));
+  return WK_OK;
 }
 
 }  // extern "C"
