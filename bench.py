@@ -194,6 +194,60 @@ def python_port_rate(case, entries, flags, q, s, m=200_000):
                       f'reference\'s data structures)'}
 
 
+def text_e2e(case, entries, flags, q, s, n_samples, m=2_000_000):
+    """Same plan fed from SAM TEXT in host memory (the form the reference
+    reads): wk_parse_text + wk_classify_parsed on the first m records of the
+    batch, checked against the column-fed result of the same records."""
+    from woltka_b200.engine import Engine
+    from tests import cases as C
+    m = min(m, len(q))
+    while 0 < m < len(q) and q[m] == q[m - 1]:
+        m += 1
+    q, s = q[:m], s[:m]
+    tax = case.tax
+    gid = [tax.genome_id(g).encode() for g in range(tax.n_genomes)]
+    tail = b'\t1\t42\t150M\t*\t0\t0\t' + b'A' * 50 + b'\t' + b'I' * 50 + b'\n'
+    text = b''.join(b'r%d\t0\t%s%s' % (qi, gid[si], tail)
+                    for qi, si in zip(q.tolist(), s.tolist()))
+    from woltka_b200.engine import pinned_empty
+    nbytes = len(text)
+    ptext = pinned_empty(nbytes, np.uint8)     # the file block, read into pinned memory
+    ptext[:] = np.frombuffer(text, dtype=np.uint8)
+    text = ptext
+    kinds, tab, _ = case.tables(entries)
+    eng = Engine(0)
+    eng.set_tree(case.ft.parent, 0)
+    eng.set_plan(kinds, flags, 0.8, n_samples, case.NF)
+    # subjects get their index in order of appearance: parse once to learn it
+    _, _, n_sub, _ = eng.parse_sam(text)
+    names = eng.fetch_names(0, 0, n_sub)
+    order = np.array([int(x[1:]) for x in names], dtype=np.int64)
+    eng.set_subjects(np.ascontiguousarray(tab[:, order]),
+                     np.ascontiguousarray(case.sub_node[order]))
+    for _ in range(2):
+        eng.reset_counts()
+        eng.parse_sam(text)
+        eng.classify_parsed(None, 0)
+        got = eng.fetch_counts()
+    t0 = time.perf_counter()
+    K = 5
+    for _ in range(K):
+        eng.reset_counts()
+        eng.parse_sam(text)
+        eng.classify_parsed(None, 0)
+        got = eng.fetch_counts()
+    dt = (time.perf_counter() - t0) / K
+    ref = Engine(0)
+    exp = C.run_engine(ref, case, entries, flags, 0.8, q, s, n_samples=n_samples)[0]
+    ref.close()
+    eng.close()
+    return {'value': m / dt, 'unit': UNIT, 'records': int(m),
+            'text_bytes': nbytes, 'ms': dt * 1e3,
+            'matches_column_fed_result': bool(np.array_equal(got, exp)),
+            'api': 'wk_parse_text(host SAM text) + wk_classify_parsed + '
+                   'wk_fetch_counts (text in pinned host memory, H2D inside)'}
+
+
 def run_reference(args):
     """CPU arm: the oracle port of the reference's path, all host threads."""
     rank = int(os.environ.get('RANK', '0'))
@@ -446,6 +500,11 @@ def run_ours(args):
                'python_port': python_port_rate(case, entries, flags, qh, sh)}
         assert parity, 'GPU result differs from the oracle on the sample'
 
+    text = None
+    if rank == 0 and world == 1 and not args.no_e2e and qs is None:
+        text = text_e2e(case, entries, flags, q[:2_100_000].cpu().numpy(),
+                        s[:2_100_000].cpu().numpy(), S_all)
+
     if rank == 0:
         achieved = bytes_per_rec * n / (k_ms * 1e-3) / 1e9
         line = {
@@ -466,6 +525,8 @@ def run_ours(args):
             'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
             'clocks': clocks, 'parity_on_sample': parity,
         }
+        if text is not None:
+            line['e2e_from_text'] = text
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

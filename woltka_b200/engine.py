@@ -277,11 +277,16 @@ class Engine:
         """Parse a chunk of alignment text (bytes; SAM body or b6o / paf /
         map lines); returns (n_rec, n_qry, n_subjects_total,
         n_samples_total)."""
-        buf = text if isinstance(text, bytes) else bytes(text)
+        if isinstance(text, np.ndarray):      # e.g. pinned_empty(n, np.uint8)
+            buf = np.ascontiguousarray(text, dtype=np.uint8)
+            ptr, nbytes = C.c_void_p(buf.ctypes.data), buf.nbytes
+        else:
+            buf = text if isinstance(text, bytes) else bytes(text)
+            ptr, nbytes = C.cast(C.c_char_p(buf), C.c_void_p), len(buf)
         n_rec, n_qry = C.c_int64(), C.c_int64()
         n_sub, n_smp = C.c_int32(), C.c_int32()
         _lib.check(self.lib.wk_parse_text(
-            self.ctx, C.cast(C.c_char_p(buf), C.c_void_p), len(buf),
+            self.ctx, ptr, nbytes,
             self.FORMATS[fmt], int(bool(demux)),
             C.byref(n_rec), C.byref(n_qry), C.byref(n_sub), C.byref(n_smp)))
         return n_rec.value, n_qry.value, n_sub.value, n_smp.value
