@@ -368,17 +368,24 @@ __global__ void __launch_bounds__(SW_NT, 1)
               uint32_t code = lds16(row + svc * 2u);
               // set semantics (align.py:339): signature of the query's
               // subjects, exact look-back only when the bit is already taken
-              const uint32_t b = 1u << (sv & 31u);
+              // (--uniq and --above do not need it at a rank: a repeat carries
+              // the value of its first occurrence, so the all-equal test, the
+              // LCA and `nvalid != k` come out the same with repeats counted)
+              constexpr bool DEDUP =
+                  !(KIND == WK_KIND_RANK && (MODE == FX_UNIQ || MODE == FX_ABOVE));
               bool nd = true;
-              if (sig & b) {
-                uint32_t j = a;
+              if (DEDUP) {
+                const uint32_t b = 1u << (sv & 31u);
+                if (sig & b) {
+                  uint32_t j = a;
 #pragma unroll 1
-                do {
-                  if ((uint32_t)lds32(j + SCOL) == sv) nd = false;
-                  j += 4u;
-                } while (j < x);
+                  do {
+                    if ((uint32_t)lds32(j + SCOL) == sv) nd = false;
+                    j += 4u;
+                  } while (j < x);
+                }
+                sig |= b;
               }
-              sig |= b;
               const bool ishead = x == a;
               if (ishead) t0 = code;
               if (nd) {
