@@ -11,7 +11,7 @@ A step is one pass of the hot path over one batch of synthetic records
 already resident in HBM; `e2e` goes through the reference-facing C-ABI call
 with pinned HOST buffers (H2D of the columns and D2H of the count table inside
 the timed region).  Every rank works on its own batch (weak scaling); the
-per-rank count tables are merged by one NCCL all-reduce per step.
+per-rank count tables are merged by one NCCL reduce to rank 0 per step.
 """
 import argparse
 import json
@@ -392,7 +392,7 @@ def run_ours(args):
         eng.reset_counts()
         classify_dev()
         if world > 1:
-            dist.all_reduce(counts)
+            dist.reduce(counts, dst=0)
 
     for _ in range(args.warmup):
         step()
@@ -412,7 +412,7 @@ def run_ours(args):
         classify_dev()
         k_ev[i][1].record()
         if world > 1:
-            dist.all_reduce(counts)
+            dist.reduce(counts, dst=0)
     t_end.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -451,7 +451,7 @@ def run_ours(args):
             eng.reset_counts()
             eng.classify_chunk(hq, hs, hqs, None, smp)      # H2D inside
             if world > 1:
-                dist.all_reduce(counts)
+                dist.reduce(counts, dst=0)
             res = eng.fetch_counts()        # D2H of the count table
         b1.record()
         barrier()
@@ -553,7 +553,7 @@ def run_ours_cfg3(args, eng, dev, world, rank, barrier, hbm_peak, peak_src):
         eng.reset_counts()
         eng.ordinal_device(ptrs, n, 0.8)
         if world > 1:
-            dist.all_reduce(counts)
+            dist.reduce(counts, dst=0)
 
     for _ in range(args.warmup):
         step()
@@ -573,7 +573,7 @@ def run_ours_cfg3(args, eng, dev, world, rank, barrier, hbm_peak, peak_src):
         eng.ordinal_device(ptrs, n, 0.8)
         k_ev[i][1].record()
         if world > 1:
-            dist.all_reduce(counts)
+            dist.reduce(counts, dst=0)
     t_end.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -602,7 +602,7 @@ def run_ours_cfg3(args, eng, dev, world, rank, barrier, hbm_peak, peak_src):
             eng.reset_counts()
             eng.ordinal_chunk(*host, 0.8)
             if world > 1:
-                dist.all_reduce(counts)
+                dist.reduce(counts, dst=0)
             res = eng.fetch_counts()
         barrier()
         ems = (time.perf_counter() - t0) * 1e3

@@ -6,7 +6,8 @@ input, run independent jobs, `woltka merge` the tables"
 (/root/reference/doc/perform.md:70-92; tools.merge_wf sums cells).  Counts are
 additive over any partition of the queries, so the same holds here: each rank
 classifies its shard into its own units table and the tables are summed by
-one NCCL all-reduce over NVLink (int64, exact).
+one NCCL reduce to rank 0 (or all-reduce when every rank wants the merged
+table) over NVLink (int64, exact).
 """
 import numpy as np
 
@@ -33,4 +34,14 @@ def allreduce_counts(tensor):
     if dist.is_available() and dist.is_initialized() and \
             dist.get_world_size() > 1:
         dist.all_reduce(tensor, op=dist.ReduceOp.SUM)
+    return tensor
+
+
+def reduce_counts(tensor, dst=0):
+    """Sum the per-rank units tables into rank `dst` (the single NCCL reduce
+    that replaces `woltka merge`); no-op for a single rank."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and \
+            dist.get_world_size() > 1:
+        dist.reduce(tensor, dst=dst, op=dist.ReduceOp.SUM)
     return tensor
