@@ -370,3 +370,33 @@ def test_short_runs_and_fewer_warps(engine, small_case, monkeypatch, r, block):
             assert engine.last_kernel() == 'classify_fast_kernel'
     finally:
         engine.set_tuning(0, 0, 0)
+
+
+def test_randomised_shapes_both_kernels_agree(engine, small_case):
+    """Many small random streams whose sizes straddle the warp-tile and run
+    boundaries (32 x 13 = 416 records, runs of 13), with long queries and
+    repeats placed at random: run-per-lane kernel == window kernel == oracle."""
+    rng = np.random.default_rng(2026)
+    ents = (['genus'], ['none'], ['phylum', 'species'])
+    modes = ('default', 'uniq', 'major', 'above', 'major+unassigned')
+    for it in range(40):
+        nq = int(rng.choice([1, 3, 40, 200, 205, 416, 420, 832, 1000, 3000]))
+        p = float(rng.choice([0.2, 0.48, 0.9]))
+        every = int(rng.choice([0, 7, 50]))
+        q, s = cases.random_hits(small_case, nq, seed=1000 + it, kmax=45, p=p,
+                                 long_every=every,
+                                 long_len=int(rng.choice([38, 40, 41, 43, 90])),
+                                 window=int(rng.choice([2, 20, 400])))
+        ent = ents[it % len(ents)]
+        mode = modes[it % len(modes)]
+        fl = cases.MODES[mode]
+        th = float(rng.choice([0.5, 0.51, 0.8]))
+        exp = cases.run_oracle(small_case, ent, fl, th, q, s)
+        got = cases.run_engine(engine, small_case, ent, fl, th, q, s)
+        assert engine.last_kernel() == 'classify_fast_kernel'
+        _same(got, exp)
+        engine.set_tuning(0, 1, 0)
+        try:
+            _same(cases.run_engine(engine, small_case, ent, fl, th, q, s), exp)
+        finally:
+            engine.set_tuning(0, 0, 0)

@@ -838,7 +838,8 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   P.seg_list = nullptr;
   P.skip_flag = nullptr;
   if (c->tune_block != 1 && same_kind && staged && !dqstrat && c->tune_cache == 0 &&
-      dir_cells != 0xFFFFFFFFu && !n_dev && !P.assign && !getenv("WK_NO_FAST")) {
+      dir_cells != 0xFFFFFFFFu && !n_dev && !P.assign && !getenv("WK_NO_FAST") &&
+      r1 - r0 < (1ll << 31) - (1 << 20)) {  // its tile counters are 32-bit
     int NTmax = c->tune_block;
     if (NTmax < 64 || NTmax > SW_NT) NTmax = SW_NT;
     NTmax &= ~31;
