@@ -30,7 +30,7 @@
 
 namespace wk {
 
-constexpr int ORD_NT = 512;
+constexpr int ORD_NT = 256;
 constexpr int ORD_ITEMS = 4;
 constexpr int ORD_TILE = ORD_NT * ORD_ITEMS;
 
@@ -91,7 +91,7 @@ __device__ __forceinline__ void ord_scan(const OrdParams &P, const ReadQ &r,
   }
 }
 
-__global__ void __launch_bounds__(ORD_NT, 2)
+__global__ void __launch_bounds__(ORD_NT, 4)
     ordinal_match_kernel(const __grid_constant__ OrdParams P) {
   __shared__ int s_warp[ORD_NT / 32];
   __shared__ long long s_base;
