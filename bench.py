@@ -644,7 +644,7 @@ def run_ours_cfg3(args, eng, dev, world, rank, barrier, hbm_peak, peak_src):
                          'peak': hbm_peak, 'unit': 'GB/s',
                          'frac': achieved / hbm_peak,
                          'traffic': measured_traffic('ordinal:cfg3', n),
-                         'kernel': 'ordinal_match_kernel+classify_kernel',
+                         'kernel': 'ordinal_match_kernel+' + eng.last_kernel(),
                          'kernel_ms': k_ms, 'peak_source': peak_src,
                          'algorithmic_bytes_per_record': 20,
                          'algorithmic_bytes_per_gene': 8},

@@ -400,3 +400,31 @@ def test_randomised_shapes_both_kernels_agree(engine, small_case):
             _same(cases.run_engine(engine, small_case, ent, fl, th, q, s), exp)
         finally:
             engine.set_tuning(0, 0, 0)
+
+
+@pytest.mark.parametrize('NF', [5000, 3_000_000])
+@pytest.mark.parametrize('mode', ['default', 'uniq+unassigned'])
+def test_rank_none_without_a_table(engine, mode, NF):
+    """feature == subject (KIND_NONE_ID: an OGU table, or genes of the ordinal
+    path): the run-per-lane kernel with 24-bit codes, counts in the private
+    table when it fits (NF = 5000) and straight to global memory when it does
+    not (NF = 3e6)."""
+    from oracle import oracle as O
+    from woltka_b200._lib import KIND_NONE_ID
+    rng = np.random.default_rng(NF)
+    nq = 40000
+    k = np.minimum(rng.geometric(0.4, nq), 20)
+    k[::997] = 75                                   # long queries
+    q = np.repeat(np.arange(nq, dtype=np.int32), k)
+    first = rng.integers(0, NF, nq)
+    s = ((first[q] + rng.integers(0, 6, len(q)) * 65537) % NF).astype(np.int32)
+    kinds = np.array([KIND_NONE_ID], dtype=np.int32)
+    fl = cases.MODES[mode]
+    engine.set_plan(kinds, fl, 0.0, 2, NF)
+    engine.set_subjects(None, None, NF)
+    engine.classify_chunk(q, s, None, None, 1)
+    assert engine.last_kernel() == 'classify_fast_kernel'
+    got = cases.collect(engine, 2, NF)
+    exp = O.classify(q, s, kinds=kinds, flags=fl, n_samples=2, n_features=NF,
+                     sample=1, n_threads=4)
+    _same(got, exp)

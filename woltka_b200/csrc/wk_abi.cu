@@ -290,6 +290,10 @@ int wk_create(int device, wk_ctx **out) {
         (const void *)classify_fast_kernel<WK_KIND_NONE, FX_FRAC, 5, true>,
         (const void *)classify_fast_kernel<WK_KIND_NONE, FX_UNIQ, 5, false>,
         (const void *)classify_fast_kernel<WK_KIND_NONE, FX_UNIQ, 5, true>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE_ID, FX_FRAC, 5, false>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE_ID, FX_FRAC, 5, true>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE_ID, FX_UNIQ, 5, false>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE_ID, FX_UNIQ, 5, true>,
         (const void *)classify_fast_kernel<WK_KIND_RANK, FX_FRAC, 9, false>,
         (const void *)classify_fast_kernel<WK_KIND_RANK, FX_FRAC, 9, true>,
         (const void *)classify_fast_kernel<WK_KIND_RANK, FX_UNIQ, 9, false>,
@@ -302,6 +306,10 @@ int wk_create(int device, wk_ctx **out) {
         (const void *)classify_fast_kernel<WK_KIND_NONE, FX_FRAC, 9, true>,
         (const void *)classify_fast_kernel<WK_KIND_NONE, FX_UNIQ, 9, false>,
         (const void *)classify_fast_kernel<WK_KIND_NONE, FX_UNIQ, 9, true>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE_ID, FX_FRAC, 9, false>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE_ID, FX_FRAC, 9, true>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE_ID, FX_UNIQ, 9, false>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE_ID, FX_UNIQ, 9, true>,
         (const void *)classify_fast_kernel<WK_KIND_RANK, FX_FRAC, 13, false>,
         (const void *)classify_fast_kernel<WK_KIND_RANK, FX_FRAC, 13, true>,
         (const void *)classify_fast_kernel<WK_KIND_RANK, FX_UNIQ, 13, false>,
@@ -313,7 +321,11 @@ int wk_create(int device, wk_ctx **out) {
         (const void *)classify_fast_kernel<WK_KIND_NONE, FX_FRAC, 13, false>,
         (const void *)classify_fast_kernel<WK_KIND_NONE, FX_FRAC, 13, true>,
         (const void *)classify_fast_kernel<WK_KIND_NONE, FX_UNIQ, 13, false>,
-        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_UNIQ, 13, true>};
+        (const void *)classify_fast_kernel<WK_KIND_NONE, FX_UNIQ, 13, true>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE_ID, FX_FRAC, 13, false>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE_ID, FX_FRAC, 13, true>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE_ID, FX_UNIQ, 13, false>,
+        (const void *)classify_fast_kernel<WK_KIND_NONE_ID, FX_UNIQ, 13, true>};
     for (const void *fn : fast)
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)c->smem_optin));
@@ -833,13 +845,17 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   // --rank none through a table), staged tables, no strata, no read map; a
   // per-query sample column is accepted when the samples are contiguous.
   // tune_block: 1 = always the window kernel; otherwise threads per CTA
-  bool same_kind = c->kind[0] == WK_KIND_RANK || c->kind[0] == WK_KIND_NONE;
+  bool same_kind = c->kind[0] == WK_KIND_RANK || c->kind[0] == WK_KIND_NONE ||
+                   c->kind[0] == WK_KIND_NONE_ID;
   for (int e = 1; e < c->E; ++e) same_kind &= c->kind[e] == c->kind[0];
   P.seg_list = nullptr;
   P.skip_flag = nullptr;
-  if (c->tune_block != 1 && same_kind && staged && !dqstrat && c->tune_cache == 0 &&
-      dir_cells != 0xFFFFFFFFu && !n_dev && !P.assign && !getenv("WK_NO_FAST") &&
-      r1 - r0 < (1ll << 31) - (1 << 20)) {  // its tile counters are 32-bit
+  P.fast_gsink = 0;
+  const bool wide = c->kind[0] == WK_KIND_NONE_ID;  // feature == subject, no table
+  if (c->tune_block != 1 && same_kind && (wide ? P.V < 0xFFFFFD : staged) &&
+      !dqstrat && c->tune_cache == 0 && !(n_dev && dqsamp) && !P.assign &&
+      !getenv("WK_NO_FAST") &&
+      (n_dev ? n_bound : r1 - r0) < (1ll << 31) - (1 << 20)) {  // 32-bit tile counters
     int NTmax = c->tune_block;
     if (NTmax < 64 || NTmax > SW_NT) NTmax = SW_NT;
     NTmax &= ~31;
@@ -855,9 +871,13 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
     // (run length, warps) for entries [e0, e0+en): long runs first (fewer
     // records walked twice at run ends), then as many warps as fit
     struct Shape { int R, NW; };
+    // counts straight to global memory when the private table cannot fit
+    // (--rank none over millions of genes)
+    bool gsink = dir_cells == 0xFFFFFFFFu;
     auto pick = [&](int e0, int en) {
-      const uint32_t cells = (uint32_t)(P.dir_base[e0 + en] - P.dir_base[e0]);
-      const int64_t tb = (int64_t)en * c->Vp * 2 + par_bytes;
+      const uint32_t cells =
+          gsink ? 0u : (uint32_t)(P.dir_base[e0 + en] - P.dir_base[e0]);
+      const int64_t tb = wide ? 0 : (int64_t)en * c->Vp * 2 + par_bytes;
       for (int r : {13, 9})
         for (int nw : {32, 28, 24})
           if (r <= rmax && nw * 32 <= NTmax &&
@@ -872,6 +892,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
     // all entries in one launch when that leaves room for runs of 13 (or the
     // plan is one entry); otherwise one launch per entry
     int group = c->E;
+    if (!gsink && wide && pick(0, c->E).R < 13) gsink = true;
     int FR = par_ok ? pick(0, c->E).R : 0;
     if (par_ok && c->E > 1 && FR < 13) {
       int worst = 13;
@@ -881,10 +902,11 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
         FR = worst;
       }
     }
-    const int64_t span = r1 - (r0 & ~3ll);
+    const int64_t span = n_dev ? n_bound : r1 - (r0 & ~3ll);
     if (span <= 0) return WK_OK;
     if (FR) {
       const bool multi = !lean;
+      P.fast_gsink = gsink ? 1 : 0;
       if (dqsamp) {
         // where the sample of the stream changes (device side, no host sync)
         TRY(c->seglist.reserve(sizeof(SegList)));
@@ -902,9 +924,9 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
         P.e_hi = e0 + group;
         const Shape sh = pick(e0, group);
         const int R1 = sh.R, NW = sh.NW, NT = sh.NW * 32;
-        const SwSmemLayout FL =
-            sw_layout(NW, R1, (uint32_t)(P.dir_base[e0 + group] - P.dir_base[e0]),
-                      (int64_t)group * c->Vp * 2 + par_bytes);
+        const SwSmemLayout FL = sw_layout(
+            NW, R1, gsink ? 0u : (uint32_t)(P.dir_base[e0 + group] - P.dir_base[e0]),
+            wide ? 0 : (int64_t)group * c->Vp * 2 + par_bytes);
         const int64_t ft = (span + 32ll * R1 - 1) / (32ll * R1);
         const int fgrid = (int)std::min<int64_t>(grid, (ft + NW - 1) / NW);
 #define WK_FAST4(KD, MD, RR, MU) \
@@ -925,6 +947,9 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
           else if (mode == FX_ABOVE) WK_FAST2(WK_KIND_RANK, FX_ABOVE);
           else if (mode == FX_UNIQ) WK_FAST2(WK_KIND_RANK, FX_UNIQ);
           else WK_FAST2(WK_KIND_RANK, FX_FRAC);
+        } else if (wide) {
+          if (mode == FX_UNIQ) WK_FAST2(WK_KIND_NONE_ID, FX_UNIQ);
+          else WK_FAST2(WK_KIND_NONE_ID, FX_FRAC);
         } else {
           if (mode == FX_UNIQ) WK_FAST2(WK_KIND_NONE, FX_UNIQ);
           else WK_FAST2(WK_KIND_NONE, FX_FRAC);
@@ -937,6 +962,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
       }
       P.e_lo = 0;
       P.e_hi = c->E;
+      P.fast_gsink = 0;
       c->last_kernel = "classify_fast_kernel";
       if (!dqsamp) return WK_OK;
       // interleaved samples (more than FX_MAX_SEG changes): the kernel above

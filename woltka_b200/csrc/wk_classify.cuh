@@ -100,6 +100,7 @@ struct ClsParams {
   int32_t e_lo, e_hi;         // entries this launch works on (process_long, fast kernel)
   const void *seg_list;       // classify_fast_kernel<MULTI>: SegList of the stream, or null
   const int32_t *skip_flag;   // classify_kernel: do nothing if *skip_flag >= 0
+  int32_t fast_gsink;         // classify_fast_kernel: no private table, global reductions
 };
 
 enum { ERR_BAD_SUBJECT = 1, ERR_OVF_FULL = 2, ERR_HASH_FULL = 4,

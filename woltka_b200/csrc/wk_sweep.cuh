@@ -129,8 +129,11 @@ enum { FX_FRAC = 0, FX_UNIQ = 1, FX_MAJOR = 2, FX_ABOVE = 3 };
 // run again; called only when some lane of the warp met such a record.
 __device__ __noinline__ void fx_slow_emit(const ClsParams &P, int e, int sample,
                                           uint32_t em, uint32_t first,
-                                          uint32_t stop) {
-  const uint32_t off = (uint32_t)P.dir_off[e], wid = (uint32_t)P.dir_w[e];
+                                          uint32_t stop, bool wide, bool gsink) {
+  const uint32_t off = (uint32_t)P.dir_off[e], wid = gsink ? 0u : (uint32_t)P.dir_w[e];
+  const uint32_t c_mask = wide ? 0xFFFFFFu : FX_CODE;
+  const uint32_t c_unas = wide ? 0xFFFFFEu : FX_UNAS;
+  const uint32_t c_vend = wide ? 0xFFFFFDu : FX_NONE;  // values are below this
   uint32_t d = 0, u = 0;
 #pragma unroll 1
   for (uint32_t yo = first; yo < stop; yo += 4u) {
@@ -139,14 +142,14 @@ __device__ __noinline__ void fx_slow_emit(const ClsParams &P, int e, int sample,
       d = ((uint32_t)w >> 24) & 63u;
       u = c_units64[d];
     }
-    const uint32_t code = (uint32_t)w & FX_CODE;
-    const bool isun = code == FX_UNAS;
-    if (!(w < 0 || d != 0) || !(code < FX_NONE || isun)) continue;
-    const bool inr = isun || code - off < wid;
+    const uint32_t code = (uint32_t)w & c_mask;
+    const bool isun = code == c_unas;
+    if (!(w < 0 || d != 0) || !(code < c_vend || isun)) continue;
+    const bool inr = !gsink && (isun || code - off < wid);
     const int64_t f = isun ? P.NF1 - 1 : (int64_t)code;
     if (!u)
       fx_overflow(P, e, sample, f, (int)d);
-    else if (!inr)
+    else if (!inr && !gsink)
       atomicAdd(P.cnt + ((int64_t)e * P.S + sample) * P.NF1 + f, (ull)u);
   }
 }
@@ -232,15 +235,24 @@ __global__ void __launch_bounds__(SW_NT, 1)
   constexpr int TBUF = WT + SW_PRE + SW_POST;
   constexpr uint32_t SCOL = (uint32_t)TBUF * 4u;  // subject column after the query column
   constexpr uint32_t ECOL = 2u * SCOL;            // scratch column
+  // --rank none without a table (feature == subject): 24-bit codes, no rows
+  constexpr bool WIDE = KIND == WK_KIND_NONE_ID;
+  constexpr uint32_t C_NONE = WIDE ? 0xFFFFFFu : FX_NONE;
+  constexpr uint32_t C_UNAS = WIDE ? 0xFFFFFEu : FX_UNAS;
+  constexpr uint32_t C_DUP = WIDE ? 0xFFFFFDu : FX_DUP;
+  constexpr uint32_t C_MASK = WIDE ? 0xFFFFFFu : FX_CODE;
+  constexpr uint32_t C_VEND = WIDE ? C_DUP : C_NONE;  // values are below this
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int NW = blockDim.x >> 5;
   // this launch: entries [e_lo, e_hi), their rows (+ the parent array for
   // --above) staged as uint16, their slice of the private count table
   const int e_lo = MULTI ? P.e_lo : 0;
   const int E = MULTI ? P.e_hi - P.e_lo : 1;
-  const uint32_t cells = (uint32_t)(P.dir_base[e_lo + E] - P.dir_base[e_lo]);
+  const bool gsink = P.fast_gsink != 0;  // counts straight to the global table
+  const uint32_t cells =
+      gsink ? 0u : (uint32_t)(P.dir_base[e_lo + E] - P.dir_base[e_lo]);
   const bool need_par = KIND == WK_KIND_RANK && MODE == FX_ABOVE;
-  const uint32_t rows_bytes = (uint32_t)E * (uint32_t)P.Vp * 2u;
+  const uint32_t rows_bytes = WIDE ? 0u : (uint32_t)E * (uint32_t)P.Vp * 2u;
   const uint32_t par_bytes = need_par ? (((uint32_t)P.T + 7u) & ~7u) * 2u : 0u;
   const SwSmemLayout L = sw_layout(NW, R, cells, (int64_t)rows_bytes + par_bytes);
   const uint32_t sbase32 = smem_u32(smem);
@@ -253,6 +265,9 @@ __global__ void __launch_bounds__(SW_NT, 1)
   const SegList *SG = MULTI ? reinterpret_cast<const SegList *>(P.seg_list) : nullptr;
   const int nseg = SG ? SG->nseg : 1;
   if (nseg < 0) return;  // interleaved samples: classify_kernel does this chunk
+  if (*P.err & ERR_PAIR_FULL) return;  // upstream stage overflowed: do nothing
+  // ordinal pairs: the record count lives in device memory
+  const int64_t n_all = P.n_dev ? (int64_t)*P.n_dev : P.n;
 
   if (lane == 0) mbar_init(mybar, 1);
   if (tid == 0) {
@@ -261,7 +276,7 @@ __global__ void __launch_bounds__(SW_NT, 1)
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
-  if (tid == 0) {
+  if (tid == 0 && rows_bytes + par_bytes) {
     mbar_expect_tx(tabbar, rows_bytes + par_bytes);
     bulk_g2s(stab, P.tab16 + (size_t)e_lo * P.Vp, rows_bytes, tabbar);
     if (need_par) bulk_g2s(stab + rows_bytes, P.tab16 + P.par16_off, par_bytes, tabbar);
@@ -269,10 +284,10 @@ __global__ void __launch_bounds__(SW_NT, 1)
 #pragma unroll 1
   for (uint32_t h = tid; h < cells; h += blockDim.x) sts32(tbl + h * 4, 0);
   __syncthreads();
-  mbar_wait(tabbar, 0);
+  if (rows_bytes + par_bytes) mbar_wait(tabbar, 0);
 
   const uint32_t V32 = (uint32_t)P.V;  // the staged rows have a 'none' pad slot at V
-  const uint32_t unas_code = (P.flags & WK_F_UNASSIGNED) ? FX_UNAS : FX_NONE;
+  const uint32_t unas_code = (P.flags & WK_F_UNASSIGNED) ? C_UNAS : C_NONE;
   const uint32_t badflag = tabbar + 8u;
   const int GW = (int)gridDim.x * NW;
   const int gw = (int)blockIdx.x * NW + warp;
@@ -283,8 +298,8 @@ __global__ void __launch_bounds__(SW_NT, 1)
 
 #pragma unroll 1
   for (int sg = 0; sg < nseg; ++sg) {
-    const int64_t r0 = SG ? SG->at[sg] : P.r0;
-    const int64_t r1 = SG ? SG->at[sg + 1] : P.r1;
+    const int64_t r0 = SG ? SG->at[sg] : (P.n_dev ? 0 : P.r0);
+    const int64_t r1 = SG ? SG->at[sg + 1] : (P.n_dev ? n_all : P.r1);
     const int sample = SG ? SG->sample[sg] : P.sample;
     if ((unsigned)sample >= (unsigned)P.S) continue;  // dropped sample (CTA-uniform)
     const int64_t tb0 = r0 & ~3ll;
@@ -295,7 +310,7 @@ __global__ void __launch_bounds__(SW_NT, 1)
       const int64_t tb = tb0 + (int64_t)tile * WT;
       const int64_t g0 = tb >= SW_PRE ? tb - SW_PRE : 0;
       int64_t g1 = tb + WT + SW_POST;
-      if (g1 > P.n) g1 = P.n;
+      if (g1 > n_all) g1 = n_all;
       const uint32_t bytes = (uint32_t)(((g1 - g0) * 4 + 15) & ~15ll);
       const uint32_t dq = aq + (uint32_t)(g0 - (tb - SW_PRE)) * 4u;
       mbar_expect_tx(mybar, 2 * bytes);
@@ -316,7 +331,7 @@ __global__ void __launch_bounds__(SW_NT, 1)
         // end of the column, and plant the sentinels (record 0 of the column
         // starts a query, the last one ends one)
         const int64_t sbase = tb0 + (int64_t)tile * WT - SW_PRE;
-        const int nrel = (int)(P.n - sbase < TBUF ? P.n - sbase : TBUF);
+        const int nrel = (int)(n_all - sbase < TBUF ? n_all - sbase : TBUF);
         if (lane == 0) {
           if (sbase + SW_PRE == 0)
             sts32(aq + SW_PRE * 4u - 4u, ~(uint32_t)lds32(aq + SW_PRE * 4u));
@@ -365,7 +380,11 @@ __global__ void __launch_bounds__(SW_NT, 1)
               const int qn = lds32(x + 4u);
               const uint32_t svc = min(sv, V32);
               if (sv != svc) sts32(badflag, 1u);
-              uint32_t code = lds16(row + svc * 2u);
+              uint32_t code;
+              if (WIDE)
+                code = sv < V32 ? sv : C_NONE;  // the subject is the feature
+              else
+                code = lds16(row + svc * 2u);
               // set semantics (align.py:339): signature of the query's
               // subjects, exact look-back only when the bit is already taken
               // (--uniq and --above do not need it at a rank: a repeat carries
@@ -390,13 +409,13 @@ __global__ void __launch_bounds__(SW_NT, 1)
               if (ishead) t0 = code;
               if (nd) {
                 neq |= code ^ t0;
-                nvalid += (code != FX_NONE);
+                nvalid += (code != C_NONE);
                 ++k;
                 if (KIND == WK_KIND_RANK && MODE == FX_ABOVE) {
                   // tree.find_lca (tree.py:513-566), folded as the records pass
                   if (ishead)
                     acc = code;
-                  else if (code != acc && code != FX_NONE && acc != FX_NONE)
+                  else if (code != acc && code != C_NONE && acc != C_NONE)
                     acc = (uint32_t)lca2(TR, (int)acc, (int)code);
                 }
                 if (KIND == WK_KIND_RANK && MODE == FX_MAJOR) {
@@ -409,7 +428,7 @@ __global__ void __launch_bounds__(SW_NT, 1)
                   }
                 }
               } else {
-                code = FX_DUP;
+                code = C_DUP;
               }
               sts32(x + ECOL, code | (ishead ? EM_HEAD : 0u));
               x += 4u;
@@ -421,7 +440,7 @@ __global__ void __launch_bounds__(SW_NT, 1)
                   if (MODE == FX_FRAC) {
                     if (neq) d = nvalid;  // 1/k' per subject with a taxon
                   } else if (MODE == FX_UNIQ) {
-                    if (neq) r = FX_NONE;
+                    if (neq) r = C_NONE;
                   } else if (MODE == FX_MAJOR) {
                     // classify.majority (classify.py:300-317)
                     if (neq) {
@@ -429,25 +448,25 @@ __global__ void __launch_bounds__(SW_NT, 1)
                         int c = 0;  // occurrences of the candidate
 #pragma unroll 1
                         for (uint32_t j = a; j < x; j += 4u)
-                          c += ((uint32_t)lds32(j + ECOL) & FX_CODE) == acc;
-                        r = ((double)c >= __dmul_rn((double)k, P.major_th)) ? acc : FX_NONE;
+                          c += ((uint32_t)lds32(j + ECOL) & C_MASK) == acc;
+                        r = ((double)c >= __dmul_rn((double)k, P.major_th)) ? acc : C_NONE;
                       } else {
                         r = fx_majority(ECOL, a, x - 4u, (int)k, P.major_th);
                       }
                     }
                   } else {
                     // --above: None if any subject has no taxon, else the LCA
-                    if (neq) r = (nvalid != k || acc == (uint32_t)P.root) ? FX_NONE : acc;
+                    if (neq) r = (nvalid != k || acc == (uint32_t)P.root) ? C_NONE : acc;
                   }
                 } else {
                   // classify.assign_none (classify.py:32-51)
                   if (MODE == FX_FRAC) {
                     if (k > 1) d = k;
                   } else {
-                    if (k > 1) r = FX_NONE;
+                    if (k > 1) r = C_NONE;
                   }
                 }
-                if (d == 0 && r == FX_NONE) r = unas_code;
+                if (d == 0 && r == C_NONE) r = unas_code;
                 sts32(a + ECOL, (d << 24) + (r | EM_HEAD));
                 a = x;
                 sig = 0;
@@ -480,20 +499,27 @@ __global__ void __launch_bounds__(SW_NT, 1)
               d = ((uint32_t)w >> 24) & 63u;
               u = c_units64[d];
             }
-            const uint32_t code = (uint32_t)w & FX_CODE;
-            const bool isun = code == FX_UNAS;
-            const uint32_t slot = isun ? wid : code - off;
-            const bool want = w < 0 || d != 0;    // head, or a 1/k' share
-            const bool inr = slot < wid || isun;  // a value of the private range
-            if (want && inr && u) {
-              const uint32_t old = atoms_add(tlo + slot * 4u, u);
-              if (old + u < old)  // carry out of the 32-bit low word (rare)
-                atomicAdd(crow + (isun ? (uint32_t)(P.NF1 - 1) : code), 1ull << 32);
-            } else if (want && (inr || code < FX_NONE)) {
-              slow = true;  // overflow denominator or out-of-range value
+            const uint32_t code = (uint32_t)w & C_MASK;
+            const bool isun = code == C_UNAS;
+            const bool want = (w < 0 || d != 0) &&    // head, or a 1/k' share
+                              (code < C_VEND || isun);  // of a value
+            if (want) {
+              const uint32_t slot = isun ? wid : code - off;
+              if (!u) {
+                slow = true;  // the denominator does not divide WK_UNITS
+              } else if (gsink) {
+                atomicAdd(crow + (isun ? (uint32_t)(P.NF1 - 1) : code), (ull)u);
+              } else if (slot < wid || isun) {  // a value of the private range
+                const uint32_t old = atoms_add(tlo + slot * 4u, u);
+                if (old + u < old)  // carry out of the 32-bit low word (rare)
+                  atomicAdd(crow + (isun ? (uint32_t)(P.NF1 - 1) : code), 1ull << 32);
+              } else {
+                slow = true;  // a value outside the private range
+              }
             }
           }
-          if (__any_sync(FULL, slow)) fx_slow_emit(P, e, sample, ECOL, first, stop);
+          if (__any_sync(FULL, slow))
+            fx_slow_emit(P, e, sample, ECOL, first, stop, WIDE, gsink);
         }
         if (MULTI) __syncwarp();
       }
@@ -510,7 +536,7 @@ __global__ void __launch_bounds__(SW_NT, 1)
           lm &= lm - 1;
           const uint32_t la = __shfl_sync(FULL, longa, src);
           process_long<false, SINK_GLOBAL>(
-              P, K, 0u, P.n,
+              P, K, 0u, n_all,
               tb0 + (int64_t)tile * WT - SW_PRE + (int64_t)((la - aq) >> 2), lane);
         }
       }
