@@ -33,6 +33,7 @@ namespace wk {
 constexpr int ORD_NT = 256;
 constexpr int ORD_ITEMS = 4;
 constexpr int ORD_TILE = ORD_NT * ORD_ITEMS;
+constexpr int ORD_CAND = 2;  // candidate genes loaded up front per read
 
 struct OrdParams {
   const int32_t *q, *contig, *beg, *end, *len;
@@ -175,11 +176,11 @@ __global__ void __launch_bounds__(ORD_NT, 4)
     rq[j] = ord_prepare(P, cv[j], bv[j], ev[j], lv[j]);
   // first four candidate genes of every read, all loads in flight together
   // (the scan is otherwise a chain of dependent L2 round trips)
-  int2 cand[ORD_ITEMS][4];
+  int2 cand[ORD_ITEMS][ORD_CAND];
 #pragma unroll
   for (int j = 0; j < ORD_ITEMS; ++j)
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < ORD_CAND; ++u) {
       const int g = rq[j].g0 + u;
       cand[j][u] = g < rq[j].g1 ? __ldg(P.genes + g) : make_int2(INT32_MAX, 0);
     }
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(ORD_NT, 4)
     const int64_t y = (int64_t)rq[j].re - rq[j].L;
     bool more = rq[j].g0 < rq[j].g1;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < ORD_CAND; ++u) {
       const int2 ge = cand[j][u];
       if (more && (int64_t)ge.x > y) more = false;  // also ends at the pad
       if (more) {
@@ -204,9 +205,9 @@ __global__ void __launch_bounds__(ORD_NT, 4)
         if (ov >= rq[j].L) hit(rq[j].g0 + u);
       }
     }
-    if (more && rq[j].g0 + 4 < rq[j].g1) {  // rare: keep scanning
+    if (more && rq[j].g0 + ORD_CAND < rq[j].g1) {  // keep scanning
       ReadQ rest = rq[j];
-      rest.g0 += 4;
+      rest.g0 += ORD_CAND;
       ord_scan(P, rest, hit);
     }
     cnt[j] = c;

@@ -38,9 +38,10 @@
 //     separate routine, queries longer than SW_LONGK records are handed to
 //     the warp-cooperative process_long after the sweeps.
 //
-// Scope: ONE entry (a rank, or --rank none through a table), scalar sample,
-// no strata, no read map, tables staged as uint16.  Every other plan takes
-// classify_kernel.
+// Scope: plans whose entries are all of one kind — ranks, --rank none through
+// a table, or --rank none with feature == subject — with a scalar sample or a
+// stream of contiguous samples, no strata, no read map, tables staged as
+// uint16.  Every other plan takes classify_kernel.
 #pragma once
 #include "wk_classify.cuh"
 
