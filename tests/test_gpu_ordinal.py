@@ -172,3 +172,12 @@ def test_queries_straddling_tiles(engine):
                                   n_features=G)
         assert np.array_equal(units, exp)
         assert len(ovf[0]) == len(eovf)
+
+
+@pytest.mark.parametrize('sub', ['1000', '2048', '6004'])
+def test_host_chunk_is_matched_sub_chunk_by_sub_chunk(engine, monkeypatch, sub):
+    """wk_ordinal_chunk copies the columns in sub-chunks and runs the matcher
+    behind the copies; a query that runs over a sub-chunk border stays whole."""
+    monkeypatch.setenv('WK_ORD_SUB', sub)
+    test_queries_straddling_tiles(engine)
+    test_ordinal_then_classify(engine)

@@ -1127,10 +1127,17 @@ int wk_classify_chunk(wk_ctx *c, const int32_t *qidx, const int32_t *sidx,
     CK(cudaEventCreateWithFlags(&evs[j], cudaEventDisableTiming));
     CK(cudaEventRecord(evs[j], c->copy_stream));
   }
+  // a query running over more than one sub-chunk border (longer than SUB
+  // records) needs everything resident before its kernel starts
+  bool all_first = false;
+  for (int64_t j = 0; j + 1 < nsub && !all_first; ++j) {
+    const int64_t b = (j + 1) * SUB, e2 = std::min(n_rec, b + SUB);
+    all_first = e2 < n_rec && qidx[b - 1] == qidx[e2];
+  }
   int rc = WK_OK;
   for (int64_t j = 0; j < nsub && rc == WK_OK; ++j) {
     int64_t a = j * SUB, b = std::min(n_rec, a + SUB);
-    int64_t jn = std::min(nsub - 1, j + 1);
+    int64_t jn = all_first ? nsub - 1 : std::min(nsub - 1, j + 1);
     int64_t nread = std::min(n_rec, (jn + 1) * SUB);
     cudaStreamWaitEvent(c->stream, evs[jn], 0);
     rc = launch_classify(c, c->dq.as<int32_t>(), c->ds.as<int32_t>(), nread,
@@ -1226,11 +1233,17 @@ static int run_ordinal(wk_ctx *c, const int32_t *dq, const int32_t *dcontig,
                        const int32_t *dbeg, const int32_t *dend,
                        const int32_t *dlen, int64_t n_rec, double th,
                        const int32_t *dqs, const int32_t *dqt, int32_t sample,
-                       bool classify) {
+                       bool classify, const std::vector<cudaEvent_t> *copied = nullptr,
+                       int64_t sub = 0, bool all_first = false) {
+  // `copied`: the columns arrive in sub-chunks of `sub` records on the copy
+  // stream (event j = sub-chunk j resident); the matcher runs sub-chunk by
+  // sub-chunk behind the copies.  A query may run into the next sub-chunk,
+  // so launch j waits for copy j+1.
   if (((uintptr_t)dq | (uintptr_t)dcontig | (uintptr_t)dbeg | (uintptr_t)dend |
        (uintptr_t)dlen) & 15)
     return fail(WK_ERR_ARG, "record columns must be 16-byte aligned");
-  const int64_t n_tiles = (n_rec + ORD_TILE - 1) / ORD_TILE;
+  if (!copied || sub <= 0) sub = n_rec;
+  const int64_t nsub = (n_rec + sub - 1) / sub;
   if (c->pair_cap < n_rec + 1024) {
     c->pair_cap = n_rec + (n_rec >> 2) + 1024;
   }
@@ -1249,7 +1262,6 @@ static int run_ordinal(wk_ctx *c, const int32_t *dq, const int32_t *dcontig,
     P.beg = dbeg;
     P.end = dend;
     P.len = dlen;
-    P.n = n_rec;
     P.th = th;
     P.cinfo = c->cinfo.as<int4>();
     P.genes = c->genes.as<int2>();
@@ -1266,7 +1278,14 @@ static int run_ordinal(wk_ctx *c, const int32_t *dq, const int32_t *dcontig,
     P.cap = c->pair_cap;
     P.n_pairs = c->d_n_pairs();
     P.err = c->d_err();
-    {
+    for (int64_t j = 0; j < nsub; ++j) {
+      // all_first: some query is longer than a sub-chunk - wait for everything
+      const int64_t jn = all_first ? nsub - 1 : std::min(nsub - 1, j + 1);
+      if (copied) CK(cudaStreamWaitEvent(c->stream, (*copied)[(size_t)jn], 0));
+      P.r0 = j * sub;
+      P.r1 = std::min(n_rec, P.r0 + sub);
+      P.n = std::min(n_rec, (jn + 1) * sub);
+      const int64_t n_tiles = (P.r1 - P.r0 + ORD_TILE - 1) / ORD_TILE;
       // keep the gene table + bins persisting in L2, stream everything else
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)n_tiles);
@@ -1291,8 +1310,8 @@ static int run_ordinal(wk_ctx *c, const int32_t *dq, const int32_t *dcontig,
       cfg.attrs = attr;
       cfg.numAttrs = nattr;
       CK(cudaLaunchKernelEx(&cfg, ordinal_match_kernel, P));
+      c->launches++;
     }
-    c->launches++;
     CK(cudaGetLastError());
     if (classify)
       TRY(launch_classify(c, c->pair_q.as<int32_t>(), c->pair_s.as<int32_t>(),
@@ -1349,17 +1368,40 @@ int wk_ordinal_chunk(wk_ctx *c, const int32_t *qidx, const int32_t *contig,
   if (classify && q_stratum) TRY(ensure_strata(c, 4 * n_rec * c->E));
   DevBuf *bufs[5] = {&c->dq, &c->dcontig, &c->dbeg, &c->dend, &c->dlen};
   const int32_t *src[5] = {qidx, contig, beg, end, len};
-  for (int i = 0; i < 5; ++i) {
-    TRY(bufs[i]->reserve((size_t)n_rec * 4 + 64));
-    CK(cudaMemcpyAsync(bufs[i]->p, src[i], (size_t)n_rec * 4,
-                       cudaMemcpyHostToDevice, c->stream));
-  }
+  for (int i = 0; i < 5; ++i) TRY(bufs[i]->reserve((size_t)n_rec * 4 + 64));
   const int32_t *dqs = nullptr, *dqt = nullptr;
   if (classify) TRY(upload_per_query(c, q_sample, q_stratum, n_qry, &dqs, &dqt));
-  return run_ordinal(c, c->dq.as<int32_t>(), c->dcontig.as<int32_t>(),
-                     c->dbeg.as<int32_t>(), c->dend.as<int32_t>(),
-                     c->dlen.as<int32_t>(), n_rec, th, dqs, dqt, sample,
-                     classify);
+  // H2D in sub-chunks on the copy stream, the matcher follows one sub-chunk
+  // behind (wk_classify_chunk does the same for the plain path)
+  int64_t SUB = 8ll << 20;
+  if (const char *ev = getenv("WK_ORD_SUB")) SUB = std::max<int64_t>(4, atoll(ev) & ~3ll);
+  const int64_t nsub = (n_rec + SUB - 1) / SUB;
+  CK(cudaEventRecord(c->ev_free, c->stream));
+  CK(cudaStreamWaitEvent(c->copy_stream, c->ev_free, 0));
+  std::vector<cudaEvent_t> evs((size_t)nsub);
+  for (int64_t j = 0; j < nsub; ++j) {
+    const int64_t a = j * SUB, b = std::min(n_rec, a + SUB);
+    for (int i = 0; i < 5; ++i)
+      CK(cudaMemcpyAsync(bufs[i]->as<int32_t>() + a, src[i] + a, (size_t)(b - a) * 4,
+                         cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaEventCreateWithFlags(&evs[(size_t)j], cudaEventDisableTiming));
+    CK(cudaEventRecord(evs[(size_t)j], c->copy_stream));
+  }
+  // a query running over more than one sub-chunk border (longer than SUB
+  // records) needs everything resident before its matcher starts
+  bool all_first = false;
+  for (int64_t j = 0; j + 1 < nsub && !all_first; ++j) {
+    const int64_t b = (j + 1) * SUB, e2 = std::min(n_rec, b + SUB);
+    all_first = e2 < n_rec && qidx[b - 1] == qidx[e2];
+  }
+  const int rc = run_ordinal(c, c->dq.as<int32_t>(), c->dcontig.as<int32_t>(),
+                             c->dbeg.as<int32_t>(), c->dend.as<int32_t>(),
+                             c->dlen.as<int32_t>(), n_rec, th, dqs, dqt, sample,
+                             classify, &evs, SUB, all_first);
+  cudaStreamSynchronize(c->copy_stream);
+  for (auto &e : evs)
+    if (e) cudaEventDestroy(e);
+  return rc;
 }
 
 int wk_ordinal_fetch_pairs(wk_ctx *c, int64_t *n_pairs, int32_t *read_idx,

@@ -37,7 +37,8 @@ constexpr int ORD_CAND = 2;  // candidate genes loaded up front per read
 
 struct OrdParams {
   const int32_t *q, *contig, *beg, *end, *len;
-  int64_t n;
+  int64_t n;                   // records readable in the columns
+  int64_t r0, r1;              // this launch matches the records [r0, r1)
   double th;
   const int4 *cinfo;           // [C] (first bin, n bins, gene end, 0)
   const int2 *genes;           // [G] (gbeg, gend), sorted by gbeg per contig
@@ -98,8 +99,8 @@ __global__ void __launch_bounds__(ORD_NT, 4)
   __shared__ long long s_base;
   __shared__ int s_skip, s_ext, s_ext_tot;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t t0 = (int64_t)blockIdx.x * ORD_TILE;
-  const int64_t t1 = t0 + ORD_TILE < P.n ? t0 + ORD_TILE : P.n;
+  const int64_t t0 = P.r0 + (int64_t)blockIdx.x * ORD_TILE;
+  const int64_t t1 = t0 + ORD_TILE < P.r1 ? t0 + ORD_TILE : P.r1;
 
   // tile ownership by query: skip the records that continue the previous
   // tile's last query, follow our last query past the tile end
