@@ -68,6 +68,9 @@ enum wk_kind {
 #define WK_F_ABOVE 2u      /* --above                                      */
 #define WK_F_MAJOR 4u      /* --major given (threshold in major_th)        */
 #define WK_F_UNASSIGNED 8u /* --unassigned (workflow.py:1038-1039)         */
+#define WK_F_SIZES 16u     /* --sizes: counts keyed by (subject, feature), see
+                              wk_fetch_strata (classify.counter_size,
+                              classify.py:174-213)                          */
 
 typedef struct wk_ctx wk_ctx;
 
@@ -180,7 +183,11 @@ int wk_fetch_counts(wk_ctx *ctx, int64_t *units);
  * Call with cell == NULL to get the count. */
 int wk_fetch_overflow(wk_ctx *ctx, int64_t *n, int64_t *cell, int32_t *stratum,
                       int32_t *den, int64_t cap);
-/* Stratified counts: (entry, sample, stratum, feature) -> units. */
+/* Stratified counts: (entry, sample, stratum, feature) -> units.  With
+ * WK_F_SIZES the 'stratum' is the SUBJECT index: the units every subject
+ * contributed to every feature (1/k per subject of a uniquely assigned query,
+ * 1/k' per listed subject otherwise); the caller multiplies by the subject's
+ * weight (workflow.parse_sizes, workflow.py:588-633). */
 int wk_fetch_strata(wk_ctx *ctx, int64_t *n, int32_t *entry, int32_t *sample,
                     int32_t *stratum, int64_t *feature, int64_t *units,
                     int64_t cap);

@@ -124,6 +124,24 @@ def tally(queries, results, strata=None):
     return res
 
 
+def tally_sized(subjects, results, sizes):
+    """classify.counter_size (classify.py:174-213): a uniquely assigned query
+    adds the mean weight of its subjects, a list adds weight / k' per listed
+    subject; a subject without a weight is a KeyError."""
+    res = defaultdict(int)
+    for subs, taxa in zip(subjects, results):
+        if not taxa:
+            continue
+        if isinstance(taxa, list):
+            share = 1 / len([t for t in taxa if t])
+            for t, sub in zip(taxa, subs):
+                if t:
+                    res[t] += sizes[sub] * share
+        else:
+            res[taxa] += sum(sizes[x] for x in subs) / len(subs)
+    return res
+
+
 # ---- workflow.py ---------------------------------------------------------------
 def split_by_sample(qryque, subque, samples=None):
     """workflow.demultiplex (workflow.py:844-909)."""
@@ -162,7 +180,8 @@ def readmap_lines(queries, results, namedic=None):
 def classify_chunks(chunks, ranks, tree=None, rankdic=None, root=None,
                     uniq=False, major=None, above=False, subok=False,
                     unasgd=False, demux=False, samples=None, sample=None,
-                    trimsub=None, strata_of=None, maps=None, namedic=None):
+                    trimsub=None, strata_of=None, maps=None, namedic=None,
+                    sizes=None):
     """workflow.classify body (workflow.py:304-335, 1017-1058) over an
     iterable of (qryque, subque) chunks; `major` is the fraction."""
     data = {r: {} for r in ranks}
@@ -184,7 +203,8 @@ def classify_chunks(chunks, ranks, tree=None, rankdic=None, root=None,
                 if maps is not None:
                     maps.setdefault(rank, {}).setdefault(sname, []).extend(
                         readmap_lines(qs, res, namedic))
-                counts = tally(qs, res, strata)
+                counts = tally(qs, res, strata) if sizes is None else \
+                    tally_sized(ss, res, sizes)
                 total = data[rank].setdefault(sname, {})
                 for k, v in counts.items():           # util.sum_dict
                     total[k] = total.get(k, 0) + v

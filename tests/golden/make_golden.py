@@ -130,7 +130,7 @@ def run_case(name, input_rel, *, hier=None, ranks, coords_rel=None,
              overlap=80, strata_rel=None, fmt=None, demux=None, samples=None,
              trimsub=None, uniq=False, major=None, above=False, subok=False,
              unasgd=False, exclude=None, chunk=None, note='', maps=False,
-             name_as_id=False):
+             name_as_id=False, sizes=None):
     input_fp = join(OUT, input_rel)
     samples_, files, demux_ = W.parse_samples(input_fp, None, samples, demux)
     tree = rankdic = namedic = root = None
@@ -143,6 +143,8 @@ def run_case(name, input_rel, *, hier=None, ranks, coords_rel=None,
     stratmap = W.parse_strata(join(OUT, strata_rel), samples_) \
         if strata_rel else None
     excl = W.parse_exclude(exclude)
+    sizemap = W.parse_sizes(sizes if sizes in (None, '.') else join(OUT, sizes),
+                            mapper, {})
     rank2dir = None
     if maps:
         mapdir = tempfile.mkdtemp()
@@ -152,7 +154,7 @@ def run_case(name, input_rel, *, hier=None, ranks, coords_rel=None,
             os.makedirs(rank2dir[r])
     data = W.classify(mapper, files, samples_, fmt, demux_, trimsub, tree,
                       rankdic, namedic if name_as_id else None, root, ranks_,
-                      rank2dir, None, uniq, major, above, subok, None, unasgd,
+                      rank2dir, None, uniq, major, above, subok, sizemap, unasgd,
                       stratmap, excl, chunk_, 1024, {}, None, None)
     expected_maps = None
     if maps:
@@ -186,6 +188,17 @@ def run_case(name, input_rel, *, hier=None, ranks, coords_rel=None,
             seeds.update(subjects_of(flist, fmt, trimsub))
         tree_small = closure(tree, seeds)
     prefix = mapper.keywords['prefix'] if coords_rel else None
+    if sizemap:
+        # only the subjects this case can reach (a run without a hierarchy
+        # lists them as its features)
+        d3 = W.classify(mapper, files, samples_, fmt, demux_, trimsub, None,
+                        None, None, None, ['none'], None, None, False, None,
+                        False, False, None, False, None, excl, chunk_, 1024,
+                        {}, None, None)
+        reach = set()
+        for prof in d3['none'].values():
+            reach.update(prof)
+        sizemap = {k: v for k, v in sizemap.items() if k in reach}
     case = {
         'name': name, 'note': note, 'input': input_rel,
         'files': ({basename(k): v for k, v in files.items()}
@@ -199,7 +212,7 @@ def run_case(name, input_rel, *, hier=None, ranks, coords_rel=None,
         'above': above, 'subok': subok, 'unasgd': unasgd,
         'exclude': sorted(excl) if excl else None, 'coords': coords_rel,
         'overlap': overlap, 'prefix': prefix, 'strata': strata_rel,
-        'chunk': chunk, 'expected_maps': expected_maps,
+        'chunk': chunk, 'expected_maps': expected_maps, 'sizes': sizemap,
         'namedic': ({k: v for k, v in namedic.items() if k in tree_small}
                     if name_as_id and tree_small is not None else None),
         'expected_raw': enc(raw),
@@ -294,6 +307,23 @@ def bundled():
     run_case('bowtie2_orf_s01', join('bowtie2', 'S01.sam.xz'), ranks=None,
              coords_rel='coords.txt.xz', overlap=81,
              note='SAM + CIGAR lengths, overlap 81')
+    # --sizes (classify.counter_size): a subject-length map for the plain
+    # path, gene lengths from the coordinates ('.') for the ordinal path
+    os.makedirs(join(OUT, 'sizes'), exist_ok=True)
+    subs = sorted(subjects_of([join(OUT, 'bt2sho', f) for f in
+                               sorted(os.listdir(join(OUT, 'bt2sho')))]))
+    with open(join(OUT, 'sizes', 'bt2sho.length.map'), 'w') as f:
+        for x in subs:
+            f.write(f'{x}\t{1000000 + (int(x[1:]) % 977) * 1013}\n')
+    run_case('bt2sho_order_sizes', 'bt2sho', hier=nodes,
+             ranks='order,genus,none', sizes=join('sizes', 'bt2sho.length.map'),
+             note='cf. bt2sho.order.cpm.tsv: size-weighted, multi-hit data')
+    run_case('bt2sho_order_sizes_unasgd', 'bt2sho', hier=nodes,
+             ranks='order', sizes=join('sizes', 'bt2sho.length.map'),
+             unasgd=True, major=60, note='size-weighted, majority, Unassigned')
+    run_case('burst_process_sizes', 'burst', hier=fmaps, ranks='process,none',
+             coords_rel='coords.txt.xz', sizes='.',
+             note='cf. bt2sho.component.rpk.tsv: ordinal, gene lengths as sizes')
 
 
 def synthetic():

@@ -173,4 +173,59 @@ def test_gene_coords_encoding():
 
 def test_unsupported_options_are_loud():
     with pytest.raises(NotImplementedError):
-        classify(None, [], ranks=['none'], sizes={'a': 1.0})
+        classify(None, [], ranks=['none'], sizes={'a': 1.0},
+                 stratmap={'S1': 'x'})
+    with pytest.raises(NotImplementedError):
+        classify(None, [], ranks=['none'], outcov_dir='cov')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('opts', [dict(), dict(uniq=True, unasgd=True),
+                                  dict(major=60), dict(above=True)])
+def test_size_weighted_counts_vs_pure_python(opts):
+    """--sizes (classify.counter_size, classify.py:174-213) through the
+    kernels' (subject, feature) table, against the pure-Python restatement:
+    multi-rank, repeats, a 70-subject query (slow path), subjects without a
+    taxon."""
+    import random
+    from oracle import pyport
+    rnd = random.Random(5)
+    tree = {'root': 'root'}
+    rankdic = {}
+    for g in range(12):
+        tree[f'genus{g}'] = 'root'
+        rankdic[f'genus{g}'] = 'genus'
+        for s in range(4):
+            sp = f'sp{g}_{s}'
+            tree[sp] = f'genus{g}'
+            rankdic[sp] = 'species'
+            for x in range(3):
+                tree[f'G{g}_{s}_{x}'] = sp
+    leaves = [k for k in tree if k.startswith('G')]
+    sizes = {x: 1 / rnd.randint(1000, 9000) for x in leaves}
+    sizes.update({f'X{i}': 1 / (500 + i) for i in range(5)})
+    queries = []
+    for i in range(3000):
+        k = 70 if i % 600 == 7 else min(1 + int(rnd.expovariate(0.7)), 12)
+        base = rnd.randrange(len(leaves))
+        subs = [leaves[(base + rnd.randrange(9)) % len(leaves)] for _ in range(k)]
+        if rnd.random() < 0.05:
+            subs.append(f'X{rnd.randrange(5)}')
+        queries.append((f'R{i}', subs))
+    ranks = ['genus', 'species', 'none', 'free']
+    kw = dict(tree=tree, rankdic=rankdic, root='root')
+    got = run('gpu', queries, ranks, sizes=sizes, **kw, **opts)
+    chunks = [([q for q, _ in queries], [set(s) for _, s in queries])]
+    po = dict(opts)
+    if 'major' in po:
+        po['major'] = po['major'] / 100
+    exp = pyport.classify_chunks(chunks, ranks, tree, rankdic, 'root',
+                                 sample='S1', sizes=sizes, **po)
+    for r in ranks:
+        g, e = got[r]['S1'], exp[r]['S1']
+        assert set(g) == set(e), (r, set(g) ^ set(e))
+        for key, v in e.items():
+            assert abs(g[key] - v) <= 1e-9 * abs(v), (r, key, g[key], v)
+    # a subject without a size is the reference's error
+    with pytest.raises(ValueError, match='not found in the size map'):
+        run('gpu', queries, ['none'], sizes={'G0_0_0': 1.0})

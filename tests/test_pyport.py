@@ -45,12 +45,13 @@ def test_pyport_matches_reference(name):
                 samples=set(case['samples']) if case['demux'] and
                 case['samples'] else None,
                 sample=files[fp], trimsub=case['trimsub'], maps=maps,
-                namedic=case.get('namedic'))
+                namedic=case.get('namedic'), sizes=case.get('sizes'))
         for r in ranks:
             for s, prof in data[r].items():
                 tgt = total[r].setdefault(s, {})
                 for k, v in prof.items():
                     tgt[k] = tgt.get(k, 0) + v
+    check.relative = bool(case.get('sizes'))
     check(total, dec(case['expected_raw']), dec(case['expected_rounded']))
     if maps is not None:
         # taxon:count lists tie-break on the taxon name, so set order of the

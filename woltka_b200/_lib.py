@@ -14,7 +14,7 @@ UNITS = 720720
 MAX_ENTRIES = 8
 
 KIND_NONE, KIND_FREE, KIND_RANK, KIND_NONE_ID = 0, 1, 2, 3
-F_UNIQ, F_ABOVE, F_MAJOR, F_UNASSIGNED = 1, 2, 4, 8
+F_UNIQ, F_ABOVE, F_MAJOR, F_UNASSIGNED, F_SIZES = 1, 2, 4, 8, 16
 
 _i32p = C.POINTER(C.c_int32)
 _i64p = C.POINTER(C.c_int64)

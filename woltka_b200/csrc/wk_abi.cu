@@ -618,7 +618,9 @@ static int check_plan_ready(wk_ctx *c, bool strata) {
     return fail(WK_ERR_STATE, "plan needs a tree (wk_set_tree)");
   if (need_node && !c->have_sub_node)
     return fail(WK_ERR_STATE, "plan needs sub_node (wk_set_subjects)");
-  if (strata && (c->S > (1 << 16) || c->NF >= (int64_t)KEY_F24))
+  if (strata && (c->flags & WK_F_SIZES))
+    return fail(WK_ERR_ARG, "size-weighted and stratified counting cannot be combined");
+  if ((strata || (c->flags & WK_F_SIZES)) && (c->S > (1 << 16) || c->NF >= (int64_t)KEY_F24))
     return fail(WK_ERR_ARG,
                 "stratified counting supports at most 65536 samples and "
                 "2^24-2 features");
@@ -794,7 +796,8 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   P.r1 = r1;
   P.q_sample = dqsamp;
   P.q_stratum = dqstrat;
-  if (dqstrat) c->strata_keys = true;
+  const bool sizes = (c->flags & WK_F_SIZES) != 0;  // keyed by (subject, feature)
+  if (dqstrat || sizes) c->strata_keys = true;
   P.sample = sample;
   P.E = c->E;
   P.e_lo = 0;
@@ -836,7 +839,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   P.scratch = c->scratch.as<int32_t>();
 
   bool staged = c->tab16_ok && !all_id;
-  const bool lean = c->E == 1 && !dqsamp && !dqstrat;
+  const bool lean = c->E == 1 && !dqsamp && !dqstrat && !sizes;
   const size_t cells = (size_t)c->E * c->S * (c->NF + 1);
   int grid = c->tune_grid > 0 ? c->tune_grid : c->sm_count;
 
@@ -853,7 +856,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   P.fast_gsink = 0;
   const bool wide = c->kind[0] == WK_KIND_NONE_ID;  // feature == subject, no table
   if (c->tune_block != 1 && same_kind && (wide ? P.V < 0xFFFFFD : staged) &&
-      !dqstrat && c->tune_cache == 0 && !(n_dev && dqsamp) && !P.assign &&
+      !dqstrat && !sizes && c->tune_cache == 0 && !(n_dev && dqsamp) && !P.assign &&
       !getenv("WK_NO_FAST") &&
       (n_dev ? n_bound : r1 - r0) < (1ll << 31) - (1 << 20)) {  // 32-bit tile counters
     int NTmax = c->tune_block;
@@ -976,7 +979,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   const int64_t tab_bytes = staged ? (int64_t)c->stage_elems * 2 : 0;
   // where counts are accumulated first (wk_classify.cuh, "count sinks")
   int sink = SINK_GLOBAL, cache_log = 0;
-  if (!dqstrat && c->tune_cache >= 0) {
+  if (!dqstrat && !sizes && c->tune_cache >= 0) {
     if (dir_cells != 0xFFFFFFFFu &&
         cls_layout(SINK_DIRECT, 0, dir_cells, tab_bytes).total <=
             c->smem_optin) {
@@ -1089,7 +1092,7 @@ int wk_classify_device(wk_ctx *c, const int32_t *d_qidx, const int32_t *d_sidx,
   if (!d_q_sample && (sample < 0 || sample >= c->S))
     return fail(WK_ERR_ARG, "sample %d out of range", sample);
   if (n_rec == 0) return WK_OK;
-  if (d_q_stratum) TRY(ensure_strata(c, n_rec * c->E));
+  if (d_q_stratum || (c->flags & WK_F_SIZES)) TRY(ensure_strata(c, n_rec * c->E));
   TRY(launch_classify(c, d_qidx, d_sidx, n_rec, nullptr, n_rec, 0, n_rec,
                       d_q_sample, d_q_stratum, sample));
   return WK_OK;
@@ -1105,7 +1108,7 @@ int wk_classify_chunk(wk_ctx *c, const int32_t *qidx, const int32_t *sidx,
   if (!q_sample && (sample < 0 || sample >= c->S))
     return fail(WK_ERR_ARG, "sample %d out of range", sample);
   if (n_rec == 0) return WK_OK;
-  if (q_stratum) TRY(ensure_strata(c, n_rec * c->E));
+  if (q_stratum || (c->flags & WK_F_SIZES)) TRY(ensure_strata(c, n_rec * c->E));
   TRY(c->dq.reserve((size_t)n_rec * 4 + 64));
   TRY(c->ds.reserve((size_t)n_rec * 4 + 64));
   const int32_t *dqs, *dqt;
@@ -1345,7 +1348,7 @@ int wk_ordinal_device(wk_ctx *c, const int32_t *d_qidx, const int32_t *d_contig,
   if (!d_q_sample && (sample < 0 || sample >= c->S))
     return fail(WK_ERR_ARG, "sample %d out of range", sample);
   if (n_rec == 0) return WK_OK;
-  if (d_q_stratum) TRY(ensure_strata(c, 4 * n_rec * c->E));
+  if (d_q_stratum || (c->flags & WK_F_SIZES)) TRY(ensure_strata(c, 4 * n_rec * c->E));
   return run_ordinal(c, d_qidx, d_contig, d_beg, d_end, d_len, n_rec, th,
                      d_q_sample, d_q_stratum, sample, true);
 }
@@ -1365,7 +1368,8 @@ int wk_ordinal_chunk(wk_ctx *c, const int32_t *qidx, const int32_t *contig,
     return fail(WK_ERR_ARG, "sample %d out of range", sample);
   c->last_pairs = 0;
   if (n_rec == 0) return WK_OK;
-  if (classify && q_stratum) TRY(ensure_strata(c, 4 * n_rec * c->E));
+  if (classify && (q_stratum || (c->flags & WK_F_SIZES)))
+    TRY(ensure_strata(c, 4 * n_rec * c->E));
   DevBuf *bufs[5] = {&c->dq, &c->dcontig, &c->dbeg, &c->dend, &c->dlen};
   const int32_t *src[5] = {qidx, contig, beg, end, len};
   for (int i = 0; i < 5; ++i) TRY(bufs[i]->reserve((size_t)n_rec * 4 + 64));
@@ -1822,6 +1826,7 @@ int wk_classify_parsed(wk_ctx *c, const int32_t *sample_map, int32_t n_map,
   TRY(check_plan_ready(c, false));
   TRY(use_device(c));
   const int64_t N = c->p_nrec, Q = c->p_nqry;
+  if (N && (c->flags & WK_F_SIZES)) TRY(ensure_strata(c, N * c->E));
   if (N == 0) return WK_OK;
   const int32_t *dqs = nullptr;
   if (c->p_demux) {

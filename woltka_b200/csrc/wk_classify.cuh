@@ -264,7 +264,7 @@ __device__ __forceinline__ void emit_units(const ClsParams &P, const Sink &K,
       if (old + units < old) atomicAdd(&P.cnt[cell], 1ull << 32);
       return;
     }
-  } else if (P.q_stratum) {
+  } else if (P.q_stratum || (P.flags & WK_F_SIZES)) {
     strat_add(P, pack_strat(P, strat, e, samp, f), units);
     return;
   }
@@ -284,7 +284,8 @@ __device__ __forceinline__ void emit_frac(const ClsParams &P, const Sink &K,
   }
   ull at = atomicAdd(P.ovf_n, 1ull);
   if ((int64_t)at < P.ovf_cap) {
-    P.ovf_key[at] = (int64_t)(P.q_stratum ? pack_strat(P, strat, e, samp, f)
+    P.ovf_key[at] = (int64_t)((P.q_stratum || (P.flags & WK_F_SIZES))
+                                  ? pack_strat(P, strat, e, samp, f)
                                           : pack_plain(P, e, samp, f));
     P.ovf_den[at] = (int32_t)d;
   } else {
@@ -465,7 +466,8 @@ __device__ __noinline__ int64_t process_long(const ClsParams &P, const Sink &K,
           if (__ldcg(P.scratch + j) == DUPMARK) continue;
           int sj = gs[j];
           int f = kind == WK_KIND_NONE_ID ? sj : tab_get<STAGED>(P, stab, e, sj);
-          if (live) emit_frac<SINK>(P, K, e, samp, strat, f, k);
+          if (live)
+            emit_frac<SINK>(P, K, e, samp, (P.flags & WK_F_SIZES) ? sj : strat, f, k);
           if (asg) asg[j] = f;
         }
       }
@@ -543,7 +545,9 @@ __device__ __noinline__ int64_t process_long(const ClsParams &P, const Sink &K,
           for (int64_t j = start + lane; j < end; j += 32) {
             int t = __ldcg(P.scratch + j);
             if (t == DUPMARK || t < 0) continue;
-            if (live) emit_frac<SINK>(P, K, e, samp, strat, t, nvalid);
+            if (live)
+              emit_frac<SINK>(P, K, e, samp, (P.flags & WK_F_SIZES) ? gs[j] : strat, t,
+                              nvalid);
             if (asg) asg[j] = t;
           }
         }
@@ -554,7 +558,14 @@ __device__ __noinline__ int64_t process_long(const ClsParams &P, const Sink &K,
         __syncwarp();
       }
     }
-    if (lane == 0 && uniqres) {
+    if (uniqres && (P.flags & WK_F_SIZES)) {
+      // classify.counter_size (classify.py:204-205): every subject of the
+      // query carries 1/k of the unit
+      if (live && (result >= 0 || unas))
+        for (int64_t j = start + lane; j < end; j += 32)
+          if (__ldcg(P.scratch + j) != DUPMARK)
+            emit_frac<SINK>(P, K, e, samp, gs[j], result >= 0 ? result : NF, k);
+    } else if (lane == 0 && uniqres) {
       if (live && result >= 0)
         emit_units<SINK>(P, K, e, samp, strat, result, (uint32_t)WK_UNITS);
       else if (live && unas)
@@ -871,7 +882,8 @@ __global__ void __launch_bounds__(CLS_NT, 1)
                 uniqres = false;
                 if (nd && t >= 0) aval = t;
                 if (live && nd && t >= 0)
-                  emit_frac<SINK>(P, K, e, samp, strat, t, __popc(vm));
+                  emit_frac<SINK>(P, K, e, samp, (flags & WK_F_SIZES) ? sv : strat, t,
+                                  __popc(vm));
               }
             }
           }
@@ -914,10 +926,19 @@ __global__ void __launch_bounds__(CLS_NT, 1)
           } else if (!(flags & WK_F_UNIQ)) {
             uniqres = false;
             if (nd) aval = f;
-            if (live && nd) emit_frac<SINK>(P, K, e, samp, strat, f, k);
+            if (live && nd)
+              emit_frac<SINK>(P, K, e, samp, (flags & WK_F_SIZES) ? sv : strat, f, k);
           }
         }
-        if (ishead && live && uniqres) {
+        if (!LEAN && (flags & WK_F_SIZES)) {
+          // classify.counter_size (classify.py:204-205): every subject of a
+          // uniquely assigned query carries 1/k of the unit
+          dedup();
+          const int rq = __shfl_sync(FULL, result, sl);
+          const bool uq = __shfl_sync(FULL, (int)uniqres, sl);
+          if (act && live && uq && nd && (rq >= 0 || unas))
+            emit_frac<SINK>(P, K, e, samp, sv, rq >= 0 ? rq : NF, k);
+        } else if (ishead && live && uniqres) {
           if (result >= 0)
             emit_units<SINK>(P, K, e, samp, strat, result, (uint32_t)WK_UNITS);
           else if (unas)

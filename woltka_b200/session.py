@@ -19,7 +19,8 @@ from fractions import Fraction
 import numpy as np
 
 from ._lib import (UNITS, MAX_ENTRIES, KIND_NONE, KIND_FREE, KIND_RANK,
-                   KIND_NONE_ID, F_UNIQ, F_ABOVE, F_MAJOR, F_UNASSIGNED)
+                   KIND_NONE_ID, F_UNIQ, F_ABOVE, F_MAJOR, F_UNASSIGNED,
+                   F_SIZES)
 from .hierarchy import FlatTree
 
 _SEP = '_'
@@ -36,7 +37,7 @@ class Session:
     def __init__(self, ranks, tree=None, rankdic=None, root=None, uniq=False,
                  major=None, above=False, subok=False, unasgd=False,
                  trimsub=None, engine_factory=None, device=0, rank2dir=None,
-                 outzip=None, namedic=None):
+                 outzip=None, namedic=None, sizes=None):
         if engine_factory is None:
             from .engine import Engine
             engine_factory = Engine
@@ -68,7 +69,11 @@ class Session:
                              'fill_root before LCA-based assignment.')
         self.flags = ((F_UNIQ if uniq else 0) | (F_ABOVE if above else 0) |
                       (F_MAJOR if major else 0) |
-                      (F_UNASSIGNED if unasgd else 0))
+                      (F_UNASSIGNED if unasgd else 0) |
+                      (F_SIZES if sizes else 0))
+        # --sizes: the device keeps (subject, feature) -> units, weighted here
+        # (classify.counter_size, classify.py:174-213)
+        self.sizes = sizes
         self.major_th = float(major) if major else 0.0
 
         # vocabularies
@@ -368,6 +373,38 @@ class Session:
         for eng in self.engines:
             eng.ordinal_chunk(*cols, th, q_sample, q_stratum)
 
+    def _sized_results(self, data):
+        """--sizes: sum over subjects of weight x the exact share the subject
+        contributed to the feature (the device's (subject, feature) table)."""
+        names = [None] * len(self.sub_index)
+        for name, idx in self.sub_index.items():
+            names[idx] = name
+        NF1 = self.NF_cap + 1
+        for grp, eng in zip(self.groups, self.engines):
+            shares = {}   # (e, sample, feature, subject) -> Fraction
+            e_, s_, t_, f_, u_ = eng.fetch_strata()
+            for e, s, t, f, u in zip(e_.tolist(), s_.tolist(), t_.tolist(),
+                                     f_.tolist(), u_.tolist()):
+                shares[(e, s, f, t)] = Fraction(u, UNITS)
+            ocell, ostrat, oden = eng.fetch_overflow()
+            for cell, t, den in zip(ocell.tolist(), ostrat.tolist(),
+                                    oden.tolist()):
+                es, f = divmod(cell, NF1)
+                k = (es // self.S_cap, es % self.S_cap, f, t)
+                shares[k] = shares.get(k, 0) + Fraction(1, den)
+            try:
+                for (e, s, f, t) in sorted(shares):
+                    rank = self.order[grp[e]]
+                    prof = data[rank][self.sample_names[s]]
+                    name = self.feature_name(f)
+                    prof[name] = prof.get(name, 0) + \
+                        self.sizes[names[t]] * float(shares[(e, s, f, t)]) * \
+                        self.mult[rank]
+            except KeyError:
+                raise ValueError('One or more subjects are not found in the '
+                                 'size map.')
+        return data
+
     # -- results --------------------------------------------------------------
     def feature_name(self, f):
         if f == self.NF_cap:
@@ -384,6 +421,8 @@ class Session:
             for sname in self.sample_names:
                 data[rank][sname] = {}
         NF1 = self.NF_cap + 1
+        if self.sizes:
+            return self._sized_results(data)
         for grp, eng in zip(self.groups, self.engines):
             cells = {}    # (e, sample, stratum | None, feature) -> Fraction
             ocell, ostrat, oden = eng.fetch_overflow()

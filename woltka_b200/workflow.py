@@ -15,10 +15,11 @@ frac/scale/round, table writers) is the reference's own code and is called
 unchanged by its `workflow()`.
 
 Read maps (`rank2dir`) come from a per-record
-assignment column the kernel writes next to the counts.  Not re-implemented in
-this round (rows F4-F5): size-weighted counting (`sizes`), coverage
-(`outcov_dir`) and read maps of the ordinal path raise NotImplementedError
-instead of silently falling back.
+assignment column the kernel writes next to the counts; size-weighted counts
+(`sizes`, row F4) from the kernels' exact (subject, feature) shares, weighted
+on the host.  Not re-implemented in this round: coverage (`outcov_dir`, row
+F5), read maps of the ordinal path and `sizes` together with `stratmap` raise
+NotImplementedError instead of silently falling back.
 """
 import bz2
 import gzip
@@ -182,10 +183,10 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
         raise NotImplementedError(
             'Read-map output (--outmap) with --coords is not part of the GPU '
             'hot path yet.')
-    if sizes:
+    if sizes and stratmap:
         raise NotImplementedError(
-            'Size-normalised counting (--sizes) is not part of the GPU hot '
-            'path yet.')
+            'Size-normalised counting (--sizes) together with --stratify is '
+            'not part of the GPU hot path yet.')
     if outcov_dir:
         raise NotImplementedError(
             'Subject coverage (--outcov) is not part of the GPU hot path.')
@@ -198,7 +199,7 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
 
     sess = Session(ranks, tree, rankdic, root, uniq, major and major / 100,
                    above, subok, unasgd, trimsub, _engine_factory, _device,
-                   rank2dir, outzip, namedic)
+                   rank2dir, outzip, namedic, sizes)
     samset = set(samples) if samples else None
     strata_cache = {}
 
