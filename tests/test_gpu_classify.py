@@ -21,6 +21,17 @@ def big_case():
     return cases.Case(synth.Taxonomy(seed=42))
 
 
+def _lean_kernel(entries, mode):
+    """The kernel a one-sample plan takes: one entry (a rank, or `none`
+    through a table) in default or --uniq mode -> classify_seg_kernel; other
+    one-kind plans -> classify_fast_kernel."""
+    if len(entries) == 1 and entries[0] != 'free' and (
+            mode in ('default', 'uniq', 'uniq+unassigned') or
+            entries[0] == 'none'):     # assign_none knows no --major / --above
+        return 'classify_seg_kernel'
+    return 'classify_fast_kernel'
+
+
 def _same(a, b):
     ua, oa, sa = a
     ub, ob, sb = b
@@ -269,10 +280,13 @@ def test_contiguous_samples_take_the_run_per_lane_kernel(engine, small_case,
 
 
 def test_which_kernel_runs(engine, small_case):
-    """One-kind plans with staged tables take classify_fast_kernel; strata,
-    mixed kinds and read maps take classify_kernel."""
+    """One entry in default / --uniq mode takes classify_seg_kernel, other
+    one-kind plans with staged tables classify_fast_kernel; strata, mixed
+    kinds and read maps take classify_kernel."""
     q, s = cases.random_hits(small_case, 5000, seed=1)
     cases.run_engine(engine, small_case, ['genus'], 0, 0, q, s)
+    assert engine.last_kernel() == 'classify_seg_kernel'
+    cases.run_engine(engine, small_case, ['genus'], cases.MODES['major'], 0.8, q, s)
     assert engine.last_kernel() == 'classify_fast_kernel'
     cases.run_engine(engine, small_case, ['phylum', 'genus'], 0, 0, q, s)
     assert engine.last_kernel() == 'classify_fast_kernel'
@@ -292,8 +306,12 @@ def test_which_kernel_runs(engine, small_case):
     _same(a, cases.run_engine(engine, small_case, ['genus'], 0, 0, q, s))
 
 
-def test_run_per_lane_kernel_at_1e6(engine, big_case):
-    # one-entry plans on the 21,603-node taxonomy, every mode, both kinds
+@pytest.mark.parametrize('noseg', ['', '1'])
+def test_run_per_lane_kernel_at_1e6(engine, big_case, monkeypatch, noseg):
+    # one-entry plans on the 21,603-node taxonomy, every mode, both kinds;
+    # with and without the lane-per-record kernel of the default / --uniq mode
+    if noseg:
+        monkeypatch.setenv('WK_NO_SEG', noseg)
     qi, si, _, nq = synth.gen_hits(1_000_000, seed=1002)
     q, s = qi.numpy(), si.numpy()
     for ent in (['genus'], ['species'], ['none']):
@@ -301,7 +319,8 @@ def test_run_per_lane_kernel_at_1e6(engine, big_case):
             fl = cases.MODES[mode]
             _same(cases.run_engine(engine, big_case, ent, fl, 0.8, q, s),
                   cases.run_oracle(big_case, ent, fl, 0.8, q, s, n_threads=4))
-            assert engine.last_kernel() == 'classify_fast_kernel'
+            assert engine.last_kernel() == (
+                'classify_fast_kernel' if noseg else _lean_kernel(ent, mode))
 
 
 def test_cfg5_shape_gene_to_ko_stratified_by_genus(engine):
@@ -357,6 +376,7 @@ def test_short_runs_and_fewer_warps(engine, small_case, monkeypatch, r, block):
     """The run-per-lane kernel at every run length it is built for (13 is the
     default) and with fewer warps per CTA, as chosen for large tables."""
     monkeypatch.setenv('WK_SWEEP_R', r)
+    monkeypatch.setenv('WK_NO_SEG', '1')
     q, s = cases.random_hits(small_case, 30000, seed=int(r), long_every=3000,
                              long_len=60)
     engine.set_tuning(0, block, 0)
@@ -372,15 +392,20 @@ def test_short_runs_and_fewer_warps(engine, small_case, monkeypatch, r, block):
         engine.set_tuning(0, 0, 0)
 
 
-def test_randomised_shapes_both_kernels_agree(engine, small_case):
+@pytest.mark.parametrize('noseg', ['', '1'])
+def test_randomised_shapes_both_kernels_agree(engine, small_case, monkeypatch,
+                                              noseg):
     """Many small random streams whose sizes straddle the warp-tile and run
-    boundaries (32 x 13 = 416 records, runs of 13), with long queries and
-    repeats placed at random: run-per-lane kernel == window kernel == oracle."""
+    boundaries (32 x 13 = 416 records, runs of 13; tiles of 512), with long
+    queries and repeats placed at random: lane-per-record kernel ==
+    run-per-lane kernel == window kernel == oracle."""
+    if noseg:
+        monkeypatch.setenv('WK_NO_SEG', noseg)
     rng = np.random.default_rng(2026)
     ents = (['genus'], ['none'], ['phylum', 'species'])
     modes = ('default', 'uniq', 'major', 'above', 'major+unassigned')
     for it in range(40):
-        nq = int(rng.choice([1, 3, 40, 200, 205, 416, 420, 832, 1000, 3000]))
+        nq = int(rng.choice([1, 3, 40, 200, 205, 247, 416, 420, 832, 1000, 3000]))
         p = float(rng.choice([0.2, 0.48, 0.9]))
         every = int(rng.choice([0, 7, 50]))
         q, s = cases.random_hits(small_case, nq, seed=1000 + it, kmax=45, p=p,
@@ -393,7 +418,8 @@ def test_randomised_shapes_both_kernels_agree(engine, small_case):
         th = float(rng.choice([0.5, 0.51, 0.8]))
         exp = cases.run_oracle(small_case, ent, fl, th, q, s)
         got = cases.run_engine(engine, small_case, ent, fl, th, q, s)
-        assert engine.last_kernel() == 'classify_fast_kernel'
+        assert engine.last_kernel() == (
+            'classify_fast_kernel' if noseg else _lean_kernel(ent, mode))
         _same(got, exp)
         engine.set_tuning(0, 1, 0)
         try:
@@ -428,3 +454,25 @@ def test_rank_none_without_a_table(engine, mode, NF):
     exp = O.classify(q, s, kinds=kinds, flags=fl, n_samples=2, n_features=NF,
                      sample=1, n_threads=4)
     _same(got, exp)
+
+
+@pytest.mark.parametrize('sub', ['36', '516', '4000'])
+@pytest.mark.parametrize('noseg', ['', '1'])
+def test_host_chunk_in_sub_chunks(engine, small_case, monkeypatch, sub, noseg):
+    """wk_classify_chunk launches one kernel per sub-chunk of the host columns
+    (records [r0, r1), not cut at query boundaries: a query belongs to the
+    launch that holds its first record).  Small sub-chunks put those cuts, the
+    512-record warp tiles and the 32-record windows in every relative
+    position, with queries longer than a window and longer than a sub-chunk."""
+    monkeypatch.setenv('WK_CLS_SUB', sub)
+    if noseg:
+        monkeypatch.setenv('WK_NO_SEG', noseg)
+    q, s = cases.random_hits(small_case, 2500, seed=int(sub), kmax=31, p=0.3,
+                             long_every=211, long_len=70, window=6)
+    for ent, mode in ((['genus'], 'default'), (['genus'], 'uniq+unassigned'),
+                      (['none'], 'default'), (['species'], 'major')):
+        fl = cases.MODES[mode]
+        _same(cases.run_engine(engine, small_case, ent, fl, 0.8, q, s),
+              cases.run_oracle(small_case, ent, fl, 0.8, q, s))
+        assert engine.last_kernel() == (
+            'classify_fast_kernel' if noseg else _lean_kernel(ent, mode))

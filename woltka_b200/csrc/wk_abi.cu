@@ -15,6 +15,7 @@
 
 #include "wk_classify.cuh"
 #include "wk_ordinal.cuh"
+#include "wk_seg.cuh"
 #include "wk_sweep.cuh"
 #include "wk_parse.cuh"
 
@@ -160,6 +161,7 @@ struct wk_ctx {
   int32_t n_levels = 0, level_off[40];
   std::vector<int64_t> dir_lo, dir_hi;  // per entry: range of the table values
   // overflow + err
+  DevBuf longlist;  // classify_seg_kernel: [0] = count, then first records of long queries
   DevBuf ovf_key, ovf_den, small;  // small: [0]=ovf_n [1]=sh_used [2]=n_pairs [3]=cursor, err after
   int64_t ovf_cap = 0;
   // strata hash
@@ -326,6 +328,18 @@ int wk_create(int device, wk_ctx **out) {
         (const void *)classify_fast_kernel<WK_KIND_NONE_ID, FX_FRAC, 13, true>,
         (const void *)classify_fast_kernel<WK_KIND_NONE_ID, FX_UNIQ, 13, false>,
         (const void *)classify_fast_kernel<WK_KIND_NONE_ID, FX_UNIQ, 13, true>};
+    const void *seg[] = {
+        (const void *)classify_seg_kernel<WK_KIND_RANK, FX_FRAC, 512>,
+        (const void *)classify_seg_kernel<WK_KIND_RANK, FX_FRAC, 256>,
+        (const void *)classify_seg_kernel<WK_KIND_RANK, FX_UNIQ, 512>,
+        (const void *)classify_seg_kernel<WK_KIND_RANK, FX_UNIQ, 256>,
+        (const void *)classify_seg_kernel<WK_KIND_NONE, FX_FRAC, 512>,
+        (const void *)classify_seg_kernel<WK_KIND_NONE, FX_FRAC, 256>,
+        (const void *)classify_seg_kernel<WK_KIND_NONE, FX_UNIQ, 512>,
+        (const void *)classify_seg_kernel<WK_KIND_NONE, FX_UNIQ, 256>};
+    for (const void *fn : seg)
+      CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)c->smem_optin));
     for (const void *fn : fast)
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)c->smem_optin));
@@ -342,7 +356,7 @@ int wk_destroy(wk_ctx *c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   DevBuf *bufs[] = {&c->parent, &c->cnt, &c->tab, &c->tab16, &c->sub_node,
-                    &c->ovf_key, &c->ovf_den, &c->small, &c->sh_keys,
+                    &c->ovf_key, &c->ovf_den, &c->small, &c->longlist, &c->sh_keys,
                     &c->sh_vals, &c->dq, &c->ds, &c->dqsamp, &c->dqstrat,
                     &c->scratch, &c->dcontig, &c->dbeg, &c->dend, &c->dlen,
                     &c->cinfo, &c->genes, &c->pair_q, &c->pair_s, &c->pair_r,
@@ -907,6 +921,51 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
     }
     const int64_t span = n_dev ? n_bound : r1 - (r0 & ~3ll);
     if (span <= 0) return WK_OK;
+    // one entry, one sample, default or --uniq: the lane-per-record kernel
+    // with warp-private tiles (wk_seg.cuh)
+    if (lean && !gsink && !wide && !n_dev && (mode == FX_FRAC || mode == FX_UNIQ) &&
+        NTmax == SW_NT && !getenv("WK_NO_SEG")) {
+      int WT = 0;
+      const uint32_t cells1 = (uint32_t)(P.dir_base[1] - P.dir_base[0]);
+      const uint32_t stamps = 0u;
+      for (int wt : {512, 256})
+        if (!WT && sg_layout(SG_NT / 32, wt, cells1, (int64_t)c->Vp * 2, stamps).total <=
+                       c->smem_optin)
+          WT = wt;
+      if (const char *ev = getenv("WK_SEG_WT")) WT = atoi(ev) == 256 ? (WT ? 256 : 0) : WT;
+      if (WT) {
+        const SgSmemLayout GL = sg_layout(SG_NT / 32, WT, cells1, (int64_t)c->Vp * 2, stamps);
+        const int64_t ft = (span + WT - 1) / WT;
+        const int sgrid = (int)std::min<int64_t>(grid, (ft + SG_NT / 32 - 1) / (SG_NT / 32));
+        P.direct_cells = dir_cells;
+        P.e_lo = 0;
+        P.e_hi = 1;
+        // queries longer than a window are listed and done by seg_long_kernel
+        TRY(c->longlist.reserve((size_t)(span / 33 + 4) * 8));
+        P.long_list = c->longlist.as<ull>();
+        CK(cudaMemsetAsync(P.long_list, 0, 8, c->stream));
+#define WK_SEG2(KD, MD)                                                          \
+  do {                                                                           \
+    if (WT == 512)                                                               \
+      classify_seg_kernel<KD, MD, 512><<<sgrid, SG_NT, GL.total, c->stream>>>(P); \
+    else                                                                         \
+      classify_seg_kernel<KD, MD, 256><<<sgrid, SG_NT, GL.total, c->stream>>>(P); \
+  } while (0)
+        if (rk) {
+          if (mode == FX_UNIQ) WK_SEG2(WK_KIND_RANK, FX_UNIQ);
+          else WK_SEG2(WK_KIND_RANK, FX_FRAC);
+        } else {
+          if (mode == FX_UNIQ) WK_SEG2(WK_KIND_NONE, FX_UNIQ);
+          else WK_SEG2(WK_KIND_NONE, FX_FRAC);
+        }
+#undef WK_SEG2
+        seg_long_kernel<<<c->sm_count, 128, 0, c->stream>>>(P);
+        c->launches += 2;
+        CK(cudaGetLastError());
+        c->last_kernel = "classify_seg_kernel";
+        return WK_OK;
+      }
+    }
     if (FR) {
       const bool multi = !lean;
       P.fast_gsink = gsink ? 1 : 0;
@@ -1116,7 +1175,8 @@ int wk_classify_chunk(wk_ctx *c, const int32_t *qidx, const int32_t *sidx,
   // H2D in sub-chunks on the copy stream; the kernel for sub-chunk j needs
   // sub-chunk j+1 resident (a query may straddle the boundary), so it waits
   // on copy j+1 while copy j+2 is already in flight.
-  const int64_t SUB = 8ll << 20;
+  int64_t SUB = 8ll << 20;
+  if (const char *ev = getenv("WK_CLS_SUB")) SUB = std::max<int64_t>(4, atoll(ev) & ~3ll);
   const int64_t nsub = (n_rec + SUB - 1) / SUB;
   CK(cudaEventRecord(c->ev_free, c->stream));
   CK(cudaStreamWaitEvent(c->copy_stream, c->ev_free, 0));

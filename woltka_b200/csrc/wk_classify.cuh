@@ -101,6 +101,7 @@ struct ClsParams {
   const void *seg_list;       // classify_fast_kernel<MULTI>: SegList of the stream, or null
   const int32_t *skip_flag;   // classify_kernel: do nothing if *skip_flag >= 0
   int32_t fast_gsink;         // classify_fast_kernel: no private table, global reductions
+  ull *long_list;             // classify_seg_kernel: [0] = count, [1..] first record of a long query
 };
 
 enum { ERR_BAD_SUBJECT = 1, ERR_OVF_FULL = 2, ERR_HASH_FULL = 4,
@@ -132,6 +133,14 @@ __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
 __device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t v) {
   uint32_t old;
   asm volatile("atom.shared.add.u32 %0, [%1], %2;"
+               : "=r"(old)
+               : "r"(a), "r"(v)
+               : "memory");
+  return old;
+}
+__device__ __forceinline__ uint32_t atoms_exch(uint32_t a, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.exch.b32 %0, [%1], %2;"
                : "=r"(old)
                : "r"(a), "r"(v)
                : "memory");
