@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3', 'cfg4'])
+    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3', 'cfg4', 'cfg5'])
     ap.add_argument('--records', type=int, default=100_000_000)
     ap.add_argument('--mode', default='default',
                     choices=['default', 'major', 'uniq', 'above'])
@@ -318,6 +318,15 @@ def run_reference_cfg3(args, threads):
 
 
 def workload_config(args, entries):
+    if args.workload == 'cfg5':
+        return {'workload': 'cfg5: stratified taxonomy x function: gene '
+                            'subjects (10k genomes x 500 genes), rank ko '
+                            'through a gene -> KO map (10k KOs, 60 % '
+                            'annotated), counts keyed by (genus stratum, KO), '
+                            '8 samples per GPU',
+                'records_per_gpu': args.records, 'ranks': entries,
+                'subjects': 5_000_000, 'kos': 10_000, 'genera': 3000,
+                'samples_per_gpu': 8, 'l2': 'inputs larger than L2'}
     if args.workload == 'cfg3':
         return {'workload': 'cfg3: coord-match ordinal profile, synthetic '
                             'reads x 5M gene intervals over 1k contigs, '
@@ -365,6 +374,9 @@ def run_ours(args):
 
     if args.workload == 'cfg3':
         return run_ours_cfg3(args, eng, dev, world, rank, barrier, hbm_peak,
+                             peak_src)
+    if args.workload == 'cfg5':
+        return run_ours_cfg5(args, eng, dev, world, rank, barrier, hbm_peak,
                              peak_src)
 
     from tests import cases
@@ -650,6 +662,177 @@ def run_ours_cfg3(args, eng, dev, world, rank, barrier, hbm_peak, peak_src):
                          'algorithmic_bytes_per_gene': 8},
             'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
             'clocks': clocks, 'parity_on_sample': parity}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def make_cfg5(n, seed, device, n_genomes=10_000, genes_per=500, n_ko=10_000,
+              n_genus=3000, n_samples=8, p=0.48, kmax=16):
+    """the second pass of a stratified run.  Subjects are
+    genes, the rank is 'ko' through a gene -> KO map (tree.read_map read as a
+    two-level tree; 60 % of the genes annotated), every query carries the
+    stratum its unique genus assignment of the first pass gave it (80 %
+    assigned, classify.counter_strat skips the others)."""
+    import torch
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    q_est = int(n / 1.8) + 1024
+    u = torch.rand(q_est, generator=g, device=dev, dtype=torch.float64)
+    k = torch.floor(torch.log1p(-u) / np.log(1.0 - p)).to(torch.int64) + 1
+    k.clamp_(1, kmax)
+    csum = torch.cumsum(k, 0)
+    nq = int(torch.searchsorted(csum, torch.tensor(n, device=dev)).item()) + 1
+    k = k[:nq].clone()
+    k[-1] -= csum[nq - 1] - n
+    q = torch.repeat_interleave(torch.arange(nq, device=dev, dtype=torch.int32), k)
+    first = torch.randint(0, n_genomes, (nq,), generator=g, device=dev)
+    genome = (first[q.long()] + torch.randint(0, 3, (n,), generator=g, device=dev)) % n_genomes
+    s = (genome * genes_per + torch.randint(0, genes_per, (n,), generator=g,
+                                            device=dev)).to(torch.int32)
+    del genome
+    # genera own contiguous blocks of genomes (like the taxonomy generator)
+    genus_of = (torch.arange(n_genomes, device=dev) * n_genus // n_genomes)
+    strat = torch.where(torch.rand(nq, generator=g, device=dev) < 0.8,
+                        genus_of[first], torch.full_like(first, -1)).to(torch.int32)
+    q_sample = (torch.arange(nq, device=dev, dtype=torch.int64) * n_samples //
+                nq).to(torch.int32)
+    gk = torch.Generator(device='cpu')
+    gk.manual_seed(1005)
+    V = n_genomes * genes_per
+    ko = torch.randint(1, n_ko + 1, (V,), generator=gk)
+    ko[torch.rand(V, generator=gk) >= 0.6] = -1
+    return q, s, q_sample, strat, nq, ko.to(torch.int32).numpy()[None, :], n_ko
+
+
+def run_ours_cfg5(args, eng, dev, world, rank, barrier, hbm_peak, peak_src):
+    import torch
+    import torch.distributed as dist
+    from woltka_b200._lib import KIND_RANK
+    from woltka_b200.engine import pinned_empty
+    n = args.records
+    S_loc = 8
+    q, s, qs, qt, nq, tab, n_ko = make_cfg5(n, 1005 + rank, dev, n_samples=S_loc)
+    T = 1 + n_ko                      # root + KOs; the genes are the subjects
+    parent = np.zeros(T, dtype=np.int32)
+    eng.set_tree(parent, 0)
+    # samples are sharded: every rank owns its own 8 sample columns, so the
+    # (sample, genus, KO) cells of the ranks are disjoint - no collective
+    eng.set_plan(np.array([KIND_RANK], dtype=np.int32), 0, 0.0, S_loc, T)
+    eng.set_subjects(tab, None)
+    ptr = (q.data_ptr(), s.data_ptr(), qs.data_ptr(), qt.data_ptr())
+
+    def classify_dev():
+        eng.classify_device(ptr[0], ptr[1], n, ptr[2], ptr[3], nq, 0)
+
+    # the strata table keeps growing over the steps like over the chunks of a
+    # run (same keys every step); it is not cleared inside the timed region
+    for _ in range(max(args.warmup, 1)):
+        classify_dev()
+    barrier()
+    l0 = eng.launch_count()
+    sampler = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()
+    t_beg = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_beg.record()
+    for i in range(args.steps):
+        classify_dev()
+    t_end.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = t_beg.elapsed_time(t_end)
+    launches = eng.launch_count() - l0
+    tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    k_ms = ms / args.steps
+    value = n * world * args.steps / (ms * 1e-3)
+    cells = len(eng.fetch_strata()[0])
+
+    e2e = None
+    if not args.no_e2e:
+        host = []
+        for x, m in ((q, n), (s, n), (qs, nq), (qt, nq)):
+            h = pinned_empty(m)
+            h[:] = x.cpu().numpy()
+            host.append(h)
+        eng.classify_chunk(*host)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = 3
+        for _ in range(e2e_steps):
+            eng.classify_chunk(*host)
+            nc = len(eng.fetch_strata()[0])
+        barrier()
+        ems = (time.perf_counter() - t0) * 1e3
+        e2e = {'value': n * world * e2e_steps / (ems * 1e-3), 'unit': UNIT,
+               'h2d_bytes_per_step': int(8 * n + 8 * nq),
+               'd2h_bytes_per_step': int(nc * 28), 'steps': e2e_steps,
+               'ms_per_step': ems / e2e_steps,
+               'api': 'wk_classify_chunk(host SoA + per-query sample and '
+                      'stratum) + wk_fetch_strata'}
+
+    cpu = None
+    parity = None
+    if rank == 0 and not args.no_cpu:
+        from oracle import oracle as O
+        from woltka_b200.engine import Engine
+        m = min(n, 5_000_000)
+        qh = q[:m + 64].cpu().numpy()
+        while m < len(qh) and qh[m] == qh[m - 1]:
+            m += 1
+        qh, sh = qh[:m], s[:m].cpu().numpy()
+        mq = int(qh[-1]) + 1
+        qsh, qth = qs[:mq].cpu().numpy(), qt[:mq].cpu().numpy()
+        node_rank = np.zeros(T, dtype=np.int32)
+        node_rank[0] = -1
+        # the oracle walks the tree: gene -> KO node (or none) as sub_node
+        sub_node = tab[0].astype(np.int32)
+        threads = host_threads()
+        t0 = time.perf_counter()
+        exp = O.classify(qh, sh, parent=parent, node_rank=node_rank, root=0,
+                         sub_node=sub_node, sub_feat=None,
+                         kinds=np.array([KIND_RANK], dtype=np.int32),
+                         target_rank=[0], flags=0, n_samples=S_loc,
+                         n_features=T, q_sample=qsh, q_stratum=qth,
+                         n_threads=threads)
+        dt = time.perf_counter() - t0
+        from tests import cases
+        e2 = Engine(torch.cuda.current_device())
+        e2.set_tree(parent, 0)
+        e2.set_plan(np.array([KIND_RANK], dtype=np.int32), 0, 0.0, S_loc, T)
+        e2.set_subjects(tab, None)
+        e2.classify_chunk(qh, sh, qsh, qth, 0)
+        got = cases.collect(e2, S_loc, T)
+        e2.close()
+        parity = bool(np.array_equal(got[0], exp[0]) and got[1] == exp[1] and
+                      got[2] == exp[2])
+        cpu = {'value': m / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+               'sample': f'{m} records of the timed batch, C restatement of '
+                         f'the reference path (oracle/woltka_oracle.c), '
+                         f'{threads} OpenMP threads'}
+        assert parity, 'GPU strata cells differ from the oracle on the sample'
+
+    if rank == 0:
+        achieved = 8 * n / (k_ms * 1e-3) / 1e9
+        print(json.dumps({
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32',
+            'data': 'synthetic', 'config': workload_config(args, ['ko']),
+            'roofline': {'bound': 'hbm', 'achieved': achieved,
+                         'peak': hbm_peak, 'unit': 'GB/s',
+                         'frac': achieved / hbm_peak, 'traffic': None,
+                         'kernel': eng.last_kernel(), 'kernel_ms': k_ms,
+                         'peak_source': peak_src,
+                         'algorithmic_bytes_per_record': 8},
+            'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
+            'clocks': clocks, 'parity_on_sample': parity,
+            'strata_cells': cells}))
     if world > 1:
         dist.destroy_process_group()
 

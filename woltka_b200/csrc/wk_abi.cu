@@ -263,6 +263,7 @@ int wk_create(int device, wk_ctx **out) {
   CK(cudaMemset(c->small.p, 0, 64));
   c->ovf_cap = 1 << 20;
   if (const char *ev = getenv("WK_TUNE_BLOCK")) c->tune_block = atoi(ev);
+  if (const char *ev = getenv("WK_TUNE_GRID")) c->tune_grid = atoi(ev);
   TRY(c->ovf_key.reserve(c->ovf_cap * 8));
   TRY(c->ovf_den.reserve(c->ovf_cap * 4));
   {
