@@ -73,6 +73,8 @@ def reduce_sam(src, dst):
 
 
 def copy_dir(src, dst, reduce=False):
+    if ONLY is not None and os.path.isdir(dst):
+        return
     os.makedirs(dst, exist_ok=True)
     for fn in sorted(os.listdir(src)):
         sp = join(src, fn)
@@ -124,6 +126,9 @@ def subjects_of(files, fmt=None, trimsub=None, mapper=None):
 
 
 CASES = []
+# `make_golden.py --only name[,name...]`: add cases to an existing tests/golden/
+# (the bundled inputs under data/ are kept, other fixtures are not rewritten)
+ONLY = None
 
 
 def run_case(name, input_rel, *, hier=None, ranks, coords_rel=None,
@@ -131,6 +136,8 @@ def run_case(name, input_rel, *, hier=None, ranks, coords_rel=None,
              trimsub=None, uniq=False, major=None, above=False, subok=False,
              unasgd=False, exclude=None, chunk=None, note='', maps=False,
              name_as_id=False, sizes=None):
+    if ONLY is not None and name not in ONLY:
+        return
     input_fp = join(OUT, input_rel)
     samples_, files, demux_ = W.parse_samples(input_fp, None, samples, demux)
     tree = rankdic = namedic = root = None
@@ -284,14 +291,15 @@ def bundled():
                        sorted(os.listdir(join(OUT, 'burst')))]) | \
         subjects_of([join(OUT, 'bowtie2', f) for f in
                      sorted(os.listdir(join(OUT, 'bowtie2')))][:1])
-    with lzma.open(join(fun, 'coords.txt.xz'), 'rt') as fi, \
-            lzma.open(join(OUT, 'coords.txt.xz'), 'wt') as fo:
-        keep = False
-        for line in fi:
-            if line[0] in '>#':
-                keep = line[1:].strip() in hit
-            if keep:
-                fo.write(line)
+    if ONLY is None or not os.path.exists(join(OUT, 'coords.txt.xz')):
+        with lzma.open(join(fun, 'coords.txt.xz'), 'rt') as fi, \
+                lzma.open(join(OUT, 'coords.txt.xz'), 'wt') as fo:
+            keep = False
+            for line in fi:
+                if line[0] in '>#':
+                    keep = line[1:].strip() in hit
+                if keep:
+                    fo.write(line)
     fmaps = dict(map_fps=[join(fun, 'uniref', 'uniref.map.xz'),
                           join(fun, 'go', 'process.tsv.xz')], map_rank=True)
     run_case('burst_orf', 'burst', ranks=None, coords_rel='coords.txt.xz',
@@ -312,9 +320,10 @@ def bundled():
     os.makedirs(join(OUT, 'sizes'), exist_ok=True)
     subs = sorted(subjects_of([join(OUT, 'bt2sho', f) for f in
                                sorted(os.listdir(join(OUT, 'bt2sho')))]))
-    with open(join(OUT, 'sizes', 'bt2sho.length.map'), 'w') as f:
-        for x in subs:
-            f.write(f'{x}\t{1000000 + (int(x[1:]) % 977) * 1013}\n')
+    if ONLY is None:
+        with open(join(OUT, 'sizes', 'bt2sho.length.map'), 'w') as f:
+            for x in subs:
+                f.write(f'{x}\t{1000000 + (int(x[1:]) % 977) * 1013}\n')
     run_case('bt2sho_order_sizes', 'bt2sho', hier=nodes,
              ranks='order,genus,none', sizes=join('sizes', 'bt2sho.length.map'),
              note='cf. bt2sho.order.cpm.tsv: size-weighted, multi-hit data')
@@ -324,6 +333,14 @@ def bundled():
     run_case('burst_process_sizes', 'burst', hier=fmaps, ranks='process,none',
              coords_rel='coords.txt.xz', sizes='.',
              note='cf. bt2sho.component.rpk.tsv: ordinal, gene lengths as sizes')
+    # read maps of the ordinal path (the gene sets of ordinal_mapper through
+    # assign_readmap / write_readmap)
+    run_case('burst_process_map', 'burst', hier=fmaps, ranks='process,none',
+             coords_rel='coords.txt.xz', maps=True,
+             note='--coords with --outmap: gene and process read maps')
+    run_case('bowtie2_orf_s01_map', join('bowtie2', 'S01.sam.xz'), ranks=None,
+             coords_rel='coords.txt.xz', overlap=81, maps=True,
+             note='--coords with --outmap on SAM, no hierarchy')
 
 
 def synthetic():
@@ -384,6 +401,15 @@ def synthetic():
 
 
 if __name__ == '__main__':
+    if len(sys.argv) > 2 and sys.argv[1] == '--only':
+        ONLY = set(sys.argv[2].split(','))
+        bundled()
+        with open(join(HERE, 'INDEX.json')) as f:
+            old = json.load(f)
+        with open(join(HERE, 'INDEX.json'), 'w') as f:
+            json.dump(old + [c for c in CASES if c not in old], f)
+        shutil.rmtree(stub)
+        sys.exit(0)
     if os.path.isdir(OUT):
         shutil.rmtree(OUT)
     os.makedirs(OUT)

@@ -117,11 +117,20 @@ class GeneIndex:
         table to its engine(s) — once per session."""
         if self._bound is session:
             return
-        subj = np.fromiter((session.subject(g) for g in self.gene_ids),
-                           dtype=np.int32, count=len(self.gene_ids))
+        subj = self.subjects(session)
         for eng in session.engines:
             eng.ordinal_set_genes(self.contig_off, self.gbeg, self.gend, subj)
         self._bound = session
+
+    def subjects(self, session):
+        """Subject index of every gene in `session` (interning the gene
+        identifiers on first use)."""
+        if getattr(self, '_subj_of', None) is not session:
+            self._subj = np.fromiter(
+                (session.subject(g) for g in self.gene_ids), dtype=np.int32,
+                count=len(self.gene_ids))
+            self._subj_of = session
+        return self._subj
 
 
 def iter_records(fh, fmt=None, excl=None, n=2**20):

@@ -41,6 +41,8 @@ class Session:
         if engine_factory is None:
             from .engine import Engine
             engine_factory = Engine
+        self._engine_factory, self._device = engine_factory, device
+        self._matcher = None
         self.ranks = list(ranks)
         self.order = list(dict.fromkeys(self.ranks))   # unique, first-seen
         self.mult = Counter(self.ranks)
@@ -112,6 +114,9 @@ class Session:
         for eng in self.engines:
             eng.close()
         self.engines = []
+        if self._matcher is not None:
+            self._matcher.close()
+            self._matcher = None
 
     # -- vocabularies ------------------------------------------------------
     def subject(self, name):
@@ -326,8 +331,7 @@ class Session:
         use_strata = strata_of is not None
         qindex = {}
         q = np.empty(len(qnames), dtype=np.int32)
-        q_sample, q_stratum = [], []
-        keep = np.ones(len(qnames), dtype=bool)
+        q_sample, q_stratum, reads = [], [], []
         for i, query in enumerate(qnames):
             j = qindex.get(query)
             if j is None:
@@ -338,6 +342,7 @@ class Session:
                         sname = None
                 else:
                     sname, read = sample_name, query
+                reads.append(read)
                 if sname is None and demux:
                     q_sample.append(-1)
                     q_stratum.append(-1)
@@ -370,8 +375,38 @@ class Session:
         q_sample = np.asarray(q_sample, dtype=np.int32)
         q_stratum = np.asarray(q_stratum, dtype=np.int32) if use_strata \
             else None
+        if self.rank2dir is not None:
+            return self._ordinal_chunk_with_maps(genes, cols, th, q_sample,
+                                                 q_stratum, reads)
         for eng in self.engines:
             eng.ordinal_chunk(*cols, th, q_sample, q_stratum)
+
+    def _ordinal_chunk_with_maps(self, genes, cols, th, q_sample, q_stratum,
+                                 reads):
+        """--coords with --outmap: the matcher alone runs first (a plan-less
+        engine), its (query, gene) pairs come back and go through the plain
+        path, whose kernel also writes the per-record assignment column the
+        read maps are made of (workflow.py:1042-1046 on the gene sets of
+        ordinal.flush_chunk).  Lines are in the order of the reads' first
+        records; the reference's order follows its per-contig sweep."""
+        if getattr(self, '_matcher', None) is None:
+            self._matcher = self._engine_factory(self._device)
+            self._matcher.ordinal_set_genes(
+                genes.contig_off, genes.gbeg, genes.gend,
+                np.arange(len(genes.gbeg), dtype=np.int32))
+            self._matcher.ordinal_enable_pairs()
+        self._matcher.ordinal_chunk(*cols, th)
+        r, g = self._matcher.ordinal_pairs()      # sorted by (query, gene)
+        live = q_sample[r] >= 0
+        r, g = r[live], g[live]
+        if not len(r):
+            return
+        s2 = genes.subjects(self)[g]
+        for eng in self.engines:
+            eng.classify_chunk(r, s2, q_sample, q_stratum)
+        qs_u, starts = np.unique(r, return_index=True)
+        self._write_readmaps(len(r), [reads[j] for j in qs_u.tolist()],
+                             starts.tolist() + [len(r)], q_sample[qs_u])
 
     def _sized_results(self, data):
         """--sizes: sum over subjects of weight x the exact share the subject

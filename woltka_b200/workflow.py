@@ -17,9 +17,10 @@ unchanged by its `workflow()`.
 Read maps (`rank2dir`) come from a per-record
 assignment column the kernel writes next to the counts; size-weighted counts
 (`sizes`, row F4) from the kernels' exact (subject, feature) shares, weighted
-on the host.  Not re-implemented in this round: coverage (`outcov_dir`, row
-F5), read maps of the ordinal path and `sizes` together with `stratmap` raise
-NotImplementedError instead of silently falling back.
+on the host.  With `--coords` the read maps are made from the matcher's
+(query, gene) pairs sent through the plain path.  Not re-implemented in this
+round: coverage (`outcov_dir`, row F5) and `sizes` together with `stratmap`
+raise NotImplementedError instead of silently falling back.
 """
 import bz2
 import gzip
@@ -179,10 +180,6 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
     `round_profiles` the two are identical.
     """
     is_ordinal = getattr(mapper, 'func', None) is ordinal_mapper
-    if rank2dir is not None and is_ordinal:
-        raise NotImplementedError(
-            'Read-map output (--outmap) with --coords is not part of the GPU '
-            'hot path yet.')
     if sizes and stratmap:
         raise NotImplementedError(
             'Size-normalised counting (--sizes) together with --stratify is '
