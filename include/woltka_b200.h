@@ -242,6 +242,22 @@ int wk_classify_parsed(wk_ctx *ctx, const int32_t *sample_map, int32_t n_map,
  * caller-side NCCL reduce (torch.distributed) across GPUs. */
 int wk_counts_device(wk_ctx *ctx, void **d_ptr, int64_t *n_elems);
 
+/* ---- subject coverage (--outcov) ----------------------------------------------
+ * Replaces range.parse_ranges / merge_ranges / calc_coverage
+ * (woltka/range.py:79-180; called from workflow.py:312-313 and :346-350): the
+ * ranges of every subject covered by at least one alignment, per sample.
+ * wk_cover_add appends n intervals [beg, end] (as the extended parsers give
+ * them, align.py:382-398) of (sample, subject) index pairs (sample < 4096,
+ * subject < 2^21, 0 <= beg, end < 2^31); the store merges itself when it grows
+ * large.  wk_cover_merge sorts and fuses overlapping or touching intervals
+ * (`cend >= start`) and reports the number of merged ranges; wk_cover_fetch
+ * returns them ordered by (sample, subject, beg). */
+int wk_cover_add(wk_ctx *ctx, const int32_t *sample, const int32_t *subject,
+                 const int32_t *beg, const int32_t *end, int64_t n);
+int wk_cover_merge(wk_ctx *ctx, int64_t *n_ranges);
+int wk_cover_fetch(wk_ctx *ctx, int32_t *sample, int32_t *subject, int32_t *beg,
+                   int32_t *end, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

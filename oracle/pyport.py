@@ -209,3 +209,21 @@ def classify_chunks(chunks, ranks, tree=None, rankdic=None, root=None,
                 for k, v in counts.items():           # util.sum_dict
                     total[k] = total.get(k, 0) + v
     return data
+
+
+def merge_ranges(ranges):
+    """range.merge_ranges (range.py:79-109): sort the (start, end) pairs of an
+    interleaved list and fuse those that overlap or touch (`cend >= start`)."""
+    res = []
+    cstart = cend = None
+    for start, end in sorted(zip(ranges[0::2], ranges[1::2])):
+        if cend is None:
+            cstart, cend = start, end
+        elif cend >= start:
+            cend = max(cend, end)
+        else:
+            res.extend((cstart, cend))
+            cstart, cend = start, end
+    if cend is not None:
+        res.extend((cstart, cend))
+    return res

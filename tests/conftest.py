@@ -19,3 +19,10 @@ def engine():
     eng = Engine(0)
     yield eng
     eng.close()
+
+
+@pytest.fixture
+def engine_factory():
+    """A function that makes a fresh Engine on device 0 (the caller closes it)."""
+    from woltka_b200.engine import Engine
+    return lambda: Engine(0)

@@ -135,7 +135,7 @@ def run_case(name, input_rel, *, hier=None, ranks, coords_rel=None,
              overlap=80, strata_rel=None, fmt=None, demux=None, samples=None,
              trimsub=None, uniq=False, major=None, above=False, subok=False,
              unasgd=False, exclude=None, chunk=None, note='', maps=False,
-             name_as_id=False, sizes=None):
+             name_as_id=False, sizes=None, cov=None):
     if ONLY is not None and name not in ONLY:
         return
     input_fp = join(OUT, input_rel)
@@ -143,8 +143,9 @@ def run_case(name, input_rel, *, hier=None, ranks, coords_rel=None,
     tree = rankdic = namedic = root = None
     if hier:
         tree, rankdic, namedic, root = W.build_hierarchy(**hier)
+    covdir = tempfile.mkdtemp() if cov else None
     mapper, chunk_ = W.build_mapper(
-        join(OUT, coords_rel) if coords_rel else None, None, overlap, chunk,
+        join(OUT, coords_rel) if coords_rel else None, covdir, overlap, chunk,
         {})
     ranks_, _ = W.prepare_ranks(ranks, None, tree, rankdic)
     stratmap = W.parse_strata(join(OUT, strata_rel), samples_) \
@@ -162,7 +163,15 @@ def run_case(name, input_rel, *, hier=None, ranks, coords_rel=None,
     data = W.classify(mapper, files, samples_, fmt, demux_, trimsub, tree,
                       rankdic, namedic if name_as_id else None, root, ranks_,
                       rank2dir, None, uniq, major, above, subok, sizemap, unasgd,
-                      stratmap, excl, chunk_, 1024, {}, None, None)
+                      stratmap, excl, chunk_, 1024, {}, covdir,
+                      None if cov in (None, True) else cov)
+    expected_cov = None
+    if cov:
+        expected_cov = {}
+        for fn in sorted(os.listdir(covdir)):
+            with open(join(covdir, fn)) as fh:
+                expected_cov[fn] = fh.read()
+        shutil.rmtree(covdir)
     expected_maps = None
     if maps:
         expected_maps = {}
@@ -220,6 +229,7 @@ def run_case(name, input_rel, *, hier=None, ranks, coords_rel=None,
         'exclude': sorted(excl) if excl else None, 'coords': coords_rel,
         'overlap': overlap, 'prefix': prefix, 'strata': strata_rel,
         'chunk': chunk, 'expected_maps': expected_maps, 'sizes': sizemap,
+        'cov': cov, 'expected_cov': expected_cov,
         'namedic': ({k: v for k, v in namedic.items() if k in tree_small}
                     if name_as_id and tree_small is not None else None),
         'expected_raw': enc(raw),
@@ -333,6 +343,15 @@ def bundled():
     run_case('burst_process_sizes', 'burst', hier=fmaps, ranks='process,none',
              coords_rel='coords.txt.xz', sizes='.',
              note='cf. bt2sho.component.rpk.tsv: ordinal, gene lengths as sizes')
+    # subject coverage (--outcov; range.py): SAM with CIGAR spans, multi-hit
+    # reads, five samples; BED-like and GFF-like coordinates
+    run_case('bowtie2_ogu_cov', 'bowtie2', ranks=None, cov=True,
+             note='--outcov: bowtie2 SAM, default (BED-like) coordinates')
+    run_case('bt2sho_genus_cov_gff', 'bt2sho', hier=nodes, ranks='genus',
+             cov='gff', note='--outcov --outcov-fmt gff with a hierarchy')
+    run_case('blastn_species_cov', join('blastn', 'mux.b6o.xz'),
+             hier=nodes, ranks='species', cov='1i', samples='S01,S03',
+             note='--outcov on demultiplexed b6o, sample whitelist, 1i')
     # read maps of the ordinal path (the gene sets of ordinal_mapper through
     # assign_readmap / write_readmap)
     run_case('burst_process_map', 'burst', hier=fmaps, ranks='process,none',

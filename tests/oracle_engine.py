@@ -147,6 +147,23 @@ class OracleEngine:
             return
         self.classify_chunk(qidx[r], gsub[g], q_sample, q_stratum, sample)
 
+    # -- subject coverage ----------------------------------------------------
+    def cover_add(self, sample, subject, beg, end):
+        store = self.__dict__.setdefault('cover', {})
+        for sm, sb, b, e in zip(*[np.asarray(x).tolist()
+                                  for x in (sample, subject, beg, end)]):
+            store.setdefault((sm, sb), []).extend((b, e))
+
+    def cover_ranges(self):
+        from oracle import pyport
+        rows = []
+        for (sm, sb), ranges in sorted(self.__dict__.get('cover', {}).items()):
+            merged = pyport.merge_ranges(ranges)
+            rows.extend((sm, sb, merged[k], merged[k + 1])
+                        for k in range(0, len(merged), 2))
+        cols = np.asarray(rows, dtype=np.int32).reshape(-1, 4)
+        return [np.ascontiguousarray(cols[:, k]) for k in range(4)]
+
     # -- results -----------------------------------------------------------
     def fetch_counts(self):
         return self.units.copy()

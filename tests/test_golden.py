@@ -72,7 +72,11 @@ def run_case(name, engine_factory=None):
     else:
         files = [join(inp, k) if isdir(inp) else inp for k in case['files']]
     coords = join(DATA, case['coords']) if case['coords'] else None
-    mapper, chunk = build_mapper(coords, None, case['overlap'], case['chunk'])
+    covdir = None
+    if case.get('cov'):
+        import tempfile
+        covdir = tempfile.mkdtemp()
+    mapper, chunk = build_mapper(coords, covdir, case['overlap'], case['chunk'])
     if coords:
         kw = dict(mapper.keywords)
         assert kw['th'] == case['overlap'] / 100
@@ -106,7 +110,15 @@ def run_case(name, engine_factory=None):
         subok=case['subok'], unasgd=case['unasgd'], stratmap=stratmap,
         exclude=set(case['exclude']) if case['exclude'] else None,
         chunk=chunk, _engine_factory=engine_factory, rank2dir=rank2dir,
-        namedic=case.get('namedic'), sizes=case.get('sizes'))
+        namedic=case.get('namedic'), sizes=case.get('sizes'),
+        outcov_dir=covdir,
+        outcov_fmt=None if case.get('cov') in (None, True) else case['cov'])
+    if covdir is not None:
+        got_cov = {}
+        for fn in sorted(os.listdir(covdir)):
+            with open(join(covdir, fn)) as fh:
+                got_cov[fn] = fh.read()
+        assert got_cov == case['expected_cov'], 'coverage files differ'
     if rank2dir is not None:
         maps = {}
         for r, d in rank2dir.items():

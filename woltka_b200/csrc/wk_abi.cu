@@ -16,6 +16,7 @@
 #include "wk_classify.cuh"
 #include "wk_ordinal.cuh"
 #include "wk_seg.cuh"
+#include "wk_cover.cuh"
 #include "wk_sweep.cuh"
 #include "wk_parse.cuh"
 
@@ -161,6 +162,8 @@ struct wk_ctx {
   int32_t n_levels = 0, level_off[40];
   std::vector<int64_t> dir_lo, dir_hi;  // per entry: range of the table values
   // overflow + err
+  DevBuf cov_keys, cov_ends;  // coverage store (wk_cover.cuh)
+  int64_t cov_n = 0, cov_cap = 0;
   DevBuf longlist;  // classify_seg_kernel: [0] = count, then first records of long queries
   DevBuf ovf_key, ovf_den, small;  // small: [0]=ovf_n [1]=sh_used [2]=n_pairs [3]=cursor, err after
   int64_t ovf_cap = 0;
@@ -357,7 +360,7 @@ int wk_destroy(wk_ctx *c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   DevBuf *bufs[] = {&c->parent, &c->cnt, &c->tab, &c->tab16, &c->sub_node,
-                    &c->ovf_key, &c->ovf_den, &c->small, &c->longlist, &c->sh_keys,
+                    &c->ovf_key, &c->ovf_den, &c->small, &c->longlist, &c->cov_keys, &c->cov_ends, &c->sh_keys,
                     &c->sh_vals, &c->dq, &c->ds, &c->dqsamp, &c->dqstrat,
                     &c->scratch, &c->dcontig, &c->dbeg, &c->dend, &c->dlen,
                     &c->cinfo, &c->genes, &c->pair_q, &c->pair_s, &c->pair_r,
@@ -1614,6 +1617,141 @@ int wk_fetch_assignments(wk_ctx *c, int32_t *out, int64_t n_rec) {
 }
 
 // ---- SAM reader (wk_parse.cuh) ---------------------------------------------------
+}  // extern "C"
+
+// ---- subject coverage (wk_cover.cuh; range.py:112-180) ---------------------------
+static int cover_merge(wk_ctx *c) {
+  const int64_t n = c->cov_n;
+  if (n <= 1) return WK_OK;
+  if (n >= (1ll << 31)) return fail(WK_ERR_CAPACITY, "too many coverage intervals");
+  DevBuf k2, e2, ge, rm, op, rk, tmp;
+  TRY(k2.reserve((size_t)n * 8));
+  TRY(e2.reserve((size_t)n * 4));
+  size_t t1 = 0, t2 = 0, t3 = 0;
+  ull *K = c->cov_keys.as<ull>();
+  int32_t *E = c->cov_ends.as<int32_t>();
+  cub::DeviceRadixSort::SortPairs(nullptr, t1, K, k2.as<ull>(), E, e2.as<int32_t>(),
+                                  (int)n, 0, 64, c->stream);
+  TRY(ge.reserve((size_t)n * 8));
+  TRY(rm.reserve((size_t)n * 8));
+  TRY(op.reserve((size_t)n * 4));
+  TRY(rk.reserve((size_t)n * 4));
+  cub::DeviceScan::InclusiveScan(nullptr, t2, ge.as<ull>(), rm.as<ull>(), CovMax(), (int)n,
+                                 c->stream);
+  cub::DeviceScan::InclusiveSum(nullptr, t3, op.as<int32_t>(), rk.as<int32_t>(), (int)n,
+                                c->stream);
+  TRY(tmp.reserve(std::max(t1, std::max(t2, t3)) + 256));
+  CK(cub::DeviceRadixSort::SortPairs(tmp.p, t1, K, k2.as<ull>(), E, e2.as<int32_t>(), (int)n,
+                                     0, 64, c->stream));
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->sm_count * 16);
+  cover_groupend_kernel<<<grid, 256, 0, c->stream>>>(k2.as<ull>(), e2.as<int32_t>(), n,
+                                                     ge.as<ull>());
+  CK(cub::DeviceScan::InclusiveScan(tmp.p, t2, ge.as<ull>(), rm.as<ull>(), CovMax(), (int)n,
+                                    c->stream));
+  cover_open_kernel<<<grid, 256, 0, c->stream>>>(k2.as<ull>(), rm.as<ull>(), n,
+                                                 op.as<int32_t>());
+  CK(cub::DeviceScan::InclusiveSum(tmp.p, t3, op.as<int32_t>(), rk.as<int32_t>(), (int)n,
+                                   c->stream));
+  // the merged ranges replace the store
+  cover_scatter_kernel<<<grid, 256, 0, c->stream>>>(k2.as<ull>(), rm.as<ull>(),
+                                                    op.as<int32_t>(), rk.as<int32_t>(), n, K, E);
+  c->launches += 6;
+  CK(cudaGetLastError());
+  int32_t m = 0;
+  CK(cudaMemcpyAsync(&m, rk.as<int32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->cov_n = m;
+  for (DevBuf *b : {&k2, &e2, &ge, &rm, &op, &rk, &tmp}) b->release();
+  return WK_OK;
+}
+
+extern "C" {
+
+int wk_cover_add(wk_ctx *c, const int32_t *sample, const int32_t *subject,
+                 const int32_t *beg, const int32_t *end, int64_t n) {
+  if (!c) return fail(WK_ERR_ARG, "ctx is NULL");
+  TRY(use_device(c));
+  if (n < 0 || (n && (!sample || !subject || !beg || !end)))
+    return fail(WK_ERR_ARG, "bad interval columns");
+  if (n == 0) return WK_OK;
+  // parse_ranges' auto-compress: merge what is there before the store grows
+  // past 2^26 intervals
+  if (c->cov_n + n > c->cov_cap && c->cov_n > (1ll << 26)) TRY(cover_merge(c));
+  if (c->cov_n + n > c->cov_cap) {
+    const int64_t ncap = std::max<int64_t>(2 * c->cov_cap, c->cov_n + n + (1 << 16));
+    DevBuf nk, ne;
+    TRY(nk.reserve((size_t)ncap * 8));
+    TRY(ne.reserve((size_t)ncap * 4));
+    if (c->cov_n) {
+      CK(cudaMemcpyAsync(nk.p, c->cov_keys.p, (size_t)c->cov_n * 8, cudaMemcpyDeviceToDevice,
+                         c->stream));
+      CK(cudaMemcpyAsync(ne.p, c->cov_ends.p, (size_t)c->cov_n * 4, cudaMemcpyDeviceToDevice,
+                         c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+    }
+    c->cov_keys.release();
+    c->cov_ends.release();
+    c->cov_keys = nk;
+    c->cov_ends = ne;
+    c->cov_cap = ncap;
+  }
+  DevBuf st;
+  TRY(st.reserve((size_t)n * 16 + 64));
+  int32_t *d = st.as<int32_t>();
+  const int32_t *src[4] = {sample, subject, beg, end};
+  for (int i = 0; i < 4; ++i)
+    CK(cudaMemcpyAsync(d + (size_t)i * n, src[i], (size_t)n * 4, cudaMemcpyHostToDevice,
+                       c->stream));
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->sm_count * 16);
+  cover_pack_kernel<<<grid, 256, 0, c->stream>>>(d, d + n, d + 2 * n, d + 3 * n, n,
+                                                 c->cov_keys.as<ull>(),
+                                                 c->cov_ends.as<int32_t>(), c->cov_n,
+                                                 c->d_err() + 1);
+  c->launches++;
+  CK(cudaGetLastError());
+  int32_t bad = 0;
+  CK(cudaMemcpyAsync(&bad, c->d_err() + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  st.release();
+  if (bad) {
+    CK(cudaMemsetAsync(c->d_err() + 1, 0, 4, c->stream));
+    return fail(WK_ERR_ARG,
+                "coverage interval out of range (sample < 4096, subject < 2^21, "
+                "0 <= start, end < 2^31)");
+  }
+  c->cov_n += n;
+  return WK_OK;
+}
+
+int wk_cover_merge(wk_ctx *c, int64_t *n_ranges) {
+  if (!c || !n_ranges) return fail(WK_ERR_ARG, "bad arguments");
+  TRY(use_device(c));
+  TRY(cover_merge(c));
+  *n_ranges = c->cov_n;
+  return WK_OK;
+}
+
+int wk_cover_fetch(wk_ctx *c, int32_t *sample, int32_t *subject, int32_t *beg,
+                   int32_t *end, int64_t cap) {
+  if (!c || !sample || !subject || !beg || !end) return fail(WK_ERR_ARG, "bad arguments");
+  TRY(use_device(c));
+  const int64_t n = c->cov_n;
+  if (cap < n) return fail(WK_ERR_CAPACITY, "coverage output too small");
+  if (!n) return WK_OK;
+  std::vector<ull> keys((size_t)n);
+  CK(cudaMemcpyAsync(keys.data(), c->cov_keys.p, (size_t)n * 8, cudaMemcpyDeviceToHost,
+                     c->stream));
+  CK(cudaMemcpyAsync(end, c->cov_ends.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int64_t i = 0; i < n; ++i) {
+    const ull k = keys[(size_t)i];
+    sample[i] = (int32_t)(k >> (COV_SUBJECT_BITS + COV_POS_BITS));
+    subject[i] = (int32_t)((k >> COV_POS_BITS) & ((1u << COV_SUBJECT_BITS) - 1));
+    beg[i] = (int32_t)(k & COV_POS_MASK);
+  }
+  return WK_OK;
+}
+
 }  // extern "C"
 
 static const uint64_t kInternCap[2] = {1ull << 21, 1ull << 16};     // subjects, samples

@@ -328,6 +328,27 @@ class Engine:
         _lib.check(self.lib.wk_classify_parsed(
             self.ctx, _ptr(sm), 0 if sm is None else len(sm), sample))
 
+    # -- subject coverage (--outcov) ------------------------------------------
+    def cover_add(self, sample, subject, beg, end):
+        """Append intervals [beg, end] of (sample, subject) index pairs
+        (range.parse_ranges, range.py:112-151)."""
+        cols = [_i32(x) for x in (sample, subject, beg, end)]
+        if len({len(x) for x in cols}) != 1:
+            raise ValueError('interval columns differ in length')
+        _lib.check(self.lib.wk_cover_add(self.ctx, *[_ptr(x) for x in cols],
+                                         len(cols[0])))
+
+    def cover_ranges(self):
+        """Merged ranges (range.calc_coverage, range.py:154-180) as four
+        columns ordered by (sample, subject, beg)."""
+        n = C.c_int64()
+        _lib.check(self.lib.wk_cover_merge(self.ctx, C.byref(n)))
+        out = [np.empty(n.value, dtype=np.int32) for _ in range(4)]
+        if n.value:
+            _lib.check(self.lib.wk_cover_fetch(self.ctx, *[_ptr(x) for x in out],
+                                               n.value))
+        return out
+
     def counts_tensor(self):
         """Zero-copy torch view of the units table (for an NCCL reduce)."""
         import torch

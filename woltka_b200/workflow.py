@@ -18,9 +18,9 @@ Read maps (`rank2dir`) come from a per-record
 assignment column the kernel writes next to the counts; size-weighted counts
 (`sizes`, row F4) from the kernels' exact (subject, feature) shares, weighted
 on the host.  With `--coords` the read maps are made from the matcher's
-(query, gene) pairs sent through the plain path.  Not re-implemented in this
-round: coverage (`outcov_dir`, row F5) and `sizes` together with `stratmap`
-raise NotImplementedError instead of silently falling back.
+(query, gene) pairs sent through the plain path.  Subject coverage (`outcov_dir`, row F5) is
+accumulated and merged on the GPU (woltka_b200.coverage).  `sizes` together
+with `stratmap` raises NotImplementedError instead of silently falling back.
 """
 import bz2
 import gzip
@@ -32,9 +32,10 @@ from os.path import basename
 
 from .align import plain_mapper
 from .ordinal import load_gene_coords, ordinal_mapper, GeneIndex, iter_records
-from .session import Session
+from .session import Session, _split_sample
+from .coverage import range_mapper, Coverage, coverage_offsets
 
-__all__ = ['classify', 'build_mapper', 'readzip']
+__all__ = ['classify', 'build_mapper', 'readzip', 'range_mapper']
 
 _OPENERS = {'.gz': gzip.open, '.bz2': bz2.open, '.xz': lzma.open,
             '.lzma': lzma.open}
@@ -129,10 +130,7 @@ def build_mapper(coords_fp=None, outcov_dir=None, overlap=None, chunk=None,
         chunk = chunk or 2 ** 20
         return partial(ordinal_mapper, coords=coords, idmap=idmap,
                        prefix=prefix, th=overlap and overlap / 100), chunk
-    if outcov_dir:
-        raise NotImplementedError(
-            'Subject coverage (--outcov) is not part of the GPU hot path.')
-    return plain_mapper, chunk or 1024
+    return (range_mapper if outcov_dir else plain_mapper), chunk or 1024
 
 
 def _device_format(fileobj, fmt):
@@ -185,8 +183,12 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
             'Size-normalised counting (--sizes) together with --stratify is '
             'not part of the GPU hot path yet.')
     if outcov_dir:
-        raise NotImplementedError(
-            'Subject coverage (--outcov) is not part of the GPU hot path.')
+        coverage_offsets(outcov_fmt)     # an invalid format fails up front
+        if is_ordinal:
+            # (the reference breaks on the gene sets of ordinal_mapper,
+            # range.py:142: `subjects.items()`)
+            raise ValueError('Subject coverage (--outcov) cannot be combined '
+                             'with --coords.')
 
     genes = None
     if is_ordinal:
@@ -199,6 +201,7 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
                    rank2dir, outzip, namedic, sizes)
     samset = set(samples) if samples else None
     strata_cache = {}
+    cover = Coverage(sess.engines[0]) if outcov_dir else None
 
     def strata_of(sname):
         try:
@@ -249,6 +252,15 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
                     for qryque, subque in mapper(iter(fileobj), fmt=fmt,
                                                  excl=exclude, n=chunk):
                         nqry += len(qryque)
+                        if cover is not None:
+                            # range.parse_ranges on the demultiplexed chunk
+                            # (workflow.py:312-313)
+                            for query, ranges in zip(qryque, subque):
+                                sam = _split_sample(query)[0] if demux \
+                                    else sname
+                                if not demux or samset is None or \
+                                        sam in samset:
+                                    cover.add(sam, ranges)
                         sess.add_chunk(qryque, subque, **kwargs)
                         istep = nqry // 1000000 - nstep
                         if istep:
@@ -259,6 +271,10 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
                     fileobj.close()
             _echo(' Done.')
             _echo(f'  Number of sequences classified: {nqry}.')
+        if cover is not None:
+            _echo('Calculating per sample coverage...', nl=False)
+            cover.write(outcov_dir, outcov_fmt)
+            _echo(' Done.')
         _echo('Classification completed.')
         data = sess.results()
     finally:
