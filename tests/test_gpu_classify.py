@@ -21,13 +21,17 @@ def big_case():
     return cases.Case(synth.Taxonomy(seed=42))
 
 
-def _lean_kernel(entries, mode):
-    """The kernel a one-sample plan takes: one entry (a rank, or `none`
-    through a table) in default or --uniq mode -> classify_seg_kernel; other
-    one-kind plans -> classify_fast_kernel."""
-    if len(entries) == 1 and entries[0] != 'free' and (
-            mode in ('default', 'uniq', 'uniq+unassigned') or
-            entries[0] == 'none'):     # assign_none knows no --major / --above
+def _lean_kernel(entries, mode, seg_above=False):
+    """The kernel a plan of one kind takes (ranks only, or `none` only, staged
+    tables, no strata, no read map): default or --uniq -> classify_seg_kernel,
+    one launch per entry; --major and --above -> classify_fast_kernel (--above
+    -> classify_seg_kernel with WK_SEG_ABOVE).  assign_none knows no --major /
+    --above."""
+    none = all(x == 'none' for x in entries)
+    if not none and any(x in ('none', 'free') for x in entries):
+        return 'classify_kernel'
+    if none or mode.startswith(('default', 'uniq')) or \
+            (seg_above and mode.startswith('above')):
         return 'classify_seg_kernel'
     return 'classify_fast_kernel'
 
@@ -255,14 +259,22 @@ def test_lca_on_a_tree_that_is_not_level_ordered(engine):
     assert np.array_equal(got, exp)
 
 
-@pytest.mark.parametrize('mode', ['default', 'above', 'major+unassigned'])
+@pytest.mark.parametrize('noseg', ['', '1', 'above'])
+@pytest.mark.parametrize('mode', ['default', 'above', 'major+unassigned',
+                                  'uniq+unassigned'])
 @pytest.mark.parametrize('entries', [['genus'], ['phylum', 'genus', 'species'],
                                      ['none']])
 def test_contiguous_samples_take_the_run_per_lane_kernel(engine, small_case,
-                                                         entries, mode):
+                                                         entries, mode,
+                                                         monkeypatch, noseg):
     """Samples that follow one another in the stream (one file per sample):
-    the run-per-lane kernel works segment by segment; a dropped sample (-1)
-    in the middle and long queries are part of the stream."""
+    the lane-per-record and the run-per-lane kernel work segment by segment;
+    a dropped sample (-1) in the middle and long queries are part of the
+    stream."""
+    if noseg == 'above':   # the lane-per-record kernel's --above variant
+        monkeypatch.setenv('WK_SEG_ABOVE', '1')
+    elif noseg:
+        monkeypatch.setenv('WK_NO_SEG', noseg)
     q, s = cases.random_hits(small_case, 60000, seed=77, long_every=5000,
                              long_len=90)
     nq = int(q.max()) + 1
@@ -276,7 +288,9 @@ def test_contiguous_samples_take_the_run_per_lane_kernel(engine, small_case,
         _same(cases.run_engine(engine, small_case, entries, fl, 0.7, q, s,
                                n_samples=6, q_sample=q_sample, chunks=chunks),
               ref)
-    assert engine.last_kernel() == 'classify_fast_kernel'
+    assert engine.last_kernel() == (
+        'classify_fast_kernel' if noseg == '1' else
+        _lean_kernel(entries, mode, noseg == 'above'))
 
 
 def test_which_kernel_runs(engine, small_case):
@@ -289,6 +303,9 @@ def test_which_kernel_runs(engine, small_case):
     cases.run_engine(engine, small_case, ['genus'], cases.MODES['major'], 0.8, q, s)
     assert engine.last_kernel() == 'classify_fast_kernel'
     cases.run_engine(engine, small_case, ['phylum', 'genus'], 0, 0, q, s)
+    assert engine.last_kernel() == 'classify_seg_kernel'
+    cases.run_engine(engine, small_case, ['phylum', 'genus'],
+                     cases.MODES['major'], 0.8, q, s)
     assert engine.last_kernel() == 'classify_fast_kernel'
     cases.run_engine(engine, small_case, ['none', 'free'], 0, 0, q, s)
     assert engine.last_kernel() == 'classify_kernel'
@@ -392,14 +409,16 @@ def test_short_runs_and_fewer_warps(engine, small_case, monkeypatch, r, block):
         engine.set_tuning(0, 0, 0)
 
 
-@pytest.mark.parametrize('noseg', ['', '1'])
+@pytest.mark.parametrize('noseg', ['', '1', 'above'])
 def test_randomised_shapes_both_kernels_agree(engine, small_case, monkeypatch,
                                               noseg):
     """Many small random streams whose sizes straddle the warp-tile and run
     boundaries (32 x 13 = 416 records, runs of 13; tiles of 512), with long
     queries and repeats placed at random: lane-per-record kernel ==
     run-per-lane kernel == window kernel == oracle."""
-    if noseg:
+    if noseg == 'above':
+        monkeypatch.setenv('WK_SEG_ABOVE', '1')
+    elif noseg:
         monkeypatch.setenv('WK_NO_SEG', noseg)
     rng = np.random.default_rng(2026)
     ents = (['genus'], ['none'], ['phylum', 'species'])
@@ -419,7 +438,8 @@ def test_randomised_shapes_both_kernels_agree(engine, small_case, monkeypatch,
         exp = cases.run_oracle(small_case, ent, fl, th, q, s)
         got = cases.run_engine(engine, small_case, ent, fl, th, q, s)
         assert engine.last_kernel() == (
-            'classify_fast_kernel' if noseg else _lean_kernel(ent, mode))
+            'classify_fast_kernel' if noseg == '1' else
+            _lean_kernel(ent, mode, noseg == 'above'))
         _same(got, exp)
         engine.set_tuning(0, 1, 0)
         try:

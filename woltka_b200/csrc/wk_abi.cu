@@ -93,7 +93,14 @@ __global__ void rehash_kernel(const ull *ok, const ull *ov, uint64_t ocap,
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t st = (size_t)gridDim.x * blockDim.x;
   for (; i < ocap; i += st)
-    if (ok[i] != ~0ull) strat_add(P, ok[i], ov[i]);
+    if (ok[2 * i] != ~0ull) strat_add(P, ok[2 * i], ov[2 * i]);
+}
+
+// empty strata slots: key = all ones, units = 0
+__global__ void fill_slots_kernel(ull *p, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t st = (size_t)gridDim.x * blockDim.x;
+  for (; i < 2 * n; i += st) p[i] = (i & 1) ? 0ull : ~0ull;
 }
 
 __global__ void compact_hash_kernel(const ull *k, const ull *v, uint64_t cap,
@@ -101,10 +108,10 @@ __global__ void compact_hash_kernel(const ull *k, const ull *v, uint64_t cap,
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t st = (size_t)gridDim.x * blockDim.x;
   for (; i < cap; i += st)
-    if (k[i] != ~0ull) {
+    if (k[2 * i] != ~0ull) {
       ull at = atomicAdd(cursor, 1ull);
-      outk[at] = k[i];
-      outv[at] = v[i];
+      outk[at] = k[2 * i];
+      outv[at] = v[2 * i];
     }
 }
 
@@ -209,6 +216,7 @@ static int use_device(wk_ctx *c) {
   return WK_OK;
 }
 
+static int fill_slots(wk_ctx *c, ull *p, size_t n);
 static int fill_u64(wk_ctx *c, ull *p, size_t n, ull v) {
   if (!n) return WK_OK;
   if (v == 0) {
@@ -332,15 +340,15 @@ int wk_create(int device, wk_ctx **out) {
         (const void *)classify_fast_kernel<WK_KIND_NONE_ID, FX_FRAC, 13, true>,
         (const void *)classify_fast_kernel<WK_KIND_NONE_ID, FX_UNIQ, 13, false>,
         (const void *)classify_fast_kernel<WK_KIND_NONE_ID, FX_UNIQ, 13, true>};
-    const void *seg[] = {
-        (const void *)classify_seg_kernel<WK_KIND_RANK, FX_FRAC, 512>,
-        (const void *)classify_seg_kernel<WK_KIND_RANK, FX_FRAC, 256>,
-        (const void *)classify_seg_kernel<WK_KIND_RANK, FX_UNIQ, 512>,
-        (const void *)classify_seg_kernel<WK_KIND_RANK, FX_UNIQ, 256>,
-        (const void *)classify_seg_kernel<WK_KIND_NONE, FX_FRAC, 512>,
-        (const void *)classify_seg_kernel<WK_KIND_NONE, FX_FRAC, 256>,
-        (const void *)classify_seg_kernel<WK_KIND_NONE, FX_UNIQ, 512>,
-        (const void *)classify_seg_kernel<WK_KIND_NONE, FX_UNIQ, 256>};
+#define WK_SEGV(KD, MD)                                              \
+  (const void *)classify_seg_kernel<KD, MD, 512, false>,             \
+      (const void *)classify_seg_kernel<KD, MD, 512, true>,          \
+      (const void *)classify_seg_kernel<KD, MD, 256, false>,         \
+      (const void *)classify_seg_kernel<KD, MD, 256, true>
+    const void *seg[] = {WK_SEGV(WK_KIND_RANK, FX_FRAC), WK_SEGV(WK_KIND_RANK, FX_UNIQ),
+                         WK_SEGV(WK_KIND_RANK, FX_ABOVE), WK_SEGV(WK_KIND_NONE, FX_FRAC),
+                         WK_SEGV(WK_KIND_NONE, FX_UNIQ)};
+#undef WK_SEGV
     for (const void *fn : seg)
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)c->smem_optin));
@@ -609,14 +617,20 @@ int wk_reset_counts(wk_ctx *c) {
   CK(cudaMemsetAsync(c->cnt.p, 0, len * 8, c->stream));
   CK(cudaMemsetAsync(c->small.p, 0, 64, c->stream));
   c->strata_keys = false;
-  if (c->sh_cap) {
-    TRY(fill_u64(c, c->sh_keys.as<ull>(), c->sh_cap, ~0ull));
-    TRY(fill_u64(c, c->sh_vals.as<ull>(), c->sh_cap, 0));
-  }
+  if (c->sh_cap) TRY(fill_slots(c, c->sh_keys.as<ull>(), c->sh_cap));
   return WK_OK;
 }
 
 }  // extern "C"
+
+static int fill_slots(wk_ctx *c, ull *p, size_t n) {
+  if (!n) return WK_OK;
+  int grid = (int)std::min<size_t>((2 * n + 255) / 256, (size_t)c->sm_count * 16);
+  fill_slots_kernel<<<grid, 256, 0, c->stream>>>(p, n);
+  c->launches++;
+  CK(cudaGetLastError());
+  return WK_OK;
+}
 
 // ---- launch helpers ---------------------------------------------------------
 static int check_plan_ready(wk_ctx *c, bool strata) {
@@ -657,32 +671,28 @@ static int ensure_strata(wk_ctx *c, int64_t new_keys_bound) {
   if (need <= c->sh_cap) return WK_OK;
   uint64_t ncap = 1 << 16;
   while (ncap < need) ncap <<= 1;
-  DevBuf nk, nv;
-  TRY(nk.reserve(ncap * 8));
-  TRY(nv.reserve(ncap * 8));
-  TRY(fill_u64(c, nk.as<ull>(), ncap, ~0ull));
-  TRY(fill_u64(c, nv.as<ull>(), ncap, 0));
-  DevBuf ok = c->sh_keys, ov = c->sh_vals;
+  DevBuf nk;  // ncap slots of {key, units}
+  TRY(nk.reserve(ncap * 16));
+  TRY(fill_slots(c, nk.as<ull>(), ncap));
+  DevBuf ok = c->sh_keys;
   uint64_t ocap = c->sh_cap;
   c->sh_keys = nk;
-  c->sh_vals = nv;
   c->sh_cap = ncap;
   if (ocap) {
     CK(cudaMemsetAsync(c->d_sh_used(), 0, 8, c->stream));
     ClsParams P;
     memset(&P, 0, sizeof P);
     P.sh_keys = nk.as<ull>();
-    P.sh_vals = nv.as<ull>();
+    P.sh_vals = nk.as<ull>() + 1;
     P.sh_mask = ncap - 1;
     P.sh_used = c->d_sh_used();
     P.err = c->d_err();
     int grid = (int)std::min<uint64_t>((ocap + 255) / 256, (uint64_t)c->sm_count * 8);
-    rehash_kernel<<<grid, 256, 0, c->stream>>>(ok.as<ull>(), ov.as<ull>(), ocap, P);
+    rehash_kernel<<<grid, 256, 0, c->stream>>>(ok.as<ull>(), ok.as<ull>() + 1, ocap, P);
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
     ok.release();
-    ov.release();
   }
   return WK_OK;
 }
@@ -842,7 +852,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   P.ovf_den = c->ovf_den.as<int32_t>();
   P.ovf_cap = c->ovf_cap;
   P.sh_keys = c->sh_keys.as<ull>();
-  P.sh_vals = c->sh_vals.as<ull>();
+  P.sh_vals = c->sh_keys.as<ull>() + 1;
   P.sh_mask = c->sh_cap ? c->sh_cap - 1 : 0;
   P.sh_used = c->d_sh_used();
   P.err = c->d_err();
@@ -925,51 +935,97 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
     }
     const int64_t span = n_dev ? n_bound : r1 - (r0 & ~3ll);
     if (span <= 0) return WK_OK;
-    // one entry, one sample, default or --uniq: the lane-per-record kernel
-    // with warp-private tiles (wk_seg.cuh)
-    if (lean && !gsink && !wide && !n_dev && (mode == FX_FRAC || mode == FX_UNIQ) &&
-        NTmax == SW_NT && !getenv("WK_NO_SEG")) {
-      int WT = 0;
-      const uint32_t cells1 = (uint32_t)(P.dir_base[1] - P.dir_base[0]);
-      const uint32_t stamps = 0u;
-      for (int wt : {512, 256})
-        if (!WT && sg_layout(SG_NT / 32, wt, cells1, (int64_t)c->Vp * 2, stamps).total <=
-                       c->smem_optin)
-          WT = wt;
-      if (const char *ev = getenv("WK_SEG_WT")) WT = atoi(ev) == 256 ? (WT ? 256 : 0) : WT;
-      if (WT) {
-        const SgSmemLayout GL = sg_layout(SG_NT / 32, WT, cells1, (int64_t)c->Vp * 2, stamps);
-        const int64_t ft = (span + WT - 1) / WT;
-        const int sgrid = (int)std::min<int64_t>(grid, (ft + SG_NT / 32 - 1) / (SG_NT / 32));
+    // default or --uniq: the lane-per-record kernel with warp-private tiles
+    // (wk_seg.cuh), one launch per entry.  Its --above variant (log-step LCA
+    // fold over the lanes of a query) is correct but measured slower than the
+    // run-per-lane kernel wherever LCAs are common (genus 1.71 vs 1.39 ms,
+    // species 2.09 vs 1.58; phylum 0.39 vs 0.69): opt-in with WK_SEG_ABOVE.
+    bool seg_done = false;
+    if (!gsink && !wide && !n_dev && NTmax == SW_NT && !getenv("WK_NO_SEG") &&
+        (mode == FX_FRAC || mode == FX_UNIQ ||
+         (mode == FX_ABOVE && par_ok && getenv("WK_SEG_ABOVE")))) {
+      int WTe[WK_MAX_ENTRIES];
+      bool fits = true;
+      const char *wt_env = getenv("WK_SEG_WT");
+      for (int e = 0; e < c->E && fits; ++e) {
+        const uint32_t ce = (uint32_t)(P.dir_base[e + 1] - P.dir_base[e]);
+        WTe[e] = 0;
+        for (int wt : {512, 256})
+          if (!WTe[e] && !(wt == 512 && wt_env && atoi(wt_env) == 256) &&
+              sg_layout(SG_NT / 32, wt, ce, (int64_t)c->Vp * 2 + par_bytes, 0u).total <=
+                  c->smem_optin)
+            WTe[e] = wt;
+        fits = WTe[e] != 0;
+      }
+      if (fits) {
+        const bool multi = !lean;
+        if (dqsamp) {
+          // where the sample of the stream changes (device side, no host sync)
+          TRY(c->seglist.reserve(sizeof(SegList)));
+          SegList *sl = c->seglist.as<SegList>();
+          CK(cudaMemsetAsync(sl, 0, 8, c->stream));
+          const int sgrid =
+              (int)std::min<int64_t>((r1 - r0 + 255) / 256, (int64_t)c->sm_count * 16);
+          seg_scan_kernel<<<sgrid, 256, 0, c->stream>>>(dq, dqsamp, r0, r1, sl);
+          seg_sort_kernel<<<1, 256, 0, c->stream>>>(dq, dqsamp, r0, r1, sl);
+          c->launches += 2;
+          P.seg_list = sl;
+        }
         P.direct_cells = dir_cells;
-        P.e_lo = 0;
-        P.e_hi = 1;
         // queries longer than a window are listed and done by seg_long_kernel
         TRY(c->longlist.reserve((size_t)(span / 33 + 4) * 8));
         P.long_list = c->longlist.as<ull>();
-        CK(cudaMemsetAsync(P.long_list, 0, 8, c->stream));
-#define WK_SEG2(KD, MD)                                                          \
-  do {                                                                           \
-    if (WT == 512)                                                               \
-      classify_seg_kernel<KD, MD, 512><<<sgrid, SG_NT, GL.total, c->stream>>>(P); \
-    else                                                                         \
-      classify_seg_kernel<KD, MD, 256><<<sgrid, SG_NT, GL.total, c->stream>>>(P); \
+        for (int e = 0; e < c->E; ++e) {
+          P.e_lo = e;
+          P.e_hi = e + 1;
+          const int WT = WTe[e];
+          const SgSmemLayout GL =
+              sg_layout(SG_NT / 32, WT, (uint32_t)(P.dir_base[e + 1] - P.dir_base[e]),
+                        (int64_t)c->Vp * 2 + par_bytes, 0u);
+          const int64_t ft = (span + WT - 1) / WT;
+          const int sgrid =
+              (int)std::min<int64_t>(grid, (ft + SG_NT / 32 - 1) / (SG_NT / 32));
+          CK(cudaMemsetAsync(P.long_list, 0, 8, c->stream));
+#define WK_SEG4(KD, MD, WW, MU) \
+  classify_seg_kernel<KD, MD, WW, MU><<<sgrid, SG_NT, GL.total, c->stream>>>(P)
+#define WK_SEG3(KD, MD, WW)               \
+  do {                                    \
+    if (multi) WK_SEG4(KD, MD, WW, true); \
+    else WK_SEG4(KD, MD, WW, false);      \
   } while (0)
-        if (rk) {
-          if (mode == FX_UNIQ) WK_SEG2(WK_KIND_RANK, FX_UNIQ);
-          else WK_SEG2(WK_KIND_RANK, FX_FRAC);
-        } else {
-          if (mode == FX_UNIQ) WK_SEG2(WK_KIND_NONE, FX_UNIQ);
-          else WK_SEG2(WK_KIND_NONE, FX_FRAC);
-        }
+#define WK_SEG2(KD, MD)                  \
+  do {                                   \
+    if (WT == 512) WK_SEG3(KD, MD, 512); \
+    else WK_SEG3(KD, MD, 256);           \
+  } while (0)
+          if (rk) {
+            if (mode == FX_UNIQ) WK_SEG2(WK_KIND_RANK, FX_UNIQ);
+            else if (mode == FX_ABOVE) WK_SEG2(WK_KIND_RANK, FX_ABOVE);
+            else WK_SEG2(WK_KIND_RANK, FX_FRAC);
+          } else {
+            if (mode == FX_UNIQ) WK_SEG2(WK_KIND_NONE, FX_UNIQ);
+            else WK_SEG2(WK_KIND_NONE, FX_FRAC);
+          }
 #undef WK_SEG2
-        seg_long_kernel<<<c->sm_count, 128, 0, c->stream>>>(P);
-        c->launches += 2;
-        CK(cudaGetLastError());
+#undef WK_SEG3
+#undef WK_SEG4
+          seg_long_kernel<<<c->sm_count, 128, 0, c->stream>>>(P);
+          c->launches += 2;
+          CK(cudaGetLastError());
+        }
+        P.e_lo = 0;
+        P.e_hi = c->E;
         c->last_kernel = "classify_seg_kernel";
-        return WK_OK;
+        if (!dqsamp) return WK_OK;
+        // interleaved samples (more than FX_MAX_SEG changes): the kernels above
+        // returned at once and classify_kernel below does the chunk; otherwise
+        // classify_kernel returns at once
+        P.seg_list = nullptr;
+        P.skip_flag = &c->seglist.as<SegList>()->nseg;
+        seg_done = true;
       }
     }
+    if (seg_done) FR = 0;
     if (FR) {
       const bool multi = !lean;
       P.fast_gsink = gsink ? 1 : 0;
@@ -1573,7 +1629,7 @@ int wk_fetch_strata(wk_ctx *c, int64_t *n, int32_t *entry, int32_t *sample,
   CK(cudaMemsetAsync(c->d_cursor(), 0, 8, c->stream));
   int grid = (int)std::min<uint64_t>((c->sh_cap + 255) / 256, (uint64_t)c->sm_count * 8);
   compact_hash_kernel<<<grid, 256, 0, c->stream>>>(
-      c->sh_keys.as<ull>(), c->sh_vals.as<ull>(), c->sh_cap, ok.as<ull>(),
+      c->sh_keys.as<ull>(), c->sh_keys.as<ull>() + 1, c->sh_cap, ok.as<ull>(),
       ov.as<ull>(), c->d_cursor());
   c->launches++;
   CK(cudaGetLastError());

@@ -84,7 +84,7 @@ struct ClsParams {
   int64_t *ovf_key;
   int32_t *ovf_den;
   int64_t ovf_cap;
-  ull *sh_keys, *sh_vals;     // strata hash (open addressing)
+  ull *sh_keys, *sh_vals;     // strata hash (open addressing): slot i = {sh_keys[2i], sh_vals[2i]}, sh_vals = sh_keys + 1
   uint64_t sh_mask;
   ull *sh_used;
   int32_t *err;               // device error word (bit flags)
@@ -201,17 +201,18 @@ __device__ __forceinline__ void strat_add(const ClsParams &P, ull key,
   ull h = key * 0x9E3779B97F4A7C15ull;
   h ^= h >> 29;
   uint64_t i = h & P.sh_mask;
+  // a slot is 16 bytes: key, then units — one DRAM sector per emission
   for (uint64_t probe = 0; probe <= P.sh_mask; ++probe) {
-    ull k0 = P.sh_keys[i];
+    ull k0 = P.sh_keys[2 * i];
     if (k0 == ~0ull) {
-      k0 = atomicCAS(&P.sh_keys[i], ~0ull, key);
+      k0 = atomicCAS(&P.sh_keys[2 * i], ~0ull, key);
       if (k0 == ~0ull) {
         atomicAdd(P.sh_used, 1ull);
         k0 = key;
       }
     }
     if (k0 == key) {
-      atomicAdd(&P.sh_vals[i], units);
+      atomicAdd(&P.sh_vals[2 * i], units);
       return;
     }
     i = (i + 1) & P.sh_mask;

@@ -59,21 +59,28 @@ __host__ __device__ inline SgSmemLayout sg_layout(int NW, int WT, uint32_t cells
   return L;
 }
 
-template <int KIND, int MODE, int WT>
+// MULTI: the plan has several entries (one launch per entry, P.e_lo) and / or
+// the stream is a sequence of contiguous samples given as a segment table
+// (seg_scan_kernel / seg_sort_kernel, wk_sweep.cuh); the private table is
+// flushed between segments.
+template <int KIND, int MODE, int WT, bool MULTI>
 __global__ void __launch_bounds__(SG_NT, 1)
     classify_seg_kernel(const __grid_constant__ ClsParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int TBUF = WT + SG_PRE + SG_POST;
   constexpr uint32_t SCOL = (uint32_t)TBUF * 4u;  // subject column after the query column
   constexpr uint32_t C_NONE = FX_NONE;
+  constexpr bool ABOVE = KIND == WK_KIND_RANK && MODE == FX_ABOVE;
   const int tid = threadIdx.x, warp = tid >> 5;
   int lane = tid & 31;
   asm volatile("" : "+r"(lane));
   const int NW = blockDim.x >> 5;
-  const uint32_t cells = (uint32_t)(P.dir_base[1] - P.dir_base[0]);
+  const int e = MULTI ? P.e_lo : 0;  // the entry of this launch
+  const uint32_t cells = (uint32_t)(P.dir_base[e + 1] - P.dir_base[e]);
   const uint32_t rows_bytes = (uint32_t)P.Vp * 2u;
-  const uint32_t stamps = 0u;
-  const SgSmemLayout L = sg_layout(NW, WT, cells, (int64_t)rows_bytes, stamps);
+  // --above: the parent array as uint16 behind the row
+  const uint32_t par_bytes = ABOVE ? (((uint32_t)P.T + 7u) & ~7u) * 2u : 0u;
+  const SgSmemLayout L = sg_layout(NW, WT, cells, (int64_t)rows_bytes + par_bytes, 0u);
   const uint32_t sbase32 = smem_u32(smem);
   const uint32_t tabbar = sbase32 + L.bars + (uint32_t)NW * 8u;
   const uint32_t mybar = sbase32 + L.bars + (uint32_t)warp * 8u;
@@ -81,13 +88,14 @@ __global__ void __launch_bounds__(SG_NT, 1)
   const uint32_t row = sbase32 + L.tab;
   const uint32_t tbl = sbase32 + L.sink0;
   const uint32_t usm = sbase32 + L.units;
-  const uint32_t stp = sbase32 + L.stamp;
   const uint32_t badflag = tabbar + 8u;
 
   if (*P.err & ERR_PAIR_FULL) return;
-  const int64_t n_all = P.n, r0 = P.r0, r1 = P.r1;
-  const int sample = P.sample;
-  if ((unsigned)sample >= (unsigned)P.S) return;
+  const SegList *SG = MULTI ? reinterpret_cast<const SegList *>(P.seg_list) : nullptr;
+  const int nseg = SG ? SG->nseg : 1;
+  if (nseg < 0) return;  // interleaved samples: classify_kernel does this chunk
+  const int64_t n_all = P.n;
+  if (!SG && (unsigned)P.sample >= (unsigned)P.S) return;
 
   if (lane == 0) mbar_init(mybar, 1);
   if (tid == 0) {
@@ -97,29 +105,38 @@ __global__ void __launch_bounds__(SG_NT, 1)
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   if (tid == 0) {
-    mbar_expect_tx(tabbar, rows_bytes);
-    bulk_g2s(row, P.tab16, rows_bytes, tabbar);
+    mbar_expect_tx(tabbar, rows_bytes + par_bytes);
+    bulk_g2s(row, P.tab16 + (size_t)e * P.Vp, rows_bytes, tabbar);
+    if (ABOVE) bulk_g2s(row + rows_bytes, P.tab16 + P.par16_off, par_bytes, tabbar);
   }
   if (tid < 33) sts32(usm + (uint32_t)tid * 4u, c_units[tid]);
 #pragma unroll 1
   for (uint32_t h = tid; h < cells; h += blockDim.x) sts32(tbl + h * 4, 0);
-#pragma unroll 1
-  for (uint32_t h = tid; h < stamps; h += blockDim.x) sts32(stp + h * 4, 0xFFFFFFFFu);
   __syncthreads();
   mbar_wait(tabbar, 0);
 
   const uint32_t V32 = (uint32_t)P.V;  // the staged row has a 'none' pad slot at V
-  const uint32_t off = (uint32_t)P.dir_off[0], wid = (uint32_t)P.dir_w[0];
+  const uint32_t off = (uint32_t)P.dir_off[e], wid = (uint32_t)P.dir_w[e];
   // 'Unassigned' is counted when asked for: slot wid passes `slot < wid1`
   const uint32_t wid1 = (P.flags & WK_F_UNASSIGNED) ? wid + 1u : 0u;
-  ull *const crow = P.cnt + (int64_t)sample * P.NF1;
   const unsigned le = FULL >> (31 - lane), ge = FULL << lane;
   const unsigned mybit = 1u << lane;
   const int GW = (int)gridDim.x * NW;
   const int gw = (int)blockIdx.x * NW + warp;
+  TreeRef TR;
+  TR.parent = P.parent;
+  TR.par16 = row + rows_bytes;
+  uint32_t phase = 0;
+
+#pragma unroll 1
+  for (int sg = 0; sg < nseg; ++sg) {
+  const int64_t r0 = SG ? SG->at[sg] : P.r0;
+  const int64_t r1 = SG ? SG->at[sg + 1] : P.r1;
+  const int sample = SG ? SG->sample[sg] : P.sample;
+  if ((unsigned)sample >= (unsigned)P.S) continue;  // dropped sample (CTA-uniform)
+  ull *const crow = P.cnt + ((int64_t)e * P.S + sample) * P.NF1;
   const int64_t tb0 = r0 & ~3ll;
   const int n_tiles = r1 > tb0 ? (int)((r1 - tb0 + WT - 1) / WT) : 0;
-  uint32_t phase = 0;
 
   auto issue = [&](int tile) {
     const int64_t tb = tb0 + (int64_t)tile * WT;
@@ -132,7 +149,10 @@ __global__ void __launch_bounds__(SG_NT, 1)
     bulk_g2s(dq, P.q + g0, bytes, mybar);
     bulk_g2s(dq + SCOL, P.s + g0, bytes, mybar);
   };
-  if (lane == 0 && gw < n_tiles) issue(gw);
+  if (lane == 0 && gw < n_tiles) {
+    if (MULTI) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    issue(gw);
+  }
 
 #pragma unroll 1
   for (int tile = gw; tile < n_tiles; tile += GW, phase ^= 1u) {
@@ -202,6 +222,22 @@ __global__ void __launch_bounds__(SG_NT, 1)
         const bool alleq = (NE & segm) == 0;
         if (MODE == FX_UNIQ) {
           if (!alleq) c = C_NONE;
+        } else if (ABOVE) {
+          // classify.assign_rank with --above (classify.py:119-123): None if
+          // a subject has no taxon, else tree.find_lca of the taxa
+          // (tree.py:513-566), the root -> None.  Repeats do not matter.  The
+          // taxa of a query are folded towards its head lane in log steps.
+          const unsigned NB = __ballot_sync(FULL, act && code == C_NONE) & segm;
+          const int se = __ffs(tge);  // one past my query's last lane
+          const int dist = alleq ? 0 : se - 1 - lane;  // lanes after me
+          const int maxd = __reduce_max_sync(FULL, dist);
+          uint32_t v = code;
+#pragma unroll 1
+          for (int o = 1; o <= maxd; o <<= 1) {
+            const uint32_t w = __shfl_down_sync(FULL, v, o);
+            if (o <= dist && !NB && w != v) v = (uint32_t)lca2(TR, (int)v, (int)w);
+          }
+          if (!alleq) c = (NB || v == (uint32_t)P.root) ? C_NONE : v;
         } else {
           // set semantics of the subject pool (align.py:339): a repeat has
           // an equal subject earlier in its query.  Only the records of
@@ -234,7 +270,7 @@ __global__ void __launch_bounds__(SG_NT, 1)
               // rare: 1/d with d not dividing WK_UNITS (overflow list)
               const ull at = atomicAdd(P.ovf_n, 1ull);
               if ((int64_t)at < P.ovf_cap) {
-                P.ovf_key[at] = (int64_t)pack_plain(P, 0, sample, (int64_t)code);
+                P.ovf_key[at] = (int64_t)pack_plain(P, e, sample, (int64_t)code);
                 P.ovf_den[at] = d;
               } else {
                 atomicOr(P.err, ERR_OVF_FULL);
@@ -272,8 +308,11 @@ __global__ void __launch_bounds__(SG_NT, 1)
     if (v) {
       const int64_t f = h < wid ? (int64_t)off + h : P.NF1 - 1;
       atomicAdd(crow + f, (ull)v);
+      if (MULTI) sts32(tbl + h * 4u, 0);
     }
   }
+  if (MULTI) __syncthreads();
+  }  // segments
   if (tid == 0 && lds32(badflag)) atomicOr(P.err, ERR_BAD_SUBJECT);
 }
 
