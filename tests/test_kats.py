@@ -175,8 +175,16 @@ def test_unsupported_options_are_loud():
     with pytest.raises(NotImplementedError):
         classify(None, [], ranks=['none'], sizes={'a': 1.0},
                  stratmap={'S1': 'x'})
-    with pytest.raises(NotImplementedError):
-        classify(None, [], ranks=['none'], outcov_dir='cov')
+    # coverage needs ranges: not with --coords (the reference crashes on the
+    # gene sets, range.py:142), and the coordinate format is checked up front
+    # (range.py:229-245)
+    from functools import partial
+    from woltka_b200.ordinal import ordinal_mapper
+    om = partial(ordinal_mapper, coords={}, idmap={}, prefix=False, th=0.8)
+    with pytest.raises(ValueError, match='--coords'):
+        classify(om, [], ranks=['none'], outcov_dir='cov')
+    with pytest.raises(ValueError, match='Invalid coverage format: xyz.'):
+        classify(None, [], ranks=['none'], outcov_dir='cov', outcov_fmt='xyz')
 
 
 @pytest.mark.gpu
