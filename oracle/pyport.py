@@ -124,21 +124,29 @@ def tally(queries, results, strata=None):
     return res
 
 
-def tally_sized(subjects, results, sizes):
-    """classify.counter_size (classify.py:174-213): a uniquely assigned query
-    adds the mean weight of its subjects, a list adds weight / k' per listed
-    subject; a subject without a weight is a KeyError."""
+def tally_sized(subjects, results, sizes, queries=None, strata=None):
+    """classify.counter_size / counter_size_strat (classify.py:174-213,
+    252-297): a uniquely assigned query adds the mean weight of its subjects,
+    a list adds weight / k' per listed subject; a subject without a weight is
+    a KeyError.  With strata only the queries that have one count, keyed by
+    (stratum, taxon)."""
     res = defaultdict(int)
-    for subs, taxa in zip(subjects, results):
+    for i, (subs, taxa) in enumerate(zip(subjects, results)):
         if not taxa:
             continue
+        if strata is not None:
+            if queries[i] not in strata:
+                continue
+            key = (lambda t, s=strata[queries[i]]: (s, t))
+        else:
+            key = (lambda t: t)
         if isinstance(taxa, list):
             share = 1 / len([t for t in taxa if t])
             for t, sub in zip(taxa, subs):
                 if t:
-                    res[t] += sizes[sub] * share
+                    res[key(t)] += sizes[sub] * share
         else:
-            res[taxa] += sum(sizes[x] for x in subs) / len(subs)
+            res[key(taxa)] += sum(sizes[x] for x in subs) / len(subs)
     return res
 
 
@@ -204,7 +212,7 @@ def classify_chunks(chunks, ranks, tree=None, rankdic=None, root=None,
                     maps.setdefault(rank, {}).setdefault(sname, []).extend(
                         readmap_lines(qs, res, namedic))
                 counts = tally(qs, res, strata) if sizes is None else \
-                    tally_sized(ss, res, sizes)
+                    tally_sized(ss, res, sizes, qs, strata)
                 total = data[rank].setdefault(sname, {})
                 for k, v in counts.items():           # util.sum_dict
                     total[k] = total.get(k, 0) + v

@@ -343,6 +343,22 @@ def bundled():
     run_case('burst_process_sizes', 'burst', hier=fmaps, ranks='process,none',
              coords_rel='coords.txt.xz', sizes='.',
              note='cf. bt2sho.component.rpk.tsv: ordinal, gene lengths as sizes')
+    # --sizes together with --stratify (classify.counter_size_strat)
+    fp = join(OUT, 'sizes', 'burst.length.map')
+    if not os.path.exists(fp):
+        bsubs = sorted(subjects_of([join(OUT, 'burst', f) for f in
+                                    sorted(os.listdir(join(OUT, 'burst')))]))
+        with open(fp, 'w') as f:
+            for x in bsubs:
+                f.write(f'{x}\t{900000 + (int(x[1:]) % 911) * 1009}\n')
+    run_case('burst_ogu_strat_sizes', 'burst', ranks=None,
+             strata_rel='burst.genus.map',
+             sizes=join('sizes', 'burst.length.map'),
+             note='plain: genome counts weighted by length, per genus stratum')
+    run_case('burst_genus_process_sizes', 'burst', hier=fmaps,
+             ranks='process,none', coords_rel='coords.txt.xz',
+             strata_rel='burst.genus.map', sizes='.',
+             note='ordinal + stratified + gene lengths as sizes')
     # subject coverage (--outcov; range.py): SAM with CIGAR spans, multi-hit
     # reads, five samples; BED-like and GFF-like coordinates
     run_case('bowtie2_ogu_cov', 'bowtie2', ranks=None, cov=True,

@@ -34,6 +34,12 @@ def test_pyport_matches_reference(name):
     total = {r: {} for r in ranks}
     maps = {} if case.get('expected_maps') else None
     excl = set(case['exclude']) if case['exclude'] else None
+    strata_of = None
+    if case['strata']:
+        sdir = join(DATA, case['strata'])
+        smap = {fn.split('.')[0]: join(sdir, fn) for fn in os.listdir(sdir)}
+        cache = {}
+        strata_of = lambda s: cache.setdefault(s, _read_strata(smap[s]))
     for fp in sorted(files):
         with readzip(fp) as fh:
             chunks = plain_mapper(fh, fmt=case['fmt'], excl=excl, n=1024)
@@ -45,7 +51,8 @@ def test_pyport_matches_reference(name):
                 samples=set(case['samples']) if case['demux'] and
                 case['samples'] else None,
                 sample=files[fp], trimsub=case['trimsub'], maps=maps,
-                namedic=case.get('namedic'), sizes=case.get('sizes'))
+                namedic=case.get('namedic'), sizes=case.get('sizes'),
+                strata_of=strata_of)
         for r in ranks:
             for s, prof in data[r].items():
                 tgt = total[r].setdefault(s, {})

@@ -37,7 +37,7 @@ class Session:
     def __init__(self, ranks, tree=None, rankdic=None, root=None, uniq=False,
                  major=None, above=False, subok=False, unasgd=False,
                  trimsub=None, engine_factory=None, device=0, rank2dir=None,
-                 outzip=None, namedic=None, sizes=None):
+                 outzip=None, namedic=None, sizes=None, stratified=False):
         if engine_factory is None:
             from .engine import Engine
             engine_factory = Engine
@@ -59,7 +59,10 @@ class Session:
         self.kinds = []
         for rank in self.order:
             if rank is None or rank == 'none' or tree is None:
-                self.kinds.append(KIND_NONE_ID if tree is None else KIND_NONE)
+                # (feature == subject needs no table, except when a subject
+                # has one device copy per stratum: --sizes with --stratify)
+                self.kinds.append(KIND_NONE_ID if tree is None and
+                                  not (sizes and stratified) else KIND_NONE)
             elif rank == 'free':
                 self.kinds.append(KIND_FREE)
             else:
@@ -82,6 +85,13 @@ class Session:
         self.sub_index = {}
         self.sub_node = []
         self.sub_feat = []
+        # --sizes with --stratify: a subject seen in stratum t is its own
+        # device subject (same tables), so that the (subject, feature) shares
+        # of the device also tell the stratum (classify.counter_size_strat,
+        # classify.py:252-297)
+        self.sub_name = []           # subject index -> name
+        self.sub_stratum = []        # subject index -> stratum index or -1
+        self._pair_index = {}        # (subject index, stratum) -> index
         self.extra_names = []        # features beyond the tree
         self.extra_index = {}
         self.sample_index = {}
@@ -137,6 +147,8 @@ class Session:
                 self.extra_names.append(name)
         self.sub_node.append(node)
         self.sub_feat.append(feat)
+        self.sub_name.append(name)
+        self.sub_stratum.append(-1)
         for e, kind in enumerate(self.kinds):
             if kind == KIND_RANK:
                 v = int(self._rank_tabs[e][node]) if node >= 0 else -1
@@ -148,6 +160,22 @@ class Session:
                 v = feat
             self._tab_rows[e].append(v)
         self._dirty = True
+        return idx
+
+    def subject_in_stratum(self, base, stratum):
+        """Device subject standing for subject index `base` seen in a query of
+        `stratum`: a copy of its table entries under a new index."""
+        key = (base, stratum)
+        idx = self._pair_index.get(key)
+        if idx is None:
+            idx = self._pair_index[key] = len(self.sub_node)
+            self.sub_node.append(self.sub_node[base])
+            self.sub_feat.append(self.sub_feat[base])
+            self.sub_name.append(self.sub_name[base])
+            self.sub_stratum.append(stratum)
+            for row in self._tab_rows:
+                row.append(row[base])
+            self._dirty = True
         return idx
 
     def sample(self, name):
@@ -201,6 +229,7 @@ class Session:
         reads, starts = [], []
         nq = 0
         use_strata = strata_of is not None
+        sized_strata = bool(self.sizes) and use_strata
         for query, subjects in zip(qryque, subque):
             if demux:
                 sname, read = _split_sample(query)
@@ -218,9 +247,17 @@ class Session:
             q_stratum.append(stratum)
             reads.append(read)
             starts.append(len(q))
-            for sub in subjects:
-                q.append(nq)
-                s.append(self.subject(sub))
+            if sized_strata:
+                # the stratum travels with the subject; reads without one
+                # contribute nothing (classify.py:283-284)
+                if stratum >= 0:
+                    for idx in {self.subject(sub) for sub in subjects}:
+                        q.append(nq)
+                        s.append(self.subject_in_stratum(idx, stratum))
+            else:
+                for sub in subjects:
+                    q.append(nq)
+                    s.append(self.subject(sub))
             nq += 1
         if not q:
             return
@@ -229,8 +266,8 @@ class Session:
         q = np.asarray(q, dtype=np.int32)
         s = np.asarray(s, dtype=np.int32)
         q_sample = np.asarray(q_sample, dtype=np.int32)
-        q_stratum = np.asarray(q_stratum, dtype=np.int32) if use_strata \
-            else None
+        q_stratum = np.asarray(q_stratum, dtype=np.int32) \
+            if use_strata and not sized_strata else None
         for eng in self.engines:
             eng.classify_chunk(q, s, q_sample, q_stratum)
         if self.rank2dir is not None:
@@ -375,7 +412,7 @@ class Session:
         q_sample = np.asarray(q_sample, dtype=np.int32)
         q_stratum = np.asarray(q_stratum, dtype=np.int32) if use_strata \
             else None
-        if self.rank2dir is not None:
+        if self.rank2dir is not None or (self.sizes and use_strata):
             return self._ordinal_chunk_with_maps(genes, cols, th, q_sample,
                                                  q_stratum, reads)
         for eng in self.engines:
@@ -402,18 +439,28 @@ class Session:
         if not len(r):
             return
         s2 = genes.subjects(self)[g]
+        if self.sizes and q_stratum is not None:
+            # --sizes with --stratify: the stratum travels with the subject
+            live = q_stratum[r] >= 0
+            r, s2 = r[live], s2[live]
+            s2 = np.fromiter((self.subject_in_stratum(a, b) for a, b in
+                              zip(s2.tolist(), q_stratum[r].tolist())),
+                             dtype=np.int32, count=len(r))
+            q_stratum = None
+            self._sync_tables()
+            if not len(r):
+                return
         for eng in self.engines:
             eng.classify_chunk(r, s2, q_sample, q_stratum)
-        qs_u, starts = np.unique(r, return_index=True)
-        self._write_readmaps(len(r), [reads[j] for j in qs_u.tolist()],
-                             starts.tolist() + [len(r)], q_sample[qs_u])
+        if self.rank2dir is not None:
+            qs_u, starts = np.unique(r, return_index=True)
+            self._write_readmaps(len(r), [reads[j] for j in qs_u.tolist()],
+                                 starts.tolist() + [len(r)], q_sample[qs_u])
 
     def _sized_results(self, data):
         """--sizes: sum over subjects of weight x the exact share the subject
         contributed to the feature (the device's (subject, feature) table)."""
-        names = [None] * len(self.sub_index)
-        for name, idx in self.sub_index.items():
-            names[idx] = name
+        names, strat_of = self.sub_name, self.sub_stratum
         NF1 = self.NF_cap + 1
         for grp, eng in zip(self.groups, self.engines):
             shares = {}   # (e, sample, feature, subject) -> Fraction
@@ -432,6 +479,8 @@ class Session:
                     rank = self.order[grp[e]]
                     prof = data[rank][self.sample_names[s]]
                     name = self.feature_name(f)
+                    if strat_of[t] >= 0:
+                        name = (self.stratum_names[strat_of[t]], name)
                     prof[name] = prof.get(name, 0) + \
                         self.sizes[names[t]] * float(shares[(e, s, f, t)]) * \
                         self.mult[rank]

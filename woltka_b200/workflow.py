@@ -19,8 +19,10 @@ assignment column the kernel writes next to the counts; size-weighted counts
 (`sizes`, row F4) from the kernels' exact (subject, feature) shares, weighted
 on the host.  With `--coords` the read maps are made from the matcher's
 (query, gene) pairs sent through the plain path.  Subject coverage (`outcov_dir`, row F5) is
-accumulated and merged on the GPU (woltka_b200.coverage).  `sizes` together
-with `stratmap` raises NotImplementedError instead of silently falling back.
+accumulated and merged on the GPU (woltka_b200.coverage).  With `sizes` and
+`stratmap` together (classify.counter_size_strat) a subject seen in a stratum
+becomes its own device subject, so the same (subject, feature) shares also
+carry the stratum.
 """
 import bz2
 import gzip
@@ -178,9 +180,9 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
     `round_profiles` the two are identical.
     """
     is_ordinal = getattr(mapper, 'func', None) is ordinal_mapper
-    if sizes and stratmap:
+    if sizes and stratmap and rank2dir is not None:
         raise NotImplementedError(
-            'Size-normalised counting (--sizes) together with --stratify is '
+            'Read maps (--outmap) together with --sizes and --stratify are '
             'not part of the GPU hot path yet.')
     if outcov_dir:
         coverage_offsets(outcov_fmt)     # an invalid format fails up front
@@ -198,7 +200,7 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
 
     sess = Session(ranks, tree, rankdic, root, uniq, major and major / 100,
                    above, subok, unasgd, trimsub, _engine_factory, _device,
-                   rank2dir, outzip, namedic, sizes)
+                   rank2dir, outzip, namedic, sizes, bool(stratmap))
     samset = set(samples) if samples else None
     strata_cache = {}
     cover = Coverage(sess.engines[0]) if outcov_dir else None
