@@ -183,6 +183,7 @@ struct wk_ctx {
   // ordinal
   DevBuf cinfo, genes;  // genes buffer = [genes | bin_first | gene_subject]
   size_t bins_offset = 0, subj_offset = 0, hot_bytes = 0;
+  bool subj_identity = false;  // gene_subject[g] == g: the matcher skips the load
   size_t l2_persist_max = 0;
   size_t l2_window_max = 0;
   int32_t C = 0;
@@ -952,7 +953,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
         WTe[e] = 0;
         for (int wt : {512, 256})
           if (!WTe[e] && !(wt == 512 && wt_env && atoi(wt_env) == 256) &&
-              sg_layout(SG_NT / 32, wt, ce, (int64_t)c->Vp * 2 + par_bytes, 0u).total <=
+              sg_layout(SG_NT / 32, wt, ce, (int64_t)c->Vp * 2 + par_bytes).total <=
                   c->smem_optin)
             WTe[e] = wt;
         fits = WTe[e] != 0;
@@ -981,7 +982,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
           const int WT = WTe[e];
           const SgSmemLayout GL =
               sg_layout(SG_NT / 32, WT, (uint32_t)(P.dir_base[e + 1] - P.dir_base[e]),
-                        (int64_t)c->Vp * 2 + par_bytes, 0u);
+                        (int64_t)c->Vp * 2 + par_bytes);
           const int64_t ft = (span + WT - 1) / WT;
           const int sgrid =
               (int)std::min<int64_t>(grid, (ft + SG_NT / 32 - 1) / (SG_NT / 32));
@@ -1344,6 +1345,9 @@ int wk_ordinal_set_genes(wk_ctx *c, const int64_t *contig_off,
   CK(cudaMemcpy(c->genes.p, genes.data(), (size_t)n_genes * 8, cudaMemcpyHostToDevice));
   if (n_genes)
     CK(cudaMemcpy((char *)c->genes.p + c->subj_offset, gene_subject, (size_t)n_genes * 4, cudaMemcpyHostToDevice));
+  c->subj_identity = true;
+  for (int64_t g = 0; g < n_genes && c->subj_identity; ++g)
+    c->subj_identity = gene_subject[g] == (int32_t)g;
   CK(cudaMemcpy((char *)c->genes.p + c->bins_offset, bin_first.data(),
                 (size_t)nbins * 4, cudaMemcpyHostToDevice));
   c->C = n_contigs;
@@ -1388,8 +1392,9 @@ static int run_ordinal(wk_ctx *c, const int32_t *dq, const int32_t *dcontig,
     P.th = th;
     P.cinfo = c->cinfo.as<int4>();
     P.genes = c->genes.as<int2>();
-    P.gene_subject = reinterpret_cast<const int32_t *>(
-        (const char *)c->genes.p + c->subj_offset);
+    P.gene_subject = c->subj_identity ? nullptr
+                                      : reinterpret_cast<const int32_t *>(
+                                            (const char *)c->genes.p + c->subj_offset);
     P.bin_first = reinterpret_cast<const int32_t *>(
         (const char *)c->genes.p + c->bins_offset);
     P.shift = c->shift;

@@ -42,7 +42,7 @@ struct OrdParams {
   double th;
   const int4 *cinfo;           // [C] (first bin, n bins, gene end, 0)
   const int2 *genes;           // [G] (gbeg, gend), sorted by gbeg per contig
-  const int32_t *gene_subject; // [G]
+  const int32_t *gene_subject; // [G], or null when gene g is subject g
   const int32_t *bin_first;    // [sum bins]
   int32_t shift;
   int32_t C;
@@ -272,7 +272,8 @@ __global__ void __launch_bounds__(ORD_NT, 4)
   int64_t off = s_base + s_warp[warp] + (incl - tot);
   auto put = [&](int64_t ri, int qq, int g) {
     __stcs(P.pair_q + off, qq);
-    __stcs(P.pair_s + off, __ldg(P.gene_subject + g));
+    // (null = the genes are the subjects in this order: one random sector less)
+    __stcs(P.pair_s + off, P.gene_subject ? __ldg(P.gene_subject + g) : g);
     if (P.pair_r) {
       P.pair_r[off] = (int32_t)ri;
       P.pair_g[off] = g;

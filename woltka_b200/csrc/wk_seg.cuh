@@ -40,12 +40,11 @@ __device__ __forceinline__ uint32_t lds16w(uint32_t a) {
 }
 
 struct SgSmemLayout {
-  uint32_t bars, units, warp0, warp_bytes, sink0, tab, stamp, total;
+  uint32_t bars, units, warp0, warp_bytes, sink0, tab, total;
   int tbuf;
 };
-// `stamps` 32-bit words of duplicate stamps (one per subject + pad, 0 = --uniq)
 __host__ __device__ inline SgSmemLayout sg_layout(int NW, int WT, uint32_t cells,
-                                                  int64_t tab_bytes, uint32_t stamps) {
+                                                  int64_t tab_bytes) {
   SgSmemLayout L;
   L.tbuf = WT + SG_PRE + SG_POST;
   L.bars = 0;  // NW tile barriers, 1 table barrier, 1 flag word
@@ -54,8 +53,7 @@ __host__ __device__ inline SgSmemLayout sg_layout(int NW, int WT, uint32_t cells
   L.warp_bytes = 2u * (uint32_t)L.tbuf * 4u;  // query and subject columns
   L.sink0 = L.warp0 + (uint32_t)NW * L.warp_bytes;
   L.tab = (L.sink0 + cells * 4u + 127) & ~127u;
-  L.stamp = L.tab + (uint32_t)((tab_bytes + 15) & ~15ll);
-  L.total = L.stamp + stamps * 4u;
+  L.total = L.tab + (uint32_t)((tab_bytes + 15) & ~15ll);
   return L;
 }
 
@@ -80,7 +78,7 @@ __global__ void __launch_bounds__(SG_NT, 1)
   const uint32_t rows_bytes = (uint32_t)P.Vp * 2u;
   // --above: the parent array as uint16 behind the row
   const uint32_t par_bytes = ABOVE ? (((uint32_t)P.T + 7u) & ~7u) * 2u : 0u;
-  const SgSmemLayout L = sg_layout(NW, WT, cells, (int64_t)rows_bytes + par_bytes, 0u);
+  const SgSmemLayout L = sg_layout(NW, WT, cells, (int64_t)rows_bytes + par_bytes);
   const uint32_t sbase32 = smem_u32(smem);
   const uint32_t tabbar = sbase32 + L.bars + (uint32_t)NW * 8u;
   const uint32_t mybar = sbase32 + L.bars + (uint32_t)warp * 8u;
@@ -130,188 +128,188 @@ __global__ void __launch_bounds__(SG_NT, 1)
 
 #pragma unroll 1
   for (int sg = 0; sg < nseg; ++sg) {
-  const int64_t r0 = SG ? SG->at[sg] : P.r0;
-  const int64_t r1 = SG ? SG->at[sg + 1] : P.r1;
-  const int sample = SG ? SG->sample[sg] : P.sample;
-  if ((unsigned)sample >= (unsigned)P.S) continue;  // dropped sample (CTA-uniform)
-  ull *const crow = P.cnt + ((int64_t)e * P.S + sample) * P.NF1;
-  const int64_t tb0 = r0 & ~3ll;
-  const int n_tiles = r1 > tb0 ? (int)((r1 - tb0 + WT - 1) / WT) : 0;
+    const int64_t r0 = SG ? SG->at[sg] : P.r0;
+    const int64_t r1 = SG ? SG->at[sg + 1] : P.r1;
+    const int sample = SG ? SG->sample[sg] : P.sample;
+    if ((unsigned)sample >= (unsigned)P.S) continue;  // dropped sample (CTA-uniform)
+    ull *const crow = P.cnt + ((int64_t)e * P.S + sample) * P.NF1;
+    const int64_t tb0 = r0 & ~3ll;
+    const int n_tiles = r1 > tb0 ? (int)((r1 - tb0 + WT - 1) / WT) : 0;
 
-  auto issue = [&](int tile) {
-    const int64_t tb = tb0 + (int64_t)tile * WT;
-    const int64_t g0 = tb >= SG_PRE ? tb - SG_PRE : 0;
-    int64_t g1 = tb + WT + SG_POST;
-    if (g1 > n_all) g1 = n_all;
-    const uint32_t bytes = (uint32_t)(((g1 - g0) * 4 + 15) & ~15ll);
-    const uint32_t dq = aq + (uint32_t)(g0 - (tb - SG_PRE)) * 4u;
-    mbar_expect_tx(mybar, 2 * bytes);
-    bulk_g2s(dq, P.q + g0, bytes, mybar);
-    bulk_g2s(dq + SCOL, P.s + g0, bytes, mybar);
-  };
-  if (lane == 0 && gw < n_tiles) {
-    if (MULTI) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    issue(gw);
-  }
-
-#pragma unroll 1
-  for (int tile = gw; tile < n_tiles; tile += GW, phase ^= 1u) {
-    mbar_wait(mybar, phase);
-    const int64_t sbase = tb0 + (int64_t)tile * WT - SG_PRE;  // record of slot 0
-    int w0 = SG_PRE, w1 = SG_PRE + WT;
-    if (tile == 0 || tile >= n_tiles - 2) {
-      // first and last tiles: clip to [r0, r1) and to the end of the column,
-      // plant the sentinels (record 0 starts a query, the last one ends one)
-      const int nrel = (int)(n_all - sbase < TBUF ? n_all - sbase : TBUF);
-      if (lane == 0) {
-        if (sbase + SG_PRE == 0)
-          sts32(aq + SG_PRE * 4u - 4u, ~(uint32_t)lds32(aq + SG_PRE * 4u));
-        if (nrel < TBUF)
-          sts32(aq + (uint32_t)nrel * 4u, ~(uint32_t)lds32(aq + (uint32_t)nrel * 4u - 4u));
-      }
-      if (r0 - sbase > w0) w0 = (int)(r0 - sbase < (1 << 30) ? r0 - sbase : (1 << 30));
-      if (r1 - sbase < w1) w1 = (int)(r1 - sbase);
-      if (w1 > nrel) w1 = nrel;
-      __syncwarp();
+    auto issue = [&](int tile) {
+      const int64_t tb = tb0 + (int64_t)tile * WT;
+      const int64_t g0 = tb >= SG_PRE ? tb - SG_PRE : 0;
+      int64_t g1 = tb + WT + SG_POST;
+      if (g1 > n_all) g1 = n_all;
+      const uint32_t bytes = (uint32_t)(((g1 - g0) * 4 + 15) & ~15ll);
+      const uint32_t dq = aq + (uint32_t)(g0 - (tb - SG_PRE)) * 4u;
+      mbar_expect_tx(mybar, 2 * bytes);
+      bulk_g2s(dq, P.q + g0, bytes, mybar);
+      bulk_g2s(dq + SCOL, P.s + g0, bytes, mybar);
+    };
+    if (lane == 0 && gw < n_tiles) {
+      if (MULTI) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(gw);
     }
-    // seeking: skip to the record after the next tail (the first own head is
-    // the record after the first tail at or after w0 - 1; a listed long query
-    // is skipped the same way)
-    int cur = w0 - 1;
-    bool seeking = true;
+
 #pragma unroll 1
-    while (cur < w1) {
-      const uint32_t ax = aq + (uint32_t)(cur + lane) * 4u;
-      const int qa = lds32(ax), qb = lds32(ax + 4u);
-      const uint32_t sv = (uint32_t)lds32(ax + SCOL);
-      const unsigned T = __ballot_sync(FULL, qa != qb);
-      if (seeking || T == 0) {
-        if (!seeking && lane == 0) {
-          // no tail within 32 records of the head: seg_long_kernel's query
-          const ull at = atomicAdd(P.long_list, 1ull);
-          P.long_list[1 + at] = (ull)(sbase + cur);
+    for (int tile = gw; tile < n_tiles; tile += GW, phase ^= 1u) {
+      mbar_wait(mybar, phase);
+      const int64_t sbase = tb0 + (int64_t)tile * WT - SG_PRE;  // record of slot 0
+      int w0 = SG_PRE, w1 = SG_PRE + WT;
+      if (tile == 0 || tile >= n_tiles - 2) {
+        // first and last tiles: clip to [r0, r1) and to the end of the column,
+        // plant the sentinels (record 0 starts a query, the last one ends one)
+        const int nrel = (int)(n_all - sbase < TBUF ? n_all - sbase : TBUF);
+        if (lane == 0) {
+          if (sbase + SG_PRE == 0)
+            sts32(aq + SG_PRE * 4u - 4u, ~(uint32_t)lds32(aq + SG_PRE * 4u));
+          if (nrel < TBUF)
+            sts32(aq + (uint32_t)nrel * 4u, ~(uint32_t)lds32(aq + (uint32_t)nrel * 4u - 4u));
         }
-        seeking = T == 0;
-        cur += T ? __ffs(T) : 32;
-        continue;
+        if (r0 - sbase > w0) w0 = (int)(r0 - sbase < (1 << 30) ? r0 - sbase : (1 << 30));
+        if (r1 - sbase < w1) w1 = (int)(r1 - sbase);
+        if (w1 > nrel) w1 = nrel;
+        __syncwarp();
       }
-      // whole queries whose head lies before w1
-      const int lim = w1 - cur;
-      unsigned Tl = T;
-      if (lim <= 32) {
-        const unsigned t2 = T & (FULL << (lim - 1));
-        if (t2) Tl = T & (FULL >> (32 - __ffs(t2)));
-      }
-      const int cons = 32 - __clz(Tl);
-      const unsigned tge = Tl & ge;             // tails at or after me
-      const bool act = tge != 0;                // a lane of a whole query
-      const unsigned H = (Tl << 1) | 1u;        // heads
-      const int sl = 31 - __clz(H & le);        // my query's first lane
-      // my query's lanes: from sl up to the first tail at or after me
-      const unsigned segm = act ? ((tge ^ (tge - 1u)) & (FULL << sl)) : 0u;
-      const uint32_t svc = min(sv, V32);
-      if (act && sv != svc) sts32(badflag, 1u);
-      const uint32_t code = lds16w(row + svc * 2u);
-      // classify.assign_rank: all taxa equal; classify.assign_none: one subject
-      const uint32_t key = KIND == WK_KIND_RANK ? code : sv;
-      const uint32_t kh = __shfl_sync(FULL, key, sl);
-      const unsigned NE = __ballot_sync(FULL, act && key != kh);
-      uint32_t amt = (act && (H & mybit)) ? (uint32_t)WK_UNITS : 0u;
-      uint32_t c = code;
-      if (NE) {
-        const bool alleq = (NE & segm) == 0;
-        if (MODE == FX_UNIQ) {
-          if (!alleq) c = C_NONE;
-        } else if (ABOVE) {
-          // classify.assign_rank with --above (classify.py:119-123): None if
-          // a subject has no taxon, else tree.find_lca of the taxa
-          // (tree.py:513-566), the root -> None.  Repeats do not matter.  The
-          // taxa of a query are folded towards its head lane in log steps.
-          const unsigned NB = __ballot_sync(FULL, act && code == C_NONE) & segm;
-          const int se = __ffs(tge);  // one past my query's last lane
-          const int dist = alleq ? 0 : se - 1 - lane;  // lanes after me
-          const int maxd = __reduce_max_sync(FULL, dist);
-          uint32_t v = code;
+      // seeking: skip to the record after the next tail (the first own head is
+      // the record after the first tail at or after w0 - 1; a listed long query
+      // is skipped the same way)
+      int cur = w0 - 1;
+      bool seeking = true;
 #pragma unroll 1
-          for (int o = 1; o <= maxd; o <<= 1) {
-            const uint32_t w = __shfl_down_sync(FULL, v, o);
-            if (o <= dist && !NB && w != v) v = (uint32_t)lca2(TR, (int)v, (int)w);
+      while (cur < w1) {
+        const uint32_t ax = aq + (uint32_t)(cur + lane) * 4u;
+        const int qa = lds32(ax), qb = lds32(ax + 4u);
+        const uint32_t sv = (uint32_t)lds32(ax + SCOL);
+        const unsigned T = __ballot_sync(FULL, qa != qb);
+        if (seeking || T == 0) {
+          if (!seeking && lane == 0) {
+            // no tail within 32 records of the head: seg_long_kernel's query
+            const ull at = atomicAdd(P.long_list, 1ull);
+            P.long_list[1 + at] = (ull)(sbase + cur);
           }
-          if (!alleq) c = (NB || v == (uint32_t)P.root) ? C_NONE : v;
-        } else {
-          // set semantics of the subject pool (align.py:339): a repeat has
-          // an equal subject earlier in its query.  Only the records of
-          // non-unanimous queries look back (straight from the staged
-          // column): three records unconditionally, further ones two per
-          // trip as far as the longest such query of the window reaches.
-          const int dist = alleq ? 0 : lane - sl;
-          const uint32_t as = ax + SCOL;
-          const uint32_t p1 = (uint32_t)lds32(as - 4u), p2 = (uint32_t)lds32(as - 8u),
-                         p3 = (uint32_t)lds32(as - 12u);
-          bool rep = (p1 == sv && dist >= 1) || (p2 == sv && dist >= 2) ||
-                     (p3 == sv && dist >= 3);
-          const int maxd = __reduce_max_sync(FULL, dist);
+          seeking = T == 0;
+          cur += T ? __ffs(T) : 32;
+          continue;
+        }
+        // whole queries whose head lies before w1
+        const int lim = w1 - cur;
+        unsigned Tl = T;
+        if (lim <= 32) {
+          const unsigned t2 = T & (FULL << (lim - 1));
+          if (t2) Tl = T & (FULL >> (32 - __ffs(t2)));
+        }
+        const int cons = 32 - __clz(Tl);
+        const unsigned tge = Tl & ge;             // tails at or after me
+        const bool act = tge != 0;                // a lane of a whole query
+        const unsigned H = (Tl << 1) | 1u;        // heads
+        const int sl = 31 - __clz(H & le);        // my query's first lane
+        // my query's lanes: from sl up to the first tail at or after me
+        const unsigned segm = act ? ((tge ^ (tge - 1u)) & (FULL << sl)) : 0u;
+        const uint32_t svc = min(sv, V32);
+        if (act && sv != svc) sts32(badflag, 1u);
+        const uint32_t code = lds16w(row + svc * 2u);
+        // classify.assign_rank: all taxa equal; classify.assign_none: one subject
+        const uint32_t key = KIND == WK_KIND_RANK ? code : sv;
+        const uint32_t kh = __shfl_sync(FULL, key, sl);
+        const unsigned NE = __ballot_sync(FULL, act && key != kh);
+        uint32_t amt = (act && (H & mybit)) ? (uint32_t)WK_UNITS : 0u;
+        uint32_t c = code;
+        if (NE) {
+          const bool alleq = (NE & segm) == 0;
+          if (MODE == FX_UNIQ) {
+            if (!alleq) c = C_NONE;
+          } else if (ABOVE) {
+            // classify.assign_rank with --above (classify.py:119-123): None if
+            // a subject has no taxon, else tree.find_lca of the taxa
+            // (tree.py:513-566), the root -> None.  Repeats do not matter.  The
+            // taxa of a query are folded towards its head lane in log steps.
+            const unsigned NB = __ballot_sync(FULL, act && code == C_NONE) & segm;
+            const int se = __ffs(tge);  // one past my query's last lane
+            const int dist = alleq ? 0 : se - 1 - lane;  // lanes after me
+            const int maxd = __reduce_max_sync(FULL, dist);
+            uint32_t v = code;
 #pragma unroll 1
-          for (int m = 4; m <= maxd; m += 2) {
-            const uint32_t o1 = (uint32_t)lds32(as - 4u * (uint32_t)m);
-            const uint32_t o2 = (uint32_t)lds32(as - 4u * (uint32_t)m - 4u);
-            rep = rep || (o1 == sv && m <= dist) || (o2 == sv && m < dist);
-          }
-          const bool nd = !alleq && !rep;
-          // k' = subjects with a taxon (rank) / distinct subjects (none)
-          const bool contrib = nd && (KIND != WK_KIND_RANK || code != C_NONE);
-          const unsigned CB = __ballot_sync(FULL, contrib) & segm;
-          if (!alleq) {
-            const int d = __popc(CB);
-            const uint32_t u = (uint32_t)lds32(usm + (uint32_t)d * 4u);
-            const bool em = contrib && code != C_NONE;
-            amt = em ? u : 0u;
-            if (em && u == 0u) {
-              // rare: 1/d with d not dividing WK_UNITS (overflow list)
-              const ull at = atomicAdd(P.ovf_n, 1ull);
-              if ((int64_t)at < P.ovf_cap) {
-                P.ovf_key[at] = (int64_t)pack_plain(P, e, sample, (int64_t)code);
-                P.ovf_den[at] = d;
-              } else {
-                atomicOr(P.err, ERR_OVF_FULL);
+            for (int o = 1; o <= maxd; o <<= 1) {
+              const uint32_t w = __shfl_down_sync(FULL, v, o);
+              if (o <= dist && !NB && w != v) v = (uint32_t)lca2(TR, (int)v, (int)w);
+            }
+            if (!alleq) c = (NB || v == (uint32_t)P.root) ? C_NONE : v;
+          } else {
+            // set semantics of the subject pool (align.py:339): a repeat has
+            // an equal subject earlier in its query.  Only the records of
+            // non-unanimous queries look back (straight from the staged
+            // column): three records unconditionally, further ones two per
+            // trip as far as the longest such query of the window reaches.
+            const int dist = alleq ? 0 : lane - sl;
+            const uint32_t as = ax + SCOL;
+            const uint32_t p1 = (uint32_t)lds32(as - 4u), p2 = (uint32_t)lds32(as - 8u),
+                           p3 = (uint32_t)lds32(as - 12u);
+            bool rep = (p1 == sv && dist >= 1) || (p2 == sv && dist >= 2) ||
+                       (p3 == sv && dist >= 3);
+            const int maxd = __reduce_max_sync(FULL, dist);
+#pragma unroll 1
+            for (int m = 4; m <= maxd; m += 2) {
+              const uint32_t o1 = (uint32_t)lds32(as - 4u * (uint32_t)m);
+              const uint32_t o2 = (uint32_t)lds32(as - 4u * (uint32_t)m - 4u);
+              rep = rep || (o1 == sv && m <= dist) || (o2 == sv && m < dist);
+            }
+            const bool nd = !alleq && !rep;
+            // k' = subjects with a taxon (rank) / distinct subjects (none)
+            const bool contrib = nd && (KIND != WK_KIND_RANK || code != C_NONE);
+            const unsigned CB = __ballot_sync(FULL, contrib) & segm;
+            if (!alleq) {
+              const int d = __popc(CB);
+              const uint32_t u = (uint32_t)lds32(usm + (uint32_t)d * 4u);
+              const bool em = contrib && code != C_NONE;
+              amt = em ? u : 0u;
+              if (em && u == 0u) {
+                // rare: 1/d with d not dividing WK_UNITS (overflow list)
+                const ull at = atomicAdd(P.ovf_n, 1ull);
+                if ((int64_t)at < P.ovf_cap) {
+                  P.ovf_key[at] = (int64_t)pack_plain(P, e, sample, (int64_t)code);
+                  P.ovf_den[at] = d;
+                } else {
+                  atomicOr(P.err, ERR_OVF_FULL);
+                }
               }
             }
           }
         }
-      }
-      // 'Unassigned' sits in the slot after the private range
-      const bool isun = c == C_NONE;
-      const uint32_t slot = isun ? wid : c - off;
-      if (amt) {
-        if (slot < (isun ? wid1 : wid)) {
-          const uint32_t old = atoms_add(tbl + slot * 4u, amt);
-          if (old + amt < old)  // carry out of the 32-bit low word (rare)
-            atomicAdd(crow + (isun ? (uint32_t)(P.NF1 - 1) : c), 1ull << 32);
-        } else if (!isun) {
-          atomicAdd(crow + c, (ull)amt);  // a value outside the private range
+        // 'Unassigned' sits in the slot after the private range
+        const bool isun = c == C_NONE;
+        const uint32_t slot = isun ? wid : c - off;
+        if (amt) {
+          if (slot < (isun ? wid1 : wid)) {
+            const uint32_t old = atoms_add(tbl + slot * 4u, amt);
+            if (old + amt < old)  // carry out of the 32-bit low word (rare)
+              atomicAdd(crow + (isun ? (uint32_t)(P.NF1 - 1) : c), 1ull << 32);
+          } else if (!isun) {
+            atomicAdd(crow + c, (ull)amt);  // a value outside the private range
+          }
         }
+        cur += cons;
       }
-      cur += cons;
+      __syncwarp();  // every lane is done with this stage
+      if (lane == 0 && tile + GW < n_tiles) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(tile + GW);
+      }
     }
-    __syncwarp();  // every lane is done with this stage
-    if (lane == 0 && tile + GW < n_tiles) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      issue(tile + GW);
-    }
-  }
 
-  // write the CTA's partial counts back (util.sum_dict, util.py:78-94)
-  __syncthreads();
+    // write the CTA's partial counts back (util.sum_dict, util.py:78-94)
+    __syncthreads();
 #pragma unroll 1
-  for (uint32_t h = tid; h < cells; h += blockDim.x) {
-    const uint32_t v = (uint32_t)lds32(tbl + h * 4u);
-    if (v) {
-      const int64_t f = h < wid ? (int64_t)off + h : P.NF1 - 1;
-      atomicAdd(crow + f, (ull)v);
-      if (MULTI) sts32(tbl + h * 4u, 0);
+    for (uint32_t h = tid; h < cells; h += blockDim.x) {
+      const uint32_t v = (uint32_t)lds32(tbl + h * 4u);
+      if (v) {
+        const int64_t f = h < wid ? (int64_t)off + h : P.NF1 - 1;
+        atomicAdd(crow + f, (ull)v);
+        if (MULTI) sts32(tbl + h * 4u, 0);
+      }
     }
-  }
-  if (MULTI) __syncthreads();
+    if (MULTI) __syncthreads();
   }  // segments
   if (tid == 0 && lds32(badflag)) atomicOr(P.err, ERR_BAD_SUBJECT);
 }
