@@ -258,6 +258,8 @@ def run_reference(args):
     n = min(args.records, args.cpu_sample)
     if args.workload == 'cfg3':
         return run_reference_cfg3(args, threads)
+    if args.workload == 'cfg5':
+        return run_reference_cfg5(args, threads)
     args_records = args.records
     args.records = n
     case, entries, flags, q, s, nq = make_cfg2(args, 'cpu', 1002)
@@ -290,6 +292,45 @@ def run_reference(args):
         'gpu_launches': 0,
     }
     print(json.dumps(line))
+
+
+def run_reference_cfg5(args, threads):
+    """CPU arm of cfg5: the C port over a bounded sample (the strata table is
+    a hash on the CPU too)."""
+    from oracle import oracle as O
+    from woltka_b200._lib import KIND_RANK
+    n = min(args.records, 5_000_000)
+    q, s, qs, qt, nq, tab, n_ko = make_cfg5(n, 1005, 'cpu')
+    T = 1 + n_ko
+    parent = np.zeros(T, dtype=np.int32)
+    node_rank = np.zeros(T, dtype=np.int32)
+    node_rank[0] = -1
+    kw = dict(parent=parent, node_rank=node_rank, root=0,
+              sub_node=tab[0].astype(np.int32), sub_feat=None,
+              kinds=np.array([KIND_RANK], dtype=np.int32), target_rank=[0],
+              flags=0, n_samples=8, n_features=T, q_sample=qs.numpy(),
+              q_stratum=qt.numpy(), n_threads=threads)
+    q, s = q.numpy(), s.numpy()
+    steps = max(1, min(args.steps, 3))
+    O.classify(q, s, **kw)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.classify(q, s, **kw)
+    dt = time.perf_counter() - t0
+    val = n * steps / dt
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT,
+        'n_gpus': args.gpus, 'steps': steps, 'warmup': 1,
+        'ms_per_step': dt / steps * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32',
+        'data': 'synthetic', 'config': workload_config(args, ['ko']),
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads,
+                         'kind': 'port',
+                         'sample': f'{n} records of the same generator per '
+                                   f'step (C restatement, OpenMP)'},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+        'gpu_launches': 0}))
 
 
 def run_reference_cfg3(args, threads):
