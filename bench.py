@@ -399,8 +399,15 @@ def run_ours(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    near = None
     if world > 1:
+        # ranks of one box: keep each rank's pinned host columns and copy
+        # threads on its GPU's NUMA node (N = 1 keeps every core for the CPU arm)
+        from woltka_b200.distributed import bind_near_gpu
+        if not os.environ.get('WK_NO_BIND'):
+            near = bind_near_gpu(local)
         dist.init_process_group('nccl', device_id=dev)
+    args._near_cpus = len(near) if near else None
 
     def barrier():
         if world > 1:
@@ -578,6 +585,8 @@ def run_ours(args):
             'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
             'clocks': clocks, 'parity_on_sample': parity,
         }
+        if args._near_cpus:
+            line['cpus_bound_per_rank'] = args._near_cpus
         if text is not None:
             line['e2e_from_text'] = text
         print(json.dumps(line))

@@ -45,3 +45,32 @@ def reduce_counts(tensor, dst=0):
             dist.get_world_size() > 1:
         dist.reduce(tensor, dst=dst, op=dist.ReduceOp.SUM)
     return tensor
+
+
+def bind_near_gpu(device):
+    """Restrict this process to the CPUs NVML lists as local to CUDA device
+    `device`, so that host buffers pinned afterwards (first touch) and the
+    copy threads sit on the GPU's NUMA node — with one rank per GPU the ranks
+    otherwise share one socket's memory and the inter-socket link.  Returns
+    the CPU list, or None when NVML / the topology is not available (the
+    binding is an optimisation, never a requirement)."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(device)
+        bus = '%08x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id,
+                                    pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        ncpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        near = {64 * w + b for w, m in enumerate(words) for b in range(64)
+                if (int(m) >> b) & 1}
+        cpus = sorted(near & os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
