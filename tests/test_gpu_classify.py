@@ -450,11 +450,14 @@ def test_randomised_shapes_both_kernels_agree(engine, small_case, monkeypatch,
 
 @pytest.mark.parametrize('NF', [5000, 3_000_000])
 @pytest.mark.parametrize('mode', ['default', 'uniq+unassigned'])
-def test_rank_none_without_a_table(engine, mode, NF):
+@pytest.mark.parametrize('noseg', ['', '1'])
+def test_rank_none_without_a_table(engine, mode, NF, monkeypatch, noseg):
     """feature == subject (KIND_NONE_ID: an OGU table, or genes of the ordinal
-    path): the run-per-lane kernel with 24-bit codes, counts in the private
-    table when it fits (NF = 5000) and straight to global memory when it does
-    not (NF = 3e6)."""
+    path): the lane-per-record kernel, or the run-per-lane kernel with 24-bit
+    codes; counts in the private table when it fits (NF = 5000) and straight
+    to global memory when it does not (NF = 3e6)."""
+    if noseg:
+        monkeypatch.setenv('WK_NO_SEG', noseg)
     from oracle import oracle as O
     from woltka_b200._lib import KIND_NONE_ID
     rng = np.random.default_rng(NF)
@@ -469,7 +472,8 @@ def test_rank_none_without_a_table(engine, mode, NF):
     engine.set_plan(kinds, fl, 0.0, 2, NF)
     engine.set_subjects(None, None, NF)
     engine.classify_chunk(q, s, None, None, 1)
-    assert engine.last_kernel() == 'classify_fast_kernel'
+    assert engine.last_kernel() == ('classify_fast_kernel' if noseg else
+                                    'classify_seg_kernel')
     got = cases.collect(engine, 2, NF)
     exp = O.classify(q, s, kinds=kinds, flags=fl, n_samples=2, n_features=NF,
                      sample=1, n_threads=4)

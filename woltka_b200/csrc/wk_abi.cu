@@ -348,7 +348,8 @@ int wk_create(int device, wk_ctx **out) {
       (const void *)classify_seg_kernel<KD, MD, 256, true>
     const void *seg[] = {WK_SEGV(WK_KIND_RANK, FX_FRAC), WK_SEGV(WK_KIND_RANK, FX_UNIQ),
                          WK_SEGV(WK_KIND_RANK, FX_ABOVE), WK_SEGV(WK_KIND_NONE, FX_FRAC),
-                         WK_SEGV(WK_KIND_NONE, FX_UNIQ)};
+                         WK_SEGV(WK_KIND_NONE, FX_UNIQ), WK_SEGV(WK_KIND_NONE_ID, FX_FRAC),
+                         WK_SEGV(WK_KIND_NONE_ID, FX_UNIQ)};
 #undef WK_SEGV
     for (const void *fn : seg)
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -942,19 +943,19 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
     // run-per-lane kernel wherever LCAs are common (genus 1.71 vs 1.39 ms,
     // species 2.09 vs 1.58; phylum 0.39 vs 0.69): opt-in with WK_SEG_ABOVE.
     bool seg_done = false;
-    if (!gsink && !wide && !n_dev && NTmax == SW_NT && !getenv("WK_NO_SEG") &&
+    if (NTmax == SW_NT && !getenv("WK_NO_SEG") &&
         (mode == FX_FRAC || mode == FX_UNIQ ||
          (mode == FX_ABOVE && par_ok && getenv("WK_SEG_ABOVE")))) {
       int WTe[WK_MAX_ENTRIES];
       bool fits = true;
       const char *wt_env = getenv("WK_SEG_WT");
       for (int e = 0; e < c->E && fits; ++e) {
-        const uint32_t ce = (uint32_t)(P.dir_base[e + 1] - P.dir_base[e]);
+        const uint32_t ce = gsink ? 0u : (uint32_t)(P.dir_base[e + 1] - P.dir_base[e]);
         WTe[e] = 0;
         for (int wt : {512, 256})
           if (!WTe[e] && !(wt == 512 && wt_env && atoi(wt_env) == 256) &&
-              sg_layout(SG_NT / 32, wt, ce, (int64_t)c->Vp * 2 + par_bytes).total <=
-                  c->smem_optin)
+              sg_layout(SG_NT / 32, wt, ce, (wide ? 0 : (int64_t)c->Vp * 2) + par_bytes)
+                      .total <= c->smem_optin)
             WTe[e] = wt;
         fits = WTe[e] != 0;
       }
@@ -973,6 +974,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
           P.seg_list = sl;
         }
         P.direct_cells = dir_cells;
+        P.fast_gsink = gsink ? 1 : 0;
         // queries longer than a window are listed and done by seg_long_kernel
         TRY(c->longlist.reserve((size_t)(span / 33 + 4) * 8));
         P.long_list = c->longlist.as<ull>();
@@ -980,9 +982,9 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
           P.e_lo = e;
           P.e_hi = e + 1;
           const int WT = WTe[e];
-          const SgSmemLayout GL =
-              sg_layout(SG_NT / 32, WT, (uint32_t)(P.dir_base[e + 1] - P.dir_base[e]),
-                        (int64_t)c->Vp * 2 + par_bytes);
+          const SgSmemLayout GL = sg_layout(
+              SG_NT / 32, WT, gsink ? 0u : (uint32_t)(P.dir_base[e + 1] - P.dir_base[e]),
+              (wide ? 0 : (int64_t)c->Vp * 2) + par_bytes);
           const int64_t ft = (span + WT - 1) / WT;
           const int sgrid =
               (int)std::min<int64_t>(grid, (ft + SG_NT / 32 - 1) / (SG_NT / 32));
@@ -1003,6 +1005,9 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
             if (mode == FX_UNIQ) WK_SEG2(WK_KIND_RANK, FX_UNIQ);
             else if (mode == FX_ABOVE) WK_SEG2(WK_KIND_RANK, FX_ABOVE);
             else WK_SEG2(WK_KIND_RANK, FX_FRAC);
+          } else if (wide) {
+            if (mode == FX_UNIQ) WK_SEG2(WK_KIND_NONE_ID, FX_UNIQ);
+            else WK_SEG2(WK_KIND_NONE_ID, FX_FRAC);
           } else {
             if (mode == FX_UNIQ) WK_SEG2(WK_KIND_NONE, FX_UNIQ);
             else WK_SEG2(WK_KIND_NONE, FX_FRAC);
@@ -1016,6 +1021,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
         }
         P.e_lo = 0;
         P.e_hi = c->E;
+        P.fast_gsink = 0;
         c->last_kernel = "classify_seg_kernel";
         if (!dqsamp) return WK_OK;
         // interleaved samples (more than FX_MAX_SEG changes): the kernels above

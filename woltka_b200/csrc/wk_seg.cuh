@@ -67,15 +67,18 @@ __global__ void __launch_bounds__(SG_NT, 1)
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int TBUF = WT + SG_PRE + SG_POST;
   constexpr uint32_t SCOL = (uint32_t)TBUF * 4u;  // subject column after the query column
-  constexpr uint32_t C_NONE = FX_NONE;
+  // --rank none without a table: the subject is the feature (no staged row)
+  constexpr bool WIDE = KIND == WK_KIND_NONE_ID;
+  constexpr uint32_t C_NONE = WIDE ? 0xFFFFFFFFu : FX_NONE;
   constexpr bool ABOVE = KIND == WK_KIND_RANK && MODE == FX_ABOVE;
   const int tid = threadIdx.x, warp = tid >> 5;
   int lane = tid & 31;
   asm volatile("" : "+r"(lane));
   const int NW = blockDim.x >> 5;
   const int e = MULTI ? P.e_lo : 0;  // the entry of this launch
-  const uint32_t cells = (uint32_t)(P.dir_base[e + 1] - P.dir_base[e]);
-  const uint32_t rows_bytes = (uint32_t)P.Vp * 2u;
+  const bool gsink = P.fast_gsink != 0;  // counts straight to the global table
+  const uint32_t cells = gsink ? 0u : (uint32_t)(P.dir_base[e + 1] - P.dir_base[e]);
+  const uint32_t rows_bytes = WIDE ? 0u : (uint32_t)P.Vp * 2u;
   // --above: the parent array as uint16 behind the row
   const uint32_t par_bytes = ABOVE ? (((uint32_t)P.T + 7u) & ~7u) * 2u : 0u;
   const SgSmemLayout L = sg_layout(NW, WT, cells, (int64_t)rows_bytes + par_bytes);
@@ -92,7 +95,8 @@ __global__ void __launch_bounds__(SG_NT, 1)
   const SegList *SG = MULTI ? reinterpret_cast<const SegList *>(P.seg_list) : nullptr;
   const int nseg = SG ? SG->nseg : 1;
   if (nseg < 0) return;  // interleaved samples: classify_kernel does this chunk
-  const int64_t n_all = P.n;
+  // ordinal pairs: the record count lives in device memory
+  const int64_t n_all = P.n_dev ? (int64_t)*P.n_dev : P.n;
   if (!SG && (unsigned)P.sample >= (unsigned)P.S) return;
 
   if (lane == 0) mbar_init(mybar, 1);
@@ -102,7 +106,7 @@ __global__ void __launch_bounds__(SG_NT, 1)
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
-  if (tid == 0) {
+  if (tid == 0 && !WIDE) {
     mbar_expect_tx(tabbar, rows_bytes + par_bytes);
     bulk_g2s(row, P.tab16 + (size_t)e * P.Vp, rows_bytes, tabbar);
     if (ABOVE) bulk_g2s(row + rows_bytes, P.tab16 + P.par16_off, par_bytes, tabbar);
@@ -111,12 +115,15 @@ __global__ void __launch_bounds__(SG_NT, 1)
 #pragma unroll 1
   for (uint32_t h = tid; h < cells; h += blockDim.x) sts32(tbl + h * 4, 0);
   __syncthreads();
-  mbar_wait(tabbar, 0);
+  if (!WIDE) mbar_wait(tabbar, 0);
 
   const uint32_t V32 = (uint32_t)P.V;  // the staged row has a 'none' pad slot at V
-  const uint32_t off = (uint32_t)P.dir_off[e], wid = (uint32_t)P.dir_w[e];
+  // (no private table: every slot test fails and the counts go to HBM)
+  const uint32_t off = gsink ? 0u : (uint32_t)P.dir_off[e];
+  const uint32_t wid = gsink ? 0u : (uint32_t)P.dir_w[e];
   // 'Unassigned' is counted when asked for: slot wid passes `slot < wid1`
-  const uint32_t wid1 = (P.flags & WK_F_UNASSIGNED) ? wid + 1u : 0u;
+  const bool unas_on = (P.flags & WK_F_UNASSIGNED) != 0;
+  const uint32_t wid1 = (unas_on && !gsink) ? wid + 1u : 0u;
   const unsigned le = FULL >> (31 - lane), ge = FULL << lane;
   const unsigned mybit = 1u << lane;
   const int GW = (int)gridDim.x * NW;
@@ -128,8 +135,8 @@ __global__ void __launch_bounds__(SG_NT, 1)
 
 #pragma unroll 1
   for (int sg = 0; sg < nseg; ++sg) {
-    const int64_t r0 = SG ? SG->at[sg] : P.r0;
-    const int64_t r1 = SG ? SG->at[sg + 1] : P.r1;
+    const int64_t r0 = SG ? SG->at[sg] : (P.n_dev ? 0 : P.r0);
+    const int64_t r1 = SG ? SG->at[sg + 1] : (P.n_dev ? n_all : P.r1);
     const int sample = SG ? SG->sample[sg] : P.sample;
     if ((unsigned)sample >= (unsigned)P.S) continue;  // dropped sample (CTA-uniform)
     ull *const crow = P.cnt + ((int64_t)e * P.S + sample) * P.NF1;
@@ -209,7 +216,7 @@ __global__ void __launch_bounds__(SG_NT, 1)
         const unsigned segm = act ? ((tge ^ (tge - 1u)) & (FULL << sl)) : 0u;
         const uint32_t svc = min(sv, V32);
         if (act && sv != svc) sts32(badflag, 1u);
-        const uint32_t code = lds16w(row + svc * 2u);
+        const uint32_t code = WIDE ? (sv < V32 ? sv : C_NONE) : lds16w(row + svc * 2u);
         // classify.assign_rank: all taxa equal; classify.assign_none: one subject
         const uint32_t key = KIND == WK_KIND_RANK ? code : sv;
         const uint32_t kh = __shfl_sync(FULL, key, sl);
@@ -286,7 +293,10 @@ __global__ void __launch_bounds__(SG_NT, 1)
             if (old + amt < old)  // carry out of the 32-bit low word (rare)
               atomicAdd(crow + (isun ? (uint32_t)(P.NF1 - 1) : c), 1ull << 32);
           } else if (!isun) {
-            atomicAdd(crow + c, (ull)amt);  // a value outside the private range
+            // a value outside the private range, or no private table at all
+            atomicAdd(crow + c, (ull)amt);
+          } else if (gsink && unas_on) {
+            atomicAdd(crow + (uint32_t)(P.NF1 - 1), (ull)amt);  // 'Unassigned'
           }
         }
         cur += cons;
@@ -318,6 +328,7 @@ __global__ void __launch_bounds__(SG_NT, 1)
 __global__ void __launch_bounds__(128)
     seg_long_kernel(const __grid_constant__ ClsParams P) {
   const ull n = P.long_list[0];
+  const int64_t n_rec = P.n_dev ? (int64_t)*P.n_dev : P.n;
   const int lane = threadIdx.x & 31;
   const ull GW = (ull)gridDim.x * (blockDim.x >> 5);
   Sink K;  // unused by the global sink; tables come from global memory
@@ -325,7 +336,7 @@ __global__ void __launch_bounds__(128)
   K.sh = 0;
   K.cur = -1;
   for (ull i = (ull)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += GW)
-    process_long<false, SINK_GLOBAL>(P, K, 0u, P.n, (int64_t)P.long_list[1 + i], lane);
+    process_long<false, SINK_GLOBAL>(P, K, 0u, n_rec, (int64_t)P.long_list[1 + i], lane);
 }
 
 }  // namespace wk
