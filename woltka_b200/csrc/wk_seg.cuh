@@ -1,6 +1,7 @@
 // wk_seg.cuh — lane-per-record classify+count kernel with warp-private tiles
-// (classify_seg_kernel): one-entry plans in default (1/k' split) or --uniq
-// mode, one sample.
+// (classify_seg_kernel): plans of one kind — ranks, `--rank none` through a
+// table, or feature == subject — in default (1/k' split) or --uniq mode; one
+// launch per entry, one sample or a stream of contiguous samples.
 //
 // Same contract as the other two classify kernels (reference
 // workflow.py:316-335, :1017-1058, classify.py:32-51, :81-127, :144-171).
@@ -10,20 +11,24 @@
 // its lane 0 brings to the warp's slice of shared memory with TMA bulk copies
 // on the warp's own mbarrier (no CTA barrier in the steady state), the plan is
 // a template parameter (no flag tests, no entry loop), and the count sink is
-// the CTA's private range-compacted table.  A warp walks its tile in
-// 32-record windows that start at a query head and consume whole queries:
+// the CTA's private range-compacted table (or, for feature spaces that do not
+// fit, straight 64-bit reductions).  A warp walks its tile in 32-record
+// windows that start at a query head and consume whole queries:
 //   * T = ballot(q[i] != q[i+1]) gives every lane its query [sl, se);
 //   * unanimity (all taxa equal, classify.py:107-108; one distinct subject,
 //     classify.py:46-47) is one shuffle from the head lane and one ballot;
 //     a window whose queries are all unanimous needs nothing else: each head
 //     lane adds one unit;
-//   * only the lanes of non-unanimous queries enter the duplicate look-back
-//     (set semantics of the subject pool, align.py:339), then one ballot
+//   * only the records of non-unanimous queries look back for an equal
+//     subject earlier in their query (set semantics of the subject pool,
+//     align.py:339), straight from the staged subject column; one ballot then
 //     counts the contributing subjects k' and every such lane adds 1/k'
 //     (classify.py:167-170);
 //   * unit and share emissions are ONE shared-memory atomic per window.
-// Queries with no tail within 32 records of their head go to the
-// warp-cooperative process_long.
+// Queries with no tail within 32 records of their head are listed and done by
+// seg_long_kernel (the warp-cooperative process_long) right after.
+// An --above variant (log-step LCA fold over the lanes of a query) exists but
+// is slower than the run-per-lane kernel's and is opt-in (WK_SEG_ABOVE).
 #pragma once
 #include "wk_sweep.cuh"
 
