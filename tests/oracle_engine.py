@@ -14,7 +14,8 @@ import numpy as np
 
 from oracle import oracle as O
 from woltka_b200._lib import (KIND_NONE, KIND_FREE, KIND_RANK, KIND_NONE_ID,
-                              UNITS)
+                              UNITS, F_UNIQ, F_ABOVE, F_MAJOR, F_SIZES,
+                              F_UNASSIGNED)
 from woltka_b200.hierarchy import FlatTree
 
 
@@ -104,8 +105,76 @@ class OracleEngine:
         return np.zeros(self.V, dtype=np.int32)
 
     # -- classify ----------------------------------------------------------
+    def _one(self, subs, flags):
+        """Units [E, NF+1] and overflow of ONE query with subjects `subs`."""
+        sub_node = self.sub_node if self.sub_node is not None else \
+            np.full(self.V, -1, dtype=np.int32)
+        units, ovf, _ = O.classify(
+            np.zeros(len(subs), dtype=np.int32),
+            np.asarray(subs, dtype=np.int32), parent=self.parent,
+            node_rank=None if self.ft is None else self.ft.node_rank,
+            root=self.root, sub_node=sub_node, sub_feat=self._sub_feat(),
+            kinds=self.kinds, target_rank=self.trk, flags=flags,
+            major_th=self.major_th, subok=self.subok, n_samples=1,
+            n_features=self.NF, sample=0)
+        return units[:, 0, :], ovf
+
+    def _classify_sized(self, qidx, sidx, q_sample, sample):
+        """WK_F_SIZES: exact (subject, feature) shares per query
+        (classify.counter_size, classify.py:174-213): a uniquely assigned
+        query gives 1/k of its unit to each of its k subjects, a list gives
+        1/k' to every listed subject under its own taxon.  Built from
+        single-query calls of the oracle; results in the strata table with the
+        subject in the stratum's place, like the kernels."""
+        flags = self.flags & ~F_SIZES
+        plain = not (flags & (F_UNIQ | F_ABOVE | F_MAJOR))
+        un = (lambda f: None if f == self.NF else f)
+        own = self.__dict__.setdefault('_own_feature', {})
+        q = np.asarray(qidx)
+        cuts = np.flatnonzero(np.diff(q)) + 1
+        for a, b in zip(np.r_[0, cuts], np.r_[cuts, len(q)]):
+            qi = int(q[a])
+            samp = int(q_sample[qi]) if q_sample is not None else sample
+            if samp < 0 or samp >= self.S:
+                continue
+            subs = list(dict.fromkeys(np.asarray(sidx[a:b]).tolist()))
+            units, ovf = self._one(subs, flags)
+            for e, kind in enumerate(self.kinds):
+                listed = None
+                if (kind == KIND_RANK and plain) or \
+                        (kind in (KIND_NONE, KIND_NONE_ID) and
+                         not flags & F_UNIQ):
+                    # taxon of every subject alone (find_rank / the subject)
+                    taxa = []
+                    for sub in subs:
+                        if (e, sub) not in own:
+                            u1, _ = self._one([sub], flags & ~F_UNASSIGNED)
+                            nz = np.flatnonzero(u1[e])
+                            own[(e, sub)] = int(nz[0]) if len(nz) else None
+                        taxa.append(own[(e, sub)])
+                    if len(set(taxa)) > 1 or \
+                            (kind != KIND_RANK and len(subs) > 1):
+                        listed = [(sub, t) for sub, t in zip(subs, taxa)
+                                  if t is not None]
+                if listed is None:
+                    nz = np.flatnonzero(units[e])
+                    if not len(nz):
+                        continue
+                    assert len(nz) == 1 and units[e, nz[0]] == UNITS
+                    pairs, k = [(sub, int(nz[0])) for sub in subs], len(subs)
+                else:
+                    pairs, k = listed, len(listed)
+                for sub, f in pairs:
+                    if UNITS % k == 0:
+                        key = (e, samp, sub, un(f))
+                        self.strata[key] = self.strata.get(key, 0) + UNITS // k
+                    else:
+                        self.overflow.append((e, samp, sub, un(f), k))
+
     def classify_chunk(self, qidx, sidx, q_sample=None, q_stratum=None,
                        sample=0):
+        if self.flags & F_SIZES:
+            return self._classify_sized(qidx, sidx, q_sample, sample)
         sub_node = self.sub_node if self.sub_node is not None else \
             np.full(self.V, -1, dtype=np.int32)
         units, ovf, strata = O.classify(

@@ -160,16 +160,8 @@ def check(got, exp_raw, exp_rounded):
     assert round_like_reference(got) == exp_rounded
 
 
-def _has_sizes(name):
-    with open(join(GOLD, f'{name}.json')) as f:
-        return '"sizes": null' not in f.read()
-
-
 @pytest.mark.parametrize('name', CASES)
 def test_golden_oracle(name):
-    if _has_sizes(name):
-        pytest.skip('--sizes needs the kernels\' (subject, feature) table: '
-                    'GPU test; tests/test_pyport.py is the CPU twin')
     check(*run_case(name, 'oracle'))
 
 
