@@ -181,3 +181,52 @@ def test_host_chunk_is_matched_sub_chunk_by_sub_chunk(engine, monkeypatch, sub):
     monkeypatch.setenv('WK_ORD_SUB', sub)
     test_queries_straddling_tiles(engine)
     test_ordinal_then_classify(engine)
+
+
+def test_read_maps_with_coords_on_multi_hit_queries(tmp_path):
+    """--coords with --outmap sends the matcher's (record, gene) pairs through
+    the plain path (Session._ordinal_chunk_with_maps).  With several records
+    per query (multi-hit reads, mates) the counts must equal those of the
+    fused device route, every mapped read must be listed once, and a read with
+    one gene must list exactly that gene."""
+    from woltka_b200.workflow import classify, build_mapper
+    rng = np.random.default_rng(12)
+    contigs = [f'C{i}' for i in range(6)]
+    coords = tmp_path / 'coords.txt'
+    with open(coords, 'w') as f:
+        for c in contigs:
+            f.write(f'>{c}\n')
+            pos = 1
+            for gi in range(60):
+                ln = int(rng.integers(200, 900))
+                f.write(f'{c}_g{gi}\t{pos}\t{pos + ln}\n')
+                pos += ln - int(rng.integers(0, 150))
+    sam = tmp_path / 'S1.sam'
+    with open(sam, 'w') as f:
+        for qi in range(3000):
+            k = int(min(rng.geometric(0.5), 6))
+            for _ in range(k):
+                c = contigs[int(rng.integers(0, 6))]
+                p = int(rng.integers(1, 30000))
+                flag = int(rng.choice([0, 65, 129]))
+                f.write(f'R{qi}\t{flag}\t{c}\t{p}\t42\t100M\t*\t0\t0\t*\t*\n')
+    mapper, chunk = build_mapper(str(coords), None, 80, None)
+    kw = dict(ranks=['none'], chunk=chunk)
+    plain = classify(mapper, {str(sam): 'S1'}, **kw)
+    mapdir = tmp_path / 'maps'
+    mapdir.mkdir()
+    routed = classify(mapper, {str(sam): 'S1'}, rank2dir={'none': str(mapdir)},
+                      **kw)
+    assert set(routed['none']['S1']) == set(plain['none']['S1'])
+    for k, v in plain['none']['S1'].items():
+        assert abs(routed['none']['S1'][k] - v) < 1e-9
+    lines = (mapdir / 'S1.txt').read_text().splitlines()
+    names = [ln.split('\t')[0] for ln in lines]
+    assert len(names) == len(set(names)) > 1000
+    total = 0.0
+    for ln in lines:
+        parts = ln.split('\t')[1:]
+        total += 1.0
+        if len(parts) > 1:
+            assert all(p.endswith(':1') for p in parts)
+    assert abs(total - sum(plain['none']['S1'].values())) < 1e-6

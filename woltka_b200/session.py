@@ -433,7 +433,10 @@ class Session:
                 np.arange(len(genes.gbeg), dtype=np.int32))
             self._matcher.ordinal_enable_pairs()
         self._matcher.ordinal_chunk(*cols, th)
-        r, g = self._matcher.ordinal_pairs()      # sorted by (query, gene)
+        r, g = self._matcher.ordinal_pairs()      # (record, gene), sorted
+        # record -> query: the records of a query are contiguous and the query
+        # indices ascend, so the pairs of a query stay contiguous
+        r = cols[0][r]
         live = q_sample[r] >= 0
         r, g = r[live], g[live]
         if not len(r):
