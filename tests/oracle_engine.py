@@ -119,51 +119,71 @@ class OracleEngine:
             n_features=self.NF, sample=0)
         return units[:, 0, :], ovf
 
+    def _query_results(self, subs, flags):
+        """Per entry the assignment of ONE query with distinct subjects
+        `subs`: ('unique', feature) | ('list', [(subject, taxon), ...]) | None
+        — the str / list / None of classify.assign_* — from single-query calls
+        of the oracle."""
+        plain = not (flags & (F_UNIQ | F_ABOVE | F_MAJOR))
+        own = self.__dict__.setdefault('_own_feature', {})
+        units, _ = self._one(subs, flags)
+        out = []
+        for e, kind in enumerate(self.kinds):
+            listed = None
+            if (kind == KIND_RANK and plain) or \
+                    (kind in (KIND_NONE, KIND_NONE_ID) and
+                     not flags & F_UNIQ):
+                # taxon of every subject alone (find_rank / the subject)
+                taxa = []
+                for sub in subs:
+                    if (e, sub) not in own:
+                        u1, _ = self._one([sub], flags & ~F_UNASSIGNED)
+                        nz = np.flatnonzero(u1[e])
+                        own[(e, sub)] = int(nz[0]) if len(nz) else None
+                    taxa.append(own[(e, sub)])
+                if len(set(taxa)) > 1 or \
+                        (kind != KIND_RANK and len(subs) > 1):
+                    listed = [(sub, t) for sub, t in zip(subs, taxa)
+                              if t is not None]
+            if listed is not None:
+                out.append(('list', listed) if listed else None)
+                continue
+            nz = np.flatnonzero(units[e])
+            if not len(nz):
+                out.append(None)
+                continue
+            assert len(nz) == 1 and units[e, nz[0]] == UNITS
+            out.append(('unique', int(nz[0])))
+        return out
+
+    @staticmethod
+    def _queries(qidx):
+        q = np.asarray(qidx)
+        cuts = np.flatnonzero(np.diff(q)) + 1
+        return zip(np.r_[0, cuts].tolist(), np.r_[cuts, len(q)].tolist())
+
     def _classify_sized(self, qidx, sidx, q_sample, sample):
         """WK_F_SIZES: exact (subject, feature) shares per query
         (classify.counter_size, classify.py:174-213): a uniquely assigned
         query gives 1/k of its unit to each of its k subjects, a list gives
-        1/k' to every listed subject under its own taxon.  Built from
-        single-query calls of the oracle; results in the strata table with the
-        subject in the stratum's place, like the kernels."""
+        1/k' to every listed subject under its own taxon.  Results in the
+        strata table with the subject in the stratum's place, like the
+        kernels."""
         flags = self.flags & ~F_SIZES
-        plain = not (flags & (F_UNIQ | F_ABOVE | F_MAJOR))
         un = (lambda f: None if f == self.NF else f)
-        own = self.__dict__.setdefault('_own_feature', {})
-        q = np.asarray(qidx)
-        cuts = np.flatnonzero(np.diff(q)) + 1
-        for a, b in zip(np.r_[0, cuts], np.r_[cuts, len(q)]):
-            qi = int(q[a])
+        for a, b in self._queries(qidx):
+            qi = int(qidx[a])
             samp = int(q_sample[qi]) if q_sample is not None else sample
             if samp < 0 or samp >= self.S:
                 continue
             subs = list(dict.fromkeys(np.asarray(sidx[a:b]).tolist()))
-            units, ovf = self._one(subs, flags)
-            for e, kind in enumerate(self.kinds):
-                listed = None
-                if (kind == KIND_RANK and plain) or \
-                        (kind in (KIND_NONE, KIND_NONE_ID) and
-                         not flags & F_UNIQ):
-                    # taxon of every subject alone (find_rank / the subject)
-                    taxa = []
-                    for sub in subs:
-                        if (e, sub) not in own:
-                            u1, _ = self._one([sub], flags & ~F_UNASSIGNED)
-                            nz = np.flatnonzero(u1[e])
-                            own[(e, sub)] = int(nz[0]) if len(nz) else None
-                        taxa.append(own[(e, sub)])
-                    if len(set(taxa)) > 1 or \
-                            (kind != KIND_RANK and len(subs) > 1):
-                        listed = [(sub, t) for sub, t in zip(subs, taxa)
-                                  if t is not None]
-                if listed is None:
-                    nz = np.flatnonzero(units[e])
-                    if not len(nz):
-                        continue
-                    assert len(nz) == 1 and units[e, nz[0]] == UNITS
-                    pairs, k = [(sub, int(nz[0])) for sub in subs], len(subs)
+            for e, res in enumerate(self._query_results(subs, flags)):
+                if res is None:
+                    continue
+                if res[0] == 'unique':
+                    pairs, k = [(sub, res[1]) for sub in subs], len(subs)
                 else:
-                    pairs, k = listed, len(listed)
+                    pairs, k = res[1], len(res[1])
                 for sub, f in pairs:
                     if UNITS % k == 0:
                         key = (e, samp, sub, un(f))
@@ -171,10 +191,39 @@ class OracleEngine:
                     else:
                         self.overflow.append((e, samp, sub, un(f), k))
 
+    # -- read maps: the per-record assignment column of classify_kernel --------
+    def set_assign_output(self, enable=True):
+        self.want_assign = bool(enable)
+
+    def _record_assignments(self, qidx, sidx):
+        from woltka_b200.engine import ASSIGN_UNIQ
+        sidx = np.asarray(sidx)
+        asg = np.full((self.E, len(sidx)), -1, dtype=np.int32)
+        for a, b in self._queries(qidx):
+            first = {}
+            for i in range(a, b):
+                first.setdefault(int(sidx[i]), i)
+            for e, res in enumerate(self._query_results(list(first),
+                                                        self.flags)):
+                if res is None:
+                    continue
+                if res[0] == 'unique':
+                    asg[e, a] = res[1] | ASSIGN_UNIQ
+                else:
+                    for sub, t in res[1]:
+                        asg[e, first[sub]] = t
+        self._assign = asg
+
+    def fetch_assignments(self, n_rec):
+        assert self._assign.shape[1] == n_rec
+        return self._assign
+
     def classify_chunk(self, qidx, sidx, q_sample=None, q_stratum=None,
                        sample=0):
         if self.flags & F_SIZES:
             return self._classify_sized(qidx, sidx, q_sample, sample)
+        if getattr(self, 'want_assign', False):
+            self._record_assignments(qidx, sidx)
         sub_node = self.sub_node if self.sub_node is not None else \
             np.full(self.V, -1, dtype=np.int32)
         units, ovf, strata = O.classify(

@@ -91,11 +91,9 @@ def run_case(name, engine_factory=None):
     ranks = case['ranks']
     rank2dir = None
     if engine_factory == 'oracle':
-        # (read maps need the kernel's assignment column: GPU test only; the
-        # CPU twin of that check is tests/test_pyport.py)
         engine_factory = make_factory(case['tree'], case['rankdic'],
                                       case['root'], ranks, case['subok'])
-    elif case.get('expected_maps'):
+    if case.get('expected_maps'):
         import tempfile
         mapdir = tempfile.mkdtemp()
         rank2dir = {}
@@ -126,15 +124,7 @@ def run_case(name, engine_factory=None):
             for fn in sorted(os.listdir(d)):
                 with open(join(d, fn)) as fh:
                     maps[str(r)][fn[:-4]] = fh.read().splitlines()
-        if coords:
-            # --coords: the reference lists the reads in the order its
-            # per-contig sweep meets them, this path in the order of their
-            # first records; the lines themselves are identical
-            srt = lambda m: {r: {s: sorted(v) for s, v in d.items()}
-                             for r, d in m.items()}
-            assert srt(maps) == srt(case['expected_maps']), 'read maps differ'
-        else:
-            assert maps == case['expected_maps'], 'read maps differ'
+        assert maps == case['expected_maps'], 'read maps differ'
     exp_raw = dec(case['expected_raw'])
     exp_rounded = dec(case['expected_rounded'])
     if case.get('sizes'):

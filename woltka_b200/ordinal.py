@@ -18,7 +18,8 @@ import numpy as np
 
 from .align import iter_align
 
-__all__ = ['load_gene_coords', 'ordinal_mapper', 'GeneIndex', 'iter_records']
+__all__ = ['load_gene_coords', 'ordinal_mapper', 'GeneIndex', 'iter_records',
+           'reference_read_order']
 
 _IDX = (1 << 22) - 1
 
@@ -83,7 +84,7 @@ class GeneIndex:
     def __init__(self, coords, idmap, prefix=False):
         self.contig_names = list(coords)
         self.contig_index = {c: i for i, c in enumerate(self.contig_names)}
-        offs, begs, ends, gids = [0], [], [], []
+        offs, begs, ends, gids, local = [0], [], [], [], []
         for name in self.contig_names:
             codes = np.asarray(coords[name], dtype=np.int64)
             idx = codes & _IDX
@@ -97,6 +98,7 @@ class GeneIndex:
             order = np.argsort(gb, kind='stable')
             begs.append(gb[order])
             ends.append(ge[order])
+            local.append(order)
             ids = idmap[name]
             pfx = name + '_' if prefix else ''
             gids.extend(pfx + ids[i] for i in order)
@@ -110,6 +112,9 @@ class GeneIndex:
         self.gbeg = gb.astype(np.int32)
         self.gend = ge.astype(np.int32)
         self.gene_ids = gids
+        # index of every gene within its contig as the file listed it (the
+        # index the reference packs into its endpoint codes)
+        self.local_idx = cat(local).astype(np.int64)
         self._bound = None
 
     def bind(self, session):
@@ -131,6 +136,47 @@ class GeneIndex:
                 count=len(self.gene_ids))
             self._subj_of = session
         return self._subj
+
+
+def reference_read_order(genes, q, cidx, beg, end, pos, pair_rec, pair_gene):
+    """Query indices in the order the reference's result dict of one chunk
+    lists them (ordinal.flush_chunk, ordinal.py:296-332): contigs in the order
+    they first appear among the chunk's records; inside a contig with more than
+    five records the matches come out of the endpoint sweep — a pair is
+    emitted at the earlier of its two END events, several reads at one gene
+    end in the order of their starts (match_read_gene, ordinal.py:476-582) —
+    and with five or fewer, read by read (match_read_gene_quart, :650-811); a
+    query is listed where its first match is.
+
+    q, cidx, beg, end: per record (any order); pos: position of the record in
+    the chunk as read; pair_rec / pair_gene: the matches (record, gene)."""
+    q, cidx = np.asarray(q), np.asarray(cidx)
+    beg, end = np.asarray(beg, dtype=np.int64), np.asarray(end, dtype=np.int64)
+    pos = np.asarray(pos, dtype=np.int64)
+    pair_rec, pair_gene = np.asarray(pair_rec), np.asarray(pair_gene)
+    if not len(pair_rec):
+        return np.zeros(0, dtype=np.int64)
+    # contigs by first appearance, records per contig
+    by_pos = np.argsort(pos, kind='stable')
+    seen, first = np.unique(cidx[by_pos], return_index=True)
+    corder = np.full(int(cidx.max()) + 2, 0, dtype=np.int64)
+    corder[seen] = np.argsort(np.argsort(first))
+    count = np.bincount(cidx[cidx >= 0], minlength=len(corder))
+    # first emission of every matched record
+    r, g = pair_rec, pair_gene
+    re_code = (end[r] << 24) + (1 << 23) + pos[r]
+    ge_code = (genes.gend[g].astype(np.int64) << 24) + (3 << 22) + \
+        genes.local_idx[g]
+    ev = np.minimum(re_code, ge_code)
+    sweep = count[cidx[r]] > 5
+    k1 = np.where(sweep, ev, pos[r])
+    k2 = np.where(sweep, (beg[r] << 24) + pos[r], 0)
+    k0 = corder[cidx[r]]
+    # smallest key per query
+    order = np.lexsort((k2, k1, k0))
+    qs = q[r][order]
+    _, firsts = np.unique(qs, return_index=True)
+    return qs[np.sort(firsts)]
 
 
 def iter_records(fh, fmt=None, excl=None, n=2**20):

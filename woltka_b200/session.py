@@ -314,7 +314,7 @@ class Session:
             eng.classify_parsed(None, si)
         return n_qry
 
-    def _write_readmaps(self, n_rec, reads, starts, q_sample):
+    def _write_readmaps(self, n_rec, reads, starts, q_sample, stops=None):
         """Append this chunk's read-to-taxon lines (file.write_readmap,
         file.py:469-500, called at workflow.py:1042-1046): one line per
         assigned query; a unique assignment prints the taxon, a list prints
@@ -330,7 +330,7 @@ class Session:
                 lines = {}
                 row = asg[e]
                 for j, read in enumerate(reads):
-                    vals = row[starts[j]:starts[j + 1]]
+                    vals = row[starts[j]:stops[j] if stops else starts[j + 1]]
                     vals = vals[vals >= 0]
                     if not len(vals):
                         continue
@@ -413,19 +413,21 @@ class Session:
         q_stratum = np.asarray(q_stratum, dtype=np.int32) if use_strata \
             else None
         if self.rank2dir is not None or (self.sizes and use_strata):
+            pos = order if order is not None else np.arange(len(q))
             return self._ordinal_chunk_with_maps(genes, cols, th, q_sample,
-                                                 q_stratum, reads)
+                                                 q_stratum, reads, pos)
         for eng in self.engines:
             eng.ordinal_chunk(*cols, th, q_sample, q_stratum)
 
     def _ordinal_chunk_with_maps(self, genes, cols, th, q_sample, q_stratum,
-                                 reads):
+                                 reads, pos):
         """--coords with --outmap: the matcher alone runs first (a plan-less
-        engine), its (query, gene) pairs come back and go through the plain
+        engine), its (record, gene) pairs come back and go through the plain
         path, whose kernel also writes the per-record assignment column the
         read maps are made of (workflow.py:1042-1046 on the gene sets of
-        ordinal.flush_chunk).  Lines are in the order of the reads' first
-        records; the reference's order follows its per-contig sweep."""
+        ordinal.flush_chunk).  The lines come in the order the reference's
+        per-contig sweep lists the reads (ordinal.reference_read_order);
+        `pos` is the position of every record in the chunk as read."""
         if getattr(self, '_matcher', None) is None:
             self._matcher = self._engine_factory(self._device)
             self._matcher.ordinal_set_genes(
@@ -434,6 +436,11 @@ class Session:
             self._matcher.ordinal_enable_pairs()
         self._matcher.ordinal_chunk(*cols, th)
         r, g = self._matcher.ordinal_pairs()      # (record, gene), sorted
+        listed = None
+        if self.rank2dir is not None:
+            from .ordinal import reference_read_order
+            listed = reference_read_order(genes, cols[0], cols[1], cols[2],
+                                          cols[3], pos, r, g)
         # record -> query: the records of a query are contiguous and the query
         # indices ascend, so the pairs of a query stay contiguous
         r = cols[0][r]
@@ -456,9 +463,12 @@ class Session:
         for eng in self.engines:
             eng.classify_chunk(r, s2, q_sample, q_stratum)
         if self.rank2dir is not None:
-            qs_u, starts = np.unique(r, return_index=True)
-            self._write_readmaps(len(r), [reads[j] for j in qs_u.tolist()],
-                                 starts.tolist() + [len(r)], q_sample[qs_u])
+            listed = listed[q_sample[listed] >= 0]
+            starts = np.searchsorted(r, listed, 'left')
+            stops = np.searchsorted(r, listed, 'right')
+            self._write_readmaps(len(r), [reads[j] for j in listed.tolist()],
+                                 starts.tolist(), q_sample[listed],
+                                 stops.tolist())
 
     def _sized_results(self, data):
         """--sizes: sum over subjects of weight x the exact share the subject
