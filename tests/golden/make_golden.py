@@ -355,6 +355,14 @@ def bundled():
              strata_rel='burst.genus.map',
              sizes=join('sizes', 'burst.length.map'),
              note='plain: genome counts weighted by length, per genus stratum')
+    run_case('burst_ogu_strat_sizes_map', 'burst', ranks=None,
+             strata_rel='burst.genus.map', maps=True,
+             sizes=join('sizes', 'burst.length.map'),
+             note='--sizes + --stratify + --outmap: the map lists every read')
+    run_case('burst_genus_process_sizes_map', 'burst', hier=fmaps,
+             ranks='process,none', coords_rel='coords.txt.xz',
+             strata_rel='burst.genus.map', sizes='.', maps=True,
+             note='ordinal + stratified + sizes + read maps')
     run_case('burst_genus_process_sizes', 'burst', hier=fmaps,
              ranks='process,none', coords_rel='coords.txt.xz',
              strata_rel='burst.genus.map', sizes='.',

@@ -203,8 +203,8 @@ class OracleEngine:
             first = {}
             for i in range(a, b):
                 first.setdefault(int(sidx[i]), i)
-            for e, res in enumerate(self._query_results(list(first),
-                                                        self.flags)):
+            for e, res in enumerate(self._query_results(
+                    list(first), self.flags & ~F_SIZES)):
                 if res is None:
                     continue
                 if res[0] == 'unique':
@@ -220,10 +220,10 @@ class OracleEngine:
 
     def classify_chunk(self, qidx, sidx, q_sample=None, q_stratum=None,
                        sample=0):
-        if self.flags & F_SIZES:
-            return self._classify_sized(qidx, sidx, q_sample, sample)
         if getattr(self, 'want_assign', False):
             self._record_assignments(qidx, sidx)
+        if self.flags & F_SIZES:
+            return self._classify_sized(qidx, sidx, q_sample, sample)
         sub_node = self.sub_node if self.sub_node is not None else \
             np.full(self.V, -1, dtype=np.int32)
         units, ovf, strata = O.classify(

@@ -172,9 +172,6 @@ def test_gene_coords_encoding():
 
 
 def test_unsupported_options_are_loud():
-    with pytest.raises(NotImplementedError):
-        classify(None, [], ranks=['none'], sizes={'a': 1.0},
-                 stratmap={'S1': 'x'}, rank2dir={'none': 'x'})
     # coverage needs ranges: not with --coords (the reference crashes on the
     # gene sets, range.py:142), and the coordinate format is checked up front
     # (range.py:229-245)

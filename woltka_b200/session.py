@@ -24,6 +24,7 @@ from ._lib import (UNITS, MAX_ENTRIES, KIND_NONE, KIND_FREE, KIND_RANK,
 from .hierarchy import FlatTree
 
 _SEP = '_'
+_NO_STRATUM = -2     # device copy of a subject for reads without a stratum
 
 
 def _split_sample(query):
@@ -249,11 +250,14 @@ class Session:
             starts.append(len(q))
             if sized_strata:
                 # the stratum travels with the subject; reads without one
-                # contribute nothing (classify.py:283-284)
-                if stratum >= 0:
+                # contribute nothing (classify.py:283-284) — they only stay
+                # in the stream (as copies whose shares are dropped) when
+                # read maps are written, which list every read
+                if stratum >= 0 or self.rank2dir is not None:
                     for idx in {self.subject(sub) for sub in subjects}:
                         q.append(nq)
-                        s.append(self.subject_in_stratum(idx, stratum))
+                        s.append(self.subject_in_stratum(
+                            idx, stratum if stratum >= 0 else _NO_STRATUM))
             else:
                 for sub in subjects:
                     q.append(nq)
@@ -451,10 +455,13 @@ class Session:
         s2 = genes.subjects(self)[g]
         if self.sizes and q_stratum is not None:
             # --sizes with --stratify: the stratum travels with the subject
-            live = q_stratum[r] >= 0
-            r, s2 = r[live], s2[live]
-            s2 = np.fromiter((self.subject_in_stratum(a, b) for a, b in
-                              zip(s2.tolist(), q_stratum[r].tolist())),
+            if self.rank2dir is None:
+                live = q_stratum[r] >= 0
+                r, s2 = r[live], s2[live]
+            s2 = np.fromiter((self.subject_in_stratum(
+                                  a, b if b >= 0 else _NO_STRATUM)
+                              for a, b in zip(s2.tolist(),
+                                              q_stratum[r].tolist())),
                              dtype=np.int32, count=len(r))
             q_stratum = None
             self._sync_tables()
@@ -489,6 +496,8 @@ class Session:
                 shares[k] = shares.get(k, 0) + Fraction(1, den)
             try:
                 for (e, s, f, t) in sorted(shares):
+                    if strat_of[t] == _NO_STRATUM:
+                        continue
                     rank = self.order[grp[e]]
                     prof = data[rank][self.sample_names[s]]
                     name = self.feature_name(f)

@@ -180,10 +180,6 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
     `round_profiles` the two are identical.
     """
     is_ordinal = getattr(mapper, 'func', None) is ordinal_mapper
-    if sizes and stratmap and rank2dir is not None:
-        raise NotImplementedError(
-            'Read maps (--outmap) together with --sizes and --stratify are '
-            'not part of the GPU hot path yet.')
     if outcov_dir:
         coverage_offsets(outcov_fmt)     # an invalid format fails up front
         if is_ordinal:
