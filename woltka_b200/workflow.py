@@ -18,8 +18,9 @@ Read maps (`rank2dir`) come from a per-record
 assignment column the kernel writes next to the counts; size-weighted counts
 (`sizes`, row F4) from the kernels' exact (subject, feature) shares, weighted
 on the host.  With `--coords` the read maps are made from the matcher's
-(query, gene) pairs sent through the plain path.  Subject coverage (`outcov_dir`, row F5) is
-accumulated and merged on the GPU (woltka_b200.coverage).  With `sizes` and
+(record, gene) pairs sent through the plain path, in the reference's line
+order.  Subject coverage (`outcov_dir`, row F5) is accumulated and merged on
+the GPU (woltka_b200.coverage).  With `sizes` and
 `stratmap` together (classify.counter_size_strat) a subject seen in a stratum
 becomes its own device subject, so the same (subject, feature) shares also
 carry the stratum.
