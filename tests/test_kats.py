@@ -234,3 +234,24 @@ def test_size_weighted_counts_vs_pure_python(opts):
     # a subject without a size is the reference's error
     with pytest.raises(ValueError, match='not found in the size map'):
         run('gpu', queries, ['none'], sizes={'G0_0_0': 1.0})
+
+
+def test_gene_coords_cache(tmp_path, monkeypatch):
+    """WOLTKA_B200_CACHE: build_mapper reads the coordinates file once, later
+    runs load the binary table; a changed file is parsed again."""
+    import numpy as np
+    fp = tmp_path / 'coords.txt'
+    fp.write_text('##genome\n>n1\ng1\t29\t5\ng2\t40\t90\n#n2\ng1\t7\t9\n')
+    plain = build_mapper(str(fp))[0].keywords
+    monkeypatch.setenv('WOLTKA_B200_CACHE', str(tmp_path / 'cache'))
+    for _ in range(2):                       # miss, then hit
+        kw = build_mapper(str(fp))[0].keywords
+        assert list(kw['coords']) == list(plain['coords'])
+        for c in plain['coords']:
+            assert np.array_equal(kw['coords'][c], plain['coords'][c])
+        assert kw['idmap'] == plain['idmap'] and kw['prefix'] == plain['prefix']
+    assert len(list((tmp_path / 'cache').iterdir())) == 1
+    fp.write_text('>n1\ng1\t29\t5\n>n3\ng9\t1\t2\ng8\t5\t9\n')
+    kw = build_mapper(str(fp))[0].keywords
+    assert list(kw['coords']) == ['n1', 'n3'] and kw['prefix'] is False
+    assert kw['idmap'] == {'n1': ['g1'], 'n3': ['g9', 'g8']}

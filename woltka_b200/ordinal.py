@@ -18,7 +18,8 @@ import numpy as np
 
 from .align import iter_align
 
-__all__ = ['load_gene_coords', 'ordinal_mapper', 'GeneIndex', 'iter_records',
+__all__ = ['load_gene_coords', 'load_gene_coords_cached', 'ordinal_mapper',
+           'GeneIndex', 'iter_records',
            'reference_read_order']
 
 _IDX = (1 << 22) - 1
@@ -74,6 +75,54 @@ def load_gene_coords(fh, sort=False):
         if sort:
             codes.sort(kind='stable')
         coords[name] = codes
+    return coords, idmap, isdup
+
+
+def load_gene_coords_cached(fp, opener, cache_dir):
+    """load_gene_coords(sort=True) of file `fp` through a binary cache
+    (the text parse is the one-off cost that grows with
+    the database, ordinal.py:338-430).  The cache file is keyed by the path,
+    size and mtime of `fp`; anything unreadable or stale is rebuilt."""
+    import hashlib
+    import os
+    st = os.stat(fp)
+    key = hashlib.sha1(f'{os.path.abspath(fp)}|{st.st_size}|{st.st_mtime_ns}'
+                       .encode()).hexdigest()[:20]
+    cfp = os.path.join(cache_dir, f'coords-{key}.npz')
+    try:
+        with np.load(cfp, allow_pickle=False) as z:
+            names = str(z['names']).split('\n')
+            off = z['off']
+            codes = z['codes']
+            ids = str(z['ids']).split('\n')
+            isdup = bool(z['isdup'])
+        if len(names) + 1 != len(off) or len(ids) * 2 != len(codes):
+            raise ValueError('inconsistent cache')
+        coords = {n: codes[2 * off[i]:2 * off[i + 1]]
+                  for i, n in enumerate(names)}
+        idmap = {n: ids[off[i]:off[i + 1]] for i, n in enumerate(names)}
+        return coords, idmap, isdup
+    except (OSError, KeyError, ValueError):
+        pass
+    with opener(fp) as fh:
+        coords, idmap, isdup = load_gene_coords(fh, sort=True)
+    names = list(coords)
+    if any('\n' in x for x in names) or \
+            any('\n' in g for n in names for g in idmap[n]):
+        return coords, idmap, isdup
+    off = np.cumsum([0] + [len(idmap[n]) for n in names]).astype(np.int64)
+    try:
+        os.makedirs(cache_dir, exist_ok=True)
+        tmp = f'{cfp}.{os.getpid()}.tmp.npz'
+        np.savez(tmp, names=np.asarray('\n'.join(names)), off=off,
+                 codes=np.concatenate([coords[n] for n in names])
+                 if names else np.zeros(0, dtype=np.int64),
+                 ids=np.asarray('\n'.join(g for n in names
+                                          for g in idmap[n])),
+                 isdup=np.asarray(isdup))
+        os.replace(tmp, cfp)
+    except OSError:
+        pass
     return coords, idmap, isdup
 
 

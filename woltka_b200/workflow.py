@@ -34,7 +34,8 @@ from functools import partial
 from os.path import basename
 
 from .align import plain_mapper
-from .ordinal import load_gene_coords, ordinal_mapper, GeneIndex, iter_records
+from .ordinal import (load_gene_coords, load_gene_coords_cached,
+                      ordinal_mapper, GeneIndex, iter_records)
 from .session import Session, _split_sample
 from .coverage import range_mapper, Coverage, coverage_offsets
 
@@ -126,8 +127,14 @@ def build_mapper(coords_fp=None, outcov_dir=None, overlap=None, chunk=None,
     """Plain or ordinal mapper and its chunk size (workflow.py:536-585)."""
     if coords_fp:
         _echo('Reading gene coordinates...', nl=False)
-        with readzip(coords_fp, zippers) as fh:
-            coords, idmap, prefix = load_gene_coords(fh, sort=True)
+        cache = os.environ.get('WOLTKA_B200_CACHE')
+        if cache:
+            # binary cache of the parsed table (SURVEY.md 8f row F2)
+            coords, idmap, prefix = load_gene_coords_cached(
+                coords_fp, partial(readzip, zippers=zippers), cache)
+        else:
+            with readzip(coords_fp, zippers) as fh:
+                coords, idmap, prefix = load_gene_coords(fh, sort=True)
         _echo(' Done.')
         _echo(f'  Total number of host sequences: {len(coords)}.')
         chunk = chunk or 2 ** 20
