@@ -34,26 +34,25 @@ def range_mapper(fh, fmt=None, excl=None, n=1000):
         yield qryque, subque
 
 
+_NAMED_FORMATS = {'bed': (0, 0), 'gff': (1, 0)}
+
+
 def coverage_offsets(fmt):
-    """Start / end offsets of an output coordinate format
-    (range.py:229-245)."""
-    begoff, endoff = 0, 0
-    errmsg = f'Invalid coverage format: {fmt}.'
-    if fmt is not None:
-        if fmt.lower() == 'bed':
-            pass
-        elif fmt.lower() == 'gff':
-            begoff, endoff = 1, 0
-        elif fmt.endswith(('i', 'e')):
-            try:
-                begoff = endoff = int(fmt[:-1])
-            except ValueError:
-                raise ValueError(errmsg)
-            if fmt[-1] == 'i':
-                endoff -= 1
-        else:
-            raise ValueError(errmsg)
-    return begoff, endoff
+    """(start offset, end offset) of an output coordinate format: 'bed'
+    (default) = 0-based exclusive, 'gff' = 1-based inclusive, or `<n>e` /
+    `<n>i` = n-based exclusive / inclusive (range.py:229-245, same error
+    text)."""
+    if fmt is None:
+        return 0, 0
+    if fmt.lower() in _NAMED_FORMATS:
+        return _NAMED_FORMATS[fmt.lower()]
+    try:
+        if fmt[-1] not in 'ie':
+            raise ValueError
+        base = int(fmt[:-1])
+    except (ValueError, IndexError):
+        raise ValueError(f'Invalid coverage format: {fmt}.')
+    return base, base - (fmt[-1] == 'i')
 
 
 class Coverage:
