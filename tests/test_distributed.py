@@ -57,3 +57,16 @@ def test_shard_bounds_never_split_a_query():
             assert c == 0 or c == len(q) or q[c] != q[c - 1]
     assert shard_bounds(np.zeros(50, dtype=int), 4) == [0, 50, 50, 50, 50]
     assert shard_bounds(np.zeros(0, dtype=int), 2) == [0, 0, 0]
+
+
+def test_bind_near_gpu_without_a_gpu_is_a_no_op():
+    """The NUMA binding of multi-rank runs is an optimisation: without NVML or
+    a device it leaves the affinity alone and says so."""
+    import os
+    from woltka_b200.distributed import bind_near_gpu
+    before = os.sched_getaffinity(0)
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    assert bind_near_gpu(0) is None
+    assert os.sched_getaffinity(0) == before
