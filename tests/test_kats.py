@@ -255,3 +255,47 @@ def test_gene_coords_cache(tmp_path, monkeypatch):
     kw = build_mapper(str(fp))[0].keywords
     assert list(kw['coords']) == ['n1', 'n3'] and kw['prefix'] is False
     assert kw['idmap'] == {'n1': ['g1'], 'n3': ['g9', 'g8']}
+
+
+@pytest.mark.parametrize('engine', ENGINES)
+def test_assign_readmap_seam(engine, tmp_path):
+    """The per-chunk seam with the reference's own vectors
+    (tests/test_workflow.py:545-603): counts are added into `data`, the read
+    map is appended, sizes weigh the subjects, a missing size is the
+    reference's ValueError."""
+    from woltka_b200.workflow import assign_readmap
+    qryq = ['R1', 'R2', 'R3']
+    subq = [('G1',), ('G1', 'G2'), ('G2', 'G3')]
+
+    def call(data, rank, **kw):
+        fac = make_factory(kw.get('tree'), kw.get('rankdic'), kw.get('root'),
+                           [rank], kw.get('subok', False)) \
+            if engine == 'oracle' else None
+        assign_readmap(qryq, subq, data, rank, 'S1', {}, _engine_factory=fac,
+                       **kw)
+        return data[rank]['S1']
+
+    assert call({'none': {}}, 'none') == {'G1': 1.5, 'G2': 1.0, 'G3': 0.5}
+    # added into what is there (util.sum_dict), read map appended
+    data = {'none': {'S1': {'G1': 1, 'G9': 2}}}
+    got = call(data, 'none', rank2dir={'none': str(tmp_path)})
+    assert got == {'G1': 2.5, 'G2': 1.0, 'G3': 0.5, 'G9': 2}
+    assert (tmp_path / 'S1.txt').read_text().splitlines() == \
+        ['R1\tG1', 'R2\tG1:1\tG2:1', 'R3\tG2:1\tG3:1']
+    assert call({'none': {}}, 'none', uniq=True, unasgd=True) == \
+        {'G1': 1, 'Unassigned': 2}
+    assert call({'free': {}}, 'free', tree=TREE) == {'T0': 1, 'T1': 2}
+    rankdic = {'T1': 'ko', 'T2': 'ko', 'T0': 'mo'}
+    assert call({'ko': {}}, 'ko', tree=TREE, rankdic=rankdic) == \
+        {'T1': 2.5, 'T2': 0.5}
+    sizes = {'G1': 0.3, 'G2': 0.5, 'G3': 1.0}
+    got = call({'ko': {}}, 'ko', tree=TREE, rankdic=rankdic, sizes=sizes)
+    assert got.keys() == {'T1', 'T2'}
+    assert abs(got['T1'] - 0.95) < 1e-12 and abs(got['T2'] - 0.5) < 1e-12
+    # stratified (classify.counter_strat): reads without a stratum are skipped
+    got = call({'none': {}}, 'none', strata={'R1': 'Esch', 'R3': 'Shig'})
+    assert got == {('Esch', 'G1'): 1, ('Shig', 'G2'): 0.5, ('Shig', 'G3'): 0.5}
+    del sizes['G3']
+    with pytest.raises(ValueError, match='One or more subjects are not found '
+                                         'in the size map.'):
+        call({'ko': {}}, 'ko', tree=TREE, rankdic=rankdic, sizes=sizes)

@@ -39,7 +39,8 @@ from .ordinal import (load_gene_coords, load_gene_coords_cached,
 from .session import Session, _split_sample
 from .coverage import range_mapper, Coverage, coverage_offsets
 
-__all__ = ['classify', 'build_mapper', 'readzip', 'range_mapper']
+__all__ = ['classify', 'build_mapper', 'assign_readmap', 'readzip',
+           'range_mapper']
 
 _OPENERS = {'.gz': gzip.open, '.bz2': bz2.open, '.xz': lzma.open,
             '.lzma': lzma.open}
@@ -287,3 +288,30 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
         sess.close()
     # one (possibly empty) profile per requested rank, like workflow.py:268
     return {rank: data[rank] for rank in dict.fromkeys(ranks)}
+
+
+def assign_readmap(qryque, subque, data, rank, sample, assigners, cache=1024,
+                   rank2dir=None, outzip=None, tree=None, rankdic=None,
+                   namedic=None, root=None, uniq=False, major=None,
+                   above=False, subok=False, sizes=None, unasgd=False,
+                   strata=None, _engine_factory=None, _device=0):
+    """The per-chunk seam of the reference (workflow.py:941-1058): assign the
+    queries of one (qryque, subque) chunk of `sample` at `rank` on the GPU,
+    optionally append the read map, and add the counts into
+    `data[rank][sample]` (util.sum_dict).  `major` is the fraction here (the
+    reference divides the percentage before it calls this, workflow.py:276);
+    `assigners` and `cache` (the reference's memoised assigner closures) are
+    accepted and not needed."""
+    sess = Session([rank], tree, rankdic, root, uniq, major, above, subok,
+                   unasgd, None, _engine_factory, _device, rank2dir, outzip,
+                   namedic, sizes, strata is not None)
+    try:
+        sess.add_chunk(qryque, subque, demux=False, sample_name=sample,
+                       strata_of=(lambda _: strata) if strata is not None
+                       else None)
+        counts = sess.results()[rank].get(sample, {})
+    finally:
+        sess.close()
+    total = data[rank].setdefault(sample, {})
+    for key, value in counts.items():
+        total[key] = total.get(key, 0) + value
