@@ -299,3 +299,39 @@ def test_assign_readmap_seam(engine, tmp_path):
     with pytest.raises(ValueError, match='One or more subjects are not found '
                                          'in the size map.'):
         call({'ko': {}}, 'ko', tree=TREE, rankdic=rankdic, sizes=sizes)
+
+
+def test_chunk_loop_helpers_under_their_reference_names(tmp_path):
+    # tests/test_workflow.py:489-547, :604-612
+    from woltka_b200.workflow import demultiplex, strip_suffix, read_strata
+    subs = [{'G1_1', 'G1_2', 'G2_3', 'G3'}, {'G1_1', 'G1.3', 'G4_5', 'G4_x'}]
+    assert list(strip_suffix(subs, sep='_')) == \
+        [{'G1', 'G2', 'G3'}, {'G1', 'G1.3', 'G4'}]
+    assert list(strip_suffix([{'NC_123456.1_300', 'ABCD000001.20_101'}],
+                             sep='_')) == [{'NC_123456.1', 'ABCD000001.20'}]
+    assert list(strip_suffix([{'G1.1', 'G1.2', 'G2'}, {'G1.1', 'G1.3', 'G3_x'}],
+                             sep='.')) == [{'G1', 'G2'}, {'G1', 'G3_x'}]
+    rmap = [('S1_R1', 5), ('S1_R2', 12), ('S1_R3', 3), ('S2_R1', 10),
+            ('S2_R2', 8), ('S2_R4', 7), ('S3_R2', 15), ('S3_R3', 1),
+            ('S3_R4', 5)]
+    exp = {'S1': [('R1', 5), ('R2', 12), ('R3', 3)],
+           'S2': [('R1', 10), ('R2', 8), ('R4', 7)],
+           'S3': [('R2', 15), ('R3', 1), ('R4', 5)]}
+    obs = demultiplex(*zip(*rmap))
+    assert list(obs) == ['S1', 'S2', 'S3']
+    for s in obs:
+        assert list(map(tuple, obs[s])) == list(zip(*exp[s]))
+    obs = demultiplex(*zip(*rmap), sep='.')
+    assert obs.keys() == {''}
+    assert list(map(tuple, obs[''])) == list(zip(*rmap))
+    obs = demultiplex(*zip(*rmap), samples=['S1', 'S2', 'SX'])
+    assert obs.keys() == {'S1', 'S2'}
+    assert list(map(tuple, obs['S2'])) == list(zip(*exp['S2']))
+    fp = tmp_path / 'S1.txt'
+    fp.write_text('R1\tEsch\nR2\tEsch\tx\nR3\tShig\n')
+    assert read_strata(str(fp)) == {'R1': 'Esch', 'R3': 'Shig'}
+    bad = tmp_path / 'tree.nwk'
+    bad.write_text('(a,b);\n')
+    with pytest.raises(ValueError, match='No stratification information is '
+                                         'found in file: tree.nwk.'):
+        read_strata(str(bad))

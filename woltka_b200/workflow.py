@@ -39,8 +39,8 @@ from .ordinal import (load_gene_coords, load_gene_coords_cached,
 from .session import Session, _split_sample
 from .coverage import range_mapper, Coverage, coverage_offsets
 
-__all__ = ['classify', 'build_mapper', 'assign_readmap', 'readzip',
-           'range_mapper']
+__all__ = ['classify', 'build_mapper', 'assign_readmap', 'demultiplex',
+           'strip_suffix', 'read_strata', 'readzip', 'range_mapper']
 
 _OPENERS = {'.gz': gzip.open, '.bz2': bz2.open, '.xz': lzma.open,
             '.lzma': lzma.open}
@@ -315,3 +315,36 @@ def assign_readmap(qryque, subque, data, rank, sample, assigners, cache=1024,
     total = data[rank].setdefault(sample, {})
     for key, value in counts.items():
         total[key] = total.get(key, 0) + value
+
+
+# The three host-side helpers of the chunk loop under their reference names
+# (the GPU path does the same work inside Session.add_chunk while it interns
+# the strings; these are for callers and tests that use them directly).
+
+def strip_suffix(subque, sep):
+    """Subject sets with everything from the last `sep` on removed
+    (workflow.py:818-841); trimmed names that coincide fall together."""
+    return ({name.rsplit(sep, 1)[0] for name in subjects}
+            for subjects in subque)
+
+
+def demultiplex(qryque, subque, samples=None, sep='_'):
+    """{sample: (reads, subjects)} of a multiplexed chunk (workflow.py:844-909):
+    the sample is the text before the first `sep` when something follows it,
+    else ''; with `samples` only those are kept.  Samples and reads keep the
+    order of the chunk."""
+    keep = None if samples is None else set(samples)
+    res = {}
+    for query, subjects in zip(qryque, subque):
+        left, _, right = query.partition(sep)
+        sample, read = (left, right) if right else ('', right or left)
+        if keep is None or sample in keep:
+            reads, subs = res.setdefault(sample, ([], []))
+            reads.append(read)
+            subs.append(subjects)
+    return res
+
+
+def read_strata(fp, zippers=None):
+    """Read-to-stratum map of one sample (workflow.py:912-938)."""
+    return _read_strata(fp, zippers)
