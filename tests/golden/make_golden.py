@@ -443,10 +443,36 @@ def synthetic():
                       '40-hit queries')
 
 
+def synthetic_ordinal():
+    """cfg3 at test size through the generator the bench uses (gen_genes,
+    gen_reads): reverse-strand genes, multi-hit reads, gapped CIGARs — pins
+    the generator's (beg, end, len) columns to what the reference derives
+    from the SAM lines."""
+    if ONLY is not None and 'synth_ordinal' not in ONLY and \
+            'synth_ordinal_ov55' not in ONLY:
+        return
+    d = join(OUT, 'synth_ordinal')
+    os.makedirs(d, exist_ok=True)
+    coff, gb, ge = synth.gen_genes(12, 150, 200_000, seed=31)
+    synth.write_coords(join(OUT, 'synth_coords.txt'), coff, gb, ge)
+    for si in range(2):
+        q, c, b, e, ln, _ = synth.gen_reads(4000, 12, 200_000, seed=40 + si)
+        assert set((e - b).tolist()) == {150}
+        synth.reads_as_sam(join(d, f'S{si}.sam'), q.numpy(), c.numpy(),
+                           b.numpy(), ln.numpy())
+    run_case('synth_ordinal', 'synth_ordinal', ranks=None,
+             coords_rel='synth_coords.txt', maps=True,
+             note='cfg3-shaped synthetic reads and genes, overlap 80, maps')
+    run_case('synth_ordinal_ov55', 'synth_ordinal', ranks=None,
+             coords_rel='synth_coords.txt', overlap=55,
+             note='same, overlap 55')
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 2 and sys.argv[1] == '--only':
         ONLY = set(sys.argv[2].split(','))
         bundled()
+        synthetic_ordinal()
         with open(join(HERE, 'INDEX.json')) as f:
             old = json.load(f)
         with open(join(HERE, 'INDEX.json'), 'w') as f:
@@ -458,6 +484,7 @@ if __name__ == '__main__':
     os.makedirs(OUT)
     bundled()
     synthetic()
+    synthetic_ordinal()
     with open(join(HERE, 'INDEX.json'), 'w') as f:
         json.dump(CASES, f)
     shutil.rmtree(stub)

@@ -123,3 +123,24 @@ def test_plain_mapper_chunks():
             [n] * (7 // n) + ([7 % n] if 7 % n else [])
         assert sum((q for q, _ in chunks), []) == [f'R{i}' for i in range(7)]
     assert plain_mapper.__name__ == 'plain_mapper'
+
+
+def test_generator_columns_equal_what_the_readers_derive_from_its_sam_lines():
+    """The cfg3 bench feeds gen_reads' integer columns; the golden case
+    `synth_ordinal` is the same reads as SAM text through the real reference.
+    The two meet here: the readers turn the SAM lines back into exactly the
+    generator's (contig, beg, end, aligned length) columns."""
+    from os.path import join, dirname, abspath
+    import numpy as np
+    from woltka_b200 import synth
+    from woltka_b200.ordinal import iter_records
+    data = join(dirname(abspath(__file__)), 'golden', 'data', 'synth_ordinal')
+    for si in range(2):
+        q, c, b, e, ln, _ = synth.gen_reads(4000, 12, 200_000, seed=40 + si)
+        with open(join(data, f'S{si}.sam')) as fh:
+            qn, cn, bg, en, le = next(iter_records(iter(fh), 'sam'))
+        assert qn == [f'R{x}' for x in q.tolist()]
+        assert cn == [f'C{x}' for x in c.tolist()]
+        assert np.array_equal(bg, b.numpy()) and np.array_equal(en, e.numpy())
+        assert np.array_equal(le, ln.numpy())
+        assert set(le) == {148, 150}

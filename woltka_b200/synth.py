@@ -176,3 +176,30 @@ def write_sam(fp, qnames, subjects, pos=None, cigar=None, flags=None):
             c_ = '150M' if cigar is None else cigar[i]
             fl = 0 if flags is None else flags[i]
             f.write(f'{qn}\t{fl}\t{sn}\t{p_}\t42\t{c_}\t*\t0\t0\t*\t*\n')
+
+
+def write_coords(fp, contig_off, gbeg, gend, contig_name='C%d',
+                 gene_name='g%d', flip_every=2):
+    """The gene table of gen_genes as a coordinates file the reference's
+    load_gene_coords reads (ordinal.py:338-430): `>contig` then
+    `gene<TAB>beg<TAB>end`, 1-based inclusive, every `flip_every`-th gene
+    written end first (a gene on the reverse strand)."""
+    with open(fp, 'w') as f:
+        for c in range(len(contig_off) - 1):
+            f.write('>' + contig_name % c + '\n')
+            for g in range(int(contig_off[c]), int(contig_off[c + 1])):
+                lo, hi = int(gbeg[g]) + 1, int(gend[g])
+                if flip_every and g % flip_every == 1:
+                    lo, hi = hi, lo
+                f.write(f'{gene_name % (g - int(contig_off[c]))}\t{lo}\t{hi}\n')
+
+
+def reads_as_sam(fp, qidx, contig, beg, length, contig_name='C%d',
+                 query_name='R%d'):
+    """The reads of gen_reads as SAM lines: POS = beg + 1, CIGAR 150M, or
+    70M2D78M2S for the gapped ones (aligned length 148, span 150)."""
+    write_sam(fp, [query_name % q for q in np.asarray(qidx).tolist()],
+              [contig_name % c for c in np.asarray(contig).tolist()],
+              pos=(np.asarray(beg) + 1).tolist(),
+              cigar=['150M' if ln == 150 else '70M2D78M2S'
+                     for ln in np.asarray(length).tolist()])
