@@ -90,6 +90,13 @@ int64_t wk_launch_count(wk_ctx *ctx);
  * run-per-lane kernel (block == 1 forces the window kernel); count sink
  * (0 = automatic, > 0 = hashed cache with that many slots, -1 = global). */
 int wk_set_tuning(wk_ctx *ctx, int grid, int block, int cache_slots);
+/* Named knobs for tests and measurements (nothing in the library reads the
+ * process environment); value 0 restores the default.  "no_seg" / "no_fast":
+ * skip the lane-per-record / the run-per-lane kernel; "sweep_r": longest run
+ * of the run-per-lane kernel; "seg_wt": tile of the lane-per-record kernel
+ * (256); "cls_sub" / "ord_sub": records per H2D sub-chunk of the host-fed
+ * calls; "ord_nowin": no persisting L2 window over the gene table. */
+int wk_set_option(wk_ctx *ctx, const char *name, int64_t value);
 /* Name of the classify kernel the last chunk was launched with. */
 const char *wk_last_kernel(wk_ctx *ctx);
 
@@ -241,6 +248,23 @@ int wk_classify_parsed(wk_ctx *ctx, const int32_t *sample_map, int32_t n_map,
 /* Device address / length (in int64 elements) of the units table, for a
  * caller-side NCCL reduce (torch.distributed) across GPUs. */
 int wk_counts_device(wk_ctx *ctx, void **d_ptr, int64_t *n_elems);
+
+/* ---- merging contexts (one per GPU): the device form of `woltka merge`
+ *      (tools.merge_wf, tools.py:153-208; doc/perform.md:70-98) -----------
+ * All contexts must share the plan and the index spaces.  The units table is
+ * summed by the caller's collective on wk_counts_device; the two sparse parts
+ * travel as device arrays (e.g. through an NCCL all-gather) and are added
+ * into the receiving context:
+ *   strata cells   (key, units) pairs, uint64 each, keys as packed by the
+ *                  kernels (independent of the table dimensions);
+ *   overflow list  (key int64, den int32) pairs.
+ * Exported pointers stay valid until the next call on the context. */
+int wk_strata_export_device(wk_ctx *ctx, void **d_keys, void **d_units, int64_t *n);
+int wk_strata_import_device(wk_ctx *ctx, const void *d_keys, const void *d_units,
+                            int64_t n);
+int wk_overflow_export_device(wk_ctx *ctx, void **d_keys, void **d_den, int64_t *n);
+int wk_overflow_import_device(wk_ctx *ctx, const void *d_keys, const void *d_den,
+                              int64_t n, int stratified);
 
 /* ---- subject coverage (--outcov) ----------------------------------------------
  * Replaces range.parse_ranges / merge_ranges / calc_coverage

@@ -21,17 +21,15 @@ def big_case():
     return cases.Case(synth.Taxonomy(seed=42))
 
 
-def _lean_kernel(entries, mode, seg_above=False):
+def _lean_kernel(entries, mode):
     """The kernel a plan of one kind takes (ranks only, or `none` only, staged
     tables, no strata, no read map): default or --uniq -> classify_seg_kernel,
-    one launch per entry; --major and --above -> classify_fast_kernel (--above
-    -> classify_seg_kernel with WK_SEG_ABOVE).  assign_none knows no --major /
-    --above."""
+    one launch per entry; --major and --above -> classify_fast_kernel.
+    assign_none knows no --major / --above."""
     none = all(x == 'none' for x in entries)
     if not none and any(x in ('none', 'free') for x in entries):
         return 'classify_kernel'
-    if none or mode.startswith(('default', 'uniq')) or \
-            (seg_above and mode.startswith('above')):
+    if none or mode.startswith(('default', 'uniq')):
         return 'classify_seg_kernel'
     return 'classify_fast_kernel'
 
@@ -259,22 +257,20 @@ def test_lca_on_a_tree_that_is_not_level_ordered(engine):
     assert np.array_equal(got, exp)
 
 
-@pytest.mark.parametrize('noseg', ['', '1', 'above'])
+@pytest.mark.parametrize('noseg', ['', '1'])
 @pytest.mark.parametrize('mode', ['default', 'above', 'major+unassigned',
                                   'uniq+unassigned'])
 @pytest.mark.parametrize('entries', [['genus'], ['phylum', 'genus', 'species'],
                                      ['none']])
 def test_contiguous_samples_take_the_run_per_lane_kernel(engine, small_case,
                                                          entries, mode,
-                                                         monkeypatch, noseg):
+                                                         knobs, noseg):
     """Samples that follow one another in the stream (one file per sample):
     the lane-per-record and the run-per-lane kernel work segment by segment;
     a dropped sample (-1) in the middle and long queries are part of the
     stream."""
-    if noseg == 'above':   # the lane-per-record kernel's --above variant
-        monkeypatch.setenv('WK_SEG_ABOVE', '1')
-    elif noseg:
-        monkeypatch.setenv('WK_NO_SEG', noseg)
+    if noseg:
+        knobs.set('no_seg', 1)
     q, s = cases.random_hits(small_case, 60000, seed=77, long_every=5000,
                              long_len=90)
     nq = int(q.max()) + 1
@@ -290,7 +286,7 @@ def test_contiguous_samples_take_the_run_per_lane_kernel(engine, small_case,
               ref)
     assert engine.last_kernel() == (
         'classify_fast_kernel' if noseg == '1' else
-        _lean_kernel(entries, mode, noseg == 'above'))
+        _lean_kernel(entries, mode))
 
 
 def test_which_kernel_runs(engine, small_case):
@@ -324,11 +320,11 @@ def test_which_kernel_runs(engine, small_case):
 
 
 @pytest.mark.parametrize('noseg', ['', '1'])
-def test_run_per_lane_kernel_at_1e6(engine, big_case, monkeypatch, noseg):
+def test_run_per_lane_kernel_at_1e6(engine, big_case, knobs, noseg):
     # one-entry plans on the 21,603-node taxonomy, every mode, both kinds;
     # with and without the lane-per-record kernel of the default / --uniq mode
     if noseg:
-        monkeypatch.setenv('WK_NO_SEG', noseg)
+        knobs.set('no_seg', 1)
     qi, si, _, nq = synth.gen_hits(1_000_000, seed=1002)
     q, s = qi.numpy(), si.numpy()
     for ent in (['genus'], ['species'], ['none']):
@@ -389,11 +385,11 @@ def test_cfg5_shape_gene_to_ko_stratified_by_genus(engine):
 
 @pytest.mark.parametrize('r', ['5', '9'])
 @pytest.mark.parametrize('block', [0, 768, 512])
-def test_short_runs_and_fewer_warps(engine, small_case, monkeypatch, r, block):
+def test_short_runs_and_fewer_warps(engine, small_case, knobs, r, block):
     """The run-per-lane kernel at every run length it is built for (13 is the
     default) and with fewer warps per CTA, as chosen for large tables."""
-    monkeypatch.setenv('WK_SWEEP_R', r)
-    monkeypatch.setenv('WK_NO_SEG', '1')
+    knobs.set('sweep_r', int(r))
+    knobs.set('no_seg', 1)
     q, s = cases.random_hits(small_case, 30000, seed=int(r), long_every=3000,
                              long_len=60)
     engine.set_tuning(0, block, 0)
@@ -409,17 +405,15 @@ def test_short_runs_and_fewer_warps(engine, small_case, monkeypatch, r, block):
         engine.set_tuning(0, 0, 0)
 
 
-@pytest.mark.parametrize('noseg', ['', '1', 'above'])
-def test_randomised_shapes_both_kernels_agree(engine, small_case, monkeypatch,
+@pytest.mark.parametrize('noseg', ['', '1'])
+def test_randomised_shapes_both_kernels_agree(engine, small_case, knobs,
                                               noseg):
     """Many small random streams whose sizes straddle the warp-tile and run
     boundaries (32 x 13 = 416 records, runs of 13; tiles of 512), with long
     queries and repeats placed at random: lane-per-record kernel ==
     run-per-lane kernel == window kernel == oracle."""
-    if noseg == 'above':
-        monkeypatch.setenv('WK_SEG_ABOVE', '1')
-    elif noseg:
-        monkeypatch.setenv('WK_NO_SEG', noseg)
+    if noseg:
+        knobs.set('no_seg', 1)
     rng = np.random.default_rng(2026)
     ents = (['genus'], ['none'], ['phylum', 'species'])
     modes = ('default', 'uniq', 'major', 'above', 'major+unassigned')
@@ -439,7 +433,7 @@ def test_randomised_shapes_both_kernels_agree(engine, small_case, monkeypatch,
         got = cases.run_engine(engine, small_case, ent, fl, th, q, s)
         assert engine.last_kernel() == (
             'classify_fast_kernel' if noseg == '1' else
-            _lean_kernel(ent, mode, noseg == 'above'))
+            _lean_kernel(ent, mode))
         _same(got, exp)
         engine.set_tuning(0, 1, 0)
         try:
@@ -451,13 +445,13 @@ def test_randomised_shapes_both_kernels_agree(engine, small_case, monkeypatch,
 @pytest.mark.parametrize('NF', [5000, 3_000_000])
 @pytest.mark.parametrize('mode', ['default', 'uniq+unassigned'])
 @pytest.mark.parametrize('noseg', ['', '1'])
-def test_rank_none_without_a_table(engine, mode, NF, monkeypatch, noseg):
+def test_rank_none_without_a_table(engine, mode, NF, knobs, noseg):
     """feature == subject (KIND_NONE_ID: an OGU table, or genes of the ordinal
     path): the lane-per-record kernel, or the run-per-lane kernel with 24-bit
     codes; counts in the private table when it fits (NF = 5000) and straight
     to global memory when it does not (NF = 3e6)."""
     if noseg:
-        monkeypatch.setenv('WK_NO_SEG', noseg)
+        knobs.set('no_seg', 1)
     from oracle import oracle as O
     from woltka_b200._lib import KIND_NONE_ID
     rng = np.random.default_rng(NF)
@@ -482,15 +476,15 @@ def test_rank_none_without_a_table(engine, mode, NF, monkeypatch, noseg):
 
 @pytest.mark.parametrize('sub', ['36', '516', '4000'])
 @pytest.mark.parametrize('noseg', ['', '1'])
-def test_host_chunk_in_sub_chunks(engine, small_case, monkeypatch, sub, noseg):
+def test_host_chunk_in_sub_chunks(engine, small_case, knobs, sub, noseg):
     """wk_classify_chunk launches one kernel per sub-chunk of the host columns
     (records [r0, r1), not cut at query boundaries: a query belongs to the
     launch that holds its first record).  Small sub-chunks put those cuts, the
     512-record warp tiles and the 32-record windows in every relative
     position, with queries longer than a window and longer than a sub-chunk."""
-    monkeypatch.setenv('WK_CLS_SUB', sub)
+    knobs.set('cls_sub', int(sub))
     if noseg:
-        monkeypatch.setenv('WK_NO_SEG', noseg)
+        knobs.set('no_seg', 1)
     q, s = cases.random_hits(small_case, 2500, seed=int(sub), kmax=31, p=0.3,
                              long_every=211, long_len=70, window=6)
     for ent, mode in ((['genus'], 'default'), (['genus'], 'uniq+unassigned'),

@@ -113,7 +113,7 @@ def test_edges():
         _check(coff, gb, ge, cc, 0.8)
 
 
-def test_ordinal_then_classify(engine):
+def test_ordinal_then_classify(engine, ord_sub=0):
     """match + classify fused on the device == oracle sweep + oracle classify
     over the (query, gene) pairs."""
     coff, gb, ge = synth.gen_genes(20, 300, 300_000, seed=21)
@@ -123,6 +123,7 @@ def test_ordinal_then_classify(engine):
     from woltka_b200._lib import KIND_NONE_ID
     eng = Engine(0)
     try:
+        eng.set_option('ord_sub', ord_sub)
         eng.set_plan(np.array([KIND_NONE_ID]), 0, 0.0, 2, G)
         eng.set_subjects(None, None, G)
         eng.ordinal_set_genes(coff, gb, ge, np.arange(G, dtype=np.int32))
@@ -140,7 +141,7 @@ def test_ordinal_then_classify(engine):
     assert np.array_equal(units, exp)
 
 
-def test_queries_straddling_tiles(engine):
+def test_queries_straddling_tiles(engine, ord_sub=0):
     """A CTA owns the queries whose first record lies in its tile and follows
     the last one past the tile end — including queries longer than a tile."""
     coff, gb, ge = synth.gen_genes(6, 400, 200_000, seed=31)
@@ -156,6 +157,7 @@ def test_queries_straddling_tiles(engine):
         ln = rng.integers(20, 200, n).astype(np.int32)
         eng = Engine(0)
         try:
+            eng.set_option('ord_sub', ord_sub)
             eng.set_plan(np.array([KIND_NONE_ID]), 0, 0.0, 1, G)
             eng.set_subjects(None, None, G)
             eng.ordinal_set_genes(coff, gb, ge, np.arange(G, dtype=np.int32))
@@ -175,12 +177,11 @@ def test_queries_straddling_tiles(engine):
 
 
 @pytest.mark.parametrize('sub', ['1000', '2048', '6004'])
-def test_host_chunk_is_matched_sub_chunk_by_sub_chunk(engine, monkeypatch, sub):
+def test_host_chunk_is_matched_sub_chunk_by_sub_chunk(engine, sub):
     """wk_ordinal_chunk copies the columns in sub-chunks and runs the matcher
     behind the copies; a query that runs over a sub-chunk border stays whole."""
-    monkeypatch.setenv('WK_ORD_SUB', sub)
-    test_queries_straddling_tiles(engine)
-    test_ordinal_then_classify(engine)
+    test_queries_straddling_tiles(engine, int(sub))
+    test_ordinal_then_classify(engine, int(sub))
 
 
 def test_read_maps_with_coords_on_multi_hit_queries(tmp_path):

@@ -31,6 +31,7 @@ SIGNATURES = {
     'wk_sync': (C.c_int, [_vp]),
     'wk_launch_count': (C.c_int64, [_vp]),
     'wk_set_tuning': (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
+    'wk_set_option': (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     'wk_last_kernel': (C.c_char_p, [_vp]),
     'wk_host_alloc': (C.c_int, [C.POINTER(_vp), C.c_int64]),
     'wk_host_free': (C.c_int, [_vp]),
@@ -57,6 +58,10 @@ SIGNATURES = {
     'wk_fetch_strata': (C.c_int, [_vp, _i64p, _vp, _vp, _vp, _vp, _vp,
                                   C.c_int64]),
     'wk_reset_counts': (C.c_int, [_vp]),
+    'wk_strata_export_device': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), _i64p]),
+    'wk_strata_import_device': (C.c_int, [_vp, _vp, _vp, C.c_int64]),
+    'wk_overflow_export_device': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), _i64p]),
+    'wk_overflow_import_device': (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int]),
     'wk_set_assign_output': (C.c_int, [_vp, C.c_int]),
     'wk_fetch_assignments': (C.c_int, [_vp, _vp, C.c_int64]),
     'wk_counts_device': (C.c_int, [_vp, C.POINTER(_vp), _i64p]),

@@ -115,6 +115,13 @@ __global__ void compact_hash_kernel(const ull *k, const ull *v, uint64_t cap,
     }
 }
 
+// add n (key, units) cells into the strata hash (merge of another rank's table)
+__global__ void import_cells_kernel(const ull *k, const ull *v, int64_t n, ClsParams P) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t st = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) strat_add(P, k[i], v[i]);
+}
+
 // copy [E][oS][oNF1] into [E][nS][nNF1]; the Unassigned column moves last
 __global__ void regrid_kernel(const ull *o, ull *nw, int E, int oS, int64_t oNF1,
                               int nS, int64_t nNF1) {
@@ -144,6 +151,9 @@ struct wk_ctx {
   cudaEvent_t ev_free = nullptr;
   int64_t launches = 0;
   int tune_grid = 0, tune_cache = 0, tune_block = 0;
+  // wk_set_option knobs (tests and measurements; 0 = default behaviour)
+  int opt_no_seg = 0, opt_no_fast = 0, opt_sweep_r = 0, opt_seg_wt = 0, opt_ord_nowin = 0;
+  int64_t opt_cls_sub = 0, opt_ord_sub = 0;
   const char *last_kernel = "";
   // tree
   DevBuf parent;
@@ -172,6 +182,7 @@ struct wk_ctx {
   DevBuf cov_keys, cov_ends;  // coverage store (wk_cover.cuh)
   int64_t cov_n = 0, cov_cap = 0;
   DevBuf longlist;  // classify_seg_kernel: [0] = count, then first records of long queries
+  DevBuf exp_k, exp_v;  // wk_strata_export_device: compacted (key, units)
   DevBuf ovf_key, ovf_den, small;  // small: [0]=ovf_n [1]=sh_used [2]=n_pairs [3]=cursor, err after
   int64_t ovf_cap = 0;
   // strata hash
@@ -274,8 +285,6 @@ int wk_create(int device, wk_ctx **out) {
   TRY(c->small.reserve(64));
   CK(cudaMemset(c->small.p, 0, 64));
   c->ovf_cap = 1 << 20;
-  if (const char *ev = getenv("WK_TUNE_BLOCK")) c->tune_block = atoi(ev);
-  if (const char *ev = getenv("WK_TUNE_GRID")) c->tune_grid = atoi(ev);
   TRY(c->ovf_key.reserve(c->ovf_cap * 8));
   TRY(c->ovf_den.reserve(c->ovf_cap * 4));
   {
@@ -347,7 +356,7 @@ int wk_create(int device, wk_ctx **out) {
       (const void *)classify_seg_kernel<KD, MD, 256, false>,         \
       (const void *)classify_seg_kernel<KD, MD, 256, true>
     const void *seg[] = {WK_SEGV(WK_KIND_RANK, FX_FRAC), WK_SEGV(WK_KIND_RANK, FX_UNIQ),
-                         WK_SEGV(WK_KIND_RANK, FX_ABOVE), WK_SEGV(WK_KIND_NONE, FX_FRAC),
+                         WK_SEGV(WK_KIND_NONE, FX_FRAC),
                          WK_SEGV(WK_KIND_NONE, FX_UNIQ), WK_SEGV(WK_KIND_NONE_ID, FX_FRAC),
                          WK_SEGV(WK_KIND_NONE_ID, FX_UNIQ)};
 #undef WK_SEGV
@@ -370,7 +379,7 @@ int wk_destroy(wk_ctx *c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   DevBuf *bufs[] = {&c->parent, &c->cnt, &c->tab, &c->tab16, &c->sub_node,
-                    &c->ovf_key, &c->ovf_den, &c->small, &c->longlist, &c->cov_keys, &c->cov_ends, &c->sh_keys,
+                    &c->ovf_key, &c->ovf_den, &c->small, &c->exp_k, &c->exp_v, &c->longlist, &c->cov_keys, &c->cov_ends, &c->sh_keys,
                     &c->sh_vals, &c->dq, &c->ds, &c->dqsamp, &c->dqstrat,
                     &c->scratch, &c->dcontig, &c->dbeg, &c->dend, &c->dlen,
                     &c->cinfo, &c->genes, &c->pair_q, &c->pair_s, &c->pair_r,
@@ -414,6 +423,20 @@ int wk_set_tuning(wk_ctx *c, int grid, int block, int cache_slots) {
   c->tune_block = block;  // 1 = window kernel (classify_kernel) instead of sweep
   c->tune_grid = grid;
   c->tune_cache = cache_slots;
+  return WK_OK;
+}
+
+int wk_set_option(wk_ctx *c, const char *name, int64_t value) {
+  if (!c || !name) return fail(WK_ERR_ARG, "bad arguments");
+  const std::string k(name);
+  if (k == "no_seg") c->opt_no_seg = (int)value;
+  else if (k == "no_fast") c->opt_no_fast = (int)value;
+  else if (k == "sweep_r") c->opt_sweep_r = (int)value;
+  else if (k == "seg_wt") c->opt_seg_wt = (int)value;
+  else if (k == "ord_nowin") c->opt_ord_nowin = (int)value;
+  else if (k == "cls_sub") c->opt_cls_sub = value;
+  else if (k == "ord_sub") c->opt_ord_sub = value;
+  else return fail(WK_ERR_ARG, "unknown option '%s'", name);
   return WK_OK;
 }
 
@@ -887,13 +910,13 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   const bool wide = c->kind[0] == WK_KIND_NONE_ID;  // feature == subject, no table
   if (c->tune_block != 1 && same_kind && (wide ? P.V < 0xFFFFFD : staged) &&
       !dqstrat && !sizes && c->tune_cache == 0 && !(n_dev && dqsamp) && !P.assign &&
-      !getenv("WK_NO_FAST") &&
+      !c->opt_no_fast &&
       (n_dev ? n_bound : r1 - r0) < (1ll << 31) - (1 << 20)) {  // 32-bit tile counters
     int NTmax = c->tune_block;
     if (NTmax < 64 || NTmax > SW_NT) NTmax = SW_NT;
     NTmax &= ~31;
     int rmax = 13;
-    if (const char *ev = getenv("WK_SWEEP_R")) rmax = atoi(ev);
+    if (c->opt_sweep_r > 0) rmax = c->opt_sweep_r;
     const bool rk = c->kind[0] == WK_KIND_RANK;
     const int mode = (rk && (c->flags & WK_F_MAJOR))   ? FX_MAJOR
                      : (rk && (c->flags & WK_F_ABOVE)) ? FX_ABOVE
@@ -938,24 +961,20 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
     const int64_t span = n_dev ? n_bound : r1 - (r0 & ~3ll);
     if (span <= 0) return WK_OK;
     // default or --uniq: the lane-per-record kernel with warp-private tiles
-    // (wk_seg.cuh), one launch per entry.  Its --above variant (log-step LCA
-    // fold over the lanes of a query) is correct but measured slower than the
-    // run-per-lane kernel wherever LCAs are common (genus 1.71 vs 1.39 ms,
-    // species 2.09 vs 1.58; phylum 0.39 vs 0.69): opt-in with WK_SEG_ABOVE.
+    // (wk_seg.cuh), one launch per entry; its staged row keeps two codes for
+    // itself (SG_BAD16 and the 'Unassigned' slot)
     bool seg_done = false;
-    if (NTmax == SW_NT && !getenv("WK_NO_SEG") &&
-        (mode == FX_FRAC || mode == FX_UNIQ ||
-         (mode == FX_ABOVE && par_ok && getenv("WK_SEG_ABOVE")))) {
+    if (NTmax == SW_NT && !c->opt_no_seg && (mode == FX_FRAC || mode == FX_UNIQ) &&
+        (wide || c->stage_vmax < (int32_t)SG_BAD16 - 2)) {
       int WTe[WK_MAX_ENTRIES];
       bool fits = true;
-      const char *wt_env = getenv("WK_SEG_WT");
       for (int e = 0; e < c->E && fits; ++e) {
         const uint32_t ce = gsink ? 0u : (uint32_t)(P.dir_base[e + 1] - P.dir_base[e]);
         WTe[e] = 0;
         for (int wt : {512, 256})
-          if (!WTe[e] && !(wt == 512 && wt_env && atoi(wt_env) == 256) &&
-              sg_layout(SG_NT / 32, wt, ce, (wide ? 0 : (int64_t)c->Vp * 2) + par_bytes)
-                      .total <= c->smem_optin)
+          if (!WTe[e] && !(wt == 512 && c->opt_seg_wt == 256) &&
+              sg_layout(SG_NT / 32, wt, ce, wide ? 0 : (int64_t)c->Vp * 2).total <=
+                  c->smem_optin)
             WTe[e] = wt;
         fits = WTe[e] != 0;
       }
@@ -984,7 +1003,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
           const int WT = WTe[e];
           const SgSmemLayout GL = sg_layout(
               SG_NT / 32, WT, gsink ? 0u : (uint32_t)(P.dir_base[e + 1] - P.dir_base[e]),
-              (wide ? 0 : (int64_t)c->Vp * 2) + par_bytes);
+              wide ? 0 : (int64_t)c->Vp * 2);
           const int64_t ft = (span + WT - 1) / WT;
           const int sgrid =
               (int)std::min<int64_t>(grid, (ft + SG_NT / 32 - 1) / (SG_NT / 32));
@@ -1003,7 +1022,6 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   } while (0)
           if (rk) {
             if (mode == FX_UNIQ) WK_SEG2(WK_KIND_RANK, FX_UNIQ);
-            else if (mode == FX_ABOVE) WK_SEG2(WK_KIND_RANK, FX_ABOVE);
             else WK_SEG2(WK_KIND_RANK, FX_FRAC);
           } else if (wide) {
             if (mode == FX_UNIQ) WK_SEG2(WK_KIND_NONE_ID, FX_UNIQ);
@@ -1243,7 +1261,7 @@ int wk_classify_chunk(wk_ctx *c, const int32_t *qidx, const int32_t *sidx,
   // sub-chunk j+1 resident (a query may straddle the boundary), so it waits
   // on copy j+1 while copy j+2 is already in flight.
   int64_t SUB = 8ll << 20;
-  if (const char *ev = getenv("WK_CLS_SUB")) SUB = std::max<int64_t>(4, atoll(ev) & ~3ll);
+  if (c->opt_cls_sub > 0) SUB = std::max<int64_t>(4, c->opt_cls_sub & ~3ll);
   const int64_t nsub = (n_rec + SUB - 1) / SUB;
   CK(cudaEventRecord(c->ev_free, c->stream));
   CK(cudaStreamWaitEvent(c->copy_stream, c->ev_free, 0));
@@ -1427,7 +1445,7 @@ static int run_ordinal(wk_ctx *c, const int32_t *dq, const int32_t *dcontig,
       cfg.stream = c->stream;
       cudaLaunchAttribute attr[1];
       int nattr = 0;
-      if (c->l2_window_max && c->hot_bytes && !getenv("WK_ORD_NOWIN")) {
+      if (c->l2_window_max && c->hot_bytes && !c->opt_ord_nowin) {
         attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
         attr[0].val.accessPolicyWindow.base_ptr = c->genes.p;
         attr[0].val.accessPolicyWindow.num_bytes =
@@ -1509,7 +1527,7 @@ int wk_ordinal_chunk(wk_ctx *c, const int32_t *qidx, const int32_t *contig,
   // H2D in sub-chunks on the copy stream, the matcher follows one sub-chunk
   // behind (wk_classify_chunk does the same for the plain path)
   int64_t SUB = 8ll << 20;
-  if (const char *ev = getenv("WK_ORD_SUB")) SUB = std::max<int64_t>(4, atoll(ev) & ~3ll);
+  if (c->opt_ord_sub > 0) SUB = std::max<int64_t>(4, c->opt_ord_sub & ~3ll);
   const int64_t nsub = (n_rec + SUB - 1) / SUB;
   CK(cudaEventRecord(c->ev_free, c->stream));
   CK(cudaStreamWaitEvent(c->copy_stream, c->ev_free, 0));
@@ -2117,6 +2135,87 @@ int wk_classify_parsed(wk_ctx *c, const int32_t *sample_map, int32_t n_map,
   TRY(launch_classify(c, c->dq.as<int32_t>(), c->ds.as<int32_t>(), N, nullptr, N, 0, N,
                       nullptr, nullptr, sample));
   return check_device_err(c);
+}
+
+// ---- merging the results of several contexts (one per GPU) ------------------------
+int wk_strata_export_device(wk_ctx *c, void **d_keys, void **d_units, int64_t *n) {
+  if (!c || !d_keys || !d_units || !n) return fail(WK_ERR_ARG, "bad arguments");
+  if (!c->have_plan) return fail(WK_ERR_STATE, "no plan set");
+  TRY(use_device(c));
+  ull used = 0;
+  if (c->sh_cap) {
+    CK(cudaMemcpyAsync(&used, c->d_sh_used(), 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  *n = (int64_t)used;
+  TRY(c->exp_k.reserve(std::max<ull>(used, 1) * 8));
+  TRY(c->exp_v.reserve(std::max<ull>(used, 1) * 8));
+  *d_keys = c->exp_k.p;
+  *d_units = c->exp_v.p;
+  if (!used) return WK_OK;
+  CK(cudaMemsetAsync(c->d_cursor(), 0, 8, c->stream));
+  int grid = (int)std::min<uint64_t>((c->sh_cap + 255) / 256, (uint64_t)c->sm_count * 8);
+  compact_hash_kernel<<<grid, 256, 0, c->stream>>>(
+      c->sh_keys.as<ull>(), c->sh_keys.as<ull>() + 1, c->sh_cap, c->exp_k.as<ull>(),
+      c->exp_v.as<ull>(), c->d_cursor());
+  c->launches++;
+  CK(cudaGetLastError());
+  return WK_OK;
+}
+
+int wk_strata_import_device(wk_ctx *c, const void *d_keys, const void *d_units, int64_t n) {
+  if (!c || n < 0 || (n && (!d_keys || !d_units))) return fail(WK_ERR_ARG, "bad arguments");
+  if (!c->have_plan) return fail(WK_ERR_STATE, "no plan set");
+  TRY(use_device(c));
+  if (!n) return WK_OK;
+  TRY(ensure_strata(c, n));
+  ClsParams P;
+  memset(&P, 0, sizeof P);
+  P.sh_keys = c->sh_keys.as<ull>();
+  P.sh_vals = c->sh_keys.as<ull>() + 1;
+  P.sh_mask = c->sh_cap - 1;
+  P.sh_used = c->d_sh_used();
+  P.err = c->d_err();
+  int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->sm_count * 8);
+  import_cells_kernel<<<grid, 256, 0, c->stream>>>(static_cast<const ull *>(d_keys),
+                                                  static_cast<const ull *>(d_units), n, P);
+  c->launches++;
+  CK(cudaGetLastError());
+  c->strata_keys = true;
+  return check_device_err(c);
+}
+
+int wk_overflow_export_device(wk_ctx *c, void **d_keys, void **d_den, int64_t *n) {
+  if (!c || !d_keys || !d_den || !n) return fail(WK_ERR_ARG, "bad arguments");
+  TRY(use_device(c));
+  ull cnt = 0;
+  CK(cudaMemcpyAsync(&cnt, c->d_ovf_n(), 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *n = (int64_t)std::min<ull>(cnt, (ull)c->ovf_cap);
+  *d_keys = c->ovf_key.p;
+  *d_den = c->ovf_den.p;
+  return WK_OK;
+}
+
+int wk_overflow_import_device(wk_ctx *c, const void *d_keys, const void *d_den, int64_t n,
+                              int stratified) {
+  if (!c || n < 0 || (n && (!d_keys || !d_den))) return fail(WK_ERR_ARG, "bad arguments");
+  TRY(use_device(c));
+  if (!n) return WK_OK;
+  ull cnt = 0;
+  CK(cudaMemcpyAsync(&cnt, c->d_ovf_n(), 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if ((int64_t)cnt + n > c->ovf_cap)
+    return fail(WK_ERR_CAPACITY, "fraction overflow list is full");
+  CK(cudaMemcpyAsync(c->ovf_key.as<int64_t>() + cnt, d_keys, (size_t)n * 8,
+                     cudaMemcpyDeviceToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->ovf_den.as<int32_t>() + cnt, d_den, (size_t)n * 4,
+                     cudaMemcpyDeviceToDevice, c->stream));
+  cnt += (ull)n;
+  CK(cudaMemcpyAsync(c->d_ovf_n(), &cnt, 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (stratified) c->strata_keys = true;
+  return WK_OK;
 }
 
 int wk_counts_device(wk_ctx *c, void **d_ptr, int64_t *n_elems) {

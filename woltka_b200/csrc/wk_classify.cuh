@@ -792,7 +792,7 @@ __global__ void __launch_bounds__(CLS_NT, 1)
       }
       if (SINK == SINK_DIRECT && per_query && act && samp != K.cur &&
           (unsigned)samp < (unsigned)P.S)
-        sts32(prop_addr, (uint32_t)samp);  // ask for the table to follow
+        atoms_exch(prop_addr, (uint32_t)samp);  // ask for the table to follow
       int sv = act ? lds32(as + (uint32_t)x * 4u) : ~lane;
       if (act && (unsigned)sv >= (unsigned)V32) {
         atomicOr(P.err, ERR_BAD_SUBJECT);

@@ -3,45 +3,59 @@
 // table, or feature == subject — in default (1/k' split) or --uniq mode; one
 // launch per entry, one sample or a stream of contiguous samples.
 //
-// Same contract as the other two classify kernels (reference
+// Same contract as the other classify kernels (reference
 // workflow.py:316-335, :1017-1058, classify.py:32-51, :81-127, :144-171).
 //
-// Decomposition: one lane = one record, as in classify_kernel, but with the
-// plumbing of classify_fast_kernel: every warp owns tiles of WT records that
-// its lane 0 brings to the warp's slice of shared memory with TMA bulk copies
-// on the warp's own mbarrier (no CTA barrier in the steady state), the plan is
-// a template parameter (no flag tests, no entry loop), and the count sink is
-// the CTA's private range-compacted table (or, for feature spaces that do not
-// fit, straight 64-bit reductions).  A warp walks its tile in 32-record
+// Decomposition: one lane = one record.  Every warp owns tiles of WT records
+// that its lane 0 brings to the warp's slice of shared memory with TMA bulk
+// copies on the warp's own mbarrier (no CTA barrier in the steady state), the
+// plan is a template parameter (no flag tests, no entry loop), and the count
+// sink is the CTA's private range-compacted table (or, for feature spaces that
+// do not fit, straight 64-bit reductions).  A warp walks its tile in 32-record
 // windows that start at a query head and consume whole queries:
 //   * T = ballot(q[i] != q[i+1]) gives every lane its query [sl, se);
-//   * unanimity (all taxa equal, classify.py:107-108; one distinct subject,
-//     classify.py:46-47) is one shuffle from the head lane and one ballot;
-//     a window whose queries are all unanimous needs nothing else: each head
-//     lane adds one unit;
-//   * only the records of non-unanimous queries look back for an equal
-//     subject earlier in their query (set semantics of the subject pool,
-//     align.py:339), straight from the staged subject column; one ballot then
-//     counts the contributing subjects k' and every such lane adds 1/k'
-//     (classify.py:167-170);
+//   * a window whose queries are all unanimous (all taxa equal,
+//     classify.py:107-108; one distinct subject, classify.py:46-47) — one
+//     shuffle from the head lane and one ballot — needs nothing else: each
+//     head lane adds one unit;
+//   * otherwise (default mode) every record adds 1/k' for its subject unless
+//     an equal subject sits earlier in its query (set semantics of the subject
+//     pool, align.py:339) or the subject has no taxon; k' = the number of
+//     such records of the query (classify.py:165-170).  A unanimous query
+//     needs no special case there: k' shares of 1/k' are the one unit
+//     classify.py:107-108 asks for (exactly: units are integers, and shares
+//     whose denominator does not divide WK_UNITS are summed as rationals on
+//     the host);
+//   * the repeat test reads earlier records straight from the staged subject
+//     column, which every consumed record overwrites with a KEY = its subject
+//     | a 7-bit tag of its query's head position | bit 31: equal keys are
+//     equal subjects of the same query, so the look-back needs no bounds;
 //   * unit and share emissions are ONE shared-memory atomic per window.
 // Queries with no tail within 32 records of their head are listed and done by
 // seg_long_kernel (the warp-cooperative process_long) right after.
-// An --above variant (log-step LCA fold over the lanes of a query) exists but
-// is slower than the run-per-lane kernel's and is opt-in (WK_SEG_ABOVE).
 #pragma once
 #include "wk_sweep.cuh"
 
 namespace wk {
 
 constexpr int SG_NT = 1024;
-constexpr int SG_PRE = 4;    // records staged before the tile
+constexpr int SG_PRE = 4;    // records staged before the tile (>= SG_LB)
 constexpr int SG_POST = 44;  // halo after the tile (a window may start at WT-1)
+constexpr int SG_LB = 4;     // look-backs done unconditionally
+constexpr uint32_t SG_BAD16 = 0xFFFEu;  // staged code of an out-of-range subject
 
 __device__ __forceinline__ uint32_t lds16w(uint32_t a) {
   uint32_t v;
   asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
   return v;
+}
+__device__ __forceinline__ int bfind32(unsigned v) {  // highest set bit (FLO)
+  int r;
+  asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
 }
 
 struct SgSmemLayout {
@@ -74,8 +88,6 @@ __global__ void __launch_bounds__(SG_NT, 1)
   constexpr uint32_t SCOL = (uint32_t)TBUF * 4u;  // subject column after the query column
   // --rank none without a table: the subject is the feature (no staged row)
   constexpr bool WIDE = KIND == WK_KIND_NONE_ID;
-  constexpr uint32_t C_NONE = WIDE ? 0xFFFFFFFFu : FX_NONE;
-  constexpr bool ABOVE = KIND == WK_KIND_RANK && MODE == FX_ABOVE;
   const int tid = threadIdx.x, warp = tid >> 5;
   int lane = tid & 31;
   asm volatile("" : "+r"(lane));
@@ -84,13 +96,13 @@ __global__ void __launch_bounds__(SG_NT, 1)
   const bool gsink = P.fast_gsink != 0;  // counts straight to the global table
   const uint32_t cells = gsink ? 0u : (uint32_t)(P.dir_base[e + 1] - P.dir_base[e]);
   const uint32_t rows_bytes = WIDE ? 0u : (uint32_t)P.Vp * 2u;
-  // --above: the parent array as uint16 behind the row
-  const uint32_t par_bytes = ABOVE ? (((uint32_t)P.T + 7u) & ~7u) * 2u : 0u;
-  const SgSmemLayout L = sg_layout(NW, WT, cells, (int64_t)rows_bytes + par_bytes);
+  const SgSmemLayout L = sg_layout(NW, WT, cells, (int64_t)rows_bytes);
   const uint32_t sbase32 = smem_u32(smem);
   const uint32_t tabbar = sbase32 + L.bars + (uint32_t)NW * 8u;
   const uint32_t mybar = sbase32 + L.bars + (uint32_t)warp * 8u;
-  const uint32_t aq = sbase32 + L.warp0 + (uint32_t)warp * L.warp_bytes;
+  uint32_t aq = sbase32 + L.warp0 + (uint32_t)warp * L.warp_bytes;
+  // (a value ptxas cannot rematerialise inside the window loop)
+  asm volatile("shfl.sync.idx.b32 %0, %0, 0, 31, 0xffffffff;" : "+r"(aq));
   const uint32_t row = sbase32 + L.tab;
   const uint32_t tbl = sbase32 + L.sink0;
   const uint32_t usm = sbase32 + L.units;
@@ -104,6 +116,17 @@ __global__ void __launch_bounds__(SG_NT, 1)
   const int64_t n_all = P.n_dev ? (int64_t)*P.n_dev : P.n;
   if (!SG && (unsigned)P.sample >= (unsigned)P.S) return;
 
+  // (no private table: every slot test fails and the counts go to HBM)
+  const uint32_t off = gsink ? 0u : (uint32_t)P.dir_off[e];
+  const uint32_t wid = gsink ? 0u : (uint32_t)P.dir_w[e];
+  // 'Unassigned' is counted when asked for: it sits in the slot after the
+  // private range, and the staged row says `off + wid` where a subject has no
+  // taxon, so that slot = code - off needs no special case
+  const bool unas_on = (P.flags & WK_F_UNASSIGNED) != 0;
+  const uint32_t wid1 = gsink ? 0u : wid + (unas_on ? 1u : 0u);
+  const uint32_t V32 = (uint32_t)P.V;  // the staged row has a pad slot at V
+  const uint32_t c_none = gsink ? (WIDE ? 0xFFFFFFFFu : FX_NONE) : off + wid;
+
   if (lane == 0) mbar_init(mybar, 1);
   if (tid == 0) {
     mbar_init(tabbar, 1);
@@ -112,30 +135,34 @@ __global__ void __launch_bounds__(SG_NT, 1)
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   if (tid == 0 && !WIDE) {
-    mbar_expect_tx(tabbar, rows_bytes + par_bytes);
+    mbar_expect_tx(tabbar, rows_bytes);
     bulk_g2s(row, P.tab16 + (size_t)e * P.Vp, rows_bytes, tabbar);
-    if (ABOVE) bulk_g2s(row + rows_bytes, P.tab16 + P.par16_off, par_bytes, tabbar);
   }
-  if (tid < 33) sts32(usm + (uint32_t)tid * 4u, c_units[tid]);
+  // units of 1/d; a query without any taxon adds one unit to 'Unassigned'
+  if (tid < 33) sts32(usm + (uint32_t)tid * 4u, tid ? c_units[tid] : (uint32_t)WK_UNITS);
 #pragma unroll 1
   for (uint32_t h = tid; h < cells; h += blockDim.x) sts32(tbl + h * 4, 0);
   __syncthreads();
-  if (!WIDE) mbar_wait(tabbar, 0);
+  if (!WIDE) {
+    mbar_wait(tabbar, 0);
+    // the CTA's copy of the row: 'no taxon' becomes the code of the
+    // 'Unassigned' slot, the pad slot at V marks an out-of-range subject
+    if (c_none != FX_NONE)
+#pragma unroll 1
+      for (uint32_t h = tid; h < V32; h += blockDim.x)
+        if (lds16w(row + h * 2u) == FX_NONE) sts16(row + h * 2u, c_none);
+    if (tid == 0) sts16(row + V32 * 2u, SG_BAD16);
+    __syncthreads();
+  }
 
-  const uint32_t V32 = (uint32_t)P.V;  // the staged row has a 'none' pad slot at V
-  // (no private table: every slot test fails and the counts go to HBM)
-  const uint32_t off = gsink ? 0u : (uint32_t)P.dir_off[e];
-  const uint32_t wid = gsink ? 0u : (uint32_t)P.dir_w[e];
-  // 'Unassigned' is counted when asked for: slot wid passes `slot < wid1`
-  const bool unas_on = (P.flags & WK_F_UNASSIGNED) != 0;
-  const uint32_t wid1 = (unas_on && !gsink) ? wid + 1u : 0u;
-  const unsigned le = FULL >> (31 - lane), ge = FULL << lane;
-  const unsigned mybit = 1u << lane;
+  unsigned ge = FULL << lane, le = FULL >> (31 - lane), ones = FULL;
+  uint32_t r_V = V32, r_off = off, r_wid1 = wid1, r_none = c_none, r_row = row,
+           r_tbl = tbl, r_usm = usm;
+  // keep them in registers: ptxas would reload / recompute them per window
+  asm volatile("" : "+r"(ge), "+r"(le), "+r"(ones), "+r"(r_V), "+r"(r_off), "+r"(r_wid1),
+               "+r"(r_none), "+r"(r_row), "+r"(r_tbl), "+r"(r_usm));
   const int GW = (int)gridDim.x * NW;
   const int gw = (int)blockIdx.x * NW + warp;
-  TreeRef TR;
-  TR.parent = P.parent;
-  TR.par16 = row + rows_bytes;
   uint32_t phase = 0;
 
 #pragma unroll 1
@@ -160,9 +187,21 @@ __global__ void __launch_bounds__(SG_NT, 1)
       bulk_g2s(dq + SCOL, P.s + g0, bytes, mybar);
     };
     if (lane == 0 && gw < n_tiles) {
-      if (MULTI) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       issue(gw);
     }
+
+    // a value outside the private range, no private table at all, an
+    // out-of-range subject, or 'Unassigned' without a private slot
+    auto emit_far = [&](uint32_t c, uint32_t amt) {
+      if (c == c_none) {
+        if (unas_on) atomicAdd(crow + (uint32_t)(P.NF1 - 1), (ull)amt);
+      } else if (WIDE ? c >= V32 : c == SG_BAD16) {
+        atoms_exch(badflag, 1u);
+      } else {
+        atomicAdd(crow + c, (ull)amt);
+      }
+    };
 
 #pragma unroll 1
     for (int tile = gw; tile < n_tiles; tile += GW, phase ^= 1u) {
@@ -174,8 +213,11 @@ __global__ void __launch_bounds__(SG_NT, 1)
         // plant the sentinels (record 0 starts a query, the last one ends one)
         const int nrel = (int)(n_all - sbase < TBUF ? n_all - sbase : TBUF);
         if (lane == 0) {
-          if (sbase + SG_PRE == 0)
+          if (sbase + SG_PRE == 0) {
             sts32(aq + SG_PRE * 4u - 4u, ~(uint32_t)lds32(aq + SG_PRE * 4u));
+            // nothing before record 0: no stale keys in the look-back slots
+            for (int j = 0; j < SG_PRE; ++j) sts32(aq + SCOL + (uint32_t)j * 4u, 0u);
+          }
           if (nrel < TBUF)
             sts32(aq + (uint32_t)nrel * 4u, ~(uint32_t)lds32(aq + (uint32_t)nrel * 4u - 4u));
         }
@@ -184,101 +226,115 @@ __global__ void __launch_bounds__(SG_NT, 1)
         if (w1 > nrel) w1 = nrel;
         __syncwarp();
       }
-      // seeking: skip to the record after the next tail (the first own head is
-      // the record after the first tail at or after w0 - 1; a listed long query
-      // is skipped the same way)
+      // skip to the record after the next tail at or after `cur` (the first
+      // own head of a tile follows the first tail at or after w0 - 1; a listed
+      // long query is skipped the same way)
       int cur = w0 - 1;
-      bool seeking = true;
+      const int wlast = w1 - 32;  // windows from here on are clipped to w1
+      auto seek = [&]() {
+#pragma unroll 1
+        while (cur < w1) {
+          const uint32_t ax = aq + (uint32_t)(cur + lane) * 4u;
+          const unsigned T = __ballot_sync(FULL, lds32(ax) != lds32(ax + 4u));
+          if (T) {
+            cur += __ffs(T);
+            break;
+          }
+          cur += 32;
+        }
+      };
+      seek();
 #pragma unroll 1
       while (cur < w1) {
         const uint32_t ax = aq + (uint32_t)(cur + lane) * 4u;
         const int qa = lds32(ax), qb = lds32(ax + 4u);
         const uint32_t sv = (uint32_t)lds32(ax + SCOL);
         const unsigned T = __ballot_sync(FULL, qa != qb);
-        if (seeking || T == 0) {
-          if (!seeking && lane == 0) {
-            // no tail within 32 records of the head: seg_long_kernel's query
+        // whole queries whose head lies before w1
+        unsigned Tl = T;
+        if (cur >= wlast) {
+          const unsigned t2 = T & (FULL << (w1 - cur - 1));
+          if (t2) Tl = T & (FULL >> (32 - __ffs(t2)));
+        }
+        if (Tl == 0) {
+          // no tail within 32 records of the head: seg_long_kernel's query
+          if (lane == 0) {
             const ull at = atomicAdd(P.long_list, 1ull);
             P.long_list[1 + at] = (ull)(sbase + cur);
           }
-          seeking = T == 0;
-          cur += T ? __ffs(T) : 32;
+          cur += 32;
+          seek();
           continue;
         }
-        // whole queries whose head lies before w1
-        const int lim = w1 - cur;
-        unsigned Tl = T;
-        if (lim <= 32) {
-          const unsigned t2 = T & (FULL << (lim - 1));
-          if (t2) Tl = T & (FULL >> (32 - __ffs(t2)));
-        }
-        const int cons = 32 - __clz(Tl);
+        const int tp = bfind32(Tl);               // the last whole query's tail
         const unsigned tge = Tl & ge;             // tails at or after me
         const bool act = tge != 0;                // a lane of a whole query
-        const unsigned H = (Tl << 1) | 1u;        // heads
-        const int sl = 31 - __clz(H & le);        // my query's first lane
+        const unsigned H = Tl + Tl + 1u;          // heads
+        const int sl = bfind32(H & le);           // my query's first lane
         // my query's lanes: from sl up to the first tail at or after me
-        const unsigned segm = act ? ((tge ^ (tge - 1u)) & (FULL << sl)) : 0u;
-        const uint32_t svc = min(sv, V32);
-        if (act && sv != svc) sts32(badflag, 1u);
-        const uint32_t code = WIDE ? (sv < V32 ? sv : C_NONE) : lds16w(row + svc * 2u);
+        const unsigned segm = (tge ^ (tge - 1u)) & (ones << sl);
+        const uint32_t svc = min(sv, r_V);
+        const uint32_t code = WIDE ? sv : lds16w(r_row + svc * 2u);
         // classify.assign_rank: all taxa equal; classify.assign_none: one subject
         const uint32_t key = KIND == WK_KIND_RANK ? code : sv;
         const uint32_t kh = __shfl_sync(FULL, key, sl);
         const unsigned NE = __ballot_sync(FULL, act && key != kh);
-        uint32_t amt = (act && (H & mybit)) ? (uint32_t)WK_UNITS : 0u;
-        uint32_t c = code;
-        if (NE) {
-          const bool alleq = (NE & segm) == 0;
-          if (MODE == FX_UNIQ) {
-            if (!alleq) c = C_NONE;
-          } else if (ABOVE) {
-            // classify.assign_rank with --above (classify.py:119-123): None if
-            // a subject has no taxon, else tree.find_lca of the taxa
-            // (tree.py:513-566), the root -> None.  Repeats do not matter.  The
-            // taxa of a query are folded towards its head lane in log steps.
-            const unsigned NB = __ballot_sync(FULL, act && code == C_NONE) & segm;
-            const int se = __ffs(tge);  // one past my query's last lane
-            const int dist = alleq ? 0 : se - 1 - lane;  // lanes after me
-            const int maxd = __reduce_max_sync(FULL, dist);
-            uint32_t v = code;
+        uint32_t amt, c = code;
+        if (MODE == FX_UNIQ || NE == 0) {
+          // every query is unanimous, or --uniq drops the others: one unit
+          // from the head lane
+          bool ok = WIDE || code != r_none;
+          if (MODE == FX_UNIQ && (NE & segm)) {
+            c = r_none;
+            ok = false;
+          }
+          amt = (act && sl == lane && (ok || unas_on)) ? (uint32_t)WK_UNITS : 0u;
+        } else {
+          // set semantics of the subject pool (align.py:339): a repeat has an
+          // equal KEY earlier in the column
+          const int dist = lane - sl;
+          const uint32_t mykey =
+              ((uint32_t)(cur + sl) << 24) | 0x80000000u | (WIDE ? min(sv, 0xFFFFFFu) : svc);
+          const uint32_t as = ax + SCOL;
+          if (act) sts32(as, mykey);
+          __syncwarp();
+          bool rep = false;
+#pragma unroll
+          for (int m = 1; m <= SG_LB; ++m) rep |= (uint32_t)lds32(as - 4u * m) == mykey;
+          // (the lanes after the last whole query may ask for more trips than
+          // needed; they come back in the next window)
+          const int maxd = __reduce_max_sync(FULL, dist);
+          if (maxd > SG_LB) {
+            bool far = false;
+            uint32_t pa = as - 4u * (SG_LB + 1);
 #pragma unroll 1
-            for (int o = 1; o <= maxd; o <<= 1) {
-              const uint32_t w = __shfl_down_sync(FULL, v, o);
-              if (o <= dist && !NB && w != v) v = (uint32_t)lca2(TR, (int)v, (int)w);
+            for (int m = SG_LB + 1; m <= maxd; m += 2, pa -= 8u) {
+              const uint32_t o1 = (uint32_t)lds32(pa);
+              const uint32_t o2 = (uint32_t)lds32(pa - 4u);
+              far |= (o1 == mykey && m <= dist) || (o2 == mykey && m < dist);
             }
-            if (!alleq) c = (NB || v == (uint32_t)P.root) ? C_NONE : v;
-          } else {
-            // set semantics of the subject pool (align.py:339): a repeat has
-            // an equal subject earlier in its query.  Only the records of
-            // non-unanimous queries look back (straight from the staged
-            // column): three records unconditionally, further ones two per
-            // trip as far as the longest such query of the window reaches.
-            const int dist = alleq ? 0 : lane - sl;
-            const uint32_t as = ax + SCOL;
-            const uint32_t p1 = (uint32_t)lds32(as - 4u), p2 = (uint32_t)lds32(as - 8u),
-                           p3 = (uint32_t)lds32(as - 12u);
-            bool rep = (p1 == sv && dist >= 1) || (p2 == sv && dist >= 2) ||
-                       (p3 == sv && dist >= 3);
-            const int maxd = __reduce_max_sync(FULL, dist);
-#pragma unroll 1
-            for (int m = 4; m <= maxd; m += 2) {
-              const uint32_t o1 = (uint32_t)lds32(as - 4u * (uint32_t)m);
-              const uint32_t o2 = (uint32_t)lds32(as - 4u * (uint32_t)m - 4u);
-              rep = rep || (o1 == sv && m <= dist) || (o2 == sv && m < dist);
-            }
-            const bool nd = !alleq && !rep;
-            // k' = subjects with a taxon (rank) / distinct subjects (none)
-            const bool contrib = nd && (KIND != WK_KIND_RANK || code != C_NONE);
-            const unsigned CB = __ballot_sync(FULL, contrib) & segm;
-            if (!alleq) {
-              const int d = __popc(CB);
-              const uint32_t u = (uint32_t)lds32(usm + (uint32_t)d * 4u);
-              const bool em = contrib && code != C_NONE;
-              amt = em ? u : 0u;
-              if (em && u == 0u) {
-                // rare: 1/d with d not dividing WK_UNITS (overflow list)
-                const ull at = atomicAdd(P.ovf_n, 1ull);
+            rep |= far;
+          }
+          // k' = subjects with a taxon (rank) / distinct subjects (none)
+          const bool valid = WIDE || code != r_none;
+          const bool contrib = act && !rep && (KIND != WK_KIND_RANK || valid);
+          const unsigned CB = __ballot_sync(FULL, contrib) & segm;
+          const int d = __popc(CB);
+          const uint32_t u = (uint32_t)lds32(r_usm + (uint32_t)d * 4u);
+          amt = (contrib && valid) ? u : 0u;
+          if (unas_on) {
+            // no subject of the query has a taxon: 'Unassigned' (the head's
+            // code says so; units[0] is one unit)
+            if (act && sl == lane && d == 0) amt = u;
+          }
+          if (maxd >= 16) {
+            if (contrib && valid && u == 0u) {
+              // rare: 1/d with d not dividing WK_UNITS
+              if ((NE & segm) == 0) {
+                // all taxa equal (classify.py:107-108): the unit, whole
+                if (sl == lane) amt = (uint32_t)WK_UNITS;
+              } else {
+                const ull at = atomicAdd(P.ovf_n, 1ull);  // overflow list
                 if ((int64_t)at < P.ovf_cap) {
                   P.ovf_key[at] = (int64_t)pack_plain(P, e, sample, (int64_t)code);
                   P.ovf_den[at] = d;
@@ -289,22 +345,17 @@ __global__ void __launch_bounds__(SG_NT, 1)
             }
           }
         }
-        // 'Unassigned' sits in the slot after the private range
-        const bool isun = c == C_NONE;
-        const uint32_t slot = isun ? wid : c - off;
         if (amt) {
-          if (slot < (isun ? wid1 : wid)) {
-            const uint32_t old = atoms_add(tbl + slot * 4u, amt);
+          const uint32_t slot = c - r_off;
+          if (slot < r_wid1) {
+            const uint32_t old = atoms_add(r_tbl + slot * 4u, amt);
             if (old + amt < old)  // carry out of the 32-bit low word (rare)
-              atomicAdd(crow + (isun ? (uint32_t)(P.NF1 - 1) : c), 1ull << 32);
-          } else if (!isun) {
-            // a value outside the private range, or no private table at all
-            atomicAdd(crow + c, (ull)amt);
-          } else if (gsink && unas_on) {
-            atomicAdd(crow + (uint32_t)(P.NF1 - 1), (ull)amt);  // 'Unassigned'
+              atomicAdd(crow + (slot == wid ? (uint32_t)(P.NF1 - 1) : c), 1ull << 32);
+          } else {
+            emit_far(c, amt);
           }
         }
-        cur += cons;
+        cur += tp + 1;
       }
       __syncwarp();  // every lane is done with this stage
       if (lane == 0 && tile + GW < n_tiles) {

@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(SW_NT, 1)
               const uint32_t sv = (uint32_t)lds32(x + SCOL);
               const int qn = lds32(x + 4u);
               const uint32_t svc = min(sv, V32);
-              if (sv != svc) sts32(badflag, 1u);
+              if (sv != svc) atoms_exch(badflag, 1u);
               uint32_t code;
               if (WIDE)
                 code = sv < V32 ? sv : C_NONE;  // the subject is the feature

@@ -47,6 +47,81 @@ def reduce_counts(tensor, dst=0):
     return tensor
 
 
+def _active():
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized() and \
+        dist.get_world_size() > 1
+
+
+def merge_engine(eng, dst=0, dense=True, strata=False):
+    """Merge every rank's results into rank `dst`'s context — the device form
+    of `woltka merge` (/root/reference/woltka/tools.py:153-208): ONE reduce
+    of the dense units table, and the two sparse parts — the strata cells
+    (classify.counter_strat keys) and the list of shares whose denominator
+    does not divide UNITS — sent to `dst`, which adds them into its own table
+    (reduce by key).  All ranks must share the plan and the index spaces.
+    Collective: every rank calls it."""
+    import torch
+    import torch.distributed as dist
+    if not _active():
+        return
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if dense:
+        dist.reduce(eng.counts_tensor(), dst=dst, op=dist.ReduceOp.SUM)
+    parts = [eng.overflow_export()]
+    if strata:
+        parts.append(eng.strata_export())
+    dev = parts[0][0].device
+    sizes = torch.tensor([p[0].numel() for p in parts], device=dev,
+                         dtype=torch.int64)
+    every = [torch.empty_like(sizes) for _ in range(world)]
+    dist.all_gather(every, sizes)
+    every = torch.stack(every).cpu().tolist()      # [rank][part]
+    for pi, (a, b) in enumerate(parts):
+        if rank == dst:
+            for src in range(world):
+                n = every[src][pi]
+                if src == dst or not n:
+                    continue
+                ka = torch.empty(n, dtype=a.dtype, device=dev)
+                kb = torch.empty(n, dtype=b.dtype, device=dev)
+                dist.recv(ka, src=src)
+                dist.recv(kb, src=src)
+                torch.cuda.current_stream(dev).synchronize()
+                if pi == 0:
+                    eng.overflow_import(ka, kb, stratified=strata)
+                else:
+                    eng.strata_import(ka, kb)
+        elif every[rank][pi]:
+            dist.send(a.contiguous(), dst=dst)
+            dist.send(b.contiguous(), dst=dst)
+
+
+def merge_profiles(data, dst=0):
+    """Object-level merge for the drop-in `classify()`: every rank interns its
+    own strings, so the per-rank results travel as exact cells keyed by NAMES
+    ({rank: {sample: {feature: Fraction}}}) and are summed on `dst`
+    (util.sum_dict, util.py:78-94, applied across jobs like `woltka merge`).
+    Returns the merged dict on `dst`, None elsewhere."""
+    import torch.distributed as dist
+    if not _active():
+        return data
+    rank, world = dist.get_rank(), dist.get_world_size()
+    got = [None] * world if rank == dst else None
+    dist.gather_object(data, got, dst=dst)
+    if rank != dst:
+        return None
+    out = {}
+    for part in got:
+        for rk, samples in part.items():
+            orow = out.setdefault(rk, {})
+            for sample, prof in samples.items():
+                o = orow.setdefault(sample, {})
+                for key, val in prof.items():
+                    o[key] = o.get(key, 0) + val
+    return out
+
+
 def bind_near_gpu(device):
     """Restrict this process to the CPUs NVML lists as local to CUDA device
     `device`, so that host buffers pinned afterwards (first touch) and the

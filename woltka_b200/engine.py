@@ -116,6 +116,10 @@ class Engine:
     def set_tuning(self, grid=0, block=0, cache_slots=0):
         _lib.check(self.lib.wk_set_tuning(self.ctx, grid, block, cache_slots))
 
+    def set_option(self, name, value):
+        """Named knob of the context (wk_set_option); 0 = default."""
+        _lib.check(self.lib.wk_set_option(self.ctx, name.encode(), int(value)))
+
     # -- model -------------------------------------------------------------
     def set_tree(self, parent, root):
         parent = _i32(parent)
@@ -349,16 +353,52 @@ class Engine:
                                                n.value))
         return out
 
-    def counts_tensor(self):
-        """Zero-copy torch view of the units table (for an NCCL reduce)."""
+    def device_tensor(self, ptr, n, typestr='<i8'):
+        """Zero-copy torch view of n elements of this context's device memory."""
         import torch
-        ptr, n = self.counts_device()
 
         class _Wrap:
             __cuda_array_interface__ = {
-                'shape': (n,), 'typestr': '<i8', 'data': (ptr, False),
-                'version': 2}
+                'shape': (int(n),), 'typestr': typestr,
+                'data': (int(ptr), False), 'version': 2}
+        if not n:
+            dt = {'<i8': torch.int64, '<i4': torch.int32}[typestr]
+            return torch.empty(0, dtype=dt, device=f'cuda:{self.device}')
         return torch.as_tensor(_Wrap(), device=f'cuda:{self.device}')
+
+    def counts_tensor(self):
+        """Zero-copy torch view of the units table (for an NCCL reduce)."""
+        ptr, n = self.counts_device()
+        return self.device_tensor(ptr, n)
+
+    # -- merging contexts (distributed.merge_engine) -----------------------
+    def strata_export(self):
+        """(keys, units) int64 views of the compacted strata cells; valid
+        until the next call on this engine."""
+        k, v, n = C.c_void_p(), C.c_void_p(), C.c_int64()
+        _lib.check(self.lib.wk_strata_export_device(
+            self.ctx, C.byref(k), C.byref(v), C.byref(n)))
+        return (self.device_tensor(k.value, n.value),
+                self.device_tensor(v.value, n.value))
+
+    def strata_import(self, keys, units):
+        """Add (key, units) cells (int64 CUDA tensors) into the strata table."""
+        _lib.check(self.lib.wk_strata_import_device(
+            self.ctx, C.c_void_p(keys.data_ptr()),
+            C.c_void_p(units.data_ptr()), keys.numel()))
+
+    def overflow_export(self):
+        """(keys int64, den int32) views of the overflow list."""
+        k, d, n = C.c_void_p(), C.c_void_p(), C.c_int64()
+        _lib.check(self.lib.wk_overflow_export_device(
+            self.ctx, C.byref(k), C.byref(d), C.byref(n)))
+        return (self.device_tensor(k.value, n.value),
+                self.device_tensor(d.value, n.value, '<i4'))
+
+    def overflow_import(self, keys, den, stratified=False):
+        _lib.check(self.lib.wk_overflow_import_device(
+            self.ctx, C.c_void_p(keys.data_ptr()), C.c_void_p(den.data_ptr()),
+            keys.numel(), int(bool(stratified))))
 
 
 def units_to_value(units, extra=None):

@@ -97,6 +97,8 @@ class Session:
         self.extra_index = {}
         self.sample_index = {}
         self.sample_names = []
+        self.file_index = 0          # set by classify() before each file
+        self.sample_seen = {}        # sample -> (file index, order in file)
         self.stratum_index = {}
         self.stratum_names = []
         self.uses_strata = False
@@ -184,6 +186,7 @@ class Session:
         if idx is None:
             idx = self.sample_index[name] = len(self.sample_names)
             self.sample_names.append(name)
+            self.sample_seen[name] = (self.file_index, idx)
         return idx
 
     def stratum(self, name):
@@ -284,7 +287,23 @@ class Session:
         the device reader (the test stand-in engine does not)."""
         return (len(self.engines) == 1 and not self.trimsub and
                 self.rank2dir is None and
+                not getattr(self, 'device_reader_off', False) and
                 hasattr(self.engines[0], 'parse_sam'))
+
+    def add_text_chunk_host(self, text, demux, sample_name, samples=None,
+                            fmt='sam', n=1024):
+        """The same chunk of text through the host reader (the device
+        reader's tables were full).  Subjects the device named keep their
+        indices; from here on the host numbers the new ones, so the device
+        reader is not used again in this run."""
+        from .align import plain_mapper
+        self.device_reader_off = True
+        lines = iter(text.decode().splitlines(True))
+        nqry = 0
+        for qryque, subque in plain_mapper(lines, fmt=fmt, n=n):
+            nqry += len(qryque)
+            self.add_chunk(qryque, subque, demux, sample_name, samples)
+        return nqry
 
     def add_text_chunk(self, text, demux, sample_name, samples=None,
                        fmt='sam'):
@@ -362,7 +381,10 @@ class Session:
                     if self.outzip:
                         fp = f'{fp}.{self.outzip}'
                     with openzip(fp, 'at') as fh:
-                        fh.write('\n'.join(rows) + '\n')
+                        # a rank listed twice gets its lines twice: the
+                        # reference runs assign_readmap per entry of `ranks`
+                        # (workflow.py:333-335)
+                        fh.write(('\n'.join(rows) + '\n') * self.mult[rank])
 
     def add_ordinal_chunk(self, genes, qnames, contigs, beg, end, length, th,
                           demux, sample_name, samples=None, strata_of=None):
@@ -522,6 +544,11 @@ class Session:
     def results(self):
         """{rank: {sample: {feature | (stratum, feature): count}}} with exact
         counts: int when integral, else the correctly rounded double."""
+        return finalize(self.exact_results())
+
+    def exact_results(self):
+        """The same dict with the counts as exact Fractions (floats with
+        --sizes): what `distributed.merge_profiles` sums across ranks."""
         data = {rank: {} for rank in self.order}
         for rank in self.order:
             for sname in self.sample_names:
@@ -550,10 +577,19 @@ class Session:
                 cells[k] = cells.get(k, 0) + Fraction(1, den)
             for (e, s, t, f), v in cells.items():
                 rank = self.order[grp[e]]
-                v = v * self.mult[rank]
-                val = int(v) if v.denominator == 1 else float(v)
                 name = self.feature_name(f)
                 if t is not None:
                     name = (self.stratum_names[t], name)
-                data[rank][self.sample_names[s]][name] = val
+                data[rank][self.sample_names[s]][name] = v * self.mult[rank]
         return data
+
+
+def finalize(data):
+    """Exact cells -> what the reference holds: int where the count is whole,
+    else the correctly rounded double (in place; returns `data`)."""
+    for samples in data.values():
+        for prof in samples.values():
+            for key, v in prof.items():
+                if isinstance(v, Fraction):
+                    prof[key] = int(v) if v.denominator == 1 else float(v)
+    return data

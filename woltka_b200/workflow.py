@@ -37,6 +37,7 @@ from .align import plain_mapper
 from .ordinal import (load_gene_coords, load_gene_coords_cached,
                       ordinal_mapper, GeneIndex, iter_records)
 from .session import Session, _split_sample
+from ._lib import WoltkaB200Error
 from .coverage import range_mapper, Coverage, coverage_offsets
 
 __all__ = ['classify', 'build_mapper', 'assign_readmap', 'demultiplex',
@@ -78,18 +79,22 @@ def _text_chunks(fp, block=64 << 20, header=True):
             data = fh.read(block)
             buf = carry + data
             if first and buf:
+                # drop the complete '@' lines; an '@' line cut by the block
+                # end waits for the rest of it (the header may be longer than
+                # a block)
                 pos = 0
-                while pos < len(buf) and buf[pos:pos + 1] == b'@':
+                while buf[pos:pos + 1] == b'@':
                     nl = buf.find(b'\n', pos)
                     if nl < 0:
-                        pos = len(buf) if not data else pos
                         break
                     pos = nl + 1
-                if pos < len(buf) or not data:
-                    buf, first = buf[pos:], False
-                elif data:
-                    carry = buf
-                    continue
+                buf = buf[pos:]
+                if buf[:1] == b'@' or not buf:
+                    if data:
+                        carry = buf
+                        continue
+                    return       # the file ends inside its header
+                first = False
             if not data:
                 if buf:
                     yield buf
@@ -179,8 +184,16 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
              subok=False, sizes=None, unasgd=False, stratmap=None,
              exclude=None, chunk=None, cache=1024, zippers=None,
              outcov_dir=None, outcov_fmt=None, _engine_factory=None,
-             _device=0):
+             _device=None):
     """Core of the classification workflow (workflow.py:162-353) on the GPU.
+
+    Under `torchrun` (torch.distributed initialised, one process per GPU) the
+    alignment files are dealt out to the ranks, every rank classifies its
+    share on its own GPU and the exact per-rank profiles are summed on rank 0
+    — the reference's "split, run, `woltka merge`" recipe
+    (/root/reference/doc/perform.md:70-98) inside one call.  Rank 0 returns
+    the merged profiles, the other ranks empty ones (`is_output_rank()` tells
+    a caller which process writes the tables).
 
     `cache` (LRU size of the reference's assigners) has no effect on results
     and is ignored.  Counts are exact: integers where the reference holds
@@ -189,6 +202,15 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
     `round_profiles` the two are identical.
     """
     is_ordinal = getattr(mapper, 'func', None) is ordinal_mapper
+    world, rank = _dist_info()
+    if _device is None:
+        _device = int(os.environ.get('LOCAL_RANK', '0')) if world > 1 else 0
+    # side files are appended per sample: share the work only when no two
+    # ranks can meet the same sample (one file per sample)
+    if world > 1 and ('-' in files or (demux and (rank2dir or outcov_dir))):
+        world = 1
+        if rank != 0:
+            files = type(files)()
     if outcov_dir:
         coverage_offsets(outcov_fmt)     # an invalid format fails up front
         if is_ordinal:
@@ -217,8 +239,10 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
             st = strata_cache[sname] = _read_strata(stratmap[sname], zippers)
             return st
 
+    file_order = {fp: i for i, fp in enumerate(sorted(files))}
     try:
-        for fp in sorted(files):
+        for fp in sorted(files)[rank::world] if world > 1 else sorted(files):
+            sess.file_index = file_index = file_order[fp]
             if fp == '-':
                 fileobj = sys.stdin
                 _echo('Parsing alignment from stdin ', nl=False)
@@ -242,9 +266,24 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
             try:
                 if on_device:
                     for text in _text_chunks(fp, header=dfmt == 'sam'):
-                        nqry += sess.add_text_chunk(
+                        if sess.can_parse_on_device():
+                            try:
+                                nqry += sess.add_text_chunk(
+                                    text, bool(demux), sname,
+                                    samset if demux else None, dfmt)
+                                continue
+                            except WoltkaB200Error as err:
+                                if err.code != 5:      # WK_ERR_CAPACITY
+                                    raise
+                                # the device reader's tables are full (> 1M
+                                # subjects, 64 MiB of names, 32k samples or a
+                                # 64k-line query): this chunk and the rest
+                                # of the run go through the host reader
+                                sess.device_reader_off = True
+                                LAST_READER = 'host'
+                        nqry += sess.add_text_chunk_host(
                             text, bool(demux), sname,
-                            samset if demux else None, dfmt)
+                            samset if demux else None, dfmt, chunk or 1024)
                         istep = nqry // 1000000 - nstep
                         if istep:
                             _echo('.' * istep, nl=False)
@@ -283,11 +322,54 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
             cover.write(outcov_dir, outcov_fmt)
             _echo(' Done.')
         _echo('Classification completed.')
-        data = sess.results()
+        if _dist_info()[0] > 1:
+            data = _merge_ranks(sess)
+        else:
+            data = sess.results()
     finally:
         sess.close()
     # one (possibly empty) profile per requested rank, like workflow.py:268
     return {rank: data[rank] for rank in dict.fromkeys(ranks)}
+
+
+def _dist_info():
+    """(world size, rank) of torch.distributed when it is initialised."""
+    if 'torch' not in sys.modules:
+        return 1, 0
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+def is_output_rank():
+    """True in the process that holds the merged profiles of `classify()`."""
+    return _dist_info()[1] == 0
+
+
+def _merge_ranks(sess):
+    """Sum the exact per-rank profiles on rank 0 (`woltka merge`,
+    tools.py:153-208); samples come back in the order a single process meets
+    them (sorted files, first appearance)."""
+    from .distributed import merge_profiles
+    from .session import finalize
+    import torch.distributed as dist
+    exact = sess.exact_results()
+    seen = [None] * dist.get_world_size() if dist.get_rank() == 0 else None
+    dist.gather_object(sess.sample_seen, seen, dst=0)
+    merged = merge_profiles(exact)
+    if merged is None:
+        return {rk: {} for rk in sess.order}
+    first = {}
+    for part in seen:
+        for name, key in part.items():
+            if name not in first or key < first[name]:
+                first[name] = key
+    out = {}
+    for rk in sess.order:
+        row = merged.get(rk, {})
+        out[rk] = {name: row[name] for name in sorted(row, key=first.get)}
+    return finalize(out)
 
 
 def assign_readmap(qryque, subque, data, rank, sample, assigners, cache=1024,
@@ -333,7 +415,7 @@ def demultiplex(qryque, subque, samples=None, sep='_'):
     the sample is the text before the first `sep` when something follows it,
     else ''; with `samples` only those are kept.  Samples and reads keep the
     order of the chunk."""
-    keep = None if samples is None else set(samples)
+    keep = set(samples) if samples else None
     res = {}
     for query, subjects in zip(qryque, subque):
         left, _, right = query.partition(sep)
