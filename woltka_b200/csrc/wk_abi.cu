@@ -350,16 +350,18 @@ int wk_create(int device, wk_ctx **out) {
         (const void *)classify_fast_kernel<WK_KIND_NONE_ID, FX_FRAC, 13, true>,
         (const void *)classify_fast_kernel<WK_KIND_NONE_ID, FX_UNIQ, 13, false>,
         (const void *)classify_fast_kernel<WK_KIND_NONE_ID, FX_UNIQ, 13, true>};
-#define WK_SEGV(KD, MD)                                              \
-  (const void *)classify_seg_kernel<KD, MD, 512, false>,             \
-      (const void *)classify_seg_kernel<KD, MD, 512, true>,          \
-      (const void *)classify_seg_kernel<KD, MD, 256, false>,         \
-      (const void *)classify_seg_kernel<KD, MD, 256, true>
+#define WK_SEGU(KD, MD, UN)                                          \
+  (const void *)classify_seg_kernel<KD, MD, 512, false, UN>,         \
+      (const void *)classify_seg_kernel<KD, MD, 512, true, UN>,      \
+      (const void *)classify_seg_kernel<KD, MD, 256, false, UN>,     \
+      (const void *)classify_seg_kernel<KD, MD, 256, true, UN>
+#define WK_SEGV(KD, MD) WK_SEGU(KD, MD, false), WK_SEGU(KD, MD, true)
     const void *seg[] = {WK_SEGV(WK_KIND_RANK, FX_FRAC), WK_SEGV(WK_KIND_RANK, FX_UNIQ),
                          WK_SEGV(WK_KIND_NONE, FX_FRAC),
                          WK_SEGV(WK_KIND_NONE, FX_UNIQ), WK_SEGV(WK_KIND_NONE_ID, FX_FRAC),
                          WK_SEGV(WK_KIND_NONE_ID, FX_UNIQ)};
 #undef WK_SEGV
+#undef WK_SEGU
     for (const void *fn : seg)
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)c->smem_optin));
@@ -1008,8 +1010,13 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
           const int sgrid =
               (int)std::min<int64_t>(grid, (ft + SG_NT / 32 - 1) / (SG_NT / 32));
           CK(cudaMemsetAsync(P.long_list, 0, 8, c->stream));
-#define WK_SEG4(KD, MD, WW, MU) \
-  classify_seg_kernel<KD, MD, WW, MU><<<sgrid, SG_NT, GL.total, c->stream>>>(P)
+#define WK_SEG4(KD, MD, WW, MU)                                                      \
+  do {                                                                               \
+    if (c->flags & WK_F_UNASSIGNED)                                                  \
+      classify_seg_kernel<KD, MD, WW, MU, true><<<sgrid, SG_NT, GL.total, c->stream>>>(P);  \
+    else                                                                             \
+      classify_seg_kernel<KD, MD, WW, MU, false><<<sgrid, SG_NT, GL.total, c->stream>>>(P); \
+  } while (0)
 #define WK_SEG3(KD, MD, WW)               \
   do {                                    \
     if (multi) WK_SEG4(KD, MD, WW, true); \

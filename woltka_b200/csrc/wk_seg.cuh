@@ -80,7 +80,7 @@ __host__ __device__ inline SgSmemLayout sg_layout(int NW, int WT, uint32_t cells
 // the stream is a sequence of contiguous samples given as a segment table
 // (seg_scan_kernel / seg_sort_kernel, wk_sweep.cuh); the private table is
 // flushed between segments.
-template <int KIND, int MODE, int WT, bool MULTI>
+template <int KIND, int MODE, int WT, bool MULTI, bool UNAS>
 __global__ void __launch_bounds__(SG_NT, 1)
     classify_seg_kernel(const __grid_constant__ ClsParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(SG_NT, 1)
   // 'Unassigned' is counted when asked for: it sits in the slot after the
   // private range, and the staged row says `off + wid` where a subject has no
   // taxon, so that slot = code - off needs no special case
-  const bool unas_on = (P.flags & WK_F_UNASSIGNED) != 0;
+  constexpr bool unas_on = UNAS;  // (P.flags & WK_F_UNASSIGNED)
   const uint32_t wid1 = gsink ? 0u : wid + (unas_on ? 1u : 0u);
   const uint32_t V32 = (uint32_t)P.V;  // the staged row has a pad slot at V
   const uint32_t c_none = gsink ? (WIDE ? 0xFFFFFFFFu : FX_NONE) : off + wid;
@@ -298,22 +298,31 @@ __global__ void __launch_bounds__(SG_NT, 1)
           const uint32_t as = ax + SCOL;
           if (act) sts32(as, mykey);
           __syncwarp();
+          // (no bounds: what lies further back is another query's keys, a
+          // skipped record's raw subject or, before the column, this warp's
+          // raw query indices — none has bit 31 and this tag)
           bool rep = false;
 #pragma unroll
           for (int m = 1; m <= SG_LB; ++m) rep |= (uint32_t)lds32(as - 4u * m) == mykey;
-          // (the lanes after the last whole query may ask for more trips than
-          // needed; they come back in the next window)
+          // longer queries: two more records per step, as far as the longest
+          // query of the window reaches (the lanes after the last whole query
+          // may ask for more than needed; they come back in the next window)
           const int maxd = __reduce_max_sync(FULL, dist);
           if (maxd > SG_LB) {
-            bool far = false;
-            uint32_t pa = as - 4u * (SG_LB + 1);
+            rep |= (uint32_t)lds32(as - 4u * (SG_LB + 1)) == mykey;
+            rep |= (uint32_t)lds32(as - 4u * (SG_LB + 2)) == mykey;
+            if (maxd > SG_LB + 2) {
+              rep |= (uint32_t)lds32(as - 4u * (SG_LB + 3)) == mykey;
+              rep |= (uint32_t)lds32(as - 4u * (SG_LB + 4)) == mykey;
+              if (maxd > SG_LB + 4) {
+                uint32_t pa = as - 4u * (SG_LB + 5);
+                bool far = false;
 #pragma unroll 1
-            for (int m = SG_LB + 1; m <= maxd; m += 2, pa -= 8u) {
-              const uint32_t o1 = (uint32_t)lds32(pa);
-              const uint32_t o2 = (uint32_t)lds32(pa - 4u);
-              far |= (o1 == mykey && m <= dist) || (o2 == mykey && m < dist);
+                for (int m = SG_LB + 5; m <= maxd; m += 2, pa -= 8u)
+                  far = far | ((uint32_t)lds32(pa) == mykey) | ((uint32_t)lds32(pa - 4u) == mykey);
+                rep |= far;
+              }
             }
-            rep |= far;
           }
           // k' = subjects with a taxon (rank) / distinct subjects (none)
           const bool valid = WIDE || code != r_none;
@@ -322,37 +331,37 @@ __global__ void __launch_bounds__(SG_NT, 1)
           const int d = __popc(CB);
           const uint32_t u = (uint32_t)lds32(r_usm + (uint32_t)d * 4u);
           amt = (contrib && valid) ? u : 0u;
-          if (unas_on) {
+          if (UNAS) {
             // no subject of the query has a taxon: 'Unassigned' (the head's
             // code says so; units[0] is one unit)
             if (act && sl == lane && d == 0) amt = u;
           }
-          if (maxd >= 16) {
-            if (contrib && valid && u == 0u) {
-              // rare: 1/d with d not dividing WK_UNITS
-              if ((NE & segm) == 0) {
-                // all taxa equal (classify.py:107-108): the unit, whole
-                if (sl == lane) amt = (uint32_t)WK_UNITS;
+          if (contrib && valid && u == 0u) {
+            // rare: 1/d with d not dividing WK_UNITS
+            if ((NE & segm) == 0) {
+              // all taxa equal (classify.py:107-108): the unit, whole
+              if (sl == lane) amt = (uint32_t)WK_UNITS;
+            } else {
+              const ull at = atomicAdd(P.ovf_n, 1ull);  // overflow list
+              if ((int64_t)at < P.ovf_cap) {
+                P.ovf_key[at] = (int64_t)pack_plain(P, e, sample, (int64_t)code);
+                P.ovf_den[at] = d;
               } else {
-                const ull at = atomicAdd(P.ovf_n, 1ull);  // overflow list
-                if ((int64_t)at < P.ovf_cap) {
-                  P.ovf_key[at] = (int64_t)pack_plain(P, e, sample, (int64_t)code);
-                  P.ovf_den[at] = d;
-                } else {
-                  atomicOr(P.err, ERR_OVF_FULL);
-                }
+                atomicOr(P.err, ERR_OVF_FULL);
               }
             }
           }
         }
-        if (amt) {
+        {
           const uint32_t slot = c - r_off;
-          if (slot < r_wid1) {
-            const uint32_t old = atoms_add(r_tbl + slot * 4u, amt);
-            if (old + amt < old)  // carry out of the 32-bit low word (rare)
+          const bool inr = slot < r_wid1;
+          uint32_t old = 0u;
+          if (amt != 0u && inr) old = atoms_add(r_tbl + slot * 4u, amt);
+          if (amt != 0u && (!inr || old + amt < old)) {
+            if (inr)  // carry out of the 32-bit low word (rare)
               atomicAdd(crow + (slot == wid ? (uint32_t)(P.NF1 - 1) : c), 1ull << 32);
-          } else {
-            emit_far(c, amt);
+            else
+              emit_far(c, amt);
           }
         }
         cur += tp + 1;
