@@ -29,6 +29,9 @@ def _lean_kernel(entries, mode):
     none = all(x == 'none' for x in entries)
     if not none and any(x in ('none', 'free') for x in entries):
         return 'classify_kernel'
+    if not none and (mode.startswith('above') or (
+            len(entries) > 1 and mode.startswith(('default', 'uniq')))):
+        return 'classify_multi_kernel'    # all ranks in one pass
     if none or mode.startswith(('default', 'uniq')):
         return 'classify_seg_kernel'
     return 'classify_fast_kernel'
@@ -271,6 +274,7 @@ def test_contiguous_samples_take_the_run_per_lane_kernel(engine, small_case,
     stream."""
     if noseg:
         knobs.set('no_seg', 1)
+        knobs.set('no_multi', 1)
     q, s = cases.random_hits(small_case, 60000, seed=77, long_every=5000,
                              long_len=90)
     nq = int(q.max()) + 1
@@ -299,7 +303,9 @@ def test_which_kernel_runs(engine, small_case):
     cases.run_engine(engine, small_case, ['genus'], cases.MODES['major'], 0.8, q, s)
     assert engine.last_kernel() == 'classify_fast_kernel'
     cases.run_engine(engine, small_case, ['phylum', 'genus'], 0, 0, q, s)
-    assert engine.last_kernel() == 'classify_seg_kernel'
+    assert engine.last_kernel() == 'classify_multi_kernel'
+    cases.run_engine(engine, small_case, ['genus'], cases.MODES['above'], 0, q, s)
+    assert engine.last_kernel() == 'classify_multi_kernel'
     cases.run_engine(engine, small_case, ['phylum', 'genus'],
                      cases.MODES['major'], 0.8, q, s)
     assert engine.last_kernel() == 'classify_fast_kernel'
@@ -325,6 +331,7 @@ def test_run_per_lane_kernel_at_1e6(engine, big_case, knobs, noseg):
     # with and without the lane-per-record kernel of the default / --uniq mode
     if noseg:
         knobs.set('no_seg', 1)
+        knobs.set('no_multi', 1)
     qi, si, _, nq = synth.gen_hits(1_000_000, seed=1002)
     q, s = qi.numpy(), si.numpy()
     for ent in (['genus'], ['species'], ['none']):
@@ -390,6 +397,7 @@ def test_short_runs_and_fewer_warps(engine, small_case, knobs, r, block):
     default) and with fewer warps per CTA, as chosen for large tables."""
     knobs.set('sweep_r', int(r))
     knobs.set('no_seg', 1)
+    knobs.set('no_multi', 1)
     q, s = cases.random_hits(small_case, 30000, seed=int(r), long_every=3000,
                              long_len=60)
     engine.set_tuning(0, block, 0)
@@ -414,6 +422,7 @@ def test_randomised_shapes_both_kernels_agree(engine, small_case, knobs,
     run-per-lane kernel == window kernel == oracle."""
     if noseg:
         knobs.set('no_seg', 1)
+        knobs.set('no_multi', 1)
     rng = np.random.default_rng(2026)
     ents = (['genus'], ['none'], ['phylum', 'species'])
     modes = ('default', 'uniq', 'major', 'above', 'major+unassigned')
@@ -452,6 +461,7 @@ def test_rank_none_without_a_table(engine, mode, NF, knobs, noseg):
     to global memory when it does not (NF = 3e6)."""
     if noseg:
         knobs.set('no_seg', 1)
+        knobs.set('no_multi', 1)
     from oracle import oracle as O
     from woltka_b200._lib import KIND_NONE_ID
     rng = np.random.default_rng(NF)
@@ -485,6 +495,7 @@ def test_host_chunk_in_sub_chunks(engine, small_case, knobs, sub, noseg):
     knobs.set('cls_sub', int(sub))
     if noseg:
         knobs.set('no_seg', 1)
+        knobs.set('no_multi', 1)
     q, s = cases.random_hits(small_case, 2500, seed=int(sub), kmax=31, p=0.3,
                              long_every=211, long_len=70, window=6)
     for ent, mode in ((['genus'], 'default'), (['genus'], 'uniq+unassigned'),

@@ -16,6 +16,7 @@
 #include "wk_classify.cuh"
 #include "wk_ordinal.cuh"
 #include "wk_seg.cuh"
+#include "wk_multi.cuh"
 #include "wk_cover.cuh"
 #include "wk_sweep.cuh"
 #include "wk_parse.cuh"
@@ -177,6 +178,8 @@ struct wk_ctx {
   bool stage_dirty = true;
   int32_t sn16_off = -1, par16_off = -1, stage_elems = 0, stage_vmax = -1;
   int32_t n_levels = 0, level_off[40];
+  bool minmax_ok = false;  // --above through min / max index (classify_multi_kernel)
+  int opt_no_multi = 0;
   std::vector<int64_t> dir_lo, dir_hi;  // per entry: range of the table values
   // overflow + err
   DevBuf cov_keys, cov_ends;  // coverage store (wk_cover.cuh)
@@ -365,6 +368,17 @@ int wk_create(int device, wk_ctx **out) {
     for (const void *fn : seg)
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)c->smem_optin));
+#define WK_MUV(MD, UN)                                               \
+  (const void *)classify_multi_kernel<MD, 512, UN>,                  \
+      (const void *)classify_multi_kernel<MD, 256, UN>,              \
+      (const void *)classify_multi_kernel<MD, 128, UN>
+    const void *multi[] = {WK_MUV(FX_FRAC, false), WK_MUV(FX_FRAC, true),
+                           WK_MUV(FX_UNIQ, false), WK_MUV(FX_UNIQ, true),
+                           WK_MUV(FX_ABOVE, false), WK_MUV(FX_ABOVE, true)};
+#undef WK_MUV
+    for (const void *fn : multi)
+      CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)c->smem_optin));
     for (const void *fn : fast)
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)c->smem_optin));
@@ -433,6 +447,7 @@ int wk_set_option(wk_ctx *c, const char *name, int64_t value) {
   const std::string k(name);
   if (k == "no_seg") c->opt_no_seg = (int)value;
   else if (k == "no_fast") c->opt_no_fast = (int)value;
+  else if (k == "no_multi") c->opt_no_multi = (int)value;
   else if (k == "sweep_r") c->opt_sweep_r = (int)value;
   else if (k == "seg_wt") c->opt_seg_wt = (int)value;
   else if (k == "ord_nowin") c->opt_ord_nowin = (int)value;
@@ -748,6 +763,28 @@ static int pack_stage(wk_ctx *c) {
     for (int64_t i = 0; i < V; ++i) vmax = std::max(vmax, c->h_tab[(size_t)e * V + i]);
   }
   c->stage_vmax = vmax;
+  // --above by smallest and largest index (wk_multi.cuh): the nodes are
+  // numbered level by level, every level in the order of the parents, and the
+  // values of every rank row sit on one level
+  c->minmax_ok = false;
+  if (c->n_levels > 0 && need_lca && !any_free) {
+    bool ok = true;
+    for (int l = 1; l < c->n_levels && ok; ++l)
+      for (int32_t i = c->level_off[l] + 1; i < c->level_off[l + 1] && ok; ++i)
+        ok = c->h_parent[i] >= c->h_parent[i - 1];
+    for (int e = 0; e < c->E && ok; ++e) {
+      int lev = -1;
+      for (int64_t i = 0; i < V && ok; ++i) {
+        const int32_t v = c->h_tab[(size_t)e * V + i];
+        if (v < 0) continue;
+        int l = 0;
+        while (l + 1 < c->n_levels && v >= c->level_off[l + 1]) ++l;
+        if (lev < 0) lev = l;
+        ok = l == lev;
+      }
+    }
+    c->minmax_ok = ok;
+  }
   if (vmax >= 0xFFFF) return WK_OK;
   const int64_t Vp = (V + 8) & ~7ll;  // at least one 'none' pad slot after V
   size_t elems = (size_t)c->E * Vp;
@@ -962,6 +999,70 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
     }
     const int64_t span = n_dev ? n_bound : r1 - (r0 & ~3ll);
     if (span <= 0) return WK_OK;
+    // several ranks (or --above at one rank) in ONE pass: classify_multi_kernel
+    // (wk_multi.cuh).  --above needs the tree numbered level by level with the
+    // taxa of every row on one level (pack_stage), and the count range of
+    // --above reaches down to the root.
+    if (NTmax == SW_NT && !c->opt_no_multi && rk && !gsink && staged &&
+        c->stage_vmax < 0xFFFE && (mode == FX_ABOVE ? (par_ok && c->minmax_ok) : c->E > 1) &&
+        (mode == FX_FRAC || mode == FX_UNIQ || mode == FX_ABOVE)) {
+      // parents of the taxa and of their ancestors: indices below the largest value
+      const int32_t par_n = mode == FX_ABOVE ? std::min<int32_t>(c->T, c->stage_vmax + 1) : 0;
+      const int64_t tabb = (int64_t)c->E * c->Vp * 2 + (((int64_t)par_n + 7) & ~7ll) * 2;
+      int WTm = 0;
+      for (int wt : {512, 256, 128})
+        if (!WTm && mu_layout(SG_NT / 32, wt, c->E, dir_cells, tabb).total <= c->smem_optin)
+          WTm = wt;
+      if (WTm) {
+        if (dqsamp) {
+          // where the sample of the stream changes (device side, no host sync)
+          TRY(c->seglist.reserve(sizeof(SegList)));
+          SegList *sl = c->seglist.as<SegList>();
+          CK(cudaMemsetAsync(sl, 0, 8, c->stream));
+          const int sgrid =
+              (int)std::min<int64_t>((r1 - r0 + 255) / 256, (int64_t)c->sm_count * 16);
+          seg_scan_kernel<<<sgrid, 256, 0, c->stream>>>(dq, dqsamp, r0, r1, sl);
+          seg_sort_kernel<<<1, 256, 0, c->stream>>>(dq, dqsamp, r0, r1, sl);
+          c->launches += 2;
+          P.seg_list = sl;
+        }
+        P.direct_cells = dir_cells;
+        P.par_n = par_n;
+        TRY(c->longlist.reserve((size_t)(span / 33 + 4) * 8));
+        P.long_list = c->longlist.as<ull>();
+        CK(cudaMemsetAsync(P.long_list, 0, 8, c->stream));
+        const MuSmemLayout ML = mu_layout(SG_NT / 32, WTm, c->E, dir_cells, tabb);
+        const int64_t ft = (span + WTm - 1) / WTm;
+        const int mgrid = (int)std::min<int64_t>(grid, (ft + SG_NT / 32 - 1) / (SG_NT / 32));
+        const bool un = (c->flags & WK_F_UNASSIGNED) != 0;
+#define WK_MU3(MD, WW)                                                                \
+  do {                                                                                \
+    if (un) classify_multi_kernel<MD, WW, true><<<mgrid, SG_NT, ML.total, c->stream>>>(P);  \
+    else classify_multi_kernel<MD, WW, false><<<mgrid, SG_NT, ML.total, c->stream>>>(P);    \
+  } while (0)
+#define WK_MU2(MD)                          \
+  do {                                      \
+    if (WTm == 512) WK_MU3(MD, 512);        \
+    else if (WTm == 256) WK_MU3(MD, 256);   \
+    else WK_MU3(MD, 128);                   \
+  } while (0)
+        if (mode == FX_ABOVE) WK_MU2(FX_ABOVE);
+        else if (mode == FX_UNIQ) WK_MU2(FX_UNIQ);
+        else WK_MU2(FX_FRAC);
+#undef WK_MU2
+#undef WK_MU3
+        seg_long_kernel<<<c->sm_count, 128, 0, c->stream>>>(P);
+        c->launches += 2;
+        CK(cudaGetLastError());
+        c->last_kernel = "classify_multi_kernel";
+        if (!dqsamp) return WK_OK;
+        // interleaved samples (more than FX_MAX_SEG changes): the kernels above
+        // returned at once and classify_kernel below does the chunk
+        P.seg_list = nullptr;
+        P.skip_flag = &c->seglist.as<SegList>()->nseg;
+        goto window_kernel;
+      }
+    }
     // default or --uniq: the lane-per-record kernel with warp-private tiles
     // (wk_seg.cuh), one launch per entry; its staged row keeps two codes for
     // itself (SG_BAD16 and the 'Unassigned' slot)
@@ -1127,6 +1228,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
     }
   }
 
+window_kernel:
   const int64_t tab_bytes = staged ? (int64_t)c->stage_elems * 2 : 0;
   // where counts are accumulated first (wk_classify.cuh, "count sinks")
   int sink = SINK_GLOBAL, cache_log = 0;

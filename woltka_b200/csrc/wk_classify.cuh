@@ -102,6 +102,7 @@ struct ClsParams {
   const int32_t *skip_flag;   // classify_kernel: do nothing if *skip_flag >= 0
   int32_t fast_gsink;         // classify_fast_kernel: no private table, global reductions
   ull *long_list;             // classify_seg_kernel: [0] = count, [1..] first record of a long query
+  int32_t par_n;              // classify_multi_kernel: nodes of the parent array to stage
 };
 
 enum { ERR_BAD_SUBJECT = 1, ERR_OVF_FULL = 2, ERR_HASH_FULL = 4,
