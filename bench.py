@@ -2,16 +2,25 @@
 """Benchmark of the classify hot path (BASELINE.json metric: alignment
 records classified per second; achieved HBM GB/s vs peak).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg4|cfg5]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N
-    python bench.py --impl reference        # CPU arm (oracle port, all cores)
+    python bench.py --impl reference        # CPU arm (the reference itself when
+                                            # it is importable, else the C port)
 
 A step is one pass of the hot path over one batch of synthetic records
-(SURVEY.md §8d generator).  `value` is timed with the int32 SoA columns
-already resident in HBM; `e2e` goes through the reference-facing C-ABI call
-with pinned HOST buffers (H2D of the columns and D2H of the count table inside
-the timed region).  Every rank works on its own batch (weak scaling); the
-per-rank count tables are merged by one NCCL reduce to rank 0 per step.
+(SURVEY.md §8d generator) and ends with the merged result on rank 0.  `value`
+is timed with the int32 SoA columns already resident in HBM; `e2e` goes
+through the reference-facing C-ABI call with pinned HOST buffers (H2D of the
+columns and D2H of the result inside the timed region).  Every rank works on
+its own batch (weak scaling: its own samples of one shared table); per step
+the per-rank results are merged on rank 0: ONE NCCL reduce of the dense units
+table, and for stratified plans the strata cells sent to rank 0 and added by
+key (woltka_b200.distributed.merge_engine).
+
+The default workload is cfg2 (BASELINE.json configs[1]); its line carries, as
+`extra`, short runs of cfg3, cfg4 and cfg5 at the same number of GPUs (cfg4 /
+cfg5 at 8 GPUs are BASELINE.json configs[3] / [4]: 1e9 records over 64 samples,
+5e8 stratified records).
 """
 import argparse
 import json
@@ -29,6 +38,9 @@ if ROOT not in sys.path:
 
 METRIC = 'alignment records classified per second'
 UNIT = 'records/s'
+# records per GPU: BASELINE.json sizes / 8 GPUs for the 8-GPU configs
+DEFAULT_RECORDS = {'cfg2': 100_000_000, 'cfg3': 100_000_000,
+                   'cfg4': 125_000_000, 'cfg5': 62_500_000}
 
 
 def parse_args():
@@ -37,21 +49,32 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3', 'cfg4', 'cfg5'])
-    ap.add_argument('--records', type=int, default=100_000_000)
+    ap.add_argument('--workload', default='cfg2',
+                    choices=['cfg2', 'cfg3', 'cfg4', 'cfg5'])
+    ap.add_argument('--records', type=int, default=0,
+                    help='records per GPU (default: the config\'s size)')
     ap.add_argument('--mode', default='default',
                     choices=['default', 'major', 'uniq', 'above'])
     ap.add_argument('--ranks', default='genus')
     ap.add_argument('--cpu-sample', type=int, default=20_000_000)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-extra', action='store_true',
+                    help='default workload: skip the cfg3 / cfg4 / cfg5 extras')
     ap.add_argument('--samples', type=int, default=1,
                     help='samples per GPU (per-query sample column if > 1)')
+    ap.add_argument('--opt', action='append', default=[],
+                    help='name=value knob of the context (wk_set_option)')
     args = ap.parse_args()
+    args.explicit_records = args.records
+    if not args.records:
+        args.records = DEFAULT_RECORDS[args.workload]
     if args.workload == 'cfg4':
         # BASELINE.json configs[3]: phylum/genus/species with multi-hit LCA,
-        # 64 samples sharded 8 per GPU
-        args.ranks, args.mode, args.samples = 'phylum,genus,species', 'above', 8
+        # 64 samples sharded 8 per GPU (pass --mode major for its second run)
+        args.ranks, args.samples = 'phylum,genus,species', 8
+        if args.mode == 'default':
+            args.mode = 'above'
     return args
 
 
@@ -64,9 +87,21 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def cpu_model():
+    try:
+        with open('/proc/cpuinfo') as f:
+            for line in f:
+                if line.startswith('model name'):
+                    return line.split(':', 1)[1].strip()
+    except OSError:
+        pass
+    return 'unknown'
+
+
 def measured_traffic(kernel, records):
-    """DRAM bytes per launch from the committed `ncu --set full` capture
-    (profiles/traffic.json), valid for the same record count only."""
+    """DRAM bytes per launch read from the committed `ncu --set full` capture
+    (profiles/traffic.json: measured under ncu once, NOT in this run), valid
+    for the same record count only."""
     try:
         with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
             t = json.load(f)[kernel]
@@ -138,25 +173,103 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-# ---- workloads ---------------------------------------------------------------
-def make_cfg2(args, device, seed):
-    """genus-rank (or --ranks) classify over the 21,603-node taxonomy."""
-    from tests import cases
-    from woltka_b200 import synth
-    case = cases.Case(synth.Taxonomy(seed=42))
-    entries = args.ranks.split(',')
-    flags = cases.MODES[args.mode]
-    q, s, qs, nq = synth.gen_hits(args.records, seed=seed, device=device,
-                                  n_samples=args.samples)
-    args._q_sample = qs if args.samples > 1 else None
-    return case, entries, flags, q, s, nq
+class Ctx:
+    """One rank of the bench: its GPU, its engine, the process group."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from woltka_b200.engine import Engine
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device('cuda', self.local)
+        self.near = None
+        if self.world > 1:
+            # ranks of one box: keep each rank's pinned host columns and copy
+            # threads on its GPU's NUMA node
+            from woltka_b200.distributed import bind_near_gpu
+            if not os.environ.get('WK_NO_BIND'):
+                self.near = bind_near_gpu(self.local)
+            dist.init_process_group('nccl', device_id=self.dev)
+        self.opts = [o.split('=', 1) for o in args.opt]
+        self.hbm_peak, self.peak_src = peaks()
+        self.torch, self.dist = torch, dist
+
+    def engine(self):
+        from woltka_b200.engine import Engine
+        eng = Engine(self.local)
+        eng.set_stream(self.torch.cuda.current_stream().cuda_stream)
+        for name, value in self.opts:
+            eng.set_option(name, int(value))
+        return eng
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        t = self.torch.tensor([ms], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def event(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
 
 
-def cpu_classify(case, entries, flags, q, s, threads, **kw):
-    from tests import cases
+def timed_steps(ctx, steps, warmup, step, classify_only=None, clocks=False):
+    """W warm-up steps, then K steps between a barrier + synchronize on both
+    sides, device events, max over ranks.  Returns (ms total, ms per kernel
+    part, launches delta is the caller's, clocks)."""
+    for _ in range(warmup):
+        step()
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local) if clocks and ctx.rank == 0 else None
+    if sampler:
+        sampler.start()
+    k_ev = [(ctx.event(), ctx.event()) for _ in range(steps)]
+    t_beg, t_end = ctx.event(), ctx.event()
+    t_beg.record()
+    for i in range(steps):
+        step(k_ev[i])
+    t_end.record()
+    ctx.barrier()
+    ck = sampler.stop() if sampler else None
+    ms = ctx.max_over_ranks(t_beg.elapsed_time(t_end))
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    return ms, k_ms, ck
+
+
+def collect(eng, n_samples, NF):
+    """Engine results in the canonical form oracle.classify returns."""
+    units = eng.fetch_counts()
+    cell, strat, den = eng.fetch_overflow()
+    NF1 = NF + 1
+    overflow = []
+    for c, t, d in zip(cell.tolist(), strat.tolist(), den.tolist()):
+        es, f = divmod(c, NF1)
+        overflow.append((es // n_samples, es % n_samples, t, f, d))
+    overflow.sort()
+    e, sm, st, f, u = eng.fetch_strata()
+    return units, overflow, (e, sm, st, f, u)
+
+
+def oracle_classify(case, entries, flags, q, s, threads, **kw):
+    """The CPU oracle (checker / CPU baseline only)."""
+    from oracle import oracle as O
+    kinds, _, trk = case.tables(entries)
     t0 = time.perf_counter()
-    out = cases.run_oracle(case, entries, flags, 0.8, q, s, n_threads=threads,
-                           **kw)
+    out = O.classify(q, s, parent=case.ft.parent, node_rank=case.ft.node_rank,
+                     root=0, sub_node=case.sub_node, sub_feat=case.sub_feat,
+                     kinds=kinds, target_rank=trk, flags=flags, major_th=0.8,
+                     n_features=case.NF, n_threads=threads, **kw)
     return out, time.perf_counter() - t0
 
 
@@ -164,7 +277,6 @@ def python_port_rate(case, entries, flags, q, s, m=200_000):
     """Records/s of the pure-Python restatement (oracle/pyport.py: str / set
     / dict like the reference) on the first m records of the batch."""
     from oracle import pyport
-    from tests import cases as C
     tax = case.tax
     ids = tax.ids()
     tree = {ids[i]: ids[tax.parent[i]] for i in range(tax.T)}
@@ -194,12 +306,54 @@ def python_port_rate(case, entries, flags, q, s, m=200_000):
                       f'reference\'s data structures)'}
 
 
-def text_e2e(case, entries, flags, q, s, n_samples, m=2_000_000):
+def workload_config(workload, records, entries, mode=None, samples=1):
+    if workload == 'cfg5':
+        return {'workload': 'cfg5: stratified taxonomy x function: gene '
+                            'subjects (10k genomes x 500 genes), rank ko '
+                            'through a gene -> KO map (10k KOs, 60 % '
+                            'annotated), counts keyed by (genus stratum, KO), '
+                            '8 samples per GPU, strata cells merged on rank 0',
+                'records_per_gpu': records, 'ranks': entries,
+                'subjects': 5_000_000, 'kos': 10_000, 'genera': 3000,
+                'samples_per_gpu': 8, 'l2': 'inputs larger than L2'}
+    if workload == 'cfg3':
+        return {'workload': 'cfg3: coord-match ordinal profile, synthetic '
+                            'reads x 5M gene intervals over 1k contigs, '
+                            'overlap 80, rank none',
+                'records_per_gpu': records, 'genes': 5_000_000,
+                'contigs': 1000,
+                'l2': 'inputs larger than L2 (2 GB of columns per step)'}
+    if workload == 'cfg4':
+        return {'workload': 'cfg4: phylum/genus/species with multi-hit LCA '
+                            '(--above), synthetic records, 8 samples per GPU',
+                'records_per_gpu': records, 'ranks': entries,
+                'mode': mode, 'samples_per_gpu': samples,
+                'taxonomy_nodes': 21603, 'genomes': 10000,
+                'l2': 'inputs larger than L2'}
+    return {'workload': 'cfg2: genus-rank taxonomic classify, synthetic SAM '
+                        'records x 10k-genome / 21,603-node taxonomy',
+            'records_per_gpu': records, 'ranks': entries,
+            'mode': mode, 'taxonomy_nodes': 21603, 'genomes': 10000,
+            'l2': 'inputs larger than L2 (0.8 GB of columns per step)'}
+
+
+def base_line(ctx, workload, records, entries, mode, samples, steps, warmup,
+              ms, value):
+    return {'metric': METRIC, 'value': value, 'unit': UNIT,
+            'n_gpus': ctx.world, 'steps': steps, 'warmup': warmup,
+            'ms_per_step': ms / steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32',
+            'data': 'synthetic',
+            'config': workload_config(workload, records, entries, mode,
+                                      samples)}
+
+
+# ---- cfg2 / cfg4: classify over the taxonomy ---------------------------------
+def text_e2e(ctx, case, entries, flags, q, s, n_samples, m=2_000_000):
     """Same plan fed from SAM TEXT in host memory (the form the reference
     reads): wk_parse_text + wk_classify_parsed on the first m records of the
     batch, checked against the column-fed result of the same records."""
-    from woltka_b200.engine import Engine
-    from tests import cases as C
+    from woltka_b200.engine import Engine, pinned_empty
     m = min(m, len(q))
     while 0 < m < len(q) and q[m] == q[m - 1]:
         m += 1
@@ -209,13 +363,12 @@ def text_e2e(case, entries, flags, q, s, n_samples, m=2_000_000):
     tail = b'\t1\t42\t150M\t*\t0\t0\t' + b'A' * 50 + b'\t' + b'I' * 50 + b'\n'
     text = b''.join(b'r%d\t0\t%s%s' % (qi, gid[si], tail)
                     for qi, si in zip(q.tolist(), s.tolist()))
-    from woltka_b200.engine import pinned_empty
     nbytes = len(text)
     ptext = pinned_empty(nbytes, np.uint8)     # the file block, read into pinned memory
     ptext[:] = np.frombuffer(text, dtype=np.uint8)
     text = ptext
     kinds, tab, _ = case.tables(entries)
-    eng = Engine(0)
+    eng = Engine(ctx.local)
     eng.set_tree(case.ft.parent, 0)
     eng.set_plan(kinds, flags, 0.8, n_samples, case.NF)
     # subjects get their index in order of appearance: parse once to learn it
@@ -237,8 +390,12 @@ def text_e2e(case, entries, flags, q, s, n_samples, m=2_000_000):
         eng.classify_parsed(None, 0)
         got = eng.fetch_counts()
     dt = (time.perf_counter() - t0) / K
-    ref = Engine(0)
-    exp = C.run_engine(ref, case, entries, flags, 0.8, q, s, n_samples=n_samples)[0]
+    ref = Engine(ctx.local)
+    ref.set_tree(case.ft.parent, 0)
+    ref.set_plan(kinds, flags, 0.8, n_samples, case.NF)
+    ref.set_subjects(tab, case.sub_node)
+    ref.classify_chunk(q, s, None, None, 0)
+    exp = ref.fetch_counts()
     ref.close()
     eng.close()
     return {'value': m / dt, 'unit': UNIT, 'records': int(m),
@@ -248,361 +405,218 @@ def text_e2e(case, entries, flags, q, s, n_samples, m=2_000_000):
                    'wk_fetch_counts (text in pinned host memory, H2D inside)'}
 
 
-def run_reference(args):
-    """CPU arm: the oracle port of the reference's path, all host threads."""
-    rank = int(os.environ.get('RANK', '0'))
-    if rank != 0:
-        return
-    from oracle import oracle as O
-    threads = host_threads()
-    n = min(args.records, args.cpu_sample)
-    if args.workload == 'cfg3':
-        return run_reference_cfg3(args, threads)
-    if args.workload == 'cfg5':
-        return run_reference_cfg5(args, threads)
-    args_records = args.records
-    args.records = n
-    case, entries, flags, q, s, nq = make_cfg2(args, 'cpu', 1002)
-    args.records = args_records
-    q, s = q.numpy(), s.numpy()
-    kw = {}
-    if args._q_sample is not None:
-        kw = dict(n_samples=args.samples, q_sample=args._q_sample.numpy())
-    for _ in range(args.warmup):
-        cpu_classify(case, entries, flags, q, s, threads, **kw)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_classify(case, entries, flags, q, s, threads, **kw)
-    dt = time.perf_counter() - t0
-    val = n * args.steps / dt
-    line = {
-        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT,
-        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32',
-        'data': 'synthetic',
-        'config': workload_config(args, entries),
-        'cpu_baseline': {
-            'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-            'sample': f'{n} records of the same generator per step '
-                      f'(C restatement oracle/woltka_oracle.c, OpenMP)',
-            'python_port': python_port_rate(case, entries, flags, q, s)},
-        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0,
-                'd2h_bytes_per_step': 0},
-        'gpu_launches': 0,
-    }
-    print(json.dumps(line))
-
-
-def run_reference_cfg5(args, threads):
-    """CPU arm of cfg5: the C port over a bounded sample (the strata table is
-    a hash on the CPU too)."""
-    from oracle import oracle as O
-    from woltka_b200._lib import KIND_RANK
-    n = min(args.records, 5_000_000)
-    q, s, qs, qt, nq, tab, n_ko = make_cfg5(n, 1005, 'cpu')
-    T = 1 + n_ko
-    parent = np.zeros(T, dtype=np.int32)
-    node_rank = np.zeros(T, dtype=np.int32)
-    node_rank[0] = -1
-    kw = dict(parent=parent, node_rank=node_rank, root=0,
-              sub_node=tab[0].astype(np.int32), sub_feat=None,
-              kinds=np.array([KIND_RANK], dtype=np.int32), target_rank=[0],
-              flags=0, n_samples=8, n_features=T, q_sample=qs.numpy(),
-              q_stratum=qt.numpy(), n_threads=threads)
-    q, s = q.numpy(), s.numpy()
-    steps = max(1, min(args.steps, 3))
-    O.classify(q, s, **kw)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        O.classify(q, s, **kw)
-    dt = time.perf_counter() - t0
-    val = n * steps / dt
-    print(json.dumps({
-        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT,
-        'n_gpus': args.gpus, 'steps': steps, 'warmup': 1,
-        'ms_per_step': dt / steps * 1e3, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32',
-        'data': 'synthetic', 'config': workload_config(args, ['ko']),
-        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads,
-                         'kind': 'port',
-                         'sample': f'{n} records of the same generator per '
-                                   f'step (C restatement, OpenMP)'},
-        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0,
-                'd2h_bytes_per_step': 0},
-        'gpu_launches': 0}))
-
-
-def run_reference_cfg3(args, threads):
-    from oracle import oracle as O
+def bench_classify(ctx, workload, records, ranks, mode, samples, steps, warmup,
+                   full, cpu_sample, no_e2e=False, no_cpu=False):
+    """cfg2 (one sample per GPU) / cfg4 (8 contiguous samples per GPU)."""
+    torch, dist = ctx.torch, ctx.dist
     from woltka_b200 import synth
-    n = min(args.records, 1_000_000)
-    coff, gb, ge = synth.gen_genes()
-    rq, rc, rb, re_, rl, nq = synth.gen_reads(n, seed=1003)
-    cols = [x.numpy() for x in (rc, rb, re_, rl)]
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        O.ordinal_match(*cols, 0.8, coff, gb, ge)
-    dt = time.perf_counter() - t0
-    val = n * args.steps / dt
-    print(json.dumps({
-        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT,
-        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': 0,
-        'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32',
-        'data': 'synthetic', 'config': workload_config(args, ['none']),
-        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': 1,
-                         'kind': 'port',
-                         'sample': f'{n} reads, sweep matcher only'},
-        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0,
-                'd2h_bytes_per_step': 0}, 'gpu_launches': 0}))
-
-
-def workload_config(args, entries):
-    if args.workload == 'cfg5':
-        return {'workload': 'cfg5: stratified taxonomy x function: gene '
-                            'subjects (10k genomes x 500 genes), rank ko '
-                            'through a gene -> KO map (10k KOs, 60 % '
-                            'annotated), counts keyed by (genus stratum, KO), '
-                            '8 samples per GPU',
-                'records_per_gpu': args.records, 'ranks': entries,
-                'subjects': 5_000_000, 'kos': 10_000, 'genera': 3000,
-                'samples_per_gpu': 8, 'l2': 'inputs larger than L2'}
-    if args.workload == 'cfg3':
-        return {'workload': 'cfg3: coord-match ordinal profile, synthetic '
-                            'reads x 5M gene intervals over 1k contigs, '
-                            'overlap 80, rank none',
-                'records_per_gpu': args.records, 'genes': 5_000_000,
-                'contigs': 1000,
-                'l2': 'inputs larger than L2 (2 GB of columns per step)'}
-    if args.workload == 'cfg4':
-        return {'workload': 'cfg4: phylum/genus/species with multi-hit LCA '
-                            '(--above), synthetic records, 8 samples per GPU',
-                'records_per_gpu': args.records, 'ranks': entries,
-                'mode': args.mode, 'samples_per_gpu': args.samples,
-                'taxonomy_nodes': 21603, 'genomes': 10000,
-                'l2': 'inputs larger than L2'}
-    return {'workload': 'cfg2: genus-rank taxonomic classify, synthetic SAM '
-                        'records x 10k-genome / 21,603-node taxonomy',
-            'records_per_gpu': args.records, 'ranks': entries,
-            'mode': args.mode, 'taxonomy_nodes': 21603, 'genomes': 10000,
-            'l2': 'inputs larger than L2 (0.8 GB of columns per step)'}
-
-
-# ---- our arm -----------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from woltka_b200.engine import Engine, pinned_empty
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    near = None
-    if world > 1:
-        # ranks of one box: keep each rank's pinned host columns and copy
-        # threads on its GPU's NUMA node (N = 1 keeps every core for the CPU arm)
-        from woltka_b200.distributed import bind_near_gpu
-        if not os.environ.get('WK_NO_BIND'):
-            near = bind_near_gpu(local)
-        dist.init_process_group('nccl', device_id=dev)
-    args._near_cpus = len(near) if near else None
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    eng = Engine(local)
-    stream = torch.cuda.current_stream()
-    eng.set_stream(stream.cuda_stream)
-    n = args.records
-    hbm_peak, peak_src = peaks()
-
-    if args.workload == 'cfg3':
-        return run_ours_cfg3(args, eng, dev, world, rank, barrier, hbm_peak,
-                             peak_src)
-    if args.workload == 'cfg5':
-        return run_ours_cfg5(args, eng, dev, world, rank, barrier, hbm_peak,
-                             peak_src)
-
-    from tests import cases
-    case, entries, flags, q, s, nq = make_cfg2(args, dev, 1002 + rank)
+    from woltka_b200.distributed import merge_engine
+    from woltka_b200.engine import pinned_empty
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    n = records
+    case = synth.Case(synth.Taxonomy(seed=42))
+    entries = ranks.split(',')
+    flags = synth.MODES[mode]
+    seed = {'cfg2': 1002, 'cfg4': 1004}[workload] + rank
+    q, s, qs, nq = synth.gen_hits(n, seed=seed, device=dev, n_samples=samples)
     kinds, tab, _ = case.tables(entries)
     # every rank owns `samples` sample columns of one shared table
-    S_loc = args.samples
-    S_all = S_loc * world
-    qs = args._q_sample
-    if qs is not None:
-        qs = (qs + rank * S_loc).contiguous()
+    S_loc, S_all = samples, samples * world
+    qs = (qs + rank * S_loc).contiguous() if samples > 1 else None
     qs_ptr = qs.data_ptr() if qs is not None else None
     smp = 0 if qs is not None else rank * S_loc
+    eng = ctx.engine()
     eng.set_tree(case.ft.parent, 0)
     eng.set_plan(kinds, flags, 0.8, S_all, case.NF)
     eng.set_subjects(tab, case.sub_node)
     counts = eng.counts_tensor()
-    bytes_per_rec = 8
 
     def classify_dev():
         eng.classify_device(q.data_ptr(), s.data_ptr(), n, qs_ptr, None, nq,
                             smp)
 
-    def step():
+    def step(ev=None):
         eng.reset_counts()
+        if ev:
+            ev[0].record()
         classify_dev()
+        if ev:
+            ev[1].record()
         if world > 1:
+            # the merge of a job: ONE reduce of the dense units table.  The
+            # sparse part (shares 1/d, d > 16) is empty for this generator
+            # (at most 16 hits per query) - checked after the timed region.
             dist.reduce(counts, dst=0)
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    k_ev = [(torch.cuda.Event(enable_timing=True),
-             torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     l0 = eng.launch_count()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    t_beg = torch.cuda.Event(enable_timing=True)
-    t_end = torch.cuda.Event(enable_timing=True)
-    t_beg.record()
-    for i in range(args.steps):
-        eng.reset_counts()
-        k_ev[i][0].record()
-        classify_dev()
-        k_ev[i][1].record()
-        if world > 1:
-            dist.reduce(counts, dst=0)
-    t_end.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = t_beg.elapsed_time(t_end)
-    k_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    for _ in range(warmup):
+        step()
+    l0 = eng.launch_count()
+    ms, k_ms, clocks = timed_steps(ctx, steps, 0, step, clocks=full)
     launches = eng.launch_count() - l0
-    tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    value = n * world * steps / (ms * 1e-3)
+    line = base_line(ctx, workload, n, entries, mode, samples, steps, warmup,
+                     ms, value)
+    kernel = eng.last_kernel()
+
+    # ---- merged table on hardware: rank 0's table after the merge must be
+    # the sum of the tables the ranks computed on their own
+    parity_merged = None
     if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms = float(tms.item())
-    value = n * world * args.steps / (ms * 1e-3)
-    # parity of the timed configuration on a bounded sample + CPU baseline
-    final_units = eng.fetch_counts() if world == 1 else None
+        eng.reset_counts()
+        classify_dev()
+        local = eng.fetch_counts()
+        n_ovf = len(eng.fetch_overflow()[0])
+        eng.reset_counts()
+        classify_dev()
+        merge_engine(eng, dst=0, dense=True, strata=False)
+        merged = eng.fetch_counts() if rank == 0 else None
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object((local, n_ovf), parts, dst=0)
+        if rank == 0:
+            total = sum(p[0] for p in parts)
+            parity_merged = bool(np.array_equal(total, merged)) and \
+                sum(p[1] for p in parts) == len(eng.fetch_overflow()[0])
+            assert parity_merged, 'merged table differs from the sum of the ranks'
+            # the samples of the ranks are disjoint columns of one table
+            assert all(int((p[0] != 0).any(axis=(0, 2)).sum()) <= S_loc
+                       for p in parts)
+    final_units = None
+    if world == 1:
+        eng.reset_counts()
+        classify_dev()
+        final_units = eng.fetch_counts()
 
     e2e = None
-    if not args.no_e2e:
-        hq = pinned_empty(n)
-        hs = pinned_empty(n)
+    if full and not no_e2e:
+        hq, hs = pinned_empty(n), pinned_empty(n)
         hq[:] = q.cpu().numpy()
         hs[:] = s.cpu().numpy()
         hqs = None
         if qs is not None:
             hqs = pinned_empty(nq)
             hqs[:] = qs.cpu().numpy()
-        for _ in range(2):
-            eng.reset_counts()
-            eng.classify_chunk(hq, hs, hqs, None, smp)
-            res = eng.fetch_counts()
-        barrier()
-        t0 = time.perf_counter()
-        b0 = torch.cuda.Event(enable_timing=True)
-        b1 = torch.cuda.Event(enable_timing=True)
-        b0.record()
-        e2e_steps = max(3, min(args.steps, 10))
-        for _ in range(e2e_steps):
-            eng.reset_counts()
-            eng.classify_chunk(hq, hs, hqs, None, smp)      # H2D inside
-            if world > 1:
-                dist.reduce(counts, dst=0)
-            res = eng.fetch_counts()        # D2H of the count table
-        b1.record()
-        barrier()
-        ems = max(b0.elapsed_time(b1), (time.perf_counter() - t0) * 1e3)
-        tms = torch.tensor([ems], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ems = float(tms.item())
-        e2e = {'value': n * world * e2e_steps / (ems * 1e-3), 'unit': UNIT,
-               'h2d_bytes_per_step': int(2 * 4 * n + (4 * nq if hqs is not
-                                                      None else 0)),
-               'd2h_bytes_per_step': int(res.nbytes),
-               'steps': e2e_steps, 'ms_per_step': ems / e2e_steps,
-               'api': 'wk_classify_chunk(host SoA) + wk_fetch_counts'}
-        if final_units is not None:
-            assert np.array_equal(res, final_units), 'e2e != device path'
+        e2e = {}
+        for name, fn in (('soa', lambda: eng.classify_chunk(hq, hs, hqs, None, smp)),
+                         ('packed', None)):
+            if fn is None:
+                if not hasattr(eng, 'classify_packed'):
+                    continue
+                packed = eng.pack_columns(hq, hs)
+                fn = lambda: eng.classify_packed(packed, hqs, smp)  # noqa: E731
+            for _ in range(2):
+                eng.reset_counts()
+                fn()
+                res = eng.fetch_counts()
+            ctx.barrier()
+            t0 = time.perf_counter()
+            b0, b1 = ctx.event(), ctx.event()
+            b0.record()
+            e2e_steps = max(3, min(steps, 10))
+            for _ in range(e2e_steps):
+                eng.reset_counts()
+                fn()                            # H2D inside
+                if world > 1:
+                    dist.reduce(counts, dst=0)
+                res = eng.fetch_counts()        # D2H of the count table
+            b1.record()
+            ctx.barrier()
+            ems = ctx.max_over_ranks(max(b0.elapsed_time(b1),
+                                         (time.perf_counter() - t0) * 1e3))
+            if final_units is not None:
+                assert np.array_equal(res, final_units), 'e2e != device path'
+            if name == 'soa':
+                h2d = int(2 * 4 * n + (4 * nq if hqs is not None else 0))
+                api = 'wk_classify_chunk(host int32 SoA) + wk_fetch_counts'
+            else:
+                h2d = int(packed.nbytes + (4 * nq if hqs is not None else 0))
+                api = ('wk_classify_packed(host head bits + uint16 subjects) '
+                       '+ wk_fetch_counts')
+            e2e[name] = {'value': n * world * e2e_steps / (ems * 1e-3),
+                         'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                         'd2h_bytes_per_step': int(res.nbytes),
+                         'steps': e2e_steps, 'ms_per_step': ems / e2e_steps,
+                         'api': api}
+        # the headline is the north-star wire format (int32 SoA); the packed
+        # form of the same records is reported next to it
+        head = dict(e2e['soa'])
+        if 'packed' in e2e:
+            head['packed'] = e2e['packed']
+        e2e = head
 
-    cpu = None
-    parity = None
-    if rank == 0 and not args.no_cpu:
-        from oracle import oracle as O
+    cpu = parity = None
+    if rank == 0 and not no_cpu:
         threads = host_threads()
-        m = min(n, args.cpu_sample)
-        # cut the sample at a query boundary
-        qh = q[:m + 64].cpu().numpy()
+        m = min(n, cpu_sample)
+        qh = q[:m + 64].cpu().numpy()        # cut the sample at a query boundary
         sh = s[:m + 64].cpu().numpy()
         while m < len(qh) and m > 0 and qh[m] == qh[m - 1]:
             m += 1
         qh, sh = qh[:m], sh[:m]
         qsh = qs.cpu().numpy() if qs is not None else None
         kw = dict(n_samples=S_all, q_sample=qsh, sample=smp)
-        (eu, eo, _), dt = cpu_classify(case, entries, flags, qh, sh, threads,
-                                       **kw)
-        (_, _, _), dt1 = cpu_classify(case, entries, flags, qh[:m // 8],
-                                      sh[:m // 8], 1, **kw)
-        eng.reset_counts()
-        eng.classify_chunk(qh, sh, qsh, None, smp)
-        gu, go, _ = cases.collect(eng, S_all, case.NF)
+        (eu, eo, _), dt = oracle_classify(case, entries, flags, qh, sh, threads,
+                                          **kw)
+        e2 = ctx.engine()
+        e2.set_tree(case.ft.parent, 0)
+        e2.set_plan(kinds, flags, 0.8, S_all, case.NF)
+        e2.set_subjects(tab, case.sub_node)
+        e2.classify_chunk(qh, sh, qsh, None, smp)
+        gu, go, _ = collect(e2, S_all, case.NF)
+        e2.close()
         parity = bool(np.array_equal(gu, eu)) and go == eo
-        cpu = {'value': m / dt, 'unit': UNIT, 'cores': threads,
-               'kind': 'port',
-               'sample': f'{m} records of the timed batch, C restatement '
-                         f'of the reference path (oracle/woltka_oracle.c), '
-                         f'{threads} OpenMP threads',
-               'single_thread_value': (m // 8) / dt1,
-               'python_port': python_port_rate(case, entries, flags, qh, sh)}
         assert parity, 'GPU result differs from the oracle on the sample'
+        if full:
+            (_, _, _), dt1 = oracle_classify(case, entries, flags, qh[:m // 8],
+                                             sh[:m // 8], 1, **kw)
+            cpu = {'value': m / dt, 'unit': UNIT, 'cores': threads,
+                   'kind': 'port',
+                   'sample': f'{m} records of the timed batch, C restatement '
+                             f'of the reference path (oracle/woltka_oracle.c), '
+                             f'{threads} OpenMP threads',
+                   'single_thread_value': (m // 8) / dt1,
+                   'python_port': python_port_rate(case, entries, flags, qh, sh)}
 
     text = None
-    if rank == 0 and world == 1 and not args.no_e2e and qs is None:
-        text = text_e2e(case, entries, flags, q[:2_100_000].cpu().numpy(),
+    if full and rank == 0 and world == 1 and not no_e2e and qs is None:
+        text = text_e2e(ctx, case, entries, flags, q[:2_100_000].cpu().numpy(),
                         s[:2_100_000].cpu().numpy(), S_all)
 
-    if rank == 0:
-        achieved = bytes_per_rec * n / (k_ms * 1e-3) / 1e9
-        line = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
-            'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32',
-            'data': 'synthetic', 'config': workload_config(args, entries),
-            'roofline': {'bound': 'hbm', 'achieved': achieved,
-                         'peak': hbm_peak, 'unit': 'GB/s',
-                         'frac': achieved / hbm_peak,
-                         'traffic': measured_traffic(
-                             eng.last_kernel() + ':' + ','.join(entries) +
-                             ':' + args.mode, n),
-                         'kernel': eng.last_kernel(),
-                         'kernel_ms': k_ms, 'peak_source': peak_src,
-                         'algorithmic_bytes_per_record': bytes_per_rec},
-            'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
-            'clocks': clocks, 'parity_on_sample': parity,
-        }
-        if args._near_cpus:
-            line['cpus_bound_per_rank'] = args._near_cpus
-        if text is not None:
-            line['e2e_from_text'] = text
-        print(json.dumps(line))
+    achieved = 8 * n / (k_ms * 1e-3) / 1e9
+    line['roofline'] = {
+        'bound': 'hbm', 'achieved': achieved, 'peak': ctx.hbm_peak,
+        'unit': 'GB/s', 'frac': achieved / ctx.hbm_peak,
+        'traffic': measured_traffic(
+            kernel + ':' + ','.join(entries) + ':' + mode, n),
+        'traffic_source': 'profiles/traffic.json (ncu capture of the same '
+                          'launch, not measured in this run)',
+        'kernel': kernel, 'kernel_ms': k_ms, 'peak_source': ctx.peak_src,
+        'algorithmic_bytes_per_record': 8}
+    line.update({'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
+                 'clocks': clocks, 'parity_on_sample': parity})
     if world > 1:
-        dist.destroy_process_group()
+        line['parity_merged'] = parity_merged
+    if ctx.near:
+        line['cpus_bound_per_rank'] = len(ctx.near)
+    if text is not None:
+        line['e2e_from_text'] = text
+    eng.close()
+    del q, s, qs
+    torch.cuda.empty_cache()
+    return line
 
 
-def run_ours_cfg3(args, eng, dev, world, rank, barrier, hbm_peak, peak_src):
-    import torch
-    import torch.distributed as dist
+# ---- cfg3: coord-match --------------------------------------------------------
+def bench_cfg3(ctx, records, steps, warmup, full, no_e2e=False, no_cpu=False):
+    torch, dist = ctx.torch, ctx.dist
     from woltka_b200 import synth
     from woltka_b200._lib import KIND_NONE_ID
     from woltka_b200.engine import pinned_empty
-    n = args.records
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    n = records
     coff, gb, ge = synth.gen_genes()
     G = len(gb)
+    eng = ctx.engine()
     eng.set_plan(np.array([KIND_NONE_ID]), 0, 0.0, 1, G)
     eng.set_subjects(None, None, G)
     eng.ordinal_set_genes(coff, gb, ge, np.arange(G, dtype=np.int32))
@@ -611,45 +625,38 @@ def run_ours_cfg3(args, eng, dev, world, rank, barrier, hbm_peak, peak_src):
     ptrs = [x.data_ptr() for x in (rq, rc, rb, re_, rl)]
     counts = eng.counts_tensor()
 
-    def step():
+    def step(ev=None):
         eng.reset_counts()
+        if ev:
+            ev[0].record()
         eng.ordinal_device(ptrs, n, 0.8)
+        if ev:
+            ev[1].record()
         if world > 1:
-            dist.reduce(counts, dst=0)
+            dist.reduce(counts, dst=0)     # the ranks share one gene table
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
-    barrier()
     l0 = eng.launch_count()
-    sampler = ClockSampler(torch.cuda.current_device())
-    if rank == 0:
-        sampler.start()
-    t_beg = torch.cuda.Event(enable_timing=True)
-    t_end = torch.cuda.Event(enable_timing=True)
-    k_ev = [(torch.cuda.Event(enable_timing=True),
-             torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    t_beg.record()
-    for i in range(args.steps):
-        eng.reset_counts()
-        k_ev[i][0].record()
-        eng.ordinal_device(ptrs, n, 0.8)
-        k_ev[i][1].record()
-        if world > 1:
-            dist.reduce(counts, dst=0)
-    t_end.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = t_beg.elapsed_time(t_end)
-    k_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    ms, k_ms, clocks = timed_steps(ctx, steps, 0, step, clocks=full)
     launches = eng.launch_count() - l0
-    tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    value = n * world * steps / (ms * 1e-3)
+    line = base_line(ctx, 'cfg3', n, ['none'], None, 1, steps, warmup, ms, value)
+
+    parity_merged = None
     if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms = float(tms.item())
-    value = n * world * args.steps / (ms * 1e-3)
+        eng.reset_counts()
+        eng.ordinal_device(ptrs, n, 0.8)
+        local = eng.counts_tensor().clone()
+        step()
+        tot = local.clone()
+        dist.reduce(tot, dst=0)
+        if rank == 0:
+            parity_merged = bool(torch.equal(tot, eng.counts_tensor()))
+            assert parity_merged
 
     e2e = None
-    if not args.no_e2e:
+    if full and not no_e2e:
         host = []
         for x in (rq, rc, rb, re_, rl):
             h = pinned_empty(n)
@@ -657,7 +664,7 @@ def run_ours_cfg3(args, eng, dev, world, rank, barrier, hbm_peak, peak_src):
             host.append(h)
         eng.reset_counts()
         eng.ordinal_chunk(*host, 0.8)
-        barrier()
+        ctx.barrier()
         t0 = time.perf_counter()
         e2e_steps = 3
         for _ in range(e2e_steps):
@@ -666,56 +673,57 @@ def run_ours_cfg3(args, eng, dev, world, rank, barrier, hbm_peak, peak_src):
             if world > 1:
                 dist.reduce(counts, dst=0)
             res = eng.fetch_counts()
-        barrier()
-        ems = (time.perf_counter() - t0) * 1e3
+        ctx.barrier()
+        ems = ctx.max_over_ranks((time.perf_counter() - t0) * 1e3)
         e2e = {'value': n * world * e2e_steps / (ems * 1e-3), 'unit': UNIT,
                'h2d_bytes_per_step': int(5 * 4 * n),
                'd2h_bytes_per_step': int(res.nbytes), 'steps': e2e_steps,
                'ms_per_step': ems / e2e_steps,
                'api': 'wk_ordinal_chunk(host SoA) + wk_fetch_counts'}
+        del host
 
-    cpu = None
-    parity = None
-    if rank == 0 and not args.no_cpu:
+    cpu = parity = None
+    if rank == 0 and not no_cpu:
         from oracle import oracle as O
-        m = min(n, 1_000_000)
+        m = min(n, 1_000_000 if full else 200_000)
         c4 = [x[:m].cpu().numpy() for x in (rc, rb, re_, rl)]
         t0 = time.perf_counter()
         er, eg = O.ordinal_match(*c4, 0.8, coff, gb, ge)
         dt = time.perf_counter() - t0
-        eng.ordinal_enable_pairs()
-        eng.reset_counts()
-        eng.ordinal_chunk(rq[:m].cpu().numpy(), *c4, 0.8)
-        r, g = eng.ordinal_pairs()
+        e2 = ctx.engine()
+        e2.ordinal_set_genes(coff, gb, ge, np.arange(G, dtype=np.int32))
+        e2.ordinal_enable_pairs()
+        e2.ordinal_chunk(rq[:m].cpu().numpy(), *c4, 0.8)
+        r, g = e2.ordinal_pairs()
+        e2.close()
         parity = bool(np.array_equal(r, er) and np.array_equal(g, eg))
+        assert parity, 'GPU pairs differ from the oracle sweep on the sample'
         cpu = {'value': m / dt, 'unit': UNIT, 'cores': 1, 'kind': 'port',
                'sample': f'{m} reads of the timed batch, sweep matcher '
                          f'(ordinal.match_read_gene restated in C)'}
-        assert parity, 'GPU pairs differ from the oracle sweep on the sample'
 
-    if rank == 0:
-        alg_bytes = 20 * n + 8 * G
-        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-        print(json.dumps({
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
-            'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32',
-            'data': 'synthetic', 'config': workload_config(args, ['none']),
-            'roofline': {'bound': 'hbm', 'achieved': achieved,
-                         'peak': hbm_peak, 'unit': 'GB/s',
-                         'frac': achieved / hbm_peak,
-                         'traffic': measured_traffic('ordinal:cfg3', n),
-                         'kernel': 'ordinal_match_kernel+' + eng.last_kernel(),
-                         'kernel_ms': k_ms, 'peak_source': peak_src,
-                         'algorithmic_bytes_per_record': 20,
-                         'algorithmic_bytes_per_gene': 8},
-            'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
-            'clocks': clocks, 'parity_on_sample': parity}))
+    alg_bytes = 20 * n + 8 * G
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    line['roofline'] = {
+        'bound': 'hbm', 'achieved': achieved, 'peak': ctx.hbm_peak,
+        'unit': 'GB/s', 'frac': achieved / ctx.hbm_peak,
+        'traffic': measured_traffic('ordinal:cfg3', n),
+        'traffic_source': 'profiles/traffic.json (ncu capture, not measured '
+                          'in this run)',
+        'kernel': 'ordinal_match_kernel+' + eng.last_kernel(),
+        'kernel_ms': k_ms, 'peak_source': ctx.peak_src,
+        'algorithmic_bytes_per_record': 20, 'algorithmic_bytes_per_gene': 8}
+    line.update({'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
+                 'clocks': clocks, 'parity_on_sample': parity})
     if world > 1:
-        dist.destroy_process_group()
+        line['parity_merged'] = parity_merged
+    eng.close()
+    del rq, rc, rb, re_, rl, cols
+    torch.cuda.empty_cache()
+    return line
 
 
+# ---- cfg5: stratified ----------------------------------------------------------
 def make_cfg5(n, seed, device, n_genomes=10_000, genes_per=500, n_ko=10_000,
               n_genus=3000, n_samples=8, p=0.48, kmax=16):
     """the second pass of a stratified run.  Subjects are
@@ -755,82 +763,114 @@ def make_cfg5(n, seed, device, n_genomes=10_000, genes_per=500, n_ko=10_000,
     return q, s, q_sample, strat, nq, ko.to(torch.int32).numpy()[None, :], n_ko
 
 
-def run_ours_cfg5(args, eng, dev, world, rank, barrier, hbm_peak, peak_src):
-    import torch
-    import torch.distributed as dist
+def cells_checksum(torch, keys, units):
+    """(cells, total units, sum of mix(key) * units mod 2^64) of a strata
+    table: additive under a merge by key, so the merged table of N ranks must
+    carry the sum of their checksums."""
+    if not keys.numel():
+        return [0, 0, 0]
+    h = keys * -7046029254386353131         # 0x9E3779B97F4A7C15 as int64
+    h = h ^ (h >> 29)
+    return [int(keys.numel()), int(units.sum().item()),
+            int((h * units).sum().item())]
+
+
+def bench_cfg5(ctx, records, steps, warmup, full, no_e2e=False, no_cpu=False):
+    torch, dist = ctx.torch, ctx.dist
     from woltka_b200._lib import KIND_RANK
+    from woltka_b200.distributed import merge_engine
     from woltka_b200.engine import pinned_empty
-    n = args.records
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    n = records
     S_loc = 8
+    S_all = S_loc * world
     q, s, qs, qt, nq, tab, n_ko = make_cfg5(n, 1005 + rank, dev, n_samples=S_loc)
+    qs = (qs + rank * S_loc).contiguous()     # this rank's samples of the shared table
     T = 1 + n_ko                      # root + KOs; the genes are the subjects
     parent = np.zeros(T, dtype=np.int32)
+    eng = ctx.engine()
     eng.set_tree(parent, 0)
-    # samples are sharded: every rank owns its own 8 sample columns, so the
-    # (sample, genus, KO) cells of the ranks are disjoint - no collective
-    eng.set_plan(np.array([KIND_RANK], dtype=np.int32), 0, 0.0, S_loc, T)
+    eng.set_plan(np.array([KIND_RANK], dtype=np.int32), 0, 0.0, S_all, T)
     eng.set_subjects(tab, None)
     ptr = (q.data_ptr(), s.data_ptr(), qs.data_ptr(), qt.data_ptr())
 
     def classify_dev():
         eng.classify_device(ptr[0], ptr[1], n, ptr[2], ptr[3], nq, 0)
 
-    # the strata table keeps growing over the steps like over the chunks of a
-    # run (same keys every step); it is not cleared inside the timed region
-    for _ in range(max(args.warmup, 1)):
+    def step(ev=None):
+        # one job: empty table -> classify -> strata cells of every rank
+        # merged on rank 0 (sent over NCCL, added by key)
+        eng.reset_counts()
+        if ev:
+            ev[0].record()
         classify_dev()
-    barrier()
+        if ev:
+            ev[1].record()
+        if world > 1:
+            merge_engine(eng, dst=0, dense=False, strata=True)
+
+    for _ in range(max(warmup, 1)):
+        step()
     l0 = eng.launch_count()
-    sampler = ClockSampler(torch.cuda.current_device())
-    if rank == 0:
-        sampler.start()
-    t_beg = torch.cuda.Event(enable_timing=True)
-    t_end = torch.cuda.Event(enable_timing=True)
-    t_beg.record()
-    for i in range(args.steps):
-        classify_dev()
-    t_end.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = t_beg.elapsed_time(t_end)
+    ms, k_ms, clocks = timed_steps(ctx, steps, 0, step, clocks=full)
     launches = eng.launch_count() - l0
-    tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    value = n * world * steps / (ms * 1e-3)
+    line = base_line(ctx, 'cfg5', n, ['ko'], None, S_loc, steps, warmup, ms,
+                     value)
+
+    # merged strata table: checksum of checksums (additive under merge by key)
+    parity_merged = None
     if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms = float(tms.item())
-    k_ms = ms / args.steps
-    value = n * world * args.steps / (ms * 1e-3)
-    cells = len(eng.fetch_strata()[0])
+        eng.reset_counts()
+        classify_dev()
+        k_, u_ = eng.strata_export()
+        mine = torch.tensor(cells_checksum(torch, k_, u_), device=dev,
+                            dtype=torch.int64)
+        step()
+        tot = mine.clone()
+        dist.reduce(tot, dst=0)               # int64 wrap-around = mod 2^64
+        if rank == 0:
+            k_, u_ = eng.strata_export()
+            got = cells_checksum(torch, k_, u_)
+            # samples are disjoint over the ranks, so even the cell counts add up
+            parity_merged = got == [int(x) for x in tot.tolist()]
+            assert parity_merged, ('merged strata table', got, tot.tolist())
+    eng.reset_counts()
+    classify_dev()
+    cells = int(eng.strata_export()[0].numel())
 
     e2e = None
-    if not args.no_e2e:
+    if full and not no_e2e:
         host = []
         for x, m in ((q, n), (s, n), (qs, nq), (qt, nq)):
             h = pinned_empty(m)
             h[:] = x.cpu().numpy()
             host.append(h)
+        eng.reset_counts()
         eng.classify_chunk(*host)
-        barrier()
+        ctx.barrier()
         t0 = time.perf_counter()
         e2e_steps = 3
         for _ in range(e2e_steps):
+            eng.reset_counts()
             eng.classify_chunk(*host)
-            nc = len(eng.fetch_strata()[0])
-        barrier()
-        ems = (time.perf_counter() - t0) * 1e3
+            if world > 1:
+                merge_engine(eng, dst=0, dense=False, strata=True)
+            nc = len(eng.fetch_strata()[0]) if rank == 0 else 0
+        ctx.barrier()
+        ems = ctx.max_over_ranks((time.perf_counter() - t0) * 1e3)
         e2e = {'value': n * world * e2e_steps / (ems * 1e-3), 'unit': UNIT,
                'h2d_bytes_per_step': int(8 * n + 8 * nq),
                'd2h_bytes_per_step': int(nc * 28), 'steps': e2e_steps,
                'ms_per_step': ems / e2e_steps,
                'api': 'wk_classify_chunk(host SoA + per-query sample and '
                       'stratum) + wk_fetch_strata'}
+        del host
 
-    cpu = None
-    parity = None
-    if rank == 0 and not args.no_cpu:
+    cpu = parity = None
+    if rank == 0 and not no_cpu:
         from oracle import oracle as O
-        from woltka_b200.engine import Engine
-        m = min(n, 5_000_000)
+        m = min(n, 5_000_000 if full else 1_000_000)
         qh = q[:m + 64].cpu().numpy()
         while m < len(qh) and qh[m] == qh[m - 1]:
             m += 1
@@ -846,45 +886,104 @@ def run_ours_cfg5(args, eng, dev, world, rank, barrier, hbm_peak, peak_src):
         exp = O.classify(qh, sh, parent=parent, node_rank=node_rank, root=0,
                          sub_node=sub_node, sub_feat=None,
                          kinds=np.array([KIND_RANK], dtype=np.int32),
-                         target_rank=[0], flags=0, n_samples=S_loc,
+                         target_rank=[0], flags=0, n_samples=S_all,
                          n_features=T, q_sample=qsh, q_stratum=qth,
                          n_threads=threads)
         dt = time.perf_counter() - t0
-        from tests import cases
-        e2 = Engine(torch.cuda.current_device())
+        e2 = ctx.engine()
         e2.set_tree(parent, 0)
-        e2.set_plan(np.array([KIND_RANK], dtype=np.int32), 0, 0.0, S_loc, T)
+        e2.set_plan(np.array([KIND_RANK], dtype=np.int32), 0, 0.0, S_all, T)
         e2.set_subjects(tab, None)
         e2.classify_chunk(qh, sh, qsh, qth, 0)
-        got = cases.collect(e2, S_loc, T)
+        gu, go, (e_, s_, t_, f_, u_) = collect(e2, S_all, T)
         e2.close()
-        parity = bool(np.array_equal(got[0], exp[0]) and got[1] == exp[1] and
-                      got[2] == exp[2])
+        got = dict(zip(zip(e_.tolist(), s_.tolist(), t_.tolist(), f_.tolist()),
+                       u_.tolist()))
+        parity = bool(np.array_equal(gu, exp[0]) and go == exp[1] and
+                      got == exp[2])
+        assert parity, 'GPU strata cells differ from the oracle on the sample'
         cpu = {'value': m / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                'sample': f'{m} records of the timed batch, C restatement of '
                          f'the reference path (oracle/woltka_oracle.c), '
                          f'{threads} OpenMP threads'}
-        assert parity, 'GPU strata cells differ from the oracle on the sample'
 
-    if rank == 0:
-        achieved = 8 * n / (k_ms * 1e-3) / 1e9
-        print(json.dumps({
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
-            'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32',
-            'data': 'synthetic', 'config': workload_config(args, ['ko']),
-            'roofline': {'bound': 'hbm', 'achieved': achieved,
-                         'peak': hbm_peak, 'unit': 'GB/s',
-                         'frac': achieved / hbm_peak, 'traffic': None,
-                         'kernel': eng.last_kernel(), 'kernel_ms': k_ms,
-                         'peak_source': peak_src,
-                         'algorithmic_bytes_per_record': 8},
-            'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
-            'clocks': clocks, 'parity_on_sample': parity,
-            'strata_cells': cells}))
+    achieved = 8 * n / (k_ms * 1e-3) / 1e9
+    line['roofline'] = {
+        'bound': 'hbm', 'achieved': achieved, 'peak': ctx.hbm_peak,
+        'unit': 'GB/s', 'frac': achieved / ctx.hbm_peak,
+        'traffic': measured_traffic('classify_kernel:cfg5', n),
+        'traffic_source': 'profiles/traffic.json (ncu capture, not measured '
+                          'in this run)',
+        'kernel': eng.last_kernel(), 'kernel_ms': k_ms,
+        'peak_source': ctx.peak_src, 'algorithmic_bytes_per_record': 8}
+    line.update({'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
+                 'clocks': clocks, 'parity_on_sample': parity,
+                 'strata_cells_per_gpu': cells})
     if world > 1:
-        dist.destroy_process_group()
+        line['parity_merged'] = parity_merged
+    eng.close()
+    del q, s, qs, qt
+    torch.cuda.empty_cache()
+    return line
+
+
+def brief(line):
+    """What an `extra` entry keeps of a sub-run's line."""
+    keep = ('value', 'unit', 'n_gpus', 'steps', 'ms_per_step', 'config',
+            'roofline', 'parity_on_sample', 'parity_merged', 'gpu_launches',
+            'strata_cells_per_gpu')
+    return {k: line[k] for k in keep if k in line}
+
+
+def run_ours(args):
+    ctx = Ctx(args)
+    wl, n = args.workload, args.records
+    kw = dict(no_e2e=args.no_e2e, no_cpu=args.no_cpu)
+    if wl == 'cfg3':
+        line = bench_cfg3(ctx, n, args.steps, args.warmup, True, **kw)
+    elif wl == 'cfg5':
+        line = bench_cfg5(ctx, n, args.steps, args.warmup, True, **kw)
+    else:
+        line = bench_classify(ctx, wl, n, args.ranks, args.mode, args.samples,
+                              args.steps, args.warmup, True, args.cpu_sample,
+                              **kw)
+        default = (wl == 'cfg2' and args.ranks == 'genus' and
+                   args.mode == 'default' and args.samples == 1 and
+                   not args.explicit_records)
+        if default and not args.no_extra:
+            # the other BASELINE.json configs at the same number of GPUs, short
+            xs, xw = max(3, min(args.steps, 5)), 3
+            extra = {}
+            extra['cfg4'] = brief(bench_classify(
+                ctx, 'cfg4', DEFAULT_RECORDS['cfg4'], 'phylum,genus,species',
+                'above', 8, xs, xw, False, 2_000_000, no_cpu=args.no_cpu))
+            extra['cfg4_major80'] = brief(bench_classify(
+                ctx, 'cfg4', DEFAULT_RECORDS['cfg4'], 'phylum,genus,species',
+                'major', 8, xs, xw, False, 2_000_000, no_cpu=args.no_cpu))
+            extra['cfg5'] = brief(bench_cfg5(
+                ctx, DEFAULT_RECORDS['cfg5'], xs, xw, False,
+                no_cpu=args.no_cpu))
+            extra['cfg3'] = brief(bench_cfg3(
+                ctx, DEFAULT_RECORDS['cfg3'], xs, xw, False,
+                no_cpu=args.no_cpu))
+            line['extra'] = extra
+    if ctx.rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+
+
+# ---- reference arm ---------------------------------------------------------------
+def run_reference(args):
+    """CPU arm on rank 0: the reference's own `woltka.workflow.classify()`
+    (baseline/_ref or /root/reference, when importable) on the box's host
+    cores - single process and one process per core with a dict merge, its
+    documented scale-out (doc/perform.md:70-92) - else the C port."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from baseline import reference_arm
+    print(json.dumps(reference_arm.run(args, METRIC, UNIT, workload_config,
+                                       host_threads(), cpu_model())))
 
 
 def main():

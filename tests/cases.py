@@ -4,54 +4,7 @@ import numpy as np
 from woltka_b200 import synth
 from woltka_b200._lib import (KIND_NONE, KIND_FREE, KIND_RANK, KIND_NONE_ID,
                               F_UNIQ, F_ABOVE, F_MAJOR, F_UNASSIGNED)
-from woltka_b200.hierarchy import FlatTree
-
-
-class Case:
-    """A classify problem in the integer world of include/woltka_b200.h."""
-
-    def __init__(self, tax, n_extra=0, internal_subjects=0, seed=0):
-        # subjects: every genome, then `internal_subjects` internal nodes,
-        # then `n_extra` subjects that are not in the tree
-        rng = np.random.default_rng(seed)
-        self.tax = tax
-        self.ft = FlatTree.from_arrays(tax.parent, tax.node_rank,
-                                       tax.rank_names, tax.level_off)
-        T = tax.T
-        g = np.arange(tax.n_genomes, dtype=np.int32) + tax.genome_node0
-        inner = rng.integers(0, tax.genome_node0, internal_subjects,
-                             dtype=np.int32)
-        self.sub_node = np.concatenate(
-            [g, inner, np.full(n_extra, -1, dtype=np.int32)]).astype(np.int32)
-        self.sub_feat = self.sub_node.copy()
-        self.sub_feat[self.sub_node < 0] = T + np.arange(n_extra)
-        self.V = len(self.sub_node)
-        self.NF = T + n_extra
-
-    def tables(self, entries, subok=False):
-        """entries: list of 'none' | 'free' | rank name -> (kinds, tab, trk)"""
-        kinds, rows, trk = [], [], []
-        for e in entries:
-            if e == 'none':
-                kinds.append(KIND_NONE)
-                rows.append(self.sub_feat)
-                trk.append(0)
-            elif e == 'free':
-                kinds.append(KIND_FREE)
-                par = np.where(self.sub_node >= 0,
-                               self.ft.parent[np.maximum(self.sub_node, 0)],
-                               -1)
-                rows.append(self.sub_feat if subok else par)
-                trk.append(0)
-            else:
-                kinds.append(KIND_RANK)
-                anc = self.ft.anc_at_rank(e)
-                rows.append(np.where(self.sub_node >= 0,
-                                     anc[np.maximum(self.sub_node, 0)], -1))
-                trk.append(self.ft.rank_id(e))
-        return (np.array(kinds, dtype=np.int32),
-                np.stack(rows).astype(np.int32),
-                np.array(trk, dtype=np.int32))
+from woltka_b200.synth import Case, MODES  # noqa: F401  (the bench uses them too)
 
 
 def random_hits(case, n_qry, seed, kmax=16, p=0.48, long_every=0,
@@ -71,17 +24,6 @@ def random_hits(case, n_qry, seed, kmax=16, p=0.48, long_every=0,
     dup = (rng.random(n) < 0.05) & (pos > 0)
     s = np.where(dup, np.roll(s, 1), s)
     return q, s.astype(np.int32)
-
-
-MODES = {
-    'default': 0,
-    'uniq': F_UNIQ,
-    'above': F_ABOVE,
-    'major': F_MAJOR,
-    'uniq+unassigned': F_UNIQ | F_UNASSIGNED,
-    'major+unassigned': F_MAJOR | F_UNASSIGNED,
-    'above+unassigned': F_ABOVE | F_UNASSIGNED,
-}
 
 
 def run_engine(eng, case, entries, flags, major_th, q, s, n_samples=1,

@@ -203,3 +203,71 @@ def reads_as_sam(fp, qidx, contig, beg, length, contig_name='C%d',
               pos=(np.asarray(beg) + 1).tolist(),
               cigar=['150M' if ln == 150 else '70M2D78M2S'
                      for ln in np.asarray(length).tolist()])
+
+
+# ---- a classify problem in the integer world of include/woltka_b200.h -------
+# (shared by bench.py, the GPU parity tests and smoke())
+from ._lib import (KIND_NONE, KIND_FREE, KIND_RANK, F_UNIQ, F_ABOVE,  # noqa: E402
+                   F_MAJOR, F_UNASSIGNED)
+from .hierarchy import FlatTree  # noqa: E402
+
+
+class Case:
+    """A classify problem in the integer world of include/woltka_b200.h."""
+
+    def __init__(self, tax, n_extra=0, internal_subjects=0, seed=0):
+        # subjects: every genome, then `internal_subjects` internal nodes,
+        # then `n_extra` subjects that are not in the tree
+        rng = np.random.default_rng(seed)
+        self.tax = tax
+        self.ft = FlatTree.from_arrays(tax.parent, tax.node_rank,
+                                       tax.rank_names, tax.level_off)
+        T = tax.T
+        g = np.arange(tax.n_genomes, dtype=np.int32) + tax.genome_node0
+        inner = rng.integers(0, tax.genome_node0, internal_subjects,
+                             dtype=np.int32)
+        self.sub_node = np.concatenate(
+            [g, inner, np.full(n_extra, -1, dtype=np.int32)]).astype(np.int32)
+        self.sub_feat = self.sub_node.copy()
+        self.sub_feat[self.sub_node < 0] = T + np.arange(n_extra)
+        self.V = len(self.sub_node)
+        self.NF = T + n_extra
+
+    def tables(self, entries, subok=False):
+        """entries: list of 'none' | 'free' | rank name -> (kinds, tab, trk)"""
+        kinds, rows, trk = [], [], []
+        for e in entries:
+            if e == 'none':
+                kinds.append(KIND_NONE)
+                rows.append(self.sub_feat)
+                trk.append(0)
+            elif e == 'free':
+                kinds.append(KIND_FREE)
+                par = np.where(self.sub_node >= 0,
+                               self.ft.parent[np.maximum(self.sub_node, 0)],
+                               -1)
+                rows.append(self.sub_feat if subok else par)
+                trk.append(0)
+            else:
+                kinds.append(KIND_RANK)
+                anc = self.ft.anc_at_rank(e)
+                rows.append(np.where(self.sub_node >= 0,
+                                     anc[np.maximum(self.sub_node, 0)], -1))
+                trk.append(self.ft.rank_id(e))
+        return (np.array(kinds, dtype=np.int32),
+                np.stack(rows).astype(np.int32),
+                np.array(trk, dtype=np.int32))
+
+
+
+MODES = {
+    'default': 0,
+    'uniq': F_UNIQ,
+    'above': F_ABOVE,
+    'major': F_MAJOR,
+    'uniq+unassigned': F_UNIQ | F_UNASSIGNED,
+    'major+unassigned': F_MAJOR | F_UNASSIGNED,
+    'above+unassigned': F_ABOVE | F_UNASSIGNED,
+}
+
+
