@@ -150,7 +150,11 @@ def _nccl_merge_worker(rank, world, port, out):
     case = cases.Case(tax, n_extra=10, internal_subjects=20, seed=3)
     # long queries of 17 and 19 distinct subjects: shares that go to the
     # overflow list; strata on every query
-    q, s = cases.random_hits(case, 40000, seed=5, kmax=19, p=0.2)
+    q, s = cases.random_hits(case, 40000, seed=5, long_every=997, long_len=17)
+    k = np.bincount(q)
+    pos = np.arange(len(q)) - (np.cumsum(k) - k)[q]
+    long = k[q] == 17          # 17 distinct subjects: shares of 1/17
+    s[long] = ((q[long] * 7 + pos[long]) % case.V).astype(np.int32)
     nq = int(q.max()) + 1
     rng = np.random.default_rng(1)
     q_sample = np.sort(rng.integers(0, 4, nq)).astype(np.int32)

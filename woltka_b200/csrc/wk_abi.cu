@@ -91,10 +91,15 @@ __global__ void fill_u64_kernel(ull *p, size_t n, ull v) {
 
 __global__ void rehash_kernel(const ull *ok, const ull *ov, uint64_t ocap,
                               ClsParams P) {
+  __shared__ uint32_t made;
+  if (threadIdx.x == 0) made = 0;
+  __syncthreads();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t st = (size_t)gridDim.x * blockDim.x;
   for (; i < ocap; i += st)
-    if (ok[2 * i] != ~0ull) strat_add(P, ok[2 * i], ov[2 * i]);
+    if (ok[2 * i] != ~0ull) strat_add(P, ok[2 * i], ov[2 * i], smem_u32(&made));
+  __syncthreads();
+  if (threadIdx.x == 0 && made) atomicAdd(P.sh_used, (ull)made);
 }
 
 // empty strata slots: key = all ones, units = 0
@@ -118,9 +123,33 @@ __global__ void compact_hash_kernel(const ull *k, const ull *v, uint64_t cap,
 
 // add n (key, units) cells into the strata hash (merge of another rank's table)
 __global__ void import_cells_kernel(const ull *k, const ull *v, int64_t n, ClsParams P) {
+  __shared__ uint32_t made;
+  if (threadIdx.x == 0) made = 0;
+  __syncthreads();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t st = (int64_t)gridDim.x * blockDim.x;
-  for (; i < n; i += st) strat_add(P, k[i], v[i]);
+  for (; i < n; i += st) strat_add(P, k[i], v[i], smem_u32(&made));
+  __syncthreads();
+  if (threadIdx.x == 0 && made) atomicAdd(P.sh_used, (ull)made);
+}
+
+// live cells of the strata table as five columns (wk_fetch_strata)
+__global__ void unpack_cells_kernel(const ull *k, const ull *v, uint64_t cap, int64_t NF,
+                                    int32_t *entry, int32_t *sample, int32_t *stratum,
+                                    int64_t *feature, int64_t *units, ull *cursor) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t st = (size_t)gridDim.x * blockDim.x;
+  for (; i < cap; i += st) {
+    const ull key = k[2 * i];
+    if (key == ~0ull) continue;
+    const ull at = atomicAdd(cursor, 1ull);
+    stratum[at] = (int32_t)(key >> 43);
+    entry[at] = (int32_t)((key >> 40) & 7);
+    sample[at] = (int32_t)((key >> 24) & 0xFFFF);
+    const uint32_t f24 = (uint32_t)(key & KEY_F24);
+    feature[at] = f24 == KEY_F24 ? NF : (int64_t)f24;
+    units[at] = (int64_t)v[2 * i];
+  }
 }
 
 // copy [E][oS][oNF1] into [E][nS][nNF1]; the Unassigned column moves last
@@ -186,6 +215,9 @@ struct wk_ctx {
   int64_t cov_n = 0, cov_cap = 0;
   DevBuf longlist;  // classify_seg_kernel: [0] = count, then first records of long queries
   DevBuf exp_k, exp_v;  // wk_strata_export_device: compacted (key, units)
+  DevBuf sp_k[2], sp_v[2];  // spill lists of the strata table (strat_add)
+  uint64_t sp_cap[2] = {0, 0};
+  DevBuf unp;           // wk_fetch_strata: unpacked columns
   DevBuf ovf_key, ovf_den, small;  // small: [0]=ovf_n [1]=sh_used [2]=n_pairs [3]=cursor, err after
   int64_t ovf_cap = 0;
   // strata hash
@@ -223,6 +255,7 @@ struct wk_ctx {
   ull *d_sh_used() { return small.as<ull>() + 1; }
   ull *d_n_pairs() { return small.as<ull>() + 2; }
   ull *d_cursor() { return small.as<ull>() + 3; }
+  ull *d_sp_n(int w) { return small.as<ull>() + 5 + w; }
   int32_t *d_err() { return reinterpret_cast<int32_t *>(small.as<ull>() + 4); }
 };
 
@@ -395,7 +428,8 @@ int wk_destroy(wk_ctx *c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   DevBuf *bufs[] = {&c->parent, &c->cnt, &c->tab, &c->tab16, &c->sub_node,
-                    &c->ovf_key, &c->ovf_den, &c->small, &c->exp_k, &c->exp_v, &c->longlist, &c->cov_keys, &c->cov_ends, &c->sh_keys,
+                    &c->ovf_key, &c->ovf_den, &c->small, &c->exp_k, &c->exp_v, &c->sp_k[0], &c->sp_k[1],
+                    &c->sp_v[0], &c->sp_v[1], &c->unp, &c->longlist, &c->cov_keys, &c->cov_ends, &c->sh_keys,
                     &c->sh_vals, &c->dq, &c->ds, &c->dqsamp, &c->dqstrat,
                     &c->scratch, &c->dcontig, &c->dbeg, &c->dend, &c->dlen,
                     &c->cinfo, &c->genes, &c->pair_q, &c->pair_s, &c->pair_r,
@@ -702,14 +736,20 @@ static int check_plan_ready(wk_ctx *c, bool strata) {
   return WK_OK;
 }
 
-static int ensure_strata(wk_ctx *c, int64_t new_keys_bound) {
-  ull used = 0;
-  if (c->sh_cap) {
-    CK(cudaMemcpyAsync(&used, c->d_sh_used(), 8, cudaMemcpyDeviceToHost,
-                       c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-  }
-  uint64_t need = 2 * (used + (uint64_t)new_keys_bound) + 1024;
+static void strata_params(wk_ctx *c, ClsParams &P, int spill) {
+  P.sh_keys = c->sh_keys.as<ull>();
+  P.sh_vals = c->sh_keys.as<ull>() + 1;
+  P.sh_mask = c->sh_cap ? c->sh_cap - 1 : 0;
+  P.sh_used = c->d_sh_used();
+  P.sp_n = c->d_sp_n(spill);
+  P.sp_keys = c->sp_k[spill].as<ull>();
+  P.sp_vals = c->sp_v[spill].as<ull>();
+  P.sp_cap = c->sp_cap[spill];
+  P.err = c->d_err();
+}
+
+// a table of at least `need` slots (a power of two); the cells move over
+static int grow_strata(wk_ctx *c, uint64_t need) {
   if (need <= c->sh_cap) return WK_OK;
   uint64_t ncap = 1 << 16;
   while (ncap < need) ncap <<= 1;
@@ -724,17 +764,56 @@ static int ensure_strata(wk_ctx *c, int64_t new_keys_bound) {
     CK(cudaMemsetAsync(c->d_sh_used(), 0, 8, c->stream));
     ClsParams P;
     memset(&P, 0, sizeof P);
-    P.sh_keys = nk.as<ull>();
-    P.sh_vals = nk.as<ull>() + 1;
-    P.sh_mask = ncap - 1;
-    P.sh_used = c->d_sh_used();
-    P.err = c->d_err();
+    strata_params(c, P, 1);  // (cannot spill: the new table is at most half full)
     int grid = (int)std::min<uint64_t>((ocap + 255) / 256, (uint64_t)c->sm_count * 8);
     rehash_kernel<<<grid, 256, 0, c->stream>>>(ok.as<ull>(), ok.as<ull>() + 1, ocap, P);
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
     ok.release();
+  }
+  return WK_OK;
+}
+
+// Cells the last kernels could not place (strat_add): grow the table, add them.
+static int resolve_spill(wk_ctx *c, ull *used_out = nullptr) {
+  for (int w = 0;; w ^= 1) {
+    ull hv[2] = {0, 0};
+    CK(cudaMemcpyAsync(&hv[0], c->d_sh_used(), 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&hv[1], c->d_sp_n(w), 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (used_out) *used_out = hv[0];
+    if (!hv[1]) return WK_OK;
+    const ull n = std::min<ull>(hv[1], c->sp_cap[w]);
+    TRY(grow_strata(c, 2 * (hv[0] + n) + 1024));
+    // the other list takes what still does not fit (practically nothing)
+    TRY(c->sp_k[w ^ 1].reserve(n * 8 + 64));
+    TRY(c->sp_v[w ^ 1].reserve(n * 8 + 64));
+    c->sp_cap[w ^ 1] = n;
+    CK(cudaMemsetAsync(c->d_sp_n(w ^ 1), 0, 8, c->stream));
+    ClsParams P;
+    memset(&P, 0, sizeof P);
+    strata_params(c, P, w ^ 1);
+    int grid = (int)std::min<ull>((n + 255) / 256, (ull)c->sm_count * 8);
+    import_cells_kernel<<<grid, 256, 0, c->stream>>>(c->sp_k[w].as<ull>(), c->sp_v[w].as<ull>(),
+                                                    (int64_t)n, P);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(c->d_sp_n(w), 0, 8, c->stream));
+  }
+}
+
+// Room for a chunk that creates at most `bound` cells.  The table is sized for
+// bound / denom new cells (a chunk of n records rarely makes n new cells);
+// what does not fit goes to the spill list, which always can hold `bound`.
+static int ensure_strata(wk_ctx *c, int64_t bound, int denom = 4) {
+  ull used = 0;
+  TRY(resolve_spill(c, &used));
+  TRY(grow_strata(c, 2 * (used + (uint64_t)bound / (uint64_t)denom) + 1024));
+  if ((uint64_t)bound > c->sp_cap[0]) {
+    TRY(c->sp_k[0].reserve((size_t)bound * 8 + 64));
+    TRY(c->sp_v[0].reserve((size_t)bound * 8 + 64));
+    c->sp_cap[0] = (uint64_t)bound;
   }
   return WK_OK;
 }
@@ -915,11 +994,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
   P.ovf_key = c->ovf_key.as<int64_t>();
   P.ovf_den = c->ovf_den.as<int32_t>();
   P.ovf_cap = c->ovf_cap;
-  P.sh_keys = c->sh_keys.as<ull>();
-  P.sh_vals = c->sh_keys.as<ull>() + 1;
-  P.sh_mask = c->sh_cap ? c->sh_cap - 1 : 0;
-  P.sh_used = c->d_sh_used();
-  P.err = c->d_err();
+  strata_params(c, P, 0);
   P.assign = nullptr;
   if (c->want_assign && !n_dev) {
     TRY(c->assign.reserve((size_t)c->E * (size_t)std::max<int64_t>(n_bound, 1) * 4));
@@ -1751,41 +1826,35 @@ int wk_fetch_strata(wk_ctx *c, int64_t *n, int32_t *entry, int32_t *sample,
   if (!c->have_plan) return fail(WK_ERR_STATE, "no plan set");
   TRY(use_device(c));
   ull used = 0;
-  if (c->sh_cap) {
-    CK(cudaMemcpyAsync(&used, c->d_sh_used(), 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-  }
+  if (c->sh_cap) TRY(resolve_spill(c, &used));
   *n = (int64_t)used;
   if (!entry) return WK_OK;
   if (!sample || !stratum || !feature || !units)
     return fail(WK_ERR_ARG, "output arrays are NULL");
   if (cap < (int64_t)used) return fail(WK_ERR_CAPACITY, "strata output too small");
   if (!used) return WK_OK;
-  DevBuf ok, ov;
-  TRY(ok.reserve(used * 8));
-  TRY(ov.reserve(used * 8));
+  // unpack on the device into five columns, then one copy per column straight
+  // into the caller's arrays (at full rate when they are pinned, wk_host_alloc)
+  const size_t m = (size_t)used;
+  const size_t o_e = 0, o_s = m * 4, o_t = m * 8, o_f = (m * 12 + 7) & ~(size_t)7,
+               o_u = o_f + m * 8;
+  TRY(c->unp.reserve(o_u + m * 8));
+  char *base = c->unp.as<char>();
   CK(cudaMemsetAsync(c->d_cursor(), 0, 8, c->stream));
   int grid = (int)std::min<uint64_t>((c->sh_cap + 255) / 256, (uint64_t)c->sm_count * 8);
-  compact_hash_kernel<<<grid, 256, 0, c->stream>>>(
-      c->sh_keys.as<ull>(), c->sh_keys.as<ull>() + 1, c->sh_cap, ok.as<ull>(),
-      ov.as<ull>(), c->d_cursor());
+  unpack_cells_kernel<<<grid, 256, 0, c->stream>>>(
+      c->sh_keys.as<ull>(), c->sh_keys.as<ull>() + 1, c->sh_cap, c->NF,
+      reinterpret_cast<int32_t *>(base + o_e), reinterpret_cast<int32_t *>(base + o_s),
+      reinterpret_cast<int32_t *>(base + o_t), reinterpret_cast<int64_t *>(base + o_f),
+      reinterpret_cast<int64_t *>(base + o_u), c->d_cursor());
   c->launches++;
   CK(cudaGetLastError());
-  std::vector<ull> hk(used), hv(used);
-  CK(cudaMemcpyAsync(hk.data(), ok.p, used * 8, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(hv.data(), ov.p, used * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(entry, base + o_e, m * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(sample, base + o_s, m * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(stratum, base + o_t, m * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(feature, base + o_f, m * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(units, base + o_u, m * 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  ok.release();
-  ov.release();
-  for (ull i = 0; i < used; ++i) {
-    ull key = hk[i];
-    stratum[i] = (int32_t)(key >> 43);
-    entry[i] = (int32_t)((key >> 40) & 7);
-    sample[i] = (int32_t)((key >> 24) & 0xFFFF);
-    uint32_t f24 = (uint32_t)(key & KEY_F24);
-    feature[i] = f24 == KEY_F24 ? c->NF : (int64_t)f24;
-    units[i] = (int64_t)hv[i];
-  }
   return WK_OK;
 }
 
@@ -2252,10 +2321,7 @@ int wk_strata_export_device(wk_ctx *c, void **d_keys, void **d_units, int64_t *n
   if (!c->have_plan) return fail(WK_ERR_STATE, "no plan set");
   TRY(use_device(c));
   ull used = 0;
-  if (c->sh_cap) {
-    CK(cudaMemcpyAsync(&used, c->d_sh_used(), 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-  }
+  if (c->sh_cap) TRY(resolve_spill(c, &used));
   *n = (int64_t)used;
   TRY(c->exp_k.reserve(std::max<ull>(used, 1) * 8));
   TRY(c->exp_v.reserve(std::max<ull>(used, 1) * 8));
@@ -2277,14 +2343,10 @@ int wk_strata_import_device(wk_ctx *c, const void *d_keys, const void *d_units, 
   if (!c->have_plan) return fail(WK_ERR_STATE, "no plan set");
   TRY(use_device(c));
   if (!n) return WK_OK;
-  TRY(ensure_strata(c, n));
+  TRY(ensure_strata(c, n, 1));  // cells of another rank: mostly new ones
   ClsParams P;
   memset(&P, 0, sizeof P);
-  P.sh_keys = c->sh_keys.as<ull>();
-  P.sh_vals = c->sh_keys.as<ull>() + 1;
-  P.sh_mask = c->sh_cap - 1;
-  P.sh_used = c->d_sh_used();
-  P.err = c->d_err();
+  strata_params(c, P, 0);
   int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->sm_count * 8);
   import_cells_kernel<<<grid, 256, 0, c->stream>>>(static_cast<const ull *>(d_keys),
                                                   static_cast<const ull *>(d_units), n, P);

@@ -87,6 +87,8 @@ struct ClsParams {
   ull *sh_keys, *sh_vals;     // strata hash (open addressing): slot i = {sh_keys[2i], sh_vals[2i]}, sh_vals = sh_keys + 1
   uint64_t sh_mask;
   ull *sh_used;
+  ull *sp_n, *sp_keys, *sp_vals;  // spill list: cells that found no slot within SH_PROBES
+  uint64_t sp_cap;
   int32_t *err;               // device error word (bit flags)
   int32_t *scratch;           // [>= n] long-query scratch
   int32_t *assign;            // optional per-record assignment [E][stride]
@@ -195,20 +197,32 @@ struct Sink {
   uint32_t a1;   // HASHED: low words
   int sh;        // HASHED: 32 - log2(slots)
   int cur;       // DIRECT: the sample the CTA's private table belongs to
+  uint32_t ins;  // shared-memory counter of the strata cells this CTA created (0 = none)
 };
 
+// One (key, units) contribution to the strata table: open addressing, linear
+// probing, a slot is 16 bytes (key, then units: one DRAM sector per emission).
+// The table is sized for the cells EXPECTED, not for the worst case: a cell
+// that finds no slot within SH_PROBES goes to the spill list (sized for the
+// worst case), which the host adds after growing the table.  New cells are
+// counted per CTA in shared memory (`ins`), one global add per CTA at the end:
+// a global counter bumped by every insert serialises the whole kernel on one
+// L2 address.
+constexpr int SH_PROBES = 96;
 __device__ __forceinline__ void strat_add(const ClsParams &P, ull key,
-                                          ull units) {
+                                          ull units, uint32_t ins) {
   ull h = key * 0x9E3779B97F4A7C15ull;
   h ^= h >> 29;
   uint64_t i = h & P.sh_mask;
-  // a slot is 16 bytes: key, then units — one DRAM sector per emission
-  for (uint64_t probe = 0; probe <= P.sh_mask; ++probe) {
+  for (int probe = 0; probe < SH_PROBES; ++probe) {
     ull k0 = P.sh_keys[2 * i];
     if (k0 == ~0ull) {
       k0 = atomicCAS(&P.sh_keys[2 * i], ~0ull, key);
       if (k0 == ~0ull) {
-        atomicAdd(P.sh_used, 1ull);
+        if (ins)
+          atoms_add(ins, 1u);
+        else
+          atomicAdd(P.sh_used, 1ull);
         k0 = key;
       }
     }
@@ -218,7 +232,13 @@ __device__ __forceinline__ void strat_add(const ClsParams &P, ull key,
     }
     i = (i + 1) & P.sh_mask;
   }
-  atomicOr(P.err, ERR_HASH_FULL);
+  const ull at = atomicAdd(P.sp_n, 1ull);
+  if (at < P.sp_cap) {
+    P.sp_keys[at] = key;
+    P.sp_vals[at] = units;
+  } else {
+    atomicOr(P.err, ERR_HASH_FULL);
+  }
 }
 
 // Capacity-independent keys of the strata hash and of the overflow list (the
@@ -276,7 +296,7 @@ __device__ __forceinline__ void emit_units(const ClsParams &P, const Sink &K,
       return;
     }
   } else if (P.q_stratum || (P.flags & WK_F_SIZES)) {
-    strat_add(P, pack_strat(P, strat, e, samp, f), units);
+    strat_add(P, pack_strat(P, strat, e, samp, f), units, K.ins);
     return;
   }
   atomicAdd(&P.cnt[cell], (ull)units);
@@ -682,6 +702,8 @@ __global__ void __launch_bounds__(CLS_NT, 1)
     }
   }
   const uint32_t prop_addr = bars + 64;  // DIRECT: sample proposed for the table
+  K.ins = bars + 72;                     // strata cells created by this CTA
+  if (tid == 0) sts32(K.ins, 0u);
   K.cur = P.q_sample ? -1 : P.sample;
   if (SINK == SINK_DIRECT) {
     for (uint32_t h = tid; h < sink_words; h += CLS_NT) sts32(K.a0 + h * 4, 0);
@@ -987,8 +1009,12 @@ __global__ void __launch_bounds__(CLS_NT, 1)
   }
 
   // write the CTA's partial counts back (util.sum_dict, util.py:78-94)
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t made = (uint32_t)lds32(K.ins);
+    if (made) atomicAdd(P.sh_used, (ull)made);
+  }
   if (SINK != SINK_GLOBAL) {
-    __syncthreads();
     if (SINK == SINK_DIRECT) {
       flush_direct();
     } else {

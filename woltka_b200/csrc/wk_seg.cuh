@@ -400,6 +400,7 @@ __global__ void __launch_bounds__(128)
   K.a0 = K.a1 = 0;
   K.sh = 0;
   K.cur = -1;
+  K.ins = 0;
   for (ull i = (ull)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += GW)
     process_long<false, SINK_GLOBAL>(P, K, 0u, n_rec, (int64_t)P.long_list[1 + i], lane);
 }

@@ -532,6 +532,7 @@ __global__ void __launch_bounds__(SW_NT, 1)
         K.a0 = K.a1 = 0;
         K.sh = 0;
         K.cur = -1;
+        K.ins = 0;
         while (lm) {
           const int src = __ffs(lm) - 1;
           lm &= lm - 1;

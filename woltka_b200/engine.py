@@ -238,21 +238,27 @@ class Engine:
         return cell, strat, den
 
     def fetch_strata(self):
-        """(entry, sample, stratum, feature, units) arrays."""
+        """(entry, sample, stratum, feature, units) arrays.  Large results
+        land in page-locked buffers the engine keeps (D2H at full PCIe rate);
+        the arrays are views of them, valid until the next fetch_strata()."""
         n = C.c_int64()
         _lib.check(self.lib.wk_fetch_strata(self.ctx, C.byref(n), None, None,
                                             None, None, None, 0))
         m = n.value
-        e = np.empty(m, dtype=np.int32)
-        s = np.empty(m, dtype=np.int32)
-        t = np.empty(m, dtype=np.int32)
-        f = np.empty(m, dtype=np.int64)
-        u = np.empty(m, dtype=np.int64)
+        spec = (('e', np.int32), ('s', np.int32), ('t', np.int32),
+                ('f', np.int64), ('u', np.int64))
+        if m >= (1 << 20):
+            pin = getattr(self, '_pin', None)
+            if pin is None or len(pin['e']) < m:
+                cap = m + m // 8
+                pin = self._pin = {k: pinned_empty(cap, dt) for k, dt in spec}
+            out = [pin[k][:m] for k, _ in spec]
+        else:
+            out = [np.empty(m, dtype=dt) for _, dt in spec]
         if m:
             _lib.check(self.lib.wk_fetch_strata(
-                self.ctx, C.byref(n), _ptr(e), _ptr(s), _ptr(t), _ptr(f),
-                _ptr(u), m))
-        return e, s, t, f, u
+                self.ctx, C.byref(n), *[_ptr(x) for x in out], m))
+        return tuple(out)
 
     def set_assign_output(self, enable=True):
         _lib.check(self.lib.wk_set_assign_output(self.ctx, int(enable)))
