@@ -848,6 +848,7 @@ def bench_cfg5(ctx, records, steps, warmup, full, no_e2e=False, no_cpu=False):
             host.append(h)
         eng.reset_counts()
         eng.classify_chunk(*host)
+        eng.fetch_strata()          # (the engine pins its result buffers once)
         ctx.barrier()
         t0 = time.perf_counter()
         e2e_steps = 3

@@ -143,6 +143,16 @@ int wk_set_subjects(wk_ctx *ctx, const int32_t *tab, const int32_t *sub_node,
 int wk_classify_chunk(wk_ctx *ctx, const int32_t *qidx, const int32_t *sidx,
                       int64_t n_rec, const int32_t *q_sample,
                       const int32_t *q_stratum, int64_t n_qry, int32_t sample);
+/* The same chunk in the compact wire format (2.125 bytes per record over PCIe
+ * instead of 8): the kernels only ask whether q[i] != q[i+1], so the query
+ * column travels as ONE bit per record — bit i of head_bits (bit i % 64 of
+ * word i / 64) is set when record i starts a query; record 0 always does —
+ * and the subject column as uint16 (subj_bytes = 2) or uint32 (4).  The int32
+ * columns are rebuilt on the device (q = ordinal of the query in the chunk,
+ * which is also the index into q_sample / q_stratum). */
+int wk_classify_packed(wk_ctx *ctx, const uint64_t *head_bits, const void *subj,
+                       int subj_bytes, int64_t n_rec, const int32_t *q_sample,
+                       const int32_t *q_stratum, int64_t n_qry, int32_t sample);
 /* Same, columns already resident in device memory (16-byte aligned).  The
  * call is asynchronous on the context stream. */
 int wk_classify_device(wk_ctx *ctx, const int32_t *d_qidx,

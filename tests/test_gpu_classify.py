@@ -505,3 +505,39 @@ def test_host_chunk_in_sub_chunks(engine, small_case, knobs, sub, noseg):
               cases.run_oracle(small_case, ent, fl, 0.8, q, s))
         assert engine.last_kernel() == (
             'classify_fast_kernel' if noseg else _lean_kernel(ent, mode))
+
+
+@pytest.mark.parametrize('sub', [0, 64, 192, 4096])
+def test_packed_wire_format(engine, small_case, knobs, sub):
+    """wk_classify_packed: head bits + uint16 / uint32 subjects expanded on
+    the device must give what the int32 SoA columns give — with sub-chunks
+    that cut queries (also queries longer than two sub-chunks), a per-query
+    sample column, and an out-of-range subject reported as an error."""
+    from woltka_b200.engine import Engine
+    if sub:
+        knobs.set('cls_sub', sub)
+    q, s = cases.random_hits(small_case, 3000, seed=sub + 1, kmax=31, p=0.3,
+                             long_every=211, long_len=300, window=6)
+    # query ids with gaps and in no order: only q[i] != q[i+1] matters
+    ids = np.random.default_rng(2).permutation(10 * (int(q.max()) + 1))
+    nq = int(q.max()) + 1
+    q_sample = (np.arange(nq) * 3 // nq).astype(np.int32)
+    for ent, mode in ((['genus'], 'default'), (['none'], 'uniq+unassigned'),
+                      (['phylum', 'genus', 'species'], 'above'),
+                      (['species'], 'major')):
+        fl = cases.MODES[mode]
+        ref = cases.run_engine(engine, small_case, ent, fl, 0.8, q, s,
+                               n_samples=3, q_sample=q_sample)
+        for wide in (False, True):
+            packed = Engine.pack_columns(ids[q].astype(np.int32), s)
+            if wide:
+                packed.subj = packed.subj.astype(np.uint32)
+            engine.reset_counts()
+            engine.classify_packed(packed, q_sample, 0)
+            _same(cases.collect(engine, 3, small_case.NF), ref)
+    engine.reset_counts()
+    bad = Engine.pack_columns(q, np.where(np.arange(len(s)) == 77,
+                                          small_case.V + 5, s))
+    with pytest.raises(Exception, match='subject index'):
+        engine.classify_packed(bad, q_sample, 0)
+    engine.classify_packed(Engine.pack_columns(q[:0], s[:0]), None, 0)  # empty

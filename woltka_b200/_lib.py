@@ -42,6 +42,8 @@ SIGNATURES = {
     'wk_set_subjects': (C.c_int, [_vp, _vp, _vp, C.c_int64]),
     'wk_classify_chunk': (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, _vp,
                                     C.c_int64, C.c_int32]),
+    'wk_classify_packed': (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int64, _vp,
+                                     _vp, C.c_int64, C.c_int32]),
     'wk_classify_device': (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, _vp,
                                      C.c_int64, C.c_int32]),
     'wk_ordinal_set_genes': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32,

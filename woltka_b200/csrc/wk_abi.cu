@@ -20,6 +20,7 @@
 #include "wk_cover.cuh"
 #include "wk_sweep.cuh"
 #include "wk_parse.cuh"
+#include "wk_packed.cuh"
 
 using namespace wk;
 
@@ -225,6 +226,7 @@ struct wk_ctx {
   uint64_t sh_cap = 0;
   // staging for host chunks
   DevBuf dq, ds, dqsamp, dqstrat, scratch;
+  DevBuf pk_bits, pk_subj, pk_blk, pk_run;  // packed wire format (wk_packed.cuh)
   DevBuf dcontig, dbeg, dend, dlen;
   // ordinal
   DevBuf cinfo, genes;  // genes buffer = [genes | bin_first | gene_subject]
@@ -430,7 +432,7 @@ int wk_destroy(wk_ctx *c) {
   DevBuf *bufs[] = {&c->parent, &c->cnt, &c->tab, &c->tab16, &c->sub_node,
                     &c->ovf_key, &c->ovf_den, &c->small, &c->exp_k, &c->exp_v, &c->sp_k[0], &c->sp_k[1],
                     &c->sp_v[0], &c->sp_v[1], &c->unp, &c->longlist, &c->cov_keys, &c->cov_ends, &c->sh_keys,
-                    &c->sh_vals, &c->dq, &c->ds, &c->dqsamp, &c->dqstrat,
+                    &c->sh_vals, &c->dq, &c->ds, &c->dqsamp, &c->dqstrat, &c->pk_bits, &c->pk_subj, &c->pk_blk, &c->pk_run,
                     &c->scratch, &c->dcontig, &c->dbeg, &c->dend, &c->dlen,
                     &c->cinfo, &c->genes, &c->pair_q, &c->pair_s, &c->pair_r,
                     &c->pair_g, &c->tile_desc, &c->ticket, &c->assign, &c->seglist,
@@ -1474,6 +1476,97 @@ int wk_classify_chunk(wk_ctx *c, const int32_t *qidx, const int32_t *sidx,
     cudaStreamWaitEvent(c->stream, evs[jn], 0);
     rc = launch_classify(c, c->dq.as<int32_t>(), c->ds.as<int32_t>(), nread,
                          nullptr, n_rec, a, b, dqs, dqt, sample);
+  }
+  int rc2 = rc == WK_OK ? check_device_err(c) : rc;
+  cudaStreamSynchronize(c->copy_stream);
+  for (auto &e : evs)
+    if (e) cudaEventDestroy(e);
+  return rc2;
+}
+
+int wk_classify_packed(wk_ctx *c, const uint64_t *head_bits, const void *subj,
+                       int subj_bytes, int64_t n_rec, const int32_t *q_sample,
+                       const int32_t *q_stratum, int64_t n_qry, int32_t sample) {
+  TRY(check_plan_ready(c, q_stratum != nullptr));
+  TRY(use_device(c));
+  if (n_rec < 0 || (n_rec && (!head_bits || !subj)))
+    return fail(WK_ERR_ARG, "bad packed columns");
+  if (subj_bytes != 2 && subj_bytes != 4)
+    return fail(WK_ERR_ARG, "subj_bytes must be 2 (uint16) or 4 (uint32)");
+  if (!q_sample && (sample < 0 || sample >= c->S))
+    return fail(WK_ERR_ARG, "sample %d out of range", sample);
+  if (n_rec == 0) return WK_OK;
+  if (q_stratum || (c->flags & WK_F_SIZES)) TRY(ensure_strata(c, n_rec * c->E));
+  const int64_t n_words = (n_rec + 63) / 64;
+  TRY(c->dq.reserve((size_t)n_rec * 4 + 64));
+  TRY(c->ds.reserve((size_t)n_rec * 4 + 64));
+  TRY(c->pk_bits.reserve((size_t)n_words * 8 + 64));
+  TRY(c->pk_subj.reserve((size_t)n_rec * subj_bytes + 64));
+  const int32_t *dqs, *dqt;
+  TRY(upload_per_query(c, q_sample, q_stratum, n_qry, &dqs, &dqt));
+  // H2D in sub-chunks on the copy stream (2.125 or 4.125 bytes per record); the
+  // compute stream expands sub-chunk j + 1 into the int32 columns, then
+  // classifies sub-chunk j (a query may run into the next one).
+  int64_t SUB = 8ll << 20;
+  if (c->opt_cls_sub > 0) SUB = std::max<int64_t>(64, c->opt_cls_sub & ~63ll);
+  const int64_t nsub = (n_rec + SUB - 1) / SUB;
+  const int nb_max = (int)((SUB / 64 + PK_WORDS - 1) / PK_WORDS);
+  TRY(c->pk_blk.reserve((size_t)nb_max * 4 * 2 + 64));
+  TRY(c->pk_run.reserve(16));
+  CK(cudaMemsetAsync(c->pk_run.p, 0, 8, c->stream));
+  CK(cudaEventRecord(c->ev_free, c->stream));
+  CK(cudaStreamWaitEvent(c->copy_stream, c->ev_free, 0));
+  std::vector<cudaEvent_t> evs((size_t)nsub);
+  const char *hs = static_cast<const char *>(subj);
+  for (int64_t j = 0; j < nsub; ++j) {
+    const int64_t a = j * SUB, b = std::min(n_rec, a + SUB);
+    const int64_t wa = a / 64, wb = (b + 63) / 64;
+    CK(cudaMemcpyAsync(c->pk_bits.as<uint64_t>() + wa, head_bits + wa, (size_t)(wb - wa) * 8,
+                       cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaMemcpyAsync(c->pk_subj.as<char>() + a * subj_bytes, hs + a * subj_bytes,
+                       (size_t)(b - a) * subj_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaEventCreateWithFlags(&evs[(size_t)j], cudaEventDisableTiming));
+    CK(cudaEventRecord(evs[(size_t)j], c->copy_stream));
+  }
+  auto expand = [&](int64_t j) -> int {
+    const int64_t a = j * SUB, b = std::min(n_rec, a + SUB);
+    const int64_t wa = a / 64, nw = (b + 63) / 64 - wa;
+    const int nb = (int)((nw + PK_WORDS - 1) / PK_WORDS);
+    int32_t *blk = c->pk_blk.as<int32_t>() + (j & 1) * nb_max;
+    const unsigned long long *bits = c->pk_bits.as<unsigned long long>();
+    CK(cudaStreamWaitEvent(c->stream, evs[(size_t)j], 0));
+    pk_count_kernel<<<nb, PK_NT, 0, c->stream>>>(bits, wa, nw, blk);
+    pk_scan_kernel<<<1, 32, 0, c->stream>>>(blk, nb, c->pk_run.as<long long>());
+    if (subj_bytes == 2)
+      pk_expand_kernel<uint16_t><<<nb, PK_NT, 0, c->stream>>>(
+          bits, c->pk_subj.as<uint16_t>(), wa, nw, b, blk, c->dq.as<int32_t>(),
+          c->ds.as<int32_t>());
+    else
+      pk_expand_kernel<uint32_t><<<nb, PK_NT, 0, c->stream>>>(
+          bits, c->pk_subj.as<uint32_t>(), wa, nw, b, blk, c->dq.as<int32_t>(),
+          c->ds.as<int32_t>());
+    c->launches += 3;
+    CK(cudaGetLastError());
+    return WK_OK;
+  };
+  // a sub-chunk without any head continues a query longer than a sub-chunk:
+  // everything is expanded before the first classify launch then
+  bool all_first = false;
+  for (int64_t j = 1; j + 1 < nsub && !all_first; ++j) {
+    bool any = false;
+    for (int64_t w = j * SUB / 64; w < (j + 1) * SUB / 64 && !any; ++w) any = head_bits[w] != 0;
+    all_first = !any;
+  }
+  int rc = expand(0);
+  if (all_first)
+    for (int64_t j = 1; j < nsub && rc == WK_OK; ++j) rc = expand(j);
+  for (int64_t j = 0; j < nsub && rc == WK_OK; ++j) {
+    const int64_t a = j * SUB, b = std::min(n_rec, a + SUB);
+    if (j + 1 < nsub && !all_first) rc = expand(j + 1);
+    const int64_t nread = all_first ? n_rec : std::min(n_rec, (j + 2) * SUB);
+    if (rc == WK_OK)
+      rc = launch_classify(c, c->dq.as<int32_t>(), c->ds.as<int32_t>(), nread, nullptr, n_rec,
+                           a, b, dqs, dqt, sample);
   }
   int rc2 = rc == WK_OK ? check_device_err(c) : rc;
   cudaStreamSynchronize(c->copy_stream);

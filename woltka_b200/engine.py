@@ -70,6 +70,18 @@ class _PinnedArray(np.ndarray):
             self._owner = getattr(obj, '_owner', None)
 
 
+class PackedChunk:
+    """A chunk in the compact wire format: head bits (uint64 words) and
+    subjects (uint16 / uint32)."""
+
+    def __init__(self, bits, subj, n):
+        self.bits, self.subj, self.n = bits, subj, n
+
+    @property
+    def nbytes(self):
+        return (self.n + 63) // 64 * 8 + self.n * self.subj.dtype.itemsize
+
+
 class Engine:
     """One wk_ctx (one GPU)."""
 
@@ -164,6 +176,37 @@ class Engine:
                     len(q_stratum) if q_stratum is not None else 0)
         _lib.check(self.lib.wk_classify_chunk(
             self.ctx, _ptr(qidx), _ptr(sidx), len(qidx), _ptr(q_sample),
+            _ptr(q_stratum), n_qry, sample))
+
+    @staticmethod
+    def pack_columns(qidx, sidx, pinned=True):
+        """The compact wire format of a chunk (wk_classify_packed): one head
+        bit per record and the subjects as uint16 (uint32 when an index needs
+        it), in page-locked memory."""
+        qidx, sidx = np.asarray(qidx), np.asarray(sidx)
+        n = len(qidx)
+        heads = np.empty(n, dtype=bool)
+        if n:
+            heads[0] = True
+            np.not_equal(qidx[1:], qidx[:-1], out=heads[1:])
+        packed = np.packbits(heads, bitorder='little')
+        words = (n + 63) // 64
+        alloc = pinned_empty if pinned else (lambda k, dt: np.empty(k, dtype=dt))
+        bits = alloc(max(words, 1), np.uint64)
+        bits[:] = 0
+        bits.view(np.uint8)[:len(packed)] = packed
+        dt = np.uint16 if (not n or int(sidx.max()) < 65536) else np.uint32
+        subj = alloc(max(n, 1), dt)
+        subj[:n] = sidx
+        return PackedChunk(bits, subj, n)
+
+    def classify_packed(self, packed, q_sample=None, sample=0, q_stratum=None):
+        q_sample, q_stratum = _i32(q_sample), _i32(q_stratum)
+        n_qry = max(len(q_sample) if q_sample is not None else 0,
+                    len(q_stratum) if q_stratum is not None else 0)
+        _lib.check(self.lib.wk_classify_packed(
+            self.ctx, _ptr(packed.bits), _ptr(packed.subj),
+            packed.subj.dtype.itemsize, packed.n, _ptr(q_sample),
             _ptr(q_stratum), n_qry, sample))
 
     def classify_device(self, d_qidx, d_sidx, n_rec, d_q_sample=None,
