@@ -537,11 +537,12 @@ def bench_classify(ctx, workload, records, ranks, mode, samples, steps, warmup,
                          'd2h_bytes_per_step': int(res.nbytes),
                          'steps': e2e_steps, 'ms_per_step': ems / e2e_steps,
                          'api': api}
-        # the headline is the north-star wire format (int32 SoA); the packed
-        # form of the same records is reported next to it
-        head = dict(e2e['soa'])
+        # the headline is the wire format the host layer (woltka_b200.session)
+        # sends: head bits + uint16 subjects; the int32 SoA entry point of the
+        # north star is reported next to it
+        head = dict(e2e['packed'] if 'packed' in e2e else e2e['soa'])
         if 'packed' in e2e:
-            head['packed'] = e2e['packed']
+            head['int32_soa'] = e2e['soa']
         e2e = head
 
     cpu = parity = None

@@ -315,6 +315,9 @@ def test_which_kernel_runs(engine, small_case):
     strat = np.zeros(nq, dtype=np.int32)
     cases.run_engine(engine, small_case, ['genus'], 0, 0, q, s,
                      q_stratum=strat, q_sample=np.zeros(nq, dtype=np.int32))
+    assert engine.last_kernel() == 'classify_strata_kernel'
+    cases.run_engine(engine, small_case, ['genus'], cases.MODES['major'], 0.8,
+                     q, s, q_stratum=strat, q_sample=np.zeros(nq, dtype=np.int32))
     assert engine.last_kernel() == 'classify_kernel'
     engine.set_tuning(0, 1, 0)
     try:
@@ -541,3 +544,37 @@ def test_packed_wire_format(engine, small_case, knobs, sub):
     with pytest.raises(Exception, match='subject index'):
         engine.classify_packed(bad, q_sample, 0)
     engine.classify_packed(Engine.pack_columns(q[:0], s[:0]), None, 0)  # empty
+
+
+@pytest.mark.parametrize('gtab', [0, 1])
+@pytest.mark.parametrize('entries', [['genus'], ['none'], ['species', 'genus']])
+def test_stratified_one_kind_plans(engine, small_case, knobs, entries, gtab):
+    """classify_strata_kernel (counts keyed by the query's stratum,
+    classify.counter_strat classify.py:216-249): interleaved samples, queries
+    without a stratum, dropped samples, 17 distinct hits (shares of 1/17 go to
+    the overflow list), queries longer than a window, several chunks; table
+    staged in shared memory or read through L2."""
+    knobs.set('strata_gtab', gtab)
+    q, s = cases.random_hits(small_case, 30000, seed=31 + gtab, long_every=997,
+                             long_len=17)
+    k = np.bincount(q)
+    pos = np.arange(len(q)) - (np.cumsum(k) - k)[q]
+    lng = k[q] == 17
+    s[lng] = ((q[lng] * 7 + pos[lng]) % small_case.V).astype(np.int32)
+    q2, s2 = cases.random_hits(small_case, 2000, seed=5, long_every=301, long_len=70)
+    q = np.concatenate([q, q2 + int(q.max()) + 1])
+    s = np.concatenate([s, s2])
+    nq = int(q.max()) + 1
+    rng = np.random.default_rng(9)
+    q_sample = rng.integers(-1, 4, nq).astype(np.int32)
+    q_stratum = rng.integers(-1, 40, nq).astype(np.int32)
+    for mode in ('default', 'uniq', 'uniq+unassigned'):
+        fl = cases.MODES[mode]
+        ref = cases.run_oracle(small_case, entries, fl, 0, q, s, n_samples=4,
+                               q_sample=q_sample, q_stratum=q_stratum)
+        assert ref[2] and (mode != 'default' or ref[1])
+        for chunks in (1, 5):
+            _same(cases.run_engine(engine, small_case, entries, fl, 0, q, s,
+                                   n_samples=4, q_sample=q_sample,
+                                   q_stratum=q_stratum, chunks=chunks), ref)
+            assert engine.last_kernel() == 'classify_strata_kernel'

@@ -17,6 +17,7 @@
 #include "wk_ordinal.cuh"
 #include "wk_seg.cuh"
 #include "wk_multi.cuh"
+#include "wk_strata.cuh"
 #include "wk_cover.cuh"
 #include "wk_sweep.cuh"
 #include "wk_parse.cuh"
@@ -209,7 +210,7 @@ struct wk_ctx {
   int32_t sn16_off = -1, par16_off = -1, stage_elems = 0, stage_vmax = -1;
   int32_t n_levels = 0, level_off[40];
   bool minmax_ok = false;  // --above through min / max index (classify_multi_kernel)
-  int opt_no_multi = 0;
+  int opt_no_multi = 0, opt_strata_gtab = 0;
   std::vector<int64_t> dir_lo, dir_hi;  // per entry: range of the table values
   // overflow + err
   DevBuf cov_keys, cov_ends;  // coverage store (wk_cover.cuh)
@@ -414,6 +415,18 @@ int wk_create(int device, wk_ctx **out) {
     for (const void *fn : multi)
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)c->smem_optin));
+#define WK_STV(KD, MD)                                                   \
+  (const void *)classify_strata_kernel<KD, MD, false, false>,            \
+      (const void *)classify_strata_kernel<KD, MD, false, true>,         \
+      (const void *)classify_strata_kernel<KD, MD, true, false>,         \
+      (const void *)classify_strata_kernel<KD, MD, true, true>
+    const void *strata[] = {WK_STV(WK_KIND_RANK, FX_FRAC), WK_STV(WK_KIND_RANK, FX_UNIQ),
+                            WK_STV(WK_KIND_NONE, FX_FRAC), WK_STV(WK_KIND_NONE, FX_UNIQ),
+                            WK_STV(WK_KIND_NONE_ID, FX_FRAC), WK_STV(WK_KIND_NONE_ID, FX_UNIQ)};
+#undef WK_STV
+    for (const void *fn : strata)
+      CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)c->smem_optin));
     for (const void *fn : fast)
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)c->smem_optin));
@@ -484,6 +497,7 @@ int wk_set_option(wk_ctx *c, const char *name, int64_t value) {
   if (k == "no_seg") c->opt_no_seg = (int)value;
   else if (k == "no_fast") c->opt_no_fast = (int)value;
   else if (k == "no_multi") c->opt_no_multi = (int)value;
+  else if (k == "strata_gtab") c->opt_strata_gtab = (int)value;
   else if (k == "sweep_r") c->opt_sweep_r = (int)value;
   else if (k == "seg_wt") c->opt_seg_wt = (int)value;
   else if (k == "ord_nowin") c->opt_ord_nowin = (int)value;
@@ -1305,6 +1319,60 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
     }
   }
 
+  // ---- stratified plans of one kind in default / --uniq mode: the
+  // lane-per-record kernel with the strata hash as its sink (wk_strata.cuh)
+  {
+    const bool rk = c->kind[0] == WK_KIND_RANK;
+    const bool lca_mode = rk && (c->flags & (WK_F_MAJOR | WK_F_ABOVE));
+    const int64_t span = r1 - (r0 & ~3ll);
+    if (dqstrat && !sizes && !P.assign && !n_dev && c->tune_block != 1 && !c->opt_no_seg &&
+        same_kind && !lca_mode && P.V > 0 && P.V <= (1 << 24) && span > 0 &&
+        span < (1ll << 31) - (1 << 20) && (wide || c->tab.p)) {
+      // the table from shared memory when it fits next to the tiles, else from L2
+      const bool gtab = wide || !c->tab16_ok || c->opt_strata_gtab ||
+                        sg_layout(SG_NT / 32, 512, 0u, (int64_t)c->Vp * 2).total > c->smem_optin;
+      const SgSmemLayout SL = sg_layout(SG_NT / 32, 512, 0u, gtab ? 0 : (int64_t)c->Vp * 2);
+      TRY(c->longlist.reserve((size_t)(span / 33 + 4) * 8));
+      P.long_list = c->longlist.as<ull>();
+      const int64_t ft = (span + 511) / 512;
+      const int sgrid = (int)std::min<int64_t>(grid, (ft + SG_NT / 32 - 1) / (SG_NT / 32));
+      const bool un = (c->flags & WK_F_UNASSIGNED) != 0;
+      const bool uq = (c->flags & WK_F_UNIQ) != 0;
+      for (int e = 0; e < c->E; ++e) {
+        P.e_lo = e;
+        P.e_hi = e + 1;
+        CK(cudaMemsetAsync(P.long_list, 0, 8, c->stream));
+#define WK_ST3(KD, MD, GT)                                                                  \
+  do {                                                                                      \
+    if (un) classify_strata_kernel<KD, MD, GT, true><<<sgrid, SG_NT, SL.total, c->stream>>>(P);  \
+    else classify_strata_kernel<KD, MD, GT, false><<<sgrid, SG_NT, SL.total, c->stream>>>(P);    \
+  } while (0)
+#define WK_ST2(KD, MD)               \
+  do {                               \
+    if (gtab) WK_ST3(KD, MD, true);  \
+    else WK_ST3(KD, MD, false);      \
+  } while (0)
+#define WK_ST1(KD)                        \
+  do {                                    \
+    if (uq) WK_ST2(KD, FX_UNIQ);          \
+    else WK_ST2(KD, FX_FRAC);             \
+  } while (0)
+        if (rk) WK_ST1(WK_KIND_RANK);
+        else if (wide) WK_ST1(WK_KIND_NONE_ID);
+        else WK_ST1(WK_KIND_NONE);
+#undef WK_ST1
+#undef WK_ST2
+#undef WK_ST3
+        seg_long_kernel<<<c->sm_count, 128, 0, c->stream>>>(P);
+        c->launches += 2;
+        CK(cudaGetLastError());
+      }
+      P.e_lo = 0;
+      P.e_hi = c->E;
+      c->last_kernel = "classify_strata_kernel";
+      return WK_OK;
+    }
+  }
 window_kernel:
   const int64_t tab_bytes = staged ? (int64_t)c->stage_elems * 2 : 0;
   // where counts are accumulated first (wk_classify.cuh, "count sinks")

@@ -275,8 +275,16 @@ class Session:
         q_sample = np.asarray(q_sample, dtype=np.int32)
         q_stratum = np.asarray(q_stratum, dtype=np.int32) \
             if use_strata and not sized_strata else None
+        packed = None
         for eng in self.engines:
-            eng.classify_chunk(q, s, q_sample, q_stratum)
+            if hasattr(eng, 'classify_packed') and self.rank2dir is None:
+                # the compact wire format: one head bit per record + uint16 /
+                # uint32 subjects (wk_classify_packed)
+                if packed is None:
+                    packed = eng.pack_columns(q, s, pinned=False)
+                eng.classify_packed(packed, q_sample, 0, q_stratum)
+            else:
+                eng.classify_chunk(q, s, q_sample, q_stratum)
         if self.rank2dir is not None:
             starts.append(len(q))
             self._write_readmaps(len(q), reads, starts, q_sample)
