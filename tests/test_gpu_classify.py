@@ -390,7 +390,7 @@ def test_cfg5_shape_gene_to_ko_stratified_by_genus(engine):
                      n_threads=4)
     _same(got, exp)
     assert len(got[2]) > 10000          # (sample, genus, KO) cells
-    assert engine.last_kernel() == 'classify_kernel'
+    assert engine.last_kernel() == 'classify_strata_kernel'
 
 
 @pytest.mark.parametrize('r', ['5', '9'])

@@ -793,7 +793,7 @@ static int grow_strata(wk_ctx *c, uint64_t need) {
 
 // Cells the last kernels could not place (strat_add): grow the table, add them.
 static int resolve_spill(wk_ctx *c, ull *used_out = nullptr) {
-  for (int w = 0;; w ^= 1) {
+  for (int w = 0, pass = 0;; w ^= 1, ++pass) {
     ull hv[2] = {0, 0};
     CK(cudaMemcpyAsync(&hv[0], c->d_sh_used(), 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(&hv[1], c->d_sp_n(w), 8, cudaMemcpyDeviceToHost, c->stream));
@@ -801,7 +801,8 @@ static int resolve_spill(wk_ctx *c, ull *used_out = nullptr) {
     if (used_out) *used_out = hv[0];
     if (!hv[1]) return WK_OK;
     const ull n = std::min<ull>(hv[1], c->sp_cap[w]);
-    TRY(grow_strata(c, 2 * (hv[0] + n) + 1024));
+    // cells that spill again (long probe chains): every further pass doubles the table
+    TRY(grow_strata(c, std::max<uint64_t>(2 * (hv[0] + n) + 1024, pass ? 2 * c->sh_cap : 0)));
     // the other list takes what still does not fit (practically nothing)
     TRY(c->sp_k[w ^ 1].reserve(n * 8 + 64));
     TRY(c->sp_v[w ^ 1].reserve(n * 8 + 64));
