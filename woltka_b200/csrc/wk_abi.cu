@@ -1168,7 +1168,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
         WTe[e] = 0;
         for (int wt : {512, 256})
           if (!WTe[e] && !(wt == 512 && c->opt_seg_wt == 256) &&
-              sg_layout(SG_NT / 32, wt, ce, wide ? 0 : (int64_t)c->Vp * 2).total <=
+              sg_layout(SG_NT / 32, wt, ce + 32u, wide ? 0 : (int64_t)c->Vp * 2).total <=
                   c->smem_optin)
             WTe[e] = wt;
         fits = WTe[e] != 0;
@@ -1196,8 +1196,10 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
           P.e_lo = e;
           P.e_hi = e + 1;
           const int WT = WTe[e];
+          // (+ 32 spare words: one per lane for the branch-free emission)
           const SgSmemLayout GL = sg_layout(
-              SG_NT / 32, WT, gsink ? 0u : (uint32_t)(P.dir_base[e + 1] - P.dir_base[e]),
+              SG_NT / 32, WT,
+              (gsink ? 0u : (uint32_t)(P.dir_base[e + 1] - P.dir_base[e])) + 32u,
               wide ? 0 : (int64_t)c->Vp * 2);
           const int64_t ft = (span + WT - 1) / WT;
           const int sgrid =

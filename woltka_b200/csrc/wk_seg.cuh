@@ -34,6 +34,7 @@
 // Queries with no tail within 32 records of their head are listed and done by
 // seg_long_kernel (the warp-cooperative process_long) right after.
 #pragma once
+#include <type_traits>
 #include "wk_sweep.cuh"
 
 namespace wk {
@@ -42,6 +43,7 @@ constexpr int SG_NT = 1024;
 constexpr int SG_PRE = 4;    // records staged before the tile (>= SG_LB)
 constexpr int SG_POST = 44;  // halo after the tile (a window may start at WT-1)
 constexpr int SG_LB = 4;     // look-backs done unconditionally
+constexpr int SG_SKIP = 7;   // tiles without the unanimity probe after a tile that never used it
 constexpr uint32_t SG_BAD16 = 0xFFFEu;  // staged code of an out-of-range subject
 
 __device__ __forceinline__ uint32_t lds16w(uint32_t a) {
@@ -53,6 +55,21 @@ __device__ __forceinline__ int bfind32(unsigned v) {  // highest set bit (FLO)
   int r;
   asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v));
   return r;
+}
+// add v to the word at a unless v == 0; returns the old value (0 when skipped)
+__device__ __forceinline__ uint32_t atoms_add_if(uint32_t a, uint32_t v) {
+  uint32_t old;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.u32 p, %2, 0;\n"
+      "mov.u32 %0, 0;\n"
+      "@p atom.shared.add.u32 %0, [%1], %2;\n"
+      "}"
+      : "=r"(old)
+      : "r"(a), "r"(v)
+      : "memory");
+  return old;
 }
 __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
@@ -96,7 +113,7 @@ __global__ void __launch_bounds__(SG_NT, 1)
   const bool gsink = P.fast_gsink != 0;  // counts straight to the global table
   const uint32_t cells = gsink ? 0u : (uint32_t)(P.dir_base[e + 1] - P.dir_base[e]);
   const uint32_t rows_bytes = WIDE ? 0u : (uint32_t)P.Vp * 2u;
-  const SgSmemLayout L = sg_layout(NW, WT, cells, (int64_t)rows_bytes);
+  const SgSmemLayout L = sg_layout(NW, WT, cells + 32u, (int64_t)rows_bytes);
   const uint32_t sbase32 = smem_u32(smem);
   const uint32_t tabbar = sbase32 + L.bars + (uint32_t)NW * 8u;
   const uint32_t mybar = sbase32 + L.bars + (uint32_t)warp * 8u;
@@ -158,6 +175,8 @@ __global__ void __launch_bounds__(SG_NT, 1)
   unsigned ge = FULL << lane, le = FULL >> (31 - lane), ones = FULL;
   uint32_t r_V = V32, r_off = off, r_wid1 = wid1, r_none = c_none, r_row = row,
            r_tbl = tbl, r_usm = usm;
+  const uint32_t r_spare = tbl + (cells + (uint32_t)lane) * 4u;  // this lane's spare word
+  int probing = 1;  // > 0: windows probe for unanimity; < 0: tiles to go without
   // keep them in registers: ptxas would reload / recompute them per window
   asm volatile("" : "+r"(ge), "+r"(le), "+r"(ones), "+r"(r_V), "+r"(r_off), "+r"(r_wid1),
                "+r"(r_none), "+r"(r_row), "+r"(r_tbl), "+r"(r_usm));
@@ -244,15 +263,18 @@ __global__ void __launch_bounds__(SG_NT, 1)
         }
       };
       seek();
-#pragma unroll 1
-      while (cur < w1) {
+      int fast_hits = 0;  // windows of this tile that took the unanimity shortcut
+      // one window; CLIP: the windows of the last 32 records of the tile keep
+      // only the queries whose head lies before w1
+      auto window = [&](auto clip_tag, auto probe_tag) {
+        constexpr bool CLIP = decltype(clip_tag)::value;
+        constexpr bool PROBE = MODE == FX_UNIQ || decltype(probe_tag)::value;
         const uint32_t ax = aq + (uint32_t)(cur + lane) * 4u;
         const int qa = lds32(ax), qb = lds32(ax + 4u);
         const uint32_t sv = (uint32_t)lds32(ax + SCOL);
         const unsigned T = __ballot_sync(FULL, qa != qb);
-        // whole queries whose head lies before w1
         unsigned Tl = T;
-        if (cur >= wlast) {
+        if (CLIP) {
           const unsigned t2 = T & (FULL << (w1 - cur - 1));
           if (t2) Tl = T & (FULL >> (32 - __ffs(t2)));
         }
@@ -264,7 +286,7 @@ __global__ void __launch_bounds__(SG_NT, 1)
           }
           cur += 32;
           seek();
-          continue;
+          return;
         }
         const int tp = bfind32(Tl);               // the last whole query's tail
         const unsigned tge = Tl & ge;             // tails at or after me
@@ -275,12 +297,19 @@ __global__ void __launch_bounds__(SG_NT, 1)
         const unsigned segm = (tge ^ (tge - 1u)) & (ones << sl);
         const uint32_t svc = min(sv, r_V);
         const uint32_t code = WIDE ? sv : lds16w(r_row + svc * 2u);
-        // classify.assign_rank: all taxa equal; classify.assign_none: one subject
+        // classify.assign_rank: all taxa equal; classify.assign_none: one
+        // subject.  In default mode the probe only buys a shortcut (a window
+        // whose queries are all unanimous): a tile that never took it is
+        // followed by tiles without the probe (see below).
         const uint32_t key = KIND == WK_KIND_RANK ? code : sv;
-        const uint32_t kh = __shfl_sync(FULL, key, sl);
-        const unsigned NE = __ballot_sync(FULL, act && key != kh);
+        unsigned NE = FULL;
+        if (PROBE) {
+          const uint32_t kh = __shfl_sync(FULL, key, sl);
+          NE = __ballot_sync(FULL, act && key != kh);
+        }
         uint32_t amt, c = code;
-        if (MODE == FX_UNIQ || NE == 0) {
+        if (PROBE && (MODE == FX_UNIQ || NE == 0)) {
+          ++fast_hits;
           // every query is unanimous, or --uniq drops the others: one unit
           // from the head lane
           bool ok = WIDE || code != r_none;
@@ -336,35 +365,56 @@ __global__ void __launch_bounds__(SG_NT, 1)
             // code says so; units[0] is one unit)
             if (act && sl == lane && d == 0) amt = u;
           }
-          if (contrib && valid && u == 0u) {
-            // rare: 1/d with d not dividing WK_UNITS
-            if ((NE & segm) == 0) {
-              // all taxa equal (classify.py:107-108): the unit, whole
-              if (sl == lane) amt = (uint32_t)WK_UNITS;
-            } else {
-              const ull at = atomicAdd(P.ovf_n, 1ull);  // overflow list
-              if ((int64_t)at < P.ovf_cap) {
-                P.ovf_key[at] = (int64_t)pack_plain(P, e, sample, (int64_t)code);
-                P.ovf_den[at] = d;
+          if (maxd >= 16) {
+            // a query of 17 or more records: 1/d may not divide WK_UNITS
+            const uint32_t kh = __shfl_sync(FULL, key, sl);
+            const unsigned NE2 = __ballot_sync(FULL, act && key != kh);
+            if (contrib && valid && u == 0u) {
+              if ((NE2 & segm) == 0) {
+                // all taxa equal (classify.py:107-108): the unit, whole
+                if (sl == lane) amt = (uint32_t)WK_UNITS;
               } else {
-                atomicOr(P.err, ERR_OVF_FULL);
+                const ull at = atomicAdd(P.ovf_n, 1ull);  // overflow list
+                if ((int64_t)at < P.ovf_cap) {
+                  P.ovf_key[at] = (int64_t)pack_plain(P, e, sample, (int64_t)code);
+                  P.ovf_den[at] = d;
+                } else {
+                  atomicOr(P.err, ERR_OVF_FULL);
+                }
               }
             }
           }
         }
         {
+          // ONE shared-memory atomic per window, without a branch: a lane
+          // with nothing to add (or a value outside the private range) adds 0
+          // to its own spare word behind the table.  A carry out of the 32-bit
+          // low word and values outside the range are the rare branch.
           const uint32_t slot = c - r_off;
-          const bool inr = slot < r_wid1;
-          uint32_t old = 0u;
-          if (amt != 0u && inr) old = atoms_add(r_tbl + slot * 4u, amt);
-          if (amt != 0u && (!inr || old + amt < old)) {
-            if (inr)  // carry out of the 32-bit low word (rare)
+          const uint32_t a2 = slot < r_wid1 ? amt : 0u;
+          const uint32_t old = atoms_add(a2 ? r_tbl + slot * 4u : r_spare, a2);
+          if (amt != a2 || old + a2 < old) {
+            if (a2)
               atomicAdd(crow + (slot == wid ? (uint32_t)(P.NF1 - 1) : c), 1ull << 32);
             else
               emit_far(c, amt);
           }
         }
         cur += tp + 1;
+      };
+      if (MODE == FX_UNIQ || probing > 0) {
+#pragma unroll 1
+        while (cur < wlast) window(std::false_type(), std::true_type());
+#pragma unroll 1
+        while (cur < w1) window(std::true_type(), std::true_type());
+        // the shortcut never applied: SG_SKIP tiles without the probe
+        probing = fast_hits ? 1 : -SG_SKIP;
+      } else {
+#pragma unroll 1
+        while (cur < wlast) window(std::false_type(), std::false_type());
+#pragma unroll 1
+        while (cur < w1) window(std::true_type(), std::false_type());
+        ++probing;
       }
       __syncwarp();  // every lane is done with this stage
       if (lane == 0 && tile + GW < n_tiles) {
