@@ -97,7 +97,9 @@ int wk_set_tuning(wk_ctx *ctx, int grid, int block, int cache_slots);
  * (256); "cls_sub" / "ord_sub": records per H2D sub-chunk of the host-fed
  * calls; "ord_nowin": no persisting L2 window over the gene table; "no_multi":
  * one launch per rank instead of the all-ranks kernel; "strata_gtab": the
- * stratified kernel reads its table through L2 even when it could be staged. */
+ * stratified kernel reads its table through L2 even when it could be staged;
+ * "fuse": `--coords` at `--rank none` through the one-pass match-and-resolve
+ * kernel instead of matcher + pair counting. */
 int wk_set_option(wk_ctx *ctx, const char *name, int64_t value);
 /* Name of the classify kernel the last chunk was launched with. */
 const char *wk_last_kernel(wk_ctx *ctx);

@@ -275,6 +275,7 @@ def test_fused_match_and_count(mode, ident):
         eng = Engine(0)
         try:
             eng.set_option('ord_sub', sub)
+            eng.set_option('fuse', 1)       # (opt-in: slower than two kernels on cfg3)
             eng.set_plan(np.array([KIND_NONE_ID]), fl, 0.0, 3, NF)
             eng.set_subjects(None, None, NF)
             eng.ordinal_set_genes(coff, gb, ge, gsub)
@@ -283,7 +284,7 @@ def test_fused_match_and_count(mode, ident):
             units = eng.fetch_counts()
             ovf = eng.fetch_overflow()
             # the two-kernel route must agree too
-            eng.set_option('no_fuse', 1)
+            eng.set_option('fuse', 0)
             eng.reset_counts()
             eng.ordinal_chunk(q, c, b, e, rl, 0.5, q_sample=q_sample)
             assert eng.last_kernel() != 'ordinal_fused_kernel'

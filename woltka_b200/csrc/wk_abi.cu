@@ -211,7 +211,7 @@ struct wk_ctx {
   int32_t sn16_off = -1, par16_off = -1, stage_elems = 0, stage_vmax = -1;
   int32_t n_levels = 0, level_off[40];
   bool minmax_ok = false;  // --above through min / max index (classify_multi_kernel)
-  int opt_no_multi = 0, opt_strata_gtab = 0, opt_no_fuse = 0;
+  int opt_no_multi = 0, opt_strata_gtab = 0, opt_fuse = 0;
   std::vector<int64_t> dir_lo, dir_hi;  // per entry: range of the table values
   // overflow + err
   DevBuf cov_keys, cov_ends;  // coverage store (wk_cover.cuh)
@@ -240,6 +240,8 @@ struct wk_ctx {
   int64_t G = 0;
   int shift = 0;
   DevBuf pair_q, pair_s, pair_r, pair_g, tile_desc, ticket, seglist;
+  DevBuf con, con_n;  // ordinal_fused_kernel: per-CTA contribution lists
+  int64_t con_cap = 0;
   int64_t pair_cap = 0;
   int64_t last_pairs = 0;
   bool keep_pairs = false;
@@ -456,7 +458,7 @@ int wk_destroy(wk_ctx *c) {
                     &c->sh_vals, &c->dq, &c->ds, &c->dqsamp, &c->dqstrat, &c->pk_bits, &c->pk_subj, &c->pk_blk, &c->pk_run,
                     &c->scratch, &c->dcontig, &c->dbeg, &c->dend, &c->dlen,
                     &c->cinfo, &c->genes, &c->pair_q, &c->pair_s, &c->pair_r,
-                    &c->pair_g, &c->tile_desc, &c->ticket, &c->assign, &c->seglist,
+                    &c->pair_g, &c->tile_desc, &c->ticket, &c->assign, &c->seglist, &c->con, &c->con_n,
                     &c->p_text, &c->p_a, &c->p_b, &c->p_sums, &c->p_line_start,
                     &c->p_rec, &c->p_valid, &c->p_vpos, &c->p_vline, &c->p_ghead,
                     &c->p_slot, &c->p_phead, &c->p_qpos, &c->p_rslot, &c->p_sslot,
@@ -506,7 +508,7 @@ int wk_set_option(wk_ctx *c, const char *name, int64_t value) {
   else if (k == "no_fast") c->opt_no_fast = (int)value;
   else if (k == "no_multi") c->opt_no_multi = (int)value;
   else if (k == "strata_gtab") c->opt_strata_gtab = (int)value;
-  else if (k == "no_fuse") c->opt_no_fuse = (int)value;
+  else if (k == "fuse") c->opt_fuse = (int)value;
   else if (k == "sweep_r") c->opt_sweep_r = (int)value;
   else if (k == "seg_wt") c->opt_seg_wt = (int)value;
   else if (k == "ord_nowin") c->opt_ord_nowin = (int)value;
@@ -1752,12 +1754,14 @@ static int run_ordinal(wk_ctx *c, const int32_t *dq, const int32_t *dcontig,
     return fail(WK_ERR_ARG, "record columns must be 16-byte aligned");
   if (!copied || sub <= 0) sub = n_rec;
   const int64_t nsub = (n_rec + sub - 1) / sub;
-  // ---- the gene table of one sample stream (`--rank none`, default or --uniq):
-  // match and count in ONE kernel (wk_ordfuse.cuh); only the queries it lists
-  // (more than four genes on a read, more than 32 records) go through the pair
-  // list and the generic classify path
+  // ---- opt-in ("fuse"): the gene table of one sample stream (`--rank none`,
+  // default or --uniq) matched and resolved in ONE kernel (wk_ordfuse.cuh);
+  // only the queries it lists (more than four genes on a read, more than 32
+  // records) go through the pair list and the generic classify path.  Correct
+  // (tests/test_gpu_ordinal.py) but measured slower than the two-kernel route
+  // on cfg3 (5.5 vs 3.4 ms per 1e8 reads, profiles/README.md), hence opt-in.
   if (classify && c->E == 1 && c->kind[0] == WK_KIND_NONE_ID && !dqt &&
-      !(c->flags & WK_F_SIZES) && !c->want_assign && !c->keep_pairs && !c->opt_no_fuse &&
+      !(c->flags & WK_F_SIZES) && !c->want_assign && !c->keep_pairs && c->opt_fuse &&
       n_rec < (1ll << 31) - (1 << 20)) {
     OrdFuseParams F;
     memset(&F, 0, sizeof F);
@@ -1790,28 +1794,61 @@ static int run_ordinal(wk_ctx *c, const int32_t *dq, const int32_t *dcontig,
     TRY(c->longlist.reserve((size_t)(n_rec + 2) * 8));  // worst case: every query listed
     F.list = c->longlist.as<ull>();
     F.list_cap = n_rec;
-    CK(cudaMemsetAsync(F.list, 0, 8, c->stream));
     const OfSmemLayout FL = of_layout(SG_NT / 32);
     const bool un = (c->flags & WK_F_UNASSIGNED) != 0, uq = (c->flags & WK_F_UNIQ) != 0;
-    for (int64_t j = 0; j < nsub; ++j) {
-      const int64_t jn = all_first ? nsub - 1 : std::min(nsub - 1, j + 1);
-      if (copied) CK(cudaStreamWaitEvent(c->stream, (*copied)[(size_t)jn], 0));
-      P.r0 = j * sub;
-      P.r1 = std::min(n_rec, P.r0 + sub);
-      P.n = std::min(n_rec, (jn + 1) * sub);
-      const int64_t ft = (P.r1 - (P.r0 & ~3ll) + OF_WT - 1) / OF_WT;
-      const int grid = (int)std::min<int64_t>(c->tune_grid > 0 ? c->tune_grid : c->sm_count,
-                                              (ft + SG_NT / 32 - 1) / (SG_NT / 32));
-      if (uq) {
-        if (un) ordinal_fused_kernel<FX_UNIQ, true><<<grid, SG_NT, FL.total, c->stream>>>(F);
-        else ordinal_fused_kernel<FX_UNIQ, false><<<grid, SG_NT, FL.total, c->stream>>>(F);
-      } else {
-        if (un) ordinal_fused_kernel<FX_FRAC, true><<<grid, SG_NT, FL.total, c->stream>>>(F);
-        else ordinal_fused_kernel<FX_FRAC, false><<<grid, SG_NT, FL.total, c->stream>>>(F);
+    const int gmax = c->tune_grid > 0 ? c->tune_grid : c->sm_count;
+    if ((uint64_t)c->S * (uint64_t)(c->NF + 1) >= (1ull << 43))
+      return fail(WK_ERR_ARG, "count table too large for the fused coordinate path");
+    // contribution lists: 1.5 records per read to start with (a read matches
+    // 0.7 genes on the configs' data); a list that fills up is simply redone
+    // with the room its cursor asks for - nothing has touched the table yet
+    ull ovf0 = 0;
+    CK(cudaMemcpyAsync(&ovf0, c->d_ovf_n(), 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    int64_t want = (n_rec + gmax - 1) / gmax * 3 / 2 + 4096;
+    for (int attempt = 0;; ++attempt) {
+      if (want > c->con_cap) {
+        TRY(c->con.reserve((size_t)want * (size_t)gmax * 8));
+        c->con_cap = want;
       }
-      c->launches++;
-      CK(cudaGetLastError());
+      TRY(c->con_n.reserve((size_t)gmax * 8));
+      F.con = c->con.as<ull>();
+      F.con_n = c->con_n.as<ull>();
+      F.con_cap = c->con_cap;
+      CK(cudaMemsetAsync(F.con_n, 0, (size_t)gmax * 8, c->stream));
+      CK(cudaMemsetAsync(F.list, 0, 8, c->stream));
+      for (int64_t j = 0; j < nsub; ++j) {
+        const int64_t jn = all_first ? nsub - 1 : std::min(nsub - 1, j + 1);
+        if (copied) CK(cudaStreamWaitEvent(c->stream, (*copied)[(size_t)jn], 0));
+        P.r0 = j * sub;
+        P.r1 = std::min(n_rec, P.r0 + sub);
+        P.n = std::min(n_rec, (jn + 1) * sub);
+        const int64_t ft = (P.r1 - (P.r0 & ~3ll) + OF_WT - 1) / OF_WT;
+        const int grid = (int)std::min<int64_t>(gmax, (ft + SG_NT / 32 - 1) / (SG_NT / 32));
+        if (uq) {
+          if (un) ordinal_fused_kernel<FX_UNIQ, true><<<grid, SG_NT, FL.total, c->stream>>>(F);
+          else ordinal_fused_kernel<FX_UNIQ, false><<<grid, SG_NT, FL.total, c->stream>>>(F);
+        } else {
+          if (un) ordinal_fused_kernel<FX_FRAC, true><<<grid, SG_NT, FL.total, c->stream>>>(F);
+          else ordinal_fused_kernel<FX_FRAC, false><<<grid, SG_NT, FL.total, c->stream>>>(F);
+        }
+        c->launches++;
+        CK(cudaGetLastError());
+      }
+      std::vector<ull> filled((size_t)gmax);
+      CK(cudaMemcpyAsync(filled.data(), F.con_n, (size_t)gmax * 8, cudaMemcpyDeviceToHost,
+                         c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      const ull most = *std::max_element(filled.begin(), filled.end());
+      if ((int64_t)most <= c->con_cap) break;
+      if (attempt >= 2) return fail(WK_ERR_CAPACITY, "contribution lists could not be sized");
+      // redo the chunk with room (the overflow list goes back to where it was)
+      want = (int64_t)most + (int64_t)(most >> 4) + 4096;
+      CK(cudaMemcpyAsync(c->d_ovf_n(), &ovf0, 8, cudaMemcpyHostToDevice, c->stream));
     }
+    ordinal_apply_kernel<<<dim3(16, gmax), 256, 0, c->stream>>>(F);
+    c->launches++;
+    CK(cudaGetLastError());
     c->last_kernel = "ordinal_fused_kernel";
     // the listed queries: their pairs, then the generic classify path over them
     ull listed = 0;

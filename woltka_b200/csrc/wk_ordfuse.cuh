@@ -19,9 +19,12 @@
 //   * the genes of a query are a SET (ordinal.py:332): a lane drops a gene an
 //     earlier lane of its query already holds (shuffles over the few lanes of a
 //     query, only when two lanes' gene ranges overlap at all);
-//   * k = the genes of the query (ballots), and every gene gets 1/k straight
-//     into the units table in HBM (classify.py:165-170; --uniq: the unit if
-//     k == 1).
+//   * k = the genes of the query (ballots), and every gene gets 1/k
+//     (classify.py:165-170; --uniq: the unit if k == 1) as a (cell, units)
+//     record in the CTA's contribution list; ordinal_apply_kernel adds the
+//     records to the units table afterwards.  (Adding them here was measured
+//     at 6.4 ms per 1e8 reads: the 40 MB of the table evict the gene table
+//     from L2 — 8.3 GB of DRAM reads instead of 2.7.)
 // Queries that do not fit this picture — a read with more than four matching
 // genes, or no tail within 32 records of the head — are LISTED and done by
 // ordinal_listed_kernel (one warp per query: pairs to the pair list, which the
@@ -49,6 +52,11 @@ struct OrdFuseParams {
   int64_t ovf_cap;
   ull *list;                 // [0] = count, [1..] first record of a listed query
   int64_t list_cap;
+  // contributions: one list of (cell << 20 | units) records per CTA, con_cap
+  // records each, filled up to con_n[CTA] (may exceed con_cap: nothing beyond
+  // it is written and the host retries with room)
+  ull *con, *con_n;
+  int64_t con_cap;
 };
 
 struct OfSmemLayout {
@@ -83,6 +91,8 @@ __global__ void __launch_bounds__(SG_NT, 1)
   uint32_t aq = sbase32 + L.warp0 + (uint32_t)warp * L.warp_bytes;
   asm volatile("shfl.sync.idx.b32 %0, %0, 0, 31, 0xffffffff;" : "+r"(aq));
   const uint32_t usm = sbase32 + L.units;
+  ull *const my_cursor = F.con_n + blockIdx.x;
+  ull *const my_list = F.con + (int64_t)blockIdx.x * F.con_cap;
 
   if (lane == 0) mbar_init(mybar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -136,6 +146,75 @@ __global__ void __launch_bounds__(SG_NT, 1)
       if (w1 > nrel) w1 = nrel;
       __syncwarp();
     }
+    // ---- phase A: every record of the tile against the gene table, four
+    // records per lane in flight (the lookups are chains of dependent L2 / DRAM
+    // loads: bin -> genes; one window at a time would leave the memory system
+    // idle).  The up to four matching genes of a record replace its contig /
+    // beg / end / len slots (-1 = none; -2 in the last = more than four).
+    {
+      const int nrel = (int)(n_all - sbase < OF_TBUF ? n_all - sbase : OF_TBUF);
+      constexpr int U = 4;
+#pragma unroll 1
+      for (int base = 0; base < OF_TBUF; base += 32 * U) {
+        ReadQ R[U];
+        int2 c0[U], c1[U];
+        uint32_t ar[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int slot = base + u * 32 + lane;
+          ar[u] = aq + (uint32_t)min(slot, OF_TBUF - 1) * 4u;
+          const bool ok = slot < nrel && slot < OF_TBUF;
+          R[u] = ord_prepare(P, ok ? lds32(ar[u] + OF_CS) : -1, lds32(ar[u] + 2 * OF_CS),
+                             lds32(ar[u] + 3 * OF_CS), lds32(ar[u] + 4 * OF_CS));
+        }
+        const int2 pad = make_int2(INT32_MAX, 0);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          c0[u] = R[u].g0 < R[u].g1 ? __ldg(P.genes + R[u].g0) : pad;
+          c1[u] = R[u].g0 + 1 < R[u].g1 ? __ldg(P.genes + R[u].g0 + 1) : pad;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t y = (int64_t)R[u].re - R[u].L;  // a matching gene starts at or before y
+          int m0 = -1, m1 = -1, m2 = -1, m3 = -1, nm = 0;
+          auto take = [&](const int2 g, int gi) {
+            if (of_overlap_ok(g, R[u].rb, R[u].re, R[u].L)) {
+              if (nm == 0) m0 = gi;
+              if (nm == 1) m1 = gi;
+              if (nm == 2) m2 = gi;
+              if (nm == 3) m3 = gi;
+              ++nm;
+            }
+          };
+          bool more = (int64_t)c0[u].x <= y;
+          if (more) take(c0[u], R[u].g0);
+          more = more && (int64_t)c1[u].x <= y;
+          if (more) take(c1[u], R[u].g0 + 1);
+#pragma unroll 1
+          for (int g = R[u].g0 + 2; more && g < R[u].g1; ++g) {
+            const int2 cg = __ldg(P.genes + g);
+            more = (int64_t)cg.x <= y;
+            if (more) take(cg, g);
+          }
+          // gene -> subject (null: gene g is subject g)
+          if (P.gene_subject) {
+            if (m0 >= 0) m0 = __ldg(P.gene_subject + m0);
+            if (m1 >= 0) m1 = __ldg(P.gene_subject + m1);
+            if (m2 >= 0) m2 = __ldg(P.gene_subject + m2);
+            if (m3 >= 0) m3 = __ldg(P.gene_subject + m3);
+          }
+          if (nm > 4) m3 = -2;
+          if (base + u * 32 + lane < OF_TBUF) {
+            sts32(ar[u] + OF_CS, (uint32_t)m0);
+            sts32(ar[u] + 2 * OF_CS, (uint32_t)m1);
+            sts32(ar[u] + 3 * OF_CS, (uint32_t)m2);
+            sts32(ar[u] + 4 * OF_CS, (uint32_t)m3);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    // ---- phase B: the windows
     int cur = w0 - 1;
     auto seek = [&]() {
 #pragma unroll 1
@@ -168,8 +247,8 @@ __global__ void __launch_bounds__(SG_NT, 1)
     while (cur < w1) {
       const uint32_t ax = aq + (uint32_t)(cur + lane) * 4u;
       const int qa = lds32(ax), qb = lds32(ax + 4u);
-      const int cv = lds32(ax + OF_CS), bv = lds32(ax + 2 * OF_CS), ev = lds32(ax + 3 * OF_CS),
-                lv = lds32(ax + 4 * OF_CS);
+      int m0 = lds32(ax + OF_CS), m1 = lds32(ax + 2 * OF_CS), m2 = lds32(ax + 3 * OF_CS),
+          m3 = lds32(ax + 4 * OF_CS);
       const unsigned T = __ballot_sync(FULL, qa != qb);
       unsigned Tl = T;
       if (cur >= w1 - 32) {
@@ -190,48 +269,11 @@ __global__ void __launch_bounds__(SG_NT, 1)
       const int sl = bfind32(H & le);
       const unsigned segm = (tge ^ (tge - 1u)) & (ones << sl);
 
-      // the genes matching my read: candidates from the first gene that can
-      // reach it (wk_ordinal.cuh), the first two loaded together, the others
-      // (17 % of the reads of cfg3 have three or more) one by one; up to four
-      // matches stay in registers, a read with more is a listed query
-      const ReadQ R = ord_prepare(P, act ? cv : -1, bv, ev, lv);
-      const int64_t y = (int64_t)R.re - R.L;   // a matching gene starts at or before y
-      int m0 = -1, m1 = -1, m2 = -1, m3 = -1, nm = 0;
-      auto take = [&](const int2 g, int gi) {
-        if (of_overlap_ok(g, R.rb, R.re, R.L)) {
-          if (nm == 0) m0 = gi;
-          if (nm == 1) m1 = gi;
-          if (nm == 2) m2 = gi;
-          if (nm == 3) m3 = gi;
-          ++nm;
-        }
-      };
-      {
-        const int2 pad = make_int2(INT32_MAX, 0);
-        const int2 c0 = R.g0 < R.g1 ? __ldg(P.genes + R.g0) : pad;
-        const int2 c1 = R.g0 + 1 < R.g1 ? __ldg(P.genes + R.g0 + 1) : pad;
-        bool more = (int64_t)c0.x <= y;
-        if (more) take(c0, R.g0);
-        more = more && (int64_t)c1.x <= y;
-        if (more) take(c1, R.g0 + 1);
-#pragma unroll 1
-        for (int g = R.g0 + 2; more && g < R.g1; ++g) {
-          const int2 cg = __ldg(P.genes + g);
-          more = (int64_t)cg.x <= y;
-          if (more) take(cg, g);
-        }
-      }
-      const unsigned DEEP = __ballot_sync(FULL, act && nm > 4);
+      // more than four genes on a read of my query: a listed query
+      const unsigned DEEP = __ballot_sync(FULL, act && m3 == -2);
       const bool listed = (DEEP & segm) != 0;
       if (DEEP) list_heads(__ballot_sync(FULL, act && listed && sl == lane));
-
-      // gene -> subject (null: gene g is subject g)
-      if (P.gene_subject) {
-        if (m0 >= 0) m0 = __ldg(P.gene_subject + m0);
-        if (m1 >= 0) m1 = __ldg(P.gene_subject + m1);
-        if (m2 >= 0) m2 = __ldg(P.gene_subject + m2);
-        if (m3 >= 0) m3 = __ldg(P.gene_subject + m3);
-      }
+      const int nm = (m0 >= 0) + (m1 >= 0) + (m2 >= 0) + (m3 >= 0);
       // The genes of a query are a set (ordinal.py:332): drop a gene that an
       // earlier lane of the query holds.  Two lanes can only share a gene when
       // their ranges of subjects overlap, which one ballot rules out for almost
@@ -281,27 +323,21 @@ __global__ void __launch_bounds__(SG_NT, 1)
         k += __popc(__ballot_sync(FULL, v2) & segm) + __popc(__ballot_sync(FULL, v3) & segm);
       int samp = F.sample;
       if (F.q_sample && act) samp = __ldg(F.q_sample + qa);
+      // what this lane contributes: (cell, units) records for apply_kernel.
+      // The units table is NOT touched here: its 40 MB would compete with the
+      // gene table for the L2 and every lookup and every count would miss.
+      uint32_t u = 0;
+      bool un_head = false;
       if ((unsigned)samp < (unsigned)F.S && k > 0) {
-        ull *const crow = F.cnt + (int64_t)samp * F.NF1;
-        auto each = [&](auto &&f) {
-          if (v0) f(m0);
-          if (v1) f(m1);
-          if (v2) f(m2);
-          if (v3) f(m3);
-        };
         if (MODE == FX_UNIQ) {
           // classify.assign_none: one gene -> that gene, else None
-          if (k == 1)
-            each([&](int f) { atomicAdd(crow + f, (ull)WK_UNITS); });
-          else if (UNAS && act && sl == lane)
-            atomicAdd(crow + (F.NF1 - 1), (ull)WK_UNITS);
+          if (k == 1) u = (uint32_t)WK_UNITS;
+          else un_head = UNAS && act && sl == lane;
         } else {
-          const uint32_t u = (uint32_t)lds32(usm + (uint32_t)min(k, 64) * 4u);
-          if (u) {
-            each([&](int f) { atomicAdd(crow + f, (ull)u); });
-          } else {
+          u = (uint32_t)lds32(usm + (uint32_t)min(k, 64) * 4u);
+          if (u == 0) {
             // 1/k with k not dividing WK_UNITS: the overflow list
-            each([&](int f) {
+            auto ovf = [&](int f) {
               const ull at = atomicAdd(F.ovf_n, 1ull);
               if ((int64_t)at < F.ovf_cap) {
                 F.ovf_key[at] = ((int64_t)samp << 32) | (uint32_t)f;
@@ -309,9 +345,39 @@ __global__ void __launch_bounds__(SG_NT, 1)
               } else {
                 atomicOr(P.err, ERR_OVF_FULL);
               }
-            });
+            };
+            if (v0) ovf(m0);
+            if (v1) ovf(m1);
+            if (v2) ovf(m2);
+            if (v3) ovf(m3);
           }
         }
+      }
+      const int nc = u ? (int)v0 + (int)v1 + (int)v2 + (int)v3 : (int)un_head;
+      int inc = nc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t;
+      }
+      const int tot = __shfl_sync(FULL, inc, 31);
+      if (tot) {
+        // one bump of this CTA's cursor per window, records written in lane order
+        ull base = 0;
+        if (lane == 0) base = atomicAdd(my_cursor, (ull)tot);
+        base = __shfl_sync(FULL, base, 0) + (ull)(inc - nc);
+        if (base + (ull)nc <= (ull)F.con_cap) {
+          ull *out = my_list + base;
+          const ull row = (ull)samp * (ull)F.NF1;
+          if (u) {
+            if (v0) *out++ = ((row + (ull)m0) << 20) | u;
+            if (v1) *out++ = ((row + (ull)m1) << 20) | u;
+            if (v2) *out++ = ((row + (ull)m2) << 20) | u;
+            if (v3) *out++ = ((row + (ull)m3) << 20) | u;
+          } else if (un_head) {
+            *out = ((row + (ull)(F.NF1 - 1)) << 20) | (ull)WK_UNITS;
+          }
+        }  // (a full list: the cursor tells the host how much room to make)
       }
       cur += tp + 1;
     }
@@ -320,6 +386,20 @@ __global__ void __launch_bounds__(SG_NT, 1)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       issue(tile + GW);
     }
+  }
+}
+
+// The contributions of ordinal_fused_kernel into the units table
+// (classify.counter + util.sum_dict): one 64-bit reduction per record, the
+// table (8 bytes per gene) resident in L2.  blockIdx.y = the list of one CTA.
+__global__ void __launch_bounds__(256)
+    ordinal_apply_kernel(const __grid_constant__ OrdFuseParams F) {
+  const ull n = min(F.con_n[blockIdx.y], (ull)F.con_cap);
+  const ull *src = F.con + (int64_t)blockIdx.y * F.con_cap;
+  for (ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (ull)gridDim.x * blockDim.x) {
+    const ull r = __ldcs(src + i);
+    atomicAdd(F.cnt + (r >> 20), r & 0xFFFFFull);
   }
 }
 
