@@ -2,11 +2,16 @@
  *
  * TEST INFRASTRUCTURE ONLY.  Nothing under woltka_b200/ may import, link or
  * call this file; it is the checker for tests/, __graft_entry__.smoke() and
- * the cpu_baseline / --impl reference legs of bench.py.
+ * the cpu_baseline / --impl reference legs of bench.py
+ * (baseline/reference_arm.py).
  *
- * Parity status: PINNED.  tests/test_oracle_golden.py checks this port
- * against (a) the known-answer vectors of the reference's own unit tests and
- * (b) golden outputs produced by running the unmodified reference
+ * Parity status: PINNED.  tests/test_golden.py (test_golden_oracle: every
+ * case of tests/golden/INDEX.json through this port behind the engine
+ * interface, tests/oracle_engine.py), tests/test_kats.py and
+ * tests/test_dropin_reference.py (the reference's own `woltka classify`
+ * command with this port behind its two seams, 12 CLI goldens byte-identical)
+ * check this port against (a) the known-answer vectors of the reference's own
+ * unit tests and (b) golden outputs produced by running the unmodified reference
  * (/root/reference, woltka 0.1.7) in the build container
  * (tests/golden/make_golden.py is the generating script).
  *
