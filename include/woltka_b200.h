@@ -245,6 +245,38 @@ int wk_parse_sam(wk_ctx *ctx, const char *text, int64_t n_bytes, int demux,
 int wk_parse_text(wk_ctx *ctx, const char *text, int64_t n_bytes, int fmt,
                   int demux, int64_t *n_rec, int64_t *n_qry,
                   int32_t *n_subjects, int32_t *n_samples);
+/* The same for a BLOCK of a file of any size (replaces the chunk cut of
+ * plain_mapper, align.py:73-79, which never splits a query): unless
+ * final_block, the bytes after the last line end and the lines from the head
+ * of the last QNAME group on are left alone and *consumed returns the offset
+ * of the first byte left - the caller sends them again in front of the next
+ * block.  *consumed == 0 means the block holds no complete group: send a
+ * larger one. */
+int wk_parse_block(wk_ctx *ctx, const char *text, int64_t n_bytes, int fmt,
+                   int demux, int final_block, int64_t *consumed, int64_t *n_rec,
+                   int64_t *n_qry, int32_t *n_subjects, int32_t *n_samples);
+/* Reader options, kept until changed (all off by default):
+ *   trim / trim_len   --trim-sub: the subject is cut at the LAST occurrence of
+ *                     this separator before it is interned (strip_suffix,
+ *                     workflow.py:818-841; `x.rsplit(sep, 1)[0]`), so two
+ *                     subjects equal after the cut are one subject of the
+ *                     query; at most 8 bytes.
+ *   excl / excl_lens / n_excl
+ *                     --exclude: names concatenated in `excl`.  A QNAME group
+ *                     (all mates) any of whose records hits one of them (the
+ *                     name as written, before the cut) is dropped
+ *                     (parse_sam_file_ft, align.py:409-478, and the b6o / paf
+ *                     / map variants :677-750, :858-916, :1091-1149).
+ *   coords            the chunk is read for the coordinate matcher: next to q
+ *                     and the subject (= contig) index, beg / end / len per
+ *                     record, as parse_sam_file_ex (align.py:350-406: POS - 1,
+ *                     cigar_to_lens :550-583), parse_b6o_file_ex (:807-855) and
+ *                     parse_paf_file_ex (:1046-1088) give them; records with
+ *                     len == 0 are dropped (ordinal.py:230-231).  Follow with
+ *                     wk_ordinal_parsed instead of wk_classify_parsed. */
+int wk_parse_options(wk_ctx *ctx, const char *trim, int32_t trim_len,
+                     const char *excl, const int32_t *excl_lens, int32_t n_excl,
+                     int coords);
 /* Names with index in [from, to) of the subject (which = 0) or sample
  * (which = 1) table: bytes concatenated into buf, lengths into lens. */
 int wk_parse_fetch_names(wk_ctx *ctx, int which, int32_t from, int32_t to,
@@ -254,10 +286,20 @@ int wk_parse_fetch_names(wk_ctx *ctx, int which, int32_t from, int32_t to,
  * carrying the query's name | mate << 30. */
 int wk_parse_fetch_columns(wk_ctx *ctx, int32_t *q, int32_t *s,
                            int32_t *q_sample, uint32_t *q_line);
+/* beg / end / len [n_rec] of the last chunk parsed with `coords`. */
+int wk_parse_fetch_coords(wk_ctx *ctx, int32_t *beg, int32_t *end, int32_t *len);
 /* Classify the last parsed chunk.  demux: sample_map[parsed sample index] =
  * sample index of the plan or -1 (dropped); otherwise `sample`. */
 int wk_classify_parsed(wk_ctx *ctx, const int32_t *sample_map, int32_t n_map,
                        int32_t sample);
+
+/* Match and classify the last chunk parsed with `coords` (what
+ * ordinal_mapper + the classify loop do with the records, ordinal.py:167-335,
+ * workflow.py:304-335): contig_map[parsed subject index] = contig index of
+ * wk_ordinal_set_genes or -1; samples as in wk_classify_parsed. */
+int wk_ordinal_parsed(wk_ctx *ctx, const int32_t *contig_map,
+                      int32_t n_contig_map, double th, const int32_t *sample_map,
+                      int32_t n_map, int32_t sample);
 
 /* Device address / length (in int64 elements) of the units table, for a
  * caller-side NCCL reduce (torch.distributed) across GPUs. */

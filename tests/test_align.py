@@ -146,29 +146,6 @@ def test_generator_columns_equal_what_the_readers_derive_from_its_sam_lines():
         assert set(le) == {148, 150}
 
 
-def test_text_chunks_header_longer_than_a_block(tmp_path):
-    """The device reader's file chunker drops every leading '@' line of a SAM
-    file even when a read block ends inside one (align.py:296-300 skips them
-    line by line); small blocks put the cut everywhere."""
-    from woltka_b200.workflow import _text_chunks
-    hdr = ''.join(f'@SQ\tSN:contig{i}\tLN:{1000 + i}\n' for i in range(20))
-    body = ''.join(f'r{i // 2}\t0\tG{i % 5}\t1\t42\t50M\t*\t0\t0\tA\tI\n'
-                   for i in range(40))
-    fp = tmp_path / 'x.sam'
-    fp.write_text(hdr + body)
-    for block in (7, 16, 50, 64, 1000, 1 << 20):
-        chunks = list(_text_chunks(str(fp), block=block))
-        assert b''.join(chunks) == body.encode(), block
-        # a query is never split over two chunks
-        for a, b in zip(chunks, chunks[1:]):
-            assert a.splitlines()[-1].split(b'\t')[0] != \
-                b.splitlines()[0].split(b'\t')[0]
-    fp.write_text(hdr)                       # a header and nothing else
-    assert b''.join(_text_chunks(str(fp), block=16)) == b''
-    fp.write_text(hdr.rstrip('\n'))          # ... without the last newline
-    assert b''.join(_text_chunks(str(fp), block=16)) == b''
-
-
 def test_demultiplex_with_an_empty_sample_list_keeps_everything():
     """workflow.demultiplex (workflow.py:885-886) tests `if samples`: an empty
     list is no filter."""

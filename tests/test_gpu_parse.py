@@ -17,9 +17,9 @@ DATA = os.path.join(os.path.dirname(__file__), 'golden', 'data')
 SUFFIX = ('', '/1', '/2')
 
 
-def host_queries(text, fmt='sam'):
+def host_queries(text, fmt='sam', excl=None, extr=False):
     lines = text.decode().splitlines(keepends=True)
-    return list(align.iter_align(iter(lines), fmt))
+    return list(align.iter_align(iter(lines), fmt, excl, extr))
 
 
 def device_queries(engine, text, demux=False, fmt='sam'):
@@ -146,9 +146,8 @@ def test_classify_from_text_equals_classify_from_host_reader(monkeypatch, tmp_pa
     # multiplexed synthetic file, cut into many chunks
     fp = tmp_path / 'mux.sam'
     fp.write_bytes(b'@HD\tVN:1.0\n@SQ\tSN:x\tLN:1\n' + synthetic_sam(3000, 5))
-    orig = workflow._text_chunks
-    monkeypatch.setattr(workflow, '_text_chunks',
-                        lambda p, header=True: orig(p, block=20000, header=header))
+    from woltka_b200 import reader
+    monkeypatch.setattr(reader, 'BLOCK', 20000)
     dev, reader = _run_classify([str(fp)], True)
     assert reader == 'device'
     monkeypatch.setenv('WOLTKA_B200_HOST_READER', '1')
@@ -196,3 +195,193 @@ def test_odd_lines_of_map_b6o_paf():
         exp = host_queries(text, fmt)
         assert got == [(e[0], e[1]) for e in exp], fmt
     eng.close()
+
+
+# ---- reader options: --trim-sub, --exclude, coordinates --------------------------
+def suffixed_sam(n_groups, seed):
+    """Subjects carry `_<n>` suffixes (ORF style); some names come back after
+    another name in between (the A, B, A pattern)."""
+    rng = np.random.default_rng(seed)
+    cigars = ['50M', '10S40M', '20M2D30M', '*', '5H20M3I22M5N3M', '7=1X8=',
+              '30M1000N20M', '12I', '4P']
+    rows = []
+    for g in range(n_groups):
+        name = f'read{g if rng.random() < 0.8 else g - 2}'
+        for _ in range(int(min(rng.geometric(0.4), 9))):
+            flag = int(rng.choice([0, 16, 64 + 1, 128 + 1, 256]))
+            r = rng.random()
+            sub = '*' if r < 0.05 else (
+                f'G{rng.integers(0, 60):03d}_{rng.integers(1, 4)}' if r < 0.8
+                else f'G{rng.integers(0, 60):03d}' if r < 0.9
+                else rng.choice(['_1', 'a_b_c', 'plain', 'x__2']))
+            rows.append(f'{name}\t{flag}\t{sub}\t{rng.integers(1, 99999)}\t42\t'
+                        f'{rng.choice(cigars)}\t*\t0\t0\tACGT\tIIII')
+    return ('\n'.join(rows) + '\n').encode()
+
+
+@pytest.mark.parametrize('trim', [None, '_', '__'])
+@pytest.mark.parametrize('with_excl', [False, True])
+def test_trim_sub_and_exclude_on_device(trim, with_excl):
+    """--trim-sub (workflow.py:818-841) and --exclude (align.py:409-478) inside
+    the device reader against the host reader followed by strip_suffix."""
+    from woltka_b200.engine import Engine
+    eng = Engine(0)
+    excl = {f'G{i:03d}_2' for i in range(0, 60, 3)} | {'plain', 'G007'} \
+        if with_excl else None
+    eng.parse_options(trim, excl)
+    for seed in (21, 22):
+        text = suffixed_sam(3000, seed)
+        got, _ = device_queries(eng, text)
+        exp = host_queries(text, excl=excl)
+        if trim:
+            exp = [(q, {x.rsplit(trim, 1)[0] for x in subs}) for q, subs in exp]
+        assert [g[0] for g in got] == [e[0] for e in exp]
+        assert [g[1] for g in got] == [e[1] for e in exp]
+    # A, B (excluded), A: the two A groups stay two queries
+    eng.parse_options(None, {'bad'})
+    text = (b'A\t0\tg1\t1\t9\t5M\t*\nB\t0\tbad\t1\t9\t5M\t*\n'
+            b'A\t0\tg2\t1\t9\t5M\t*\nC\t0\tg1\t1\t9\t5M\t*\n'
+            b'C\t64\tbad\t1\t9\t5M\t*\n')
+    got, _ = device_queries(eng, text)
+    assert got == [('A', {'g1'}), ('A', {'g2'})] == host_queries(text, excl={'bad'})
+    # options are kept until changed, and can be switched off again
+    eng.parse_options()
+    got, _ = device_queries(eng, text)
+    assert [g[0] for g in got] == ['A', 'B', 'A', 'C', 'C/1']
+    eng.close()
+
+
+def device_records(engine, text, demux=False, fmt='sam'):
+    """[(query name, [(subject, len, beg, end)])] of a chunk parsed with coords."""
+    n_rec, n_qry, n_sub, n_smp = engine.parse_sam(text, demux, fmt)
+    subjects = engine.fetch_names(0, 0, n_sub)
+    q, s, qs, ql = engine.fetch_parsed_columns(n_rec, n_qry, demux)
+    beg, end, ln = engine.fetch_parsed_coords(n_rec)
+    lines = text.split(b'\n')
+    out = [None] * n_qry
+    for j in range(n_qry):
+        li, mate = int(ql[j]) & ((1 << 30) - 1), int(ql[j]) >> 30
+        out[j] = (lines[li].split(b'\t', 1)[0].decode() + SUFFIX[mate], [])
+    for i in range(n_rec):
+        out[q[i]][1].append((subjects[s[i]], int(ln[i]), int(beg[i]), int(end[i])))
+    return out
+
+
+def host_records(text, fmt='sam', excl=None):
+    out = []
+    for query, records in host_queries(text, fmt, excl, True):
+        recs = [(r[0], r[2], r[3], r[4]) for r in records if r[2]]
+        if recs:
+            out.append((query, recs))
+    return out
+
+
+def merge_adjacent(rows):
+    """Records per query name, names in order of first appearance: what
+    ordinal.py:332 makes of a chunk.  (The device groups the lines that are
+    left once the records without aligned length are gone, so two groups of
+    one name around a group that vanished are already one query there.)"""
+    out = {}
+    for query, recs in rows:
+        out.setdefault(query, []).extend(recs)
+    return list(out.items())
+
+
+@pytest.mark.parametrize('with_excl', [False, True])
+def test_sam_coordinates_on_device(with_excl):
+    """POS - 1 and cigar_to_lens (align.py:350-406, 550-583) on the device."""
+    from woltka_b200.engine import Engine
+    eng = Engine(0)
+    excl = {f'G{i:03d}_2' for i in range(0, 60, 3)} if with_excl else None
+    eng.parse_options(None, excl, coords=True)
+    for seed in (31, 32):
+        text = suffixed_sam(3000, seed)
+        got = device_records(eng, text)
+        exp = host_records(text, excl=excl)
+        if not with_excl:
+            exp = merge_adjacent(exp)
+            got = merge_adjacent(got)
+        assert got == exp
+    with pytest.raises(Exception):
+        eng.classify_parsed(None, 0)     # parsed for the matcher, not for classify
+    eng.close()
+
+
+def test_b6o_paf_coordinates_on_device():
+    """parse_b6o_file_ex (align.py:807-855) / parse_paf_file_ex (:1046-1088)."""
+    from woltka_b200.engine import Engine
+    rng = np.random.default_rng(5)
+    b6o, paf = [], []
+    for g in range(2000):
+        for _ in range(int(min(rng.geometric(0.5), 6))):
+            a, b = sorted(rng.integers(1, 50000, 2).tolist())
+            if rng.random() < 0.5:
+                a, b = b, a
+            ln = int(rng.integers(0, 300)) if rng.random() < 0.9 else 0
+            b6o.append(f'q{g}\tT{rng.integers(0, 40)}\t98.5\t{ln}\t1\t0\t1\t{ln}'
+                       f'\t{a}\t{b}\t1e-9\t{rng.integers(50, 300)}.0')
+            lo, hi = sorted((a, b))
+            paf.append(f'q{g}\t150\t0\t150\t+\tT{rng.integers(0, 40)}\t90000'
+                       f'\t{lo}\t{hi}\t140\t{ln}\t{rng.integers(0, 60)}\ttp:A:P')
+    b6o[17] = 'short\tline\t1\t2'
+    paf[23] = 'q23\t150\t0\t150\t+\tT1\t90000\tx\t5\t140\t150\t60'
+    paf[29] = 'q29\t150\t0\t150\t+\tT1'
+    eng = Engine(0)
+    eng.parse_options(None, None, coords=True)
+    for fmt, rows in (('b6o', b6o), ('paf', paf)):
+        text = ('\n'.join(rows) + '\n').encode()
+        got = merge_adjacent(device_records(eng, text, fmt=fmt))
+        exp = merge_adjacent(host_records(text, fmt))
+        assert got == exp, fmt
+    eng.close()
+
+
+def _ordinal_classify(files, coords_fp, demux=None, **kw):
+    import io
+    from contextlib import redirect_stdout
+    from woltka_b200 import workflow
+    with redirect_stdout(io.StringIO()):
+        mapper, chunk = workflow.build_mapper(coords_fp, None, 80, None)
+        out = workflow.classify(mapper, files, demux=demux, ranks=['none'],
+                                chunk=chunk, **kw)
+    return out, workflow.LAST_READER
+
+
+def test_coords_from_text_equals_host_reader(monkeypatch, tmp_path):
+    """`--coords` end to end: text -> records -> matches -> counts on the
+    device against the host reader feeding the same matcher."""
+    from woltka_b200 import workflow
+    coords_fp = os.path.join(DATA, 'synth_coords.txt')
+    files = {os.path.join(DATA, 'synth_ordinal', f'S{i}.sam'): f'S{i}'
+             for i in range(2)}
+    from woltka_b200 import reader
+    monkeypatch.setattr(reader, 'BLOCK', 30000)
+    for kw in ({}, {'uniq': True}, {'exclude': {'C4', 'C11'}},
+               {'trimsub': '_'}, {'sizes': None, 'unasgd': True}):
+        monkeypatch.delenv('WOLTKA_B200_HOST_READER', raising=False)
+        dev, reader = _ordinal_classify(files, coords_fp, **kw)
+        assert reader == 'device', kw
+        monkeypatch.setenv('WOLTKA_B200_HOST_READER', '1')
+        host, reader = _ordinal_classify(files, coords_fp, **kw)
+        assert reader == 'host'
+        assert dev == host, kw
+        assert sum(len(v) for v in dev['none'].values()) > 10
+
+
+def test_plain_options_from_text_equals_host_reader(monkeypatch, tmp_path):
+    """classify() with --trim-sub / --exclude stays on the device reader."""
+    from woltka_b200 import workflow
+    fp = tmp_path / 'S9.sam'
+    fp.write_bytes(b'@HD\tVN:1.0\n' + suffixed_sam(4000, 41))
+    from woltka_b200 import reader
+    monkeypatch.setattr(reader, 'BLOCK', 25000)
+    excl = {f'G{i:03d}_2' for i in range(0, 60, 3)}
+    for kw in ({'trimsub': '_'}, {'exclude': excl},
+               {'trimsub': '_', 'exclude': excl, 'uniq': True}):
+        monkeypatch.delenv('WOLTKA_B200_HOST_READER', raising=False)
+        dev, reader = _run_classify({str(fp): 'S9'}, False, **kw)
+        assert reader == 'device', kw
+        monkeypatch.setenv('WOLTKA_B200_HOST_READER', '1')
+        host, _ = _run_classify({str(fp): 'S9'}, False, **kw)
+        assert dev == host, kw
+        assert len(dev['none']['S9']) > 5

@@ -75,6 +75,13 @@ SIGNATURES = {
                                        C.c_int64, _i64p, _vp]),
     'wk_parse_fetch_columns': (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     'wk_classify_parsed': (C.c_int, [_vp, _vp, C.c_int32, C.c_int32]),
+    'wk_parse_block': (C.c_int, [_vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                 _i64p, _i64p, _i64p, _i32p, _i32p]),
+    'wk_parse_fetch_coords': (C.c_int, [_vp, _vp, _vp, _vp]),
+    'wk_parse_options': (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp, C.c_int32,
+                                   C.c_int]),
+    'wk_ordinal_parsed': (C.c_int, [_vp, _vp, C.c_int32, C.c_double, _vp,
+                                    C.c_int32, C.c_int32]),
     'wk_cover_add': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64]),
     'wk_cover_merge': (C.c_int, [_vp, _i64p]),
     'wk_cover_fetch': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64]),

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <mutex>
 #include <vector>
 
 #include "wk_classify.cuh"
@@ -55,34 +56,110 @@ static int fail(int code, const char *fmt, ...) {
 
 namespace {
 
+// Device blocks released by a context are kept (up to kCacheMax bytes per
+// process) and handed to the next reserve() of a similar size: a run builds a
+// context per classify() call, and cudaMalloc / cudaFree of its ~70 buffers
+// cost more than parsing a small file.  Every path into the cache has
+// synchronised the device first, so no kernel still uses a cached block.
+struct BlockCache {
+  struct Block {
+    void *p;
+    size_t cap;
+    int dev;
+  };
+  std::mutex m;
+  std::vector<Block> blocks;
+  size_t bytes = 0;
+  static constexpr size_t kCacheMax = 4ull << 30, kBlockMax = 1ull << 30;
+  void *take(size_t want, int dev, size_t *cap) {
+    std::lock_guard<std::mutex> g(m);
+    size_t best = blocks.size();
+    for (size_t i = 0; i < blocks.size(); ++i)
+      if (blocks[i].dev == dev && blocks[i].cap >= want &&
+          blocks[i].cap <= 2 * want + (1 << 20) &&
+          (best == blocks.size() || blocks[i].cap < blocks[best].cap))
+        best = i;
+    if (best == blocks.size()) return nullptr;
+    void *p = blocks[best].p;
+    *cap = blocks[best].cap;
+    bytes -= blocks[best].cap;
+    blocks[best] = blocks.back();
+    blocks.pop_back();
+    return p;
+  }
+  bool put(void *p, size_t cap, int dev) {
+    std::lock_guard<std::mutex> g(m);
+    if (cap > kBlockMax || bytes + cap > kCacheMax) return false;
+    blocks.push_back({p, cap, dev});
+    bytes += cap;
+    return true;
+  }
+  void flush(int dev) {
+    std::lock_guard<std::mutex> g(m);
+    size_t k = 0;
+    for (size_t i = 0; i < blocks.size(); ++i) {
+      if (blocks[i].dev == dev) {
+        cudaFree(blocks[i].p);
+        bytes -= blocks[i].cap;
+      } else {
+        blocks[k++] = blocks[i];
+      }
+    }
+    blocks.resize(k);
+  }
+};
+static BlockCache g_blocks;
+
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
   int reserve(size_t bytes) {
     if (bytes <= cap) return WK_OK;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (p) {
+      cudaDeviceSynchronize();  // (what cudaFree did: nothing may still read it)
+      give_back(dev);
+    }
     size_t want = bytes + (bytes >> 3) + 256;
+    p = g_blocks.take(want, dev, &cap);
+    if (p) return WK_OK;
     cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      g_blocks.flush(dev);
+      e = cudaMalloc(&p, want);
+    }
     if (e != cudaSuccess) {
       e = cudaMalloc(&p, bytes + 256);
       want = bytes + 256;
     }
-    if (e != cudaSuccess)
+    if (e != cudaSuccess) {
+      p = nullptr;
       return fail(WK_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes,
                   cudaGetErrorString(e));
+    }
     cap = want;
     return WK_OK;
   }
+  // callers have synchronised the stream(s) that used the block
   void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
+    if (p) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      give_back(dev);
+    }
   }
   template <typename T>
   T *as() const {
     return static_cast<T *>(p);
+  }
+
+ private:
+  void give_back(int dev) {
+    if (!g_blocks.put(p, cap, dev)) cudaFree(p);
+    p = nullptr;
+    cap = 0;
   }
 };
 
@@ -250,10 +327,16 @@ struct wk_ctx {
   // SAM reader (wk_parse.cuh)
   DevBuf p_text, p_a, p_b, p_sums, p_line_start, p_rec, p_valid, p_vpos, p_vline,
       p_ghead, p_slot, p_phead, p_qpos, p_rslot, p_sslot, p_qline, p_tot;
-  DevBuf t_keys[2], t_ids[2], t_soff[2], t_slen[2], t_first[2], t_pool[2], t_meta[2];
+  DevBuf t_keys[3], t_ids[3], t_soff[3], t_slen[3], t_first[3], t_pool[3], t_meta[3];
+  DevBuf p_gdrop, p_lhead, p_xbeg, p_xlen, p_xspan;
   bool p_tables = false;
   int64_t p_nrec = 0, p_nqry = 0;
   int p_demux = 0;
+  // wk_parse_options: --trim-sub, --exclude (table 2), coordinates
+  ParseOpts p_opts = {};
+  uint64_t x_cap = 0, x_pool = 0;   // exclusion table: slots, pool bytes
+  int32_t x_n = 0;
+  bool p_coords = false;            // the last parse filled dbeg / dend / dlen
   DevBuf assign;
   int64_t assign_n = 0;  // records of the chunk the buffer belongs to
 
@@ -465,7 +548,10 @@ int wk_destroy(wk_ctx *c) {
                     &c->p_qline, &c->p_tot, &c->t_keys[0], &c->t_keys[1],
                     &c->t_ids[0], &c->t_ids[1], &c->t_soff[0], &c->t_soff[1],
                     &c->t_slen[0], &c->t_slen[1], &c->t_first[0], &c->t_first[1],
-                    &c->t_pool[0], &c->t_pool[1], &c->t_meta[0], &c->t_meta[1]};
+                    &c->t_pool[0], &c->t_pool[1], &c->t_meta[0], &c->t_meta[1],
+                    &c->t_keys[2], &c->t_ids[2], &c->t_soff[2], &c->t_slen[2],
+                    &c->t_first[2], &c->t_pool[2], &c->t_meta[2], &c->p_gdrop, &c->p_lhead, &c->p_xbeg,
+                    &c->p_xlen, &c->p_xspan};
   for (DevBuf *b : bufs) b->release();
   for (int i = 0; i < 2; ++i)
     if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
@@ -2358,8 +2444,8 @@ static InternTable intern_table(wk_ctx *c, int w) {
   T.pool = c->t_pool[w].as<uint8_t>();
   T.pool_used = c->t_meta[w].as<ull>();
   T.count = reinterpret_cast<int32_t *>(c->t_meta[w].as<ull>() + 1);
-  T.cap_mask = kInternCap[w] - 1;
-  T.pool_cap = kInternPool[w];
+  T.cap_mask = (w == 2 ? c->x_cap : kInternCap[w]) - 1;
+  T.pool_cap = w == 2 ? c->x_pool : kInternPool[w];
   return T;
 }
 // out = exclusive prefix sum of in[0, n); *total (host) = sum
@@ -2385,8 +2471,9 @@ static int parse_error(wk_ctx *c) {
   if (!err) return WK_OK;
   CK(cudaMemsetAsync(c->d_err(), 0, 4, c->stream));
   if (err & PERR_FIELDS)
-    return fail(WK_ERR_ARG, "a SAM line has fewer than four tab-separated fields");
-  if (err & PERR_FLAG) return fail(WK_ERR_ARG, "a SAM line has an invalid FLAG");
+    return fail(WK_ERR_ARG, "a SAM line has too few tab-separated fields");
+  if (err & PERR_FLAG)
+    return fail(WK_ERR_ARG, "a line has an invalid FLAG or coordinate field");
   if (err & PERR_COLLISION)
     return fail(WK_ERR_CAPACITY, "two identifiers share a 64-bit hash");
   if (err & PERR_TABLE_FULL) return fail(WK_ERR_CAPACITY, "identifier table is full");
@@ -2398,18 +2485,26 @@ static int parse_error(wk_ctx *c) {
 
 extern "C" {
 
-int wk_parse_text(wk_ctx *c, const char *text, int64_t n_bytes, int fmt, int demux,
-                  int64_t *n_rec, int64_t *n_qry, int32_t *n_subjects,
-                  int32_t *n_samples) {
-  if (!c || !n_rec || !n_qry || !n_subjects || !n_samples)
+int wk_parse_block(wk_ctx *c, const char *text, int64_t n_bytes, int fmt, int demux,
+                   int final_block, int64_t *consumed, int64_t *n_rec, int64_t *n_qry,
+                   int32_t *n_subjects, int32_t *n_samples) {
+  if (!c || !n_rec || !n_qry || !n_subjects || !n_samples || (!final_block && !consumed))
     return fail(WK_ERR_ARG, "bad arguments");
+  if (consumed) *consumed = n_bytes;
   if (n_bytes < 0 || n_bytes >= (1ll << 31) || (n_bytes && !text))
     return fail(WK_ERR_ARG, "a text chunk must be smaller than 2 GiB");
   if (fmt < 0 || fmt > 3) return fail(WK_ERR_ARG, "bad format code %d", fmt);
+  ParseOpts O = c->p_opts;
+  O.fmt = fmt;
+  if (O.extr && fmt == PFMT_MAP)
+    return fail(WK_ERR_ARG, "the map format has no coordinates");
+  const bool filt = c->x_n > 0;
+  O.keep_empty = filt;
   TRY(use_device(c));
   TRY(parse_tables(c));
   c->p_nrec = c->p_nqry = 0;
   c->p_demux = demux;
+  c->p_coords = false;
   *n_rec = *n_qry = 0;
   InternTable TS = intern_table(c, 0), TP = intern_table(c, 1);
   auto counts = [&]() {
@@ -2432,46 +2527,123 @@ int wk_parse_text(wk_ctx *c, const char *text, int64_t n_bytes, int fmt, int dem
   c->launches++;
   int64_t n_nl = 0;
   TRY(device_scan(c, c->p_a.as<int32_t>(), n16, c->p_b.as<int32_t>(), &n_nl));
-  const int64_t n_lines = n_nl + (h[n_bytes - 1] != '\n' ? 1 : 0);
-  if (n_lines == 0) return counts();
+  // (not the last block: the bytes after the last line end wait for the next)
+  const int64_t n_lines = n_nl + (final_block && h[n_bytes - 1] != '\n' ? 1 : 0);
+  if (n_lines == 0) {
+    if (!final_block) *consumed = 0;
+    return counts();
+  }
   TRY(c->p_line_start.reserve((size_t)(n_nl + 2) * 4));
   line_starts_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, c->stream>>>(
       dt, n_bytes, c->p_b.as<int32_t>(), c->p_line_start.as<uint32_t>());
+  if (!final_block) {
+    uint32_t endc = 0;  // end of the complete lines
+    CK(cudaMemcpyAsync(&endc, c->p_line_start.as<uint32_t>() + n_nl, 4,
+                       cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    n_bytes = endc;
+    *consumed = endc;
+  }
   // 2 fields, 3 compaction
   TRY(c->p_rec.reserve((size_t)n_lines * sizeof(LineRec)));
   TRY(c->p_valid.reserve((size_t)n_lines * 4));
   TRY(c->p_vpos.reserve((size_t)n_lines * 4));
   const unsigned gl = (unsigned)((n_lines + 255) / 256);
-  line_fields_kernel<<<gl, 256, 0, c->stream>>>(dt, n_bytes, fmt,
+  if (O.extr) {
+    TRY(c->p_xbeg.reserve((size_t)n_lines * 4));
+    TRY(c->p_xlen.reserve((size_t)n_lines * 4));
+    TRY(c->p_xspan.reserve((size_t)n_lines * 4));
+  }
+  int32_t *xbeg = O.extr ? c->p_xbeg.as<int32_t>() : nullptr;
+  int32_t *xlen = O.extr ? c->p_xlen.as<int32_t>() : nullptr;
+  int32_t *xspan = O.extr ? c->p_xspan.as<int32_t>() : nullptr;
+  line_fields_kernel<<<gl, 256, 0, c->stream>>>(dt, n_bytes, O,
                                                c->p_line_start.as<uint32_t>(), n_lines,
                                                c->p_rec.as<LineRec>(),
-                                               c->p_valid.as<int32_t>(), c->d_err());
+                                               c->p_valid.as<int32_t>(), c->d_err(), xbeg,
+                                               xlen, xspan);
   c->launches += 2;
   int64_t N = 0;
   TRY(device_scan(c, c->p_valid.as<int32_t>(), n_lines, c->p_vpos.as<int32_t>(), &N));
   TRY(parse_error(c));
   if (N == 0) return counts();
+  unsigned gr = 0;
+  // 3 compaction, 4 grouping.  With an exclusion set: the groups of all mapped
+  // lines decide what goes; the lines that stay are compacted again and keep
+  // the group they were in (a dropped group between two groups of one name
+  // does NOT merge them: the reference's `qname != this` saw the dropped name
+  // in between, align.py:441-460)
   TRY(c->p_vline.reserve((size_t)N * 4));
   TRY(c->p_ghead.reserve((size_t)N));
+  compact_lines_kernel<<<gl, 256, 0, c->stream>>>(c->p_valid.as<int32_t>(),
+                                                 c->p_vpos.as<int32_t>(), n_lines,
+                                                 c->p_vline.as<uint32_t>());
+  gr = (unsigned)((N + 255) / 256);
+  group_heads_kernel<<<gr, 256, 0, c->stream>>>(dt, c->p_line_start.as<uint32_t>(),
+                                               c->p_rec.as<LineRec>(),
+                                               c->p_vline.as<uint32_t>(), N,
+                                               c->p_ghead.as<uint8_t>());
+  c->launches += 2;
+  if (!final_block) {
+    // the last group stays behind
+    ull cut[3] = {0, 0, 0};
+    TRY(c->p_tot.reserve(32));
+    ull *dcut = c->p_tot.as<ull>();   // (device_scan's total: free between scans)
+    CK(cudaMemsetAsync(dcut, 0, 24, c->stream));
+    const int64_t from = std::max<int64_t>(0, N - (1 << 17));
+    last_head_kernel<<<(unsigned)((N - from + 255) / 256), 256, 0, c->stream>>>(
+        c->p_ghead.as<uint8_t>(), c->p_vline.as<uint32_t>(),
+        c->p_line_start.as<uint32_t>(), N, from, dcut);
+    cut_point_kernel<<<1, 1, 0, c->stream>>>(c->p_vline.as<uint32_t>(),
+                                             c->p_line_start.as<uint32_t>(), dcut);
+    c->launches += 2;
+    CK(cudaMemcpyAsync(cut, dcut, 24, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (from > 0 && (int64_t)cut[0] == 0)
+      return fail(WK_ERR_CAPACITY, "more than 65536 adjacent lines share a query name");
+    *consumed = (int64_t)cut[2];
+    N = (int64_t)cut[0];
+    if (filt && (int64_t)cut[1] < n_lines) {
+      cut_lines_kernel<<<(unsigned)((n_lines - (int64_t)cut[1] + 255) / 256), 256, 0,
+                         c->stream>>>(c->p_valid.as<int32_t>(), (int64_t)cut[1], n_lines);
+      c->launches++;
+    }
+    if (N == 0) return counts();
+    gr = (unsigned)((N + 255) / 256);
+  }
+  if (filt) {
+    TRY(c->p_gdrop.reserve((size_t)N));
+    TRY(c->p_lhead.reserve((size_t)n_lines * 4));
+    CK(cudaMemsetAsync(c->p_gdrop.p, 0, (size_t)N, c->stream));
+    excl_mark_kernel<<<gr, 256, 0, c->stream>>>(
+        intern_table(c, 2), dt, c->p_rec.as<LineRec>(), c->p_vline.as<uint32_t>(),
+        c->p_ghead.as<uint8_t>(), N, c->p_gdrop.as<uint8_t>(), c->d_err());
+    excl_apply_kernel<<<gr, 256, 0, c->stream>>>(
+        c->p_vline.as<uint32_t>(), c->p_ghead.as<uint8_t>(), c->p_gdrop.as<uint8_t>(), N,
+        xlen, c->p_valid.as<int32_t>(), c->p_lhead.as<uint32_t>(), c->d_err());
+    c->launches += 2;
+    TRY(device_scan(c, c->p_valid.as<int32_t>(), n_lines, c->p_vpos.as<int32_t>(), &N));
+    TRY(parse_error(c));
+    if (N == 0) return counts();
+    compact_lines_kernel<<<gl, 256, 0, c->stream>>>(c->p_valid.as<int32_t>(),
+                                                   c->p_vpos.as<int32_t>(), n_lines,
+                                                   c->p_vline.as<uint32_t>());
+    gr = (unsigned)((N + 255) / 256);
+    regroup_heads_kernel<<<gr, 256, 0, c->stream>>>(c->p_lhead.as<uint32_t>(),
+                                                   c->p_vline.as<uint32_t>(), N,
+                                                   c->p_ghead.as<uint8_t>());
+    c->launches += 2;
+  }
   TRY(c->p_slot.reserve((size_t)N * 4));
   TRY(c->p_phead.reserve((size_t)N * 4));
   TRY(c->p_qpos.reserve((size_t)N * 4));
   TRY(c->p_rslot.reserve((size_t)N * 4));
   TRY(c->p_sslot.reserve((size_t)N * 4));
-  compact_lines_kernel<<<gl, 256, 0, c->stream>>>(c->p_valid.as<int32_t>(),
-                                                 c->p_vpos.as<int32_t>(), n_lines,
-                                                 c->p_vline.as<uint32_t>());
-  // 4 grouping
-  const unsigned gr = (unsigned)((N + 255) / 256);
-  group_heads_kernel<<<gr, 256, 0, c->stream>>>(dt, c->p_line_start.as<uint32_t>(),
-                                               c->p_rec.as<LineRec>(),
-                                               c->p_vline.as<uint32_t>(), N,
-                                               c->p_ghead.as<uint8_t>());
   order_kernel<<<gr, 256, 0, c->stream>>>(c->p_rec.as<LineRec>(), c->p_vline.as<uint32_t>(),
                                          c->p_ghead.as<uint8_t>(), N,
                                          c->p_slot.as<uint32_t>(), c->p_phead.as<int32_t>(),
                                          c->d_err());
-  c->launches += 3;
+  c->launches += 1;
   int64_t Q = 0;
   TRY(device_scan(c, c->p_phead.as<int32_t>(), N, c->p_qpos.as<int32_t>(), &Q));
   // 5 interning
@@ -2494,15 +2666,23 @@ int wk_parse_text(wk_ctx *c, const char *text, int64_t n_bytes, int fmt, int dem
   TRY(c->ds.reserve((size_t)N * 4 + 64));
   TRY(c->dqsamp.reserve((size_t)Q * 4 + 64));
   TRY(c->p_qline.reserve((size_t)Q * 4 + 64));
+  if (O.extr) {
+    TRY(c->dbeg.reserve((size_t)N * 4 + 64));
+    TRY(c->dend.reserve((size_t)N * 4 + 64));
+    TRY(c->dlen.reserve((size_t)N * 4 + 64));
+  }
   emit_columns_kernel<<<gr, 256, 0, c->stream>>>(
       TS, TP, demux, dt, c->p_line_start.as<uint32_t>(), c->p_rec.as<LineRec>(),
       c->p_vline.as<uint32_t>(), c->p_slot.as<uint32_t>(), c->p_phead.as<int32_t>(),
       c->p_qpos.as<int32_t>(), c->p_rslot.as<uint32_t>(), c->p_sslot.as<uint32_t>(), N,
       c->dq.as<int32_t>(), c->ds.as<int32_t>(), c->dqsamp.as<int32_t>(),
-      c->p_qline.as<uint32_t>(), c->d_err());
+      c->p_qline.as<uint32_t>(), c->d_err(), xbeg, xlen, xspan,
+      O.extr ? c->dbeg.as<int32_t>() : nullptr, O.extr ? c->dend.as<int32_t>() : nullptr,
+      O.extr ? c->dlen.as<int32_t>() : nullptr);
   c->launches++;
   CK(cudaGetLastError());
   TRY(parse_error(c));
+  c->p_coords = O.extr != 0;
   c->p_nrec = N;
   c->p_nqry = Q;
   *n_rec = N;
@@ -2517,7 +2697,76 @@ int wk_parse_text(wk_ctx *c, const char *text, int64_t n_bytes, int fmt, int dem
   return WK_OK;
 }
 
+int wk_parse_options(wk_ctx *c, const char *trim, int32_t trim_len, const char *excl,
+                     const int32_t *excl_lens, int32_t n_excl, int coords) {
+  if (!c || trim_len < 0 || n_excl < 0 || (trim_len && !trim) ||
+      (n_excl && (!excl || !excl_lens)))
+    return fail(WK_ERR_ARG, "bad arguments");
+  if (trim_len > (int32_t)sizeof(c->p_opts.trim))
+    return fail(WK_ERR_CAPACITY, "--trim-sub separator longer than %d bytes",
+                (int)sizeof(c->p_opts.trim));
+  TRY(use_device(c));
+  memset(&c->p_opts, 0, sizeof c->p_opts);
+  c->p_opts.trim_len = trim_len;
+  if (trim_len) memcpy(c->p_opts.trim, trim, (size_t)trim_len);
+  c->p_opts.extr = coords ? 1 : 0;
+  c->x_n = 0;
+  if (!n_excl) return WK_OK;
+  // the exclusion set: an intern table of its own, filled once
+  std::vector<uint32_t> off((size_t)n_excl + 1, 0);
+  for (int32_t i = 0; i < n_excl; ++i) {
+    if (excl_lens[i] < 0) return fail(WK_ERR_ARG, "negative name length");
+    const uint64_t nx = (uint64_t)off[(size_t)i] + (uint64_t)excl_lens[i];
+    if (nx >= (1ull << 31)) return fail(WK_ERR_CAPACITY, "exclusion list over 2 GiB");
+    off[(size_t)i + 1] = (uint32_t)nx;
+  }
+  const uint64_t bytes = off[(size_t)n_excl];
+  uint64_t cap = 1024;
+  while (cap < 4ull * (uint64_t)n_excl) cap <<= 1;
+  c->x_cap = cap;
+  c->x_pool = bytes + 64;
+  TRY(c->t_keys[2].reserve(cap * 8));
+  TRY(c->t_ids[2].reserve(cap * 4));
+  TRY(c->t_soff[2].reserve(cap * 4));
+  TRY(c->t_slen[2].reserve(cap * 4));
+  TRY(c->t_first[2].reserve(cap * 4));
+  TRY(c->t_pool[2].reserve(c->x_pool));
+  TRY(c->t_meta[2].reserve(16));
+  CK(cudaMemsetAsync(c->t_keys[2].p, 0xFF, cap * 8, c->stream));
+  CK(cudaMemsetAsync(c->t_ids[2].p, 0xFF, cap * 4, c->stream));
+  CK(cudaMemsetAsync(c->t_meta[2].p, 0, 16, c->stream));
+  DevBuf dn, doff;
+  TRY(dn.reserve(bytes + 64));
+  TRY(doff.reserve(((size_t)n_excl + 1) * 4));
+  CK(cudaMemcpyAsync(dn.p, excl, bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(doff.p, off.data(), ((size_t)n_excl + 1) * 4, cudaMemcpyHostToDevice,
+                     c->stream));
+  InternTable TX = intern_table(c, 2);
+  const unsigned gx = (unsigned)((n_excl + 255) / 256);
+  excl_load_kernel<<<gx, 256, 0, c->stream>>>(TX, dn.as<uint8_t>(), doff.as<uint32_t>(),
+                                             n_excl, c->d_err());
+  intern_assign_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, c->stream>>>(
+      TX, dn.as<uint8_t>(), c->d_err());
+  // two names under one 64-bit hash: the second would never be found
+  excl_verify_kernel<<<gx, 256, 0, c->stream>>>(TX, dn.as<uint8_t>(), doff.as<uint32_t>(),
+                                               n_excl, c->d_err());
+  c->launches += 3;
+  CK(cudaGetLastError());
+  const int rc = parse_error(c);
+  dn.release();
+  doff.release();
+  if (rc == WK_OK) c->x_n = n_excl;
+  return rc;
+}
+
 }  // extern "C"
+
+extern "C" int wk_parse_text(wk_ctx *c, const char *text, int64_t n_bytes, int fmt,
+                             int demux, int64_t *n_rec, int64_t *n_qry,
+                             int32_t *n_subjects, int32_t *n_samples) {
+  return wk_parse_block(c, text, n_bytes, fmt, demux, 1, nullptr, n_rec, n_qry, n_subjects,
+                        n_samples);
+}
 
 extern "C" int wk_parse_sam(wk_ctx *c, const char *text, int64_t n_bytes, int demux,
                             int64_t *n_rec, int64_t *n_qry, int32_t *n_subjects,
@@ -2593,11 +2842,26 @@ int wk_parse_fetch_columns(wk_ctx *c, int32_t *q, int32_t *s, int32_t *q_sample,
   return WK_OK;
 }
 
+int wk_parse_fetch_coords(wk_ctx *c, int32_t *beg, int32_t *end, int32_t *len) {
+  if (!c) return fail(WK_ERR_ARG, "ctx is NULL");
+  TRY(use_device(c));
+  const size_t N = (size_t)c->p_nrec;
+  if (N && !c->p_coords)
+    return fail(WK_ERR_STATE, "the last chunk was parsed without coordinates");
+  if (beg && N) CK(cudaMemcpyAsync(beg, c->dbeg.p, N * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (end && N) CK(cudaMemcpyAsync(end, c->dend.p, N * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (len && N) CK(cudaMemcpyAsync(len, c->dlen.p, N * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return WK_OK;
+}
+
 int wk_classify_parsed(wk_ctx *c, const int32_t *sample_map, int32_t n_map,
                        int32_t sample) {
   TRY(check_plan_ready(c, false));
   TRY(use_device(c));
   const int64_t N = c->p_nrec, Q = c->p_nqry;
+  if (N && c->p_coords)
+    return fail(WK_ERR_STATE, "the last chunk was parsed with coordinates: wk_ordinal_parsed");
   if (N && (c->flags & WK_F_SIZES)) TRY(ensure_strata(c, N * c->E));
   if (N == 0) return WK_OK;
   const int32_t *dqs = nullptr;
@@ -2623,6 +2887,55 @@ int wk_classify_parsed(wk_ctx *c, const int32_t *sample_map, int32_t n_map,
   TRY(launch_classify(c, c->dq.as<int32_t>(), c->ds.as<int32_t>(), N, nullptr, N, 0, N,
                       nullptr, nullptr, sample));
   return check_device_err(c);
+}
+
+int wk_ordinal_parsed(wk_ctx *c, const int32_t *contig_map, int32_t n_contig_map, double th,
+                      const int32_t *sample_map, int32_t n_map, int32_t sample) {
+  TRY(check_plan_ready(c, false));
+  TRY(use_device(c));
+  if (!c->C && !c->G) return fail(WK_ERR_STATE, "wk_ordinal_set_genes has not been called");
+  const int64_t N = c->p_nrec, Q = c->p_nqry;
+  if (N && !c->p_coords)
+    return fail(WK_ERR_STATE, "the last chunk was parsed without coordinates");
+  if (N == 0) return WK_OK;
+  if (!contig_map || n_contig_map <= 0)
+    return fail(WK_ERR_ARG, "the contig map is missing");
+  if (c->flags & WK_F_SIZES) TRY(ensure_strata(c, 4 * N * c->E));
+  // parsed subject index -> contig of the gene table (or -1)
+  TRY(c->dcontig.reserve((size_t)N * 4 + 64));
+  DevBuf dm, dsm;
+  TRY(dm.reserve((size_t)n_contig_map * 4));
+  CK(cudaMemcpyAsync(dm.p, contig_map, (size_t)n_contig_map * 4, cudaMemcpyHostToDevice,
+                     c->stream));
+  remap_column_kernel<<<(unsigned)((N + 255) / 256), 256, 0, c->stream>>>(
+      c->ds.as<int32_t>(), N, dm.as<int32_t>(), n_contig_map, c->dcontig.as<int32_t>());
+  c->launches++;
+  const int32_t *dqs = nullptr;
+  if (c->p_demux) {
+    if (!sample_map || n_map <= 0) {
+      cudaStreamSynchronize(c->stream);
+      dm.release();
+      return fail(WK_ERR_ARG, "a demultiplexed chunk needs the sample map");
+    }
+    TRY(dsm.reserve((size_t)n_map * 4));
+    CK(cudaMemcpyAsync(dsm.p, sample_map, (size_t)n_map * 4, cudaMemcpyHostToDevice,
+                       c->stream));
+    remap_samples_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, c->stream>>>(
+        c->dqsamp.as<int32_t>(), Q, dsm.as<int32_t>(), n_map);
+    c->launches++;
+    dqs = c->dqsamp.as<int32_t>();
+  } else if (sample < 0 || sample >= c->S) {
+    cudaStreamSynchronize(c->stream);
+    dm.release();
+    return fail(WK_ERR_ARG, "sample %d out of range", sample);
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  dm.release();
+  dsm.release();
+  c->p_nrec = 0;  // one ordinal pass per parse
+  return run_ordinal(c, c->dq.as<int32_t>(), c->dcontig.as<int32_t>(),
+                     c->dbeg.as<int32_t>(), c->dend.as<int32_t>(), c->dlen.as<int32_t>(), N,
+                     th, dqs, nullptr, sample, true);
 }
 
 // ---- merging the results of several contexts (one per GPU) ------------------------

@@ -145,6 +145,19 @@ struct LineRec {
   uint32_t roff;   // RNAME = text[roff, roff + rlen)
   uint32_t rlen;
   uint32_t mate;   // 0..2 (both mate bits set is an error, as in the reference)
+  uint32_t tlen;   // length of the subject that is interned: RNAME cut at the
+                   // last --trim-sub separator (workflow.strip_suffix,
+                   // workflow.py:818-841), else rlen
+};
+
+// options of one parse (wk_parse_text_ex)
+struct ParseOpts {
+  int fmt;
+  int extr;          // SAM with coordinates: POS and CIGAR -> beg / len / span
+  int keep_empty;    // records without aligned length stay until the exclusion
+                     // pass has seen them (their subject still counts there)
+  int trim_len;      // --trim-sub separator (0 = none), up to 8 bytes
+  uint8_t trim[8];
 };
 
 __device__ __forceinline__ ull hash_bytes(const uint8_t *p, uint32_t len) {
@@ -169,23 +182,67 @@ enum { PFMT_SAM = 0, PFMT_B6O = 1, PFMT_PAF = 2, PFMT_MAP = 3 };
 //   paf  fields 0 / 5, lines with < 7 fields are skipped (align.py:1026-1030)
 //   map  fields 0 / 1 (subject stripped of trailing blanks), lines without a
 //        tab are skipped (align.py:650-655)
-__global__ void line_fields_kernel(const uint8_t *text, int64_t n, int fmt,
+// align.cigar_to_lens (align.py:550-583): aligned length = sum of M, =, X;
+// span on the subject = aligned length + sum of D, N
+__device__ __forceinline__ void cigar_lens(const uint8_t *p, uint32_t len, int32_t *alen,
+                                           int32_t *span) {
+  int64_t a = 0, o = 0, n = 0;
+  for (uint32_t i = 0; i < len; ++i) {
+    const uint8_t ch = p[i];
+    if (ch >= '0' && ch <= '9') {
+      n = n * 10 + (ch - '0');
+    } else {
+      if (ch == 'M' || ch == '=' || ch == 'X') a += n;
+      else if (ch == 'D' || ch == 'N') o += n;
+      // (I, H, P, S consume nothing of the subject; other bytes are dropped
+      // with the digits before them, like `n += c` followed by a failing int()
+      // would not be: the reference raises there, this reader yields 0)
+      n = 0;
+    }
+  }
+  *alen = (int32_t)(a < INT32_MAX ? a : INT32_MAX);
+  *span = (int32_t)(a + o < INT32_MAX ? a + o : INT32_MAX);
+}
+
+// int(field) for the coordinate columns: optional sign, decimal digits
+__device__ __forceinline__ int32_t field_int(const uint8_t *text, uint32_t a, uint32_t b,
+                                             bool *good) {
+  bool neg = false;
+  if (a < b && (text[a] == '-' || text[a] == '+')) neg = text[a++] == '-';
+  bool g = a < b;
+  int64_t v = 0;
+  for (uint32_t p = a; p < b; ++p) {
+    const uint32_t d = (uint32_t)text[p] - '0';
+    if (d > 9) g = false;
+    v = v * 10 + d;
+    if (v > INT32_MAX) v = INT32_MAX;
+  }
+  if (!g) *good = false;
+  return (int32_t)(neg ? -v : v);
+}
+
+__global__ void line_fields_kernel(const uint8_t *text, int64_t n, const ParseOpts O,
                                    const uint32_t *line_start, int64_t n_lines,
-                                   LineRec *rec, int32_t *valid, int32_t *err) {
+                                   LineRec *rec, int32_t *valid, int32_t *err,
+                                   int32_t *xbeg, int32_t *xlen, int32_t *xspan) {
+  const int fmt = O.fmt;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_lines) return;
   const uint32_t s = line_start[i];
   uint32_t e = i + 1 < n_lines ? line_start[i + 1] - 1 : (uint32_t)n;  // excl. '\n'
   if (e > s && e <= n && text[e - 1] == '\n') --e;   // last line with '\n'
-  LineRec r = {0, 0, 0, 0};
+  LineRec r = {0, 0, 0, 0, 0};
   int ok = 0;
-  // positions of the first six tabs (e = not there)
-  uint32_t tab[6];
+  // positions of the first tabs (e = not there); field k = (tab[k-1], tab[k])
+  uint32_t tab[12];
   {
     uint32_t p = s;
-    const int need = fmt == PFMT_SAM ? 3 : fmt == PFMT_PAF ? 6 : 2;
+    const int need = fmt == PFMT_SAM   ? (O.extr ? 6 : 3)
+                     : fmt == PFMT_PAF ? (O.extr ? 12 : 6)
+                     : fmt == PFMT_B6O ? (O.extr ? 12 : 2)
+                                       : 2;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
+    for (int k = 0; k < 12; ++k) {
       if (k < need) {
         for (; p < e && text[p] != '\t'; ++p) {}
         tab[k] = p;
@@ -214,6 +271,24 @@ __global__ void line_fields_kernel(const uint8_t *text, int64_t n, int fmt,
       r.mate = (flag >> 6) & 3u;
       if (r.mate == 3u) atomicOr(err, PERR_FLAG);  // the reference's pool has no slot 3
       ok = !(r.rlen == 1 && text[r.roff] == '*');
+      if (O.extr) {
+        // parse_sam_file_ex (align.py:350-406): POS - 1 and the CIGAR lengths;
+        // a record without aligned length is dropped (ordinal.py:230-231)
+        if (tab[3] >= e || tab[4] >= e || tab[5] >= e) {
+          atomicOr(err, PERR_FIELDS);  // fewer than seven fields (split('\t', 6))
+          ok = 0;
+        } else if (ok) {
+          bool pg = true;
+          const int32_t pos = field_int(text, tab[2] + 1, tab[3], &pg);
+          if (!pg) atomicOr(err, PERR_FLAG);
+          int32_t al, sp;
+          cigar_lens(text + tab[4] + 1, tab[5] - tab[4] - 1, &al, &sp);
+          xbeg[i] = pos - 1;
+          xlen[i] = al;
+          xspan[i] = sp;
+          ok = al > 0 || O.keep_empty;
+        }
+      }
     }
   } else if (fmt == PFMT_B6O) {
     if (tab[0] < e && tab[1] < e) {  // at least three fields
@@ -222,12 +297,49 @@ __global__ void line_fields_kernel(const uint8_t *text, int64_t n, int fmt,
       r.rlen = tab[1] - tab[0] - 1;
       ok = 1;
     }
+    if (O.extr) {
+      // parse_b6o_file_ex (align.py:807-855): twelve fields or the line is
+      // skipped; length = field 3, (start, end) = sorted(fields 8, 9), start - 1
+      ok = ok && tab[10] < e;
+      if (ok) {
+        bool g = true;
+        const int32_t ln = field_int(text, tab[2] + 1, tab[3], &g);
+        int32_t a = field_int(text, tab[7] + 1, tab[8], &g);
+        int32_t b = field_int(text, tab[8] + 1, tab[9], &g);
+        if (!g) atomicOr(err, PERR_FLAG);  // int() raises in the reference
+        if (a > b) {
+          const int32_t t = a;
+          a = b;
+          b = t;
+        }
+        xbeg[i] = a - 1;
+        xlen[i] = ln;
+        xspan[i] = b - (a - 1);
+        ok = ln != 0 || O.keep_empty;
+      }
+    }
   } else if (fmt == PFMT_PAF) {
     if (tab[5] < e) {  // at least seven fields
       r.qlen = tab[0] - s;
       r.roff = tab[4] + 1;
       r.rlen = tab[5] - tab[4] - 1;
       ok = 1;
+    }
+    if (O.extr) {
+      // parse_paf_file_ex (align.py:1046-1088): (field 5, int(11), int(10),
+      // int(7), int(8)); a short line or a field that is no integer skips it
+      ok = ok && tab[10] < e;
+      if (ok) {
+        bool g = true;
+        const int32_t ln = field_int(text, tab[9] + 1, tab[10], &g);
+        const int32_t a = field_int(text, tab[6] + 1, tab[7], &g);
+        const int32_t b = field_int(text, tab[7] + 1, tab[8], &g);
+        (void)field_int(text, tab[10] + 1, tab[11], &g);
+        xbeg[i] = a;
+        xlen[i] = ln;
+        xspan[i] = b - a;
+        ok = g && (ln != 0 || O.keep_empty);
+      }
     }
   } else {
     if (tab[0] < e) {  // query <tab> subject [<tab> ...]
@@ -243,9 +355,26 @@ __global__ void line_fields_kernel(const uint8_t *text, int64_t n, int fmt,
       ok = 1;
     }
   }
+  // --trim-sub: everything from the last separator on goes (rsplit(sep, 1)[0])
+  r.tlen = r.rlen;
+  if (ok && O.trim_len > 0 && r.rlen >= (uint32_t)O.trim_len) {
+    for (int64_t p = (int64_t)r.rlen - O.trim_len; p >= 0; --p) {
+      bool eq = true;
+      for (int k = 0; k < O.trim_len; ++k) eq = eq && text[r.roff + p + k] == O.trim[k];
+      if (eq) {
+        r.tlen = (uint32_t)p;
+        break;
+      }
+    }
+  }
   rec[i] = r;
   valid[i] = ok;
 }
+
+// ---- 2b: --exclude (align.parse_*_file_ft, align.py:409-478 and the b6o / paf /
+// map variants): a QNAME group (all mates) goes when ANY of its records hits
+// an excluded subject (the RAW subject, before --trim-sub).
+// (kernels after the intern table below)
 
 // ---- 3: compaction ------------------------------------------------------------------
 __global__ void compact_lines_kernel(const int32_t *valid, const int32_t *vpos,
@@ -309,6 +438,28 @@ __global__ void order_kernel(const LineRec *rec, const uint32_t *vline,
   phead[out] = before == 0;
 }
 
+// Block mode (wk_parse_block, not the last block of a file): the records from
+// the head of the LAST group on wait for the next block - the group may go on
+// there (a query is never split, align.py:73-79).
+//   cut[0] = index of that head among the records, cut[1] = its line,
+//   cut[2] = byte offset of that line
+__global__ void last_head_kernel(const uint8_t *ghead, const uint32_t *vline,
+                                 const uint32_t *line_start, int64_t n_rec, int64_t from,
+                                 unsigned long long *cut) {
+  const int64_t j = from + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n_rec && ghead[j]) atomicMax(&cut[0], (unsigned long long)j);
+}
+__global__ void cut_point_kernel(const uint32_t *vline, const uint32_t *line_start,
+                                 unsigned long long *cut) {
+  const uint32_t line = vline[cut[0]];
+  cut[1] = line;
+  cut[2] = line_start[line];
+}
+__global__ void cut_lines_kernel(int32_t *valid, int64_t from, int64_t n_lines) {
+  const int64_t i = from + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_lines) valid[i] = 0;
+}
+
 // ---- 5: interning --------------------------------------------------------------------------
 struct InternTable {
   ull *keys;          // [cap] 64-bit hash, ~0 = empty
@@ -368,6 +519,75 @@ __device__ __forceinline__ int32_t intern_id(const InternTable &T, uint32_t slot
   return T.ids[slot];
 }
 
+__device__ __forceinline__ bool intern_has(const InternTable &T, const uint8_t *text,
+                                           uint32_t off, uint32_t len) {
+  const ull h = hash_bytes(text + off, len);
+  uint64_t i = h & T.cap_mask;
+  for (uint64_t probe = 0; probe <= T.cap_mask; ++probe) {
+    const ull k = T.keys[i];
+    if (k == ~0ull) return false;
+    if (k == h && T.slen[i] == len && same_bytes(T.pool + T.soff[i], text + off, len))
+      return true;
+    i = (i + 1) & T.cap_mask;
+  }
+  return false;
+}
+// names of the exclusion list -> table (one thread per name)
+__global__ void excl_load_kernel(InternTable T, const uint8_t *names, const uint32_t *off,
+                                 int32_t n, int32_t *err) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) intern_probe(T, names, off[i], off[i + 1] - off[i], err);
+}
+// gdrop[group head] = 1 when a record of the group hits an excluded subject
+__global__ void excl_mark_kernel(InternTable TX, const uint8_t *text, const LineRec *rec,
+                                 const uint32_t *vline, const uint8_t *ghead, int64_t n_rec,
+                                 uint8_t *gdrop, int32_t *err) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_rec) return;
+  const LineRec r = rec[vline[j]];
+  if (!intern_has(TX, text, r.roff, r.rlen)) return;
+  int64_t ga = j;
+  while (!ghead[ga]) {
+    --ga;
+    if (j - ga > (1 << 16)) {
+      atomicOr(err, PERR_GROUP);
+      break;
+    }
+  }
+  gdrop[ga] = 1;
+}
+// the lines of dropped groups are no longer valid
+__global__ void excl_apply_kernel(const uint32_t *vline, const uint8_t *ghead,
+                                  const uint8_t *gdrop, int64_t n_rec, const int32_t *xlen,
+                                  int32_t *valid, uint32_t *lhead, int32_t *err) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_rec) return;
+  int64_t ga = j;
+  while (!ghead[ga]) {
+    --ga;
+    if (j - ga > (1 << 16)) {
+      atomicOr(err, PERR_GROUP);
+      break;
+    }
+  }
+  // (records without aligned length were kept for the test above only)
+  if (gdrop[ga] || (xlen && xlen[vline[j]] == 0)) valid[vline[j]] = 0;
+  lhead[vline[j]] = vline[ga];  // the group this line stays in
+}
+// group heads of the lines that stayed: where the original group changes
+__global__ void regroup_heads_kernel(const uint32_t *lhead, const uint32_t *vline,
+                                     int64_t n_rec, uint8_t *ghead) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_rec) return;
+  ghead[j] = j == 0 || lhead[vline[j]] != lhead[vline[j - 1]];
+}
+__global__ void excl_verify_kernel(InternTable T, const uint8_t *names, const uint32_t *off,
+                                   int32_t n, int32_t *err) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !intern_has(T, names, off[i], off[i + 1] - off[i]))
+    atomicOr(err, PERR_COLLISION);
+}
+
 // subjects: slot per valid record (in input order)
 __global__ void subject_probe_kernel(InternTable T, const uint8_t *text, const LineRec *rec,
                                      const uint32_t *vline, int64_t n_rec,
@@ -375,7 +595,7 @@ __global__ void subject_probe_kernel(InternTable T, const uint8_t *text, const L
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_rec) return;
   const LineRec r = rec[vline[j]];
-  rslot[j] = intern_probe(T, text, r.roff, r.rlen, err);
+  rslot[j] = intern_probe(T, text, r.roff, r.tlen, err);
 }
 // sample prefix of a query name: [start, start+plen) (plen = 0: sample '')
 __device__ __forceinline__ uint32_t sample_prefix_len(const uint8_t *q, uint32_t qlen,
@@ -407,7 +627,9 @@ __global__ void emit_columns_kernel(InternTable TS, InternTable TP, int demux,
                                     const int32_t *qpos, const uint32_t *rslot,
                                     const uint32_t *sslot, int64_t n_rec, int32_t *q,
                                     int32_t *s, int32_t *q_sample, uint32_t *q_line,
-                                    int32_t *err) {
+                                    int32_t *err, const int32_t *xbeg, const int32_t *xlen,
+                                    const int32_t *xspan, int32_t *obeg, int32_t *oend,
+                                    int32_t *olen) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_rec) return;
   const uint32_t li = vline[j];
@@ -416,7 +638,13 @@ __global__ void emit_columns_kernel(InternTable TS, InternTable TP, int demux,
   // query index = number of pool heads at or before the slot, minus one
   const int32_t qi = qpos[out] + phead[out] - 1;
   q[out] = qi;
-  s[out] = intern_id(TS, rslot[j], text, r.roff, r.rlen, err);
+  s[out] = intern_id(TS, rslot[j], text, r.roff, r.tlen, err);
+  if (xbeg) {
+    // (subject, None, length, pos - 1, pos - 1 + span), align.py:398
+    obeg[out] = xbeg[li];
+    oend[out] = xbeg[li] + xspan[li];
+    olen[out] = xlen[li];
+  }
   if (phead[out]) {
     q_line[qi] = li | (r.mate << 30);  // where the query's name is (mate in the top bits)
     if (demux) {
@@ -432,6 +660,15 @@ __global__ void remap_samples_kernel(int32_t *q_sample, int64_t n_qry, const int
   if (i >= n_qry) return;
   const int32_t v = q_sample[i];
   q_sample[i] = (v >= 0 && v < n_map) ? map[v] : -1;
+}
+
+// out[i] = map[col[i]] (or -1): parsed subject index -> contig of the gene table
+__global__ void remap_column_kernel(const int32_t *col, int64_t n, const int32_t *map,
+                                    int32_t n_map, int32_t *out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t v = col[i];
+  out[i] = (v >= 0 && v < n_map) ? map[v] : -1;
 }
 
 }  // namespace wk

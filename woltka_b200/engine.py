@@ -344,6 +344,21 @@ class Engine:
             C.byref(n_rec), C.byref(n_qry), C.byref(n_sub), C.byref(n_smp)))
         return n_rec.value, n_qry.value, n_sub.value, n_smp.value
 
+    def parse_block(self, buf, demux=False, fmt='sam', final=True):
+        """Parse one block of a file (uint8 array, best page-locked); unless
+        `final`, the last query group and any cut line are left for the next
+        block.  Returns (consumed bytes, n_rec, n_qry, n_subjects_total,
+        n_samples_total) (wk_parse_block)."""
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        used, n_rec, n_qry = C.c_int64(), C.c_int64(), C.c_int64()
+        n_sub, n_smp = C.c_int32(), C.c_int32()
+        _lib.check(self.lib.wk_parse_block(
+            self.ctx, C.c_void_p(buf.ctypes.data), buf.nbytes,
+            self.FORMATS[fmt], int(bool(demux)), int(bool(final)),
+            C.byref(used), C.byref(n_rec), C.byref(n_qry), C.byref(n_sub),
+            C.byref(n_smp)))
+        return used.value, n_rec.value, n_qry.value, n_sub.value, n_smp.value
+
     def fetch_names(self, which, lo, hi):
         """Interned names [lo, hi) of the subject (0) / sample (1) table."""
         if hi <= lo:
@@ -380,6 +395,33 @@ class Engine:
         sm = _i32(sample_map)
         _lib.check(self.lib.wk_classify_parsed(
             self.ctx, _ptr(sm), 0 if sm is None else len(sm), sample))
+
+    def parse_options(self, trimsub=None, exclude=None, coords=False):
+        """Reader options for the chunks that follow (wk_parse_options):
+        `--trim-sub` separator, `--exclude` names, coordinates for the
+        coordinate matcher."""
+        trim = (trimsub or '').encode()
+        names = [x.encode() for x in (exclude or ())]
+        lens = np.asarray([len(x) for x in names], dtype=np.int32)
+        blob = b''.join(names)
+        _lib.check(self.lib.wk_parse_options(
+            self.ctx, C.cast(C.c_char_p(trim), C.c_void_p), len(trim),
+            C.cast(C.c_char_p(blob), C.c_void_p), _ptr(lens), len(names),
+            int(bool(coords))))
+
+    def fetch_parsed_coords(self, n_rec):
+        cols = [np.empty(n_rec, dtype=np.int32) for _ in range(3)]
+        _lib.check(self.lib.wk_parse_fetch_coords(self.ctx,
+                                                  *[_ptr(x) for x in cols]))
+        return cols
+
+    def ordinal_parsed(self, contig_map, th, sample_map=None, sample=0):
+        """Match + classify the last chunk parsed with coordinates."""
+        cm = _i32(contig_map)
+        sm = _i32(sample_map)
+        _lib.check(self.lib.wk_ordinal_parsed(
+            self.ctx, _ptr(cm), len(cm), float(th), _ptr(sm),
+            0 if sm is None else len(sm), sample))
 
     # -- subject coverage (--outcov) ------------------------------------------
     def cover_add(self, sample, subject, beg, end):

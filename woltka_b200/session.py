@@ -34,6 +34,12 @@ def _split_sample(query):
     return (left, right) if right else ('', right or left)
 
 
+def _as_bytes_array(text):
+    if isinstance(text, np.ndarray):
+        return text
+    return np.frombuffer(text, dtype=np.uint8)
+
+
 class Session:
     def __init__(self, ranks, tree=None, rankdic=None, root=None, uniq=False,
                  major=None, above=False, subok=False, unasgd=False,
@@ -132,9 +138,10 @@ class Session:
             self._matcher = None
 
     # -- vocabularies ------------------------------------------------------
-    def subject(self, name):
-        """Index of a subject string (after trimming), interning it."""
-        if self.trimsub:
+    def subject(self, name, trimmed=False):
+        """Index of a subject string (after trimming), interning it.
+        `trimmed`: the device reader has already cut the name."""
+        if self.trimsub and not trimmed:
             name = name.rsplit(self.trimsub, 1)[0]   # workflow.py:840-841
         idx = self.sub_index.get(name)
         if idx is not None:
@@ -291,15 +298,27 @@ class Session:
 
     # -- SAM text parsed on the device (wk_parse_sam) ---------------------------
     def can_parse_on_device(self):
-        """One engine, no --trim-sub, no read maps, and an engine that has
-        the device reader (the test stand-in engine does not)."""
-        return (len(self.engines) == 1 and not self.trimsub and
-                self.rank2dir is None and
+        """One engine, no read maps, a --trim-sub separator the reader can
+        hold, and an engine that has the device reader (the test stand-in
+        engine does not)."""
+        return (len(self.engines) == 1 and self.rank2dir is None and
+                len((self.trimsub or '').encode()) <= 8 and
                 not getattr(self, 'device_reader_off', False) and
                 hasattr(self.engines[0], 'parse_sam'))
 
+    def configure_reader(self, exclude=None, coords=False):
+        """Options of the device reader for this run (wk_parse_options):
+        --trim-sub applies to the subjects of the plain path only — with
+        --coords the reference cuts the gene identifiers, which `subject()`
+        does when they are interned."""
+        key = (bool(coords), id(exclude))
+        if getattr(self, '_reader_key', None) != key:
+            self.engines[0].parse_options(
+                None if coords else self.trimsub, exclude, coords)
+            self._reader_key = key
+
     def add_text_chunk_host(self, text, demux, sample_name, samples=None,
-                            fmt='sam', n=1024):
+                            fmt='sam', n=1024, exclude=None):
         """The same chunk of text through the host reader (the device
         reader's tables were full).  Subjects the device named keep their
         indices; from here on the host numbers the new ones, so the device
@@ -308,17 +327,26 @@ class Session:
         self.device_reader_off = True
         lines = iter(text.decode().splitlines(True))
         nqry = 0
-        for qryque, subque in plain_mapper(lines, fmt=fmt, n=n):
+        for qryque, subque in plain_mapper(lines, fmt=fmt, excl=exclude, n=n):
             nqry += len(qryque)
             self.add_chunk(qryque, subque, demux, sample_name, samples)
         return nqry
 
     def add_text_chunk(self, text, demux, sample_name, samples=None,
                        fmt='sam'):
-        """One chunk of SAM body text: lines -> queries -> indices on the
-        GPU (align.py:258-347, workflow.py:844-909); the host only names the
-        subjects and samples that appear for the first time.  Returns the
-        number of queries in the chunk."""
+        """A chunk that ends where a query ends (see add_text_block);
+        returns the number of queries in it."""
+        return self.add_text_block(text, True, demux, sample_name, samples,
+                                   fmt)[1]
+
+    def add_text_block(self, text, final, demux, sample_name, samples=None,
+                       fmt='sam'):
+        """One block of alignment text (bytes or a uint8 array, best
+        page-locked): lines -> queries -> indices on the GPU (align.py:258-347,
+        workflow.py:844-909); the host only names the subjects and samples
+        that appear for the first time.  Unless `final`, the device leaves the
+        last query group and any cut line for the next block
+        (wk_parse_block).  Returns (bytes consumed, queries classified)."""
         eng = self.engines[0]
         if not hasattr(self, '_dev_sub'):
             if self.sub_node:
@@ -326,24 +354,71 @@ class Session:
                                    'in one run')
             self._dev_sub = 0          # subjects named so far
             self._dev_smp = []         # device sample index -> plan sample
-        n_rec, n_qry, n_sub, n_smp = eng.parse_sam(text, demux, fmt)
+        used, n_rec, n_qry, n_sub, n_smp = eng.parse_block(
+            _as_bytes_array(text), demux, fmt, final)
         for name in eng.fetch_names(0, self._dev_sub, n_sub):
-            if self.subject(name) != self._dev_sub:
+            if self.subject(name, trimmed=True) != self._dev_sub:
                 raise RuntimeError('subject numbering diverged')
             self._dev_sub += 1
         if not n_rec:
-            return 0
+            return used, 0
         if demux:
-            for name in eng.fetch_names(1, len(self._dev_smp), n_smp):
-                keep = samples is None or name in samples
-                self._dev_smp.append(self.sample(name) if keep else -1)
+            self._name_device_samples(eng, n_smp, samples)
             self._sync_tables()
             eng.classify_parsed(np.asarray(self._dev_smp, dtype=np.int32))
         else:
             si = self.sample(sample_name)
             self._sync_tables()
             eng.classify_parsed(None, si)
-        return n_qry
+        return used, n_qry
+
+    def _name_device_samples(self, eng, n_smp, samples):
+        for name in eng.fetch_names(1, len(self._dev_smp), n_smp):
+            keep = samples is None or name in samples
+            self._dev_smp.append(self.sample(name) if keep else -1)
+
+    def add_text_chunk_ordinal(self, text, genes, th, demux, sample_name,
+                               samples=None, fmt='sam'):
+        return self.add_text_block_ordinal(text, True, genes, th, demux,
+                                           sample_name, samples, fmt)[1]
+
+    def add_text_block_ordinal(self, text, final, genes, th, demux,
+                               sample_name, samples=None, fmt='sam'):
+        """One block of alignment text for the coordinate matcher: the reader
+        (configured with coords) leaves query / contig / beg / end / len
+        columns on the device (align.py:350-406, 550-583, 807-855, 1046-1088),
+        the host names the contigs that appear for the first time, and the
+        matcher + classify kernels run on the resident columns
+        (ordinal.py:167-335, workflow.py:304-335).
+
+        A query is a run of adjacent lines with one name (per mate); the
+        reference also merges a name that comes back later in the same 2^20
+        record chunk (ordinal.py:332) but not across chunks — files grouped by
+        query, which every aligner writes, are unaffected.  Returns
+        (bytes consumed, queries in the block)."""
+        eng = self.engines[0]
+        if not hasattr(self, '_dev_contig'):
+            self._dev_contig = []      # device subject index -> contig index
+            self._dev_smp = []
+        used, n_rec, n_qry, n_sub, n_smp = eng.parse_block(
+            _as_bytes_array(text), demux, fmt, final)
+        lookup = genes.contig_index.get
+        for name in eng.fetch_names(0, len(self._dev_contig), n_sub):
+            self._dev_contig.append(lookup(name, -1))
+        if not n_rec:
+            return used, 0
+        genes.bind(self)
+        cmap = np.asarray(self._dev_contig, dtype=np.int32)
+        if demux:
+            self._name_device_samples(eng, n_smp, samples)
+            self._sync_tables()
+            eng.ordinal_parsed(cmap, th,
+                               np.asarray(self._dev_smp, dtype=np.int32))
+        else:
+            si = self.sample(sample_name)
+            self._sync_tables()
+            eng.ordinal_parsed(cmap, th, None, si)
+        return used, n_qry
 
     def _write_readmaps(self, n_rec, reads, starts, q_sample, stops=None):
         """Append this chunk's read-to-taxon lines (file.write_readmap,

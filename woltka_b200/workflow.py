@@ -39,6 +39,7 @@ from .ordinal import (load_gene_coords, load_gene_coords_cached,
 from .session import Session, _split_sample
 from ._lib import WoltkaB200Error
 from .coverage import range_mapper, Coverage, coverage_offsets
+from .reader import BlockReader
 
 __all__ = ['classify', 'build_mapper', 'assign_readmap', 'demultiplex',
            'strip_suffix', 'read_strata', 'readzip', 'range_mapper']
@@ -65,58 +66,23 @@ def openzip(fp, mode='rt'):
     return open(fp, mode.replace('t', '') if 'b' in mode else mode)
 
 
-def _text_chunks(fp, block=64 << 20, header=True):
-    """An alignment file as byte chunks that end at a line end and where the
-    query name changes (a query is never split, align.py:73-79); the leading
-    '@' lines of a SAM file are dropped (align.py:296-300)."""
-    opener = open
-    for ext, op in _OPENERS.items():
-        if fp.endswith(ext):
-            opener = op
-    with opener(fp, 'rb') as fh:
-        carry, first = b'', header
-        while True:
-            data = fh.read(block)
-            buf = carry + data
-            if first and buf:
-                # drop the complete '@' lines; an '@' line cut by the block
-                # end waits for the rest of it (the header may be longer than
-                # a block)
-                pos = 0
-                while buf[pos:pos + 1] == b'@':
-                    nl = buf.find(b'\n', pos)
-                    if nl < 0:
-                        break
-                    pos = nl + 1
-                buf = buf[pos:]
-                if buf[:1] == b'@' or not buf:
-                    if data:
-                        carry = buf
-                        continue
-                    return       # the file ends inside its header
-                first = False
-            if not data:
-                if buf:
-                    yield buf
-                return
-            end = buf.rfind(b'\n')
-            if end < 0:
-                carry = buf
-                continue
-            # back over the trailing lines that share the last query name
-            ls = buf.rfind(b'\n', 0, end) + 1
-            name = buf[ls:end].split(b'\t', 1)[0]
-            cut = ls
-            while cut > 0:
-                ps = buf.rfind(b'\n', 0, cut - 1) + 1
-                if buf[ps:cut - 1].split(b'\t', 1)[0] != name:
-                    break
-                cut = ps
-            if cut == 0:
-                carry = buf
-                continue
-            yield buf[:cut]
-            carry = buf[cut:]
+def _host_cut(text):
+    """Bytes of a block that end at a line end and where the query name
+    changes (a query is never split, align.py:73-79): what wk_parse_block
+    consumes, for the host reader."""
+    end = text.rfind(b'\n')
+    if end < 0:
+        return 0
+    # back over the trailing lines that share the last query name
+    ls = text.rfind(b'\n', 0, end) + 1
+    name = text[ls:end].split(b'\t', 1)[0]
+    cut = ls
+    while cut > 0:
+        ps = text.rfind(b'\n', 0, cut - 1) + 1
+        if text[ps:cut - 1].split(b'\t', 1)[0] != name:
+            break
+        cut = ps
+    return cut
 
 
 # which reader fed the last file of the last classify() call ('device' | 'host')
@@ -255,35 +221,63 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
                           samples=samset if demux else None,
                           strata_of=strata_of if stratmap else None)
             nqry, nstep = 0, -1
-            on_device = (not is_ordinal and fp != '-' and not exclude and
-                         not stratmap and mapper is plain_mapper and
+            on_device = (fp != '-' and not stratmap and
+                         (is_ordinal or mapper is plain_mapper) and
+                         not (is_ordinal and rank2dir) and
                          not os.environ.get('WOLTKA_B200_HOST_READER') and
                          sess.can_parse_on_device())
             dfmt = _device_format(fileobj, fmt) if on_device else None
-            on_device = dfmt is not None
+            on_device = dfmt is not None and not (is_ordinal and dfmt == 'map')
             global LAST_READER
             LAST_READER = 'device' if on_device else 'host'
             try:
                 if on_device:
-                    for text in _text_chunks(fp, header=dfmt == 'sam'):
+                    # text -> columns (-> read-gene matches) -> counts, all on
+                    # the device; the host moves blocks of bytes
+                    sess.configure_reader(exclude, coords=is_ordinal)
+                    common = (bool(demux), sname, samset if demux else None,
+                              dfmt)
+
+                    def host_chunk(text):
+                        lines = iter(text.decode().splitlines(True))
+                        if not is_ordinal:
+                            return sess.add_text_chunk_host(
+                                text, *common, chunk or 1024, exclude)
+                        n = 0
+                        for qn, cn, bg, en, ln in iter_records(
+                                lines, dfmt, exclude, chunk or 2 ** 20):
+                            n += len(set(qn))
+                            sess.add_ordinal_chunk(genes, qn, cn, bg, en, ln,
+                                                   th, **kwargs)
+                        return n
+
+                    blocks = BlockReader(fp, header=dfmt == 'sam')
+                    for view, final in blocks:
                         if sess.can_parse_on_device():
                             try:
-                                nqry += sess.add_text_chunk(
-                                    text, bool(demux), sname,
-                                    samset if demux else None, dfmt)
+                                if is_ordinal:
+                                    used, n = sess.add_text_block_ordinal(
+                                        view, final, genes, th, *common)
+                                else:
+                                    used, n = sess.add_text_block(
+                                        view, final, *common)
+                                blocks.consumed(used)
+                                nqry += n
                                 continue
                             except WoltkaB200Error as err:
                                 if err.code != 5:      # WK_ERR_CAPACITY
                                     raise
                                 # the device reader's tables are full (> 1M
                                 # subjects, 64 MiB of names, 32k samples or a
-                                # 64k-line query): this chunk and the rest
+                                # 64k-line query): this block and the rest
                                 # of the run go through the host reader
                                 sess.device_reader_off = True
                                 LAST_READER = 'host'
-                        nqry += sess.add_text_chunk_host(
-                            text, bool(demux), sname,
-                            samset if demux else None, dfmt, chunk or 1024)
+                        text = view.tobytes()
+                        used = len(text) if final else _host_cut(text)
+                        blocks.consumed(used)
+                        if used:
+                            nqry += host_chunk(text[:used])
                         istep = nqry // 1000000 - nstep
                         if istep:
                             _echo('.' * istep, nl=False)
