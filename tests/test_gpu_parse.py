@@ -299,8 +299,9 @@ def test_sam_coordinates_on_device(with_excl):
         got = device_records(eng, text)
         exp = host_records(text, excl=excl)
         if not with_excl:
-            exp = merge_adjacent(exp)
-            got = merge_adjacent(got)
+            # (which of two merged groups names the query first is open)
+            exp = sorted(merge_adjacent(exp))
+            got = sorted(merge_adjacent(got))
         assert got == exp
     with pytest.raises(Exception):
         eng.classify_parsed(None, 0)     # parsed for the matcher, not for classify
@@ -330,8 +331,8 @@ def test_b6o_paf_coordinates_on_device():
     eng.parse_options(None, None, coords=True)
     for fmt, rows in (('b6o', b6o), ('paf', paf)):
         text = ('\n'.join(rows) + '\n').encode()
-        got = merge_adjacent(device_records(eng, text, fmt=fmt))
-        exp = merge_adjacent(host_records(text, fmt))
+        got = sorted(merge_adjacent(device_records(eng, text, fmt=fmt)))
+        exp = sorted(merge_adjacent(host_records(text, fmt)))
         assert got == exp, fmt
     eng.close()
 

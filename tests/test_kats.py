@@ -335,3 +335,30 @@ def test_chunk_loop_helpers_under_their_reference_names(tmp_path):
     with pytest.raises(ValueError, match='No stratification information is '
                                          'found in file: tree.nwk.'):
         read_strata(str(bad))
+
+
+def test_subjects_bulk_equals_subject_by_subject():
+    """Session.subjects_bulk (gene identifiers of a coordinates file) leaves
+    the vocabularies and table rows exactly as one subject() per name does."""
+    from woltka_b200.session import Session
+    tree = {'a': 'r', 'b': 'r', 'a1': 'a', 'a2': 'a', 'b1': 'b', 'r': 'r'}
+    rankdic = {'a': 'genus', 'b': 'genus', 'a1': 'species', 'a2': 'species',
+               'b1': 'species'}
+    names = ['a1', 'zz_1', 'a2', 'b1', 'a1', 'zz_2', 'a', 'yy', 'b1_3']
+    for ranks, subok, trim in ((['none', 'free', 'genus', 'species'], False, None),
+                               (['free'], True, None), (['genus'], False, '_')):
+        def make():
+            return Session(ranks, tree, rankdic, 'r', False, None, False, subok,
+                           False, trim,
+                           make_factory(tree, rankdic, 'r', ranks, subok), 0,
+                           None, None, None, None, False)
+        one, bulk = make(), make()
+        one.subject('b')
+        bulk.subject('b')
+        assert [one.subject(n) for n in names] == \
+            bulk.subjects_bulk(names).tolist()
+        for field in ('sub_node', 'sub_feat', 'sub_name', 'sub_stratum',
+                      '_tab_rows', 'extra_names', 'sub_index', 'extra_index'):
+            assert getattr(one, field) == getattr(bulk, field), field
+        one.close()
+        bulk.close()

@@ -180,7 +180,8 @@ class GeneIndex:
         """Subject index of every gene in `session` (interning the gene
         identifiers on first use)."""
         if getattr(self, '_subj_of', None) is not session:
-            self._subj = np.fromiter(
+            bulk = getattr(session, 'subjects_bulk', None)
+            self._subj = bulk(self.gene_ids) if bulk else np.fromiter(
                 (session.subject(g) for g in self.gene_ids), dtype=np.int32,
                 count=len(self.gene_ids))
             self._subj_of = session

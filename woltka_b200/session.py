@@ -172,6 +172,56 @@ class Session:
         self._dirty = True
         return idx
 
+    def subjects_bulk(self, names):
+        """subject() for many names at once (the gene identifiers of a
+        coordinates file): int32 indices; the per-name work is a dict
+        look-up, the table rows are filled by numpy."""
+        if self.trimsub:
+            sep = self.trimsub
+            names = [x.rsplit(sep, 1)[0] for x in names]
+        index = self.sub_index
+        base = len(self.sub_node)
+        new = [x for x in dict.fromkeys(names) if x not in index]
+        index.update(zip(new, range(base, base + len(new))))
+        out = np.fromiter(map(index.__getitem__, names), dtype=np.int32,
+                          count=len(names))
+        if not new:
+            return out
+        if self.ft is not None:
+            self.ft.node_of(new[0])              # (builds the index)
+            get = self.ft.index.get
+            node = np.asarray([get(x, -1) for x in new], dtype=np.int32)
+        else:
+            node = np.full(len(new), -1, dtype=np.int32)
+        feat = node.copy()
+        extra = self.extra_index
+        unknown = np.flatnonzero(node < 0)
+        if len(unknown):
+            missing = new if len(unknown) == len(new) else \
+                [new[k] for k in unknown.tolist()]
+            fresh = [x for x in missing if x not in extra]
+            at = self.T + len(self.extra_names)
+            extra.update(zip(fresh, range(at, at + len(fresh))))
+            self.extra_names.extend(fresh)
+            feat[unknown] = np.fromiter(map(extra.__getitem__, missing),
+                                        dtype=np.int32, count=len(missing))
+        self.sub_node.extend(node.tolist())
+        self.sub_feat.extend(feat.tolist())
+        self.sub_name.extend(new)
+        self.sub_stratum.extend([-1] * len(new))
+        known = node >= 0
+        safe = np.where(known, node, 0)
+        for e, kind in enumerate(self.kinds):
+            if kind == KIND_RANK:
+                v = np.where(known, self._rank_tabs[e][safe], -1)
+            elif kind == KIND_FREE and not self.subok:
+                v = np.where(known, np.asarray(self.ft.parent)[safe], -1)
+            else:
+                v = feat
+            self._tab_rows[e].extend(v.tolist())
+        self._dirty = True
+        return out
+
     def subject_in_stratum(self, base, stratum):
         """Device subject standing for subject index `base` seen in a query of
         `stratum`: a copy of its table entries under a new index."""
@@ -624,6 +674,32 @@ class Session:
             return self.ft.ids[f]
         return self.extra_names[f - self.T]
 
+    def _dense_results(self, data, grp, units):
+        """Profiles of one engine from its units table [E, S, NF+1]."""
+        named = (list(self.ft.ids) if self.ft is not None else []) + \
+            self.extra_names
+        n_named = len(named)
+        for e in range(units.shape[0]):
+            rank = self.order[grp[e]]
+            mult = self.mult[rank]
+            for si in range(min(units.shape[1], len(self.sample_names))):
+                row = units[e, si]
+                f = np.flatnonzero(row)
+                if not len(f):
+                    continue
+                v = row[f].astype(np.int64)
+                whole = v % UNITS == 0
+                # (feature NF = 'Unassigned' lies past the named ones)
+                keys = [named[i] if i < n_named else self.feature_name(i)
+                        for i in f.tolist()]
+                if whole.all():
+                    vals = (v // UNITS * mult).tolist()
+                else:
+                    vals = [x // UNITS * mult if w else
+                            Fraction(x, UNITS) * mult
+                            for x, w in zip(v.tolist(), whole.tolist())]
+                data[rank][self.sample_names[si]].update(zip(keys, vals))
+
     def results(self):
         """{rank: {sample: {feature | (stratum, feature): count}}} with exact
         counts: int when integral, else the correctly rounded double."""
@@ -647,6 +723,11 @@ class Session:
                 for e, s, t, f, u in zip(e_.tolist(), s_.tolist(), t_.tolist(),
                                          f_.tolist(), u_.tolist()):
                     cells[(e, s, t, f)] = Fraction(u, UNITS)
+            elif len(ocell) == 0:
+                # no stratified cells, no overflow shares: whole profiles at
+                # once (a whole count stays an int - also an exact rational)
+                self._dense_results(data, grp, eng.fetch_counts())
+                continue
             else:
                 units = eng.fetch_counts()
                 for e, s, f in zip(*np.nonzero(units)):
@@ -672,7 +753,6 @@ def finalize(data):
     else the correctly rounded double (in place; returns `data`)."""
     for samples in data.values():
         for prof in samples.values():
-            for key, v in prof.items():
-                if isinstance(v, Fraction):
-                    prof[key] = int(v) if v.denominator == 1 else float(v)
+            for key, v in [kv for kv in prof.items() if type(kv[1]) is Fraction]:
+                prof[key] = int(v) if v.denominator == 1 else float(v)
     return data
