@@ -7,7 +7,7 @@ import numpy as np
 sys.path.insert(0, '.')
 from woltka_b200 import synth, workflow
 
-n_rec = int(sys.argv[1]) if len(sys.argv) > 1 else 6_000_000
+n_rec = int(sys.argv[1]) if len(sys.argv) > 1 else 12_000_000
 tax = synth.Taxonomy(seed=42)
 ids = tax.ids()
 tree = {ids[i]: ids[tax.parent[i]] for i in range(tax.T)}
@@ -45,7 +45,7 @@ for name, env in (('device_reader', None), ('host_reader', '1')):
 assert abs(res['device_reader']['checksum'] - res['host_reader']['checksum']) < 1e-6
 
 # ---- --coords: cfg3-shaped reads against a gene table (1000 contigs x 1000 genes)
-n_ord = int(sys.argv[2]) if len(sys.argv) > 2 else 12_000_000
+n_ord = int(sys.argv[2]) if len(sys.argv) > 2 else 30_000_000
 d = os.path.dirname(fp)
 co, gb, ge = synth.gen_genes(1000, 1000)
 synth.write_coords(os.path.join(d, 'coords.txt'), co, gb, ge)

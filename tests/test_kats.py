@@ -345,18 +345,28 @@ def test_subjects_bulk_equals_subject_by_subject():
     rankdic = {'a': 'genus', 'b': 'genus', 'a1': 'species', 'a2': 'species',
                'b1': 'species'}
     names = ['a1', 'zz_1', 'a2', 'b1', 'a1', 'zz_2', 'a', 'yy', 'b1_3']
-    for ranks, subok, trim in ((['none', 'free', 'genus', 'species'], False, None),
-                               (['free'], True, None), (['genus'], False, '_')):
+    cases = [(ranks, subok, trim, prior)
+             for ranks, subok, trim in (
+                 (['none', 'free', 'genus', 'species'], False, None),
+                 (['free'], True, None), (['genus'], False, '_'))
+             for prior in (True, False)]
+    for ranks, subok, trim, prior in cases:
         def make():
             return Session(ranks, tree, rankdic, 'r', False, None, False, subok,
                            False, trim,
                            make_factory(tree, rankdic, 'r', ranks, subok), 0,
                            None, None, None, None, False)
         one, bulk = make(), make()
-        one.subject('b')
-        bulk.subject('b')
+        if prior:
+            one.subject('b')
+            bulk.subject('b')
         assert [one.subject(n) for n in names] == \
             bulk.subjects_bulk(names).tolist()
+        # asking by name afterwards finds the bulk entries
+        for n in ('yy', 'fresh', 'a2', 'zz_9'):
+            assert one.subject(n) == bulk.subject(n)
+        assert one.subjects_bulk(['k1', 'a1', 'k1']).tolist() == \
+            bulk.subjects_bulk(['k1', 'a1', 'k1']).tolist()
         for field in ('sub_node', 'sub_feat', 'sub_name', 'sub_stratum',
                       '_tab_rows', 'extra_names', 'sub_index', 'extra_index'):
             assert getattr(one, field) == getattr(bulk, field), field

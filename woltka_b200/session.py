@@ -89,7 +89,8 @@ class Session:
         self.major_th = float(major) if major else 0.0
 
         # vocabularies
-        self.sub_index = {}
+        self._sub_index = {}         # name -> subject index, built on demand
+        self._sub_done = 0           # (entries of sub_name it covers)
         self.sub_node = []
         self.sub_feat = []
         # --sizes with --stratify: a subject seen in stratum t is its own
@@ -100,7 +101,8 @@ class Session:
         self.sub_stratum = []        # subject index -> stratum index or -1
         self._pair_index = {}        # (subject index, stratum) -> index
         self.extra_names = []        # features beyond the tree
-        self.extra_index = {}
+        self._extra_index = {}       # the same for extra_names
+        self._extra_done = 0
         self.sample_index = {}
         self.sample_names = []
         self.file_index = 0          # set by classify() before each file
@@ -138,26 +140,59 @@ class Session:
             self._matcher = None
 
     # -- vocabularies ------------------------------------------------------
+    @property
+    def sub_index(self):
+        """name -> subject index.  subjects_bulk() only appends to the lists;
+        the dict catches up when somebody asks by name."""
+        k = self._sub_done
+        if k != len(self.sub_name):
+            names, strata = self.sub_name[k:], self.sub_stratum[k:]
+            if any(t != -1 for t in strata):
+                # (the per-stratum copies of subject_in_stratum have no name
+                # of their own)
+                for i, (name, t) in enumerate(zip(names, strata), k):
+                    if t == -1:
+                        self._sub_index[name] = i
+            else:
+                self._sub_index.update(zip(names, range(k, k + len(names))))
+            self._sub_done = len(self.sub_name)
+        return self._sub_index
+
+    @property
+    def extra_index(self):
+        k = self._extra_done
+        if k != len(self.extra_names):
+            self._extra_index.update(zip(
+                self.extra_names[k:],
+                range(self.T + k, self.T + len(self.extra_names))))
+            self._extra_done = len(self.extra_names)
+        return self._extra_index
+
     def subject(self, name, trimmed=False):
         """Index of a subject string (after trimming), interning it.
         `trimmed`: the device reader has already cut the name."""
         if self.trimsub and not trimmed:
             name = name.rsplit(self.trimsub, 1)[0]   # workflow.py:840-841
-        idx = self.sub_index.get(name)
+        index = self._sub_index if self._sub_done == len(self.sub_name) \
+            else self.sub_index
+        idx = index.get(name)
         if idx is not None:
             return idx
-        idx = self.sub_index[name] = len(self.sub_node)
+        idx = index[name] = len(self.sub_node)
         node = self.ft.node_of(name) if self.ft else -1
         if node >= 0:
             feat = node
         else:
-            feat = self.extra_index.get(name)
+            extra = self.extra_index
+            feat = extra.get(name)
             if feat is None:
-                feat = self.extra_index[name] = self.T + len(self.extra_names)
+                feat = extra[name] = self.T + len(self.extra_names)
                 self.extra_names.append(name)
+                self._extra_done += 1
         self.sub_node.append(node)
         self.sub_feat.append(feat)
         self.sub_name.append(name)
+        self._sub_done += 1
         self.sub_stratum.append(-1)
         for e, kind in enumerate(self.kinds):
             if kind == KIND_RANK:
@@ -179,12 +214,24 @@ class Session:
         if self.trimsub:
             sep = self.trimsub
             names = [x.rsplit(sep, 1)[0] for x in names]
-        index = self.sub_index
         base = len(self.sub_node)
-        new = [x for x in dict.fromkeys(names) if x not in index]
-        index.update(zip(new, range(base, base + len(new))))
-        out = np.fromiter(map(index.__getitem__, names), dtype=np.int32,
-                          count=len(names))
+        if base == 0:
+            # the first subjects of the run: nothing to look up, and the name
+            # index is only built if somebody asks by name later
+            new = list(dict.fromkeys(names))
+            if len(new) == len(names):
+                out = np.arange(len(names), dtype=np.int32)
+            else:
+                order = dict(zip(new, range(len(new))))
+                out = np.fromiter(map(order.__getitem__, names),
+                                  dtype=np.int32, count=len(names))
+        else:
+            index = self.sub_index
+            new = [x for x in dict.fromkeys(names) if x not in index]
+            index.update(zip(new, range(base, base + len(new))))
+            self._sub_done += len(new)   # (sub_name is extended below)
+            out = np.fromiter(map(index.__getitem__, names), dtype=np.int32,
+                              count=len(names))
         if not new:
             return out
         if self.ft is not None:
@@ -194,17 +241,22 @@ class Session:
         else:
             node = np.full(len(new), -1, dtype=np.int32)
         feat = node.copy()
-        extra = self.extra_index
         unknown = np.flatnonzero(node < 0)
         if len(unknown):
             missing = new if len(unknown) == len(new) else \
                 [new[k] for k in unknown.tolist()]
-            fresh = [x for x in missing if x not in extra]
             at = self.T + len(self.extra_names)
-            extra.update(zip(fresh, range(at, at + len(fresh))))
-            self.extra_names.extend(fresh)
-            feat[unknown] = np.fromiter(map(extra.__getitem__, missing),
-                                        dtype=np.int32, count=len(missing))
+            if not self.extra_names:
+                self.extra_names.extend(missing)
+                feat[unknown] = np.arange(at, at + len(missing), dtype=np.int32)
+            else:
+                extra = self.extra_index
+                fresh = [x for x in missing if x not in extra]
+                extra.update(zip(fresh, range(at, at + len(fresh))))
+                self.extra_names.extend(fresh)
+                self._extra_done += len(fresh)
+                feat[unknown] = np.fromiter(map(extra.__getitem__, missing),
+                                            dtype=np.int32, count=len(missing))
         self.sub_node.extend(node.tolist())
         self.sub_feat.extend(feat.tolist())
         self.sub_name.extend(new)
@@ -229,10 +281,13 @@ class Session:
         idx = self._pair_index.get(key)
         if idx is None:
             idx = self._pair_index[key] = len(self.sub_node)
+            current = self._sub_done == len(self.sub_name)
             self.sub_node.append(self.sub_node[base])
             self.sub_feat.append(self.sub_feat[base])
             self.sub_name.append(self.sub_name[base])
             self.sub_stratum.append(stratum)
+            if current:
+                self._sub_done += 1      # (a copy: not in the name index)
             for row in self._tab_rows:
                 row.append(row[base])
             self._dirty = True
@@ -674,8 +729,11 @@ class Session:
             return self.ft.ids[f]
         return self.extra_names[f - self.T]
 
-    def _dense_results(self, data, grp, units):
-        """Profiles of one engine from its units table [E, S, NF+1]."""
+    def _dense_results(self, data, grp, units, final=False):
+        """Profiles of one engine from its units table [E, S, NF+1]; `final`:
+        a count that is not whole comes as the correctly rounded double
+        straight away (x / UNITS in float64 is exactly that while x < 2^53)
+        instead of as a Fraction."""
         named = (list(self.ft.ids) if self.ft is not None else []) + \
             self.extra_names
         n_named = len(named)
@@ -692,20 +750,24 @@ class Session:
                 # (feature NF = 'Unassigned' lies past the named ones)
                 keys = [named[i] if i < n_named else self.feature_name(i)
                         for i in f.tolist()]
-                if whole.all():
-                    vals = (v // UNITS * mult).tolist()
-                else:
-                    vals = [x // UNITS * mult if w else
-                            Fraction(x, UNITS) * mult
-                            for x, w in zip(v.tolist(), whole.tolist())]
+                vals = (v // UNITS * mult).tolist()
+                part = np.flatnonzero(~whole)
+                if len(part):
+                    x = v[part] * mult
+                    if final and int(x.max()) < (1 << 53):
+                        shares = (x / UNITS).tolist()
+                    else:
+                        shares = [Fraction(y, UNITS) for y in x.tolist()]
+                    for k, y in zip(part.tolist(), shares):
+                        vals[k] = y
                 data[rank][self.sample_names[si]].update(zip(keys, vals))
 
     def results(self):
         """{rank: {sample: {feature | (stratum, feature): count}}} with exact
         counts: int when integral, else the correctly rounded double."""
-        return finalize(self.exact_results())
+        return finalize(self.exact_results(final=True))
 
-    def exact_results(self):
+    def exact_results(self, final=False):
         """The same dict with the counts as exact Fractions (floats with
         --sizes): what `distributed.merge_profiles` sums across ranks."""
         data = {rank: {} for rank in self.order}
@@ -726,7 +788,7 @@ class Session:
             elif len(ocell) == 0:
                 # no stratified cells, no overflow shares: whole profiles at
                 # once (a whole count stays an int - also an exact rational)
-                self._dense_results(data, grp, eng.fetch_counts())
+                self._dense_results(data, grp, eng.fetch_counts(), final)
                 continue
             else:
                 units = eng.fetch_counts()
