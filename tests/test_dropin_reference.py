@@ -110,9 +110,10 @@ def run_all(tmp_path, monkeypatch, engine):
                 kw.get('ranks'), kw.get('subok', False))
         return ours.classify(**kw)
 
-    # the two seams (workflow.py:128 and :138)
+    # the seams (workflow.py:86, :128 and :138)
     monkeypatch.setattr(wf, 'classify', classify)
     monkeypatch.setattr(wf, 'build_mapper', ours.build_mapper)
+    monkeypatch.setattr(wf, 'build_hierarchy', ours.build_hierarchy)
     datdir = join(WHERE, 'woltka', 'tests', 'data')
     output_fp = str(tmp_path / 'output.tsv')
     runner = CliRunner()

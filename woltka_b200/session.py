@@ -58,8 +58,11 @@ class Session:
         self.rank2dir = rank2dir
         self.outzip = outzip if outzip != 'none' else None
         self.namedic = namedic
-        self.ft = FlatTree.from_dicts(tree, rankdic, root) \
-            if tree is not None else None
+        # (a tree from loaders.build_hierarchy brings its flat form along)
+        flat = getattr(tree, 'flat_tree', None)
+        self.ft = flat and flat(rankdic, root)
+        if self.ft is None and tree is not None:
+            self.ft = FlatTree.from_dicts(tree, rankdic, root)
         self.T = self.ft.n_nodes if self.ft else 0
 
         # how each entry is assigned (workflow.py:1017-1032)

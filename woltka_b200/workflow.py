@@ -40,8 +40,9 @@ from .session import Session, _split_sample
 from ._lib import WoltkaB200Error
 from .coverage import range_mapper, Coverage, coverage_offsets
 from .reader import BlockReader
+from .loaders import build_hierarchy
 
-__all__ = ['classify', 'build_mapper', 'assign_readmap', 'demultiplex',
+__all__ = ['classify', 'build_mapper', 'build_hierarchy', 'assign_readmap', 'demultiplex',
            'strip_suffix', 'read_strata', 'readzip', 'range_mapper']
 
 _OPENERS = {'.gz': gzip.open, '.bz2': bz2.open, '.xz': lzma.open,
