@@ -52,46 +52,63 @@ class FlatTree:
         tree.py:510) and ValueError for nodes that never reach a root.
         """
         rankdic = rankdic or {}
-        children = {}
-        roots = []
-        for node, par in tree.items():
-            if par == node:
-                roots.append(node)
-                continue
-            if par not in tree:
-                raise KeyError(par)
-            children.setdefault(par, []).append(node)
-        ids, parent, level_off = [], [], [0]
-        frontier = [(r, -1) for r in roots]
-        while frontier:
-            nxt = []
-            for node, pidx in frontier:
-                idx = len(ids)
-                ids.append(node)
-                parent.append(idx if pidx < 0 else pidx)
-                for ch in children.get(node, ()):
-                    nxt.append((ch, idx))
-            level_off.append(len(ids))
+        keys = list(tree)
+        n = len(keys)
+        index = dict(zip(keys, range(n)))
+        try:
+            par = np.fromiter(map(index.__getitem__, tree.values()),
+                              dtype=np.int64, count=n)
+        except KeyError as err:          # a parent that is no key (or None)
+            raise KeyError(err.args[0]) from None
+        me = np.arange(n, dtype=np.int64)
+        is_root = par == me
+        # children of every node, in dict order: a stable sort by parent
+        kids = np.argsort(np.where(is_root, n, par), kind='stable')
+        n_kids = np.bincount(par[~is_root], minlength=n)
+        first = np.concatenate([[0], np.cumsum(n_kids)[:-1]])
+        # breadth first: a level is the children of the level above, parent
+        # by parent
+        order = np.empty(n, dtype=np.int64)       # new index -> old index
+        new_par = np.empty(n, dtype=np.int64)     # in new indices
+        frontier = np.flatnonzero(is_root)
+        level_off, done = [0], 0
+        new_par[:len(frontier)] = np.arange(len(frontier))
+        while len(frontier):
+            m = len(frontier)
+            order[done:done + m] = frontier
+            cnt = n_kids[frontier]
+            total = int(cnt.sum())
+            if done + m + total > n:
+                break                              # (cannot happen in a forest)
+            # position of every child in `kids`
+            starts = np.repeat(first[frontier], cnt)
+            within = np.arange(total) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+            nxt = kids[starts + within]
+            new_par[done + m:done + m + total] = np.repeat(
+                np.arange(done, done + m), cnt)
+            done += m
+            level_off.append(done)
             frontier = nxt
-        if len(ids) != len(tree):
+        if done != n:
             raise ValueError('Hierarchy contains nodes that do not descend '
                              'from a root (cycle or dangling parent).')
-        rank_names = []
-        rank_index = {}
-        node_rank = np.full(len(ids), -1, dtype=np.int32)
-        for i, node in enumerate(ids):
-            r = rankdic.get(node)
-            if r is None:
-                continue
-            j = rank_index.get(r)
-            if j is None:
-                j = rank_index[r] = len(rank_names)
-                rank_names.append(r)
-            node_rank[i] = j
-        ft = cls(ids, np.asarray(parent, dtype=np.int32), node_rank,
-                 rank_names, level_off, -1)
-        ft.index = {x: i for i, x in enumerate(ids)}
-        ft.n_roots = len(roots)
+        ids = [keys[i] for i in order.tolist()]
+        rank_names, rank_index = [], {}
+        node_rank = np.full(n, -1, dtype=np.int32)
+        if rankdic:
+            get = rankdic.get
+            ranks = [get(x) for x in ids]
+            for r in dict.fromkeys(ranks):         # first appearance order
+                if r is not None:
+                    rank_index[r] = len(rank_names)
+                    rank_names.append(r)
+            rank_index[None] = -1
+            node_rank = np.fromiter(map(rank_index.__getitem__, ranks),
+                                    dtype=np.int32, count=n)
+        ft = cls(ids, new_par.astype(np.int32), node_rank, rank_names,
+                 level_off, -1)
+        ft.index = dict(zip(ids, range(n)))
+        ft.n_roots = int(is_root.sum())
         ft.root = ft.index.get(root, -1) if root is not None else -1
         return ft
 

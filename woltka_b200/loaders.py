@@ -16,6 +16,7 @@ tree.py:302-388).  Two things are added on the way:
     WoL / NCBI scale taxonomy (millions of nodes) loads in the time it takes
     to read that file instead of being parsed line by line again.
 """
+import gc
 import hashlib
 import os
 import pickle
@@ -52,32 +53,44 @@ class TreeDict(dict):
             self.flat_for == key else None
 
 
-def _dmp_fields(line):
-    # names.dmp / nodes.dmp rows end in "\t|": drop the bars, split on tabs
-    return line.rstrip().replace('\t|', '').split('\t')
+_LINE_END_BLANKS = re.compile(r'[^\S\n]+$', re.M)
+
+
+def _dmp_rows(fh):
+    """Fields of every line of a names.dmp / nodes.dmp style table, as
+    `line.rstrip().replace('\t|', '').split('\t')` gives them (tree.py:66, 98)
+    - done on the whole text at once: trailing blanks of every line go first,
+    then the bars, then the lines and fields are split."""
+    text = fh.read()
+    if text.endswith('\n'):
+        text = text[:-1]
+    if not text:
+        return []
+    text = _LINE_END_BLANKS.sub('', text).replace('\t|', '')
+    # (millions of small lists: the cyclic collector would walk them again
+    # and again while they are made)
+    was_on = gc.isenabled()
+    gc.disable()
+    try:
+        return [line.split('\t') for line in text.split('\n')]
+    finally:
+        if was_on:
+            gc.enable()
 
 
 def read_names(fh):
     """Taxon names: NCBI names.dmp (scientific names only) or a plain map
     (tree.py:48-71)."""
-    names = {}
-    for line in fh:
-        x = _dmp_fields(line)
-        if len(x) < 4 or x[3] == 'scientific name':
-            names[x[0]] = x[1]
-    return names
+    return {x[0]: x[1] for x in _dmp_rows(fh)
+            if len(x) < 4 or x[3] == 'scientific name'}
 
 
 def read_nodes(fh):
     """Taxon -> parent and (where given) -> rank: NCBI nodes.dmp or a plain
     table (tree.py:74-103)."""
-    tree, rankdic = {}, {}
-    for line in fh:
-        x = _dmp_fields(line)
-        tree[x[0]] = x[1]
-        if len(x) > 2:
-            rankdic[x[0]] = x[2]
-    return tree, rankdic
+    rows = _dmp_rows(fh)
+    return ({x[0]: x[1] for x in rows},
+            {x[0]: x[2] for x in rows if len(x) > 2})
 
 
 def read_newick(fh):
@@ -199,6 +212,9 @@ def _stem2rank(stem):
 
 def _update(dic, other):
     """dict.update that refuses to change a value (util.py:25-75)."""
+    if not dic:
+        dic.update(other)
+        return
     for key, value in other.items():
         if key in dic:
             assert dic[key] == value, f'Conflicting values found for "{key}".'
@@ -210,20 +226,14 @@ def fill_root(tree):
     """Seal the single top node as its own parent, or hang several top nodes
     under a new node named by the first unused positive integer
     (tree.py:302-388).  Parents that are no keys become top nodes."""
-    crown, toadd, tested = [], set(), set()
-    for taxon in tree:
-        this = taxon
-        while this not in tested:
-            tested.add(this)
-            if this not in tree:
-                crown.append(this)
-                toadd.add(this)
-                break
-            parent = tree[this]
-            if parent is None or parent == this:
-                crown.append(this)
-                break
-            this = parent
+    # a top node: its own parent, no parent, or a parent that is no key (the
+    # reference finds them walking up from every taxon; every one of them is
+    # reached, and nothing else ends a walk)
+    crown = [k for k, v in tree.items() if v is None or v == k]
+    toadd = set(tree.values())
+    toadd.discard(None)
+    toadd.difference_update(tree)
+    crown.extend(toadd)
     for node in toadd:
         tree[node] = None
     if not crown:
