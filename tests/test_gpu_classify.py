@@ -546,15 +546,18 @@ def test_packed_wire_format(engine, small_case, knobs, sub):
     engine.classify_packed(Engine.pack_columns(q[:0], s[:0]), None, 0)  # empty
 
 
-@pytest.mark.parametrize('gtab', [0, 1])
+@pytest.mark.parametrize('gtab', [0, 1, 2])
 @pytest.mark.parametrize('entries', [['genus'], ['none'], ['species', 'genus']])
 def test_stratified_one_kind_plans(engine, small_case, knobs, entries, gtab):
     """classify_strata_kernel (counts keyed by the query's stratum,
     classify.counter_strat classify.py:216-249): interleaved samples, queries
     without a stratum, dropped samples, 17 distinct hits (shares of 1/17 go to
     the overflow list), queries longer than a window, several chunks; table
-    staged in shared memory or read through L2."""
-    knobs.set('strata_gtab', gtab)
+    staged in shared memory or read through L2; updates straight into the
+    strata table or (2) staged per table region and applied region by region
+    (what a table much larger than L2 gets)."""
+    knobs.set('strata_gtab', int(gtab > 0))
+    knobs.set('strata_part', int(gtab == 2))
     q, s = cases.random_hits(small_case, 30000, seed=31 + gtab, long_every=997,
                              long_len=17)
     k = np.bincount(q)

@@ -255,7 +255,7 @@ __global__ void regrid_kernel(const ull *o, ull *nw, int E, int oS, int64_t oNF1
 struct wk_ctx {
   int device = 0;
   int sm_count = 148;
-  size_t smem_optin = 0;
+  size_t smem_optin = 0, smem_sm = 0;
   cudaStream_t own_stream = nullptr, copy_stream = nullptr, stream = nullptr;
   cudaEvent_t ev_copy[2] = {nullptr, nullptr};
   cudaEvent_t ev_free = nullptr;
@@ -289,6 +289,8 @@ struct wk_ctx {
   int32_t n_levels = 0, level_off[40];
   bool minmax_ok = false;  // --above through min / max index (classify_multi_kernel)
   int opt_no_multi = 0, opt_strata_gtab = 0, opt_fuse = 0;
+  int opt_strata_denom = 0, opt_strata_bpp = 0, opt_strata_part = 0, opt_strata_nopart = 0, opt_strata_nt = 0, opt_strata_nowin = 0, opt_strata_dbg = 0;
+  DevBuf part_list, part_cur;
   std::vector<int64_t> dir_lo, dir_hi;  // per entry: range of the table values
   // overflow + err
   DevBuf cov_keys, cov_ends;  // coverage store (wk_cover.cuh)
@@ -395,6 +397,7 @@ int wk_create(int device, wk_ctx **out) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   c->smem_optin = prop.sharedMemPerBlockOptin;
+  c->smem_sm = prop.sharedMemPerMultiprocessor;
   if (prop.persistingL2CacheMaxSize > 0) {
     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize,
                        (size_t)prop.persistingL2CacheMaxSize);
@@ -502,10 +505,12 @@ int wk_create(int device, wk_ctx **out) {
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)c->smem_optin));
 #define WK_STV(KD, MD)                                                   \
-  (const void *)classify_strata_kernel<KD, MD, false, false>,            \
-      (const void *)classify_strata_kernel<KD, MD, false, true>,         \
-      (const void *)classify_strata_kernel<KD, MD, true, false>,         \
-      (const void *)classify_strata_kernel<KD, MD, true, true>
+  (const void *)classify_strata_kernel<KD, MD, false, false, 512>,            \
+      (const void *)classify_strata_kernel<KD, MD, false, true, 512>,         \
+      (const void *)classify_strata_kernel<KD, MD, true, false, 512>,         \
+      (const void *)classify_strata_kernel<KD, MD, true, true, 512>,          \
+      (const void *)classify_strata_kernel<KD, MD, true, false, 256>,         \
+      (const void *)classify_strata_kernel<KD, MD, true, true, 256>
     const void *strata[] = {WK_STV(WK_KIND_RANK, FX_FRAC), WK_STV(WK_KIND_RANK, FX_UNIQ),
                             WK_STV(WK_KIND_NONE, FX_FRAC), WK_STV(WK_KIND_NONE, FX_UNIQ),
                             WK_STV(WK_KIND_NONE_ID, FX_FRAC), WK_STV(WK_KIND_NONE_ID, FX_UNIQ)};
@@ -551,6 +556,7 @@ int wk_destroy(wk_ctx *c) {
                     &c->t_pool[0], &c->t_pool[1], &c->t_meta[0], &c->t_meta[1],
                     &c->t_keys[2], &c->t_ids[2], &c->t_soff[2], &c->t_slen[2],
                     &c->t_first[2], &c->t_pool[2], &c->t_meta[2], &c->p_gdrop, &c->p_lhead, &c->p_xbeg,
+                    &c->part_list, &c->part_cur,
                     &c->p_xlen, &c->p_xspan};
   for (DevBuf *b : bufs) b->release();
   for (int i = 0; i < 2; ++i)
@@ -594,6 +600,18 @@ int wk_set_option(wk_ctx *c, const char *name, int64_t value) {
   else if (k == "no_fast") c->opt_no_fast = (int)value;
   else if (k == "no_multi") c->opt_no_multi = (int)value;
   else if (k == "strata_gtab") c->opt_strata_gtab = (int)value;
+  else if (k == "strata_nopart") c->opt_strata_nopart = (int)value;
+  else if (k == "strata_part") c->opt_strata_part = (int)value;
+  else if (k == "strata_bpp") c->opt_strata_bpp = (int)value;
+  else if (k == "strata_denom") c->opt_strata_denom = (int)value;
+  else if (k == "strata_nt") c->opt_strata_nt = (int)value;
+  else if (k == "strata_nowin") c->opt_strata_nowin = (int)value;
+  else if (k == "strata_dbg") c->opt_strata_dbg = (int)value;
+  else if (k == "l2_fetch") {
+    // (device-wide hint: bytes L2 fetches from HBM per miss - 32, 64 or 128)
+    TRY(use_device(c));
+    CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
+  }
   else if (k == "fuse") c->opt_fuse = (int)value;
   else if (k == "sweep_r") c->opt_sweep_r = (int)value;
   else if (k == "seg_wt") c->opt_seg_wt = (int)value;
@@ -923,6 +941,7 @@ static int resolve_spill(wk_ctx *c, ull *used_out = nullptr) {
 static int ensure_strata(wk_ctx *c, int64_t bound, int denom = 4) {
   ull used = 0;
   TRY(resolve_spill(c, &used));
+  if (c->opt_strata_denom > 0) denom = c->opt_strata_denom;
   TRY(grow_strata(c, 2 * (used + (uint64_t)bound / (uint64_t)denom) + 1024));
   if ((uint64_t)bound > c->sp_cap[0]) {
     TRY(c->sp_k[0].reserve((size_t)bound * 8 + 64));
@@ -1431,21 +1450,75 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
       // the table from shared memory when it fits next to the tiles, else from L2
       const bool gtab = wide || !c->tab16_ok || c->opt_strata_gtab ||
                         sg_layout(SG_NT / 32, 512, 0u, (int64_t)c->Vp * 2).total > c->smem_optin;
-      const SgSmemLayout SL = sg_layout(SG_NT / 32, 512, 0u, gtab ? 0 : (int64_t)c->Vp * 2);
+      // A strata table much larger than L2: the updates are staged per table
+      // region and applied region by region (wk_strata.cuh); 256-record tiles
+      // make room for the warps' queues in shared memory
+      const bool staged = gtab && !c->opt_strata_nopart && c->sh_cap >= 1024 &&
+                          (c->sh_cap * 16ull > (96ull << 20) || c->opt_strata_part);
+      int wt = staged ? 256 : 512, nt = SG_NT, per_sm = 1;
+      if (c->opt_strata_nt > 0) {
+        nt = std::min(SG_NT, std::max(32, c->opt_strata_nt & ~31));
+        per_sm = std::max(1, std::min(2048 / nt, 4));
+      }
+      const int nw = nt / 32;
+      const SgSmemLayout SL = sg_layout(nw, wt, 0u, gtab ? 0 : (int64_t)c->Vp * 2);
+      const uint32_t smem_bytes =
+          SL.total + (staged ? (uint32_t)nw * (PART_N * PART_D * 16u + PART_N * 8u) : 0u);
+      while (per_sm > 1 && (size_t)per_sm * (smem_bytes + 1024) > (size_t)c->smem_sm) --per_sm;
       TRY(c->longlist.reserve((size_t)(span / 33 + 4) * 8));
       P.long_list = c->longlist.as<ull>();
-      const int64_t ft = (span + 511) / 512;
-      const int sgrid = (int)std::min<int64_t>(grid, (ft + SG_NT / 32 - 1) / (SG_NT / 32));
+      const int64_t ft = (span + wt - 1) / wt;
+      const int sgrid = (int)std::min<int64_t>((int64_t)grid * per_sm, (ft + nw - 1) / nw);
+      if (staged) {
+        // a slice per region and warp: room for 1.25 x the warp's share of
+        // the records spread evenly over the regions by the hash (a slice
+        // that fills up sends the rest straight to the table)
+        P.part_gw = sgrid * nw;
+        const int64_t per_warp = (span + P.part_gw - 1) / P.part_gw;
+        P.part_cap = ((per_warp + per_warp / 4) / PART_N + 32 + 7) & ~7ll;
+        TRY(c->part_list.reserve((size_t)PART_N * (size_t)P.part_gw * (size_t)P.part_cap * 16));
+        TRY(c->part_cur.reserve((size_t)PART_N * (size_t)P.part_gw * 4));
+        P.part_list = c->part_list.as<ull>();
+        P.part_cur = c->part_cur.as<uint32_t>();
+      }
       const bool un = (c->flags & WK_F_UNASSIGNED) != 0;
       const bool uq = (c->flags & WK_F_UNIQ) != 0;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)sgrid);
+      cfg.blockDim = dim3((unsigned)nt);
+      cfg.dynamicSmemBytes = smem_bytes;
+      cfg.stream = c->stream;
+      cudaLaunchAttribute attr[1];
       for (int e = 0; e < c->E; ++e) {
         P.e_lo = e;
         P.e_hi = e + 1;
         CK(cudaMemsetAsync(P.long_list, 0, 8, c->stream));
-#define WK_ST3(KD, MD, GT)                                                                  \
-  do {                                                                                      \
-    if (un) classify_strata_kernel<KD, MD, GT, true><<<sgrid, SG_NT, SL.total, c->stream>>>(P);  \
-    else classify_strata_kernel<KD, MD, GT, false><<<sgrid, SG_NT, SL.total, c->stream>>>(P);    \
+        // the subject table of this entry stays in L2 while the hash sectors
+        // and the record columns stream past it
+        cfg.attrs = attr;
+        cfg.numAttrs = 0;
+        if (gtab && c->tab.p && c->l2_window_max && !c->opt_strata_nowin) {
+          const size_t bytes = (size_t)P.V * 4;
+          attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+          attr[0].val.accessPolicyWindow.base_ptr = (void *)(P.tab + (int64_t)e * P.V);
+          attr[0].val.accessPolicyWindow.num_bytes = std::min(bytes, c->l2_window_max);
+          attr[0].val.accessPolicyWindow.hitRatio =
+              c->l2_persist_max && bytes > c->l2_persist_max
+                  ? (float)((double)c->l2_persist_max / (double)bytes)
+                  : 1.0f;
+          attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+          attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+          cfg.numAttrs = 1;
+        }
+#define WK_ST4(KD, MD, GT, UN)                                                          \
+  do {                                                                                  \
+    if (wt == 256) CK(cudaLaunchKernelEx(&cfg, classify_strata_kernel<KD, MD, true, UN, 256>, P)); \
+    else CK(cudaLaunchKernelEx(&cfg, classify_strata_kernel<KD, MD, GT, UN, 512>, P));  \
+  } while (0)
+#define WK_ST3(KD, MD, GT)            \
+  do {                                \
+    if (un) WK_ST4(KD, MD, GT, true); \
+    else WK_ST4(KD, MD, GT, false);   \
   } while (0)
 #define WK_ST2(KD, MD)               \
   do {                               \
@@ -1463,8 +1536,16 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
 #undef WK_ST1
 #undef WK_ST2
 #undef WK_ST3
+#undef WK_ST4
         seg_long_kernel<<<c->sm_count, 128, 0, c->stream>>>(P);
         c->launches += 2;
+        if (staged) {
+          // blocks per region: the blocks resident at one time (8 per SM) then
+          // span two regions, 2 x 1/32 of the table in L2
+          const int bpp = c->opt_strata_bpp > 0 ? c->opt_strata_bpp : std::max(1, 4 * c->sm_count);
+          strata_apply_kernel<<<PART_N * bpp, PART_NT, 0, c->stream>>>(P, bpp);
+          c->launches++;
+        }
         CK(cudaGetLastError());
       }
       P.e_lo = 0;

@@ -105,6 +105,15 @@ struct ClsParams {
   int32_t fast_gsink;         // classify_fast_kernel: no private table, global reductions
   ull *long_list;             // classify_seg_kernel: [0] = count, [1..] first record of a long query
   int32_t par_n;              // classify_multi_kernel: nodes of the parent array to stage
+  // classify_strata_kernel<.., WT = 256> (staged strata updates, wk_strata.cuh):
+  // PART_N lists of (key, units) pairs, one per region of the strata table
+  // per region and per warp of the launch (no atomics on the way in)
+  ull *part_list;             // [PART_N][part_gw][part_cap] pairs of (key, units)
+  uint32_t *part_cur;         // [PART_N][part_gw] pairs written
+  int64_t part_cap;           // pairs per (region, warp) slice
+  int32_t part_gw;            // warps of the launch
+  int32_t dbg;                // measurement only (option "strata_dbg"): 1 = no hash update,
+                              // 2 = no table lookup
 };
 
 enum { ERR_BAD_SUBJECT = 1, ERR_OVF_FULL = 2, ERR_HASH_FULL = 4,
@@ -124,6 +133,14 @@ __device__ __forceinline__ int lds32(uint32_t a) {
   int v;
   asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
   return v;
+}
+__device__ __forceinline__ ull lds64(uint32_t a) {
+  ull v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, ull v) {
+  asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned lds16(uint32_t a) {
   unsigned short v;
@@ -213,11 +230,14 @@ struct Sink {
 // instead of a load first, were both slower - 5.6 / 5.1 / 4.8 ms against
 // 4.7 ms for this form.)
 constexpr int SH_PROBES = 96;
-__device__ __forceinline__ void strat_add(const ClsParams &P, ull key,
-                                          ull units, uint32_t ins) {
+__device__ __forceinline__ uint64_t strat_slot(const ClsParams &P, ull key) {
   ull h = key * 0x9E3779B97F4A7C15ull;
   h ^= h >> 29;
-  uint64_t i = h & P.sh_mask;
+  return h & P.sh_mask;
+}
+__device__ __forceinline__ void strat_add(const ClsParams &P, ull key,
+                                          ull units, uint32_t ins) {
+  uint64_t i = strat_slot(P, key);
   for (int probe = 0; probe < SH_PROBES; ++probe) {
     ull k0 = __ldcg(&P.sh_keys[2 * i]);
     if (k0 == ~0ull) k0 = atomicCAS(&P.sh_keys[2 * i], ~0ull, key);
