@@ -914,7 +914,7 @@ def bench_cfg5(ctx, records, steps, warmup, full, no_e2e=False, no_cpu=False):
     line['roofline'] = {
         'bound': 'hbm', 'achieved': achieved, 'peak': ctx.hbm_peak,
         'unit': 'GB/s', 'frac': achieved / ctx.hbm_peak,
-        'traffic': measured_traffic('classify_kernel:cfg5', n),
+        'traffic': measured_traffic('classify_strata_kernel:cfg5', n),
         'traffic_source': 'profiles/traffic.json (ncu capture, not measured '
                           'in this run)',
         'kernel': eng.last_kernel(), 'kernel_ms': k_ms,
