@@ -780,7 +780,7 @@ def cells_checksum(torch, keys, units):
 def bench_cfg5(ctx, records, steps, warmup, full, no_e2e=False, no_cpu=False):
     torch, dist = ctx.torch, ctx.dist
     from woltka_b200._lib import KIND_RANK
-    from woltka_b200.distributed import merge_engine
+    from woltka_b200.distributed import merge_engine, reduce_scatter_strata
     from woltka_b200.engine import pinned_empty
     world, rank, dev = ctx.world, ctx.rank, ctx.dev
     n = records
@@ -801,7 +801,9 @@ def bench_cfg5(ctx, records, steps, warmup, full, no_e2e=False, no_cpu=False):
 
     def step(ev=None):
         # one job: empty table -> classify -> strata cells of every rank
-        # merged on rank 0 (sent over NCCL, added by key)
+        # merged by key: one all-to-all, every rank ends up with the sum of
+        # the cells it owns (reduce-scatter of the sparse table); the overflow
+        # list goes to rank 0
         eng.reset_counts()
         if ev:
             ev[0].record()
@@ -809,7 +811,8 @@ def bench_cfg5(ctx, records, steps, warmup, full, no_e2e=False, no_cpu=False):
         if ev:
             ev[1].record()
         if world > 1:
-            merge_engine(eng, dst=0, dense=False, strata=True)
+            reduce_scatter_strata(eng)
+            merge_engine(eng, dst=0, dense=False, strata=False)
 
     for _ in range(max(warmup, 1)):
         step()
@@ -831,12 +834,15 @@ def bench_cfg5(ctx, records, steps, warmup, full, no_e2e=False, no_cpu=False):
         step()
         tot = mine.clone()
         dist.reduce(tot, dst=0)               # int64 wrap-around = mod 2^64
+        k_, u_ = eng.strata_export()          # the cells this rank owns now
+        got = torch.tensor(cells_checksum(torch, k_, u_), device=dev,
+                           dtype=torch.int64)
+        dist.reduce(got, dst=0)
         if rank == 0:
-            k_, u_ = eng.strata_export()
-            got = cells_checksum(torch, k_, u_)
             # samples are disjoint over the ranks, so even the cell counts add up
-            parity_merged = got == [int(x) for x in tot.tolist()]
-            assert parity_merged, ('merged strata table', got, tot.tolist())
+            parity_merged = got.tolist() == tot.tolist()
+            assert parity_merged, ('merged strata table', got.tolist(),
+                                   tot.tolist())
     eng.reset_counts()
     classify_dev()
     cells = int(eng.strata_export()[0].numel())

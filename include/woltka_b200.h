@@ -316,6 +316,14 @@ int wk_counts_device(wk_ctx *ctx, void **d_ptr, int64_t *n_elems);
  *   overflow list  (key int64, den int32) pairs.
  * Exported pointers stay valid until the next call on the context. */
 int wk_strata_export_device(wk_ctx *ctx, void **d_keys, void **d_units, int64_t *n);
+/* Room for n_cells more cells in the strata table, made in one step (the
+ * receiving side of a merge knows how many cells are on their way; growing
+ * import by import re-hashes the table again and again). */
+int wk_strata_reserve(wk_ctx *ctx, int64_t n_cells);
+/* Empty the strata table only (the dense table and the overflow list stay):
+ * a rank that has exported its cells for a merge by key ownership takes in
+ * the cells it owns afterwards. */
+int wk_reset_strata(wk_ctx *ctx);
 int wk_strata_import_device(wk_ctx *ctx, const void *d_keys, const void *d_units,
                             int64_t n);
 int wk_overflow_export_device(wk_ctx *ctx, void **d_keys, void **d_den, int64_t *n);

@@ -181,6 +181,32 @@ def _nccl_merge_worker(rank, world, port, out):
                       got[1] == exp[1] and got[2] == exp[2] and
                       (len(got[1]) > 0) and (strata == bool(got[2])))
         eng.close()
+    # strata cells merged by key ownership (reduce-scatter): the union of the
+    # ranks' tables is the oracle's, no key on two ranks
+    from woltka_b200.distributed import reduce_scatter_strata
+    eng = Engine(rank)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    kinds, tab, _ = case.tables(['genus', 'none'])
+    eng.set_tree(case.ft.parent, 0)
+    eng.set_plan(kinds, 0, 0.8, 4, case.NF)
+    eng.set_subjects(tab, case.sub_node)
+    eng.classify_chunk(q[a:b], s[a:b], q_sample, q_stratum, 0)
+    owned = reduce_scatter_strata(eng)
+    merge_engine(eng, dst=0, dense=False, strata=False)     # the overflow list
+    got = cases.collect(eng, 4, case.NF)
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object((got[2], owned), parts, dst=0)
+    if rank == 0:
+        exp = cases.run_oracle(case, ['genus', 'none'], 0, 0.8, q, s,
+                               n_samples=4, q_sample=q_sample,
+                               q_stratum=q_stratum)
+        union = {}
+        for cells, n in parts:
+            assert len(cells) == n and not (set(cells) & set(union))
+            union.update(cells)
+        ok.append(union == exp[2] and got[1] == exp[1] and
+                  all(len(c) > 0 for c, _ in parts))
+    eng.close()
     if rank == 0:
         np.save(out, np.array(ok))
     dist.destroy_process_group()
@@ -198,4 +224,4 @@ def test_merge_engine_over_nccl(tmp_path):
     out = str(tmp_path / 'res.npy')
     port = 29500 + os.getpid() % 2000
     mp.spawn(_nccl_merge_worker, args=(2, port, out), nprocs=2, join=True)
-    assert np.load(out).tolist() == [True, True]
+    assert np.load(out).tolist() == [True, True, True]

@@ -62,6 +62,8 @@ SIGNATURES = {
     'wk_reset_counts': (C.c_int, [_vp]),
     'wk_strata_export_device': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), _i64p]),
     'wk_strata_import_device': (C.c_int, [_vp, _vp, _vp, C.c_int64]),
+    'wk_strata_reserve': (C.c_int, [_vp, C.c_int64]),
+    'wk_reset_strata': (C.c_int, [_vp]),
     'wk_overflow_export_device': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), _i64p]),
     'wk_overflow_import_device': (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int]),
     'wk_set_assign_output': (C.c_int, [_vp, C.c_int]),

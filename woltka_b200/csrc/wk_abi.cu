@@ -828,6 +828,16 @@ int wk_reset_counts(wk_ctx *c) {
   return WK_OK;
 }
 
+int wk_reset_strata(wk_ctx *c) {
+  if (!c || !c->have_plan) return fail(WK_ERR_STATE, "no plan set");
+  TRY(use_device(c));
+  CK(cudaMemsetAsync(c->d_sh_used(), 0, 8, c->stream));
+  CK(cudaMemsetAsync(c->d_sp_n(0), 0, 8, c->stream));
+  CK(cudaMemsetAsync(c->d_sp_n(1), 0, 8, c->stream));
+  if (c->sh_cap) TRY(fill_slots(c, c->sh_keys.as<ull>(), c->sh_cap));
+  return WK_OK;
+}
+
 }  // extern "C"
 
 static int fill_slots(wk_ctx *c, ull *p, size_t n) {
@@ -3040,6 +3050,13 @@ int wk_strata_export_device(wk_ctx *c, void **d_keys, void **d_units, int64_t *n
   c->launches++;
   CK(cudaGetLastError());
   return WK_OK;
+}
+
+int wk_strata_reserve(wk_ctx *c, int64_t n_cells) {
+  if (!c || n_cells < 0) return fail(WK_ERR_ARG, "bad arguments");
+  if (!c->have_plan) return fail(WK_ERR_STATE, "no plan set");
+  TRY(use_device(c));
+  return n_cells ? ensure_strata(c, n_cells, 1) : WK_OK;
 }
 
 int wk_strata_import_device(wk_ctx *c, const void *d_keys, const void *d_units, int64_t n) {

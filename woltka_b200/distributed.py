@@ -79,6 +79,10 @@ def merge_engine(eng, dst=0, dense=True, strata=False):
     every = torch.stack(every).cpu().tolist()      # [rank][part]
     for pi, (a, b) in enumerate(parts):
         if rank == dst:
+            if pi == 1:
+                # every cell that is on its way may be a new one
+                eng.strata_reserve(sum(every[src][pi] for src in range(world)
+                                       if src != dst))
             for src in range(world):
                 n = every[src][pi]
                 if src == dst or not n:
@@ -95,6 +99,45 @@ def merge_engine(eng, dst=0, dense=True, strata=False):
         elif every[rank][pi]:
             dist.send(a.contiguous(), dst=dst)
             dist.send(b.contiguous(), dst=dst)
+
+
+def reduce_scatter_strata(eng):
+    """Merge the strata cells of all ranks BY KEY OWNERSHIP: rank r ends up
+    with the sum of every rank's cells whose key hashes to r (a reduce-scatter
+    of the sparse table; classify.counter_strat keys, summed like
+    `woltka merge`, tools.py:153-208).  Each rank hashes 1/world of the cells
+    instead of one rank hashing all of them: the cells go out with ONE
+    all-to-all over NVLink and come back into the (emptied) local table.
+    The merged table is the union of the ranks' tables — every rank fetches
+    its share (`Engine.fetch_strata`) and the host concatenates them.
+    Collective: every rank calls it.  Returns the number of cells owned."""
+    import torch
+    import torch.distributed as dist
+    k, u = eng.strata_export()
+    if not _active():
+        return int(k.numel())
+    world = dist.get_world_size()
+    dev = k.device
+    k, u = k.clone(), u.clone()          # (views into the engine's buffers)
+    # owner of a key: a multiplicative hash, independent of any table size
+    owner = ((k * -7046029254386353131) >> 40) % world       # int64 wraps
+    srt = torch.sort(owner.to(torch.uint8))
+    k, u = k[srt.indices], u[srt.indices]
+    edges = torch.searchsorted(srt.values, torch.arange(
+        world + 1, device=dev, dtype=torch.uint8))
+    counts = (edges[1:] - edges[:-1]).to(torch.int64)
+    got = torch.empty_like(counts)
+    dist.all_to_all_single(got, counts)
+    n_in, n_out = got.cpu().tolist(), counts.cpu().tolist()
+    rk = torch.empty(sum(n_in), dtype=k.dtype, device=dev)
+    ru = torch.empty(sum(n_in), dtype=u.dtype, device=dev)
+    dist.all_to_all_single(rk, k, n_in, n_out)
+    dist.all_to_all_single(ru, u, n_in, n_out)
+    torch.cuda.current_stream(dev).synchronize()
+    eng.reset_strata()
+    eng.strata_reserve(rk.numel())
+    eng.strata_import(rk, ru)
+    return int(eng.strata_export()[0].numel())
 
 
 def merge_profiles(data, dst=0):

@@ -472,6 +472,13 @@ class Engine:
         return (self.device_tensor(k.value, n.value),
                 self.device_tensor(v.value, n.value))
 
+    def strata_reserve(self, n_cells):
+        """Room for n_cells more strata cells, in one step."""
+        _lib.check(self.lib.wk_strata_reserve(self.ctx, int(n_cells)))
+
+    def reset_strata(self):
+        _lib.check(self.lib.wk_reset_strata(self.ctx))
+
     def strata_import(self, keys, units):
         """Add (key, units) cells (int64 CUDA tensors) into the strata table."""
         _lib.check(self.lib.wk_strata_import_device(
