@@ -121,10 +121,10 @@ def reduce_scatter_strata(eng):
     k, u = k.clone(), u.clone()          # (views into the engine's buffers)
     # owner of a key: a multiplicative hash, independent of any table size
     owner = ((k * -7046029254386353131) >> 40) % world       # int64 wraps
-    srt = torch.sort(owner.to(torch.uint8))
+    srt = torch.sort(owner.to(torch.int16))
     k, u = k[srt.indices], u[srt.indices]
     edges = torch.searchsorted(srt.values, torch.arange(
-        world + 1, device=dev, dtype=torch.uint8))
+        world + 1, device=dev, dtype=torch.int16))
     counts = (edges[1:] - edges[:-1]).to(torch.int64)
     got = torch.empty_like(counts)
     dist.all_to_all_single(got, counts)
