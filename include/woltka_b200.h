@@ -99,7 +99,13 @@ int wk_set_tuning(wk_ctx *ctx, int grid, int block, int cache_slots);
  * one launch per rank instead of the all-ranks kernel; "strata_gtab": the
  * stratified kernel reads its table through L2 even when it could be staged;
  * "fuse": `--coords` at `--rank none` through the one-pass match-and-resolve
- * kernel instead of matcher + pair counting. */
+ * kernel instead of matcher + pair counting; "strata_nopart" / "strata_part":
+ * never / always stage the updates of the strata table per table region
+ * (default: when the table exceeds 96 MB); "strata_nt", "strata_bpp",
+ * "strata_denom", "strata_nowin": threads per CTA, apply blocks per region,
+ * expected new cells = records / denom, no L2 window on the subject table;
+ * "strata_dbg" (measurement only: 1 = skip the table update, 2 = skip the
+ * subject look-up); "l2_fetch": cudaLimitMaxL2FetchGranularity of the device. */
 int wk_set_option(wk_ctx *ctx, const char *name, int64_t value);
 /* Name of the classify kernel the last chunk was launched with. */
 const char *wk_last_kernel(wk_ctx *ctx);
