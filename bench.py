@@ -530,15 +530,17 @@ def bench_classify(ctx, workload, records, ranks, mode, samples, steps, warmup,
                 api = 'wk_classify_chunk(host int32 SoA) + wk_fetch_counts'
             else:
                 h2d = int(packed.nbytes + (4 * nq if hqs is not None else 0))
-                api = ('wk_classify_packed(host head bits + uint16 subjects) '
-                       '+ wk_fetch_counts')
+                api = ((f'wk_classify_packed_bits(host head bits + '
+                        f'{packed.width}-bit subjects)' if packed.stream else
+                        'wk_classify_packed(host head bits + uint16 subjects)')
+                       + ' + wk_fetch_counts')
             e2e[name] = {'value': n * world * e2e_steps / (ems * 1e-3),
                          'unit': UNIT, 'h2d_bytes_per_step': h2d,
                          'd2h_bytes_per_step': int(res.nbytes),
                          'steps': e2e_steps, 'ms_per_step': ems / e2e_steps,
                          'api': api}
         # the headline is the wire format the host layer (woltka_b200.session)
-        # sends: head bits + uint16 subjects; the int32 SoA entry point of the
+        # sends: head bits + subjects in ceil(log2 V) bits; the int32 SoA entry point of the
         # north star is reported next to it
         head = dict(e2e['packed'] if 'packed' in e2e else e2e['soa'])
         if 'packed' in e2e:

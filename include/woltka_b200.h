@@ -163,6 +163,15 @@ int wk_classify_chunk(wk_ctx *ctx, const int32_t *qidx, const int32_t *sidx,
 int wk_classify_packed(wk_ctx *ctx, const uint64_t *head_bits, const void *subj,
                        int subj_bytes, int64_t n_rec, const int32_t *q_sample,
                        const int32_t *q_stratum, int64_t n_qry, int32_t sample);
+/* The same with the subjects as a little-endian bit stream of subj_bits bits
+ * each (1..32; subject i occupies bits [i * subj_bits, (i + 1) * subj_bits) of
+ * the stream, which must be readable up to the next multiple of 8 bytes plus
+ * 8): ceil(log2 n_subjects) bits per record, e.g. 14 for the 10,000 genomes
+ * of BASELINE.json configs[1] = 1.875 bytes per record over PCIe. */
+int wk_classify_packed_bits(wk_ctx *ctx, const uint64_t *head_bits,
+                            const uint64_t *subj_stream, int subj_bits, int64_t n_rec,
+                            const int32_t *q_sample, const int32_t *q_stratum,
+                            int64_t n_qry, int32_t sample);
 /* Same, columns already resident in device memory (16-byte aligned).  The
  * call is asynchronous on the context stream. */
 int wk_classify_device(wk_ctx *ctx, const int32_t *d_qidx,

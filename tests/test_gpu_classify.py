@@ -512,8 +512,8 @@ def test_host_chunk_in_sub_chunks(engine, small_case, knobs, sub, noseg):
 
 @pytest.mark.parametrize('sub', [0, 64, 192, 4096])
 def test_packed_wire_format(engine, small_case, knobs, sub):
-    """wk_classify_packed: head bits + uint16 / uint32 subjects expanded on
-    the device must give what the int32 SoA columns give — with sub-chunks
+    """wk_classify_packed[_bits]: head bits + subjects (bit stream of 8..28
+    bits each, or uint16 / uint32) expanded on the device must give what the int32 SoA columns give — with sub-chunks
     that cut queries (also queries longer than two sub-chunks), a per-query
     sample column, and an out-of-range subject reported as an error."""
     from woltka_b200.engine import Engine
@@ -531,10 +531,13 @@ def test_packed_wire_format(engine, small_case, knobs, sub):
         fl = cases.MODES[mode]
         ref = cases.run_engine(engine, small_case, ent, fl, 0.8, q, s,
                                n_samples=3, q_sample=q_sample)
-        for wide in (False, True):
-            packed = Engine.pack_columns(ids[q].astype(np.int32), s)
-            if wide:
-                packed.subj = packed.subj.astype(np.uint32)
+        # subjects as a bit stream of every width the packer writes, and as
+        # uint16 / uint32 arrays
+        for n_subjects in (None, 1 << 10, 1 << 12, 1 << 14, 1 << 16, 1 << 20,
+                           1 << 24, 1 << 28, 1 << 31):
+            packed = Engine.pack_columns(ids[q].astype(np.int32), s,
+                                         n_subjects=n_subjects)
+            assert packed.stream == (n_subjects not in (1 << 16, 1 << 31))
             engine.reset_counts()
             engine.classify_packed(packed, q_sample, 0)
             _same(cases.collect(engine, 3, small_case.NF), ref)

@@ -44,6 +44,8 @@ SIGNATURES = {
                                     C.c_int64, C.c_int32]),
     'wk_classify_packed': (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int64, _vp,
                                      _vp, C.c_int64, C.c_int32]),
+    'wk_classify_packed_bits': (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int64, _vp,
+                                     _vp, C.c_int64, C.c_int32]),
     'wk_classify_device': (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, _vp,
                                      C.c_int64, C.c_int32]),
     'wk_ordinal_set_genes': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32,

@@ -1743,15 +1743,20 @@ int wk_classify_chunk(wk_ctx *c, const int32_t *qidx, const int32_t *sidx,
   return rc2;
 }
 
-int wk_classify_packed(wk_ctx *c, const uint64_t *head_bits, const void *subj,
-                       int subj_bytes, int64_t n_rec, const int32_t *q_sample,
-                       const int32_t *q_stratum, int64_t n_qry, int32_t sample) {
+}  // extern "C"
+
+// subj_bits: 16 / 32 with `subj` an array of uint16 / uint32 (stream = false), or
+// any width in [1, 32] with `subj` a little-endian bit stream (stream = true)
+static int classify_packed(wk_ctx *c, const uint64_t *head_bits, const void *subj,
+                           int subj_bits, bool stream, int64_t n_rec,
+                           const int32_t *q_sample, const int32_t *q_stratum, int64_t n_qry,
+                           int32_t sample) {
   TRY(check_plan_ready(c, q_stratum != nullptr));
   TRY(use_device(c));
   if (n_rec < 0 || (n_rec && (!head_bits || !subj)))
     return fail(WK_ERR_ARG, "bad packed columns");
-  if (subj_bytes != 2 && subj_bytes != 4)
-    return fail(WK_ERR_ARG, "subj_bytes must be 2 (uint16) or 4 (uint32)");
+  if (subj_bits < 1 || subj_bits > 32)
+    return fail(WK_ERR_ARG, "subjects of %d bits", subj_bits);
   if (!q_sample && (sample < 0 || sample >= c->S))
     return fail(WK_ERR_ARG, "sample %d out of range", sample);
   if (n_rec == 0) return WK_OK;
@@ -1760,7 +1765,9 @@ int wk_classify_packed(wk_ctx *c, const uint64_t *head_bits, const void *subj,
   TRY(c->dq.reserve((size_t)n_rec * 4 + 64));
   TRY(c->ds.reserve((size_t)n_rec * 4 + 64));
   TRY(c->pk_bits.reserve((size_t)n_words * 8 + 64));
-  TRY(c->pk_subj.reserve((size_t)n_rec * subj_bytes + 64));
+  // byte offset of record i in the subject column / stream (i a multiple of 64)
+  auto soff = [&](int64_t i) { return (size_t)(((unsigned long long)i * (unsigned)subj_bits + 7) / 8); };
+  TRY(c->pk_subj.reserve(soff(n_rec) + 64));
   const int32_t *dqs, *dqt;
   TRY(upload_per_query(c, q_sample, q_stratum, n_qry, &dqs, &dqt));
   // H2D in sub-chunks on the copy stream (2.125 or 4.125 bytes per record); the
@@ -1782,8 +1789,8 @@ int wk_classify_packed(wk_ctx *c, const uint64_t *head_bits, const void *subj,
     const int64_t wa = a / 64, wb = (b + 63) / 64;
     CK(cudaMemcpyAsync(c->pk_bits.as<uint64_t>() + wa, head_bits + wa, (size_t)(wb - wa) * 8,
                        cudaMemcpyHostToDevice, c->copy_stream));
-    CK(cudaMemcpyAsync(c->pk_subj.as<char>() + a * subj_bytes, hs + a * subj_bytes,
-                       (size_t)(b - a) * subj_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaMemcpyAsync(c->pk_subj.as<char>() + soff(a), hs + soff(a), soff(b) - soff(a),
+                       cudaMemcpyHostToDevice, c->copy_stream));
     CK(cudaEventCreateWithFlags(&evs[(size_t)j], cudaEventDisableTiming));
     CK(cudaEventRecord(evs[(size_t)j], c->copy_stream));
   }
@@ -1796,14 +1803,18 @@ int wk_classify_packed(wk_ctx *c, const uint64_t *head_bits, const void *subj,
     CK(cudaStreamWaitEvent(c->stream, evs[(size_t)j], 0));
     pk_count_kernel<<<nb, PK_NT, 0, c->stream>>>(bits, wa, nw, blk);
     pk_scan_kernel<<<1, 32, 0, c->stream>>>(blk, nb, c->pk_run.as<long long>());
-    if (subj_bytes == 2)
+    if (stream)
+      pk_expand_kernel<unsigned long long><<<nb, PK_NT, 0, c->stream>>>(
+          bits, c->pk_subj.as<unsigned long long>(), wa, nw, b, blk, c->dq.as<int32_t>(),
+          c->ds.as<int32_t>(), subj_bits);
+    else if (subj_bits == 16)
       pk_expand_kernel<uint16_t><<<nb, PK_NT, 0, c->stream>>>(
           bits, c->pk_subj.as<uint16_t>(), wa, nw, b, blk, c->dq.as<int32_t>(),
-          c->ds.as<int32_t>());
+          c->ds.as<int32_t>(), 16);
     else
       pk_expand_kernel<uint32_t><<<nb, PK_NT, 0, c->stream>>>(
           bits, c->pk_subj.as<uint32_t>(), wa, nw, b, blk, c->dq.as<int32_t>(),
-          c->ds.as<int32_t>());
+          c->ds.as<int32_t>(), 32);
     c->launches += 3;
     CK(cudaGetLastError());
     return WK_OK;
@@ -1832,6 +1843,24 @@ int wk_classify_packed(wk_ctx *c, const uint64_t *head_bits, const void *subj,
   for (auto &e : evs)
     if (e) cudaEventDestroy(e);
   return rc2;
+}
+
+extern "C" {
+
+int wk_classify_packed(wk_ctx *c, const uint64_t *head_bits, const void *subj,
+                       int subj_bytes, int64_t n_rec, const int32_t *q_sample,
+                       const int32_t *q_stratum, int64_t n_qry, int32_t sample) {
+  if (subj_bytes != 2 && subj_bytes != 4)
+    return fail(WK_ERR_ARG, "subj_bytes must be 2 (uint16) or 4 (uint32)");
+  return classify_packed(c, head_bits, subj, subj_bytes * 8, false, n_rec, q_sample,
+                         q_stratum, n_qry, sample);
+}
+
+int wk_classify_packed_bits(wk_ctx *c, const uint64_t *head_bits, const uint64_t *subj_stream,
+                            int subj_bits, int64_t n_rec, const int32_t *q_sample,
+                            const int32_t *q_stratum, int64_t n_qry, int32_t sample) {
+  return classify_packed(c, head_bits, subj_stream, subj_bits, true, n_rec, q_sample,
+                         q_stratum, n_qry, sample);
 }
 
 // ---- ordinal ------------------------------------------------------------------

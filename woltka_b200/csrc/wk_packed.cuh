@@ -3,7 +3,9 @@
 // The kernels only ever ask whether q[i] != q[i+1] (align.py:325-339 groups
 // adjacent equal QNAMEs), so over PCIe a chunk travels as ONE head bit per
 // record (record i starts a query) plus its subject index as uint16 (or
-// uint32): 2.125 bytes per record instead of the 8 of the int32 SoA columns.
+// uint32) or as a bit stream of ceil(log2 n_subjects) bits per record:
+// 2.125 (1.875 for the 10k genomes of cfg2) bytes per record instead of the 8
+// of the int32 SoA columns.
 // On the device the columns are rebuilt — q = ordinal of the query in the
 // chunk (prefix popcount of the head bits), s widened to int32 — sub-chunk by
 // sub-chunk behind the copies, and the classify kernels run on them unchanged.
@@ -54,12 +56,25 @@ __global__ void pk_scan_kernel(int32_t *blk, int nb, long long *running) {
   }
 }
 
-// q[i] = (heads in records [0, i]) - 1, s[i] = subj[i]; four records per thread
+// subject i of a little-endian bit stream of `width` bits per subject
+__device__ __forceinline__ int pk_subject(const unsigned long long *stream, int64_t i,
+                                          int width) {
+  const unsigned long long off = (unsigned long long)i * (unsigned)width;
+  const unsigned long long lo = __ldg(stream + (off >> 6));
+  const unsigned sh = (unsigned)(off & 63);
+  unsigned long long v = lo >> sh;
+  if (sh + (unsigned)width > 64u) v |= __ldg(stream + (off >> 6) + 1) << (64u - sh);
+  return (int)(v & ((1ull << width) - 1ull));
+}
+
+// q[i] = (heads in records [0, i]) - 1, s[i] = subj[i]; four records per thread.
+// ST = uint16_t / uint32_t: subjects as an array; ST = unsigned long long: as a
+// bit stream of `width` bits each.
 template <typename ST>
 __global__ void __launch_bounds__(PK_NT)
     pk_expand_kernel(const unsigned long long *bits, const ST *subj, int64_t w0,
                      int64_t n_words, int64_t n_rec, const int32_t *blk, int32_t *q,
-                     int32_t *s) {
+                     int32_t *s, int width) {
   __shared__ unsigned long long s_bits[PK_WORDS];
   __shared__ int s_pre[PK_WORDS];
   __shared__ int s_warp[PK_NT / 32];
@@ -106,7 +121,11 @@ __global__ void __launch_bounds__(PK_NT)
     if (i + 4 <= n_rec) {
       *reinterpret_cast<int4 *>(q + i) = make_int4(q0, q1, q2, q3);
       int4 sv;
-      if (sizeof(ST) == 2) {
+      if (sizeof(ST) == 8) {
+        const unsigned long long *st = reinterpret_cast<const unsigned long long *>(subj);
+        sv = make_int4(pk_subject(st, i, width), pk_subject(st, i + 1, width),
+                       pk_subject(st, i + 2, width), pk_subject(st, i + 3, width));
+      } else if (sizeof(ST) == 2) {
         const uint2 u = *reinterpret_cast<const uint2 *>(subj + i);
         sv = make_int4((int)(u.x & 0xFFFFu), (int)(u.x >> 16), (int)(u.y & 0xFFFFu),
                        (int)(u.y >> 16));
@@ -118,7 +137,10 @@ __global__ void __launch_bounds__(PK_NT)
       const int qq[4] = {q0, q1, q2, q3};
       for (int j = 0; i + j < n_rec; ++j) {
         q[i + j] = qq[j];
-        s[i + j] = (int)subj[i + j];
+        s[i + j] = sizeof(ST) == 8
+                       ? pk_subject(reinterpret_cast<const unsigned long long *>(subj), i + j,
+                                    width)
+                       : (int)subj[i + j];
       }
     }
   }

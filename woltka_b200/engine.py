@@ -72,14 +72,40 @@ class _PinnedArray(np.ndarray):
 
 class PackedChunk:
     """A chunk in the compact wire format: head bits (uint64 words) and
-    subjects (uint16 / uint32)."""
+    subjects — a uint16 / uint32 array (`width` 16 / 32) or a little-endian bit
+    stream of `width` bits per subject held in uint64 words."""
 
-    def __init__(self, bits, subj, n):
+    def __init__(self, bits, subj, n, width=None):
         self.bits, self.subj, self.n = bits, subj, n
+        self.width = width or subj.dtype.itemsize * 8
+        self.stream = subj.dtype == np.uint64
 
     @property
     def nbytes(self):
-        return (self.n + 63) // 64 * 8 + self.n * self.subj.dtype.itemsize
+        return (self.n + 63) // 64 * 8 + (self.n * self.width + 7) // 8
+
+
+# widths the host packer writes: k subjects fill a whole number of bytes of
+# one 64-bit word (k = 1, 4, 4, 4, -, 2, 2, 2, -)
+_STREAM_WIDTHS = {8: 1, 10: 4, 12: 4, 14: 4, 20: 2, 24: 2, 28: 2}
+
+
+def _bit_stream(sidx, width, alloc):
+    """Subjects as a little-endian bit stream of `width` bits each."""
+    n, k = len(sidx), _STREAM_WIDTHS[width]
+    groups = (n + k - 1) // k
+    v = np.zeros(groups * k, dtype=np.uint64)
+    v[:n] = sidx
+    v = v.reshape(groups, k)
+    word = v[:, 0].copy()
+    for j in range(1, k):
+        word |= v[:, j] << np.uint64(j * width)
+    nb = k * width // 8                      # bytes per group
+    out = alloc((groups * nb + 7) // 8 + 2, np.uint64)
+    out[:] = 0
+    out.view(np.uint8)[:groups * nb] = \
+        word.view(np.uint8).reshape(groups, 8)[:, :nb].reshape(-1)
+    return out
 
 
 class Engine:
@@ -179,10 +205,12 @@ class Engine:
             _ptr(q_stratum), n_qry, sample))
 
     @staticmethod
-    def pack_columns(qidx, sidx, pinned=True):
-        """The compact wire format of a chunk (wk_classify_packed): one head
-        bit per record and the subjects as uint16 (uint32 when an index needs
-        it), in page-locked memory."""
+    def pack_columns(qidx, sidx, pinned=True, n_subjects=None):
+        """The compact wire format of a chunk (wk_classify_packed[_bits]): one
+        head bit per record and the subjects in as few bits as the largest
+        index (or `n_subjects` - 1) needs: a bit stream of 8 / 10 / 12 / 14 /
+        20 / 24 / 28 bits each, else a uint16 / uint32 array; in page-locked
+        memory."""
         qidx, sidx = np.asarray(qidx), np.asarray(sidx)
         n = len(qidx)
         heads = np.empty(n, dtype=bool)
@@ -195,7 +223,12 @@ class Engine:
         bits = alloc(max(words, 1), np.uint64)
         bits[:] = 0
         bits.view(np.uint8)[:len(packed)] = packed
-        dt = np.uint16 if (not n or int(sidx.max()) < 65536) else np.uint32
+        top = max(int(sidx.max()) if n else 0, (n_subjects or 1) - 1)
+        need = max(top.bit_length(), 1)
+        width = min(w for w in (8, 10, 12, 14, 16, 20, 24, 28, 32) if w >= need)
+        if width in _STREAM_WIDTHS and n:
+            return PackedChunk(bits, _bit_stream(sidx, width, alloc), n, width)
+        dt = np.uint16 if width <= 16 else np.uint32
         subj = alloc(max(n, 1), dt)
         subj[:n] = sidx
         return PackedChunk(bits, subj, n)
@@ -204,6 +237,11 @@ class Engine:
         q_sample, q_stratum = _i32(q_sample), _i32(q_stratum)
         n_qry = max(len(q_sample) if q_sample is not None else 0,
                     len(q_stratum) if q_stratum is not None else 0)
+        if packed.stream:
+            _lib.check(self.lib.wk_classify_packed_bits(
+                self.ctx, _ptr(packed.bits), _ptr(packed.subj), packed.width,
+                packed.n, _ptr(q_sample), _ptr(q_stratum), n_qry, sample))
+            return
         _lib.check(self.lib.wk_classify_packed(
             self.ctx, _ptr(packed.bits), _ptr(packed.subj),
             packed.subj.dtype.itemsize, packed.n, _ptr(q_sample),
