@@ -112,6 +112,9 @@ const char *wk_last_kernel(wk_ctx *ctx);
 
 /* Pinned host memory for chunk producers (H2D at full PCIe rate). */
 int wk_host_alloc(void **out, int64_t bytes);
+/* wk_destroy keeps a context's device blocks (up to 4 GiB per process) for the
+ * next wk_create of the process; this returns them to the driver. */
+int wk_release_cached_memory(int device);
 int wk_host_free(void *p);
 
 /* ---- hierarchy: replaces the dict walks of tree.py ------------------- */

@@ -33,6 +33,7 @@ SIGNATURES = {
     'wk_set_tuning': (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
     'wk_set_option': (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     'wk_last_kernel': (C.c_char_p, [_vp]),
+    'wk_release_cached_memory': (C.c_int, [C.c_int]),
     'wk_host_alloc': (C.c_int, [C.POINTER(_vp), C.c_int64]),
     'wk_host_free': (C.c_int, [_vp]),
     'wk_set_tree': (C.c_int, [_vp, _vp, C.c_int32, C.c_int32]),

@@ -622,6 +622,21 @@ int wk_set_option(wk_ctx *c, const char *name, int64_t value) {
   return WK_OK;
 }
 
+int wk_release_cached_memory(int device) {
+  // device blocks of destroyed contexts are kept for the next context
+  // (BlockCache); this hands them back to the driver
+  int prev = 0;
+  cudaGetDevice(&prev);
+  if (cudaSetDevice(device) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(WK_ERR_ARG, "no CUDA device %d", device);
+  }
+  cudaDeviceSynchronize();
+  g_blocks.flush(device);
+  cudaSetDevice(prev);
+  return WK_OK;
+}
+
 int wk_host_alloc(void **out, int64_t bytes) {
   if (!out || bytes < 0) return fail(WK_ERR_ARG, "bad arguments");
   CK(cudaMallocHost(out, (size_t)std::max<int64_t>(bytes, 16)));

@@ -70,6 +70,11 @@ class _PinnedArray(np.ndarray):
             self._owner = getattr(obj, '_owner', None)
 
 
+def release_cached_memory(device=0):
+    """Return the device blocks kept from closed engines to the driver."""
+    _lib.check(_lib.load().wk_release_cached_memory(int(device)))
+
+
 class PackedChunk:
     """A chunk in the compact wire format: head bits (uint64 words) and
     subjects — a uint16 / uint32 array (`width` 16 / 32) or a little-endian bit
