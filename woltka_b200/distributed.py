@@ -110,7 +110,8 @@ def reduce_scatter_strata(eng):
     all-to-all over NVLink and come back into the (emptied) local table.
     The merged table is the union of the ranks' tables — every rank fetches
     its share (`Engine.fetch_strata`) and the host concatenates them.
-    Collective: every rank calls it.  Returns the number of cells owned."""
+    Collective: every rank calls it.  Returns the number of cells received
+    (an upper bound of the cells owned: equal keys of two ranks become one)."""
     import torch
     import torch.distributed as dist
     k, u = eng.strata_export()
@@ -118,11 +119,11 @@ def reduce_scatter_strata(eng):
         return int(k.numel())
     world = dist.get_world_size()
     dev = k.device
-    k, u = k.clone(), u.clone()          # (views into the engine's buffers)
     # owner of a key: a multiplicative hash, independent of any table size
     owner = ((k * -7046029254386353131) >> 40) % world       # int64 wraps
     srt = torch.sort(owner.to(torch.int16))
-    k, u = k[srt.indices], u[srt.indices]
+    k, u = k[srt.indices], u[srt.indices]    # (copies: k, u were views into
+                                              # the engine's buffers)
     edges = torch.searchsorted(srt.values, torch.arange(
         world + 1, device=dev, dtype=torch.int16))
     counts = (edges[1:] - edges[:-1]).to(torch.int64)
@@ -137,7 +138,7 @@ def reduce_scatter_strata(eng):
     eng.reset_strata()
     eng.strata_reserve(rk.numel())
     eng.strata_import(rk, ru)
-    return int(eng.strata_export()[0].numel())
+    return int(rk.numel())
 
 
 def merge_profiles(data, dst=0):
