@@ -94,7 +94,7 @@ int wk_set_tuning(wk_ctx *ctx, int grid, int block, int cache_slots);
  * process environment); value 0 restores the default.  "no_seg" / "no_fast":
  * skip the lane-per-record / the run-per-lane kernel; "sweep_r": longest run
  * of the run-per-lane kernel; "seg_wt": tile of the lane-per-record kernel
- * (256); "cls_sub" / "ord_sub": records per H2D sub-chunk of the host-fed
+ * (256), "seg_nt": its threads per CTA; "cls_sub" / "ord_sub": records per H2D sub-chunk of the host-fed
  * calls; "ord_nowin": no persisting L2 window over the gene table; "no_multi":
  * one launch per rank instead of the all-ranks kernel; "strata_gtab": the
  * stratified kernel reads its table through L2 even when it could be staged;

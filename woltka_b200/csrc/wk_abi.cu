@@ -289,7 +289,7 @@ struct wk_ctx {
   int32_t n_levels = 0, level_off[40];
   bool minmax_ok = false;  // --above through min / max index (classify_multi_kernel)
   int opt_no_multi = 0, opt_strata_gtab = 0, opt_fuse = 0;
-  int opt_strata_denom = 0, opt_strata_bpp = 0, opt_strata_part = 0, opt_strata_nopart = 0, opt_strata_nt = 0, opt_strata_nowin = 0, opt_strata_dbg = 0;
+  int opt_seg_nt = 0, opt_strata_denom = 0, opt_strata_bpp = 0, opt_strata_part = 0, opt_strata_nopart = 0, opt_strata_nt = 0, opt_strata_nowin = 0, opt_strata_dbg = 0;
   DevBuf part_list, part_cur;
   std::vector<int64_t> dir_lo, dir_hi;  // per entry: range of the table values
   // overflow + err
@@ -615,6 +615,7 @@ int wk_set_option(wk_ctx *c, const char *name, int64_t value) {
   else if (k == "fuse") c->opt_fuse = (int)value;
   else if (k == "sweep_r") c->opt_sweep_r = (int)value;
   else if (k == "seg_wt") c->opt_seg_wt = (int)value;
+  else if (k == "seg_nt") c->opt_seg_nt = (int)value;
   else if (k == "ord_nowin") c->opt_ord_nowin = (int)value;
   else if (k == "cls_sub") c->opt_cls_sub = value;
   else if (k == "ord_sub") c->opt_ord_sub = value;
@@ -1337,21 +1338,27 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
           P.e_lo = e;
           P.e_hi = e + 1;
           const int WT = WTe[e];
+          // threads per CTA (option "seg_nt"): two smaller CTAs share an SM
+          // when their shared memory allows it
+          const int snt = c->opt_seg_nt > 0 ? std::min(SG_NT, std::max(32, c->opt_seg_nt & ~31))
+                                            : SG_NT;
           // (+ 32 spare words: one per lane for the branch-free emission)
           const SgSmemLayout GL = sg_layout(
-              SG_NT / 32, WT,
+              snt / 32, WT,
               (gsink ? 0u : (uint32_t)(P.dir_base[e + 1] - P.dir_base[e])) + 32u,
               wide ? 0 : (int64_t)c->Vp * 2);
+          const int per_sm =
+              snt <= 768 && 2 * ((size_t)GL.total + 1024) <= c->smem_sm ? 2 : 1;
           const int64_t ft = (span + WT - 1) / WT;
-          const int sgrid =
-              (int)std::min<int64_t>(grid, (ft + SG_NT / 32 - 1) / (SG_NT / 32));
+          const int sgrid = (int)std::min<int64_t>((int64_t)grid * per_sm,
+                                                   (ft + snt / 32 - 1) / (snt / 32));
           CK(cudaMemsetAsync(P.long_list, 0, 8, c->stream));
 #define WK_SEG4(KD, MD, WW, MU)                                                      \
   do {                                                                               \
     if (c->flags & WK_F_UNASSIGNED)                                                  \
-      classify_seg_kernel<KD, MD, WW, MU, true><<<sgrid, SG_NT, GL.total, c->stream>>>(P);  \
+      classify_seg_kernel<KD, MD, WW, MU, true><<<sgrid, snt, GL.total, c->stream>>>(P);  \
     else                                                                             \
-      classify_seg_kernel<KD, MD, WW, MU, false><<<sgrid, SG_NT, GL.total, c->stream>>>(P); \
+      classify_seg_kernel<KD, MD, WW, MU, false><<<sgrid, snt, GL.total, c->stream>>>(P); \
   } while (0)
 #define WK_SEG3(KD, MD, WW)               \
   do {                                    \
