@@ -21,15 +21,18 @@ def big_case():
     return cases.Case(synth.Taxonomy(seed=42))
 
 
-def _lean_kernel(entries, mode):
+def _lean_kernel(entries, mode, th=0.8):
     """The kernel a plan of one kind takes (ranks only, or `none` only, staged
-    tables, no strata, no read map): default or --uniq -> classify_seg_kernel,
-    one launch per entry; --major and --above -> classify_fast_kernel.
+    tables, no strata, no read map): default or --uniq at one entry ->
+    classify_seg_kernel; several ranks, --above, --major above one half ->
+    classify_multi_kernel (all ranks in one pass); --major up to one half
+    (ties between top taxa possible) -> classify_fast_kernel.
     assign_none knows no --major / --above."""
     none = all(x == 'none' for x in entries)
     if not none and any(x in ('none', 'free') for x in entries):
         return 'classify_kernel'
-    if not none and (mode.startswith('above') or (
+    if not none and (mode.startswith('above') or
+                     (mode.startswith('major') and th > 0.5) or (
             len(entries) > 1 and mode.startswith(('default', 'uniq')))):
         return 'classify_multi_kernel'    # all ranks in one pass
     if none or mode.startswith(('default', 'uniq')):
@@ -290,17 +293,20 @@ def test_contiguous_samples_take_the_run_per_lane_kernel(engine, small_case,
               ref)
     assert engine.last_kernel() == (
         'classify_fast_kernel' if noseg == '1' else
-        _lean_kernel(entries, mode))
+        _lean_kernel(entries, mode, 0.7))
 
 
 def test_which_kernel_runs(engine, small_case):
-    """One entry in default / --uniq mode takes classify_seg_kernel, other
-    one-kind plans with staged tables classify_fast_kernel; strata, mixed
-    kinds and read maps take classify_kernel."""
+    """One entry in default / --uniq mode takes classify_seg_kernel; several
+    ranks, --above and --major above one half classify_multi_kernel; --major up
+    to one half classify_fast_kernel; strata, mixed kinds and read maps take
+    classify_kernel."""
     q, s = cases.random_hits(small_case, 5000, seed=1)
     cases.run_engine(engine, small_case, ['genus'], 0, 0, q, s)
     assert engine.last_kernel() == 'classify_seg_kernel'
     cases.run_engine(engine, small_case, ['genus'], cases.MODES['major'], 0.8, q, s)
+    assert engine.last_kernel() == 'classify_multi_kernel'
+    cases.run_engine(engine, small_case, ['genus'], cases.MODES['major'], 0.5, q, s)
     assert engine.last_kernel() == 'classify_fast_kernel'
     cases.run_engine(engine, small_case, ['phylum', 'genus'], 0, 0, q, s)
     assert engine.last_kernel() == 'classify_multi_kernel'
@@ -308,7 +314,7 @@ def test_which_kernel_runs(engine, small_case):
     assert engine.last_kernel() == 'classify_multi_kernel'
     cases.run_engine(engine, small_case, ['phylum', 'genus'],
                      cases.MODES['major'], 0.8, q, s)
-    assert engine.last_kernel() == 'classify_fast_kernel'
+    assert engine.last_kernel() == 'classify_multi_kernel'
     cases.run_engine(engine, small_case, ['none', 'free'], 0, 0, q, s)
     assert engine.last_kernel() == 'classify_kernel'
     nq = int(q.max()) + 1
@@ -445,7 +451,7 @@ def test_randomised_shapes_both_kernels_agree(engine, small_case, knobs,
         got = cases.run_engine(engine, small_case, ent, fl, th, q, s)
         assert engine.last_kernel() == (
             'classify_fast_kernel' if noseg == '1' else
-            _lean_kernel(ent, mode))
+            _lean_kernel(ent, mode, th))
         _same(got, exp)
         engine.set_tuning(0, 1, 0)
         try:

@@ -68,8 +68,7 @@ def test_classify_1e8_properties(engine, stream, entries, mode):
     whole = run(0, N)
     assert engine.last_kernel() == (
         'classify_seg_kernel' if mode == 'default' else
-        'classify_multi_kernel' if mode.startswith('above') else
-        'classify_fast_kernel')
+        'classify_multi_kernel')      # --above, --major 80
     assert not len(engine.fetch_overflow()[0])
     # conservation: one unit per query and entry
     assert np.array_equal(whole.sum(axis=(1, 2)),

@@ -499,7 +499,8 @@ int wk_create(int device, wk_ctx **out) {
       (const void *)classify_multi_kernel<MD, 128, UN>
     const void *multi[] = {WK_MUV(FX_FRAC, false), WK_MUV(FX_FRAC, true),
                            WK_MUV(FX_UNIQ, false), WK_MUV(FX_UNIQ, true),
-                           WK_MUV(FX_ABOVE, false), WK_MUV(FX_ABOVE, true)};
+                           WK_MUV(FX_ABOVE, false), WK_MUV(FX_ABOVE, true),
+                           WK_MUV(FX_MAJOR, false), WK_MUV(FX_MAJOR, true)};
 #undef WK_MUV
     for (const void *fn : multi)
       CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1238,8 +1239,10 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
     // taxa of every row on one level (pack_stage), and the count range of
     // --above reaches down to the root.
     if (NTmax == SW_NT && !c->opt_no_multi && rk && !gsink && staged &&
-        c->stage_vmax < 0xFFFE && (mode == FX_ABOVE ? (par_ok && c->minmax_ok) : c->E > 1) &&
-        (mode == FX_FRAC || mode == FX_UNIQ || mode == FX_ABOVE)) {
+        c->stage_vmax < 0xFFFE &&
+        (mode == FX_ABOVE ? (par_ok && c->minmax_ok)
+                          : mode == FX_MAJOR ? c->major_th > 0.5 : c->E > 1) &&
+        (mode == FX_FRAC || mode == FX_UNIQ || mode == FX_ABOVE || mode == FX_MAJOR)) {
       // parents of the taxa and of their ancestors: indices below the largest value
       const int32_t par_n = mode == FX_ABOVE ? std::min<int32_t>(c->T, c->stage_vmax + 1) : 0;
       const int64_t tabb = (int64_t)c->E * c->Vp * 2 + (((int64_t)par_n + 7) & ~7ll) * 2;
@@ -1281,6 +1284,7 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
     else WK_MU3(MD, 128);                   \
   } while (0)
         if (mode == FX_ABOVE) WK_MU2(FX_ABOVE);
+        else if (mode == FX_MAJOR) WK_MU2(FX_MAJOR);
         else if (mode == FX_UNIQ) WK_MU2(FX_UNIQ);
         else WK_MU2(FX_FRAC);
 #undef WK_MU2

@@ -249,9 +249,9 @@ __global__ void __launch_bounds__(SG_NT, 1)
         const uint32_t svc = min(sv, V32);
         if (act && sv != svc) atoms_exch(badflag, 1u);
 
-        // default mode: the repeat test, once for all ranks (wk_seg.cuh)
+        // default mode and --major: the repeat test, once for all ranks (wk_seg.cuh)
         bool rep = false;
-        if (MODE == FX_FRAC) {
+        if (MODE == FX_FRAC || MODE == FX_MAJOR) {
           const int dist = lane - sl;
           const uint32_t mykey = ((uint32_t)(cur + sl) << 24) | 0x80000000u | svc;
           const uint32_t as = ax + SCOL;
@@ -279,7 +279,26 @@ __global__ void __launch_bounds__(SG_NT, 1)
           const uint32_t kh = __shfl_sync(FULL, code, sl);
           const unsigned NE = __ballot_sync(FULL, act && code != kh);
           uint32_t amt, c = code;
-          if (MODE != FX_FRAC || NE == 0) {
+          if (MODE == FX_MAJOR && NE != 0) {
+            // classify.majority (classify.py:300-317) for a threshold above one
+            // half: the taxon (None counts as one) held by at least th x the
+            // query's distinct subjects is the only one that can top the list,
+            // so no maximum and no tie rule are needed - the lanes of a query
+            // group themselves by taxon and the group that is large enough
+            // sends one unit from its first lane
+            const bool contrib = act && !rep;
+            const unsigned CB = __ballot_sync(FULL, contrib) & segm;
+            const unsigned peers = __match_any_sync(
+                FULL, contrib ? (code | ((uint32_t)sl << 16)) : (0x80000000u | (uint32_t)lane));
+            const bool win = contrib && valid &&
+                             (double)__popc(peers) >= __dmul_rn((double)__popc(CB), P.major_th);
+            const unsigned anyw = __ballot_sync(FULL, win) & segm;
+            amt = (win && (peers & ((1u << lane) - 1u)) == 0u) ? (uint32_t)WK_UNITS : 0u;
+            if (UNAS && act && ishead && !anyw) {
+              amt = (uint32_t)WK_UNITS;
+              c = c_none;
+            }
+          } else if (MODE != FX_FRAC || NE == 0) {
             // one unit from the head lane: the common taxon, the LCA (--above)
             // or nothing (--uniq)
             bool ok = valid;
