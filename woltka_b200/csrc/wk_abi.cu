@@ -289,7 +289,7 @@ struct wk_ctx {
   int32_t n_levels = 0, level_off[40];
   bool minmax_ok = false;  // --above through min / max index (classify_multi_kernel)
   int opt_no_multi = 0, opt_strata_gtab = 0, opt_fuse = 0;
-  int opt_seg_nt = 0, opt_strata_denom = 0, opt_strata_bpp = 0, opt_strata_part = 0, opt_strata_nopart = 0, opt_strata_nt = 0, opt_strata_nowin = 0, opt_strata_dbg = 0;
+  int opt_cnt_nowin = 0, opt_seg_nt = 0, opt_strata_denom = 0, opt_strata_bpp = 0, opt_strata_part = 0, opt_strata_nopart = 0, opt_strata_nt = 0, opt_strata_nowin = 0, opt_strata_dbg = 0;
   DevBuf part_list, part_cur;
   std::vector<int64_t> dir_lo, dir_hi;  // per entry: range of the table values
   // overflow + err
@@ -617,6 +617,7 @@ int wk_set_option(wk_ctx *c, const char *name, int64_t value) {
   else if (k == "sweep_r") c->opt_sweep_r = (int)value;
   else if (k == "seg_wt") c->opt_seg_wt = (int)value;
   else if (k == "seg_nt") c->opt_seg_nt = (int)value;
+  else if (k == "cnt_nowin") c->opt_cnt_nowin = (int)value;
   else if (k == "ord_nowin") c->opt_ord_nowin = (int)value;
   else if (k == "cls_sub") c->opt_cls_sub = value;
   else if (k == "ord_sub") c->opt_ord_sub = value;
@@ -1335,6 +1336,23 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
         }
         P.direct_cells = dir_cells;
         P.fast_gsink = gsink ? 1 : 0;
+        // counts straight into the global table (OGU / gene tables too wide
+        // for a private one): keep the table in L2 while the records stream
+        // past it - without the window its sectors are written back again
+        // and again (1.28 GB of DRAM writes for the 7e7 gene pairs of cfg3)
+        const size_t cnt_bytes = (size_t)c->E * c->S * (size_t)(c->NF + 1) * 8;
+        const bool cnt_win = gsink && c->l2_window_max && !c->opt_cnt_nowin &&
+                             cnt_bytes <= c->l2_persist_max && cnt_bytes <= c->l2_window_max;
+        if (cnt_win) {
+          cudaStreamAttrValue av;
+          memset(&av, 0, sizeof av);
+          av.accessPolicyWindow.base_ptr = c->cnt.p;
+          av.accessPolicyWindow.num_bytes = cnt_bytes;
+          av.accessPolicyWindow.hitRatio = 1.0f;
+          av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+          av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+          CK(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av));
+        }
         // queries longer than a window are listed and done by seg_long_kernel
         TRY(c->longlist.reserve((size_t)(span / 33 + 4) * 8));
         P.long_list = c->longlist.as<ull>();
@@ -1390,6 +1408,11 @@ static int launch_classify(wk_ctx *c, const int32_t *dq, const int32_t *ds,
           seg_long_kernel<<<c->sm_count, 128, 0, c->stream>>>(P);
           c->launches += 2;
           CK(cudaGetLastError());
+        }
+        if (cnt_win) {
+          cudaStreamAttrValue av;
+          memset(&av, 0, sizeof av);   // num_bytes = 0: no window
+          CK(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av));
         }
         P.e_lo = 0;
         P.e_hi = c->E;
