@@ -52,7 +52,9 @@ enum wk_status {
   WK_ERR_ARG = 2,      /* invalid argument                                 */
   WK_ERR_STATE = 3,    /* call sequence error (e.g. chunk before plan)     */
   WK_ERR_NOMEM = 4,    /* allocation failed                                */
-  WK_ERR_CAPACITY = 5  /* an output list / hash table is full              */
+  WK_ERR_CAPACITY = 5, /* an output list / hash table is full              */
+  WK_ERR_FALLBACK = 6  /* the device reader met a case it leaves to the
+                          host reader; nothing was counted                 */
 };
 
 /* How one entry of `ranks` is assigned (workflow.py:1017-1032). */

@@ -198,15 +198,15 @@ def test_odd_lines_of_map_b6o_paf():
 
 
 # ---- reader options: --trim-sub, --exclude, coordinates --------------------------
-def suffixed_sam(n_groups, seed):
+def suffixed_sam(n_groups, seed, repeats=True):
     """Subjects carry `_<n>` suffixes (ORF style); some names come back after
-    another name in between (the A, B, A pattern)."""
+    another name in between (the A, B, A pattern) unless repeats=False."""
     rng = np.random.default_rng(seed)
     cigars = ['50M', '10S40M', '20M2D30M', '*', '5H20M3I22M5N3M', '7=1X8=',
               '30M1000N20M', '12I', '4P']
     rows = []
     for g in range(n_groups):
-        name = f'read{g if rng.random() < 0.8 else g - 2}'
+        name = f'read{g if rng.random() < 0.8 or not repeats else g - 2}'
         for _ in range(int(min(rng.geometric(0.4), 9))):
             flag = int(rng.choice([0, 16, 64 + 1, 128 + 1, 256]))
             r = rng.random()
@@ -294,8 +294,12 @@ def test_sam_coordinates_on_device(with_excl):
     eng = Engine(0)
     excl = {f'G{i:03d}_2' for i in range(0, 60, 3)} if with_excl else None
     eng.parse_options(None, excl, coords=True)
+    from woltka_b200.engine import WoltkaB200Error
+    with pytest.raises(WoltkaB200Error) as err:      # a name in two places:
+        eng.parse_sam(suffixed_sam(3000, 30), False)  # the host reader's case
+    assert err.value.code == 6
     for seed in (31, 32):
-        text = suffixed_sam(3000, seed)
+        text = suffixed_sam(3000, seed, repeats=False)
         got = device_records(eng, text)
         exp = host_records(text, excl=excl)
         if not with_excl:
@@ -367,6 +371,53 @@ def test_coords_from_text_equals_host_reader(monkeypatch, tmp_path):
         assert reader == 'host'
         assert dev == host, kw
         assert sum(len(v) for v in dev['none'].values()) > 10
+
+
+def test_coords_demultiplexed_from_text(monkeypatch, tmp_path):
+    """`--coords` on a multiplexed file (sample = prefix of the read name,
+    workflow.demultiplex workflow.py:844-909), with a sample filter."""
+    from woltka_b200 import reader
+    coords_fp = os.path.join(DATA, 'synth_coords.txt')
+    rows = [b'@HD\tVN:1.0\n']
+    for i in range(2):
+        with open(os.path.join(DATA, 'synth_ordinal', f'S{i}.sam'), 'rb') as f:
+            body = [x for x in f if not x.startswith(b'@')]
+        rows += [b'S%d_' % i + x for x in body]
+        # a third sample, filtered out in the second run (its queries between
+        # the others', never inside one: the records of a query are adjacent)
+        if i == 0:
+            rows += [b'X9_' + x for x in body[:len(body) // 5]]
+    fp = tmp_path / 'mux.sam'
+    fp.write_bytes(b''.join(rows))
+    monkeypatch.setattr(reader, 'BLOCK', 40000)
+    for samples in (None, ['S0', 'S1']):
+        monkeypatch.delenv('WOLTKA_B200_HOST_READER', raising=False)
+        dev, rd = _ordinal_classify([str(fp)], coords_fp, demux=True,
+                                    samples=samples)
+        assert rd == 'device'
+        monkeypatch.setenv('WOLTKA_B200_HOST_READER', '1')
+        host, _ = _ordinal_classify([str(fp)], coords_fp, demux=True,
+                                    samples=samples)
+        assert dev == host
+        assert set(dev['none']) == ({'S0', 'S1'} if samples
+                                    else {'S0', 'S1', 'X9'})
+
+
+def test_coords_query_name_in_two_places(monkeypatch, tmp_path):
+    """The reference merges the records of a query name that comes back later
+    in a chunk (ordinal.py:296-332); the device reader, which groups adjacent
+    lines, notices such a block and leaves it to the host reader."""
+    coords_fp = os.path.join(DATA, 'synth_coords.txt')
+    with open(os.path.join(DATA, 'synth_ordinal', 'S0.sam'), 'rb') as f:
+        body = [x for x in f if not x.startswith(b'@')]
+    fp = tmp_path / 'S0.sam'
+    fp.write_bytes(b'@HD\tVN:1.0\n' + b''.join(body) + b''.join(body[:200]))
+    monkeypatch.delenv('WOLTKA_B200_HOST_READER', raising=False)
+    dev, rd = _ordinal_classify({str(fp): 'S0'}, coords_fp)
+    assert rd == 'host'                      # (the one block fell back)
+    monkeypatch.setenv('WOLTKA_B200_HOST_READER', '1')
+    host, _ = _ordinal_classify({str(fp): 'S0'}, coords_fp)
+    assert dev == host
 
 
 def test_plain_options_from_text_equals_host_reader(monkeypatch, tmp_path):

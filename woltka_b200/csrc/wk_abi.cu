@@ -330,7 +330,7 @@ struct wk_ctx {
   DevBuf p_text, p_a, p_b, p_sums, p_line_start, p_rec, p_valid, p_vpos, p_vline,
       p_ghead, p_slot, p_phead, p_qpos, p_rslot, p_sslot, p_qline, p_tot;
   DevBuf t_keys[3], t_ids[3], t_soff[3], t_slen[3], t_first[3], t_pool[3], t_meta[3];
-  DevBuf p_gdrop, p_lhead, p_xbeg, p_xlen, p_xspan;
+  DevBuf p_gdrop, p_lhead, p_xbeg, p_xlen, p_xspan, p_dup;
   bool p_tables = false;
   int64_t p_nrec = 0, p_nqry = 0;
   int p_demux = 0;
@@ -557,7 +557,7 @@ int wk_destroy(wk_ctx *c) {
                     &c->t_pool[0], &c->t_pool[1], &c->t_meta[0], &c->t_meta[1],
                     &c->t_keys[2], &c->t_ids[2], &c->t_soff[2], &c->t_slen[2],
                     &c->t_first[2], &c->t_pool[2], &c->t_meta[2], &c->p_gdrop, &c->p_lhead, &c->p_xbeg,
-                    &c->part_list, &c->part_cur,
+                    &c->part_list, &c->part_cur, &c->p_dup,
                     &c->p_xlen, &c->p_xspan};
   for (DevBuf *b : bufs) b->release();
   for (int i = 0; i < 2; ++i)
@@ -2649,6 +2649,10 @@ static int parse_error(wk_ctx *c) {
   if (err & PERR_POOL_FULL) return fail(WK_ERR_CAPACITY, "identifier pool is full");
   if (err & PERR_GROUP)
     return fail(WK_ERR_CAPACITY, "more than 65536 adjacent lines share a query name");
+  if (err & PERR_DUP)
+    return fail(WK_ERR_FALLBACK,
+                "a query name comes back later in the block: the reference merges such "
+                "queries (ordinal.py:332), a case for the host reader");
   return fail(WK_ERR_CUDA, "device error word %d", err);
 }
 
@@ -2802,6 +2806,20 @@ int wk_parse_block(wk_ctx *c, const char *text, int64_t n_bytes, int fmt, int de
                                                    c->p_vline.as<uint32_t>(), N,
                                                    c->p_ghead.as<uint8_t>());
     c->launches += 2;
+  }
+  if (O.extr) {
+    // a query name in two places of the block: the host reader's case
+    uint64_t cap = 1024;
+    while (cap < 2 * (uint64_t)N) cap <<= 1;
+    TRY(c->p_dup.reserve(cap * 8));
+    CK(cudaMemsetAsync(c->p_dup.p, 0xFF, cap * 8, c->stream));
+    dup_names_kernel<<<gr, 256, 0, c->stream>>>(dt, c->p_line_start.as<uint32_t>(),
+                                               c->p_rec.as<LineRec>(),
+                                               c->p_vline.as<uint32_t>(),
+                                               c->p_ghead.as<uint8_t>(), N,
+                                               c->p_dup.as<ull>(), cap - 1, c->d_err());
+    c->launches++;
+    TRY(parse_error(c));
   }
   TRY(c->p_slot.reserve((size_t)N * 4));
   TRY(c->p_phead.reserve((size_t)N * 4));

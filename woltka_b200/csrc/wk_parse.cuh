@@ -32,7 +32,7 @@ namespace wk {
 typedef unsigned long long ull;
 
 enum { PERR_FIELDS = 1, PERR_FLAG = 2, PERR_COLLISION = 4, PERR_TABLE_FULL = 8,
-       PERR_POOL_FULL = 16, PERR_GROUP = 32 };
+       PERR_POOL_FULL = 16, PERR_GROUP = 32, PERR_DUP = 64 };
 
 // ---- exclusive prefix sum of int32 (three small kernels) ----------------------
 constexpr int SCAN_NT = 512, SCAN_ITEMS = 8, SCAN_TILE = SCAN_NT * SCAN_ITEMS;
@@ -403,6 +403,32 @@ __global__ void group_heads_kernel(const uint8_t *text, const uint32_t *line_sta
   }
   ghead[j] = head;
 }
+// Coordinate mode: does a query name come back later in the block?  The
+// reference's ordinal_mapper keys its records by name and so merges such
+// queries inside a chunk (ordinal.py:296-332); this reader groups adjacent
+// lines only, so a block with a name in two places is handed to the host
+// reader (PERR_DUP).  A 64-bit hash per group head in a scratch table; two
+// different names under one hash only cost an unnecessary fallback.
+__global__ void dup_names_kernel(const uint8_t *text, const uint32_t *line_start,
+                                 const LineRec *rec, const uint32_t *vline,
+                                 const uint8_t *ghead, int64_t n_rec, ull *table,
+                                 uint64_t cap_mask, int32_t *err) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_rec || !ghead[j]) return;
+  const uint32_t li = vline[j];
+  const ull h = hash_bytes(text + line_start[li], rec[li].qlen);
+  uint64_t i = h & cap_mask;
+  for (uint64_t probe = 0; probe <= cap_mask; ++probe) {
+    const ull k = atomicCAS(&table[i], ~0ull, h);
+    if (k == ~0ull) return;
+    if (k == h) {
+      atomicOr(err, PERR_DUP);
+      return;
+    }
+    i = (i + 1) & cap_mask;
+  }
+}
+
 constexpr int PARSE_MAX_GROUP = 1 << 16;
 // output slot of record j: records of a group ordered by mate, stable; phead
 // (indexed by output slot) = 1 at the first record of a (group, mate) pool

@@ -499,10 +499,11 @@ class Session:
         matcher + classify kernels run on the resident columns
         (ordinal.py:167-335, workflow.py:304-335).
 
-        A query is a run of adjacent lines with one name (per mate); the
-        reference also merges a name that comes back later in the same 2^20
-        record chunk (ordinal.py:332) but not across chunks — files grouped by
-        query, which every aligner writes, are unaffected.  Returns
+        A query is a run of adjacent lines with one name (per mate).  The
+        reference also merges a name that comes back later in the same chunk
+        (ordinal.py:332): a block with a name in two places raises
+        WoltkaB200Error code 6 before anything is counted and the caller
+        hands it to the host reader.  Returns
         (bytes consumed, queries in the block)."""
         eng = self.engines[0]
         if not hasattr(self, '_dev_contig'):

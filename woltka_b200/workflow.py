@@ -266,14 +266,19 @@ def classify(mapper, files, samples=None, fmt=None, demux=None, trimsub=None,
                                 nqry += n
                                 continue
                             except WoltkaB200Error as err:
-                                if err.code != 5:      # WK_ERR_CAPACITY
+                                if err.code not in (5, 6):
                                     raise
-                                # the device reader's tables are full (> 1M
-                                # subjects, 64 MiB of names, 32k samples or a
-                                # 64k-line query): this block and the rest
-                                # of the run go through the host reader
-                                sess.device_reader_off = True
                                 LAST_READER = 'host'
+                                if err.code == 5:      # WK_ERR_CAPACITY
+                                    # the device reader's tables are full (> 1M
+                                    # subjects, 64 MiB of names, 32k samples
+                                    # or a 64k-line query): this block and
+                                    # the rest of the run go through the host
+                                    # reader
+                                    sess.device_reader_off = True
+                                # (6 = WK_ERR_FALLBACK: a query name in two
+                                # places of this block, which the reference
+                                # merges, ordinal.py:332 - this block only)
                         text = view.tobytes()
                         used = len(text) if final else _host_cut(text)
                         blocks.consumed(used)
