@@ -31,7 +31,9 @@
 namespace wk {
 
 constexpr int ORD_NT = 256;
-constexpr int ORD_ITEMS = 4;
+constexpr int ORD_ITEMS = 2;   // reads per thread (4 reads at 64 registers and 4 CTAs
+                               // per SM: 2.45 ms per 1e8 reads; 2 reads at 40 registers
+                               // and 6 CTAs: 2.2 ms - the kernel waits on L2 round trips)
 constexpr int ORD_TILE = ORD_NT * ORD_ITEMS;
 constexpr int ORD_CAND = 2;  // candidate genes loaded up front per read
 
@@ -93,7 +95,7 @@ __device__ __forceinline__ void ord_scan(const OrdParams &P, const ReadQ &r,
   }
 }
 
-__global__ void __launch_bounds__(ORD_NT, 4)
+__global__ void __launch_bounds__(ORD_NT, 6)
     ordinal_match_kernel(const __grid_constant__ OrdParams P) {
   __shared__ int s_warp[ORD_NT / 32];
   __shared__ long long s_base;
@@ -143,16 +145,29 @@ __global__ void __launch_bounds__(ORD_NT, 4)
   int32_t qv[ORD_ITEMS], cv[ORD_ITEMS], bv[ORD_ITEMS], ev[ORD_ITEMS],
       lv[ORD_ITEMS];
   if (i0 + ORD_ITEMS <= t1) {
-    int4 a = __ldcs(reinterpret_cast<const int4 *>(P.q + i0));
-    int4 b = __ldcs(reinterpret_cast<const int4 *>(P.contig + i0));
-    int4 c = __ldcs(reinterpret_cast<const int4 *>(P.beg + i0));
-    int4 d = __ldcs(reinterpret_cast<const int4 *>(P.end + i0));
-    int4 e = __ldcs(reinterpret_cast<const int4 *>(P.len + i0));
-    qv[0] = a.x, qv[1] = a.y, qv[2] = a.z, qv[3] = a.w;
-    cv[0] = b.x, cv[1] = b.y, cv[2] = b.z, cv[3] = b.w;
-    bv[0] = c.x, bv[1] = c.y, bv[2] = c.z, bv[3] = c.w;
-    ev[0] = d.x, ev[1] = d.y, ev[2] = d.z, ev[3] = d.w;
-    lv[0] = e.x, lv[1] = e.y, lv[2] = e.z, lv[3] = e.w;
+    if constexpr (ORD_ITEMS == 4) {
+      int4 a = __ldcs(reinterpret_cast<const int4 *>(P.q + i0));
+      int4 b = __ldcs(reinterpret_cast<const int4 *>(P.contig + i0));
+      int4 c = __ldcs(reinterpret_cast<const int4 *>(P.beg + i0));
+      int4 d = __ldcs(reinterpret_cast<const int4 *>(P.end + i0));
+      int4 e = __ldcs(reinterpret_cast<const int4 *>(P.len + i0));
+      qv[0] = a.x, qv[1] = a.y, qv[2] = a.z, qv[3] = a.w;
+      cv[0] = b.x, cv[1] = b.y, cv[2] = b.z, cv[3] = b.w;
+      bv[0] = c.x, bv[1] = c.y, bv[2] = c.z, bv[3] = c.w;
+      ev[0] = d.x, ev[1] = d.y, ev[2] = d.z, ev[3] = d.w;
+      lv[0] = e.x, lv[1] = e.y, lv[2] = e.z, lv[3] = e.w;
+    } else {
+      int2 a = __ldcs(reinterpret_cast<const int2 *>(P.q + i0));
+      int2 b = __ldcs(reinterpret_cast<const int2 *>(P.contig + i0));
+      int2 c = __ldcs(reinterpret_cast<const int2 *>(P.beg + i0));
+      int2 d = __ldcs(reinterpret_cast<const int2 *>(P.end + i0));
+      int2 e = __ldcs(reinterpret_cast<const int2 *>(P.len + i0));
+      qv[0] = a.x, qv[1] = a.y;
+      cv[0] = b.x, cv[1] = b.y;
+      bv[0] = c.x, bv[1] = c.y;
+      ev[0] = d.x, ev[1] = d.y;
+      lv[0] = e.x, lv[1] = e.y;
+    }
   } else {
 #pragma unroll
     for (int j = 0; j < ORD_ITEMS; ++j) {
