@@ -35,7 +35,7 @@ constexpr int ORD_ITEMS = 2;   // reads per thread (4 reads at 64 registers and 
                                // per SM: 2.45 ms per 1e8 reads; 2 reads at 40 registers
                                // and 6 CTAs: 2.2 ms - the kernel waits on L2 round trips)
 constexpr int ORD_TILE = ORD_NT * ORD_ITEMS;
-constexpr int ORD_CAND = 2;  // candidate genes loaded up front per read
+constexpr int ORD_CAND = 3;  // candidate genes loaded up front per read
 
 struct OrdParams {
   const int32_t *q, *contig, *beg, *end, *len;
