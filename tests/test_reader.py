@@ -15,8 +15,8 @@ from woltka_b200 import reader
 @pytest.fixture
 def plain_buffers(monkeypatch):
     import woltka_b200.engine as engine
-    monkeypatch.setattr(reader, '_pinned_pair', lambda room, block: [
-        np.empty(room + block, np.uint8) for _ in (0, 1)])
+    monkeypatch.setattr(reader, '_pinned_pair', lambda room, block: (
+        [np.empty(room + block, np.uint8) for _ in (0, 1)], None))
     monkeypatch.setattr(engine, 'pinned_empty', lambda n, dt: np.empty(n, dt))
 
 
@@ -96,3 +96,31 @@ def test_header_longer_than_a_block_and_host_cut(tmp_path, plain_buffers):
         for a, b in zip(chunks, chunks[1:]):
             assert a.splitlines()[-1].split(b'\t')[0] != \
                 b.splitlines()[0].split(b'\t')[0]
+
+
+def test_two_readers_at_once_do_not_share_buffers(tmp_path, monkeypatch):
+    """The process keeps one pair of page-locked buffers; a second reader
+    that starts while the first is still iterating gets its own."""
+    import woltka_b200.engine as engine
+    monkeypatch.setattr(engine, 'pinned_empty', lambda n, dt: np.empty(n, dt))
+    monkeypatch.setattr(reader, '_buffers', {})
+    monkeypatch.setattr(reader, '_busy', set())
+    a, b = tmp_path / 'a.map', tmp_path / 'b.map'
+    a.write_bytes(b''.join(b'a%d\tS\n' % i for i in range(2000)))
+    b.write_bytes(b''.join(b'b%d\tT\n' % i for i in range(2000)))
+    ra = reader.BlockReader(str(a), header=False, block=4096, room=256)
+    rb = reader.BlockReader(str(b), header=False, block=4096, room=256)
+    out_a, out_b = [], []
+    ita, itb = iter(ra), iter(rb)
+    for (va, fa), (vb, fb) in zip(ita, itb):
+        ta, tb = va.tobytes(), vb.tobytes()
+        ua = len(ta) if fa else ta.rfind(b'\n') + 1
+        ub = len(tb) if fb else tb.rfind(b'\n') + 1
+        out_a.append(ta[:ua])
+        out_b.append(tb[:ub])
+        ra.consumed(ua)
+        rb.consumed(ub)
+    assert b''.join(out_a) == a.read_bytes() and b''.join(out_b) == b.read_bytes()
+    for it in (ita, itb):
+        it.close()
+    assert not reader._busy

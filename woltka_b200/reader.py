@@ -38,13 +38,22 @@ def _executor():
     return _pool
 
 
+_busy = set()          # keys of cached pairs a reader is iterating over
+
+
 def _pinned_pair(room, block):
+    """Two page-locked buffers of room + block bytes: the process's cached
+    pair when it is free (one reader at a time uses it), else a new pair."""
     from .engine import pinned_empty
     key = (room, block)
+    if key in _busy:
+        return [pinned_empty(room + block, np.uint8) for _ in (0, 1)], None
     if key not in _buffers:
-        _buffers.clear()
+        for k in [k for k in _buffers if k not in _busy]:
+            del _buffers[k]
         _buffers[key] = [pinned_empty(room + block, np.uint8) for _ in (0, 1)]
-    return _buffers[key]
+    _busy.add(key)
+    return _buffers[key], key
 
 
 class BlockReader:
@@ -126,9 +135,9 @@ class BlockReader:
 
     def __iter__(self):
         self._open()
-        pending = None
+        pending = held = None
         try:
-            bufs = _pinned_pair(self.room, self.block)
+            bufs, held = _pinned_pair(self.room, self.block)
             cur = 0
             pending = self._fetch(bufs[cur])
             start = self.room
@@ -174,6 +183,7 @@ class BlockReader:
                     pending.result()     # nobody writes into the buffers now
                 except Exception:
                     pass
+            _busy.discard(held)
             self._close()
 
     def _skip_header(self, buf, start, end):
