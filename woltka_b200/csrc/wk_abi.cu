@@ -979,6 +979,23 @@ static int ensure_strata(wk_ctx *c, int64_t bound, int denom = 4) {
   return WK_OK;
 }
 
+// Room for n cells that are known to come (a merge): the table only grows when
+// they would fill it beyond 65 % - what does not find a slot within the probe
+// limit still goes to the spill list, which resolve_spill works off.
+static int ensure_room(wk_ctx *c, int64_t n) {
+  ull used = 0;
+  TRY(resolve_spill(c, &used));
+  if (c->sh_cap && (used + (ull)n) * 100 <= (ull)c->sh_cap * 65) {
+    if ((uint64_t)n > c->sp_cap[0]) {
+      TRY(c->sp_k[0].reserve((size_t)n * 8 + 64));
+      TRY(c->sp_v[0].reserve((size_t)n * 8 + 64));
+      c->sp_cap[0] = (uint64_t)n;
+    }
+    return WK_OK;
+  }
+  return ensure_strata(c, n, 1);
+}
+
 // (Re)pack everything the kernel gathers from into one uint16 block that a
 // single TMA bulk copy stages in shared memory: E table rows of Vp entries,
 // then sub_node (FREE plans), then parent (LCA plans).  0xFFFF = none.
@@ -3152,7 +3169,7 @@ int wk_strata_reserve(wk_ctx *c, int64_t n_cells) {
   if (!c || n_cells < 0) return fail(WK_ERR_ARG, "bad arguments");
   if (!c->have_plan) return fail(WK_ERR_STATE, "no plan set");
   TRY(use_device(c));
-  return n_cells ? ensure_strata(c, n_cells, 1) : WK_OK;
+  return n_cells ? ensure_room(c, n_cells) : WK_OK;
 }
 
 int wk_strata_import_device(wk_ctx *c, const void *d_keys, const void *d_units, int64_t n) {
@@ -3160,7 +3177,7 @@ int wk_strata_import_device(wk_ctx *c, const void *d_keys, const void *d_units, 
   if (!c->have_plan) return fail(WK_ERR_STATE, "no plan set");
   TRY(use_device(c));
   if (!n) return WK_OK;
-  TRY(ensure_strata(c, n, 1));  // cells of another rank: mostly new ones
+  TRY(ensure_room(c, n));  // cells of another rank: mostly new ones
   ClsParams P;
   memset(&P, 0, sizeof P);
   strata_params(c, P, 0);
