@@ -337,18 +337,54 @@ class Session:
         self._dirty = False
 
     # -- chunks -------------------------------------------------------------
-    def add_chunk(self, qryque, subque, demux, sample_name, samples=None,
-                  strata_of=None):
-        """One `(qryque, subque)` chunk of the mapper protocol
-        (workflow.py:304-335): demultiplex, intern, classify on the GPU.
+    def _chunk_columns(self, qryque, subque, demux, sample_name, samples,
+                       strata_of):
+        """Index columns of a chunk (everything but --sizes with --stratify):
+        per-query work as list comprehensions, the subjects of the whole
+        chunk interned in one call.  Same numbering as query-by-query
+        interning: names get their indices in order of first appearance."""
+        if demux:
+            pairs = [_split_sample(x) for x in qryque]
+            if samples is not None:
+                keep = [p[0] in samples for p in pairs]
+                if not all(keep):
+                    pairs = [p for p, k in zip(pairs, keep) if k]
+                    subque = [x for x, k in zip(subque, keep) if k]
+            snames = [p[0] for p in pairs]
+            reads = [p[1] for p in pairs]
+        else:
+            snames, reads = None, list(qryque)
+            subque = list(subque)
+        nq = len(reads)
+        flat = [x for subs in subque for x in subs]
+        if not flat:
+            return None
+        q_stratum = None
+        if strata_of is not None:
+            # counter_strat skips reads without a stratum but the sample
+            # still gets its (possibly empty) profile (workflow.py:1058)
+            if demux:
+                labels = [strata_of(a).get(b) for a, b in zip(snames, reads)]
+            else:
+                labels = list(map(strata_of(sample_name).get, reads))
+            stratum = self.stratum
+            q_stratum = [stratum(x) if x is not None else -1 for x in labels]
+        if demux:
+            q_sample = list(map(self.sample, snames))
+        else:
+            q_sample = [self.sample(sample_name)] * nq
+        lens = np.fromiter(map(len, subque), dtype=np.int64, count=nq)
+        s = self.subjects_bulk(flat)
+        q = np.repeat(np.arange(nq, dtype=np.int32), lens)
+        starts = (np.cumsum(lens) - lens).tolist()
+        return q, s, q_sample, q_stratum, reads, starts
 
-        strata_of(sample_name) -> dict read -> stratum label, or None.
-        Returns the number of queries in the chunk."""
+    def _chunk_columns_sized_strata(self, qryque, subque, demux, sample_name,
+                                    samples, strata_of):
+        """--sizes with --stratify: the stratum travels with the subject."""
         q, s, q_sample, q_stratum = [], [], [], []
         reads, starts = [], []
         nq = 0
-        use_strata = strata_of is not None
-        sized_strata = bool(self.sizes) and use_strata
         for query, subjects in zip(qryque, subque):
             if demux:
                 sname, read = _split_sample(query)
@@ -356,40 +392,54 @@ class Session:
                     continue
             else:
                 sname, read = sample_name, query
-            stratum = 0
-            if use_strata:
-                label = strata_of(sname).get(read)
-                # counter_strat skips reads without a stratum but the sample
-                # still gets its (possibly empty) profile (workflow.py:1058)
-                stratum = self.stratum(label) if label is not None else -1
+            label = strata_of(sname).get(read)
+            stratum = self.stratum(label) if label is not None else -1
             q_sample.append(self.sample(sname))
             q_stratum.append(stratum)
             reads.append(read)
             starts.append(len(q))
-            if sized_strata:
-                # the stratum travels with the subject; reads without one
-                # contribute nothing (classify.py:283-284) — they only stay
-                # in the stream (as copies whose shares are dropped) when
-                # read maps are written, which list every read
-                if stratum >= 0 or self.rank2dir is not None:
-                    for idx in {self.subject(sub) for sub in subjects}:
-                        q.append(nq)
-                        s.append(self.subject_in_stratum(
-                            idx, stratum if stratum >= 0 else _NO_STRATUM))
-            else:
-                for sub in subjects:
+            # reads without a stratum contribute nothing
+            # (classify.py:283-284) — they only stay in the stream (as copies
+            # whose shares are dropped) when read maps are written, which
+            # list every read
+            if stratum >= 0 or self.rank2dir is not None:
+                for idx in {self.subject(sub) for sub in subjects}:
                     q.append(nq)
-                    s.append(self.subject(sub))
+                    s.append(self.subject_in_stratum(
+                        idx, stratum if stratum >= 0 else _NO_STRATUM))
             nq += 1
         if not q:
-            return
+            return None
+        return q, s, q_sample, None, reads, starts
+
+    def add_chunk(self, qryque, subque, demux, sample_name, samples=None,
+                  strata_of=None):
+        """One `(qryque, subque)` chunk of the mapper protocol
+        (workflow.py:304-335): demultiplex, intern, classify on the GPU.
+
+        strata_of(sample_name) -> dict read -> stratum label, or None.
+        Returns the number of queries in the chunk."""
+        use_strata = strata_of is not None
+        sized_strata = bool(self.sizes) and use_strata
+        if not sized_strata:
+            cols = self._chunk_columns(qryque, subque, demux, sample_name,
+                                       samples, strata_of)
+            if cols is None:
+                return
+            q, s, q_sample, q_stratum, reads, starts = cols
+        else:
+            cols = self._chunk_columns_sized_strata(
+                qryque, subque, demux, sample_name, samples, strata_of)
+            if cols is None:
+                return
+            q, s, q_sample, q_stratum, reads, starts = cols
         self.uses_strata = self.uses_strata or use_strata
         self._sync_tables()
         q = np.asarray(q, dtype=np.int32)
         s = np.asarray(s, dtype=np.int32)
         q_sample = np.asarray(q_sample, dtype=np.int32)
         q_stratum = np.asarray(q_stratum, dtype=np.int32) \
-            if use_strata and not sized_strata else None
+            if q_stratum is not None else None
         packed = None
         for eng in self.engines:
             if hasattr(eng, 'classify_packed') and self.rank2dir is None:
