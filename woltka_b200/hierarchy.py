@@ -24,7 +24,11 @@ class FlatTree:
         self.rank_names = rank_names    # list of str
         self.level_off = level_off      # BFS level boundaries (len = depth+1)
         self.root = root                # index of the root passed by caller
-        self.index = None               # identifier -> index (lazy for arrays)
+        self.index = None               # identifier -> index (built on demand)
+        # from_dicts: identifier -> position in the dict it was given, and
+        # that position -> index; saves a second identifier dict
+        self._pos = None
+        self._pos_to_index = None
         self._anc = {}
 
     @property
@@ -33,8 +37,28 @@ class FlatTree:
 
     def node_of(self, name):
         if self.index is None:
+            if self._pos is not None:
+                j = self._pos.get(name)
+                return -1 if j is None else int(self._pos_to_index[j])
             self.index = {x: i for i, x in enumerate(self.ids)}
         return self.index.get(name, -1)
+
+    def nodes_of(self, names):
+        """node_of for a list of names: int32 array, -1 = not in the tree."""
+        if self.index is None and self._pos is not None:
+            get = self._pos.get
+            pos = np.fromiter((get(x, -1) for x in names), dtype=np.int64,
+                              count=len(names))
+            if not len(self._pos_to_index):      # an empty hierarchy
+                return np.full(len(names), -1, dtype=np.int32)
+            out = self._pos_to_index[np.where(pos < 0, 0, pos)].astype(np.int32)
+            out[pos < 0] = -1
+            return out
+        if self.index is None:
+            self.index = {x: i for i, x in enumerate(self.ids)}
+        get = self.index.get
+        return np.fromiter((get(x, -1) for x in names), dtype=np.int32,
+                           count=len(names))
 
     def rank_id(self, rank):
         try:
@@ -107,9 +131,11 @@ class FlatTree:
                                     dtype=np.int32, count=n)
         ft = cls(ids, new_par.astype(np.int32), node_rank, rank_names,
                  level_off, -1)
-        ft.index = dict(zip(ids, range(n)))
+        inv = np.empty(n, dtype=np.int32)
+        inv[order] = np.arange(n, dtype=np.int32)
+        ft._pos, ft._pos_to_index = index, inv
         ft.n_roots = int(is_root.sum())
-        ft.root = ft.index.get(root, -1) if root is not None else -1
+        ft.root = ft.node_of(root) if root is not None else -1
         return ft
 
     @classmethod

@@ -238,9 +238,7 @@ class Session:
         if not new:
             return out
         if self.ft is not None:
-            self.ft.node_of(new[0])              # (builds the index)
-            get = self.ft.index.get
-            node = np.asarray([get(x, -1) for x in new], dtype=np.int32)
+            node = self.ft.nodes_of(new)
         else:
             node = np.full(len(new), -1, dtype=np.int32)
         feat = node.copy()
